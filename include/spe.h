@@ -1,0 +1,145 @@
+/* libspe.so -- C ABI of the B200-native crop -> keypoint-set predictor -> PnP path.
+ *
+ * The reference (wwhitecyan/satellite-pose-estimation) has no FFI for this path: its boundary is four Python call
+ * signatures.  Each entry point below names the reference interface it sits under; INTEGRATION.md shows the ctypes
+ * stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative spe_status otherwise; spe_last_error() gives the message
+ *   - the caller owns every input/output buffer; "dev" pointers are CUDA device pointers on the ctx's device,
+ *     "host" pointers are ordinary (preferably pinned) host memory
+ *   - work is enqueued on the caller's CUDA stream (pass cudaStream_t / torch.cuda.current_stream().cuda_stream as
+ *     void*; NULL = default stream); no entry point synchronises except spe_run_batch_host and spe_sync
+ *   - one spe_ctx per process per GPU; a ctx is not thread-safe
+ *   - sm_100a only: spe_create fails on any other device; there is no CPU fallback anywhere in this library
+ */
+#ifndef SPE_H_
+#define SPE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
+#endif
+
+typedef struct spe_ctx spe_ctx;
+
+typedef enum {
+  SPE_OK = 0,
+  SPE_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  SPE_ERR_CUDA = -2,      /* a CUDA call failed */
+  SPE_ERR_DEVICE = -3,    /* not an sm_100 device */
+  SPE_ERR_WEIGHTS = -4,   /* missing / mis-shaped tensor in spe_load_weights */
+  SPE_ERR_STATE = -5      /* call order (e.g. forward before weights) */
+} spe_status;
+
+/* pose status written by spe_assign_pnp (reference behaviour: RV/gen_submission_single.py:169-175 maps solver
+ * failures to the zero pose) */
+enum { SPE_POSE_OK = 0, SPE_POSE_TOO_FEW = 1, SPE_POSE_DIVERGED = 2, SPE_POSE_REJECTED = 3 };
+
+/* Mirrors the argparse fields the reference's build_model(args) reads (RV/main.py:90-187, RV/models/detr_speed.py:
+ * 296-336, RV/models/backbone.py:184-198, RV/models/transformer.py:284-294). */
+typedef struct {
+  int input_size;       /* R: network input is [B,3,R,R]                               (--input_size)      */
+  int num_queries;      /* Q                                                             (--num_queries)     */
+  int enc_layers;       /*                                                               (--enc_layers)      */
+  int dec_layers;       /*                                                               (--dec_layers)      */
+  int hidden_dim;       /* must be 256                                                   (--hidden_dim)      */
+  int nheads;           /* must be 8 (head_dim 32)                                       (--nheads)          */
+  int dim_feedforward;  /*                                                               (--dim_feedforward) */
+  int backbone;         /* 0: ResNet-50 stride-8 fusion neck (Backbone8s), 1: ResNet-50 layer3 stride 16     */
+  int precision;        /* 0: fp32 storage + TF32 tensor cores, 1: bf16 storage + BF16 tensor cores          */
+  int has_sigma;        /* 1: self-assessment variant, sigma_embed.* head -> pred_sigmas                     */
+  int max_batch;        /* workspace is sized for this many images per call                                  */
+} spe_config;
+
+/* One tensor of the reference state_dict, fp32, HOST memory, C-contiguous. */
+typedef struct {
+  const char* name;
+  const float* data;
+  int ndim;
+  long long shape[4];
+} spe_tensor_desc;
+
+/* ---- lifetime --------------------------------------------------------------------------------------------- */
+/* replaces: build_model(args) + model.to(device)            (RV/models/__init__.py:5-6, RV/main.py:210-211) */
+int spe_create(const spe_config* cfg, int device, spe_ctx** out);
+void spe_destroy(spe_ctx* ctx);
+/* message of the last failure on this ctx (ctx == NULL: last failure of spe_create) */
+const char* spe_last_error(const spe_ctx* ctx);
+/* replaces: model.load_state_dict(checkpoint['model'])      (RV/gen_submission_single.py:216-218)
+ * folds FrozenBatchNorm2d (RV/models/backbone.py:44-54) and repacks to kernel layouts once */
+int spe_load_weights(spe_ctx* ctx, const spe_tensor_desc* tensors, int n);
+int spe_sync(spe_ctx* ctx, void* stream);
+
+/* ---- stage 1: crop -------------------------------------------------------------------------------------------- */
+/* replaces: SpeedSubmission.generate_clip_bbox               (RV/datasets/speed.py:92-108)
+ * host-side, float64, int() truncation toward zero; det_boxes [B,4] = x1,y1,x2,y2 ; boxes [B,4] int32 */
+int spe_clip_boxes(const double* det_boxes_host, int B, int32_t* boxes_host);
+/* replaces: canvas copy + cv2.resize(INTER_CUBIC) + to_tensor + Normalize   (RV/datasets/speed.py:113-160)
+ * frames: uint8 grayscale, image b at frames + b*frame_stride, rows `pitch` bytes apart; out: fp32 [B,3,R,R] */
+int spe_crop_resize_norm(spe_ctx* ctx, const uint8_t* frames_dev, int H, int W, long long pitch,
+                         long long frame_stride, const int32_t* boxes_dev, int B, int R, float* out_nchw_dev,
+                         void* stream);
+
+/* ---- stage 2: keypoint-set predictor ------------------------------------------------------------------------- */
+/* replaces: DETR.forward                                     (RV/models/detr_speed.py:59-92)
+ * images [B,3,R,R] fp32 NCHW.  logits [B,Q,12], points [B,Q,2] (sigmoid, normalised), log_sigma [B,Q,2] or NULL,
+ * aux_logits [(L-1),B,Q,12] / aux_points [(L-1),B,Q,2] or NULL (the 'aux_outputs' list). */
+int spe_forward(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev, float* points_dev,
+                float* log_sigma_dev, float* aux_logits_dev, float* aux_points_dev, void* stream);
+
+/* ---- stage 3: set post-processing + pose -------------------------------------------------------------------- */
+/* replaces: PostProcess.forward (RV/models/detr_speed.py:264-293), SimplePoseSolver.__call__
+ * (RV/utils/speed_eval.py:164-242), SimplePoseSolverSigma (SA/utils/speed_eval.py:322-420).
+ * Optional outputs may be NULL.  quat is (w,x,y,z) with w >= 0; failed images get the zero pose + status != 0. */
+typedef struct {
+  float reproj_thresh;   /* RANSAC reprojectionError in pixels (args.repro: 20 / 25)                      */
+  int weighted;          /* 1: sigma-weighted Huber LM in normalised image coordinates (needs log_sigma)  */
+  int reject;            /* 1: apply the self-assessment reject filter (status SPE_POSE_REJECTED)          */
+  float reject_rms_px;   /* reject when inlier RMS reprojection error exceeds this (default 5)            */
+  float reject_sigma_px; /* reject when mean predicted sigma (pixels) exceeds this (default 12)           */
+} spe_pnp_params;
+
+int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_dev, const float* log_sigma_dev,
+                   const int32_t* boxes_dev, int B, int Q, const spe_pnp_params* params,
+                   double* quat_dev /*[B,4]*/, double* tvec_dev /*[B,3]*/, int32_t* assign_dev /*[B,11]*/,
+                   int32_t* status_dev /*[B]*/, float* probs_dev /*[B,Q,12] or NULL*/,
+                   float* points_px_dev /*[B,Q,2] or NULL*/, float* sigmas_dev /*[B,Q,2] or NULL*/,
+                   int32_t* inlier_mask_dev /*[B] or NULL*/, void* stream);
+
+/* ---- whole path, host buffers in, host buffers out ---------------------------------------------------------- */
+/* replaces the hot loop of gen_submission (RV/gen_submission_single.py:136-181): frames + detector boxes in
+ * host memory -> poses in host memory.  Uploads, runs crop -> forward -> assign/PnP on `stream`, downloads and
+ * synchronises.  frames_host: uint8 [B,H,W]; det_boxes_host: double [B,4]. */
+int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, const double* det_boxes_host, int B,
+                       const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
+                       int32_t* boxes_host /*[B,4] or NULL*/, void* stream);
+
+/* ---- test / bring-up hooks (not part of the drop-in surface) ------------------------------------------------- */
+/* out = act(scale * A.W^T + bias + residual) with A [M,K], W [N,K], storage dtype 0=fp32/TF32, 1=bf16 */
+int spe_debug_gemm(int dtype, const void* A_dev, const void* W_dev, long long M, int N, int K, const float* scale_dev,
+                   const float* bias_dev, const void* residual_dev, int res_mod, int relu, void* out_dev,
+                   void* stream);
+/* stride-1 'same' convolution as implicit GEMM: x [NB,H,W,C] NHWC, w [Cout, R*S*C] (tap-major, channel-minor) */
+int spe_debug_conv(int dtype, const void* x_dev, const void* w_dev, int NB, int H, int W, int C, int Cout, int R,
+                   int S, int pad, const float* scale_dev, const float* bias_dev, int relu, void* out_dev,
+                   void* stream);
+int spe_debug_attention(int dtype, const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int B,
+                        int heads, int Lq, int Lk, int ldq, int ldk, int ldv, int ldo, void* stream);
+/* keep copies of intermediate activations during spe_forward (names: stem, layer1, layer2, layer3, neck,
+ * input_proj, enc<i>, hs) and read them back as raw storage-dtype bytes in kernel layout (NHWC / [rows, C]) */
+int spe_debug_enable_taps(spe_ctx* ctx, int enable);
+long long spe_debug_read_tap(spe_ctx* ctx, const char* name, void* host_out, long long max_bytes);
+const char* spe_global_last_error(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPE_H_ */

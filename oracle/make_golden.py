@@ -1,0 +1,213 @@
+"""Writes tests/golden/* by running the REAL reference (build container only; TEST INFRASTRUCTURE).
+
+    python -m oracle.make_golden
+
+The reference ships no golden vectors for this path, so they are produced here by executing the
+reference's own classes from /root/reference -- the DETR model, ``SpeedSubmission.__getitem__``, ``PostProcess`` and
+``SimplePoseSolver`` -- on the seeded synthetic inputs of oracle/synth.py.  Missing third-party modules are replaced
+by minimal in-process stand-ins (no reference file is edited):
+  albumentations  ``Compose([Resize(h, w, interp)])(image=img)`` -> ``cv2.resize(img, (w, h), interpolation=interp)``,
+                  which is what albumentations 0.5.1 ``Resize`` does (pinned in RV/requirements.txt:5)
+  mathutils       ``Matrix(R).to_quaternion()`` -> rotation matrix to (w, x, y, z), w >= 0
+  matplotlib      empty module (only imported for plotting helpers)
+Fixtures written:
+  wz_synt_test_boxes.npy / wz_real_test_boxes.npy   detector boxes shipped with the reference (RV/annos/*.json)
+  crop_golden.npz     reference crop boxes + uint8 resized crops for a spread of boxes
+  model_golden.npz    reference model outputs for seeded weights/inputs (weights are regenerated, never stored)
+  pnp_golden.npz      reference SimplePoseSolver poses for seeded synthetic predictions
+"""
+import json
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+from . import crop_ref, model_ref, pnp_ref, ref_import, synth
+from .model_ref import ModelCfg
+
+GOLDEN = synth.GOLDEN_DIR
+
+CROP_INDICES = [0, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144]   # + largest / smallest / most out-of-frame boxes
+MODEL_CASES = {
+    # name: (cfg kwargs, batch, input size, seed)
+    "s8_q40": (dict(backbone="resnet50s8", num_queries=40, enc_layers=4, dec_layers=4), 2, 224, 0),
+    "s16_q100": (dict(backbone="resnet50", num_queries=100, enc_layers=6, dec_layers=6), 1, 256, 1),
+}
+
+
+def model_inputs(B, R, seed):
+    rng = np.random.default_rng(1000 + seed)
+    return torch.from_numpy(rng.standard_normal((B, 3, R, R)).astype(np.float32))
+
+
+def _install_stubs():
+    import cv2
+    if "albumentations" not in sys.modules:
+        A = types.ModuleType("albumentations")
+
+        class Resize:
+            def __init__(self, height, width, interpolation=cv2.INTER_LINEAR, **kw):
+                self.h, self.w, self.interp = height, width, interpolation
+
+            def __call__(self, image):
+                return cv2.resize(image, (self.w, self.h), interpolation=self.interp)
+
+        class Compose:
+            def __init__(self, transforms, **kw):
+                self.transforms = transforms
+
+            def __call__(self, image, **kw):
+                for t in self.transforms:
+                    image = t(image)
+                return {"image": image}
+
+        def _unsupported(*a, **k):
+            return None
+
+        def _getattr(name):          # training-only augmentations are never called on this path
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _unsupported
+        A.Resize, A.Compose = Resize, Compose
+        A.__getattr__ = _getattr
+        A.__file__ = "<oracle stub>"
+        sys.modules["albumentations"] = A
+    if "mathutils" not in sys.modules:
+        M = types.ModuleType("mathutils")
+
+        class Matrix:
+            def __init__(self, m):
+                self.m = np.asarray(m, dtype=np.float64)
+
+            def to_quaternion(self):
+                return pnp_ref.rot_to_quat(self.m)
+        M.Matrix = Matrix
+        M.Quaternion = object
+        M.__file__ = "<oracle stub>"
+        sys.modules["mathutils"] = M
+    if "matplotlib" not in sys.modules:
+        mp = types.ModuleType("matplotlib")
+        mp.pyplot = types.ModuleType("matplotlib.pyplot")
+        mp.__file__ = mp.pyplot.__file__ = "<oracle stub>"
+        sys.modules["matplotlib"] = mp
+        sys.modules["matplotlib.pyplot"] = mp.pyplot
+
+
+def import_rv_dataset_and_solver():
+    _install_stubs()
+    ref_import.import_rv_models()
+    with ref_import._rv_on_path():
+        import datasets.speed as rv_speed
+        import utils.speed_eval as rv_eval
+    rv_eval.world_pt_path = os.path.join(ref_import.RV_ROOT, "all_result.json")
+    return rv_speed, rv_eval
+
+
+def write_boxes():
+    for name in ("wz_synt_test", "wz_real_test"):
+        with open(os.path.join(ref_import.RV_ROOT, "annos", name + ".json")) as f:
+            anns = json.load(f)
+        boxes = np.asarray([v[0][:4] for v in anns.values()], dtype=np.float64)
+        np.save(os.path.join(GOLDEN, name + "_boxes.npy"), boxes)
+        print(name, boxes.shape)
+
+
+def crop_case_boxes():
+    boxes = synth.load_detector_boxes()
+    sides = np.maximum(boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1])
+    clip = np.stack([crop_ref.generate_clip_bbox(b) for b in boxes])
+    outside = np.maximum(0, -clip[:, 0]) + np.maximum(0, -clip[:, 1]) + np.maximum(0, clip[:, 2] - 1920) + \
+        np.maximum(0, clip[:, 3] - 1200)
+    idx = CROP_INDICES + [int(np.argmax(sides)), int(np.argmin(sides))] + [int(i) for i in np.argsort(-outside)[:4]]
+    return np.asarray(idx), boxes[idx]
+
+
+def write_crop(rv_speed):
+    from PIL import Image
+    idx, det = crop_case_boxes()
+    frames = synth.make_frames(len(idx), det, seed=0)
+    R = 224
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "annos")); os.makedirs(os.path.join(tmp, "images"))
+        anns = {}
+        for i in range(len(idx)):
+            fn = f"img{i:06d}.png"
+            Image.fromarray(frames[i]).save(os.path.join(tmp, "images", fn))
+            anns[fn] = [list(det[i]) + [1.0]]
+        with open(os.path.join(tmp, "annos", "a.json"), "w") as f:
+            json.dump(anns, f)
+        rv_speed.DATA_ROOT = tmp
+        ds = rv_speed.SpeedSubmission("a.json", "images", R)       # the reference's own dataset class
+        u8s, clips = [], []
+        for i in range(len(ds)):
+            img, target = ds[i]
+            clip = target["clip_bbox"].numpy()
+            u8 = crop_ref.crop_resize_u8(frames[i], clip, R)
+            # the reference tensor must equal normalise(oracle uint8 crop) bit for bit
+            assert torch.equal(img, crop_ref.normalize_u8(u8)), f"oracle crop != reference for case {i}"
+            assert (clip == crop_ref.generate_clip_bbox(det[i])).all()
+            u8s.append(u8[:, :, 0]); clips.append(clip)
+    np.savez_compressed(os.path.join(GOLDEN, "crop_golden.npz"), box_index=idx, det_boxes=det,
+                        clip_boxes=np.stack(clips), crops_u8=np.stack(u8s), input_size=R, frame_seed=0)
+    print("crop cases", len(idx), "sides", [int(c[2] - c[0]) for c in clips])
+
+
+def write_model():
+    out = {}
+    for name, (kw, B, R, seed) in MODEL_CASES.items():
+        cfg = ModelCfg(**kw)
+        sd = synth.make_state_dict(cfg, seed=seed)
+        model, _, _ = ref_import.build_reference_model(cfg, sd)
+        x = model_inputs(B, R, seed)
+        with torch.no_grad():
+            ref = model(x)
+        port = model_ref.forward(sd, cfg, x)
+        err = max((ref[k] - port[k]).abs().max().item() for k in ("pred_logits", "pred_points"))
+        print(name, "restatement vs live reference max|d|", err)
+        assert err < 1e-4
+        out[name + "/checksum"] = np.frombuffer(synth.weights_checksum(sd).encode(), dtype=np.uint8)
+        out[name + "/pred_logits"] = ref["pred_logits"].numpy()
+        out[name + "/pred_points"] = ref["pred_points"].numpy()
+        out[name + "/aux_logits"] = torch.stack([a["pred_logits"] for a in ref["aux_outputs"]]).numpy()
+        out[name + "/aux_points"] = torch.stack([a["pred_points"] for a in ref["aux_outputs"]]).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "model_golden.npz"), **out)
+
+
+def write_pnp(rv_eval, n=400):
+    import cv2
+    d = synth.make_predictions(n, seed=1)
+    solver = rv_eval.SimplePoseSolver(synth.reference_args(ModelCfg()))     # the reference's own solver class
+    models = sys.modules["models"]
+    post = models.PostProcess()                                            # the reference's own PostProcess
+    res = post({"pred_logits": torch.from_numpy(d["logits"]), "pred_points": torch.from_numpy(d["points"]).clone()},
+               [torch.from_numpy(b) for b in d["boxes"]])
+    quat = np.zeros((n, 4)); tvec = np.zeros((n, 3)); ok = np.zeros(n, dtype=np.int32)
+    probs = np.stack([r["logits"] for r in res]); pts = np.stack([r["points"] for r in res])
+    assign = np.stack([pnp_ref.assign_table(r["points"], r["logits"]) for r in res])
+    for i, r in enumerate(res):
+        try:                                                               # RV/gen_submission_single.py:169-175
+            q, t = solver(r["points"], r["logits"])
+            quat[i], tvec[i], ok[i] = q, t, 1
+        except (IndexError, cv2.error):
+            pass
+    np.savez_compressed(os.path.join(GOLDEN, "pnp_golden.npz"), quat=quat, tvec=tvec, ok=ok, probs=probs,
+                        points_px=pts, assign=assign, n=n, seed=1)
+    print("pnp cases", n, "solved", int(ok.sum()))
+
+
+def main():
+    if not ref_import.available():
+        raise SystemExit("/root/reference is not mounted: golden vectors can only be regenerated in the build container")
+    os.makedirs(GOLDEN, exist_ok=True)
+    write_boxes()
+    rv_speed, rv_eval = import_rv_dataset_and_solver()
+    write_crop(rv_speed)
+    write_model()
+    write_pnp(rv_eval)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+"""Import the REAL reference from /root/reference (build container only; TEST INFRASTRUCTURE).
+
+The reference is not importable as shipped on this image; two in-process shims (no file edits) are needed
+(SURVEY.md section 8c):
+  1. ``torchvision.__version__`` is parsed with ``float(v[:3]) < 0.7`` (RV/utils/misc.py:21-23): "0.26.0" reads as
+     0.2 and pulls removed private symbols -> present a large version string while importing.
+  2. ``Backbone8s`` asks torchvision for pretrained weights on the main process (RV/models/backbone.py:98, :116):
+     no network here -> force ``is_main_process() == False`` so ``pretrained=False``.
+"""
+import os
+import sys
+import contextlib
+
+REFERENCE_ROOT = "/root/reference"
+RV_ROOT = os.path.join(REFERENCE_ROOT, "Revisiting Monocular Satellite Pose Estimation With Transformer")
+
+
+def available():
+    return os.path.isdir(RV_ROOT)
+
+
+@contextlib.contextmanager
+def _rv_on_path():
+    sys.path.insert(0, RV_ROOT)
+    cwd = os.getcwd()
+    os.chdir(RV_ROOT)
+    try:
+        yield
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(RV_ROOT)
+
+
+def import_rv_models():
+    """Returns the reference's ``models`` package (``models.build_model``, ``models.PostProcess``)."""
+    import torchvision
+    real_version = torchvision.__version__
+    with _rv_on_path():
+        torchvision.__version__ = "9.9.0"
+        try:
+            import utils.misc  # noqa: F401  (reference module)
+            import models  # noqa: F401
+            import models.backbone as rv_backbone
+        finally:
+            torchvision.__version__ = real_version
+        rv_backbone.is_main_process = lambda: False
+    return sys.modules["models"]
+
+
+def build_reference_model(cfg, state_dict=None):
+    """``build_model(args)`` of the reference (RV/models/__init__.py:5-6), eval mode, optional weights."""
+    import warnings
+    from .synth import reference_args
+    models = import_rv_models()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, criterion, postprocessors = models.build_model(reference_args(cfg))
+    model.eval()
+    if state_dict is not None:
+        model.load_state_dict(state_dict, strict=True)
+    return model, criterion, postprocessors

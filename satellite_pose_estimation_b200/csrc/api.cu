@@ -1,0 +1,164 @@
+// C-ABI entry points for the crop and pose stages, the host-buffer pipeline and the bring-up hooks.
+// (ctx lifetime, weights and spe_forward live in model.cu.)
+#include "spe_internal.h"
+#include "../../include/spe.h"
+
+#include <string>
+#include <vector>
+
+// spe_ctx is defined in model.cu; the pipeline needs a few of its fields, exposed through these accessors.
+namespace spe {
+struct PipelineBuffers {
+  uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
+  float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
+  int has_sigma;
+};
+PipelineBuffers pipeline_buffers(spe_ctx* ctx);
+int set_error(spe_ctx* ctx, int code, const std::string& msg);
+}  // namespace spe
+
+using namespace spe;
+
+extern "C" {
+
+int spe_clip_boxes(const double* det, int B, int32_t* boxes) {
+  if (!det || !boxes || B < 0) return set_error(nullptr, SPE_ERR_INVALID, "spe_clip_boxes: null argument");
+  for (int i = 0; i < B; ++i) {
+    // SpeedSubmission.generate_clip_bbox, RV/datasets/speed.py:92-108 (float64; int() truncates toward zero)
+    const double x1 = det[4 * i + 0], y1 = det[4 * i + 1], x2 = det[4 * i + 2], y2 = det[4 * i + 3];
+    const double bw = x2 - x1, bh = y2 - y1;
+    const double scale = (bw > bh ? bw : bh) * 1.2;
+    const double xc = (x1 + x2) / 2, yc = (y1 + y2) / 2;
+    const double half = scale / 2;
+    const int32_t cx1 = static_cast<int32_t>(xc - half), cy1 = static_cast<int32_t>(yc - half);
+    const int32_t s = static_cast<int32_t>(scale);
+    boxes[4 * i + 0] = cx1; boxes[4 * i + 1] = cy1; boxes[4 * i + 2] = cx1 + s; boxes[4 * i + 3] = cy1 + s;
+  }
+  return SPE_OK;
+}
+
+int spe_crop_resize_norm(spe_ctx* ctx, const uint8_t* frames_dev, int H, int W, long long pitch,
+                         long long frame_stride, const int32_t* boxes_dev, int B, int R, float* out_nchw_dev,
+                         void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_crop_resize_norm: null ctx");
+  if (!frames_dev || !boxes_dev || !out_nchw_dev || H <= 0 || W <= 0 || pitch < W || B < 0)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_crop_resize_norm: bad argument");
+  std::string s = launch_crop_resize_norm(frames_dev, H, W, pitch, frame_stride, boxes_dev, B, R, out_nchw_dev,
+                                          static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(ctx, SPE_ERR_CUDA, "spe_crop_resize_norm: " + s);
+  return SPE_OK;
+}
+
+int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_dev, const float* log_sigma_dev,
+                   const int32_t* boxes_dev, int B, int Q, const spe_pnp_params* params, double* quat_dev,
+                   double* tvec_dev, int32_t* assign_dev, int32_t* status_dev, float* probs_dev,
+                   float* points_px_dev, float* sigmas_dev, int32_t* inlier_mask_dev, void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_assign_pnp: null ctx");
+  if (!logits_dev || !points_dev || !boxes_dev || !quat_dev || !tvec_dev || !assign_dev || !status_dev || !params)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_assign_pnp: null buffer");
+  if (params->weighted && !log_sigma_dev)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_assign_pnp: weighted solve needs log_sigma");
+  PnpDesc d{};
+  d.logits = logits_dev; d.points = points_dev; d.logsig = log_sigma_dev; d.boxes = boxes_dev;
+  d.B = B; d.Q = Q;
+  d.reproj_thresh = params->reproj_thresh;
+  d.weighted = params->weighted;
+  d.reject = params->reject;
+  d.reject_rms_px = params->reject_rms_px > 0 ? params->reject_rms_px : 5.0f;
+  d.reject_sigma = params->reject_sigma_px > 0 ? params->reject_sigma_px : 12.0f;
+  d.quat = quat_dev; d.tvec = tvec_dev; d.assign = assign_dev; d.status = status_dev;
+  d.probs = probs_dev; d.points_px = points_px_dev; d.sigmas = sigmas_dev; d.inlier_mask = inlier_mask_dev;
+  std::string s = launch_assign_pnp(d, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(ctx, SPE_ERR_CUDA, "spe_assign_pnp: " + s);
+  return SPE_OK;
+}
+
+int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, const double* det_boxes_host, int B,
+                       const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
+                       int32_t* boxes_host, void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_run_batch_host: null ctx");
+  if (!frames_host || !det_boxes_host || !params || !quat_host || !tvec_host || !status_host)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_run_batch_host: null buffer");
+  PipelineBuffers pb = pipeline_buffers(ctx);
+  if (B <= 0 || B > pb.max_batch) return set_error(ctx, SPE_ERR_INVALID, "spe_run_batch_host: batch outside [1, max_batch]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaSetDevice(pb.device);
+  const long long need = static_cast<long long>(B) * H * W;
+  if (*pb.frames_cap < need) {
+    if (*pb.frames_dev) cudaFree(*pb.frames_dev);
+    *pb.frames_dev = nullptr;
+    *pb.frames_cap = 0;
+    const long long cap = static_cast<long long>(pb.max_batch) * H * W;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(pb.frames_dev), static_cast<size_t>(cap));
+    if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("frame buffer: ") + cudaGetErrorString(e));
+    *pb.frames_cap = cap;
+  }
+  std::vector<int32_t> boxes(static_cast<size_t>(B) * 4);
+  spe_clip_boxes(det_boxes_host, B, boxes.data());
+  if (boxes_host) memcpy(boxes_host, boxes.data(), boxes.size() * sizeof(int32_t));
+  cudaError_t e;
+  e = cudaMemcpyAsync(*pb.frames_dev, frames_host, static_cast<size_t>(need), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(pb.boxes_dev, boxes.data(), boxes.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e));
+  int rc = spe_crop_resize_norm(ctx, *pb.frames_dev, H, W, W, static_cast<long long>(H) * W, pb.boxes_dev, B, pb.R,
+                                pb.images_dev, stream);
+  if (rc != SPE_OK) return rc;
+  const bool sig = pb.has_sigma != 0;
+  rc = spe_forward(ctx, pb.images_dev, B, pb.logits, pb.points, sig ? pb.logsig : nullptr, nullptr, nullptr, stream);
+  if (rc != SPE_OK) return rc;
+  spe_pnp_params pp = *params;
+  if (!sig) pp.weighted = 0;
+  rc = spe_assign_pnp(ctx, pb.logits, pb.points, sig ? pb.logsig : nullptr, pb.boxes_dev, B, pb.Q, &pp, pb.quat,
+                      pb.tvec, pb.assign, pb.status, nullptr, nullptr, nullptr, nullptr, stream);
+  if (rc != SPE_OK) return rc;
+  e = cudaMemcpyAsync(quat_host, pb.quat, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tvec_host, pb.tvec, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(status_host, pb.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_run_batch_host: ") + cudaGetErrorString(e));
+  return SPE_OK;
+}
+
+// ---- bring-up hooks ---------------------------------------------------------------------------------------------
+static int sm_count() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+int spe_debug_gemm(int dtype, const void* A, const void* Wt, long long M, int N, int K, const float* scale,
+                   const float* bias, const void* residual, int res_mod, int relu, void* out, void* stream) {
+  GemmDesc d;
+  d.mode = 0; d.A = A; d.M = M; d.K = K; d.lda = K; d.Wt = Wt; d.N = N;
+  d.scale = scale; d.bias = bias; d.residual = residual; d.res_ld = N; d.res_mod = res_mod; d.relu = relu;
+  d.out = out; d.out_ld = N;
+  std::string s = launch_gemm(dtype == 0 ? kTF32 : kBF16, d, sm_count(), static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_gemm: " + s);
+  return SPE_OK;
+}
+
+int spe_debug_conv(int dtype, const void* x, const void* w, int NB, int H, int W, int C, int Cout, int R, int S,
+                   int pad, const float* scale, const float* bias, int relu, void* out, void* stream) {
+  GemmDesc d;
+  d.mode = 1; d.A = x; d.NB = NB; d.H = H; d.W = W; d.C = C; d.R = R; d.S = S; d.pad = pad; d.Wt = w; d.N = Cout;
+  d.scale = scale; d.bias = bias; d.relu = relu; d.out = out; d.out_ld = Cout;
+  std::string s = launch_gemm(dtype == 0 ? kTF32 : kBF16, d, sm_count(), static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_conv: " + s);
+  return SPE_OK;
+}
+
+int spe_debug_attention(int dtype, const void* q, const void* k, const void* v, void* out, int B, int heads, int Lq,
+                        int Lk, int ldq, int ldk, int ldv, int ldo, void* stream) {
+  AttnDesc a;
+  a.q = q; a.k = k; a.v = v; a.out = out; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.bsq = static_cast<long long>(Lq) * ldq; a.bsk = static_cast<long long>(Lk) * ldk;
+  a.bsv = static_cast<long long>(Lk) * ldv; a.bso = static_cast<long long>(Lq) * ldo;
+  a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.scale = 0.17677669529663687f;
+  std::string s = launch_attention(dtype == 0 ? kTF32 : kBF16, a, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_attention: " + s);
+  return SPE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// Memory-bound layout / pooling / normalisation kernels around the tensor-core GEMMs.  All activations are NHWC
+// (channels contiguous) so every access below is a 16-byte vector along C and warps touch contiguous memory.
+//
+//   stem_im2col      NCHW fp32 image -> [pixels, 192] patch matrix for the 7x7/s2 stem (RV backbone conv1)
+//   im2col_nhwc      patch matrix for the few strided convolutions (layerN.0.conv2 3x3/s2, downsample 1x1/s2)
+//   maxpool3x3s2     torchvision resnet stem max-pool
+//   upsample2x       nn.UpsamplingBilinear2d(scale_factor=2) == bilinear, align_corners=True
+//                    (reference: RV/models/backbone.py:125, :140)
+//   layernorm        nn.LayerNorm(256), eps 1e-5, fp32 statistics (RV/models/transformer.py:159-166)
+#include "spe_internal.h"
+#include <cuda_bf16.h>
+
+namespace spe {
+
+namespace {
+
+template <typename T> struct Vec;  // 16-byte vector of T
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  float4 v;
+  __device__ __forceinline__ float get(int i) const { return reinterpret_cast<const float*>(&v)[i]; }
+  __device__ __forceinline__ void set(int i, float x) { reinterpret_cast<float*>(&v)[i] = x; }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  uint4 v;
+  __device__ __forceinline__ float get(int i) const {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&v)[i]);
+  }
+  __device__ __forceinline__ void set(int i, float x) {
+    reinterpret_cast<__nv_bfloat16*>(&v)[i] = __float2bfloat16_rn(x);
+  }
+};
+template <typename T> __device__ __forceinline__ Vec<T> vload(const T* p) {
+  Vec<T> r;
+  r.v = *reinterpret_cast<const decltype(r.v)*>(p);
+  return r;
+}
+template <typename T> __device__ __forceinline__ void vstore(T* p, const Vec<T>& x) {
+  *reinterpret_cast<decltype(x.v)*>(p) = x.v;
+}
+template <typename T> __device__ __forceinline__ T from_float(float x);
+template <> __device__ __forceinline__ float from_float<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// stem im2col: out[(n, oy, ox), (r*7 + s)*3 + c] = in[n, c, 2*oy - 3 + r, 2*ox - 3 + s]  (0 outside), K padded to 192
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStemK = 147, kStemKPad = 192;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ in, int Hin, int Win, int Ho, int Wo, long long total_vec,
+                   T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int VPR = kStemKPad / VN;  // vectors per output row
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int kv = static_cast<int>(idx % VPR);
+  const long long pix = idx / VPR;
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const float* img = in + n * 3 * Hin * Win;
+  Vec<T> r;
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    const int kk = kv * VN + e;
+    float x = 0.f;
+    if (kk < kStemK) {
+      const int c = kk % 3, tap = kk / 3;
+      const int fr = tap / 7, fs = tap % 7;
+      const int iy = 2 * oy - 3 + fr, ix = 2 * ox - 3 + fs;
+      if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) x = __ldg(img + (static_cast<long long>(c) * Hin + iy) * Win + ix);
+    }
+    r.set(e, x);
+  }
+  vstore(out + pix * kStemKPad + kv * VN, r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// generic NHWC im2col (used only for stride-2 convolutions)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const T* __restrict__ in, int H, int W, int C, int R, int S, int stride, int pad, int Ho, int Wo,
+                   long long total_vec, T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int cv = C / VN;
+  const int c0 = static_cast<int>(idx % cv) * VN;
+  long long rest = idx / cv;
+  const int tap = static_cast<int>(rest % (R * S));
+  const long long pix = rest / (R * S);
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const int fr = tap / S, fs = tap % S;
+  const int iy = oy * stride - pad + fr, ix = ox * stride - pad + fs;
+  Vec<T> r;
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+    r = vload(in + ((n * H + iy) * W + ix) * C + c0);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) r.set(e, 0.f);
+  }
+  vstore(out + (pix * (R * S) + tap) * C + c0, r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// max-pool 3x3 stride 2 pad 1 (padding never wins: torch pads with -inf)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int Wo, long long total_vec,
+                    T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int cv = C / VN;
+  const int c0 = static_cast<int>(idx % cv) * VN;
+  const long long pix = idx / cv;
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  float m[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) m[e] = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = 2 * oy - 1 + dy;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = 2 * ox - 1 + dx;
+      if (ix < 0 || ix >= W) continue;
+      const Vec<T> x = vload(in + ((n * H + iy) * W + ix) * C + c0);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) m[e] = fmaxf(m[e], x.get(e));
+    }
+  }
+  Vec<T> r;
+#pragma unroll
+  for (int e = 0; e < VN; ++e) r.set(e, m[e]);
+  vstore(out + pix * C + c0, r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bilinear x2 upsample, align_corners=True (torch upsample_bilinear2d arithmetic: fp32 scale = (in-1)/(out-1))
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, long long total_vec, T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int cv = C / VN;
+  const int c0 = static_cast<int>(idx % cv) * VN;
+  const long long pix = idx / cv;
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const float sh = Ho > 1 ? static_cast<float>(H - 1) / static_cast<float>(Ho - 1) : 0.f;
+  const float sw = Wo > 1 ? static_cast<float>(W - 1) / static_cast<float>(Wo - 1) : 0.f;
+  const float fy = sh * oy, fx = sw * ox;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly1 = fy - y0, lx1 = fx - x0;
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const T* base = in + n * H * W * C + c0;
+  const Vec<T> a = vload(base + (static_cast<long long>(y0) * W + x0) * C);
+  const Vec<T> b = vload(base + (static_cast<long long>(y0) * W + x1) * C);
+  const Vec<T> c = vload(base + (static_cast<long long>(y1) * W + x0) * C);
+  const Vec<T> d = vload(base + (static_cast<long long>(y1) * W + x1) * C);
+  Vec<T> r;
+#pragma unroll
+  for (int e = 0; e < VN; ++e)
+    r.set(e, ly0 * (lx0 * a.get(e) + lx1 * b.get(e)) + ly1 * (lx0 * c.get(e) + lx1 * d.get(e)));
+  vstore(out + pix * C + c0, r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (dim = 32 * 8 = 256): one warp per row, two-pass fp32 statistics in registers
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    long long rows, T* __restrict__ out) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int VN = Vec<T>::N;
+  constexpr int NV = 8 / VN;  // vectors per lane
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const Vec<T> vv = vload(in + row * 256 + (i * 32 + lane) * VN);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) x[i * VN + e] = vv.get(e);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s += x[e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { const float d = x[e] - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.f / 256.f) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * VN;
+    Vec<T> r;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) r.set(e, (x[i * VN + e] - mean) * rstd * gamma[c + e] + beta[c + e]);
+    vstore(out + row * 256 + c, r);
+  }
+}
+
+inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
+
+}  // namespace
+
+#define DISPATCH_T(dt, ...)                                    \
+  if ((dt) == kTF32) { using T = float; __VA_ARGS__; }         \
+  else { using T = __nv_bfloat16; __VA_ARGS__; }
+
+std::string launch_stem_im2col(Dtype dt, const float* nchw, int NB, int Hin, int Win, void* out, cudaStream_t s) {
+  const int Ho = (Hin + 6 - 7) / 2 + 1, Wo = (Win + 6 - 7) / 2 + 1;
+  DISPATCH_T(dt, {
+    const long long total = static_cast<long long>(NB) * Ho * Wo * (kStemKPad / Vec<T>::N);
+    stem_im2col_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(nchw, Hin, Win, Ho, Wo, total,
+                                                                 reinterpret_cast<T*>(out));
+  });
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
+std::string launch_im2col_nhwc(Dtype dt, const void* in, int NB, int H, int W, int C, int R, int S, int stride,
+                               int pad, void* out, cudaStream_t s) {
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  DISPATCH_T(dt, {
+    if (C % Vec<T>::N) return "im2col: C must be a multiple of the 16-byte vector";
+    const long long total = static_cast<long long>(NB) * Ho * Wo * R * S * (C / Vec<T>::N);
+    im2col_nhwc_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C, R, S,
+                                                                 stride, pad, Ho, Wo, total,
+                                                                 reinterpret_cast<T*>(out));
+  });
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
+std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  DISPATCH_T(dt, {
+    const long long total = static_cast<long long>(NB) * Ho * Wo * (C / Vec<T>::N);
+    maxpool3x3s2_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C, Ho, Wo,
+                                                                  total, reinterpret_cast<T*>(out));
+  });
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
+std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s) {
+  DISPATCH_T(dt, {
+    const long long total = static_cast<long long>(NB) * 4 * H * W * (C / Vec<T>::N);
+    upsample2x_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C, total,
+                                                                reinterpret_cast<T*>(out));
+  });
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
+std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
+                             int dim, void* out, cudaStream_t s) {
+  if (dim != 256) return "layernorm: only hidden_dim 256 is built";
+  if (rows <= 0) return "";
+  DISPATCH_T(dt, {
+    layernorm256_kernel<T><<<blocks_for(rows, 8), 256, 0, s>>>(reinterpret_cast<const T*>(in), gamma, beta, rows,
+                                                               reinterpret_cast<T*>(out));
+  });
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
+}  // namespace spe

@@ -1,0 +1,443 @@
+// Tensor-core GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   out[m, n] = act( scale[n] * sum_k A[m, k] * Wt[n, k] + bias[n] + residual[m', n] )
+//
+// Replaces the cuDNN / cuBLAS library calls the reference dispatches for every convolution and linear layer of
+// the keypoint-set predictor (reference: RV/models/backbone.py:133-149 conv stack, RV/models/transformer.py:154-239
+// linear layers, RV/models/detr_speed.py:50-55 projections).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: A and W tiles -> 128B-swizzled shared memory ring (mbarrier full/empty pairs)
+//   warp 1      owns TMEM; one lane issues tcgen05.mma (M=128, N=BN, K=32 bytes) into a double-buffered accumulator
+//   warps 2..5  epilogue: tcgen05.ld accumulator -> scale/bias/residual/ReLU -> global (overlaps next tile's MMAs)
+//
+// Storage dtype float  -> kind::tf32 (BK = 32 elements), storage dtype bf16 -> kind::f16 (BK = 64 elements).
+// Convolution mode reads the NHWC activation through a 4-D tensor map: for filter tap (r, s) the A tile is the box
+// {BK channels, W, hrows, 1 image} shifted by (s - pad, r - pad); TMA zero-fills outside the image, which is
+// exactly the convolution's zero padding, so no im2col buffer is ever materialised.
+#include "spe_internal.h"
+#include "spe_ptx.cuh"
+
+#include <mutex>
+
+namespace spe {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int kGemmThreads = 192;
+
+template <typename T> struct GemmTraits;
+template <> struct GemmTraits<float> {
+  static constexpr int BK = 32;
+  static constexpr bool kTf32 = true;
+  static constexpr int kFmt = 2;
+};
+template <> struct GemmTraits<__nv_bfloat16> {
+  static constexpr int BK = 64;
+  static constexpr bool kTf32 = false;
+  static constexpr int kFmt = 1;
+};
+
+template <int BN> struct StageCfg {
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * 2 * BN * 4 /*scale,bias x2 buffers*/ +
+                                    (2 * STAGES + 4) * 8 /*barriers*/ + 16 /*tmem ptr*/ + 1024 /*align slack*/;
+};
+
+struct GemmKParams {
+  int mode;
+  int M, N;            // M = number of valid output rows in total
+  int num_kb;          // k-blocks per tile
+  int num_m_tiles, num_n_tiles;
+  uint32_t a_bytes;    // bytes one A TMA box delivers
+  // conv
+  int HW, W, S, pad, hrows, tiles_per_img, kb_per_tap, H;
+  // epilogue
+  const float* scale;
+  const float* bias;
+  const void* residual;
+  int res_ld, res_mod, res_f32, relu;
+  void* out;
+  int out_ld;
+};
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmKParams p) {
+  using Tr = GemmTraits<T>;
+  using Cfg = StageCfg<BN>;
+  constexpr int BK = Tr::BK;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment of the shared-space address (required by the 128B swizzle atom)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  float* sm_scale = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BN]
+  float* sm_bias = sm_scale + 2 * BN;                                            // [2][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_bias + 2 * BN);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
+        int img = 0, h0 = 0;
+        if (p.mode == 1) {
+          img = m_tile / p.tiles_per_img;
+          h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          mbar_expect_tx(&full_bar[stage], p.a_bytes + Cfg::B_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (p.mode == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
+          } else {
+            const int tap = kb / p.kb_per_tap;
+            const int c0 = (kb - tap * p.kb_per_tap) * BK;
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 + r - p.pad, img);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(Tr::kFmt, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[buf], use_par ^ 1u, 2);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_ss<Tr::kTf32>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);                        // smem slot reusable once these MMAs retire
+          if (kb == p.num_kb - 1) tc_commit(&tfull_bar[buf]);  // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // row inside the 128-row tile
+    const int et = threadIdx.x - 64;        // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
+      long long m_base;
+      int valid_rows;
+      if (p.mode == 0) {
+        m_base = static_cast<long long>(m_tile) * BM;
+        const long long rem = static_cast<long long>(p.M) - m_base;
+        valid_rows = rem < BM ? static_cast<int>(rem) : BM;
+      } else {
+        const int img = m_tile / p.tiles_per_img;
+        const int h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
+        m_base = static_cast<long long>(img) * p.HW + static_cast<long long>(h0) * p.W;
+        const int hr = (p.H - h0) < p.hrows ? (p.H - h0) : p.hrows;
+        valid_rows = hr * p.W;
+      }
+      float* s_scale = sm_scale + buf * BN;
+      float* s_bias = sm_bias + buf * BN;
+      for (int j = et; j < BN; j += 128) {
+        const bool ok = (n0 + j) < p.N;
+        s_scale[j] = (p.scale != nullptr && ok) ? p.scale[n0 + j] : 1.0f;
+        s_bias[j] = (p.bias != nullptr && ok) ? p.bias[n0 + j] : 0.0f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&tfull_bar[buf], use_par, 4);
+      tc_fence_after();
+
+      const bool row_ok = row < valid_rows;
+      const long long grow = m_base + row;
+      const long long rrow = (p.res_mod > 0) ? (grow % p.res_mod) : grow;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+        tmem_wait_ld();
+        const int ncol = n0 + c * 32;
+        if (row_ok && ncol < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c * 32 + j);
+            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c * 32 + j);
+            f[j + 0] = fmaf(__uint_as_float(v[j + 0]), sc.x, bi.x);
+            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
+            f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
+            f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
+          }
+          if (p.residual != nullptr) {
+            if (sizeof(T) == 4 || p.res_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + rrow * p.res_ld + ncol;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = ld_f4(rp + j);
+                f[j + 0] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+              }
+            } else {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rrow * p.res_ld + ncol;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 r8 = *reinterpret_cast<const uint4*>(rp + j);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r8);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float2 ff = __bfloat1622float2(h[u]);
+                  f[j + 2 * u] += ff.x;
+                  f[j + 2 * u + 1] += ff.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (sizeof(T) == 4) {
+            float* op = reinterpret_cast<float*>(p.out) + grow * p.out_ld + ncol;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_ld + ncol;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o8;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[j + 2 * u], f[j + 2 * u + 1]);
+              *reinterpret_cast<uint4*>(op + j) = o8;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn(std::string* err) {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  static std::string once_err;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+      once_err = std::string("cuTensorMapEncodeTiled not available: ") + cudaGetErrorString(e);
+    } else {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  if (!fn && err) *err = once_err;
+  return fn;
+}
+
+std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  std::string err;
+  EncodeTiledFn fn = get_encode_fn(&err);
+  if (!fn) return err;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, dt == kTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] base %p",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+             rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+    return buf;
+  }
+  return "";
+}
+
+template <typename T, int BN>
+std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                     int num_sms, cudaStream_t stream) {
+  using Cfg = StageCfg<BN>;
+  static bool attr_set = false;
+  auto kfn = gemm_tc_kernel<T, BN>;
+  if (!attr_set) {
+    SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = kp.num_m_tiles * kp.num_n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+  SPE_CUDA_TRY(cudaGetLastError());
+  (void)d;
+  return "";
+}
+
+}  // namespace
+
+std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t stream) {
+  const int es = static_cast<int>(dtype_size(dt));
+  const int BK = 128 / es;
+  if (d.N % 32 != 0) return "gemm: N must be a multiple of 32";
+  if (d.out_ld % (16 / es) != 0) return "gemm: out_ld must keep rows 16-byte aligned";
+  const int BN = d.N <= 64 ? 64 : 128;
+
+  GemmKParams kp{};
+  kp.mode = d.mode;
+  kp.N = d.N;
+  kp.scale = d.scale;
+  kp.bias = d.bias;
+  kp.residual = d.residual;
+  kp.res_ld = d.res_ld;
+  kp.res_mod = d.res_mod;
+  kp.res_f32 = d.res_f32;
+  kp.relu = d.relu;
+  kp.out = d.out;
+  kp.out_ld = d.out_ld;
+  kp.num_n_tiles = (d.N + BN - 1) / BN;
+
+  CUtensorMap tmA, tmB;
+  std::string err;
+  int K;
+  if (d.mode == 0) {
+    K = d.K;
+    if (K % BK != 0) return "gemm: K must be a multiple of the 128-byte k-block";
+    if ((static_cast<long long>(d.lda) * es) % 16 != 0) return "gemm: lda must keep rows 16-byte aligned";
+    kp.M = static_cast<int>(d.M);
+    kp.num_m_tiles = static_cast<int>((d.M + BM - 1) / BM);
+    kp.a_bytes = BM * 128;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.M)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(d.lda) * es};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), BM};
+    err = encode_map(&tmA, dt, 2, d.A, dims, str, box);
+    if (!err.empty()) return err;
+  } else {
+    if (d.C % BK != 0) return "conv: C must be a multiple of the 128-byte k-block";
+    if (d.W > BM) return "conv: W must be <= 128";
+    K = d.R * d.S * d.C;
+    int hrows = BM / d.W;
+    if (hrows > d.H) hrows = d.H;
+    kp.hrows = hrows;
+    kp.tiles_per_img = (d.H + hrows - 1) / hrows;
+    kp.num_m_tiles = kp.tiles_per_img * d.NB;
+    kp.M = d.NB * d.H * d.W;
+    kp.HW = d.H * d.W;
+    kp.H = d.H;
+    kp.W = d.W;
+    kp.S = d.S;
+    kp.pad = d.pad;
+    kp.kb_per_tap = d.C / BK;
+    kp.a_bytes = static_cast<uint32_t>(d.W * hrows * 128);
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.C), static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H),
+                          static_cast<cuuint64_t>(d.NB)};
+    cuuint64_t str[3] = {static_cast<cuuint64_t>(d.C) * es, static_cast<cuuint64_t>(d.W) * d.C * es,
+                         static_cast<cuuint64_t>(d.H) * d.W * d.C * es};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(d.W), static_cast<cuuint32_t>(hrows), 1};
+    err = encode_map(&tmA, dt, 4, d.A, dims, str, box);
+    if (!err.empty()) return err;
+  }
+  kp.num_kb = K / BK;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.N)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(K) * es};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(BN)};
+    err = encode_map(&tmB, dt, 2, d.Wt, dims, str, box);
+    if (!err.empty()) return err;
+  }
+
+  if (dt == kTF32) {
+    if (BN == 64) return launch_t<float, 64>(d, kp, tmA, tmB, num_sms, stream);
+    return launch_t<float, 128>(d, kp, tmA, tmB, num_sms, stream);
+  } else {
+    if (BN == 64) return launch_t<__nv_bfloat16, 64>(d, kp, tmA, tmB, num_sms, stream);
+    return launch_t<__nv_bfloat16, 128>(d, kp, tmA, tmB, num_sms, stream);
+  }
+}
+
+}  // namespace spe

@@ -1,0 +1,870 @@
+// Context, weight repacking and the forward schedule of the keypoint-set predictor.
+//
+// The reference's DETR.forward (RV/models/detr_speed.py:59-92) runs ~400 eager PyTorch ops per batch.  Here the
+// whole forward is a fixed schedule of our own kernels over NHWC activations held in a reusable workspace:
+//   stem      : im2col(7x7/s2) -> GEMM(+FrozenBN+ReLU) -> maxpool                 (torchvision resnet50 stem)
+//   layer1..3 : per bottleneck 3 GEMMs (1x1, implicit 3x3, 1x1+residual+ReLU), FrozenBN folded into the epilogue
+//   neck      : s8_latern 1x1, bilinear x2, s16_latern 3x3, output_conv 3x3       (RV/models/backbone.py:139-142)
+//   encoder   : QKV GEMM (pos-embedding folded into a batch-broadcast addend), flash attention, out-proj+residual,
+//               LayerNorm, FFN GEMM pair, LayerNorm                                (RV/models/transformer.py:154-167)
+//   decoder   : cross-attention K/V of all layers in one GEMM, then per layer self-attn / cross-attn / FFN
+//                                                                                  (RV/models/transformer.py:218-239)
+//   heads     : class logits, keypoint MLP + sigmoid, optional log-sigma MLP      (RV/models/detr_speed.py:83-84)
+//
+// Identity used for the positional terms: (x + pos) W^T + b = x W^T + (pos W^T + b); the bracket is constant per
+// token position, computed once at weight-load time in fp32 and added by the GEMM epilogue (row % tokens).
+#include "spe_internal.h"
+#include "../../include/spe.h"
+
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace spe {
+
+// ------------------------------------------------------------------------------------------------------------------
+// small device helpers used at weight-load time
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void f32_to_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i]));
+    out[i] = __uint_as_float(r);
+  }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+// out[t, ncol0 + n] = sum_k X[t, k] * W[n, k] + b[n]   (fp32 FMA; setup only)
+__global__ void addend_kernel(const float* __restrict__ X, int T, int K, const float* __restrict__ W,
+                              const float* __restrict__ b, int N, float* __restrict__ out, int out_ld, int ncol0) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (n >= N || t >= T) return;
+  float acc = 0.f;
+  if (X != nullptr) {
+    const float* x = X + static_cast<long long>(t) * K;
+    const float* w = W + static_cast<long long>(n) * K;
+    for (int k = 0; k < K; ++k) acc = fmaf(x[k], w[k], acc);
+  }
+  out[static_cast<long long>(t) * out_ld + ncol0 + n] = acc + (b ? b[n] : 0.f);
+}
+
+struct HostTensor {
+  const float* data;
+  std::vector<long long> shape;
+  long long numel() const {
+    long long n = 1;
+    for (long long s : shape) n *= s;
+    return n;
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------------
+struct GemmW {          // one GEMM's parameters on the device
+  void* w = nullptr;    // [N, K] storage dtype
+  float* scale = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0;
+};
+
+struct Bottleneck {
+  GemmW c1, c2, c3, down;
+  int inplanes = 0, planes = 0, stride = 1;
+  bool has_down = false;
+};
+
+struct EncLayer {
+  GemmW qkv, out, ff1, ff2;
+  float* addend = nullptr;  // [tokens, 768]
+  float *n1g, *n1b, *n2g, *n2b;
+};
+
+struct DecLayer {
+  GemmW sa_qkv, sa_out, ca_q, ca_out, ff1, ff2;
+  float* sa_addend = nullptr;  // [Q, 768]
+  float* ca_q_addend = nullptr;  // [Q, 256]
+  float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
+};
+
+}  // namespace spe
+
+using namespace spe;
+
+struct spe_ctx {
+  spe_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  Dtype dt = kTF32;
+  std::string err;
+  bool weights_loaded = false;
+
+  int featH = 0, tokens = 0, featC = 0;
+
+  std::vector<void*> allocs;  // everything cudaMalloc'ed, freed in destroy
+
+  // weights
+  GemmW stem;
+  std::vector<Bottleneck> blocks;
+  GemmW s8_lat, s16_lat, out_conv, input_proj;
+  std::vector<EncLayer> enc;
+  std::vector<DecLayer> dec;
+  GemmW ca_kv_all;             // [L*512, 256]
+  float* ca_kv_addend = nullptr;  // [tokens, L*512]
+  float *dn_g = nullptr, *dn_b = nullptr;
+  GemmW pt0, pt1, sg0, sg1;
+  float *cls_w = nullptr, *cls_b = nullptr, *pt2_w = nullptr, *pt2_b = nullptr, *sg2_w = nullptr, *sg2_b = nullptr;
+
+  // workspace (storage dtype unless noted)
+  void *S0 = nullptr, *S1 = nullptr, *P0 = nullptr, *P1 = nullptr, *T1 = nullptr, *T2 = nullptr, *DS = nullptr,
+       *COL = nullptr, *L2OUT = nullptr, *L3OUT = nullptr, *UP = nullptr, *CAT = nullptr, *FEAT = nullptr,
+       *X = nullptr, *X2 = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr, *KV = nullptr;
+  void *TGT = nullptr, *TGT2 = nullptr, *DQKV = nullptr, *DQ = nullptr, *DATT = nullptr, *DHID = nullptr,
+       *HS = nullptr, *H1 = nullptr, *H2 = nullptr, *G1 = nullptr, *G2 = nullptr;
+  float *logits_all = nullptr, *points_all = nullptr;
+
+  // pipeline buffers for spe_run_batch_host
+  uint8_t* frames_dev = nullptr;
+  long long frames_cap = 0;
+  int32_t* boxes_dev = nullptr;
+  float* images_dev = nullptr;
+  float *p_logits = nullptr, *p_points = nullptr, *p_logsig = nullptr;
+  double *p_quat = nullptr, *p_tvec = nullptr;
+  int32_t *p_assign = nullptr, *p_status = nullptr;
+
+  // debug taps
+  bool taps_enabled = false;
+  struct Tap { void* buf; long long bytes; };
+  std::map<std::string, Tap> taps;
+};
+
+namespace spe {
+
+static std::string g_last_error;
+
+static int fail(spe_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_last_error = msg;
+  return code;
+}
+
+template <typename T>
+static std::string dmalloc(spe_ctx* ctx, T** p, long long count) {
+  void* q = nullptr;
+  SPE_CUDA_TRY(cudaMalloc(&q, static_cast<size_t>(count > 0 ? count : 1) * sizeof(T)));
+  ctx->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return "";
+}
+static std::string dmalloc_bytes(spe_ctx* ctx, void** p, long long bytes) {
+  void* q = nullptr;
+  SPE_CUDA_TRY(cudaMalloc(&q, static_cast<size_t>(bytes > 0 ? bytes : 16)));
+  ctx->allocs.push_back(q);
+  *p = q;
+  return "";
+}
+
+#define TRY_S(expr)                         \
+  do {                                      \
+    std::string _s = (expr);                \
+    if (!_s.empty()) return _s;             \
+  } while (0)
+
+// upload host fp32 -> device fp32
+static std::string upload_f32(spe_ctx* ctx, const float* host, long long n, float** out) {
+  TRY_S(dmalloc(ctx, out, n));
+  SPE_CUDA_TRY(cudaMemcpy(*out, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice));
+  return "";
+}
+
+// upload a host fp32 [N,K] matrix as GEMM weights in the storage dtype (tf32-rounded fp32 or bf16)
+static std::string upload_gemm_w(spe_ctx* ctx, const std::vector<float>& host, int N, int K, GemmW* g) {
+  float* tmp = nullptr;
+  const long long n = static_cast<long long>(N) * K;
+  SPE_CUDA_TRY(cudaMalloc(&tmp, static_cast<size_t>(n) * sizeof(float)));
+  cudaError_t e = cudaMemcpy(tmp, host.data(), static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(tmp); return std::string("upload weights: ") + cudaGetErrorString(e); }
+  std::string s = dmalloc_bytes(ctx, &g->w, n * static_cast<long long>(dtype_size(ctx->dt)));
+  if (!s.empty()) { cudaFree(tmp); return s; }
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  if (ctx->dt == kTF32) f32_to_tf32_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<float*>(g->w), n);
+  else f32_to_bf16_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<__nv_bfloat16*>(g->w), n);
+  e = cudaDeviceSynchronize();
+  cudaFree(tmp);
+  if (e != cudaSuccess) return std::string("convert weights: ") + cudaGetErrorString(e);
+  g->N = N;
+  g->K = K;
+  return "";
+}
+
+struct WeightSource {
+  std::map<std::string, HostTensor> t;
+  std::string missing;
+  const HostTensor* get(const std::string& name, std::initializer_list<long long> shape) {
+    auto it = t.find(name);
+    if (it == t.end()) { if (missing.empty()) missing = "missing tensor '" + name + "'"; return nullptr; }
+    std::vector<long long> want(shape);
+    if (it->second.shape != want) {
+      if (missing.empty()) {
+        missing = "tensor '" + name + "' has shape [";
+        for (size_t i = 0; i < it->second.shape.size(); ++i) missing += (i ? "," : "") + std::to_string(it->second.shape[i]);
+        missing += "], expected [";
+        for (size_t i = 0; i < want.size(); ++i) missing += (i ? "," : "") + std::to_string(want[i]);
+        missing += "]";
+      }
+      return nullptr;
+    }
+    return &it->second;
+  }
+};
+
+// conv weight (Cout, Cin, R, S) -> [Cout][(r*S + s)*Cin + c], K padded with zeros to Kpad
+static std::vector<float> repack_conv(const HostTensor& w, int Kpad = 0) {
+  const int Cout = static_cast<int>(w.shape[0]), Cin = static_cast<int>(w.shape[1]);
+  const int R = static_cast<int>(w.shape[2]), S = static_cast<int>(w.shape[3]);
+  const int K = R * S * Cin;
+  const int Kp = Kpad > 0 ? Kpad : K;
+  std::vector<float> out(static_cast<size_t>(Cout) * Kp, 0.f);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < Cin; ++c)
+      for (int r = 0; r < R; ++r)
+        for (int s = 0; s < S; ++s)
+          out[static_cast<size_t>(o) * Kp + (r * S + s) * Cin + c] =
+              w.data[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s];
+  return out;
+}
+
+// FrozenBatchNorm2d fold, same fp32 op order as RV/models/backbone.py:44-54
+static std::string load_bn(spe_ctx* ctx, WeightSource& ws, const std::string& prefix, int C, GemmW* g) {
+  const HostTensor* w = ws.get(prefix + ".weight", {C});
+  const HostTensor* b = ws.get(prefix + ".bias", {C});
+  const HostTensor* rm = ws.get(prefix + ".running_mean", {C});
+  const HostTensor* rv = ws.get(prefix + ".running_var", {C});
+  if (!w || !b || !rm || !rv) return ws.missing;
+  std::vector<float> scale(C), bias(C);
+  for (int i = 0; i < C; ++i) {
+    const float sc = w->data[i] * (1.0f / sqrtf(rv->data[i] + 1e-5f));
+    scale[i] = sc;
+    bias[i] = b->data[i] - rm->data[i] * sc;
+  }
+  TRY_S(upload_f32(ctx, scale.data(), C, &g->scale));
+  TRY_S(upload_f32(ctx, bias.data(), C, &g->bias));
+  return "";
+}
+
+static std::string load_conv_bn(spe_ctx* ctx, WeightSource& ws, const std::string& conv, const std::string& bn,
+                                int Cout, int Cin, int R, GemmW* g, int Kpad = 0) {
+  const HostTensor* w = ws.get(conv + ".weight", {Cout, Cin, R, R});
+  if (!w) return ws.missing;
+  TRY_S(upload_gemm_w(ctx, repack_conv(*w, Kpad), Cout, Kpad > 0 ? Kpad : R * R * Cin, g));
+  if (!bn.empty()) TRY_S(load_bn(ctx, ws, bn, Cout, g));
+  return "";
+}
+
+static std::string load_linear(spe_ctx* ctx, WeightSource& ws, const std::string& p, int out_f, int in_f, GemmW* g) {
+  const HostTensor* w = ws.get(p + ".weight", {out_f, in_f});
+  const HostTensor* b = ws.get(p + ".bias", {out_f});
+  if (!w || !b) return ws.missing;
+  TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + w->numel()), out_f, in_f, g));
+  TRY_S(upload_f32(ctx, b->data, out_f, &g->bias));
+  return "";
+}
+
+static std::string load_vec(spe_ctx* ctx, WeightSource& ws, const std::string& name, int n, float** out) {
+  const HostTensor* t = ws.get(name, {n});
+  if (!t) return ws.missing;
+  return upload_f32(ctx, t->data, n, out);
+}
+
+// PositionEmbeddingSine with an all-False mask, normalize=True (RV/models/position_encoding.py:30-53)
+static std::vector<float> make_pos(int H, int W, int E) {
+  const int npf = E / 2;
+  std::vector<float> pos(static_cast<size_t>(H) * W * E);
+  const float two_pi = 2.0f * static_cast<float>(M_PI);
+  for (int i = 0; i < H; ++i)
+    for (int j = 0; j < W; ++j) {
+      const float ye = static_cast<float>(i + 1) / (static_cast<float>(H) + 1e-6f) * two_pi;
+      const float xe = static_cast<float>(j + 1) / (static_cast<float>(W) + 1e-6f) * two_pi;
+      float* p = pos.data() + (static_cast<size_t>(i) * W + j) * E;
+      for (int k = 0; k < npf; ++k) {
+        const float dim_t = powf(10000.0f, 2.0f * static_cast<float>(k / 2) / static_cast<float>(npf));
+        const float vy = ye / dim_t, vx = xe / dim_t;
+        p[k] = (k % 2 == 0) ? sinf(vy) : cosf(vy);
+        p[npf + k] = (k % 2 == 0) ? sinf(vx) : cosf(vx);
+      }
+    }
+  return pos;
+}
+
+// addend[:, col0 : col0+N] = X W^T + b  (X may be null -> bias only); W/b are host slices
+static std::string make_addend(spe_ctx* ctx, const float* X_dev, int T, int K, const float* W_host,
+                               const float* b_host, int N, float* out_dev, int out_ld, int col0) {
+  float *Wd = nullptr, *bd = nullptr;
+  SPE_CUDA_TRY(cudaMalloc(&Wd, static_cast<size_t>(N) * K * sizeof(float)));
+  SPE_CUDA_TRY(cudaMalloc(&bd, static_cast<size_t>(N) * sizeof(float)));
+  cudaMemcpy(Wd, W_host, static_cast<size_t>(N) * K * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(bd, b_host, static_cast<size_t>(N) * sizeof(float), cudaMemcpyHostToDevice);
+  dim3 grid((N + 127) / 128, T);
+  addend_kernel<<<grid, 128>>>(X_dev, T, K, Wd, bd, N, out_dev, out_ld, col0);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(Wd);
+  cudaFree(bd);
+  if (e != cudaSuccess) return std::string("addend: ") + cudaGetErrorString(e);
+  return "";
+}
+
+static std::string load_mha_self(spe_ctx* ctx, WeightSource& ws, const std::string& p, const float* posX_dev, int T,
+                                 GemmW* qkv, GemmW* out, float** addend) {
+  const int E = 256;
+  const HostTensor* w = ws.get(p + ".in_proj_weight", {3 * E, E});
+  const HostTensor* b = ws.get(p + ".in_proj_bias", {3 * E});
+  if (!w || !b) return ws.missing;
+  TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + w->numel()), 3 * E, E, qkv));
+  TRY_S(dmalloc(ctx, addend, static_cast<long long>(T) * 3 * E));
+  // q and k see (x + pos); v sees x only
+  TRY_S(make_addend(ctx, posX_dev, T, E, w->data, b->data, 2 * E, *addend, 3 * E, 0));
+  TRY_S(make_addend(ctx, nullptr, T, E, w->data + 2 * E * E, b->data + 2 * E, E, *addend, 3 * E, 2 * E));
+  TRY_S(load_linear(ctx, ws, p + ".out_proj", E, E, out));
+  return "";
+}
+
+std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
+  const spe_config& c = ctx->cfg;
+  const int E = 256, FF = c.dim_feedforward, Q = c.num_queries, T = ctx->tokens;
+  const std::string b = "backbone.0.body";
+  // ---- stem + layers
+  TRY_S(load_conv_bn(ctx, ws, b + ".conv1", b + ".bn1", 64, 3, 7, &ctx->stem, 192));
+  ctx->blocks.clear();
+  int inplanes = 64;
+  const int nblk[3] = {3, 4, 6};
+  const int planes_[3] = {64, 128, 256};
+  for (int li = 0; li < 3; ++li)
+    for (int bi = 0; bi < nblk[li]; ++bi) {
+      Bottleneck bk;
+      bk.inplanes = inplanes;
+      bk.planes = planes_[li];
+      bk.stride = (bi == 0 && li > 0) ? 2 : 1;
+      bk.has_down = (bi == 0);
+      const std::string p = b + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      TRY_S(load_conv_bn(ctx, ws, p + ".conv1", p + ".bn1", bk.planes, inplanes, 1, &bk.c1));
+      TRY_S(load_conv_bn(ctx, ws, p + ".conv2", p + ".bn2", bk.planes, bk.planes, 3, &bk.c2));
+      TRY_S(load_conv_bn(ctx, ws, p + ".conv3", p + ".bn3", bk.planes * 4, bk.planes, 1, &bk.c3));
+      if (bk.has_down)
+        TRY_S(load_conv_bn(ctx, ws, p + ".downsample.0", p + ".downsample.1", bk.planes * 4, inplanes, 1, &bk.down));
+      inplanes = bk.planes * 4;
+      ctx->blocks.push_back(bk);
+    }
+  // ---- neck
+  if (c.backbone == 0) {
+    TRY_S(load_conv_bn(ctx, ws, "backbone.0.s8_latern", "", 256, 512, 1, &ctx->s8_lat));
+    TRY_S(load_conv_bn(ctx, ws, "backbone.0.s16_latern", "", 256, 1024, 3, &ctx->s16_lat));
+    TRY_S(load_conv_bn(ctx, ws, "backbone.0.output_conv", "", 512, 512, 3, &ctx->out_conv));
+    TRY_S(load_vec(ctx, ws, "backbone.0.output_conv.bias", 512, &ctx->out_conv.bias));
+  }
+  TRY_S(load_conv_bn(ctx, ws, "input_proj", "", E, ctx->featC, 1, &ctx->input_proj));
+  TRY_S(load_vec(ctx, ws, "input_proj.bias", E, &ctx->input_proj.bias));
+
+  // ---- positional embedding and query embedding on the device (fp32) for the addends
+  std::vector<float> pos = make_pos(ctx->featH, ctx->featH, E);
+  float *pos_dev = nullptr, *qe_dev = nullptr;
+  SPE_CUDA_TRY(cudaMalloc(&pos_dev, pos.size() * sizeof(float)));
+  cudaMemcpy(pos_dev, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice);
+  const HostTensor* qe = ws.get("query_embed.weight", {Q, E});
+  if (!qe) { cudaFree(pos_dev); return ws.missing; }
+  SPE_CUDA_TRY(cudaMalloc(&qe_dev, static_cast<size_t>(Q) * E * sizeof(float)));
+  cudaMemcpy(qe_dev, qe->data, static_cast<size_t>(Q) * E * sizeof(float), cudaMemcpyHostToDevice);
+
+  std::string s;
+  auto body = [&]() -> std::string {
+    // ---- encoder
+    ctx->enc.assign(c.enc_layers, EncLayer{});
+    for (int i = 0; i < c.enc_layers; ++i) {
+      EncLayer& L = ctx->enc[i];
+      const std::string p = "transformer.encoder.layers." + std::to_string(i);
+      TRY_S(load_mha_self(ctx, ws, p + ".self_attn", pos_dev, T, &L.qkv, &L.out, &L.addend));
+      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1));
+      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2));
+      TRY_S(load_vec(ctx, ws, p + ".norm1.weight", E, &L.n1g));
+      TRY_S(load_vec(ctx, ws, p + ".norm1.bias", E, &L.n1b));
+      TRY_S(load_vec(ctx, ws, p + ".norm2.weight", E, &L.n2g));
+      TRY_S(load_vec(ctx, ws, p + ".norm2.bias", E, &L.n2b));
+    }
+    // ---- decoder
+    ctx->dec.assign(c.dec_layers, DecLayer{});
+    const int LD = c.dec_layers;
+    std::vector<float> kv_w(static_cast<size_t>(LD) * 2 * E * E);
+    TRY_S(dmalloc(ctx, &ctx->ca_kv_addend, static_cast<long long>(T) * LD * 2 * E));
+    for (int i = 0; i < LD; ++i) {
+      DecLayer& L = ctx->dec[i];
+      const std::string p = "transformer.decoder.layers." + std::to_string(i);
+      TRY_S(load_mha_self(ctx, ws, p + ".self_attn", qe_dev, Q, &L.sa_qkv, &L.sa_out, &L.sa_addend));
+      const HostTensor* w = ws.get(p + ".multihead_attn.in_proj_weight", {3 * E, E});
+      const HostTensor* bb = ws.get(p + ".multihead_attn.in_proj_bias", {3 * E});
+      if (!w || !bb) return ws.missing;
+      // query projection: (tgt + query_pos) Wq^T + bq
+      TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + E * E), E, E, &L.ca_q));
+      TRY_S(dmalloc(ctx, &L.ca_q_addend, static_cast<long long>(Q) * E));
+      TRY_S(make_addend(ctx, qe_dev, Q, E, w->data, bb->data, E, L.ca_q_addend, E, 0));
+      // key/value projections of every layer share the encoder memory: stack them into one GEMM
+      memcpy(kv_w.data() + static_cast<size_t>(i) * 2 * E * E, w->data + E * E, sizeof(float) * 2 * E * E);
+      TRY_S(make_addend(ctx, pos_dev, T, E, w->data + E * E, bb->data + E, E, ctx->ca_kv_addend, LD * 2 * E,
+                        i * 2 * E));
+      TRY_S(make_addend(ctx, nullptr, T, E, w->data + 2 * E * E, bb->data + 2 * E, E, ctx->ca_kv_addend,
+                        LD * 2 * E, i * 2 * E + E));
+      TRY_S(load_linear(ctx, ws, p + ".multihead_attn.out_proj", E, E, &L.ca_out));
+      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1));
+      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2));
+      TRY_S(load_vec(ctx, ws, p + ".norm1.weight", E, &L.n1g));
+      TRY_S(load_vec(ctx, ws, p + ".norm1.bias", E, &L.n1b));
+      TRY_S(load_vec(ctx, ws, p + ".norm2.weight", E, &L.n2g));
+      TRY_S(load_vec(ctx, ws, p + ".norm2.bias", E, &L.n2b));
+      TRY_S(load_vec(ctx, ws, p + ".norm3.weight", E, &L.n3g));
+      TRY_S(load_vec(ctx, ws, p + ".norm3.bias", E, &L.n3b));
+    }
+    TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all));
+    TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.weight", E, &ctx->dn_g));
+    TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.bias", E, &ctx->dn_b));
+    // ---- heads
+    const HostTensor* cw = ws.get("cls_embed.weight", {12, E});
+    if (!cw) return ws.missing;
+    TRY_S(upload_f32(ctx, cw->data, 12 * E, &ctx->cls_w));
+    TRY_S(load_vec(ctx, ws, "cls_embed.bias", 12, &ctx->cls_b));
+    TRY_S(load_linear(ctx, ws, "point_embed.layers.0", E, E, &ctx->pt0));
+    TRY_S(load_linear(ctx, ws, "point_embed.layers.1", E, E, &ctx->pt1));
+    const HostTensor* p2 = ws.get("point_embed.layers.2.weight", {2, E});
+    if (!p2) return ws.missing;
+    TRY_S(upload_f32(ctx, p2->data, 2 * E, &ctx->pt2_w));
+    TRY_S(load_vec(ctx, ws, "point_embed.layers.2.bias", 2, &ctx->pt2_b));
+    if (c.has_sigma) {
+      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.0", E, E, &ctx->sg0));
+      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.1", E, E, &ctx->sg1));
+      const HostTensor* s2 = ws.get("sigma_embed.layers.2.weight", {1, E});
+      if (!s2) return ws.missing;
+      TRY_S(upload_f32(ctx, s2->data, E, &ctx->sg2_w));
+      TRY_S(load_vec(ctx, ws, "sigma_embed.layers.2.bias", 1, &ctx->sg2_b));
+    }
+    return "";
+  };
+  s = body();
+  cudaFree(pos_dev);
+  cudaFree(qe_dev);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------------------------
+std::string alloc_workspace(spe_ctx* ctx) {
+  const spe_config& c = ctx->cfg;
+  const long long B = c.max_batch;
+  const long long es = static_cast<long long>(dtype_size(ctx->dt));
+  const long long R = c.input_size;
+  const long long h2 = R / 2, h4 = R / 4, h8 = R / 8, h16 = R / 16;
+  const long long T = ctx->tokens, Q = c.num_queries, LD = c.dec_layers, FF = c.dim_feedforward;
+  auto A = [&](void** p, long long elems) { return dmalloc_bytes(ctx, p, elems * es); };
+  TRY_S(A(&ctx->S0, B * h2 * h2 * 192));
+  TRY_S(A(&ctx->S1, B * h2 * h2 * 64));
+  TRY_S(A(&ctx->P0, B * h4 * h4 * 256));
+  TRY_S(A(&ctx->P1, B * h4 * h4 * 256));
+  TRY_S(A(&ctx->T1, B * h4 * h4 * 128));
+  TRY_S(A(&ctx->T2, B * h4 * h4 * 128));
+  TRY_S(A(&ctx->DS, B * h4 * h4 * 256));
+  TRY_S(A(&ctx->COL, B * h8 * h8 * 1152));
+  TRY_S(A(&ctx->L2OUT, B * h8 * h8 * 512));
+  TRY_S(A(&ctx->L3OUT, B * h16 * h16 * 1024));
+  if (c.backbone == 0) {
+    TRY_S(A(&ctx->UP, B * h8 * h8 * 1024));
+    TRY_S(A(&ctx->CAT, B * h8 * h8 * 512));
+    TRY_S(A(&ctx->FEAT, B * h8 * h8 * 512));
+  }
+  TRY_S(A(&ctx->X, B * T * 256));
+  TRY_S(A(&ctx->X2, B * T * 256));
+  TRY_S(A(&ctx->QKV, B * T * 768));
+  TRY_S(A(&ctx->ATT, B * T * 256));
+  TRY_S(A(&ctx->HID, B * T * FF));
+  TRY_S(A(&ctx->KV, B * T * LD * 512));
+  TRY_S(A(&ctx->TGT, B * Q * 256));
+  TRY_S(A(&ctx->TGT2, B * Q * 256));
+  TRY_S(A(&ctx->DQKV, B * Q * 768));
+  TRY_S(A(&ctx->DQ, B * Q * 256));
+  TRY_S(A(&ctx->DATT, B * Q * 256));
+  TRY_S(A(&ctx->DHID, B * Q * FF));
+  TRY_S(A(&ctx->HS, LD * B * Q * 256));
+  TRY_S(A(&ctx->H1, LD * B * Q * 256));
+  TRY_S(A(&ctx->H2, LD * B * Q * 256));
+  TRY_S(A(&ctx->G1, B * Q * 256));
+  TRY_S(A(&ctx->G2, B * Q * 256));
+  // pipeline buffers
+  TRY_S(dmalloc(ctx, &ctx->boxes_dev, B * 4));
+  TRY_S(dmalloc(ctx, &ctx->images_dev, B * 3 * R * R));
+  TRY_S(dmalloc(ctx, &ctx->p_logits, B * Q * 12));
+  TRY_S(dmalloc(ctx, &ctx->p_points, B * Q * 2));
+  TRY_S(dmalloc(ctx, &ctx->p_logsig, B * Q * 2));
+  TRY_S(dmalloc(ctx, &ctx->p_quat, B * 4));
+  TRY_S(dmalloc(ctx, &ctx->p_tvec, B * 3));
+  TRY_S(dmalloc(ctx, &ctx->p_assign, B * 11));
+  TRY_S(dmalloc(ctx, &ctx->p_status, B));
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Fwd {
+  spe_ctx* ctx;
+  cudaStream_t st;
+  int B;
+  Dtype dt;
+  long long es;
+
+  void* col(void* base, long long elem_off) const { return static_cast<uint8_t*>(base) + elem_off * es; }
+
+  std::string tap(const char* name, const void* buf, long long elems) {
+    if (!ctx->taps_enabled) return "";
+    const long long bytes = elems * es;
+    auto it = ctx->taps.find(name);
+    if (it == ctx->taps.end() || it->second.bytes < bytes) {
+      void* p = nullptr;
+      SPE_CUDA_TRY(cudaMalloc(&p, static_cast<size_t>(bytes)));
+      ctx->allocs.push_back(p);
+      ctx->taps[name] = spe_ctx::Tap{p, bytes};
+      it = ctx->taps.find(name);
+    }
+    it->second.bytes = bytes;
+    SPE_CUDA_TRY(cudaMemcpyAsync(it->second.buf, buf, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, st));
+    return "";
+  }
+
+  // out[M, N] = act(scale * A W^T + bias (+ residual))
+  std::string gemm(const void* A, long long M, const GemmW& w, void* out, int out_ld, bool relu,
+                   const void* residual = nullptr, int res_ld = 0, int res_mod = 0, int res_f32 = 0,
+                   bool use_scale_bias = true) {
+    GemmDesc d;
+    d.mode = 0;
+    d.A = A; d.M = M; d.K = w.K; d.lda = w.K;
+    d.Wt = w.w; d.N = w.N;
+    d.scale = use_scale_bias ? w.scale : nullptr;
+    d.bias = use_scale_bias ? w.bias : nullptr;
+    d.residual = residual; d.res_ld = res_ld; d.res_mod = res_mod; d.res_f32 = res_f32;
+    d.relu = relu ? 1 : 0;
+    d.out = out; d.out_ld = out_ld;
+    return launch_gemm(dt, d, ctx->num_sms, st);
+  }
+  // 3x3 / stride 1 / pad 1 convolution as implicit GEMM
+  std::string conv3x3(const void* x, int H, int C, const GemmW& w, void* out, int out_ld, bool relu) {
+    GemmDesc d;
+    d.mode = 1;
+    d.A = x; d.NB = B; d.H = H; d.W = H; d.C = C; d.R = 3; d.S = 3; d.pad = 1;
+    d.Wt = w.w; d.N = w.N;
+    d.scale = w.scale; d.bias = w.bias;
+    d.relu = relu ? 1 : 0;
+    d.out = out; d.out_ld = out_ld;
+    return launch_gemm(dt, d, ctx->num_sms, st);
+  }
+  std::string attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int Lq,
+                   int Lk) {
+    AttnDesc a;
+    a.q = q; a.k = k; a.v = v; a.out = out;
+    a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = 256;
+    a.bsq = static_cast<long long>(Lq) * ldq; a.bsk = static_cast<long long>(Lk) * ldk;
+    a.bsv = static_cast<long long>(Lk) * ldv; a.bso = static_cast<long long>(Lq) * 256;
+    a.B = B; a.heads = 8; a.Lq = Lq; a.Lk = Lk;
+    a.scale = 1.0f / sqrtf(32.0f);
+    return launch_attention(dt, a, st);
+  }
+  std::string ln(const void* in, const float* g, const float* b, long long rows, void* out) {
+    return launch_layernorm(dt, in, g, b, rows, 256, out, st);
+  }
+};
+
+}  // namespace
+
+std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits, float* points, float* logsig,
+                         float* aux_logits, float* aux_points, cudaStream_t st) {
+  const spe_config& c = ctx->cfg;
+  Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
+  const int R = c.input_size;
+  const int h2 = R / 2, h4 = R / 4;
+  const long long Bl = B;
+
+  // ---- stem
+  TRY_S(launch_stem_im2col(f.dt, images, B, R, R, ctx->S0, st));
+  TRY_S(f.gemm(ctx->S0, Bl * h2 * h2, ctx->stem, ctx->S1, 64, true));
+  TRY_S(f.tap("stem", ctx->S1, Bl * h2 * h2 * 64));
+  TRY_S(launch_maxpool3x3s2(f.dt, ctx->S1, B, h2, h2, 64, ctx->P0, st));
+
+  // ---- layer1..layer3
+  void* cur = ctx->P0;
+  int H = h4;
+  int bidx = 0;
+  const int nblk[3] = {3, 4, 6};
+  for (int li = 0; li < 3; ++li) {
+    for (int bi = 0; bi < nblk[li]; ++bi, ++bidx) {
+      const Bottleneck& bk = ctx->blocks[bidx];
+      const int Ho = H / bk.stride;
+      const long long Min = Bl * H * H, Mout = Bl * Ho * Ho;
+      void* nxt;
+      if (bi == nblk[li] - 1 && li == 1) nxt = ctx->L2OUT;
+      else if (bi == nblk[li] - 1 && li == 2) nxt = ctx->L3OUT;
+      else nxt = (cur == ctx->P0) ? ctx->P1 : ctx->P0;
+      TRY_S(f.gemm(cur, Min, bk.c1, ctx->T1, bk.planes, true));
+      if (bk.stride == 1) {
+        TRY_S(f.conv3x3(ctx->T1, H, bk.planes, bk.c2, ctx->T2, bk.planes, true));
+      } else {
+        TRY_S(launch_im2col_nhwc(f.dt, ctx->T1, B, H, H, bk.planes, 3, 3, 2, 1, ctx->COL, st));
+        TRY_S(f.gemm(ctx->COL, Mout, bk.c2, ctx->T2, bk.planes, true));
+      }
+      const void* identity = cur;
+      if (bk.has_down) {
+        if (bk.stride == 1) {
+          TRY_S(f.gemm(cur, Min, bk.down, ctx->DS, bk.planes * 4, false));
+        } else {
+          TRY_S(launch_im2col_nhwc(f.dt, cur, B, H, H, bk.inplanes, 1, 1, 2, 0, ctx->COL, st));
+          TRY_S(f.gemm(ctx->COL, Mout, bk.down, ctx->DS, bk.planes * 4, false));
+        }
+        identity = ctx->DS;
+      }
+      TRY_S(f.gemm(ctx->T2, Mout, bk.c3, nxt, bk.planes * 4, true, identity, bk.planes * 4));
+      cur = nxt;
+      H = Ho;
+    }
+    const char* names[3] = {"layer1", "layer2", "layer3"};
+    TRY_S(f.tap(names[li], cur, Bl * H * H * ctx->blocks[bidx - 1].planes * 4));
+  }
+
+  // ---- neck
+  const int FH = ctx->featH;
+  const long long T = ctx->tokens;
+  const void* feat;
+  if (c.backbone == 0) {
+    const int h16 = R / 16;
+    TRY_S(f.gemm(ctx->L2OUT, Bl * T, ctx->s8_lat, ctx->CAT, 512, false));
+    TRY_S(launch_upsample2x(f.dt, ctx->L3OUT, B, h16, h16, 1024, ctx->UP, st));
+    TRY_S(f.conv3x3(ctx->UP, FH, 1024, ctx->s16_lat, f.col(ctx->CAT, 256), 512, false));
+    TRY_S(f.conv3x3(ctx->CAT, FH, 512, ctx->out_conv, ctx->FEAT, 512, false));
+    TRY_S(f.tap("neck", ctx->FEAT, Bl * T * 512));
+    feat = ctx->FEAT;
+  } else {
+    feat = ctx->L3OUT;
+  }
+  TRY_S(f.gemm(feat, Bl * T, ctx->input_proj, ctx->X, 256, false));
+  TRY_S(f.tap("input_proj", ctx->X, Bl * T * 256));
+
+  // ---- encoder
+  const int Ti = static_cast<int>(T);
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const EncLayer& L = ctx->enc[i];
+    TRY_S(f.gemm(ctx->X, Bl * T, L.qkv, ctx->QKV, 768, false, L.addend, 768, Ti, 1));
+    TRY_S(f.attn(ctx->QKV, 768, f.col(ctx->QKV, 256), 768, f.col(ctx->QKV, 512), 768, ctx->ATT, Ti, Ti));
+    TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, ctx->X, 256));
+    TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, ctx->X));
+    TRY_S(f.gemm(ctx->X, Bl * T, L.ff1, ctx->HID, c.dim_feedforward, true));
+    TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, ctx->X, 256));
+    TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, ctx->X));
+    const std::string nm = "enc" + std::to_string(i);
+    TRY_S(f.tap(nm.c_str(), ctx->X, Bl * T * 256));
+  }
+
+  // ---- decoder
+  const int Q = c.num_queries, LD = c.dec_layers;
+  const long long MQ = Bl * Q;
+  const int kvld = LD * 512;
+  TRY_S(f.gemm(ctx->X, Bl * T, ctx->ca_kv_all, ctx->KV, kvld, false, ctx->ca_kv_addend, kvld, Ti, 1));
+  SPE_CUDA_TRY(cudaMemsetAsync(ctx->TGT, 0, static_cast<size_t>(MQ * 256 * f.es), st));
+  for (int i = 0; i < LD; ++i) {
+    const DecLayer& L = ctx->dec[i];
+    TRY_S(f.gemm(ctx->TGT, MQ, L.sa_qkv, ctx->DQKV, 768, false, L.sa_addend, 768, Q, 1));
+    TRY_S(f.attn(ctx->DQKV, 768, f.col(ctx->DQKV, 256), 768, f.col(ctx->DQKV, 512), 768, ctx->DATT, Q, Q));
+    TRY_S(f.gemm(ctx->DATT, MQ, L.sa_out, ctx->TGT2, 256, false, ctx->TGT, 256));
+    TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT));
+    TRY_S(f.gemm(ctx->TGT, MQ, L.ca_q, ctx->DQ, 256, false, L.ca_q_addend, 256, Q, 1));
+    TRY_S(f.attn(ctx->DQ, 256, f.col(ctx->KV, i * 512), kvld, f.col(ctx->KV, i * 512 + 256), kvld, ctx->DATT, Q, Ti));
+    TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, ctx->TGT, 256));
+    TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT));
+    TRY_S(f.gemm(ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
+    TRY_S(f.gemm(ctx->DHID, MQ, L.ff2, ctx->TGT2, 256, false, ctx->TGT, 256));
+    TRY_S(f.ln(ctx->TGT2, L.n3g, L.n3b, MQ, ctx->TGT));
+    TRY_S(f.ln(ctx->TGT, ctx->dn_g, ctx->dn_b, MQ, f.col(ctx->HS, static_cast<long long>(i) * MQ * 256)));
+  }
+  TRY_S(f.tap("hs", ctx->HS, static_cast<long long>(LD) * MQ * 256));
+
+  // ---- heads (all decoder layers only when the caller wants aux outputs)
+  const bool want_aux = (aux_logits != nullptr && aux_points != nullptr && LD > 1);
+  const int l_first = want_aux ? 0 : LD - 1;
+  const long long rows = static_cast<long long>(LD - l_first) * MQ;
+  const void* hs = f.col(ctx->HS, static_cast<long long>(l_first) * MQ * 256);
+  TRY_S(f.gemm(hs, rows, ctx->pt0, ctx->H1, 256, true));
+  TRY_S(f.gemm(ctx->H1, rows, ctx->pt1, ctx->H2, 256, true));
+  const void* hs_last = f.col(ctx->HS, static_cast<long long>(LD - 1) * MQ * 256);
+  const void* h2_last = f.col(ctx->H2, static_cast<long long>(LD - 1 - l_first) * MQ * 256);
+  const bool sig = c.has_sigma && logsig != nullptr;
+  if (sig) {
+    TRY_S(f.gemm(hs_last, MQ, ctx->sg0, ctx->G1, 256, true));
+    TRY_S(f.gemm(ctx->G1, MQ, ctx->sg1, ctx->G2, 256, true));
+  }
+  TRY_S(launch_head_final(f.dt, hs_last, h2_last, sig ? ctx->G2 : nullptr, MQ, ctx->cls_w, ctx->cls_b, ctx->pt2_w,
+                          ctx->pt2_b, ctx->sg2_w, ctx->sg2_b, logits, points, logsig, st));
+  if (want_aux) {
+    TRY_S(launch_head_final(f.dt, ctx->HS, ctx->H2, nullptr, static_cast<long long>(LD - 1) * MQ, ctx->cls_w,
+                            ctx->cls_b, ctx->pt2_w, ctx->pt2_b, nullptr, nullptr, aux_logits, aux_points, nullptr,
+                            st));
+  }
+  return "";
+}
+
+}  // namespace spe
+
+// ------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* spe_global_last_error(void) { return g_last_error.c_str(); }
+
+const char* spe_last_error(const spe_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int spe_create(const spe_config* cfg, int device, spe_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, SPE_ERR_INVALID, "spe_create: null argument");
+  *out = nullptr;
+  if (cfg->hidden_dim != 256 || cfg->nheads != 8)
+    return fail(nullptr, SPE_ERR_INVALID, "spe_create: only hidden_dim=256, nheads=8 (head_dim 32) is built");
+  if (cfg->input_size <= 0 || cfg->input_size % 32 != 0)
+    return fail(nullptr, SPE_ERR_INVALID, "spe_create: input_size must be a positive multiple of 32");
+  if (cfg->backbone != 0 && cfg->backbone != 1) return fail(nullptr, SPE_ERR_INVALID, "spe_create: backbone must be 0 or 1");
+  if (cfg->precision != 0 && cfg->precision != 1) return fail(nullptr, SPE_ERR_INVALID, "spe_create: precision must be 0 or 1");
+  if (cfg->num_queries <= 0 || cfg->enc_layers <= 0 || cfg->dec_layers <= 0 || cfg->max_batch <= 0 ||
+      cfg->dim_feedforward <= 0 || cfg->dim_feedforward % 64 != 0)
+    return fail(nullptr, SPE_ERR_INVALID, "spe_create: bad layer/query/batch configuration");
+  const int featH = cfg->input_size / (cfg->backbone == 0 ? 8 : 16);
+  if (featH > 128) return fail(nullptr, SPE_ERR_INVALID, "spe_create: feature map wider than 128 is not built");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(nullptr, SPE_ERR_DEVICE, std::string("spe_create: no CUDA device (") + cudaGetErrorString(e) +
+                                             "); this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, SPE_ERR_INVALID, "spe_create: bad device index");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, SPE_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, SPE_ERR_DEVICE, std::string("spe_create: device '") + prop.name +
+                                             "' is not sm_100; kernels are built for sm_100a only");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, SPE_ERR_CUDA, cudaGetErrorString(e));
+  spe_ctx* ctx = new spe_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->dt = cfg->precision == 0 ? kTF32 : kBF16;
+  ctx->featH = featH;
+  ctx->tokens = featH * featH;
+  ctx->featC = cfg->backbone == 0 ? 512 : 1024;
+  std::string s = alloc_workspace(ctx);
+  if (!s.empty()) {
+    fail(nullptr, SPE_ERR_CUDA, "spe_create: " + s);
+    spe_destroy(ctx);
+    return SPE_ERR_CUDA;
+  }
+  *out = ctx;
+  return SPE_OK;
+}
+
+void spe_destroy(spe_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->frames_dev) cudaFree(ctx->frames_dev);
+  delete ctx;
+}
+
+int spe_load_weights(spe_ctx* ctx, const spe_tensor_desc* tensors, int n) {
+  if (!ctx || !tensors || n <= 0) return fail(ctx, SPE_ERR_INVALID, "spe_load_weights: null argument");
+  cudaSetDevice(ctx->device);
+  WeightSource ws;
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].name || !tensors[i].data || tensors[i].ndim < 0 || tensors[i].ndim > 4)
+      return fail(ctx, SPE_ERR_INVALID, "spe_load_weights: malformed tensor descriptor");
+    HostTensor t;
+    t.data = tensors[i].data;
+    for (int k = 0; k < tensors[i].ndim; ++k) t.shape.push_back(tensors[i].shape[k]);
+    ws.t[tensors[i].name] = t;
+  }
+  // NB: re-loading leaks the previous device weights until spe_destroy (weights are loaded once per ctx in practice)
+  std::string s = load_weights_impl(ctx, ws);
+  if (!s.empty()) return fail(ctx, SPE_ERR_WEIGHTS, "spe_load_weights: " + s);
+  ctx->weights_loaded = true;
+  return SPE_OK;
+}
+
+int spe_sync(spe_ctx* ctx, void* stream) {
+  if (!ctx) return fail(nullptr, SPE_ERR_INVALID, "spe_sync: null ctx");
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(ctx, SPE_ERR_CUDA, std::string("spe_sync: ") + cudaGetErrorString(e));
+  return SPE_OK;
+}
+
+int spe_forward(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev, float* points_dev,
+                float* log_sigma_dev, float* aux_logits_dev, float* aux_points_dev, void* stream) {
+  if (!ctx) return fail(nullptr, SPE_ERR_INVALID, "spe_forward: null ctx");
+  if (!ctx->weights_loaded) return fail(ctx, SPE_ERR_STATE, "spe_forward: call spe_load_weights first");
+  if (!images_dev || !logits_dev || !points_dev) return fail(ctx, SPE_ERR_INVALID, "spe_forward: null buffer");
+  if (B <= 0 || B > ctx->cfg.max_batch)
+    return fail(ctx, SPE_ERR_INVALID, "spe_forward: batch " + std::to_string(B) + " outside [1, max_batch=" +
+                                          std::to_string(ctx->cfg.max_batch) + "]");
+  if (log_sigma_dev && !ctx->cfg.has_sigma)
+    return fail(ctx, SPE_ERR_INVALID, "spe_forward: log_sigma requested but the model has no sigma head");
+  cudaSetDevice(ctx->device);
+  std::string s = forward_impl(ctx, images_dev, B, logits_dev, points_dev, log_sigma_dev, aux_logits_dev,
+                               aux_points_dev, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return fail(ctx, SPE_ERR_CUDA, "spe_forward: " + s);
+  return SPE_OK;
+}
+
+int spe_debug_enable_taps(spe_ctx* ctx, int enable) {
+  if (!ctx) return SPE_ERR_INVALID;
+  ctx->taps_enabled = enable != 0;
+  return SPE_OK;
+}
+
+long long spe_debug_read_tap(spe_ctx* ctx, const char* name, void* host_out, long long max_bytes) {
+  if (!ctx || !name) return SPE_ERR_INVALID;
+  auto it = ctx->taps.find(name);
+  if (it == ctx->taps.end()) return fail(ctx, SPE_ERR_INVALID, std::string("no tap named ") + name);
+  if (host_out == nullptr) return it->second.bytes;
+  const long long n = it->second.bytes < max_bytes ? it->second.bytes : max_bytes;
+  cudaError_t e = cudaMemcpy(host_out, it->second.buf, static_cast<size_t>(n), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail(ctx, SPE_ERR_CUDA, cudaGetErrorString(e));
+  return n;
+}
+
+}  // extern "C"
+
+// accessors used by api.cu (spe_ctx is private to this translation unit)
+namespace spe {
+struct PipelineBuffers {
+  uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
+  float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
+  int has_sigma;
+};
+PipelineBuffers pipeline_buffers(spe_ctx* ctx) {
+  return PipelineBuffers{&ctx->frames_dev, &ctx->frames_cap, ctx->boxes_dev, ctx->images_dev, ctx->p_logits,
+                         ctx->p_points,    ctx->p_logsig,    ctx->p_quat,    ctx->p_tvec,     ctx->p_assign,
+                         ctx->p_status,    ctx->device,      ctx->cfg.max_batch, ctx->cfg.input_size,
+                         ctx->cfg.num_queries, ctx->cfg.has_sigma};
+}
+int set_error(spe_ctx* ctx, int code, const std::string& msg) { return fail(ctx, code, msg); }
+}  // namespace spe

@@ -1,0 +1,104 @@
+// Internal (non-ABI) declarations shared by the translation units of libspe.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace spe {
+
+enum Dtype : int { kTF32 = 0, kBF16 = 1 };  // storage: fp32 (tf32 MMA) or bf16 (bf16 MMA); fp32 accumulate
+
+inline size_t dtype_size(Dtype d) { return d == kTF32 ? 4 : 2; }
+
+// One tensor-core GEMM launch:  out[m, n] = act( scale[n] * sum_k A[m,k] * Wt[n,k] + bias[n] + residual[m', n] )
+// A is either a row-major matrix (mode 0) or an NHWC activation read through R*S shifted taps (mode 1,
+// stride-1 'same' convolution, zero padding supplied by TMA out-of-bounds fill).
+struct GemmDesc {
+  int mode = 0;
+  // mode 0: A[M, K] row-major with leading dimension lda (elements)
+  const void* A = nullptr;
+  long long M = 0;
+  int K = 0;
+  int lda = 0;
+  // mode 1: A = activation [NB, H, W, C]; K = R*S*C; M = NB*H*W
+  int NB = 0, H = 0, W = 0, C = 0, R = 1, S = 1, pad = 0;
+  // weights Wt[N, K] row-major (K contiguous)
+  const void* Wt = nullptr;
+  int N = 0;
+  // epilogue
+  const float* scale = nullptr;   // [N] or null (=1)
+  const float* bias = nullptr;    // [N] or null (=0)
+  const void* residual = nullptr; // [*, res_ld] or null
+  int res_ld = 0;
+  int res_mod = 0;                // 0: residual row = output row, >0: row % res_mod (batch-broadcast addend)
+  int res_f32 = 0;                // residual stored as fp32 even when the storage dtype is bf16
+  int relu = 0;
+  void* out = nullptr;            // [M, out_ld] storage dtype
+  int out_ld = 0;
+};
+
+// returns empty string on success, else an error message
+std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t stream);
+
+// ---- memory-bound helper kernels (elementwise.cu) ----
+std::string launch_stem_im2col(Dtype dt, const float* nchw, int NB, int Hin, int Win, void* out /*[NB*Ho*Wo,192]*/,
+                               cudaStream_t s);
+std::string launch_im2col_nhwc(Dtype dt, const void* in, int NB, int H, int W, int C, int R, int S, int stride,
+                               int pad, void* out, cudaStream_t s);
+std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s);
+std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s);
+std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
+                             int dim, void* out, cudaStream_t s);
+
+// ---- attention (attention.cu) ----
+struct AttnDesc {
+  const void* q; const void* k; const void* v;  // storage dtype; row (token) major, heads along columns
+  int ldq, ldk, ldv;                            // row strides in elements
+  long long bsq, bsk, bsv;                      // batch strides in elements
+  void* out; int ldo; long long bso;
+  int B, heads, Lq, Lk;                         // head_dim fixed at 32
+  float scale;                                  // 1/sqrt(head_dim)
+};
+std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s);
+
+// ---- heads (heads.cu) ----
+std::string launch_head_final(Dtype dt, const void* hs, const void* h2, const void* s2, long long rows,
+                              const float* Wc, const float* bc, const float* W3, const float* b3,
+                              const float* Ws3, const float* bs3, float* logits, float* points, float* logsig,
+                              cudaStream_t s);
+
+// ---- crop (crop.cu) ----
+std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long long pitch, long long frame_stride,
+                                    const int32_t* boxes, int B, int R, float* out_nchw, cudaStream_t s);
+
+// ---- pnp (pnp.cu) ----
+struct PnpDesc {
+  const float* logits;   // [B,Q,12] raw class logits
+  const float* points;   // [B,Q,2] normalised crop coordinates
+  const float* logsig;   // [B,Q,2] or null
+  const int32_t* boxes;  // [B,4] crop boxes x1,y1,x2,y2
+  int B, Q;
+  float reproj_thresh;
+  int weighted;
+  int reject;            // apply the self-assessment reject filter
+  float reject_rms_px;   // filter thresholds
+  float reject_sigma;
+  double* quat;          // [B,4] wxyz
+  double* tvec;          // [B,3]
+  int32_t* assign;       // [B,11]
+  int32_t* status;       // [B]
+  float* probs;          // [B,Q,12] or null: softmax probabilities (PostProcess 'logits')
+  float* points_px;      // [B,Q,2] or null: keypoints in original-image pixels
+  float* sigmas;         // [B,Q,2] or null: exp(logsig)
+  int32_t* inlier_mask;  // [B] bit i = label i used in the final refinement, or null
+};
+std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s);
+
+#define SPE_CUDA_TRY(expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return std::string(#expr) + ": " + cudaGetErrorString(_e);                               \
+  } while (0)
+
+}  // namespace spe

@@ -1,0 +1,191 @@
+"""Thin Python owner of one ``spe_ctx``: PyTorch supplies device memory and streams, libspe.so does the work."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SpeConfig, SpePnpParams, SpeTensorDesc, check
+
+BACKBONE_S8, BACKBONE_S16 = 0, 1
+PRECISION = {"tf32": 0, "fp32": 0, "bf16": 1}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """One context per process per GPU (include/spe.h).  All tensors passed in must live on ``device``."""
+
+    def __init__(self, *, input_size=224, num_queries=40, enc_layers=4, dec_layers=4, hidden_dim=256, nheads=8,
+                 dim_feedforward=2048, backbone="resnet50s8", precision="tf32", has_sigma=False, max_batch=64,
+                 device=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("satellite_pose_estimation_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.cfg = SpeConfig(
+            input_size=input_size, num_queries=num_queries, enc_layers=enc_layers, dec_layers=dec_layers,
+            hidden_dim=hidden_dim, nheads=nheads, dim_feedforward=dim_feedforward,
+            backbone=BACKBONE_S16 if backbone in ("resnet18", "resnet34", "resnet50") else BACKBONE_S8,
+            precision=PRECISION[precision], has_sigma=int(bool(has_sigma)), max_batch=max_batch)
+        self.precision = precision
+        self.has_sigma = bool(has_sigma)
+        self.max_batch = max_batch
+        self.Q, self.L, self.R = num_queries, dec_layers, input_size
+        self._ctx = C.c_void_p()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            check(self.lib.spe_create(C.byref(self.cfg), self.device.index, C.byref(self._ctx)))
+        self.weights_loaded = False
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.spe_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        """Reference ``state_dict`` -> device weights (BN folded, kernel layouts)."""
+        keep, descs = [], []
+        for name, t in state_dict.items():
+            if name.endswith("num_batches_tracked"):
+                continue  # dropped by FrozenBatchNorm2d._load_from_state_dict, RV/models/backbone.py:34-42
+            a = t.detach().to("cpu", torch.float32).contiguous()
+            if a.dim() > 4:
+                continue
+            keep.append(a)
+            d = SpeTensorDesc()
+            d.name = name.encode()
+            d.data = a.data_ptr()
+            d.ndim = a.dim()
+            for i, s in enumerate(a.shape):
+                d.shape[i] = s
+            descs.append(d)
+        arr = (SpeTensorDesc * len(descs))(*descs)
+        with torch.cuda.device(self.device):
+            check(self.lib.spe_load_weights(self._ctx, arr, len(descs)), self._ctx)
+        self.weights_loaded = True
+
+    # ---- stage 1 ---------------------------------------------------------------------------------------------
+    def clip_boxes(self, det_boxes):
+        det = np.ascontiguousarray(np.asarray(det_boxes, dtype=np.float64).reshape(-1, 4))
+        out = np.empty((det.shape[0], 4), dtype=np.int32)
+        check(self.lib.spe_clip_boxes(det.ctypes.data_as(C.c_void_p), det.shape[0], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def crop_resize_norm(self, frames, boxes, out=None, R=None):
+        """frames: uint8 cuda [B,H,W]; boxes: int32 cuda [B,4] -> float32 cuda [B,3,R,R]."""
+        R = R or self.R
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.dim() == 3 and frames.stride(2) == 1
+        assert boxes.dtype == torch.int32 and boxes.is_cuda and boxes.is_contiguous()
+        B, H, W = frames.shape
+        if out is None:
+            out = torch.empty((B, 3, R, R), dtype=torch.float32, device=frames.device)
+        check(self.lib.spe_crop_resize_norm(self._ctx, _ptr(frames), H, W, frames.stride(1), frames.stride(0),
+                                            _ptr(boxes), B, R, _ptr(out), _stream(frames.device)), self._ctx)
+        return out
+
+    # ---- stage 2 ---------------------------------------------------------------------------------------------
+    def forward(self, images, want_aux=False):
+        """images float32 cuda [B,3,R,R] -> dict of float32 cuda tensors (reference output layout)."""
+        assert images.is_cuda and images.dtype == torch.float32
+        images = images.contiguous()
+        B = images.shape[0]
+        if images.shape[1:] != (3, self.R, self.R):
+            raise ValueError(f"expected images [B,3,{self.R},{self.R}], got {tuple(images.shape)}")
+        dev = images.device
+        logits = torch.empty((B, self.Q, 12), dtype=torch.float32, device=dev)
+        points = torch.empty((B, self.Q, 2), dtype=torch.float32, device=dev)
+        logsig = torch.empty((B, self.Q, 2), dtype=torch.float32, device=dev) if self.has_sigma else None
+        aux_l = aux_p = None
+        if want_aux and self.L > 1:
+            aux_l = torch.empty((self.L - 1, B, self.Q, 12), dtype=torch.float32, device=dev)
+            aux_p = torch.empty((self.L - 1, B, self.Q, 2), dtype=torch.float32, device=dev)
+        check(self.lib.spe_forward(self._ctx, _ptr(images), B, _ptr(logits), _ptr(points), _ptr(logsig), _ptr(aux_l),
+                                   _ptr(aux_p), _stream(dev)), self._ctx)
+        out = {"pred_logits": logits, "pred_points": points}
+        if logsig is not None:
+            out["pred_sigmas"] = logsig
+        if aux_l is not None:
+            out["aux_outputs"] = [{"pred_logits": aux_l[i], "pred_points": aux_p[i]} for i in range(self.L - 1)]
+        return out
+
+    # ---- stage 3 ---------------------------------------------------------------------------------------------
+    def assign_pnp(self, logits, points, boxes, log_sigma=None, reproj=20.0, weighted=False, reject=False,
+                   reject_rms_px=5.0, reject_sigma_px=12.0, want_post=False):
+        """Batched PostProcess + assignment + PnP.  All inputs cuda; returns dict of cuda tensors."""
+        logits = logits.contiguous().float(); points = points.contiguous().float()
+        boxes = boxes.to(torch.int32).contiguous()
+        B, Q = logits.shape[0], logits.shape[1]
+        dev = logits.device
+        quat = torch.empty((B, 4), dtype=torch.float64, device=dev)
+        tvec = torch.empty((B, 3), dtype=torch.float64, device=dev)
+        assign = torch.empty((B, 11), dtype=torch.int32, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        inl = torch.empty((B,), dtype=torch.int32, device=dev)
+        probs = pts_px = sig = None
+        if want_post:
+            probs = torch.empty((B, Q, 12), dtype=torch.float32, device=dev)
+            pts_px = torch.empty((B, Q, 2), dtype=torch.float32, device=dev)
+            if log_sigma is not None:
+                sig = torch.empty((B, Q, 2), dtype=torch.float32, device=dev)
+        if log_sigma is not None:
+            log_sigma = log_sigma.contiguous().float()
+        p = SpePnpParams(reproj_thresh=float(reproj), weighted=int(weighted), reject=int(reject),
+                         reject_rms_px=float(reject_rms_px), reject_sigma_px=float(reject_sigma_px))
+        check(self.lib.spe_assign_pnp(self._ctx, _ptr(logits), _ptr(points), _ptr(log_sigma), _ptr(boxes), B, Q,
+                                      C.byref(p), _ptr(quat), _ptr(tvec), _ptr(assign), _ptr(status), _ptr(probs),
+                                      _ptr(pts_px), _ptr(sig), _ptr(inl), _stream(dev)), self._ctx)
+        out = {"quat": quat, "tvec": tvec, "assign": assign, "status": status, "inlier_mask": inl}
+        if want_post:
+            out["probs"], out["points_px"] = probs, pts_px
+            if sig is not None:
+                out["sigmas"] = sig
+        return out
+
+    # ---- whole path, host in / host out -----------------------------------------------------------------------
+    def run_batch_host(self, frames_host, det_boxes, reproj=20.0, weighted=False, reject=False):
+        """frames_host: uint8 (pinned) torch/numpy [B,H,W]; det_boxes: float64 [B,4] -> numpy quat/tvec/status/boxes."""
+        if isinstance(frames_host, torch.Tensor):
+            assert not frames_host.is_cuda and frames_host.dtype == torch.uint8 and frames_host.is_contiguous()
+            fptr, (B, H, W) = C.c_void_p(frames_host.data_ptr()), frames_host.shape
+        else:
+            frames_host = np.ascontiguousarray(frames_host, dtype=np.uint8)
+            fptr, (B, H, W) = frames_host.ctypes.data_as(C.c_void_p), frames_host.shape
+        det = np.ascontiguousarray(np.asarray(det_boxes, dtype=np.float64).reshape(-1, 4))
+        quat = np.empty((B, 4), dtype=np.float64); tvec = np.empty((B, 3), dtype=np.float64)
+        status = np.empty((B,), dtype=np.int32); boxes = np.empty((B, 4), dtype=np.int32)
+        p = SpePnpParams(reproj_thresh=float(reproj), weighted=int(weighted), reject=int(reject),
+                         reject_rms_px=5.0, reject_sigma_px=12.0)
+        check(self.lib.spe_run_batch_host(self._ctx, fptr, H, W, det.ctypes.data_as(C.c_void_p), B, C.byref(p),
+                                          quat.ctypes.data_as(C.c_void_p), tvec.ctypes.data_as(C.c_void_p),
+                                          status.ctypes.data_as(C.c_void_p), boxes.ctypes.data_as(C.c_void_p),
+                                          _stream(self.device)), self._ctx)
+        return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes}
+
+    # ---- bring-up -----------------------------------------------------------------------------------------------
+    def enable_taps(self, on=True):
+        check(self.lib.spe_debug_enable_taps(self._ctx, int(on)), self._ctx)
+
+    def read_tap(self, name, shape):
+        """Intermediate activation as float32 torch CPU tensor of ``shape`` (kernel layout: NHWC / [rows, C])."""
+        nbytes = self.lib.spe_debug_read_tap(self._ctx, name.encode(), None, 0)
+        if nbytes < 0:
+            check(int(nbytes), self._ctx)
+        buf = torch.empty(nbytes, dtype=torch.uint8)
+        got = self.lib.spe_debug_read_tap(self._ctx, name.encode(), C.c_void_p(buf.data_ptr()), nbytes)
+        assert got == nbytes
+        dt = torch.float32 if self.cfg.precision == 0 else torch.bfloat16
+        return buf.view(dt).float().reshape(shape)
