@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/s for crop -> keypoint-set predictor -> PnP on synthetic SPEED-shaped frames.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): Revisiting-Transformer ResNet-50 stride-8 keypoint-set predictor (224^2, 40
+queries, 4+4 layers), batch 64, fp32 storage / TF32 tensor cores, fused crop-resize, batched one-warp-per-image PnP.
+A step = one pass of the whole hot path over one batch of 64 frames.  `value` times the path with the frames already
+resident in HBM; `e2e` times the C-ABI host call (pinned host frames in, host poses out, copies inside the region).
+With `--impl reference` the same metric is measured for the reference's CPU path (oracle port: PyTorch-CPU forward +
+cv2 crop + cv2 PnP on the host cores).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64
+R = 224
+Q = 40
+WORKLOAD = ("Revisiting-Transformer ResNet-50 s8 keypoint-set predictor (224^2, Q=40, enc4/dec4, d_ff 2048), "
+            "batch 64 fp32/TF32, fused crop-resize + batched warp-per-image P3P-consensus+LM PnP, "
+            "synthetic 1920x1200 uint8 frames, real detector-box distribution")
+METRIC = "images/s crop->keypoints->PnP"
+UNIT = "images/s"
+
+
+def model_flops_per_image():
+    """Algorithmic FLOPs (2*MAC, true K, no padding) of the predictor at C*: returns (gemm_kernel_flops,
+    attention_flops).  SURVEY.md section 2c: 26.57 GFLOP/img in total."""
+    f = 0
+    f += 2 * 112 * 112 * 64 * 147                                        # stem 7x7/s2
+    inpl, H = 64, 56
+    for li, (planes, nblk) in enumerate(((64, 3), (128, 4), (256, 6))):
+        for bi in range(nblk):
+            stride = 2 if (bi == 0 and li > 0) else 1
+            Ho = H // stride
+            f += 2 * H * H * planes * inpl                               # conv1 1x1
+            f += 2 * Ho * Ho * planes * planes * 9                       # conv2 3x3 (stride on conv2)
+            f += 2 * Ho * Ho * planes * 4 * planes                       # conv3 1x1
+            if bi == 0:
+                f += 2 * Ho * Ho * planes * 4 * inpl                     # downsample 1x1
+            inpl, H = planes * 4, Ho
+    T = 28 * 28
+    f += 2 * T * 256 * 512 + 2 * T * 256 * 1024 * 9 + 2 * T * 512 * 512 * 9   # neck
+    f += 2 * T * 256 * 512                                               # input_proj
+    E, FF, L = 256, 2048, 4
+    attn = 0
+    for _ in range(L):                                                   # encoder
+        f += 2 * T * 3 * E * E + 2 * T * E * E + 2 * 2 * T * E * FF
+        attn += 2 * 2 * T * T * E
+    f += 2 * T * L * 2 * E * E                                           # decoder cross K/V of all layers
+    for _ in range(L):
+        f += 2 * Q * 3 * E * E + 2 * Q * E * E                           # self-attn proj
+        f += 2 * Q * E * E + 2 * Q * E * E                               # cross q, out
+        f += 2 * 2 * Q * E * FF
+        attn += 2 * 2 * Q * Q * E + 2 * 2 * Q * T * E
+    f += 2 * Q * 2 * E * E                                               # point MLP hidden layers (last layer only)
+    return f, attn
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        load = [c for c in sm if mx and c > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+class CpuPath:
+    """crop (cv2) -> restated reference forward (PyTorch CPU, all threads) -> PostProcess + cv2 PnP, like the
+    reference's gen_submission loop but without DataLoader worker processes.  PnP consumes synthetic keypoint sets
+    (random-init outputs collapse to one label)."""
+
+    def __init__(self, n_images, threads=None):
+        import torch
+        from oracle import model_ref, pnp_ref, synth
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        self.cfg = model_ref.ModelCfg(aux_loss=False)
+        self.sd = synth.make_state_dict(self.cfg, seed=0)
+        self.det = synth.load_detector_boxes()[:n_images]
+        self.frames = synth.make_frames(min(n_images, 8), self.det, seed=0)
+        self.preds = synth.make_predictions(n_images, seed=1)
+        self.solver = pnp_ref.SimplePoseSolver(20)
+        self.n = n_images
+        model_ref.forward(self.sd, self.cfg, torch.zeros(1, 3, R, R))     # warm-up (thread pools, allocator)
+
+    def run(self, batch):
+        """one pass over the n images; returns seconds"""
+        import torch
+        from oracle import crop_ref, model_ref, pnp_ref
+        t0 = time.perf_counter()
+        for i in range(0, self.n, batch):
+            idx = list(range(i, min(i + batch, self.n)))
+            crops = [crop_ref.crop_resize_normalize(self.frames[j % len(self.frames)], self.det[j], R)[0] for j in idx]
+            model_ref.forward(self.sd, self.cfg, torch.stack(crops))
+            res = pnp_ref.post_process(self.preds["logits"][idx], self.preds["points"][idx], self.preds["boxes"][idx])
+            for r in res:
+                pnp_ref.solve_or_zero(self.solver, r["points"], r["logits"])
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step, batch = 8, 8
+    path = CpuPath(per_step)
+    for _ in range(args.warmup):
+        path.run(batch)
+    dt = sum(path.run(batch) for _ in range(args.steps))
+    v = per_step * args.steps / dt
+    sample = f"{per_step} images per step (one batch of {batch}) through cv2 crop + PyTorch-CPU forward + cv2 PnP"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_kind": "oracle port of the reference's Python path (the Python "
+                   "reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": path.threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import model_ref, synth      # synthetic inputs + the cpu_baseline leg only
+    from satellite_pose_estimation_b200 import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    eng = Engine(input_size=R, num_queries=Q, enc_layers=4, dec_layers=4, backbone="resnet50s8", precision="tf32",
+                 max_batch=BATCH, device=local)
+    eng.load_state_dict(synth.make_state_dict(model_ref.ModelCfg(), seed=0))
+
+    # ---- synthetic inputs: each rank owns a different shard of frames / boxes (weak scaling, no collective)
+    det_all = synth.load_detector_boxes()
+    n_sets = 2                                           # 2 x 147 MB of frames: every step reads inputs > L2 (126 MB)
+    base = synth.make_frames(8, det_all[rank * 8:], seed=100 + rank)
+    frames_host, frames_dev, boxes_dev, det_sets = [], [], [], []
+    for s in range(n_sets):
+        det = det_all[(rank * n_sets + s) * BATCH:(rank * n_sets + s + 1) * BATCH]
+        fh = torch.from_numpy(np.concatenate([np.roll(base, 37 * (s * 8 + k), axis=2) for k in range(BATCH // 8)]))
+        fh = fh.pin_memory()
+        frames_host.append(fh); det_sets.append(det)
+        frames_dev.append(fh.to(dev)); boxes_dev.append(torch.from_numpy(eng.clip_boxes(det)).to(dev))
+    preds = synth.make_predictions(BATCH, Q=Q, seed=1 + rank)
+    syn_logits = torch.from_numpy(preds["logits"]).to(dev)
+    syn_points = torch.from_numpy(preds["points"]).to(dev)
+    syn_boxes = torch.from_numpy(preds["boxes"]).to(torch.int32).to(dev)
+    images = torch.empty((BATCH, 3, R, R), dtype=torch.float32, device=dev)
+
+    def step(i):
+        """one pass of the hot path over one batch, inputs resident in HBM"""
+        s = i % n_sets
+        eng.crop_resize_norm(frames_dev[s], boxes_dev[s], out=images)
+        eng.forward(images)
+        # pose stage on resident synthetic keypoint sets of the same shape (random-init weights collapse to one
+        # label, which would let the solver exit early and under-count its cost)
+        return eng.assign_pnp(syn_logits, syn_points, syn_boxes, reproj=20.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    eng.profile_collect()                                 # reset launch counters
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    _, launches = eng.profile_collect()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+    solved = int((out["status"] == 0).sum().item())
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms_total / args.steps, "quick": True,
+                              "gpu_launches_by_family": launches}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- end to end through the C ABI with host buffers (H2D of the frames + D2H of the poses inside the region)
+    eng.set_pnp_override(syn_logits, syn_points)
+    for i in range(max(args.warmup, 1)):
+        eng.run_batch_host(frames_host[i % n_sets], det_sets[i % n_sets])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        r = eng.run_batch_host(frames_host[i % n_sets], det_sets[i % n_sets])
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * args.steps / float(e2e_s.item())
+    eng.set_pnp_override(None, None)
+    h2d = frames_host[0].numel() + BATCH * 4 * 4
+    d2h = BATCH * (4 * 8 + 3 * 8 + 4)
+
+    if rank == 0:
+        # ---- per-family device time of one step (CUDA events on the launch stream) -> roofline of the GEMM kernel
+        eng.profile_enable(True)
+        eng.profile_collect()
+        prof_steps = 3
+        for i in range(prof_steps):
+            step(i)
+        torch.cuda.synchronize()
+        fam_ms, fam_n = eng.profile_collect()
+        eng.profile_enable(False)
+        gemm_flops, attn_flops = model_flops_per_image()
+        gemm_ms = fam_ms["gemm"] / prof_steps
+        achieved = gemm_flops * BATCH / (gemm_ms / 1e3) / 1e12
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            pk = json.load(open(peaks_path))
+            peak, peak_src = pk["bf16_tflops_sustained"] / 2, "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense = half of bf16)"
+        else:
+            peak, peak_src = 1400.0 / 2, "fallback 1.4 PFLOP/s sustained bf16 / 2"
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32, all convolutions and linear layers)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "launches_per_step": fam_n["gemm"] // prof_steps,
+                    "kernel_ms_per_step": gemm_ms,
+                    "family_ms_per_step": {k: v / prof_steps for k, v in fam_ms.items()},
+                    "algorithmic_gflop_per_image": {"gemm_kernel": gemm_flops / 1e9, "attention_kernel": attn_flops / 1e9}}
+
+        # ---- p50 latency at batch 1 (second half of the headline metric)
+        lat = []
+        one_f, one_b = frames_dev[0][:1], boxes_dev[0][:1]
+        for i in range(60):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.crop_resize_norm(one_f, one_b, out=images[:1])
+            eng.forward(images[:1])
+            eng.assign_pnp(syn_logits[:1], syn_points[:1], syn_boxes[:1])
+            b.record(); torch.cuda.synchronize()
+            if i >= 10:
+                lat.append(a.elapsed_time(b))
+        p50 = statistics.median(lat)
+
+        # ---- CPU baseline: bounded sample of the same workload on this box's host cores
+        n_cpu = 32
+        cpu_path = CpuPath(n_cpu)
+        cpu_v, cores = n_cpu / cpu_path.run(8), cpu_path.threads
+        cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} images (4 batches of 8) through cv2 crop + PyTorch-CPU forward + cv2 PnP"}
+
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "parallelism": f"image-sharded x{world}, no collective",
+                       "l2_policy": f"inputs larger than L2: {n_sets} alternating frame sets of {frames_dev[0].numel() / 1e6:.0f} MB",
+                       "pnp_inputs": "resident synthetic keypoint sets (random-init weights collapse to one label)",
+                       "poses_solved_per_batch": solved},
+            "p50_ms_batch1": p50,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(sum(launches.values())),
+            "gpu_launches_by_family": launches,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling runs: skip the e2e / latency / cpu_baseline legs (the JSON line is then partial)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,13 @@ int spe_debug_attention(int dtype, const void* q_dev, const void* k_dev, const v
 int spe_debug_enable_taps(spe_ctx* ctx, int enable);
 long long spe_debug_read_tap(spe_ctx* ctx, const char* name, void* host_out, long long max_bytes);
 const char* spe_global_last_error(void);
+/* launch accounting for bench.py: per kernel family {gemm, attention, elementwise, heads, crop, pnp} the number of
+ * launches since the last collect and, while enabled, their CUDA-event-timed device milliseconds */
+int spe_profile_enable(int on);
+int spe_profile_collect(double* ms_by_family /*[6]*/, long long* launches_by_family /*[6]*/);
+/* bench hook: spe_run_batch_host feeds these resident [B,Q,12] / [B,Q,2] tensors to the pose stage instead of the
+ * network outputs (random-init weights collapse to one label, which would make the solve exit early); NULL resets */
+int spe_debug_set_pnp_override(spe_ctx* ctx, const float* logits_dev, const float* points_dev);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

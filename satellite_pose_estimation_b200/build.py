@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspe.so")
-SOURCES = ["gemm_tc.cu", "attention.cu", "elementwise.cu", "heads.cu", "crop.cu", "pnp.cu", "model.cu", "api.cu"]
-HEADERS = ["spe_ptx.cuh", "spe_internal.h", os.path.join("..", "..", "include", "spe.h")]
+SOURCES = ["gemm_tc.cu", "attention.cu", "elementwise.cu", "heads.cu", "crop.cu", "pnp.cu", "model.cu", "api.cu", "profile.cu"]
+HEADERS = ["spe_ptx.cuh", "spe_internal.h", "profile.h", os.path.join("..", "..", "include", "spe.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -1,6 +1,7 @@
 // C-ABI entry points for the crop and pose stages, the host-buffer pipeline and the bring-up hooks.
 // (ctx lifetime, weights and spe_forward live in model.cu.)
 #include "spe_internal.h"
+#include "profile.h"
 #include "../../include/spe.h"
 
 #include <string>
@@ -11,9 +12,10 @@ namespace spe {
 struct PipelineBuffers {
   uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
   float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
-  int has_sigma;
+  int has_sigma; const float* ov_logits; const float* ov_points;
 };
 PipelineBuffers pipeline_buffers(spe_ctx* ctx);
+void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points);
 int set_error(spe_ctx* ctx, int code, const std::string& msg);
 }  // namespace spe
 
@@ -109,7 +111,11 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
   if (rc != SPE_OK) return rc;
   spe_pnp_params pp = *params;
   if (!sig) pp.weighted = 0;
-  rc = spe_assign_pnp(ctx, pb.logits, pb.points, sig ? pb.logsig : nullptr, pb.boxes_dev, B, pb.Q, &pp, pb.quat,
+  // bench hook: with random-init weights every query collapses to one label and the solve would exit early, so the
+  // benchmark may substitute resident synthetic keypoint sets for the pose stage (spe_debug_set_pnp_override)
+  const float* pl = pb.ov_logits ? pb.ov_logits : pb.logits;
+  const float* pp_pts = pb.ov_points ? pb.ov_points : pb.points;
+  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? pb.logsig : nullptr, pb.boxes_dev, B, pb.Q, &pp, pb.quat,
                       pb.tvec, pb.assign, pb.status, nullptr, nullptr, nullptr, nullptr, stream);
   if (rc != SPE_OK) return rc;
   e = cudaMemcpyAsync(quat_host, pb.quat, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st);
@@ -117,6 +123,23 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
   if (e == cudaSuccess) e = cudaMemcpyAsync(status_host, pb.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_run_batch_host: ") + cudaGetErrorString(e));
+  return SPE_OK;
+}
+
+int spe_profile_enable(int on) {
+  profile_enable(on != 0);
+  return SPE_OK;
+}
+
+int spe_profile_collect(double* ms_by_family, long long* launches_by_family) {
+  if (!ms_by_family || !launches_by_family) return set_error(nullptr, SPE_ERR_INVALID, "spe_profile_collect: null");
+  profile_collect(ms_by_family, launches_by_family);
+  return SPE_OK;
+}
+
+int spe_debug_set_pnp_override(spe_ctx* ctx, const float* logits_dev, const float* points_dev) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_debug_set_pnp_override: null ctx");
+  set_pnp_override(ctx, logits_dev, points_dev);
   return SPE_OK;
 }
 

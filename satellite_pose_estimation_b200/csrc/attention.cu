@@ -11,6 +11,7 @@
 // Encoder self-attention (784 x 784), decoder self-attention (Q x Q) and decoder cross-attention (Q x 784) all go
 // through this kernel; ragged tails are masked.
 #include "spe_internal.h"
+#include "profile.h"
 #include <cuda_bf16.h>
 
 namespace spe {
@@ -25,6 +26,12 @@ __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2: exp2(-inf) = 0, ~2 ulp
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
@@ -58,7 +65,7 @@ template <> __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfl
 }
 template <typename T> __device__ __forceinline__ void store2(T* p, float a, float b);
 template <> __device__ __forceinline__ void store2<float>(float* p, float a, float b) {
-  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+  *reinterpret_cast<float2*>(p) = make_float2(to_tf32(a), to_tf32(b));  // consumed by a kind::tf32 GEMM
 }
 template <> __device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
@@ -144,13 +151,13 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every tile holds >= 1 valid key
-    const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    const float a0 = fast_exp2(m0 - mn0), a1 = fast_exp2(m1 - mn1);
     m0 = mn0; m1 = mn1;
     float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
     for (int j = 0; j < KT / 8; ++j) {
-      s[j][0] = exp2f(s[j][0] - mn0); s[j][1] = exp2f(s[j][1] - mn0);
-      s[j][2] = exp2f(s[j][2] - mn1); s[j][3] = exp2f(s[j][3] - mn1);
+      s[j][0] = fast_exp2(s[j][0] - mn0); s[j][1] = fast_exp2(s[j][1] - mn0);
+      s[j][2] = fast_exp2(s[j][2] - mn1); s[j][3] = fast_exp2(s[j][3] - mn1);
       ps0 += s[j][0] + s[j][1];
       ps1 += s[j][2] + s[j][3];
     }
@@ -193,6 +200,7 @@ std::string launch_attn_t(const AttnDesc& d, cudaStream_t s) {
   const T* k = reinterpret_cast<const T*>(d.k);
   const T* v = reinterpret_cast<const T*>(d.v);
   T* o = reinterpret_cast<T*>(d.out);
+  ProfScope ps(kFamAttention, s);
   if (d.Lk % 112 == 0) {
     attention_kernel<T, 112><<<grid, 128, 0, s>>>(q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq, d.bsk, d.bsv,
                                                  d.bso, d.Lq, d.Lk, sl2);

@@ -13,6 +13,7 @@
 // The gray frame is read once per tap through the read-only path; the three output channels are the same
 // uint8 value pushed through three per-channel affine maps, exactly like the reference's replicated RGB image.
 #include "spe_internal.h"
+#include "profile.h"
 
 namespace spe {
 
@@ -100,6 +101,7 @@ std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long lo
   const int tx = R >= 256 ? 256 : ((R + 31) / 32) * 32;
   dim3 block(tx);
   dim3 grid((R + tx - 1) / tx, R, B);
+  ProfScope ps(kFamCrop, s);
   crop_resize_norm_kernel<<<grid, block, 0, s>>>(frames, H, W, pitch, frame_stride, boxes, R, out_nchw);
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

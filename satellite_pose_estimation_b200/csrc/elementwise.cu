@@ -8,18 +8,28 @@
 //                    (reference: RV/models/backbone.py:125, :140)
 //   layernorm        nn.LayerNorm(256), eps 1e-5, fp32 statistics (RV/models/transformer.py:159-166)
 #include "spe_internal.h"
+#include "profile.h"
 #include <cuda_bf16.h>
 
 namespace spe {
 
 namespace {
 
-template <typename T> struct Vec;  // 16-byte vector of T
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// 16-byte vector of T.  fp32 storage feeds kind::tf32 MMAs (10-bit mantissa): values are rounded to nearest on the
+// way in, so the tensor core sees them exactly (idempotent for already-rounded data such as copies and max-pools).
+template <typename T> struct Vec;
 template <> struct Vec<float> {
   static constexpr int N = 4;
   float4 v;
   __device__ __forceinline__ float get(int i) const { return reinterpret_cast<const float*>(&v)[i]; }
-  __device__ __forceinline__ void set(int i, float x) { reinterpret_cast<float*>(&v)[i] = x; }
+  __device__ __forceinline__ void set(int i, float x) { reinterpret_cast<float*>(&v)[i] = rna_tf32(x); }
+  __device__ __forceinline__ void set_exact(int i, float x) { reinterpret_cast<float*>(&v)[i] = x; }
 };
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
@@ -30,6 +40,7 @@ template <> struct Vec<__nv_bfloat16> {
   __device__ __forceinline__ void set(int i, float x) {
     reinterpret_cast<__nv_bfloat16*>(&v)[i] = __float2bfloat16_rn(x);
   }
+  __device__ __forceinline__ void set_exact(int i, float x) { set(i, x); }
 };
 template <typename T> __device__ __forceinline__ Vec<T> vload(const T* p) {
   Vec<T> r;
@@ -187,7 +198,7 @@ upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, long long total
 template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    long long rows, T* __restrict__ out) {
+                    long long rows, T* __restrict__ out, int exact) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -217,7 +228,10 @@ layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, c
     const int c = (i * 32 + lane) * VN;
     Vec<T> r;
 #pragma unroll
-    for (int e = 0; e < VN; ++e) r.set(e, (x[i * VN + e] - mean) * rstd * gamma[c + e] + beta[c + e]);
+    for (int e = 0; e < VN; ++e) {
+      const float y = (x[i * VN + e] - mean) * rstd * gamma[c + e] + beta[c + e];
+      if (exact) r.set_exact(e, y); else r.set(e, y);
+    }
     vstore(out + row * 256 + c, r);
   }
 }
@@ -232,6 +246,7 @@ inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>(
 
 std::string launch_stem_im2col(Dtype dt, const float* nchw, int NB, int Hin, int Win, void* out, cudaStream_t s) {
   const int Ho = (Hin + 6 - 7) / 2 + 1, Wo = (Win + 6 - 7) / 2 + 1;
+  ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     const long long total = static_cast<long long>(NB) * Ho * Wo * (kStemKPad / Vec<T>::N);
     stem_im2col_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(nchw, Hin, Win, Ho, Wo, total,
@@ -244,6 +259,7 @@ std::string launch_stem_im2col(Dtype dt, const float* nchw, int NB, int Hin, int
 std::string launch_im2col_nhwc(Dtype dt, const void* in, int NB, int H, int W, int C, int R, int S, int stride,
                                int pad, void* out, cudaStream_t s) {
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     if (C % Vec<T>::N) return "im2col: C must be a multiple of the 16-byte vector";
     const long long total = static_cast<long long>(NB) * Ho * Wo * R * S * (C / Vec<T>::N);
@@ -257,6 +273,7 @@ std::string launch_im2col_nhwc(Dtype dt, const void* in, int NB, int H, int W, i
 
 std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     const long long total = static_cast<long long>(NB) * Ho * Wo * (C / Vec<T>::N);
     maxpool3x3s2_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C, Ho, Wo,
@@ -267,6 +284,7 @@ std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, 
 }
 
 std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s) {
+  ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     const long long total = static_cast<long long>(NB) * 4 * H * W * (C / Vec<T>::N);
     upsample2x_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C, total,
@@ -277,12 +295,13 @@ std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, in
 }
 
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
-                             int dim, void* out, cudaStream_t s) {
+                             int dim, void* out, cudaStream_t s, int exact) {
   if (dim != 256) return "layernorm: only hidden_dim 256 is built";
   if (rows <= 0) return "";
+  ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     layernorm256_kernel<T><<<blocks_for(rows, 8), 256, 0, s>>>(reinterpret_cast<const T*>(in), gamma, beta, rows,
-                                                               reinterpret_cast<T*>(out));
+                                                               reinterpret_cast<T*>(out), exact);
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

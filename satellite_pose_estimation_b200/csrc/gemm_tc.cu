@@ -16,6 +16,7 @@
 // {BK channels, W, hrows, 1 image} shifted by (s - pad, r - pad); TMA zero-fills outside the image, which is
 // exactly the convolution's zero padding, so no im2col buffer is ever materialised.
 #include "spe_internal.h"
+#include "profile.h"
 #include "spe_ptx.cuh"
 
 #include <mutex>
@@ -67,6 +68,11 @@ struct GemmKParams {
 };
 
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 template <typename T, int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -263,10 +269,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
           if (sizeof(T) == 4) {
+            // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round-to-nearest here so the
+            // next layer's products are exact and the error stays unbiased (truncation drifts by ~2^-11 per layer)
             float* op = reinterpret_cast<float*>(p.out) + grow * p.out_ld + ncol;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              *reinterpret_cast<float4*>(op + j) =
+                  make_float4(rna_tf32(f[j]), rna_tf32(f[j + 1]), rna_tf32(f[j + 2]), rna_tf32(f[j + 3]));
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_ld + ncol;
 #pragma unroll
@@ -353,7 +362,10 @@ std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap
   }
   const int tiles = kp.num_m_tiles * kp.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+  {
+    ProfScope ps(kFamGemm, stream);
+    kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+  }
   SPE_CUDA_TRY(cudaGetLastError());
   (void)d;
   return "";

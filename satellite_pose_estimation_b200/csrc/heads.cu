@@ -6,6 +6,7 @@
 //                                                  (SA/src/zoo/rtdetr/rtdetr_decoder.py:295-297, :367)
 // The two hidden 256 -> 256 layers of each MLP run on the tensor-core GEMM; this kernel is one warp per query row.
 #include "spe_internal.h"
+#include "profile.h"
 #include <cuda_bf16.h>
 
 namespace spe {
@@ -75,6 +76,7 @@ std::string launch_head_final(Dtype dt, const void* hs, const void* h2, const vo
                               cudaStream_t s) {
   if (rows <= 0) return "";
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  ProfScope ps(kFamHeads, s);
   if (dt == kTF32) {
     head_final_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(hs),
                                                      reinterpret_cast<const float*>(h2),

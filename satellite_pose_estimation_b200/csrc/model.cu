@@ -143,6 +143,7 @@ struct spe_ctx {
   float *p_logits = nullptr, *p_points = nullptr, *p_logsig = nullptr;
   double *p_quat = nullptr, *p_tvec = nullptr;
   int32_t *p_assign = nullptr, *p_status = nullptr;
+  const float *ov_logits = nullptr, *ov_points = nullptr;   // bench hook, see spe_debug_set_pnp_override
 
   // debug taps
   bool taps_enabled = false;
@@ -586,8 +587,8 @@ struct Fwd {
     a.scale = 1.0f / sqrtf(32.0f);
     return launch_attention(dt, a, st);
   }
-  std::string ln(const void* in, const float* g, const float* b, long long rows, void* out) {
-    return launch_layernorm(dt, in, g, b, rows, 256, out, st);
+  std::string ln(const void* in, const float* g, const float* b, long long rows, void* out, int exact = 0) {
+    return launch_layernorm(dt, in, g, b, rows, 256, out, st, exact);
   }
 };
 
@@ -698,7 +699,7 @@ std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits
     TRY_S(f.gemm(ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
     TRY_S(f.gemm(ctx->DHID, MQ, L.ff2, ctx->TGT2, 256, false, ctx->TGT, 256));
     TRY_S(f.ln(ctx->TGT2, L.n3g, L.n3b, MQ, ctx->TGT));
-    TRY_S(f.ln(ctx->TGT, ctx->dn_g, ctx->dn_b, MQ, f.col(ctx->HS, static_cast<long long>(i) * MQ * 256)));
+    TRY_S(f.ln(ctx->TGT, ctx->dn_g, ctx->dn_b, MQ, f.col(ctx->HS, static_cast<long long>(i) * MQ * 256), 1));
   }
   TRY_S(f.tap("hs", ctx->HS, static_cast<long long>(LD) * MQ * 256));
 
@@ -858,13 +859,17 @@ namespace spe {
 struct PipelineBuffers {
   uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
   float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
-  int has_sigma;
+  int has_sigma; const float* ov_logits; const float* ov_points;
 };
 PipelineBuffers pipeline_buffers(spe_ctx* ctx) {
   return PipelineBuffers{&ctx->frames_dev, &ctx->frames_cap, ctx->boxes_dev, ctx->images_dev, ctx->p_logits,
                          ctx->p_points,    ctx->p_logsig,    ctx->p_quat,    ctx->p_tvec,     ctx->p_assign,
                          ctx->p_status,    ctx->device,      ctx->cfg.max_batch, ctx->cfg.input_size,
-                         ctx->cfg.num_queries, ctx->cfg.has_sigma};
+                         ctx->cfg.num_queries, ctx->cfg.has_sigma, ctx->ov_logits, ctx->ov_points};
+}
+void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points) {
+  ctx->ov_logits = logits;
+  ctx->ov_points = points;
 }
 int set_error(spe_ctx* ctx, int code, const std::string& msg) { return fail(ctx, code, msg); }
 }  // namespace spe

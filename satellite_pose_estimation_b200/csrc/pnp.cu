@@ -17,6 +17,7 @@
 // warp-shuffle reductions for the normal equations, every lane solving the 6x6 system redundantly.
 // Failures reproduce the reference's observable contract: < 4 correspondences / no valid pose -> zero pose + status.
 #include "spe_internal.h"
+#include "profile.h"
 #include <math.h>
 
 namespace spe {
@@ -305,43 +306,68 @@ __device__ double pose_cost(const double (&R)[9], const double (&t)[3], const Po
 }
 
 __device__ bool lm_refine(double (&R)[9], double (&t)[3], const PointObs& o, double au, double cu, double av,
-                          double cv, double huber) {
+                          double cv, double huber, int n, double* sJ /*[16][14]*/, double* sA /*[27]*/) {
+  const int lane = threadIdx.x & 31;
   bool zok;
   double cost = pose_cost(R, t, o, au, cu, av, cv, huber, zok);
   if (!zok || !isfinite(cost)) return false;
   double lam = 1e-3;
-  for (int iter = 0; iter < 30; ++iter) {
-    // normal equations: lanes = points, 27 warp reductions
-    double Ju[6] = {0, 0, 0, 0, 0, 0}, Jv[6] = {0, 0, 0, 0, 0, 0}, ru = 0.0, rv = 0.0, rw = 0.0;
-    if (o.active) {
-      const double Y0 = R[0] * o.X[0] + R[1] * o.X[1] + R[2] * o.X[2];
-      const double Y1 = R[3] * o.X[0] + R[4] * o.X[1] + R[5] * o.X[2];
-      const double Y2 = R[6] * o.X[0] + R[7] * o.X[1] + R[8] * o.X[2];
-      const double x = Y0 + t[0], y = Y1 + t[1], z = Y2 + t[2];
-      const double iz = 1.0 / z;
-      ru = o.wu * (au * x * iz + cu - o.mu);
-      rv = o.wv * (av * y * iz + cv - o.mv);
-      const double s = ru * ru + rv * rv;
-      rw = (huber > 0.0 && s > huber * huber) ? huber / sqrt(s) : 1.0;  // rho'(s)
-      // d(point)/d(omega) = -[Y]x ; d(point)/dt = I ; du/d(point) = wu*au*[1/z, 0, -x/z^2]
-      const double gu[3] = {o.wu * au * iz, 0.0, -o.wu * au * x * iz * iz};
-      const double gv[3] = {0.0, o.wv * av * iz, -o.wv * av * y * iz * iz};
-      // g * (-[Y]x) = -(g x Y)^T ... (row vector times skew): (g^T [Y]x)_j ; use -[Y]x = [[0,Y2,-Y1],[-Y2,0,Y0],[Y1,-Y0,0]]
-      Ju[0] = gu[1] * (-Y2) + gu[2] * Y1;  Ju[1] = gu[0] * Y2 + gu[2] * (-Y0);  Ju[2] = gu[0] * (-Y1) + gu[1] * Y0;
-      Jv[0] = gv[1] * (-Y2) + gv[2] * Y1;  Jv[1] = gv[0] * Y2 + gv[2] * (-Y0);  Jv[2] = gv[0] * (-Y1) + gv[1] * Y0;
-      Ju[3] = gu[0]; Ju[4] = gu[1]; Ju[5] = gu[2];
-      Jv[3] = gv[0]; Jv[4] = gv[1]; Jv[5] = gv[2];
-    }
-    double Ap[21], g[6];
+  // entry e of the packed normal equations handled by lane e: e < 21 -> A(i,j) upper triangle, 21..26 -> g(e-21)
+  int ei = 0, ej = 0;
+  if (lane < 21) {
     int idx = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) { if (idx == lane) { ei = i; ej = j; } ++idx; }
+  } else {
+    ei = lane - 21;
+  }
+  for (int iter = 0; iter < 20; ++iter) {
+    // lanes = points: residuals and Jacobian rows, pre-scaled by sqrt(rho') so that A = J^T J, g = J^T r
+    if (lane < 16) {
+      double Ju[6] = {0, 0, 0, 0, 0, 0}, Jv[6] = {0, 0, 0, 0, 0, 0}, ru = 0.0, rv = 0.0;
+      if (o.active) {
+        const double Y0 = R[0] * o.X[0] + R[1] * o.X[1] + R[2] * o.X[2];
+        const double Y1 = R[3] * o.X[0] + R[4] * o.X[1] + R[5] * o.X[2];
+        const double Y2 = R[6] * o.X[0] + R[7] * o.X[1] + R[8] * o.X[2];
+        const double x = Y0 + t[0], y = Y1 + t[1], z = Y2 + t[2];
+        const double iz = 1.0 / z;
+        ru = o.wu * (au * x * iz + cu - o.mu);
+        rv = o.wv * (av * y * iz + cv - o.mv);
+        const double s = ru * ru + rv * rv;
+        const double sw = (huber > 0.0 && s > huber * huber) ? sqrt(huber / sqrt(s)) : 1.0;  // sqrt(rho'(s))
+        // d(point)/d(omega) = -[Y]x ; d(point)/dt = I ; du/d(point) = wu*au*[1/z, 0, -x/z^2]
+        const double gu0 = sw * o.wu * au * iz, gu2 = -sw * o.wu * au * x * iz * iz;
+        const double gv1 = sw * o.wv * av * iz, gv2 = -sw * o.wv * av * y * iz * iz;
+        Ju[0] = gu2 * Y1;              Ju[1] = gu0 * Y2 - gu2 * Y0;   Ju[2] = -gu0 * Y1;
+        Jv[0] = -gv1 * Y2 + gv2 * Y1;  Jv[1] = -gv2 * Y0;             Jv[2] = gv1 * Y0;
+        Ju[3] = gu0; Ju[5] = gu2;
+        Jv[4] = gv1; Jv[5] = gv2;
+        ru *= sw; rv *= sw;
+      }
+      double* row = sJ + lane * 14;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-      for (int j = i; j < 6; ++j) Ap[idx++] = wsum(rw * (Ju[i] * Ju[j] + Jv[i] * Jv[j]));
-      g[i] = wsum(rw * (Ju[i] * ru + Jv[i] * rv));
+      for (int i = 0; i < 6; ++i) { row[i] = Ju[i]; row[6 + i] = Jv[i]; }
+      row[12] = ru; row[13] = rv;
     }
+    __syncwarp();
+    if (lane < 27) {
+      double acc = 0.0;
+      for (int pnt = 0; pnt < n; ++pnt) {
+        const double* row = sJ + pnt * 14;
+        if (lane < 21) acc += row[ei] * row[ej] + row[6 + ei] * row[6 + ej];
+        else acc += row[ei] * row[12] + row[6 + ei] * row[13];
+      }
+      sA[lane] = acc;
+    }
+    __syncwarp();
+    double Ap[21], g[6];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Ap[i] = sA[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g[i] = sA[21 + i];
+    __syncwarp();
     bool accepted = false, converged = false;
-    for (int tries = 0; tries < 12; ++tries) {
+    for (int tries = 0; tries < 8; ++tries) {
       double d[6];
       if (solve6(Ap, g, lam, d)) {
         double Rn[9], tn[3] = {t[0] + d[3], t[1] + d[4], t[2] + d[5]};
@@ -350,7 +376,7 @@ __device__ bool lm_refine(double (&R)[9], double (&t)[3], const PointObs& o, dou
         const double cn = pose_cost(Rn, tn, o, au, cu, av, cv, huber, zk);
         if (zk && cn <= cost) {
           const double dn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
-          converged = (cost - cn) <= 1e-16 * fmax(cost, 1e-300) || dn < 1e-14;
+          converged = (cost - cn) <= 1e-13 * fmax(cost, 1e-300) || dn < 1e-11;
 #pragma unroll
           for (int i = 0; i < 9; ++i) R[i] = Rn[i];
           t[0] = tn[0]; t[1] = tn[1]; t[2] = tn[2];
@@ -387,15 +413,25 @@ __device__ void rot_to_quat(const double (&R)[9], double (&q)[4]) {
   q[0] *= sg; q[1] *= sg; q[2] *= sg; q[3] *= sg;
 }
 
-__global__ void __launch_bounds__(32)
+constexpr int kPnpThreads = 128;
+
+__global__ void __launch_bounds__(kPnpThreads)
 assign_pnp_kernel(const PnpDesc d) {
   const int img = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int Q = d.Q;
+  __shared__ int s_n;
   __shared__ int s_lab[11];
   __shared__ double s_uv[22];
   __shared__ double s_sig[22];
   __shared__ double s_bear[33];
+  __shared__ int s_bcnt[4];
+  __shared__ double s_berr[4];
+  __shared__ unsigned s_bmask[4];
+  __shared__ double s_bpose[4][12];
+  __shared__ double s_J[16 * 14];
+  __shared__ double s_A[27];
 
   const float* lg = d.logits + static_cast<long long>(img) * Q * 12;
   const float* pt = d.points + static_cast<long long>(img) * Q * 2;
@@ -403,102 +439,99 @@ assign_pnp_kernel(const PnpDesc d) {
   const float bw = static_cast<float>(d.boxes[img * 4 + 2] - bx1);
   const float bh = static_cast<float>(d.boxes[img * 4 + 3] - by1);
 
-  // ---- PostProcess + find_index, one query per lane per pass; per-label running best (score desc, query asc)
-  float best_s[11];
-  int best_q[11];
+  if (warp == 0) {
+    // ---- PostProcess + find_index, one query per lane per pass; per-label running best (score desc, query asc)
+    float best_s[11];
+    int best_q[11];
 #pragma unroll
-  for (int l = 0; l < 11; ++l) { best_s[l] = -1.f; best_q[l] = 0x7fffffff; }
-  for (int q = lane; q < Q; q += 32) {
-    float x[12];
-    float mx = -INFINITY;
-    int am = 0;
+    for (int l = 0; l < 11; ++l) { best_s[l] = -1.f; best_q[l] = 0x7fffffff; }
+    for (int q = lane; q < Q; q += 32) {
+      float x[12];
+      float mx = -INFINITY;
+      int am = 0;
 #pragma unroll
-    for (int c = 0; c < 12; ++c) {
-      x[c] = lg[q * 12 + c];
-      if (x[c] > mx) { mx = x[c]; am = c; }  // first maximum, like np.argmax
-    }
-    float sum = 0.f;
+      for (int c = 0; c < 12; ++c) {
+        x[c] = lg[q * 12 + c];
+        if (x[c] > mx) { mx = x[c]; am = c; }  // first maximum, like np.argmax
+      }
+      float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < 12; ++c) { x[c] = expf(x[c] - mx); sum += x[c]; }
-    const float inv = 1.0f / sum;
-    const float score = x[am] * inv;
-    if (d.probs) {
+      for (int c = 0; c < 12; ++c) { x[c] = expf(x[c] - mx); sum += x[c]; }
+      const float inv = 1.0f / sum;
+      const float score = x[am] * inv;
+      const long long gq = static_cast<long long>(img) * Q + q;
+      if (d.probs) {
 #pragma unroll
-      for (int c = 0; c < 12; ++c) d.probs[(static_cast<long long>(img) * Q + q) * 12 + c] = x[c] * inv;
-    }
-    // fp32 multiply then add, unfused, exactly like `pt[:, 0] * width + x1` on float32 tensors
-    const float px = __fadd_rn(__fmul_rn(pt[q * 2 + 0], bw), static_cast<float>(bx1));
-    const float py = __fadd_rn(__fmul_rn(pt[q * 2 + 1], bh), static_cast<float>(by1));
-    if (d.points_px) {
-      d.points_px[(static_cast<long long>(img) * Q + q) * 2 + 0] = px;
-      d.points_px[(static_cast<long long>(img) * Q + q) * 2 + 1] = py;
-    }
-    if (d.sigmas && d.logsig) {
-      d.sigmas[(static_cast<long long>(img) * Q + q) * 2 + 0] = expf(d.logsig[(static_cast<long long>(img) * Q + q) * 2 + 0]);
-      d.sigmas[(static_cast<long long>(img) * Q + q) * 2 + 1] = expf(d.logsig[(static_cast<long long>(img) * Q + q) * 2 + 1]);
-    }
-    if (am != 11) {
+        for (int c = 0; c < 12; ++c) d.probs[gq * 12 + c] = x[c] * inv;
+      }
+      if (d.points_px) {
+        // fp32 multiply then add, unfused, exactly like `pt[:, 0] * width + x1` on float32 tensors
+        d.points_px[gq * 2 + 0] = __fadd_rn(__fmul_rn(pt[q * 2 + 0], bw), static_cast<float>(bx1));
+        d.points_px[gq * 2 + 1] = __fadd_rn(__fmul_rn(pt[q * 2 + 1], bh), static_cast<float>(by1));
+      }
+      if (d.sigmas && d.logsig) {
+        d.sigmas[gq * 2 + 0] = expf(d.logsig[gq * 2 + 0]);
+        d.sigmas[gq * 2 + 1] = expf(d.logsig[gq * 2 + 1]);
+      }
+      if (am != 11) {
 #pragma unroll
-      for (int l = 0; l < 11; ++l)
-        if (l == am && score > best_s[l]) { best_s[l] = score; best_q[l] = q; }  // q ascending: first max kept
-    }
-  }
-  // warp arg-max per label: higher score wins, ties go to the lower query index
-  int n = 0;
-#pragma unroll
-  for (int l = 0; l < 11; ++l) {
-    float s = best_s[l];
-    int qi = best_q[l];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float s2 = __shfl_xor_sync(FULL, s, o);
-      const int q2 = __shfl_xor_sync(FULL, qi, o);
-      if (s2 > s || (s2 == s && q2 < qi)) { s = s2; qi = q2; }
-    }
-    const bool present = s >= 0.f;
-    if (lane == 0) {
-      d.assign[img * 11 + l] = present ? qi : -1;
-      if (present) {
-        s_lab[n] = l;
-        const float px = __fadd_rn(__fmul_rn(pt[qi * 2 + 0], bw), static_cast<float>(bx1));
-        const float py = __fadd_rn(__fmul_rn(pt[qi * 2 + 1], bh), static_cast<float>(by1));
-        s_uv[2 * n] = static_cast<double>(px);
-        s_uv[2 * n + 1] = static_cast<double>(py);
-        if (d.logsig) {
-          s_sig[2 * n] = static_cast<double>(expf(d.logsig[(static_cast<long long>(img) * Q + qi) * 2 + 0]));
-          s_sig[2 * n + 1] = static_cast<double>(expf(d.logsig[(static_cast<long long>(img) * Q + qi) * 2 + 1]));
-        } else {
-          s_sig[2 * n] = 1.0; s_sig[2 * n + 1] = 1.0;
-        }
+        for (int l = 0; l < 11; ++l)
+          if (l == am && score > best_s[l]) { best_s[l] = score; best_q[l] = q; }  // q ascending: first max kept
       }
     }
-    if (present) ++n;
+    // warp arg-max per label: higher score wins, ties go to the lower query index
+    int n = 0;
+#pragma unroll
+    for (int l = 0; l < 11; ++l) {
+      float sc = best_s[l];
+      int qi = best_q[l];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(FULL, sc, o);
+        const int q2 = __shfl_xor_sync(FULL, qi, o);
+        if (s2 > sc || (s2 == sc && q2 < qi)) { sc = s2; qi = q2; }
+      }
+      const bool present = sc >= 0.f;
+      if (lane == 0) {
+        d.assign[img * 11 + l] = present ? qi : -1;
+        if (present) {
+          s_lab[n] = l;
+          const float px = __fadd_rn(__fmul_rn(pt[qi * 2 + 0], bw), static_cast<float>(bx1));
+          const float py = __fadd_rn(__fmul_rn(pt[qi * 2 + 1], bh), static_cast<float>(by1));
+          s_uv[2 * n] = static_cast<double>(px);
+          s_uv[2 * n + 1] = static_cast<double>(py);
+          // bearing of the correspondence
+          const double bx = (static_cast<double>(px) - kCx) / kFx, by = (static_cast<double>(py) - kCy) / kFy;
+          const double inv = 1.0 / sqrt(bx * bx + by * by + 1.0);
+          s_bear[3 * n] = bx * inv; s_bear[3 * n + 1] = by * inv; s_bear[3 * n + 2] = inv;
+          if (d.logsig) {
+            s_sig[2 * n] = static_cast<double>(expf(d.logsig[(static_cast<long long>(img) * Q + qi) * 2 + 0]));
+            s_sig[2 * n + 1] = static_cast<double>(expf(d.logsig[(static_cast<long long>(img) * Q + qi) * 2 + 1]));
+          } else {
+            s_sig[2 * n] = 1.0; s_sig[2 * n + 1] = 1.0;
+          }
+        }
+      }
+      if (present) ++n;
+    }
+    if (lane == 0) s_n = n;
   }
-  __syncwarp();
+  __syncthreads();
+  const int n = s_n;
 
   double quat[4] = {0, 0, 0, 0}, tv[3] = {0, 0, 0};
   unsigned inl_mask = 0u;
-
   auto write_out = [&](int st) {
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
       for (int i = 0; i < 4; ++i) d.quat[img * 4 + i] = quat[i];
       for (int i = 0; i < 3; ++i) d.tvec[img * 3 + i] = tv[i];
       d.status[img] = st;
       if (d.inlier_mask) d.inlier_mask[img] = static_cast<int32_t>(inl_mask);
     }
   };
-
   if (n < 4) { write_out(1); return; }  // cv2.solvePnPRansac raises -> caller records the zero pose
 
-  // ---- bearings
-  if (lane < n) {
-    const double bx = (s_uv[2 * lane] - kCx) / kFx, by = (s_uv[2 * lane + 1] - kCy) / kFy;
-    const double inv = 1.0 / sqrt(bx * bx + by * by + 1.0);
-    s_bear[3 * lane] = bx * inv; s_bear[3 * lane + 1] = by * inv; s_bear[3 * lane + 2] = inv;
-  }
-  __syncwarp();
-
-  // ---- exhaustive minimal-sample consensus: triple #c goes to lane c % 32
+  // ---- exhaustive minimal-sample consensus: triple #c goes to thread c % 128
   Hyp best;
   best.cnt = 0; best.err = 1e300; best.mask = 0u;
 #pragma unroll
@@ -509,9 +542,10 @@ assign_pnp_kernel(const PnpDesc d) {
   for (int i0 = 0; i0 < n - 2; ++i0)
     for (int i1 = i0 + 1; i1 < n - 1; ++i1)
       for (int i2 = i1 + 1; i2 < n; ++i2, ++c)
-        if ((c & 31) == lane) p3p_consensus(i0, i1, i2, n, s_lab, s_uv, s_bear, thr2, best);
+        if ((c & (kPnpThreads - 1)) == static_cast<int>(threadIdx.x))
+          p3p_consensus(i0, i1, i2, n, s_lab, s_uv, s_bear, thr2, best);
   __syncwarp();
-  // warp arg-best: more inliers, then lower error, then lower lane
+  // arg-best: more inliers, then lower error, then lower thread index
   int bl = lane, bc = best.cnt;
   double be = best.err;
 #pragma unroll
@@ -521,13 +555,25 @@ assign_pnp_kernel(const PnpDesc d) {
     const int l2 = __shfl_xor_sync(FULL, bl, o);
     if (c2 > bc || (c2 == bc && (e2 < be || (e2 == be && l2 < bl)))) { bc = c2; be = e2; bl = l2; }
   }
-  if (bc < 4) { write_out(1); return; }  // no hypothesis supported by >= 4 correspondences
+  if (lane == bl) {
+    s_bcnt[warp] = best.cnt; s_berr[warp] = best.err; s_bmask[warp] = best.mask;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_bpose[warp][i] = best.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s_bpose[warp][9 + i] = best.t[i];
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  int bw_ = 0;
+  for (int w = 1; w < 4; ++w)
+    if (s_bcnt[w] > s_bcnt[bw_] || (s_bcnt[w] == s_bcnt[bw_] && s_berr[w] < s_berr[bw_])) bw_ = w;
+  if (s_bcnt[bw_] < 4) { write_out(1); return; }  // no hypothesis supported by >= 4 correspondences
   double R[9], t[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = __shfl_sync(FULL, best.R[i], bl);
+  for (int i = 0; i < 9; ++i) R[i] = s_bpose[bw_][i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = __shfl_sync(FULL, best.t[i], bl);
-  inl_mask = __shfl_sync(FULL, best.mask, bl);
+  for (int i = 0; i < 3; ++i) t[i] = s_bpose[bw_][9 + i];
+  inl_mask = s_bmask[bw_];
 
   // ---- refinement on the inliers
   PointObs o;
@@ -545,10 +591,10 @@ assign_pnp_kernel(const PnpDesc d) {
     const double su = wsum(wu), sv = wsum(wv);
     o.wu = wu / su; o.wv = wv / sv;
     if (lane < n) { o.mu = (s_uv[2 * lane] - kCx) / kFx; o.mv = (s_uv[2 * lane + 1] - kCy) / kFy; }
-    ok = lm_refine(R, t, o, 1.0, 0.0, 1.0, 0.0, 0.005);
+    ok = lm_refine(R, t, o, 1.0, 0.0, 1.0, 0.0, 0.005, n, s_J, s_A);
   } else {
     if (lane < n) { o.mu = s_uv[2 * lane]; o.mv = s_uv[2 * lane + 1]; }
-    ok = lm_refine(R, t, o, kFx, kCx, kFy, kCy, 0.0);
+    ok = lm_refine(R, t, o, kFx, kCx, kFy, kCy, 0.0, n, s_J, s_A);
   }
   if (!ok) { inl_mask = 0u; write_out(2); return; }
 
@@ -581,7 +627,8 @@ assign_pnp_kernel(const PnpDesc d) {
 std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s) {
   if (d.B <= 0) return "";
   if (d.Q <= 0 || d.Q > 4096) return "assign_pnp: bad query count";
-  assign_pnp_kernel<<<d.B, 32, 0, s>>>(d);
+  ProfScope ps(kFamPnp, s);
+  assign_pnp_kernel<<<d.B, kPnpThreads, 0, s>>>(d);
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
 }

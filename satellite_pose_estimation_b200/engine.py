@@ -175,6 +175,24 @@ class Engine:
                                           _stream(self.device)), self._ctx)
         return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes}
 
+    # ---- measurement hooks (bench.py) ------------------------------------------------------------------------------
+    FAMILIES = ("gemm", "attention", "elementwise", "heads", "crop", "pnp")
+
+    def profile_enable(self, on=True):
+        check(self.lib.spe_profile_enable(int(on)))
+
+    def profile_collect(self):
+        """-> ({family: event-timed ms}, {family: launches}) since the previous collect."""
+        ms = (C.c_double * 6)()
+        n = (C.c_longlong * 6)()
+        check(self.lib.spe_profile_collect(ms, n))
+        return dict(zip(self.FAMILIES, list(ms))), dict(zip(self.FAMILIES, list(n)))
+
+    def set_pnp_override(self, logits=None, points=None):
+        """Bench hook: run_batch_host feeds these resident tensors to the pose stage (None resets)."""
+        self._override = (logits, points)   # keep alive
+        check(self.lib.spe_debug_set_pnp_override(self._ctx, _ptr(logits), _ptr(points)), self._ctx)
+
     # ---- bring-up -----------------------------------------------------------------------------------------------
     def enable_taps(self, on=True):
         check(self.lib.spe_debug_enable_taps(self._ctx, int(on)), self._ctx)

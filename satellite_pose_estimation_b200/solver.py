@@ -1,0 +1,78 @@
+"""Host-side mirror of the reference's pose-solver interface (RV/utils/speed_eval.py:21-22, :143-242;
+SA/utils/speed_eval.py:27-28, :322-420).
+
+``build_solver(args)`` returns a callable with the reference signature ``solver(points, logits) -> (quat, tvec)``
+that raises ``IndexError`` on failure (the reference's callers map ``IndexError`` / ``cv2.error`` to the zero pose,
+RV/gen_submission_single.py:169-175).  The batched form ``solver.solve_batch(...)`` is the fast path: one kernel
+launch per batch instead of one cv2 call chain per image.  Everything runs in libspe.so; there is no cv2 / CPU
+fallback here.
+"""
+import numpy as np
+import torch
+
+from .engine import Engine
+
+
+class BatchedPoseSolver:
+    def __init__(self, engine=None, reproj=20.0, weighted=False, reject=False, post=None, device=0, model=None):
+        self._engine = engine
+        self._model = model   # B200DETR whose context is shared once its first forward has created it
+        self._device = device
+        self.reprojectionError = float(reproj)
+        self.weighted, self.reject = bool(weighted), bool(reject)
+        self._post = post   # PostProcess whose batched launch already solved these images
+
+    @property
+    def engine(self):
+        if self._model is not None and self._model.engine is not None:
+            return self._model.engine
+        if self._engine is None:
+            # assign/PnP needs no model weights: a minimal context is enough
+            self._engine = Engine(max_batch=1, device=self._device)
+        return self._engine
+
+    def solve_batch(self, logits, points, boxes, log_sigma=None):
+        """cuda tensors [B,Q,12], [B,Q,2] (normalised), int [B,4] -> dict of cuda tensors (quat wxyz f64, tvec f64,
+        status int32, assign int32 [B,11], inlier_mask)."""
+        return self.engine.assign_pnp(logits, points, boxes, log_sigma=log_sigma, reproj=self.reprojectionError,
+                                      weighted=self.weighted and log_sigma is not None, reject=self.reject)
+
+    def __call__(self, points, logits, sigmas=None):
+        """Reference per-image signature: ``points`` [Q,2] in original-image pixels, ``logits`` [Q,12] class
+        probabilities (PostProcess output).  Answers from the batch solve PostProcess already did when possible."""
+        if self._post is not None:
+            hit = self._post.pose_cache.get(id(points))
+            if hit is not None and hit[0] is points:
+                _, quat, tvec, status = hit
+                if status != 0:
+                    raise IndexError(f"pose solve failed (status {status})")
+                return quat.copy(), tvec.copy()
+        points = np.asarray(points, dtype=np.float32)
+        probs = np.asarray(logits, dtype=np.float32)
+        assert points.shape[0] == probs.shape[0], "[Solver]: num_queries!"
+        dev = self.engine.device
+        # the kernel de-normalises with box (0,0,1,1): pixel coordinates pass through unchanged (x*1+0); softmax is
+        # monotone, so feeding log-probabilities reproduces the same arg-max labels and the same scores
+        lg = torch.from_numpy(np.log(np.maximum(probs, 1e-38)))[None].to(dev)
+        pt = torch.from_numpy(points)[None].to(dev)
+        box = torch.tensor([[0, 0, 1, 1]], dtype=torch.int32, device=dev)
+        ls = None
+        if sigmas is not None:
+            ls = torch.from_numpy(np.log(np.asarray(sigmas, dtype=np.float32)))[None].to(dev)
+        r = self.engine.assign_pnp(lg, pt, box, log_sigma=ls, reproj=self.reprojectionError,
+                                   weighted=self.weighted and ls is not None, reject=self.reject)
+        status = int(r["status"].item())
+        if status != 0:
+            raise IndexError(f"pose solve failed (status {status})")
+        return r["quat"][0].cpu().numpy(), r["tvec"][0].cpu().numpy()
+
+
+def build_solver(args, model=None, postprocessors=None):
+    """Reference contract ``build_solver(args)`` (RV/utils/speed_eval.py:21-22).  Passing the ``model`` /
+    ``postprocessors`` returned by ``build_model`` lets the solver share their context and batched results."""
+    post = postprocessors["points"] if postprocessors else None
+    dev = str(getattr(args, "device", "cuda"))
+    idx = (torch.device(dev).index or 0) if dev.startswith("cuda") else 0
+    return BatchedPoseSolver(reproj=float(getattr(args, "repro", 20)),
+                             weighted=bool(getattr(args, "sigma_head", False)),
+                             reject=bool(getattr(args, "self_assessment", False)), post=post, device=idx, model=model)

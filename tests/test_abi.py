@@ -1,0 +1,84 @@
+"""The C-ABI library loads and exports every symbol include/spe.h declares (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import torch
+
+from satellite_pose_estimation_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "spe.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spe_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib):
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"include/spe.h declares {n} but libspe.so does not export it"
+    assert set(names) == set(_lib.SYMBOLS), "ctypes prototypes out of sync with include/spe.h"
+
+
+def test_only_abi_symbols_are_exported():
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert exported and all(s.startswith("spe_") for s in exported), exported
+
+
+def test_kernels_are_blackwell_native():
+    """SASS evidence: tcgen05 MMA (UTC*MMA), TMEM loads (LDTM) and TMA (UTMALDG) are in the shipped binary."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, f"{mnemonic} missing from libspe.so SASS"
+
+
+def test_clip_boxes_bit_exact_on_every_reference_box(lib):
+    """Row 1 of SURVEY.md section 8a: int64 crop boxes must be bit-exact (host-side f64 + truncation)."""
+    from oracle import crop_ref, synth
+    for name in ("wz_synt_test_boxes.npy", "wz_real_test_boxes.npy"):
+        det = np.load(os.path.join(synth.GOLDEN_DIR, name))
+        out = np.empty((len(det), 4), dtype=np.int32)
+        assert lib.spe_clip_boxes(det.ctypes.data_as(C.c_void_p), len(det), out.ctypes.data_as(C.c_void_p)) == 0
+        ref = np.stack([crop_ref.generate_clip_bbox(b) for b in det])
+        assert (out == ref).all()
+    neg = np.array([[-30.7, -12.2, 55.5, 40.1], [10.0, 10.0, 10.0, 10.0]])   # truncation toward zero, empty box
+    out = np.empty((2, 4), dtype=np.int32)
+    lib.spe_clip_boxes(neg.ctypes.data_as(C.c_void_p), 2, out.ctypes.data_as(C.c_void_p))
+    assert (out == np.stack([crop_ref.generate_clip_bbox(b) for b in neg])).all()
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU the product path fails loudly instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        return
+    cfg = _lib.SpeConfig(224, 40, 4, 4, 256, 8, 2048, 0, 0, 0, 4)
+    ctx = C.c_void_p()
+    rc = lib.spe_create(C.byref(cfg), 0, C.byref(ctx))
+    assert rc != 0 and not ctx.value
+    assert b"no CPU fallback" in lib.spe_global_last_error()
+    import pytest
+    from satellite_pose_estimation_b200 import Engine
+    with pytest.raises(RuntimeError):
+        Engine()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "satellite_pose_estimation_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f

@@ -1,0 +1,91 @@
+"""Tensor-core GEMM / implicit conv / attention kernels against a plain PyTorch fp64 reference (through the C ABI)."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DT = {0: torch.float32, 1: torch.bfloat16}
+# max|err| relative to max|ref|: TF32 carries a 10-bit mantissa (2^-11 per operand), bf16 a 7-bit one
+TOL = {0: 2e-3, 1: 1.2e-2}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _rel(got, ref):
+    return ((got.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+@pytest.mark.parametrize("M,N,K,relu,res,res_mod", [
+    (128, 64, 64, 0, 0, 0), (1, 64, 64, 0, 0, 0), (300, 256, 512, 1, 1, 0), (6272, 64, 256, 1, 0, 0),
+    (2352, 768, 256, 0, 1, 784), (40, 256, 2048, 0, 1, 0), (12544, 64, 192, 1, 0, 0), (1000, 2048, 256, 1, 0, 0),
+    (784 * 16, 128, 1152, 1, 0, 0)])
+def test_gemm(lib, cuda_dev, dt, M, N, K, relu, res, res_mod):
+    torch.manual_seed(M + N + K)
+    tdt = DT[dt]
+    A = torch.randn(M, K, device=cuda_dev).to(tdt)
+    W = (torch.randn(N, K, device=cuda_dev) / K ** 0.5).to(tdt)
+    scale = torch.rand(N, device=cuda_dev) + 0.5
+    bias = torch.randn(N, device=cuda_dev)
+    rows = res_mod if res_mod else M
+    R = torch.randn(rows, N, device=cuda_dev).to(tdt) if res else None
+    out = torch.full((M, N), float("nan"), device=cuda_dev).to(tdt)
+    assert lib.spe_debug_gemm(dt, _p(A), _p(W), M, N, K, _p(scale), _p(bias), _p(R), res_mod, relu, _p(out), None) == 0
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() * scale.double() + bias.double()
+    if res:
+        r = R.double()
+        ref = ref + (r.repeat(M // rows + 1, 1)[:M] if res_mod else r)
+    if relu:
+        ref = ref.clamp_min(0)
+    assert not torch.isnan(out.float()).any()
+    assert _rel(out, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+@pytest.mark.parametrize("NB,H,Cin,Cout", [(2, 28, 64, 64), (3, 56, 64, 64), (2, 14, 256, 256), (1, 28, 1024, 256),
+                                            (1, 7, 64, 128), (5, 32, 128, 128)])
+def test_implicit_conv3x3(lib, cuda_dev, dt, NB, H, Cin, Cout):
+    """TMA out-of-bounds zero fill == the convolution's zero padding; ragged last row-tile (H % hrows != 0)."""
+    torch.manual_seed(H * Cin)
+    tdt = DT[dt]
+    x = torch.randn(NB, H, H, Cin, device=cuda_dev).to(tdt)
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda_dev) / (9 * Cin) ** 0.5).to(tdt)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    bias = torch.randn(Cout, device=cuda_dev)
+    out = torch.full((NB, H, H, Cout), float("nan"), device=cuda_dev).to(tdt)
+    assert lib.spe_debug_conv(dt, _p(x), _p(wk), NB, H, H, Cin, Cout, 3, 3, 1, None, _p(bias), 1, _p(out), None) == 0
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1)
+    ref = ref.clamp_min(0).permute(0, 2, 3, 1)
+    assert not torch.isnan(out.float()).any()
+    assert _rel(out, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+@pytest.mark.parametrize("B,Lq,Lk", [(2, 784, 784), (3, 40, 40), (2, 40, 784), (1, 100, 1024), (1, 1, 5)])
+def test_attention(lib, cuda_dev, dt, B, Lq, Lk):
+    torch.manual_seed(Lq + Lk)
+    tdt = DT[dt]
+    q = torch.randn(B, Lq, 256, device=cuda_dev).to(tdt)
+    k = torch.randn(B, Lk, 256, device=cuda_dev).to(tdt)
+    v = torch.randn(B, Lk, 256, device=cuda_dev).to(tdt)
+    out = torch.full((B, Lq, 256), float("nan"), device=cuda_dev).to(tdt)
+    assert lib.spe_debug_attention(dt, _p(q), _p(k), _p(v), _p(out), B, 8, Lq, Lk, 256, 256, 256, 256, None) == 0
+    torch.cuda.synchronize()
+    qh = q.double().view(B, Lq, 8, 32).transpose(1, 2)
+    kh = k.double().view(B, Lk, 8, 32).transpose(1, 2)
+    vh = v.double().view(B, Lk, 8, 32).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 32 ** 0.5, -1) @ vh).transpose(1, 2).reshape(B, Lq, 256)
+    assert not torch.isnan(out.float()).any()
+    assert _rel(out, ref) < (2e-3 if dt == 0 else 8e-3)
+
+
+def test_gemm_rejects_bad_shapes(lib, cuda_dev):
+    a = torch.zeros(8, 48, device=cuda_dev)
+    assert lib.spe_debug_gemm(0, _p(a), _p(a), 8, 8, 48, None, None, None, 0, 0, _p(a), None) != 0
+    assert b"gemm" in lib.spe_global_last_error()

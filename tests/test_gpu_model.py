@@ -1,0 +1,174 @@
+"""Keypoint-set predictor forward through the C ABI against the oracle (restated reference forward, fp32 CPU) and
+the golden outputs of the real reference."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref, pnp_ref, synth
+from oracle.make_golden import MODEL_CASES, model_inputs
+from satellite_pose_estimation_b200 import Engine, build_model, build_solver
+
+pytestmark = pytest.mark.gpu
+
+# north_star: keypoints within 0.5 px in fp32/TF32 mode.  pixel = sigmoid * S + x1, so the bar on the normalised
+# output is 0.5 / S; we hold it at the LARGEST crop of the real box distribution (S = 1748) -> 2.86e-4.
+S_MAX = 1748
+PTS_TOL_TF32 = 0.5 / S_MAX
+LOGIT_TOL_TF32 = 1e-2
+PTS_TOL_BF16 = 8e-3          # bf16 cannot meet 0.5 px at large crops: reported, looser bar
+LOGIT_TOL_BF16 = 0.15
+
+
+def _engine(cfg, R, B, precision):
+    e = Engine(input_size=R, num_queries=cfg.num_queries, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers,
+               backbone=cfg.backbone, precision=precision, has_sigma=cfg.sigma_head, max_batch=B)
+    return e
+
+
+@pytest.mark.parametrize("case", list(MODEL_CASES))
+def test_forward_matches_reference_golden_tf32(lib, cuda_dev, case):
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "model_golden.npz"))
+    kw, B, R, seed = MODEL_CASES[case]
+    cfg = model_ref.ModelCfg(**kw)
+    sd = synth.make_state_dict(cfg, seed=seed)
+    assert synth.weights_checksum(sd).encode() == g[case + "/checksum"].tobytes()
+    eng = _engine(cfg, R, B, "tf32")
+    eng.load_state_dict(sd)
+    out = eng.forward(model_inputs(B, R, seed).cuda(), want_aux=True)
+    torch.cuda.synchronize()
+    dp = np.abs(out["pred_points"].cpu().numpy() - g[case + "/pred_points"]).max()
+    dl = np.abs(out["pred_logits"].cpu().numpy() - g[case + "/pred_logits"]).max()
+    assert dp <= PTS_TOL_TF32, f"keypoints off by {dp * S_MAX:.3f} px at S={S_MAX}"
+    assert dl <= LOGIT_TOL_TF32
+    aux_p = torch.stack([a["pred_points"] for a in out["aux_outputs"]]).cpu().numpy()
+    aux_l = torch.stack([a["pred_logits"] for a in out["aux_outputs"]]).cpu().numpy()
+    assert np.abs(aux_p - g[case + "/aux_points"]).max() <= PTS_TOL_TF32
+    assert np.abs(aux_l - g[case + "/aux_logits"]).max() <= LOGIT_TOL_TF32
+    assert np.array_equal(out["pred_logits"].argmax(-1).cpu().numpy(), g[case + "/pred_logits"].argmax(-1))
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_forward_layerwise_vs_oracle(lib, cuda_dev, precision):
+    cfg = model_ref.ModelCfg(sigma_head=True)
+    sd = synth.make_state_dict(cfg, seed=3)
+    B = 3
+    x = model_inputs(B, 224, 11)
+    eng = _engine(cfg, 224, 4, precision)
+    eng.load_state_dict(sd)
+    eng.enable_taps(True)
+    out = eng.forward(x.cuda(), want_aux=True)
+    torch.cuda.synchronize()
+    taps = {}
+    ref = model_ref.forward(sd, cfg, x, taps)
+    rel = 6e-3 if precision == "tf32" else 4e-2
+
+    def check(name, got, want):
+        err = (got - want).abs().max().item() / want.abs().max().item()
+        assert err < rel, f"{name}: rel err {err:.2e}"
+
+    nhwc = lambda t: t.permute(0, 2, 3, 1)
+    check("stem", eng.read_tap("stem", (B, 112, 112, 64)), nhwc(taps["stem"]))
+    check("layer1", eng.read_tap("layer1", (B, 56, 56, 256)), nhwc(taps["layer1"]))
+    check("layer2", eng.read_tap("layer2", (B, 28, 28, 512)), nhwc(taps["layer2"]))
+    check("layer3", eng.read_tap("layer3", (B, 14, 14, 1024)), nhwc(taps["layer3"]))
+    check("neck", eng.read_tap("neck", (B, 28, 28, 512)), nhwc(taps["neck"]))
+    for i in range(cfg.enc_layers):
+        check(f"enc{i}", eng.read_tap(f"enc{i}", (B, 784, 256)), taps[f"enc{i}"].permute(1, 0, 2))
+    check("hs", eng.read_tap("hs", (cfg.dec_layers, B, 40, 256)), taps["hs"])
+    ptol, ltol = (PTS_TOL_TF32, LOGIT_TOL_TF32) if precision == "tf32" else (PTS_TOL_BF16, LOGIT_TOL_BF16)
+    assert (out["pred_points"].cpu() - ref["pred_points"]).abs().max() <= ptol
+    assert (out["pred_logits"].cpu() - ref["pred_logits"]).abs().max() <= ltol
+    assert (out["pred_sigmas"].cpu() - ref["pred_sigmas"]).abs().max() <= ltol
+    assert torch.equal(out["pred_sigmas"][..., 0], out["pred_sigmas"][..., 1])
+    eng.close()
+
+
+def test_batch_invariance_and_chunking(lib, cuda_dev):
+    """An image's outputs do not depend on its batch neighbours; batches above max_batch are chunked."""
+    cfg = model_ref.ModelCfg()
+    sd = synth.make_state_dict(cfg, seed=0)
+    args = SimpleNamespace(backbone="resnet50s8", num_queries=40, enc_layers=4, dec_layers=4, hidden_dim=256, nheads=8,
+                           dim_feedforward=2048, aux_loss=False, device="cuda", repro=20, max_batch=4)
+    model, _, post = build_model(args)
+    model.to("cuda")
+    model.load_state_dict(sd, strict=True)
+    x = model_inputs(6, 224, 5).cuda()
+    full = model(x)                       # 6 > max_batch=4 -> two chunks
+    one = model(x[4:5])
+    assert "aux_outputs" not in full
+    assert torch.allclose(full["pred_points"][4], one["pred_points"][0], atol=1e-6)
+    assert torch.allclose(full["pred_logits"][4], one["pred_logits"][0], atol=1e-5)
+    lst = model([x[0], x[1]])            # list[Tensor] input like the reference
+    assert torch.allclose(lst["pred_points"], full["pred_points"][:2], atol=1e-6)
+
+
+def test_drop_in_loop_like_gen_submission(lib, cuda_dev):
+    """The reference's hot loop (RV/gen_submission_single.py:136-181) with the drop-in objects, on seeded inputs;
+    outputs are compared with the oracle chain (restated forward + PostProcess + cv2 solver)."""
+    cfg = model_ref.ModelCfg()
+    sd = synth.make_state_dict(cfg, seed=0)
+    args = SimpleNamespace(backbone="resnet50s8", num_queries=40, enc_layers=4, dec_layers=4, hidden_dim=256, nheads=8,
+                           dim_feedforward=2048, aux_loss=True, device="cuda", repro=20)
+    model, criterion, postprocessors = build_model(args)
+    model.to("cuda")
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    solver = build_solver(args, model, postprocessors)
+    x = model_inputs(2, 224, 9)
+    clip = [torch.tensor([300, 200, 816, 716]), torch.tensor([-20, 40, 1128, 1188])]
+    outputs = model(x.to("cuda"))
+    results = postprocessors["points"](outputs, clip)
+    ref_out = model_ref.forward(sd, cfg, x)
+    ref_res = pnp_ref.post_process(ref_out["pred_logits"], ref_out["pred_points"], clip)
+    for r, rr, box in zip(results, ref_res, clip):
+        side = float(box[2] - box[0])
+        assert np.abs(r["points"] - rr["points"]).max() <= 0.5 * side / S_MAX + 1e-3   # <= 0.5 px at S_MAX scale
+        assert np.abs(r["logits"] - rr["logits"]).max() < 5e-3
+        try:
+            q, t = solver(r["points"], r["logits"])
+            ok = True
+        except IndexError:
+            q, t, ok = np.zeros(4), np.zeros(3), False
+        q_ref, t_ref, ok_ref = pnp_ref.solve_or_zero(pnp_ref.SimplePoseSolver(20), rr["points"], rr["logits"])
+        assert ok == ok_ref                              # random-init weights collapse to one label -> both fail
+
+
+def test_host_pipeline_matches_stagewise(lib, cuda_dev):
+    """spe_run_batch_host (host in, host out) == the three stage calls on device buffers."""
+    cfg = model_ref.ModelCfg()
+    eng = _engine(cfg, 224, 8, "tf32")
+    eng.load_state_dict(synth.make_state_dict(cfg, seed=0))
+    det = synth.load_detector_boxes()[:8]
+    frames = synth.make_frames(8, det, seed=2)
+    r = eng.run_batch_host(torch.from_numpy(frames).pin_memory(), det)
+    clip = eng.clip_boxes(det)
+    assert np.array_equal(r["boxes"], clip)
+    img = eng.crop_resize_norm(torch.from_numpy(frames).cuda(), torch.from_numpy(clip).cuda())
+    out = eng.forward(img)
+    p = eng.assign_pnp(out["pred_logits"], out["pred_points"], torch.from_numpy(clip).cuda())
+    assert np.array_equal(r["status"], p["status"].cpu().numpy())
+    assert np.allclose(r["quat"], p["quat"].cpu().numpy()) and np.allclose(r["tvec"], p["tvec"].cpu().numpy())
+    eng.close()
+
+
+def test_errors_are_loud(lib, cuda_dev):
+    cfg = model_ref.ModelCfg()
+    eng = _engine(cfg, 224, 2, "tf32")
+    from satellite_pose_estimation_b200._lib import SpeError
+    with pytest.raises(SpeError, match="spe_load_weights first"):
+        eng.forward(torch.zeros(1, 3, 224, 224, device="cuda"))
+    sd = synth.make_state_dict(cfg, seed=0)
+    bad = dict(sd); bad.pop("input_proj.bias")
+    with pytest.raises(SpeError, match="input_proj.bias"):
+        eng.load_state_dict(bad)
+    bad = dict(sd); bad["cls_embed.weight"] = torch.zeros(13, 256)
+    with pytest.raises(SpeError, match="cls_embed.weight"):
+        eng.load_state_dict(bad)
+    eng.load_state_dict(sd)
+    with pytest.raises(SpeError, match="max_batch"):
+        eng.forward(torch.zeros(3, 3, 224, 224, device="cuda"))
+    eng.close()

@@ -1,0 +1,160 @@
+"""Batched assignment + PnP kernel against the oracle (the reference's cv2 call chain) and the golden poses."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pnp_ref, synth
+from oracle.constants import TANGO_POINTS
+from satellite_pose_estimation_b200 import Engine
+
+pytestmark = pytest.mark.gpu
+ROT_TOL_DEG, TRA_TOL = 0.01, 1e-4        # north_star: "poses match cv2 within 0.01 deg rotation and 1e-4 relative t"
+
+
+@pytest.fixture(scope="module")
+def eng(lib, cuda_dev):
+    e = Engine(max_batch=1)
+    yield e
+    e.close()
+
+
+def _solve(eng, d, **kw):
+    ls = torch.from_numpy(d["logsig"]).cuda() if "logsig" in d else None
+    r = eng.assign_pnp(torch.from_numpy(d["logits"]).cuda(), torch.from_numpy(d["points"]).cuda(),
+                       torch.from_numpy(d["boxes"]).cuda(), log_sigma=ls, want_post=True, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in r.items()}
+
+
+def _used(assign_row, mask):
+    labels = [l for l in range(11) if assign_row[l] >= 0]
+    return sorted(labels[j] for j in range(len(labels)) if (mask >> j) & 1)
+
+
+def test_postprocess_and_assignment_bit_exact(eng):
+    d = synth.make_predictions(1000, seed=11)
+    r = _solve(eng, d)
+    res = pnp_ref.post_process(d["logits"], d["points"], d["boxes"])
+    for i in range(1000):
+        assert np.array_equal(r["points_px"][i], res[i]["points"])                  # same fp32 mul-then-add
+        assert np.abs(r["probs"][i] - res[i]["logits"]).max() < 1e-6
+        assert np.array_equal(r["assign"][i], pnp_ref.assign_table(res[i]["points"], res[i]["logits"]))
+
+
+def test_pose_matches_cv2_chain(eng):
+    n = 1500
+    d = synth.make_predictions(n, seed=1)
+    r = _solve(eng, d, reproj=20.0)
+    res = pnp_ref.post_process(d["logits"], d["points"], d["boxes"])
+    solver = pnp_ref.SimplePoseSolver(20, return_inliers=True)
+    inl_mismatch = compared = 0
+    for i in range(n):
+        try:
+            q_ref, t_ref, used = solver(res[i]["points"], res[i]["logits"]); ok = True
+        except Exception:
+            ok = False
+        assert ok == (r["status"][i] == 0), f"image {i}: success/failure differs from the reference"
+        if not ok:
+            assert not r["quat"][i].any() and not r["tvec"][i].any()               # zero pose contract
+            continue
+        if _used(r["assign"][i], r["inlier_mask"][i]) != used:
+            inl_mismatch += 1                                                         # RANSAC draw ambiguity
+            continue
+        s_t, s_q = pnp_ref.speed_score(r["quat"][i], r["tvec"][i], q_ref, t_ref)
+        assert np.degrees(s_q) < ROT_TOL_DEG and s_t < TRA_TOL, (i, np.degrees(s_q), s_t)
+        assert r["quat"][i][0] >= 0 and abs(np.linalg.norm(r["quat"][i]) - 1) < 1e-12
+        compared += 1
+    assert compared > 0.9 * n and inl_mismatch <= 0.005 * n, (compared, inl_mismatch)
+    assert (d["n_outliers"] > 0).sum() > 50 and (r["status"] == 1).sum() > 20       # both paths exercised
+
+
+def test_pose_matches_reference_golden(eng):
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "pnp_golden.npz"))
+    d = synth.make_predictions(int(g["n"]), seed=int(g["seed"]))
+    r = _solve(eng, d)
+    assert np.array_equal(r["assign"], g["assign"])
+    assert np.array_equal(r["status"] == 0, g["ok"] == 1)
+    worst = 0.0
+    n_off = 0
+    for i in np.nonzero(g["ok"])[0]:
+        s_t, s_q = pnp_ref.speed_score(r["quat"][i], r["tvec"][i], g["quat"][i], g["tvec"][i])
+        if np.degrees(s_q) > ROT_TOL_DEG or s_t > TRA_TOL:
+            n_off += 1                                                                # different RANSAC inlier set
+        else:
+            worst = max(worst, np.degrees(s_q))
+    assert n_off <= 2, n_off
+
+
+def test_edge_cases(eng):
+    d = synth.make_predictions(8, seed=2, few_frac=0.0, outlier_frac=0.0)
+    d["logits"][0, :, :] = -4.0; d["logits"][0, :, 11] = 4.0                         # all background
+    fg = [q for q in range(40) if d["logits"][1, q].argmax() != 11]
+    for q in fg[3:]:
+        d["logits"][1, q, :] = -4.0; d["logits"][1, q, 11] = 4.0                     # exactly 3 keypoints
+    for q in fg[4:]:
+        d["logits"][2, q, :] = -4.0; d["logits"][2, q, 11] = 4.0                     # exactly 4 keypoints
+    r = _solve(eng, d)
+    assert r["status"][0] == 1 and (r["assign"][0] == -1).all()
+    assert r["status"][1] == 1 and (r["assign"][1] >= 0).sum() == 3
+    res = pnp_ref.post_process(d["logits"], d["points"], d["boxes"])
+    q, t, ok = pnp_ref.solve_or_zero(pnp_ref.SimplePoseSolver(20), res[2]["points"], res[2]["logits"])
+    assert ok == (r["status"][2] == 0)
+    # duplicated label: the higher score wins, ties go to the first query
+    d2 = synth.make_predictions(1, seed=4, few_frac=0.0, outlier_frac=0.0)
+    d2["logits"][0, 5] = d2["logits"][0, 9] = np.log(np.r_[0.9, np.full(11, 0.1 / 11)]).astype(np.float32)
+    r2 = _solve(eng, d2)
+    assert r2["assign"][0, 0] == 5
+
+
+def test_sigma_weighted_solve_and_reject_filter(eng):
+    """Self-assessment variant.  PARITY UNPINNED by the reference (private PyCeres cost functor): checked against
+    the scipy restatement oracle/pnp_ref.sigma_pnp and the builder-defined filter spec."""
+    n = 200
+    d = synth.make_predictions(n, seed=7, with_sigma=True)
+    r = _solve(eng, d, reproj=25.0, weighted=True, reject=True, reject_rms_px=5.0, reject_sigma_px=12.0)
+    res = pnp_ref.post_process(d["logits"], d["points"], d["boxes"], d["logsig"])
+    checked = 0
+    for i in range(n):
+        if r["status"][i] not in (0, 3):
+            continue
+        order, qidx, pts = pnp_ref.assign(res[i]["points"], res[i]["logits"])
+        used = _used(r["assign"][i], r["inlier_mask"][i])
+        sel = [j for j, l in enumerate(order) if l in used]
+        sig = np.asarray([res[i]["sigmas"][qidx[j]] for j in sel])
+        import cv2
+        ok, rv0, tv0 = cv2.solvePnP(TANGO_POINTS[[order[j] for j in sel]], pts[sel], pnp_ref.CAMERA_K, None,
+                                    flags=cv2.SOLVEPNP_EPNP)
+        rv, tv = pnp_ref.sigma_pnp(TANGO_POINTS[[order[j] for j in sel]], pts[sel], sig, rv0, tv0)
+        q_ref = pnp_ref.rot_to_quat(cv2.Rodrigues(rv.reshape(3, 1))[0])
+        if r["status"][i] == 0:
+            s_t, s_q = pnp_ref.speed_score(r["quat"][i], r["tvec"][i], q_ref, tv)
+            assert np.degrees(s_q) < ROT_TOL_DEG and s_t < TRA_TOL, (i, np.degrees(s_q), s_t)
+            checked += 1
+        rms = pnp_ref.reproj_rms_px(r["quat"][i], r["tvec"][i], TANGO_POINTS[[order[j] for j in sel]], pts[sel]) \
+            if r["status"][i] == 0 else None
+        side = d["boxes"][i, 2] - d["boxes"][i, 0]
+        mean_sigma_px = float(sig.mean() * side)
+        if rms is not None:
+            assert not pnp_ref.self_assessment(len(sel), rms, mean_sigma_px)
+    assert checked > 100
+    # a confident-but-wrong set is rejected: tiny threshold forces status 3 with the pose still reported
+    r3 = _solve(eng, d, reproj=25.0, weighted=True, reject=True, reject_rms_px=1e-3)
+    assert ((r3["status"] == 3) | (r3["status"] == 1)).all() and (r3["status"] == 3).sum() > 100
+
+
+def test_single_image_solver_interface(eng):
+    """Reference per-image signature solver(points, probs) -> (quat, tvec), IndexError on failure."""
+    from satellite_pose_estimation_b200 import BatchedPoseSolver
+    s = BatchedPoseSolver(engine=eng, reproj=20)
+    d = synth.make_predictions(6, seed=21, few_frac=0.0, outlier_frac=0.0)
+    res = pnp_ref.post_process(d["logits"], d["points"], d["boxes"])
+    ref = pnp_ref.SimplePoseSolver(20)
+    for i in range(6):
+        q, t = s(res[i]["points"], res[i]["logits"])
+        q_ref, t_ref = ref(res[i]["points"], res[i]["logits"])
+        s_t, s_q = pnp_ref.speed_score(q, t, q_ref, t_ref)
+        assert np.degrees(s_q) < ROT_TOL_DEG and s_t < TRA_TOL
+    with pytest.raises(IndexError):
+        s(res[0]["points"][:2], res[0]["logits"][:2])

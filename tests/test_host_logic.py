@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference interface + multi-process sharding (CPU; gloo, world_size 2)."""
+import os
+import subprocess
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref, ref_import, synth
+from satellite_pose_estimation_b200 import build_model, build_solver
+from satellite_pose_estimation_b200.models import param_specs
+from satellite_pose_estimation_b200.sharding import batches, shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(**kw):
+    a = dict(backbone="resnet50s8", num_queries=40, enc_layers=4, dec_layers=4, hidden_dim=256, nheads=8,
+             dim_feedforward=2048, aux_loss=True, device="cuda", repro=20)
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+@pytest.mark.parametrize("backbone,nq,enc,dec", [("resnet50s8", 40, 4, 4), ("resnet50", 100, 6, 6)])
+def test_state_dict_layout_is_the_references(backbone, nq, enc, dec):
+    cfg = model_ref.ModelCfg(backbone=backbone, num_queries=nq, enc_layers=enc, dec_layers=dec)
+    sd = synth.make_state_dict(cfg)
+    model, criterion, post = build_model(_args(backbone=backbone, num_queries=nq, enc_layers=enc, dec_layers=dec))
+    assert criterion is None and callable(post["points"])
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == {k: tuple(v.shape) for k, v in sd.items()}
+    if ref_import.available():     # against the real reference module tree
+        ref_model, _, _ = ref_import.build_reference_model(cfg)
+        assert mine == {k: tuple(v.shape) for k, v in ref_model.state_dict().items()}
+        assert {n for n, _ in model.named_parameters()} == {n for n, _ in ref_model.named_parameters()}
+
+
+def test_checkpoint_with_num_batches_tracked_loads():
+    model, _, _ = build_model(_args())
+    sd = dict(synth.make_state_dict(model_ref.ModelCfg()))
+    sd["backbone.0.body.bn1.num_batches_tracked"] = torch.tensor(3)      # dropped like backbone.py:34-42
+    model.load_state_dict(sd, strict=True)
+
+
+def test_backbone_arg_is_rewritten_like_the_reference():
+    a = _args(backbone="resnet50s8")
+    build_model(a)
+    assert a.backbone == "resnet50"                                      # RV/models/backbone.py:193
+
+
+def test_cpu_model_fails_loudly():
+    model, _, post = build_model(_args())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(RuntimeError):
+        post["points"]({"pred_logits": torch.zeros(1, 40, 12), "pred_points": torch.zeros(1, 40, 2)},
+                       [torch.tensor([0, 0, 10, 10])])
+    with pytest.raises(RuntimeError):
+        model.train()
+    with pytest.raises(ValueError):
+        model.cuda_shape_check = None
+        model._as_batch([torch.zeros(3, 8, 8), torch.zeros(3, 9, 9)])
+    assert build_solver(_args(), model, {"points": post["points"]}).reprojectionError == 20.0
+
+
+def test_unsupported_configs_are_rejected():
+    with pytest.raises(ValueError):
+        build_model(_args(hidden_dim=512))
+    with pytest.raises(ValueError):
+        build_model(_args(backbone="resnet18"))
+
+
+def test_param_specs_count():
+    assert len(param_specs("resnet50s8", 40, 4, 4, 256, 2048, False)) == 352
+    assert len(param_specs("resnet50s8", 40, 4, 4, 256, 2048, True)) == 358
+
+
+def test_shard_range_covers_everything_once():
+    for n in (0, 1, 7, 64, 2998):
+        for ws in (1, 2, 3, 8):
+            got = []
+            for r in range(ws):
+                a, b = shard_range(n, r, ws)
+                got += list(range(a, b))
+                assert 0 <= b - a <= n // ws + 1
+            assert got == list(range(n))
+    assert batches(10, 75, 32) == [(10, 42), (42, 74), (74, 75)]                      # ragged tail kept
+    assert batches(5, 5, 32) == []
+
+
+def test_two_rank_gloo_gather(tmp_path):
+    """N>1 path on CPU: 2 ranks shard 11 items, rank 0 gathers and orders by filename (no data-path collective)."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, json\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import torch.distributed as dist\n"
+        "from satellite_pose_estimation_b200.sharding import shard_range, gather_results\n"
+        "dist.init_process_group('gloo')\n"
+        "r, ws = dist.get_rank(), dist.get_world_size()\n"
+        "a, b = shard_range(11, r, ws)\n"
+        "local = {f'img{i:06d}.jpg': (i, r) for i in range(a, b)}\n"
+        "res = gather_results(local)\n"
+        "if r == 0:\n"
+        "    assert list(res) == sorted(res) and len(res) == 11, res\n"
+        "    assert sorted(v[0] for v in res.values()) == list(range(11))\n"
+        "    assert {v[1] for v in res.values()} == {0, 1}\n"
+        "    print('GATHER_OK')\n"
+        "else:\n"
+        "    assert res is None\n"
+        "dist.destroy_process_group()\n")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "GATHER_OK" in out.stdout, out.stdout + out.stderr
