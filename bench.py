@@ -205,6 +205,7 @@ def run_b200(args):
     syn_points = torch.from_numpy(preds["points"]).to(dev)
     syn_boxes = torch.from_numpy(preds["boxes"]).to(torch.int32).to(dev)
     images = torch.empty((BATCH, 3, R, R), dtype=torch.float32, device=dev)
+    eng.register_stable_input(images)
 
     def step(i):
         """one pass of the hot path over one batch, inputs resident in HBM"""

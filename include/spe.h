@@ -120,7 +120,8 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
                        int32_t* boxes_host /*[B,4] or NULL*/, void* stream);
 
 /* ---- test / bring-up hooks (not part of the drop-in surface) ------------------------------------------------- */
-/* out = act(scale * A.W^T + bias + residual) with A [M,K], W [N,K], storage dtype 0=fp32/TF32, 1=bf16 */
+/* out = act(scale * A.W^T + bias + residual) with A [M,K], W [N,K], storage dtype 0=fp32/TF32, 1=bf16,
+ * 2=fp32 with error-compensated 3xTF32 (W is then [N,2K] = [rna(W) | rna(W - rna(W))], output not rounded) */
 int spe_debug_gemm(int dtype, const void* A_dev, const void* W_dev, long long M, int N, int K, const float* scale_dev,
                    const float* bias_dev, const void* residual_dev, int res_mod, int relu, void* out_dev,
                    void* stream);

@@ -157,7 +157,8 @@ int spe_debug_gemm(int dtype, const void* A, const void* Wt, long long M, int N,
   d.mode = 0; d.A = A; d.M = M; d.K = K; d.lda = K; d.Wt = Wt; d.N = N;
   d.scale = scale; d.bias = bias; d.residual = residual; d.res_ld = N; d.res_mod = res_mod; d.relu = relu;
   d.out = out; d.out_ld = N;
-  std::string s = launch_gemm(dtype == 0 ? kTF32 : kBF16, d, sm_count(), static_cast<cudaStream_t>(stream));
+  if (dtype == 2) { d.x3 = 1; d.round_out = 0; }   // 3xTF32: Wt is the pre-split [N, 2K] matrix
+  std::string s = launch_gemm(dtype == 1 ? kBF16 : kTF32, d, sm_count(), static_cast<cudaStream_t>(stream));
   if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_gemm: " + s);
   return SPE_OK;
 }

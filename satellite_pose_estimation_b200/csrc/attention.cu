@@ -63,11 +63,12 @@ template <> __device__ __forceinline__ float load1<float>(const float* p) { retu
 template <> __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(*p);
 }
-template <typename T> __device__ __forceinline__ void store2(T* p, float a, float b);
-template <> __device__ __forceinline__ void store2<float>(float* p, float a, float b) {
-  *reinterpret_cast<float2*>(p) = make_float2(to_tf32(a), to_tf32(b));  // consumed by a kind::tf32 GEMM
+template <typename T> __device__ __forceinline__ void store2(T* p, float a, float b, int exact);
+template <> __device__ __forceinline__ void store2<float>(float* p, float a, float b, int exact) {
+  // rounded to TF32 when the consumer is a plain kind::tf32 GEMM; kept exact for the 3xTF32 decoder GEMMs
+  *reinterpret_cast<float2*>(p) = exact ? make_float2(a, b) : make_float2(to_tf32(a), to_tf32(b));
 }
-template <> __device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+template <> __device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, int) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
@@ -75,7 +76,7 @@ template <typename T, int KT>
 __global__ void __launch_bounds__(128)
 attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ out,
                  int ldq, int ldk, int ldv, int ldo, long long bsq, long long bsk, long long bsv, long long bso,
-                 int Lq, int Lk, float scale_log2e) {
+                 int Lq, int Lk, float scale_log2e, int exact_out) {
   __shared__ __align__(16) float Ks[KT * KLD];
   __shared__ __align__(16) float Vs[KT * KLD];
 
@@ -187,8 +188,8 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
     const int c = d * 8 + 2 * t;
-    if (r0 < Lq) store2(ob + static_cast<long long>(r0) * ldo + c, o[d][0] * i0, o[d][1] * i0);
-    if (r1 < Lq) store2(ob + static_cast<long long>(r1) * ldo + c, o[d][2] * i1, o[d][3] * i1);
+    if (r0 < Lq) store2(ob + static_cast<long long>(r0) * ldo + c, o[d][0] * i0, o[d][1] * i0, exact_out);
+    if (r1 < Lq) store2(ob + static_cast<long long>(r1) * ldo + c, o[d][2] * i1, o[d][3] * i1, exact_out);
   }
 }
 
@@ -203,10 +204,10 @@ std::string launch_attn_t(const AttnDesc& d, cudaStream_t s) {
   ProfScope ps(kFamAttention, s);
   if (d.Lk % 112 == 0) {
     attention_kernel<T, 112><<<grid, 128, 0, s>>>(q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq, d.bsk, d.bsv,
-                                                 d.bso, d.Lq, d.Lk, sl2);
+                                                 d.bso, d.Lq, d.Lk, sl2, d.exact_out);
   } else {
     attention_kernel<T, 64><<<grid, 128, 0, s>>>(q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq, d.bsk, d.bsv,
-                                                d.bso, d.Lq, d.Lk, sl2);
+                                                d.bso, d.Lq, d.Lk, sl2, d.exact_out);
   }
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

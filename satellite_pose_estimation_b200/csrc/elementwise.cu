@@ -50,9 +50,6 @@ template <typename T> __device__ __forceinline__ Vec<T> vload(const T* p) {
 template <typename T> __device__ __forceinline__ void vstore(T* p, const Vec<T>& x) {
   *reinterpret_cast<decltype(x.v)*>(p) = x.v;
 }
-template <typename T> __device__ __forceinline__ T from_float(float x);
-template <> __device__ __forceinline__ float from_float<float>(float x) { return x; }
-template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // stem im2col: out[(n, oy, ox), (r*7 + s)*3 + c] = in[n, c, 2*oy - 3 + r, 2*ox - 3 + s]  (0 outside), K padded to 192

@@ -26,7 +26,6 @@ namespace spe {
 namespace {
 
 constexpr int BM = 128;
-constexpr int kGemmThreads = 192;
 
 template <typename T> struct GemmTraits;
 template <> struct GemmTraits<float> {
@@ -40,14 +39,18 @@ template <> struct GemmTraits<__nv_bfloat16> {
   static constexpr int kFmt = 1;
 };
 
-template <int BN> struct StageCfg {
+// X3 = error-compensated "3xTF32": A = A_hi + A_lo (split in shared memory by dedicated warps), W = W_hi + W_lo
+// (split once at weight load, stored as [N, 2K] = [W_hi | W_lo]); D = A_hi W_hi + A_lo W_hi + A_hi W_lo in one TMEM
+// accumulator.  Used where TF32's 10-bit mantissa is not enough (decoder + heads).
+template <int BN, bool X3> struct StageCfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
+  static constexpr int STAGE_BYTES = X3 ? 2 * (A_BYTES + B_BYTES) : (A_BYTES + B_BYTES);
+  static constexpr int STAGES = X3 ? (BN <= 64 ? 4 : 3) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4));
+  static constexpr int THREADS = X3 ? 320 : 192;
+  static constexpr int TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * 2 * BN * 4 /*scale,bias x2 buffers*/ +
-                                    (2 * STAGES + 4) * 8 /*barriers*/ + 16 /*tmem ptr*/ + 1024 /*align slack*/;
+                                    (3 * STAGES + 4) * 8 /*barriers*/ + 16 /*tmem ptr*/ + 1024 /*align slack*/;
 };
 
 struct GemmKParams {
@@ -65,6 +68,8 @@ struct GemmKParams {
   int res_ld, res_mod, res_f32, relu;
   void* out;
   int out_ld;
+  int round_out;       // fp32 storage: round results to TF32 (consumer is a kind::tf32 MMA)
+  int K;               // X3: column offset of W_lo inside the [N, 2K] weight matrix
 };
 
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -74,12 +79,13 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <typename T, int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <typename T, int BN, bool X3>
+__global__ void __launch_bounds__((StageCfg<BN, X3>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKParams p) {
   using Tr = GemmTraits<T>;
-  using Cfg = StageCfg<BN>;
+  using Cfg = StageCfg<BN, X3>;
+  static_assert(!X3 || sizeof(T) == 4, "3xTF32 needs fp32 storage");
   constexpr int BK = Tr::BK;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -92,7 +98,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* sm_bias = sm_scale + 2 * BN;                                            // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_bias + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* split_bar = empty_bar + STAGES;   // X3 only: A tile has been split into hi / lo
+  uint64_t* tfull_bar = split_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -106,6 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&split_bar[i], 4);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -137,9 +145,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-          mbar_expect_tx(&full_bar[stage], p.a_bytes + Cfg::B_BYTES);
+          mbar_expect_tx(&full_bar[stage], p.a_bytes + (X3 ? 2 : 1) * Cfg::B_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          uint8_t* sb = sa + (X3 ? 2 : 1) * Cfg::A_BYTES;
           if (p.mode == 0) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
           } else {
@@ -150,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 + r - p.pad, img);
           }
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if constexpr (X3) tma_load_2d(sb + Cfg::B_BYTES, &tmB, &full_bar[stage], p.K + kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -168,15 +177,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 3);
+          mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase, 3);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+          const uint64_t bdesc = umma_desc_sw128(sa + (X3 ? 2 : 1) * Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
             umma_ss<Tr::kTf32>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (X3) {
+            const uint64_t alo = umma_desc_sw128(sa + Cfg::A_BYTES);
+            const uint64_t blo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_d, alo + 2u * k, bdesc + 2u * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_d, adesc + 2u * k, blo + 2u * k, idesc, 1u);
           }
           tc_commit(&empty_bar[stage]);                        // smem slot reusable once these MMAs retire
           if (kb == p.num_kb - 1) tc_commit(&tfull_bar[buf]);  // accumulator complete
@@ -185,6 +202,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
+  } else if (X3 && warp >= 6) {
+    // ------------------------------------------------------------------ X3: split the A tile in place (4 warps)
+    const int st = threadIdx.x - 192;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 5);
+        float4* a = reinterpret_cast<float4*>(smem + stage * Cfg::STAGE_BYTES);
+        float4* lo = a + Cfg::A_BYTES / 16;
+#pragma unroll
+        for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
+          const float4 v = a[st + i * 128];
+          const float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+          a[st + i * 128] = h;                                                   // A_hi: exactly TF32
+          lo[st + i * 128] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);  // A_lo: the remainder
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -275,7 +315,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(op + j) =
-                  make_float4(rna_tf32(f[j]), rna_tf32(f[j + 1]), rna_tf32(f[j + 2]), rna_tf32(f[j + 3]));
+                  p.round_out ? make_float4(rna_tf32(f[j]), rna_tf32(f[j + 1]), rna_tf32(f[j + 2]), rna_tf32(f[j + 3]))
+                              : make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_ld + ncol;
 #pragma unroll
@@ -350,12 +391,12 @@ std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, con
   return "";
 }
 
-template <typename T, int BN>
+template <typename T, int BN, bool X3>
 std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap& tmA, const CUtensorMap& tmB,
                      int num_sms, cudaStream_t stream) {
-  using Cfg = StageCfg<BN>;
+  using Cfg = StageCfg<BN, X3>;
   static bool attr_set = false;
-  auto kfn = gemm_tc_kernel<T, BN>;
+  auto kfn = gemm_tc_kernel<T, BN, X3>;
   if (!attr_set) {
     SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
@@ -364,7 +405,7 @@ std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap
   const int grid = tiles < num_sms ? tiles : num_sms;
   {
     ProfScope ps(kFamGemm, stream);
-    kfn<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+    kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
   }
   SPE_CUDA_TRY(cudaGetLastError());
   (void)d;
@@ -378,9 +419,16 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   const int BK = 128 / es;
   if (d.N % 32 != 0) return "gemm: N must be a multiple of 32";
   if (d.out_ld % (16 / es) != 0) return "gemm: out_ld must keep rows 16-byte aligned";
-  const int BN = d.N <= 64 ? 64 : 128;
+  if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
+  if (d.x3 && d.mode != 0) return "gemm: 3xTF32 is only built for plain matrices";
+  const long long m_tiles_est = d.mode == 0 ? (d.M + BM - 1) / BM : static_cast<long long>(d.NB) * ((d.H * d.W + BM - 1) / BM);
+  int BN = d.N <= 64 ? 64 : 128;
+  // wide tiles halve the A re-reads (L2 -> SM bandwidth is what bounds fp32-operand GEMMs) when there are still
+  // enough tiles to fill the machine
+  if (!d.x3 && d.N % 256 == 0 && m_tiles_est * (d.N / 256) >= num_sms) BN = 256;
 
   GemmKParams kp{};
+  kp.round_out = d.round_out;
   kp.mode = d.mode;
   kp.N = d.N;
   kp.scale = d.scale;
@@ -435,20 +483,28 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     if (!err.empty()) return err;
   }
   kp.num_kb = K / BK;
+  kp.K = K;
   {
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.N)};
-    cuuint64_t str[1] = {static_cast<cuuint64_t>(K) * es};
+    const int kw = d.x3 ? 2 * K : K;   // X3 weights: [N, 2K] = [W_hi | W_lo]
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kw), static_cast<cuuint64_t>(d.N)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(kw) * es};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(BN)};
     err = encode_map(&tmB, dt, 2, d.Wt, dims, str, box);
     if (!err.empty()) return err;
   }
 
   if (dt == kTF32) {
-    if (BN == 64) return launch_t<float, 64>(d, kp, tmA, tmB, num_sms, stream);
-    return launch_t<float, 128>(d, kp, tmA, tmB, num_sms, stream);
+    if (d.x3) {
+      if (BN == 64) return launch_t<float, 64, true>(d, kp, tmA, tmB, num_sms, stream);
+      return launch_t<float, 128, true>(d, kp, tmA, tmB, num_sms, stream);
+    }
+    if (BN == 64) return launch_t<float, 64, false>(d, kp, tmA, tmB, num_sms, stream);
+    if (BN == 128) return launch_t<float, 128, false>(d, kp, tmA, tmB, num_sms, stream);
+    return launch_t<float, 256, false>(d, kp, tmA, tmB, num_sms, stream);
   } else {
-    if (BN == 64) return launch_t<__nv_bfloat16, 64>(d, kp, tmA, tmB, num_sms, stream);
-    return launch_t<__nv_bfloat16, 128>(d, kp, tmA, tmB, num_sms, stream);
+    if (BN == 64) return launch_t<__nv_bfloat16, 64, false>(d, kp, tmA, tmB, num_sms, stream);
+    if (BN == 128) return launch_t<__nv_bfloat16, 128, false>(d, kp, tmA, tmB, num_sms, stream);
+    return launch_t<__nv_bfloat16, 256, false>(d, kp, tmA, tmB, num_sms, stream);
   }
 }
 

@@ -14,12 +14,14 @@
 // Identity used for the positional terms: (x + pos) W^T + b = x W^T + (pos W^T + b); the bracket is constant per
 // token position, computed once at weight-load time in fp32 and added by the GEMM epilogue (row % tokens).
 #include "spe_internal.h"
+#include "profile.h"
 #include "../../include/spe.h"
 
 #include <cuda_bf16.h>
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -38,6 +40,19 @@ __global__ void f32_to_tf32_kernel(const float* __restrict__ in, float* __restri
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i]));
     out[i] = __uint_as_float(r);
   }
+}
+// [N,K] fp32 -> [N,2K] = [rna(W) | rna(W - rna(W))] for the error-compensated 3xTF32 GEMM
+__global__ void f32_split_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int K) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+  const float w = in[i];
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w));
+  const float hi = __uint_as_float(r);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w - hi));
+  out[static_cast<long long>(n) * 2 * K + k] = hi;
+  out[static_cast<long long>(n) * 2 * K + K + k] = __uint_as_float(r);
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -78,6 +93,7 @@ struct GemmW {          // one GEMM's parameters on the device
   float* scale = nullptr;
   float* bias = nullptr;
   int N = 0, K = 0;
+  int x3 = 0;           // weights stored as [N, 2K] = [W_hi | W_lo] (3xTF32)
 };
 
 struct Bottleneck {
@@ -102,6 +118,20 @@ struct DecLayer {
 }  // namespace spe
 
 using namespace spe;
+
+struct GraphKey {
+  int B;
+  const void *images, *logits, *points, *logsig, *aux_l, *aux_p;
+  bool operator==(const GraphKey& o) const {
+    return B == o.B && images == o.images && logits == o.logits && points == o.points && logsig == o.logsig &&
+           aux_l == o.aux_l && aux_p == o.aux_p;
+  }
+};
+struct GraphEntry {
+  GraphKey key{};
+  cudaGraphExec_t exec = nullptr;
+  long long launches[kNumFamilies] = {0, 0, 0, 0, 0, 0};
+};
 
 struct spe_ctx {
   spe_config cfg{};
@@ -144,6 +174,11 @@ struct spe_ctx {
   double *p_quat = nullptr, *p_tvec = nullptr;
   int32_t *p_assign = nullptr, *p_status = nullptr;
   const float *ov_logits = nullptr, *ov_points = nullptr;   // bench hook, see spe_debug_set_pnp_override
+
+  // forward schedule
+  bool use_graphs = true;
+  int sub_batch = 0;                 // 0 = automatic (L2-sized chunks)
+  std::vector<GraphEntry> graphs;
 
   // debug taps
   bool taps_enabled = false;
@@ -191,16 +226,20 @@ static std::string upload_f32(spe_ctx* ctx, const float* host, long long n, floa
 }
 
 // upload a host fp32 [N,K] matrix as GEMM weights in the storage dtype (tf32-rounded fp32 or bf16)
-static std::string upload_gemm_w(spe_ctx* ctx, const std::vector<float>& host, int N, int K, GemmW* g) {
+static std::string upload_gemm_w(spe_ctx* ctx, const std::vector<float>& host, int N, int K, GemmW* g,
+                                 bool x3 = false) {
   float* tmp = nullptr;
   const long long n = static_cast<long long>(N) * K;
+  x3 = x3 && ctx->dt == kTF32;   // bf16 storage has its own (looser) accuracy contract
   SPE_CUDA_TRY(cudaMalloc(&tmp, static_cast<size_t>(n) * sizeof(float)));
   cudaError_t e = cudaMemcpy(tmp, host.data(), static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(tmp); return std::string("upload weights: ") + cudaGetErrorString(e); }
-  std::string s = dmalloc_bytes(ctx, &g->w, n * static_cast<long long>(dtype_size(ctx->dt)));
+  std::string s = dmalloc_bytes(ctx, &g->w, (x3 ? 2 : 1) * n * static_cast<long long>(dtype_size(ctx->dt)));
   if (!s.empty()) { cudaFree(tmp); return s; }
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-  if (ctx->dt == kTF32) f32_to_tf32_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<float*>(g->w), n);
+  g->x3 = x3 ? 1 : 0;
+  if (x3) f32_split_tf32_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<float*>(g->w), N, K);
+  else if (ctx->dt == kTF32) f32_to_tf32_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<float*>(g->w), n);
   else f32_to_bf16_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<__nv_bfloat16*>(g->w), n);
   e = cudaDeviceSynchronize();
   cudaFree(tmp);
@@ -274,11 +313,12 @@ static std::string load_conv_bn(spe_ctx* ctx, WeightSource& ws, const std::strin
   return "";
 }
 
-static std::string load_linear(spe_ctx* ctx, WeightSource& ws, const std::string& p, int out_f, int in_f, GemmW* g) {
+static std::string load_linear(spe_ctx* ctx, WeightSource& ws, const std::string& p, int out_f, int in_f, GemmW* g,
+                               bool x3 = false) {
   const HostTensor* w = ws.get(p + ".weight", {out_f, in_f});
   const HostTensor* b = ws.get(p + ".bias", {out_f});
   if (!w || !b) return ws.missing;
-  TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + w->numel()), out_f, in_f, g));
+  TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + w->numel()), out_f, in_f, g, x3));
   TRY_S(upload_f32(ctx, b->data, out_f, &g->bias));
   return "";
 }
@@ -327,17 +367,17 @@ static std::string make_addend(spe_ctx* ctx, const float* X_dev, int T, int K, c
 }
 
 static std::string load_mha_self(spe_ctx* ctx, WeightSource& ws, const std::string& p, const float* posX_dev, int T,
-                                 GemmW* qkv, GemmW* out, float** addend) {
+                                 GemmW* qkv, GemmW* out, float** addend, bool x3 = false) {
   const int E = 256;
   const HostTensor* w = ws.get(p + ".in_proj_weight", {3 * E, E});
   const HostTensor* b = ws.get(p + ".in_proj_bias", {3 * E});
   if (!w || !b) return ws.missing;
-  TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + w->numel()), 3 * E, E, qkv));
+  TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + w->numel()), 3 * E, E, qkv, x3));
   TRY_S(dmalloc(ctx, addend, static_cast<long long>(T) * 3 * E));
   // q and k see (x + pos); v sees x only
   TRY_S(make_addend(ctx, posX_dev, T, E, w->data, b->data, 2 * E, *addend, 3 * E, 0));
   TRY_S(make_addend(ctx, nullptr, T, E, w->data + 2 * E * E, b->data + 2 * E, E, *addend, 3 * E, 2 * E));
-  TRY_S(load_linear(ctx, ws, p + ".out_proj", E, E, out));
+  TRY_S(load_linear(ctx, ws, p + ".out_proj", E, E, out, x3));
   return "";
 }
 
@@ -410,12 +450,14 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
     for (int i = 0; i < LD; ++i) {
       DecLayer& L = ctx->dec[i];
       const std::string p = "transformer.decoder.layers." + std::to_string(i);
-      TRY_S(load_mha_self(ctx, ws, p + ".self_attn", qe_dev, Q, &L.sa_qkv, &L.sa_out, &L.sa_addend));
+      // the decoder and the heads run as 3xTF32: their rounding error dominates the keypoint error budget (0.5 px at
+      // crop sides up to 1748 px), while they are < 6 % of the FLOPs
+      TRY_S(load_mha_self(ctx, ws, p + ".self_attn", qe_dev, Q, &L.sa_qkv, &L.sa_out, &L.sa_addend, true));
       const HostTensor* w = ws.get(p + ".multihead_attn.in_proj_weight", {3 * E, E});
       const HostTensor* bb = ws.get(p + ".multihead_attn.in_proj_bias", {3 * E});
       if (!w || !bb) return ws.missing;
       // query projection: (tgt + query_pos) Wq^T + bq
-      TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + E * E), E, E, &L.ca_q));
+      TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + E * E), E, E, &L.ca_q, true));
       TRY_S(dmalloc(ctx, &L.ca_q_addend, static_cast<long long>(Q) * E));
       TRY_S(make_addend(ctx, qe_dev, Q, E, w->data, bb->data, E, L.ca_q_addend, E, 0));
       // key/value projections of every layer share the encoder memory: stack them into one GEMM
@@ -424,9 +466,9 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
                         i * 2 * E));
       TRY_S(make_addend(ctx, nullptr, T, E, w->data + 2 * E * E, bb->data + 2 * E, E, ctx->ca_kv_addend,
                         LD * 2 * E, i * 2 * E + E));
-      TRY_S(load_linear(ctx, ws, p + ".multihead_attn.out_proj", E, E, &L.ca_out));
-      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1));
-      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2));
+      TRY_S(load_linear(ctx, ws, p + ".multihead_attn.out_proj", E, E, &L.ca_out, true));
+      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1, true));
+      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2, true));
       TRY_S(load_vec(ctx, ws, p + ".norm1.weight", E, &L.n1g));
       TRY_S(load_vec(ctx, ws, p + ".norm1.bias", E, &L.n1b));
       TRY_S(load_vec(ctx, ws, p + ".norm2.weight", E, &L.n2g));
@@ -434,7 +476,7 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(load_vec(ctx, ws, p + ".norm3.weight", E, &L.n3g));
       TRY_S(load_vec(ctx, ws, p + ".norm3.bias", E, &L.n3b));
     }
-    TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all));
+    TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all, true));
     TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.weight", E, &ctx->dn_g));
     TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.bias", E, &ctx->dn_b));
     // ---- heads
@@ -442,15 +484,15 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
     if (!cw) return ws.missing;
     TRY_S(upload_f32(ctx, cw->data, 12 * E, &ctx->cls_w));
     TRY_S(load_vec(ctx, ws, "cls_embed.bias", 12, &ctx->cls_b));
-    TRY_S(load_linear(ctx, ws, "point_embed.layers.0", E, E, &ctx->pt0));
-    TRY_S(load_linear(ctx, ws, "point_embed.layers.1", E, E, &ctx->pt1));
+    TRY_S(load_linear(ctx, ws, "point_embed.layers.0", E, E, &ctx->pt0, true));
+    TRY_S(load_linear(ctx, ws, "point_embed.layers.1", E, E, &ctx->pt1, true));
     const HostTensor* p2 = ws.get("point_embed.layers.2.weight", {2, E});
     if (!p2) return ws.missing;
     TRY_S(upload_f32(ctx, p2->data, 2 * E, &ctx->pt2_w));
     TRY_S(load_vec(ctx, ws, "point_embed.layers.2.bias", 2, &ctx->pt2_b));
     if (c.has_sigma) {
-      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.0", E, E, &ctx->sg0));
-      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.1", E, E, &ctx->sg1));
+      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.0", E, E, &ctx->sg0, true));
+      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.1", E, E, &ctx->sg1, true));
       const HostTensor* s2 = ws.get("sigma_embed.layers.2.weight", {1, E});
       if (!s2) return ws.missing;
       TRY_S(upload_f32(ctx, s2->data, E, &ctx->sg2_w));
@@ -563,6 +605,8 @@ struct Fwd {
     d.residual = residual; d.res_ld = res_ld; d.res_mod = res_mod; d.res_f32 = res_f32;
     d.relu = relu ? 1 : 0;
     d.out = out; d.out_ld = out_ld;
+    d.x3 = w.x3;
+    d.round_out = w.x3 ? 0 : 1;   // 3xTF32 chains keep full fp32 activations
     return launch_gemm(dt, d, ctx->num_sms, st);
   }
   // 3x3 / stride 1 / pad 1 convolution as implicit GEMM
@@ -577,8 +621,9 @@ struct Fwd {
     return launch_gemm(dt, d, ctx->num_sms, st);
   }
   std::string attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int Lq,
-                   int Lk) {
+                   int Lk, int exact_out = 0) {
     AttnDesc a;
+    a.exact_out = exact_out;
     a.q = q; a.k = k; a.v = v; a.out = out;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = 256;
     a.bsq = static_cast<long long>(Lq) * ldq; a.bsk = static_cast<long long>(Lk) * ldk;
@@ -594,8 +639,10 @@ struct Fwd {
 
 }  // namespace
 
-std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits, float* points, float* logsig,
-                         float* aux_logits, float* aux_points, cudaStream_t st) {
+// backbone + neck + input_proj + encoder for `B` images starting at `images`; the encoder output (memory) of those
+// images is left in Xc ([B * tokens, 256]).  Every other buffer is the shared scratch region, so consecutive chunks
+// reuse the same cache lines (the whole working set of a chunk is sized to stay L2-resident).
+static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void* Xc, cudaStream_t st) {
   const spe_config& c = ctx->cfg;
   Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
   const int R = c.input_size;
@@ -662,23 +709,36 @@ std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits
   } else {
     feat = ctx->L3OUT;
   }
-  TRY_S(f.gemm(feat, Bl * T, ctx->input_proj, ctx->X, 256, false));
-  TRY_S(f.tap("input_proj", ctx->X, Bl * T * 256));
+  TRY_S(f.gemm(feat, Bl * T, ctx->input_proj, Xc, 256, false));
+  TRY_S(f.tap("input_proj", Xc, Bl * T * 256));
 
   // ---- encoder
   const int Ti = static_cast<int>(T);
   for (int i = 0; i < c.enc_layers; ++i) {
     const EncLayer& L = ctx->enc[i];
-    TRY_S(f.gemm(ctx->X, Bl * T, L.qkv, ctx->QKV, 768, false, L.addend, 768, Ti, 1));
+    TRY_S(f.gemm(Xc, Bl * T, L.qkv, ctx->QKV, 768, false, L.addend, 768, Ti, 1));
     TRY_S(f.attn(ctx->QKV, 768, f.col(ctx->QKV, 256), 768, f.col(ctx->QKV, 512), 768, ctx->ATT, Ti, Ti));
-    TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, ctx->X, 256));
-    TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, ctx->X));
-    TRY_S(f.gemm(ctx->X, Bl * T, L.ff1, ctx->HID, c.dim_feedforward, true));
-    TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, ctx->X, 256));
-    TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, ctx->X));
+    TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256));
+    TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc));
+    TRY_S(f.gemm(Xc, Bl * T, L.ff1, ctx->HID, c.dim_feedforward, true));
+    TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, Xc, 256));
+    // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: keep it unrounded
+    TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, i == c.enc_layers - 1 ? 1 : 0));
     const std::string nm = "enc" + std::to_string(i);
-    TRY_S(f.tap(nm.c_str(), ctx->X, Bl * T * 256));
+    TRY_S(f.tap(nm.c_str(), Xc, Bl * T * 256));
   }
+
+  return "";
+}
+
+// cross-attention K/V of all layers, decoder, heads for the whole batch
+static std::string forward_tail(spe_ctx* ctx, int B, float* logits, float* points, float* logsig, float* aux_logits,
+                                float* aux_points, cudaStream_t st) {
+  const spe_config& c = ctx->cfg;
+  Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
+  const long long Bl = B;
+  const long long T = ctx->tokens;
+  const int Ti = static_cast<int>(T);
 
   // ---- decoder
   const int Q = c.num_queries, LD = c.dec_layers;
@@ -689,16 +749,16 @@ std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits
   for (int i = 0; i < LD; ++i) {
     const DecLayer& L = ctx->dec[i];
     TRY_S(f.gemm(ctx->TGT, MQ, L.sa_qkv, ctx->DQKV, 768, false, L.sa_addend, 768, Q, 1));
-    TRY_S(f.attn(ctx->DQKV, 768, f.col(ctx->DQKV, 256), 768, f.col(ctx->DQKV, 512), 768, ctx->DATT, Q, Q));
+    TRY_S(f.attn(ctx->DQKV, 768, f.col(ctx->DQKV, 256), 768, f.col(ctx->DQKV, 512), 768, ctx->DATT, Q, Q, 1));
     TRY_S(f.gemm(ctx->DATT, MQ, L.sa_out, ctx->TGT2, 256, false, ctx->TGT, 256));
-    TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT));
+    TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT, 1));
     TRY_S(f.gemm(ctx->TGT, MQ, L.ca_q, ctx->DQ, 256, false, L.ca_q_addend, 256, Q, 1));
-    TRY_S(f.attn(ctx->DQ, 256, f.col(ctx->KV, i * 512), kvld, f.col(ctx->KV, i * 512 + 256), kvld, ctx->DATT, Q, Ti));
+    TRY_S(f.attn(ctx->DQ, 256, f.col(ctx->KV, i * 512), kvld, f.col(ctx->KV, i * 512 + 256), kvld, ctx->DATT, Q, Ti, 1));
     TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, ctx->TGT, 256));
-    TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT));
+    TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT, 1));
     TRY_S(f.gemm(ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
     TRY_S(f.gemm(ctx->DHID, MQ, L.ff2, ctx->TGT2, 256, false, ctx->TGT, 256));
-    TRY_S(f.ln(ctx->TGT2, L.n3g, L.n3b, MQ, ctx->TGT));
+    TRY_S(f.ln(ctx->TGT2, L.n3g, L.n3b, MQ, ctx->TGT, 1));
     TRY_S(f.ln(ctx->TGT, ctx->dn_g, ctx->dn_b, MQ, f.col(ctx->HS, static_cast<long long>(i) * MQ * 256), 1));
   }
   TRY_S(f.tap("hs", ctx->HS, static_cast<long long>(LD) * MQ * 256));
@@ -725,6 +785,80 @@ std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits
                             st));
   }
   return "";
+}
+
+static int chunk_images(const spe_ctx* ctx, int B) {
+  if (ctx->taps_enabled) return B;                       // taps describe whole-batch tensors
+  if (ctx->sub_batch > 0) return ctx->sub_batch < B ? ctx->sub_batch : B;
+  // largest per-image activation of the trunk: FFN hidden [tokens, d_ff] and layer1 output [R/4, R/4, 256]
+  const long long es = static_cast<long long>(dtype_size(ctx->dt));
+  const long long r4 = ctx->cfg.input_size / 4;
+  const long long per_img = std::max(static_cast<long long>(ctx->tokens) * ctx->cfg.dim_feedforward, r4 * r4 * 256) * es;
+  long long sb = (56ll << 20) / per_img;                 // keep producer->consumer tensors well inside the 126 MB L2
+  if (sb < 4) sb = 4;
+  return sb < B ? static_cast<int>(sb) : B;
+}
+
+static std::string forward_schedule(spe_ctx* ctx, const float* images, int B, float* logits, float* points,
+                                    float* logsig, float* aux_logits, float* aux_points, cudaStream_t st) {
+  const long long es = static_cast<long long>(dtype_size(ctx->dt));
+  const long long img_elems = 3ll * ctx->cfg.input_size * ctx->cfg.input_size;
+  const int SB = chunk_images(ctx, B);
+  for (int c0 = 0; c0 < B; c0 += SB) {
+    const int nb = (B - c0) < SB ? (B - c0) : SB;
+    void* Xc = static_cast<uint8_t*>(ctx->X) + static_cast<long long>(c0) * ctx->tokens * 256 * es;
+    TRY_S(forward_trunk(ctx, images + c0 * img_elems, nb, Xc, st));
+  }
+  return forward_tail(ctx, B, logits, points, logsig, aux_logits, aux_points, st);
+}
+
+// The schedule is a fixed sequence of ~150-600 launches: after one eager run per (batch, buffer set) it is captured
+// into a CUDA graph and replayed, which removes the per-launch CPU cost (tensor-map encodes, launch calls).
+std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits, float* points, float* logsig,
+                         float* aux_logits, float* aux_points, cudaStream_t st) {
+  const bool graphs_ok = ctx->use_graphs && !ctx->taps_enabled && !profile_timing_enabled();
+  if (!graphs_ok) return forward_schedule(ctx, images, B, logits, points, logsig, aux_logits, aux_points, st);
+  GraphKey key{B, images, logits, points, logsig, aux_logits, aux_points};
+  for (auto& g : ctx->graphs) {
+    if (!(g.key == key)) continue;
+    if (g.exec == nullptr) {
+      // second call with this key: capture
+      long long before[kNumFamilies];
+      profile_peek_launches(before);
+      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) { ctx->use_graphs = false; cudaGetLastError(); break; }
+      std::string s = forward_schedule(ctx, images, B, logits, points, logsig, aux_logits, aux_points, st);
+      cudaGraph_t graph = nullptr;
+      e = cudaStreamEndCapture(st, &graph);
+      if (!s.empty() || e != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->use_graphs = false;
+        if (!s.empty()) return s;
+        break;
+      }
+      e = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { g.exec = nullptr; ctx->use_graphs = false; cudaGetLastError(); break; }
+      long long after[kNumFamilies];
+      profile_peek_launches(after);
+      for (int i = 0; i < kNumFamilies; ++i) g.launches[i] = after[i] - before[i];
+      profile_add_launches(g.launches, -1);   // the capture pass itself launched nothing
+    }
+    SPE_CUDA_TRY(cudaGraphLaunch(g.exec, st));
+    profile_add_launches(g.launches, 1);
+    return "";
+  }
+  if (ctx->use_graphs) {
+    if (ctx->graphs.size() >= 8) {               // bounded cache: drop the oldest
+      if (ctx->graphs.front().exec) cudaGraphExecDestroy(ctx->graphs.front().exec);
+      ctx->graphs.erase(ctx->graphs.begin());
+    }
+    GraphEntry ge;
+    ge.key = key;
+    ctx->graphs.push_back(ge);
+  }
+  return forward_schedule(ctx, images, B, logits, points, logsig, aux_logits, aux_points, st);   // first call: eager
 }
 
 }  // namespace spe
@@ -774,6 +908,8 @@ int spe_create(const spe_config* cfg, int device, spe_ctx** out) {
   ctx->featH = featH;
   ctx->tokens = featH * featH;
   ctx->featC = cfg->backbone == 0 ? 512 : 1024;
+  if (const char* e = getenv("SPE_NO_GRAPH")) ctx->use_graphs = !(e[0] == '1');
+  if (const char* e = getenv("SPE_SUBBATCH")) ctx->sub_batch = atoi(e);
   std::string s = alloc_workspace(ctx);
   if (!s.empty()) {
     fail(nullptr, SPE_ERR_CUDA, "spe_create: " + s);
@@ -787,6 +923,8 @@ int spe_create(const spe_config* cfg, int device, spe_ctx** out) {
 void spe_destroy(spe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->frames_dev) cudaFree(ctx->frames_dev);
   delete ctx;
@@ -805,6 +943,9 @@ int spe_load_weights(spe_ctx* ctx, const spe_tensor_desc* tensors, int n) {
     ws.t[tensors[i].name] = t;
   }
   // NB: re-loading leaks the previous device weights until spe_destroy (weights are loaded once per ctx in practice)
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->graphs.clear();               // captured launches point at the previous weights
   std::string s = load_weights_impl(ctx, ws);
   if (!s.empty()) return fail(ctx, SPE_ERR_WEIGHTS, "spe_load_weights: " + s);
   ctx->weights_loaded = true;

@@ -19,6 +19,8 @@
 #include "spe_internal.h"
 #include "profile.h"
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace spe {
 
@@ -439,6 +441,7 @@ assign_pnp_kernel(const PnpDesc d) {
   const float bw = static_cast<float>(d.boxes[img * 4 + 2] - bx1);
   const float bh = static_cast<float>(d.boxes[img * 4 + 3] - by1);
 
+  const long long t_start = clock64();
   if (warp == 0) {
     // ---- PostProcess + find_index, one query per lane per pass; per-label running best (score desc, query asc)
     float best_s[11];
@@ -531,6 +534,7 @@ assign_pnp_kernel(const PnpDesc d) {
   };
   if (n < 4) { write_out(1); return; }  // cv2.solvePnPRansac raises -> caller records the zero pose
 
+  const long long t_assign = clock64();
   // ---- exhaustive minimal-sample consensus: triple #c goes to thread c % 128
   Hyp best;
   best.cnt = 0; best.err = 1e300; best.mask = 0u;
@@ -564,6 +568,7 @@ assign_pnp_kernel(const PnpDesc d) {
   }
   __syncthreads();
   if (warp != 0) return;
+  const long long t_cons = clock64();
   int bw_ = 0;
   for (int w = 1; w < 4; ++w)
     if (s_bcnt[w] > s_bcnt[bw_] || (s_bcnt[w] == s_bcnt[bw_] && s_berr[w] < s_berr[bw_])) bw_ = w;
@@ -597,6 +602,9 @@ assign_pnp_kernel(const PnpDesc d) {
     ok = lm_refine(R, t, o, kFx, kCx, kFy, kCy, 0.0, n, s_J, s_A);
   }
   if (!ok) { inl_mask = 0u; write_out(2); return; }
+  if (d.debug_timing && img < 4 && lane == 0)
+    printf("[spe pnp] img %d n=%d cycles: assign %lld consensus %lld lm %lld\n", img, n, t_assign - t_start,
+           t_cons - t_assign, clock64() - t_cons);
 
   // ---- self-assessment statistics: inlier RMS reprojection error (pixels), mean predicted sigma (pixels)
   double e2 = 0.0, sg = 0.0;
@@ -628,7 +636,10 @@ std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s) {
   if (d.B <= 0) return "";
   if (d.Q <= 0 || d.Q > 4096) return "assign_pnp: bad query count";
   ProfScope ps(kFamPnp, s);
-  assign_pnp_kernel<<<d.B, kPnpThreads, 0, s>>>(d);
+  PnpDesc dd = d;
+  static const bool timing = getenv("SPE_PNP_TIMING") != nullptr;
+  dd.debug_timing = timing ? 1 : 0;
+  assign_pnp_kernel<<<d.B, kPnpThreads, 0, s>>>(dd);
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
 }

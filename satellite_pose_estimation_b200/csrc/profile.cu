@@ -29,6 +29,13 @@ ProfScope::~ProfScope() {
 }
 
 void profile_enable(bool on) { g_timing.store(on); }
+bool profile_timing_enabled() { return g_timing.load(); }
+void profile_peek_launches(long long* out) {
+  for (int i = 0; i < kNumFamilies; ++i) out[i] = g_launches[i].load();
+}
+void profile_add_launches(const long long* n, int sign) {
+  for (int i = 0; i < kNumFamilies; ++i) g_launches[i].fetch_add(sign * n[i]);
+}
 
 void profile_collect(double* ms, long long* launches) {
   for (int i = 0; i < kNumFamilies; ++i) {

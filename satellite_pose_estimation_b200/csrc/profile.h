@@ -16,6 +16,10 @@ struct ProfScope {
 };
 
 void profile_enable(bool on);
+bool profile_timing_enabled();
+void profile_peek_launches(long long* launches_by_family);
+// account for kernels launched through a replayed CUDA graph (sign = +1) or undo capture-time counting (-1)
+void profile_add_launches(const long long* launches_by_family, int sign);
 // sums event-timed milliseconds and launch counts per family since the last collect; synchronises the events
 void profile_collect(double* ms_by_family, long long* launches_by_family);
 

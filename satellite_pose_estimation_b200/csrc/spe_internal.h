@@ -35,6 +35,8 @@ struct GemmDesc {
   int relu = 0;
   void* out = nullptr;            // [M, out_ld] storage dtype
   int out_ld = 0;
+  int round_out = 1;              // fp32 storage: round the result to TF32 (its consumer is a kind::tf32 MMA)
+  int x3 = 0;                     // error-compensated 3xTF32: Wt is [N, 2K] = [W_hi | W_lo]; fp32-grade accuracy
 };
 
 // returns empty string on success, else an error message
@@ -59,6 +61,7 @@ struct AttnDesc {
   void* out; int ldo; long long bso;
   int B, heads, Lq, Lk;                         // head_dim fixed at 32
   float scale;                                  // 1/sqrt(head_dim)
+  int exact_out = 0;                            // fp32 storage: do not round the output to TF32
 };
 std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s);
 
@@ -92,6 +95,7 @@ struct PnpDesc {
   float* points_px;      // [B,Q,2] or null: keypoints in original-image pixels
   float* sigmas;         // [B,Q,2] or null: exp(logsig)
   int32_t* inlier_mask;  // [B] bit i = label i used in the final refinement, or null
+  int debug_timing;      // print per-phase cycle counts of the first images (SPE_PNP_TIMING)
 };
 std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s);
 

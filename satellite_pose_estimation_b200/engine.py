@@ -43,6 +43,8 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.spe_create(C.byref(self.cfg), self.device.index, C.byref(self._ctx)))
         self.weights_loaded = False
+        self._fwd_bufs = {}
+        self._stable_inputs = set()
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
@@ -99,21 +101,38 @@ class Engine:
 
     # ---- stage 2 ---------------------------------------------------------------------------------------------
     def forward(self, images, want_aux=False):
-        """images float32 cuda [B,3,R,R] -> dict of float32 cuda tensors (reference output layout)."""
+        """images float32 cuda [B,3,R,R] -> dict of float32 cuda tensors (reference output layout).
+
+        Inputs are staged into, and outputs returned from, per-batch-size persistent buffers (stable addresses let
+        libspe replay the captured CUDA graph): the returned tensors are overwritten by the next ``forward`` call
+        with the same batch size -- clone them if they must outlive it."""
         assert images.is_cuda and images.dtype == torch.float32
-        images = images.contiguous()
         B = images.shape[0]
         if images.shape[1:] != (3, self.R, self.R):
             raise ValueError(f"expected images [B,3,{self.R},{self.R}], got {tuple(images.shape)}")
         dev = images.device
-        logits = torch.empty((B, self.Q, 12), dtype=torch.float32, device=dev)
-        points = torch.empty((B, self.Q, 2), dtype=torch.float32, device=dev)
-        logsig = torch.empty((B, self.Q, 2), dtype=torch.float32, device=dev) if self.has_sigma else None
-        aux_l = aux_p = None
-        if want_aux and self.L > 1:
-            aux_l = torch.empty((self.L - 1, B, self.Q, 12), dtype=torch.float32, device=dev)
-            aux_p = torch.empty((self.L - 1, B, self.Q, 2), dtype=torch.float32, device=dev)
-        check(self.lib.spe_forward(self._ctx, _ptr(images), B, _ptr(logits), _ptr(points), _ptr(logsig), _ptr(aux_l),
+        key = (B, bool(want_aux))
+        bufs = self._fwd_bufs.get(key)
+        if bufs is None:
+            bufs = {"in": torch.empty((B, 3, self.R, self.R), dtype=torch.float32, device=dev),
+                    "logits": torch.empty((B, self.Q, 12), dtype=torch.float32, device=dev),
+                    "points": torch.empty((B, self.Q, 2), dtype=torch.float32, device=dev),
+                    "logsig": torch.empty((B, self.Q, 2), dtype=torch.float32, device=dev) if self.has_sigma else None,
+                    "aux_l": None, "aux_p": None}
+            if want_aux and self.L > 1:
+                bufs["aux_l"] = torch.empty((self.L - 1, B, self.Q, 12), dtype=torch.float32, device=dev)
+                bufs["aux_p"] = torch.empty((self.L - 1, B, self.Q, 2), dtype=torch.float32, device=dev)
+            self._fwd_bufs[key] = bufs
+        if images.data_ptr() != bufs["in"].data_ptr():
+            if images.is_contiguous() and images.data_ptr() in self._stable_inputs:
+                src = images                      # caller-owned persistent buffer (e.g. the crop output)
+            else:
+                bufs["in"].copy_(images)
+                src = bufs["in"]
+        else:
+            src = images
+        logits, points, logsig, aux_l, aux_p = (bufs[k] for k in ("logits", "points", "logsig", "aux_l", "aux_p"))
+        check(self.lib.spe_forward(self._ctx, _ptr(src), B, _ptr(logits), _ptr(points), _ptr(logsig), _ptr(aux_l),
                                    _ptr(aux_p), _stream(dev)), self._ctx)
         out = {"pred_logits": logits, "pred_points": points}
         if logsig is not None:
@@ -121,6 +140,11 @@ class Engine:
         if aux_l is not None:
             out["aux_outputs"] = [{"pred_logits": aux_l[i], "pred_points": aux_p[i]} for i in range(self.L - 1)]
         return out
+
+    def register_stable_input(self, tensor):
+        """Declare a caller-owned, persistent, contiguous input buffer: ``forward`` reads it in place (no staging
+        copy), keeping the CUDA-graph key stable."""
+        self._stable_inputs.add(tensor.data_ptr())
 
     # ---- stage 3 ---------------------------------------------------------------------------------------------
     def assign_pnp(self, logits, points, boxes, log_sigma=None, reproj=20.0, weighted=False, reject=False,

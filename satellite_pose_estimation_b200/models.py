@@ -220,8 +220,14 @@ class B200DETR(nn.Module):
         if self.input_size is not None and R != self.input_size:
             raise ValueError(f"model was built for input_size={self.input_size}, got {R}")
         eng = self._get_engine(dev, R, x.shape[0])
-        outs = [eng.forward(x[i:i + eng.max_batch], want_aux=self.aux_loss)
-                for i in range(0, x.shape[0], eng.max_batch)]
+        def run(chunk):   # engine outputs live in persistent buffers: detach them from the next call
+            o = eng.forward(chunk, want_aux=self.aux_loss)
+            res = {k: v.clone() for k, v in o.items() if k != "aux_outputs"}
+            if "aux_outputs" in o:
+                res["aux_outputs"] = [{k: v.clone() for k, v in a.items()} for a in o["aux_outputs"]]
+            return res
+
+        outs = [run(x[i:i + eng.max_batch]) for i in range(0, x.shape[0], eng.max_batch)]
         if len(outs) == 1:
             out = outs[0]
         else:
