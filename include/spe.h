@@ -125,9 +125,10 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
 int spe_debug_gemm(int dtype, const void* A_dev, const void* W_dev, long long M, int N, int K, const float* scale_dev,
                    const float* bias_dev, const void* residual_dev, int res_mod, int relu, void* out_dev,
                    void* stream);
-/* stride-1 'same' convolution as implicit GEMM: x [NB,H,W,C] NHWC, w [Cout, R*S*C] (tap-major, channel-minor) */
+/* convolution (stride 1 or 2) as implicit GEMM: x [NB,H,W,C] NHWC, w [Cout, R*S*C] (tap-major, channel-minor),
+ * out [NB,Ho,Wo,Cout] with Ho = (H + 2 pad - R) / stride + 1 */
 int spe_debug_conv(int dtype, const void* x_dev, const void* w_dev, int NB, int H, int W, int C, int Cout, int R,
-                   int S, int pad, const float* scale_dev, const float* bias_dev, int relu, void* out_dev,
+                   int S, int pad, int stride, const float* scale_dev, const float* bias_dev, int relu, void* out_dev,
                    void* stream);
 int spe_debug_attention(int dtype, const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int B,
                         int heads, int Lq, int Lk, int ldq, int ldk, int ldv, int ldo, void* stream);

@@ -164,9 +164,10 @@ int spe_debug_gemm(int dtype, const void* A, const void* Wt, long long M, int N,
 }
 
 int spe_debug_conv(int dtype, const void* x, const void* w, int NB, int H, int W, int C, int Cout, int R, int S,
-                   int pad, const float* scale, const float* bias, int relu, void* out, void* stream) {
+                   int pad, int stride, const float* scale, const float* bias, int relu, void* out, void* stream) {
   GemmDesc d;
   d.mode = 1; d.A = x; d.NB = NB; d.H = H; d.W = W; d.C = C; d.R = R; d.S = S; d.pad = pad; d.Wt = w; d.N = Cout;
+  d.conv_stride = stride;
   d.scale = scale; d.bias = bias; d.relu = relu; d.out = out; d.out_ld = Cout;
   std::string s = launch_gemm(dtype == 0 ? kTF32 : kBF16, d, sm_count(), static_cast<cudaStream_t>(stream));
   if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_conv: " + s);

@@ -60,7 +60,7 @@ struct GemmKParams {
   int num_m_tiles, num_n_tiles;
   uint32_t a_bytes;    // bytes one A TMA box delivers
   // conv
-  int HW, W, S, pad, hrows, tiles_per_img, kb_per_tap, H;
+  int HW, W, S, pad, hrows, tiles_per_img, kb_per_tap, H, cstride;   // H, W = OUTPUT extent
   // epilogue
   const float* scale;
   const float* bias;
@@ -155,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int c0 = (kb - tap * p.kb_per_tap) * BK;
             const int r = tap / p.S;
             const int s = tap - r * p.S;
-            tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 + r - p.pad, img);
+            tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
           }
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
           if constexpr (X3) tma_load_2d(sb + Cfg::B_BYTES, &tmB, &full_bar[stage], p.K + kb * BK, n0);
@@ -370,11 +370,14 @@ EncodeTiledFn get_encode_fn(std::string* err) {
 }
 
 std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, const cuuint64_t* dims,
-                       const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box, int spatial_stride = 1) {
   std::string err;
   EncodeTiledFn fn = get_encode_fn(&err);
   if (!fn) return err;
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // traversal stride on the two spatial dims of an NHWC map = the convolution stride (TMA then delivers
+  // ceil(box / stride) elements per dim)
+  cuuint32_t estr[5] = {1, static_cast<cuuint32_t>(spatial_stride), static_cast<cuuint32_t>(spatial_stride), 1, 1};
+  if (rank < 4) estr[1] = estr[2] = 1;
   CUresult r = fn(m, dt == kTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -421,7 +424,9 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.out_ld % (16 / es) != 0) return "gemm: out_ld must keep rows 16-byte aligned";
   if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
   if (d.x3 && d.mode != 0) return "gemm: 3xTF32 is only built for plain matrices";
-  const long long m_tiles_est = d.mode == 0 ? (d.M + BM - 1) / BM : static_cast<long long>(d.NB) * ((d.H * d.W + BM - 1) / BM);
+  const int cs_est = d.conv_stride > 1 ? d.conv_stride : 1;
+  const long long m_tiles_est = d.mode == 0 ? (d.M + BM - 1) / BM
+                                            : static_cast<long long>(d.NB) * (((d.H / cs_est) * (d.W / cs_est) + BM - 1) / BM);
   int BN = d.N <= 64 ? 64 : 128;
   // wide tiles halve the A re-reads (L2 -> SM bandwidth is what bounds fp32-operand GEMMs) when there are still
   // enough tiles to fill the machine
@@ -459,27 +464,33 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     if (!err.empty()) return err;
   } else {
     if (d.C % BK != 0) return "conv: C must be a multiple of the 128-byte k-block";
-    if (d.W > BM) return "conv: W must be <= 128";
+    const int cs = d.conv_stride > 0 ? d.conv_stride : 1;
+    if (cs != 1 && cs != 2) return "conv: stride must be 1 or 2";
+    const int Ho = (d.H + 2 * d.pad - d.R) / cs + 1, Wo = (d.W + 2 * d.pad - d.S) / cs + 1;
+    if (Wo > BM) return "conv: output width must be <= 128";
     K = d.R * d.S * d.C;
-    int hrows = BM / d.W;
-    if (hrows > d.H) hrows = d.H;
+    int hrows = BM / Wo;
+    if (hrows > Ho) hrows = Ho;
+    if (hrows * cs > 256 || Wo * cs > 256) return "conv: TMA box too large";
     kp.hrows = hrows;
-    kp.tiles_per_img = (d.H + hrows - 1) / hrows;
+    kp.tiles_per_img = (Ho + hrows - 1) / hrows;
     kp.num_m_tiles = kp.tiles_per_img * d.NB;
-    kp.M = d.NB * d.H * d.W;
-    kp.HW = d.H * d.W;
-    kp.H = d.H;
-    kp.W = d.W;
+    kp.M = d.NB * Ho * Wo;
+    kp.HW = Ho * Wo;
+    kp.H = Ho;
+    kp.W = Wo;
     kp.S = d.S;
     kp.pad = d.pad;
+    kp.cstride = cs;
     kp.kb_per_tap = d.C / BK;
-    kp.a_bytes = static_cast<uint32_t>(d.W * hrows * 128);
+    kp.a_bytes = static_cast<uint32_t>(Wo * hrows * 128);
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.C), static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H),
                           static_cast<cuuint64_t>(d.NB)};
     cuuint64_t str[3] = {static_cast<cuuint64_t>(d.C) * es, static_cast<cuuint64_t>(d.W) * d.C * es,
                          static_cast<cuuint64_t>(d.H) * d.W * d.C * es};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(d.W), static_cast<cuuint32_t>(hrows), 1};
-    err = encode_map(&tmA, dt, 4, d.A, dims, str, box);
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(Wo * cs),
+                         static_cast<cuuint32_t>(hrows * cs), 1};
+    err = encode_map(&tmA, dt, 4, d.A, dims, str, box, cs);
     if (!err.empty()) return err;
   }
   kp.num_kb = K / BK;

@@ -542,12 +542,32 @@ assign_pnp_kernel(const PnpDesc d) {
   for (int i = 0; i < 9; ++i) best.R[i] = 0.0;
   best.t[0] = best.t[1] = best.t[2] = 0.0;
   const double thr2 = static_cast<double>(d.reproj_thresh) * static_cast<double>(d.reproj_thresh);
-  int c = 0;
-  for (int i0 = 0; i0 < n - 2; ++i0)
-    for (int i1 = i0 + 1; i1 < n - 1; ++i1)
-      for (int i2 = i1 + 1; i2 < n; ++i2, ++c)
-        if ((c & (kPnpThreads - 1)) == static_cast<int>(threadIdx.x))
-          p3p_consensus(i0, i1, i2, n, s_lab, s_uv, s_bear, thr2, best);
+  // Every thread first decodes its own triple index, then all lanes run the solver together: calling it from inside
+  // the enumeration loop would serialise the warp (one active lane per iteration).
+  const int ntriples = n * (n - 1) * (n - 2) / 6;
+  for (int c = static_cast<int>(threadIdx.x); c < ((ntriples + kPnpThreads - 1) / kPnpThreads) * kPnpThreads;
+       c += kPnpThreads) {
+    int i0 = 0, i1 = 1, i2 = 2;
+    if (c < ntriples) {
+      int rem = c;
+      for (i0 = 0; i0 < n - 2; ++i0) {                    // triples starting with i0: C(n-1-i0, 2)
+        const int cnt0 = (n - 1 - i0) * (n - 2 - i0) / 2;
+        if (rem < cnt0) break;
+        rem -= cnt0;
+      }
+      for (i1 = i0 + 1; i1 < n - 1; ++i1) {               // pairs (i1, i2) with i2 > i1: n-1-i1 each
+        const int cnt1 = n - 1 - i1;
+        if (rem < cnt1) break;
+        rem -= cnt1;
+      }
+      i2 = i1 + 1 + rem;
+    }
+    Hyp cand;
+    cand.cnt = 0; cand.err = 1e300; cand.mask = 0u;
+    p3p_consensus(i0, i1, i2, n, s_lab, s_uv, s_bear, thr2, cand);   // lanes beyond ntriples redo triple (0,1,2)
+    if (c < ntriples && (cand.cnt > best.cnt || (cand.cnt == best.cnt && cand.cnt > 0 && cand.err < best.err)))
+      best = cand;
+  }
   __syncwarp();
   // arg-best: more inliers, then lower error, then lower thread index
   int bl = lane, bc = best.cnt;

@@ -11,8 +11,8 @@ enum Dtype : int { kTF32 = 0, kBF16 = 1 };  // storage: fp32 (tf32 MMA) or bf16 
 inline size_t dtype_size(Dtype d) { return d == kTF32 ? 4 : 2; }
 
 // One tensor-core GEMM launch:  out[m, n] = act( scale[n] * sum_k A[m,k] * Wt[n,k] + bias[n] + residual[m', n] )
-// A is either a row-major matrix (mode 0) or an NHWC activation read through R*S shifted taps (mode 1,
-// stride-1 'same' convolution, zero padding supplied by TMA out-of-bounds fill).
+// A is either a row-major matrix (mode 0) or an NHWC activation read through R*S shifted taps (mode 1: stride 1
+// or 2 convolution, zero padding supplied by TMA out-of-bounds fill, stride by the TMA traversal stride).
 struct GemmDesc {
   int mode = 0;
   // mode 0: A[M, K] row-major with leading dimension lda (elements)
@@ -21,7 +21,8 @@ struct GemmDesc {
   int K = 0;
   int lda = 0;
   // mode 1: A = activation [NB, H, W, C]; K = R*S*C; M = NB*H*W
-  int NB = 0, H = 0, W = 0, C = 0, R = 1, S = 1, pad = 0;
+  int NB = 0, H = 0, W = 0, C = 0, R = 1, S = 1, pad = 0;   // H, W = input extent
+  int conv_stride = 1;            // 1 or 2 (TMA traversal stride); output extent = (H + 2 pad - R) / stride + 1
   // weights Wt[N, K] row-major (K contiguous)
   const void* Wt = nullptr;
   int N = 0;

@@ -102,7 +102,7 @@ def run_conv():
             wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()
             bias = torch.randn(Cout, device=DEV)
             out = torch.full((NB, H, H, Cout), float("nan"), device=DEV).to(tdt)
-            rc = lib.spe_debug_conv(dt, _p(x), _p(wk), NB, H, H, C, Cout, 3, 3, 1, None, _p(bias), 1, _p(out), None)
+            rc = lib.spe_debug_conv(dt, _p(x), _p(wk), NB, H, H, C, Cout, 3, 3, 1, 1, None, _p(bias), 1, _p(out), None)
             torch.cuda.synchronize()
             ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1)
             ref = ref.clamp_min(0).permute(0, 2, 3, 1)

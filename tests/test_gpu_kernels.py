@@ -58,10 +58,30 @@ def test_implicit_conv3x3(lib, cuda_dev, dt, NB, H, Cin, Cout):
     wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
     bias = torch.randn(Cout, device=cuda_dev)
     out = torch.full((NB, H, H, Cout), float("nan"), device=cuda_dev).to(tdt)
-    assert lib.spe_debug_conv(dt, _p(x), _p(wk), NB, H, H, Cin, Cout, 3, 3, 1, None, _p(bias), 1, _p(out), None) == 0
+    assert lib.spe_debug_conv(dt, _p(x), _p(wk), NB, H, H, Cin, Cout, 3, 3, 1, 1, None, _p(bias), 1, _p(out), None) == 0
     torch.cuda.synchronize()
     ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1)
     ref = ref.clamp_min(0).permute(0, 2, 3, 1)
+    assert not torch.isnan(out.float()).any()
+    assert _rel(out, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+@pytest.mark.parametrize("NB,H,Cin,Cout,R", [(2, 56, 128, 128, 3), (3, 28, 256, 256, 3), (2, 56, 256, 512, 1),
+                                              (2, 28, 512, 1024, 1), (1, 64, 128, 128, 3)])
+def test_implicit_conv_stride2(lib, cuda_dev, dt, NB, H, Cin, Cout, R):
+    """Stride-2 convolutions (layerN.0.conv2, downsample) through the TMA traversal stride: no im2col buffer."""
+    torch.manual_seed(H * Cin + R)
+    tdt = DT[dt]
+    x = torch.randn(NB, H, H, Cin, device=cuda_dev).to(tdt)
+    w = (torch.randn(Cout, Cin, R, R, device=cuda_dev) / (R * R * Cin) ** 0.5).to(tdt)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, R * R * Cin).contiguous()
+    Ho = (H + 2 * (R // 2) - R) // 2 + 1
+    out = torch.full((NB, Ho, Ho, Cout), float("nan"), device=cuda_dev).to(tdt)
+    assert lib.spe_debug_conv(dt, _p(x), _p(wk), NB, H, H, Cin, Cout, R, R, R // 2, 2, None, None, 0, _p(out), None) == 0
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), stride=2, padding=R // 2)
+    ref = ref.permute(0, 2, 3, 1)
     assert not torch.isnan(out.float()).any()
     assert _rel(out, ref) < TOL[dt]
 
@@ -109,7 +129,7 @@ def test_gemm_3xtf32_reaches_fp32_accuracy(lib, cuda_dev, M, N, K, relu, res_mod
     ref = A.double() @ W.double().t() + bias.double() + (r.repeat(M // rows + 1, 1)[:M] if res_mod else r)
     if relu:
         ref = ref.clamp_min(0)
-    assert _rel(out, ref) < 5e-6
+    assert _rel(out, ref) < 2e-5      # fp32 accumulation over up to 3 x 2048 products; plain TF32 sits at ~5e-4
 
 
 def test_gemm_rejects_bad_shapes(lib, cuda_dev):

@@ -103,9 +103,9 @@ def test_edge_cases(eng):
     assert ok == (r["status"][2] == 0)
     # duplicated label: the higher score wins, ties go to the first query
     d2 = synth.make_predictions(1, seed=4, few_frac=0.0, outlier_frac=0.0)
-    d2["logits"][0, 5] = d2["logits"][0, 9] = np.log(np.r_[0.9, np.full(11, 0.1 / 11)]).astype(np.float32)
+    d2["logits"][0, 5] = d2["logits"][0, 9] = np.log(np.r_[0.999, np.full(11, 0.001 / 11)]).astype(np.float32)
     r2 = _solve(eng, d2)
-    assert r2["assign"][0, 0] == 5
+    assert r2["assign"][0, 0] == 5                      # both beat every synthetic score (<= 0.99); first one wins
 
 
 def test_sigma_weighted_solve_and_reject_filter(eng):
