@@ -87,6 +87,34 @@ stem_im2col_kernel(const float* __restrict__ in, int Hin, int Win, int Ho, int W
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// stem input re-layout: NCHW fp32 [B,3,H,W] -> zero-bordered NHWC [B, H+6, W+6, Cp] with Cp = 16 B / sizeof(T)
+// (3 real channels + zero padding), so that 8 consecutive pixels form one 128-byte K-block that TMA can fetch as an
+// overlapping window (GEMM "stem" mode) -- replaces the 600 MB im2col patch matrix.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_pad_kernel(const float* __restrict__ in, int H, int W, long long total_px, T* __restrict__ out) {
+  constexpr int VN = Vec<T>::N;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_px) return;
+  const int Wp = W + 6, Hp = H + 6;
+  const int x = static_cast<int>(idx % Wp) - 3;
+  const int y = static_cast<int>((idx / Wp) % Hp) - 3;
+  const long long n = idx / (static_cast<long long>(Wp) * Hp);
+  Vec<T> r;
+#pragma unroll
+  for (int e = 0; e < VN; ++e) r.set(e, 0.f);
+  if (x >= 0 && x < W && y >= 0 && y < H) {
+    const float* px = in + (n * 3 * H + y) * W + x;
+    const long long plane = static_cast<long long>(H) * W;
+    r.set(0, __ldg(px));
+    r.set(1, __ldg(px + plane));
+    r.set(2, __ldg(px + 2 * plane));
+  }
+  vstore(out + idx * VN, r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // generic NHWC im2col (used only for stride-2 convolutions)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -248,6 +276,16 @@ std::string launch_stem_im2col(Dtype dt, const float* nchw, int NB, int Hin, int
     const long long total = static_cast<long long>(NB) * Ho * Wo * (kStemKPad / Vec<T>::N);
     stem_im2col_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(nchw, Hin, Win, Ho, Wo, total,
                                                                  reinterpret_cast<T*>(out));
+  });
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
+std::string launch_stem_pad(Dtype dt, const float* nchw, int NB, int Hin, int Win, void* out, cudaStream_t s) {
+  ProfScope ps(kFamElementwise, s);
+  DISPATCH_T(dt, {
+    const long long total = static_cast<long long>(NB) * (Hin + 6) * (Win + 6);
+    stem_pad_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(nchw, Hin, Win, total, reinterpret_cast<T*>(out));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

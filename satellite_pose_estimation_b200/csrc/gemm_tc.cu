@@ -49,7 +49,8 @@ template <int BN, bool X3> struct StageCfg {
   static constexpr int STAGES = X3 ? (BN <= 64 ? 4 : 3) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4));
   static constexpr int THREADS = X3 ? 320 : 192;
   static constexpr int TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * 2 * BN * 4 /*scale,bias x2 buffers*/ +
+  static constexpr int STAGING_BYTES = 4 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 2 * 2 * BN * 4 /*scale,bias x2*/ +
                                     (3 * STAGES + 4) * 8 /*barriers*/ + 16 /*tmem ptr*/ + 1024 /*align slack*/;
 };
 
@@ -61,6 +62,7 @@ struct GemmKParams {
   uint32_t a_bytes;    // bytes one A TMA box delivers
   // conv
   int HW, W, S, pad, hrows, tiles_per_img, kb_per_tap, H, cstride;   // H, W = OUTPUT extent
+  int tiles_per_row;   // stem mode: 128-wide column tiles per output row
   // epilogue
   const float* scale;
   const float* bias;
@@ -94,7 +96,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  float* sm_scale = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BN]
+  uint8_t* sm_staging = smem + STAGES * Cfg::STAGE_BYTES;                          // [4 warps][4096], 1024-aligned
+  float* sm_scale = reinterpret_cast<float*>(sm_staging + Cfg::STAGING_BYTES);   // [2][BN]
   float* sm_bias = sm_scale + 2 * BN;                                            // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_bias + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -138,10 +141,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
-        int img = 0, h0 = 0;
+        int img = 0, h0 = 0, x0 = 0;
         if (p.mode == 1) {
           img = m_tile / p.tiles_per_img;
           h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
+        } else if (p.mode == 2) {
+          img = m_tile / p.tiles_per_img;
+          const int rem = m_tile - img * p.tiles_per_img;
+          h0 = rem / p.tiles_per_row;                    // output row
+          x0 = (rem - h0 * p.tiles_per_row) * BM;        // first output column of the tile
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
@@ -150,6 +158,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + (X3 ? 2 : 1) * Cfg::A_BYTES;
           if (p.mode == 0) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
+          } else if (p.mode == 2) {
+            // k-block kb = filter row kb: 8 consecutive padded pixels x Cp channels per output pixel, windows of
+            // neighbouring output pixels overlap (dim-1 stride = 2 pixels)
+            tma_load_4d(sa, &tmA, &full_bar[stage], 0, x0, 2 * h0 + kb, img);
           } else {
             const int tap = kb / p.kb_per_tap;
             const int c0 = (kb - tap * p.kb_per_tap) * BK;
@@ -242,6 +254,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         m_base = static_cast<long long>(m_tile) * BM;
         const long long rem = static_cast<long long>(p.M) - m_base;
         valid_rows = rem < BM ? static_cast<int>(rem) : BM;
+      } else if (p.mode == 2) {
+        const int img = m_tile / p.tiles_per_img;
+        const int rem = m_tile - img * p.tiles_per_img;
+        const int oy = rem / p.tiles_per_row;
+        const int x0 = (rem - oy * p.tiles_per_row) * BM;
+        m_base = static_cast<long long>(img) * p.HW + static_cast<long long>(oy) * p.W + x0;
+        valid_rows = (p.W - x0) < BM ? (p.W - x0) : BM;
       } else {
         const int img = m_tile / p.tiles_per_img;
         const int h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
@@ -260,18 +279,81 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[buf], use_par, 4);
       tc_fence_after();
 
-      const bool row_ok = row < valid_rows;
-      const long long grow = m_base + row;
-      const long long rrow = (p.res_mod > 0) ? (grow % p.res_mod) : grow;
+      // Thread t of the warp owns accumulator row t (that is how tcgen05.ld hands the data out), but a warp-wide
+      // access "32 rows x 16 bytes" touches 32 different 128-byte lines.  Residual loads and output stores therefore
+      // go through a per-warp 32 x 128-byte staging tile in shared memory (XOR-swizzled 16-byte chunks, conflict
+      // free both row-wise and in the cooperative pattern): global memory only ever sees "4 rows x 128 contiguous
+      // bytes" per instruction.
+      constexpr int ROWB = 32 * static_cast<int>(sizeof(T));   // bytes of one 32-column row chunk: 128 (fp32) / 64 (bf16)
+      constexpr int CPR = ROWB / 16;                            // 16-byte chunks per row: 8 / 4
+      constexpr int RPI = 32 / CPR;                             // rows covered by one cooperative instruction: 4 / 8
+      uint8_t* stg = sm_staging + (warp - 2) * 4096;
+      const int crow = lane / CPR, cseg = lane % CPR;           // cooperative role of this lane
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      const int rows_here = valid_rows - q * 32;                // valid rows in this warp's 32-row slab (may be <= 0)
+      const long long slab0 = m_base + q * 32;                  // first global row of the slab
+      const bool resid = p.residual != nullptr;
+      const bool res32 = (sizeof(T) == 4) || p.res_f32;         // residual element size (fp32 addends in bf16 mode)
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
-        tmem_wait_ld();
         const int ncol = n0 + c * 32;
-        if (row_ok && ncol < p.N) {
-          float f[32];
+        const bool col_ok = ncol < p.N;
+        float f[32];
+        // ---- residual: coalesced global -> staging -> own row
+        float radd[32];
+        if (resid && col_ok && rows_here > 0) {
+          if (res32 && sizeof(T) == 2) {
+            // fp32 addend while storage is bf16: 128-byte rows, two half-passes through the 64-byte-row staging
+            // would complicate the layout; these tensors are tiny, read them directly
+            const long long grow = slab0 + lane;
+            const long long rr = (p.res_mod > 0) ? (grow % p.res_mod) : grow;
+            if (lane < rows_here) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + rr * p.res_ld + ncol;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = ld_f4(rp + j);
+                radd[j] = r4.x; radd[j + 1] = r4.y; radd[j + 2] = r4.z; radd[j + 3] = r4.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) {
+              const int r = i * RPI + crow;
+              if (r < rows_here) {
+                const long long grow = slab0 + r;
+                const long long rr = (p.res_mod > 0) ? (grow % p.res_mod) : grow;
+                const uint8_t* gp = reinterpret_cast<const uint8_t*>(p.residual) +
+                                    (rr * p.res_ld + ncol) * static_cast<long long>(sizeof(T)) + cseg * 16;
+                const uint4 x = *reinterpret_cast<const uint4*>(gp);
+                *reinterpret_cast<uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16)) = x;
+              }
+            }
+            __syncwarp();
+            if (lane < rows_here) {
+#pragma unroll
+              for (int j = 0; j < CPR; ++j) {
+                const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * ROWB + ((j ^ (lane % CPR)) * 16));
+                if (sizeof(T) == 4) {
+                  radd[4 * j] = __uint_as_float(x.x); radd[4 * j + 1] = __uint_as_float(x.y);
+                  radd[4 * j + 2] = __uint_as_float(x.z); radd[4 * j + 3] = __uint_as_float(x.w);
+                } else {
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float2 ff = __bfloat1622float2(h[u]);
+                    radd[8 * j + 2 * u] = ff.x;
+                    radd[8 * j + 2 * u + 1] = ff.y;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        tmem_wait_ld();
+        if (col_ok && rows_here > 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 sc = *reinterpret_cast<const float4*>(s_scale + c * 32 + j);
@@ -281,53 +363,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
             f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
           }
-          if (p.residual != nullptr) {
-            if (sizeof(T) == 4 || p.res_f32) {
-              const float* rp = reinterpret_cast<const float*>(p.residual) + rrow * p.res_ld + ncol;
+          if (resid) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = ld_f4(rp + j);
-                f[j + 0] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-              }
-            } else {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rrow * p.res_ld + ncol;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 r8 = *reinterpret_cast<const uint4*>(rp + j);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r8);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float2 ff = __bfloat1622float2(h[u]);
-                  f[j + 2 * u] += ff.x;
-                  f[j + 2 * u + 1] += ff.y;
-                }
-              }
-            }
+            for (int j = 0; j < 32; ++j) f[j] += radd[j];
           }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          if (sizeof(T) == 4) {
-            // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round-to-nearest here so the
-            // next layer's products are exact and the error stays unbiased (truncation drifts by ~2^-11 per layer)
-            float* op = reinterpret_cast<float*>(p.out) + grow * p.out_ld + ncol;
+          // ---- output: own row -> staging -> coalesced global
+          if (lane < rows_here) {
+            if (sizeof(T) == 4) {
+              // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here so
+              // the next layer's products are exact and the error stays unbiased
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(op + j) =
-                  p.round_out ? make_float4(rna_tf32(f[j]), rna_tf32(f[j + 1]), rna_tf32(f[j + 2]), rna_tf32(f[j + 3]))
-                              : make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.out_ld + ncol;
+              for (int j = 0; j < 8; ++j) {
+                float4 o4 = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                if (p.round_out) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
+                *reinterpret_cast<float4*>(stg + lane * ROWB + ((j ^ (lane % CPR)) * 16)) = o4;
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o8;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
+              for (int j = 0; j < 4; ++j) {
+                uint4 o8;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[j + 2 * u], f[j + 2 * u + 1]);
-              *reinterpret_cast<uint4*>(op + j) = o8;
+                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
+                *reinterpret_cast<uint4*>(stg + lane * ROWB + ((j ^ (lane % CPR)) * 16)) = o8;
+              }
             }
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            const int r = i * RPI + crow;
+            if (r < rows_here) {
+              const uint4 x = *reinterpret_cast<const uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16));
+              uint8_t* gp = reinterpret_cast<uint8_t*>(p.out) +
+                            ((slab0 + r) * p.out_ld + ncol) * static_cast<long long>(sizeof(T)) + cseg * 16;
+              *reinterpret_cast<uint4*>(gp) = x;
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -424,6 +501,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.out_ld % (16 / es) != 0) return "gemm: out_ld must keep rows 16-byte aligned";
   if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
   if (d.x3 && d.mode != 0) return "gemm: 3xTF32 is only built for plain matrices";
+  if (d.mode < 0 || d.mode > 2) return "gemm: bad mode";
   const int cs_est = d.conv_stride > 1 ? d.conv_stride : 1;
   const long long m_tiles_est = d.mode == 0 ? (d.M + BM - 1) / BM
                                             : static_cast<long long>(d.NB) * (((d.H / cs_est) * (d.W / cs_est) + BM - 1) / BM);
@@ -462,6 +540,28 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), BM};
     err = encode_map(&tmA, dt, 2, d.A, dims, str, box);
     if (!err.empty()) return err;
+  } else if (d.mode == 2) {
+    const int Cp = 16 / es;                              // padded channels per pixel (16 bytes)
+    if (d.C != Cp) return "stem: input must be the padded NHWC-Cp image";
+    if (d.H % 2 || d.W % 2) return "stem: input extent must be even";
+    const int Ho = d.H / 2, Wo = d.W / 2, Hp = d.H + 6, Wp = d.W + 6;
+    K = 7 * BK;
+    const int bw = Wo < BM ? Wo : BM;
+    kp.tiles_per_row = (Wo + BM - 1) / BM;
+    kp.tiles_per_img = Ho * kp.tiles_per_row;
+    kp.num_m_tiles = kp.tiles_per_img * d.NB;
+    kp.M = d.NB * Ho * Wo;
+    kp.HW = Ho * Wo;
+    kp.H = Ho;
+    kp.W = Wo;
+    kp.a_bytes = static_cast<uint32_t>(bw * 128);
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(BK), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Hp),
+                          static_cast<cuuint64_t>(d.NB)};
+    cuuint64_t str[3] = {static_cast<cuuint64_t>(2 * Cp) * es, static_cast<cuuint64_t>(Wp) * Cp * es,
+                         static_cast<cuuint64_t>(Hp) * Wp * Cp * es};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(bw), 1, 1};
+    err = encode_map(&tmA, dt, 4, d.A, dims, str, box);
+    if (!err.empty()) return "stem: " + err;
   } else {
     if (d.C % BK != 0) return "conv: C must be a multiple of the 128-byte k-block";
     const int cs = d.conv_stride > 0 ? d.conv_stride : 1;

@@ -146,7 +146,10 @@ struct spe_ctx {
   std::vector<void*> allocs;  // everything cudaMalloc'ed, freed in destroy
 
   // weights
-  GemmW stem;
+  GemmW stem;                  // im2col form [64, 192]
+  GemmW stem2;                 // TMA-window form [64, 7 rows x 8 taps x Cp]
+  bool stem_windowed = true;   // cleared if the overlapping-window tensor map is refused by the driver
+  void* SP = nullptr;          // padded NHWC-Cp stem input
   std::vector<Bottleneck> blocks;
   GemmW s8_lat, s16_lat, out_conv, input_proj;
   std::vector<EncLayer> enc;
@@ -387,6 +390,21 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
   const std::string b = "backbone.0.body";
   // ---- stem + layers
   TRY_S(load_conv_bn(ctx, ws, b + ".conv1", b + ".bn1", 64, 3, 7, &ctx->stem, 192));
+  {
+    // same filter laid out for the windowed stem GEMM: K = (filter row r, tap s in 0..7, channel c in 0..Cp-1)
+    const HostTensor* w = ws.get(b + ".conv1.weight", {64, 3, 7, 7});
+    if (!w) return ws.missing;
+    const int Cp = 16 / static_cast<int>(dtype_size(ctx->dt)), Kw = 7 * 8 * Cp;
+    std::vector<float> w2(static_cast<size_t>(64) * Kw, 0.f);
+    for (int o = 0; o < 64; ++o)
+      for (int ch = 0; ch < 3; ++ch)
+        for (int r = 0; r < 7; ++r)
+          for (int t = 0; t < 7; ++t)
+            w2[static_cast<size_t>(o) * Kw + (r * 8 + t) * Cp + ch] = w->data[((o * 3 + ch) * 7 + r) * 7 + t];
+    TRY_S(upload_gemm_w(ctx, w2, 64, Kw, &ctx->stem2));
+    ctx->stem2.scale = ctx->stem.scale;
+    ctx->stem2.bias = ctx->stem.bias;
+  }
   ctx->blocks.clear();
   int inplanes = 64;
   const int nblk[3] = {3, 4, 6};
@@ -518,6 +536,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
   const long long T = ctx->tokens, Q = c.num_queries, LD = c.dec_layers, FF = c.dim_feedforward;
   auto A = [&](void** p, long long elems) { return dmalloc_bytes(ctx, p, elems * es); };
   TRY_S(A(&ctx->S0, B * h2 * h2 * 192));
+  TRY_S(dmalloc_bytes(ctx, &ctx->SP, B * (R + 6) * (R + 6) * 16));
   TRY_S(A(&ctx->S1, B * h2 * h2 * 64));
   TRY_S(A(&ctx->P0, B * h4 * h4 * 256));
   TRY_S(A(&ctx->P1, B * h4 * h4 * 256));
@@ -654,8 +673,23 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   const long long Bl = B;
 
   // ---- stem
-  TRY_S(launch_stem_im2col(f.dt, images, B, R, R, ctx->S0, st));
-  TRY_S(f.gemm(ctx->S0, Bl * h2 * h2, ctx->stem, ctx->S1, 64, true));
+  bool stem_done = false;
+  if (ctx->stem_windowed) {
+    TRY_S(launch_stem_pad(f.dt, images, B, R, R, ctx->SP, st));
+    GemmDesc d;
+    d.mode = 2;
+    d.A = ctx->SP; d.NB = B; d.H = R; d.W = R; d.C = 16 / static_cast<int>(f.es);
+    d.Wt = ctx->stem2.w; d.N = 64; d.scale = ctx->stem2.scale; d.bias = ctx->stem2.bias; d.relu = 1;
+    d.out = ctx->S1; d.out_ld = 64;
+    const std::string e = launch_gemm(f.dt, d, ctx->num_sms, st);
+    if (e.empty()) stem_done = true;
+    else if (e.rfind("stem: cuTensorMapEncodeTiled", 0) == 0) ctx->stem_windowed = false;   // use the im2col form
+    else return e;
+  }
+  if (!stem_done) {
+    TRY_S(launch_stem_im2col(f.dt, images, B, R, R, ctx->S0, st));
+    TRY_S(f.gemm(ctx->S0, Bl * h2 * h2, ctx->stem, ctx->S1, 64, true));
+  }
   TRY_S(f.tap("stem", ctx->S1, Bl * h2 * h2 * 64));
   TRY_S(launch_maxpool3x3s2(f.dt, ctx->S1, B, h2, h2, 64, ctx->P0, st));
 

@@ -14,7 +14,7 @@ inline size_t dtype_size(Dtype d) { return d == kTF32 ? 4 : 2; }
 // A is either a row-major matrix (mode 0) or an NHWC activation read through R*S shifted taps (mode 1: stride 1
 // or 2 convolution, zero padding supplied by TMA out-of-bounds fill, stride by the TMA traversal stride).
 struct GemmDesc {
-  int mode = 0;
+  int mode = 0;                   // 0 matrix, 1 NHWC convolution, 2 7x7/stride-2 stem over the padded NHWC-Cp image
   // mode 0: A[M, K] row-major with leading dimension lda (elements)
   const void* A = nullptr;
   long long M = 0;
@@ -46,6 +46,8 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
 // ---- memory-bound helper kernels (elementwise.cu) ----
 std::string launch_stem_im2col(Dtype dt, const float* nchw, int NB, int Hin, int Win, void* out /*[NB*Ho*Wo,192]*/,
                                cudaStream_t s);
+std::string launch_stem_pad(Dtype dt, const float* nchw, int NB, int Hin, int Win, void* out /*[NB,H+6,W+6,Cp]*/,
+                            cudaStream_t s);
 std::string launch_im2col_nhwc(Dtype dt, const void* in, int NB, int H, int W, int C, int R, int S, int stride,
                                int pad, void* out, cudaStream_t s);
 std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s);
