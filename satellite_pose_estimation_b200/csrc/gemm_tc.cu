@@ -294,6 +294,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long slab0 = m_base + q * 32;                  // first global row of the slab
       const bool resid = p.residual != nullptr;
       const bool res32 = (sizeof(T) == 4) || p.res_f32;         // residual element size (fp32 addends in bf16 mode)
+      const bool coop_res = resid && rows_here > 0 && !(res32 && sizeof(T) == 2);
+      // residual tile of one 32-column chunk, fetched one chunk ahead so its latency hides behind the stores
+      uint4 rx[32 / RPI];
+      auto fetch_residual = [&](int ncol_) {
+#pragma unroll
+        for (int i = 0; i < 32 / RPI; ++i) {
+          const int r = i * RPI + crow;
+          rx[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < rows_here && ncol_ < p.N) {
+            const long long grow = slab0 + r;
+            const long long rr = (p.res_mod > 0) ? static_cast<long long>(static_cast<unsigned>(grow) %
+                                                                          static_cast<unsigned>(p.res_mod))
+                                                 : grow;
+            const uint8_t* gp = reinterpret_cast<const uint8_t*>(p.residual) +
+                                (rr * p.res_ld + ncol_) * static_cast<long long>(sizeof(T)) + cseg * 16;
+            rx[i] = *reinterpret_cast<const uint4*>(gp);
+          }
+        }
+      };
+      if (coop_res) fetch_residual(n0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -301,14 +321,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ncol = n0 + c * 32;
         const bool col_ok = ncol < p.N;
         float f[32];
-        // ---- residual: coalesced global -> staging -> own row
         float radd[32];
         if (resid && col_ok && rows_here > 0) {
-          if (res32 && sizeof(T) == 2) {
-            // fp32 addend while storage is bf16: 128-byte rows, two half-passes through the 64-byte-row staging
-            // would complicate the layout; these tensors are tiny, read them directly
+          if (!coop_res) {
+            // fp32 addend while storage is bf16: 128-byte rows do not fit the 64-byte-row staging; these tensors
+            // are tiny and L2-resident, read them directly
             const long long grow = slab0 + lane;
-            const long long rr = (p.res_mod > 0) ? (grow % p.res_mod) : grow;
+            const long long rr = (p.res_mod > 0) ? static_cast<long long>(static_cast<unsigned>(grow) %
+                                                                          static_cast<unsigned>(p.res_mod))
+                                                 : grow;
             if (lane < rows_here) {
               const float* rp = reinterpret_cast<const float*>(p.residual) + rr * p.res_ld + ncol;
 #pragma unroll
@@ -321,14 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32 / RPI; ++i) {
               const int r = i * RPI + crow;
-              if (r < rows_here) {
-                const long long grow = slab0 + r;
-                const long long rr = (p.res_mod > 0) ? (grow % p.res_mod) : grow;
-                const uint8_t* gp = reinterpret_cast<const uint8_t*>(p.residual) +
-                                    (rr * p.res_ld + ncol) * static_cast<long long>(sizeof(T)) + cseg * 16;
-                const uint4 x = *reinterpret_cast<const uint4*>(gp);
-                *reinterpret_cast<uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16)) = x;
-              }
+              *reinterpret_cast<uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16)) = rx[i];
             }
             __syncwarp();
             if (lane < rows_here) {
@@ -352,6 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
           }
         }
+        if (coop_res && c + 1 < BN / 32) fetch_residual(ncol + 32);   // next chunk's tile, in flight during the stores
         tmem_wait_ld();
         if (col_ok && rows_here > 0) {
 #pragma unroll
@@ -394,14 +409,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
+          uint4 ox[32 / RPI];
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            const int r = i * RPI + crow;
+            ox[i] = *reinterpret_cast<const uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16));
+          }
 #pragma unroll
           for (int i = 0; i < 32 / RPI; ++i) {
             const int r = i * RPI + crow;
             if (r < rows_here) {
-              const uint4 x = *reinterpret_cast<const uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16));
               uint8_t* gp = reinterpret_cast<uint8_t*>(p.out) +
                             ((slab0 + r) * p.out_ld + ncol) * static_cast<long long>(sizeof(T)) + cseg * 16;
-              *reinterpret_cast<uint4*>(gp) = x;
+              *reinterpret_cast<uint4*>(gp) = ox[i];
             }
           }
           __syncwarp();
