@@ -268,7 +268,7 @@ def run_b200(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * args.steps / float(e2e_s.item())
     eng.set_pnp_override(None, None)
-    h2d = frames_host[0].numel() + BATCH * 4 * 4
+    h2d = r["h2d_bytes"]   # only the crop-box / frame intersections are uploaded
     d2h = BATCH * (4 * 8 + 3 * 8 + 4)
 
     if rank == 0:

@@ -119,6 +119,9 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
                        const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
                        int32_t* boxes_host /*[B,4] or NULL*/, void* stream);
 
+/* bytes spe_run_batch_host uploaded on its last call (only the crop-box/frame intersections travel) */
+long long spe_last_h2d_bytes(spe_ctx* ctx);
+
 /* ---- test / bring-up hooks (not part of the drop-in surface) ------------------------------------------------- */
 /* out = act(scale * A.W^T + bias + residual) with A [M,K], W [N,K], storage dtype 0=fp32/TF32, 1=bf16,
  * 2=fp32 with error-compensated 3xTF32 (W is then [N,2K] = [rna(W) | rna(W - rna(W))], output not rounded) */

@@ -12,9 +12,10 @@ namespace spe {
 struct PipelineBuffers {
   uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
   float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
-  int has_sigma; const float* ov_logits; const float* ov_points;
+  int has_sigma; const float* ov_logits; const float* ov_points; long long* last_h2d_bytes;
 };
 PipelineBuffers pipeline_buffers(spe_ctx* ctx);
+long long last_h2d_bytes(spe_ctx* ctx);
 void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points);
 int set_error(spe_ctx* ctx, int code, const std::string& msg);
 }  // namespace spe
@@ -98,8 +99,21 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
   std::vector<int32_t> boxes(static_cast<size_t>(B) * 4);
   spe_clip_boxes(det_boxes_host, B, boxes.data());
   if (boxes_host) memcpy(boxes_host, boxes.data(), boxes.size() * sizeof(int32_t));
-  cudaError_t e;
-  e = cudaMemcpyAsync(*pb.frames_dev, frames_host, static_cast<size_t>(need), cudaMemcpyHostToDevice, st);
+  // Upload only what the crop kernel can touch: the intersection of each crop box with its frame (the bicubic taps
+  // are clamped to the crop canvas, so nothing outside the box is ever read).  The rectangle lands at its own
+  // position inside the device frame, so the kernel needs no extra indirection.
+  cudaError_t e = cudaSuccess;
+  long long h2d = 0;
+  for (int i = 0; i < B && e == cudaSuccess; ++i) {
+    const int x0 = boxes[4 * i + 0] < 0 ? 0 : boxes[4 * i + 0], y0 = boxes[4 * i + 1] < 0 ? 0 : boxes[4 * i + 1];
+    const int x1 = boxes[4 * i + 2] > W ? W : boxes[4 * i + 2], y1 = boxes[4 * i + 3] > H ? H : boxes[4 * i + 3];
+    if (x1 <= x0 || y1 <= y0) continue;   // box entirely outside the frame: the crop is all padding
+    const long long off = static_cast<long long>(i) * H * W + static_cast<long long>(y0) * W + x0;
+    e = cudaMemcpy2DAsync(*pb.frames_dev + off, W, frames_host + off, W, static_cast<size_t>(x1 - x0),
+                          static_cast<size_t>(y1 - y0), cudaMemcpyHostToDevice, st);
+    h2d += static_cast<long long>(x1 - x0) * (y1 - y0);
+  }
+  *pb.last_h2d_bytes = h2d + static_cast<long long>(boxes.size() * sizeof(int32_t));
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(pb.boxes_dev, boxes.data(), boxes.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e));
@@ -125,6 +139,8 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_run_batch_host: ") + cudaGetErrorString(e));
   return SPE_OK;
 }
+
+long long spe_last_h2d_bytes(spe_ctx* ctx) { return ctx ? last_h2d_bytes(ctx) : -1; }
 
 int spe_profile_enable(int on) {
   profile_enable(on != 0);

@@ -13,6 +13,7 @@
 #include "spe_internal.h"
 #include "profile.h"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace spe {
 
@@ -219,6 +220,8 @@ std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s) {
   if (d.B <= 0 || d.Lq <= 0 || d.Lk <= 0) return "attention: empty problem";
   const int vec = 8;
   if (d.ldk % vec || d.ldv % vec || d.ldq % 1) return "attention: K/V row strides must be multiples of 8 elements";
+  static const bool no_tc = getenv("SPE_ATTN_LEGACY") != nullptr;
+  if (!no_tc && attention_tc_supported(dt, d)) return launch_attention_tc(d, s);
   if (dt == kTF32) return launch_attn_t<float>(d, s);
   return launch_attn_t<__nv_bfloat16>(d, s);
 }

@@ -1,0 +1,298 @@
+// Encoder self-attention on the 5th-generation tensor cores (tcgen05 + TMEM), head_dim = 32, fp32 storage / TF32.
+//
+//   O = softmax(Q K^T / sqrt(32)) V      per (image, head); the 784 x 784 weight matrix never leaves the SM
+//   (reference: nn.MultiheadAttention inside TransformerEncoderLayer.forward_post, RV/models/transformer.py:154-158)
+//
+// One CTA = 128 query rows of one head (two CTAs co-reside per SM and overlap each other's phases), 192 threads:
+//   warp 0      TMA producer: Q tile once, then K / V tiles of NK keys through a 2-stage mbarrier ring
+//   warp 1      owns TMEM, one lane issues   S = Q K^T   (tcgen05.mma kind::tf32, A and B from shared memory)
+//                                  and       O += P V     (A = P read straight from TMEM, B = V tile, MN-major)
+//   warps 2..5  softmax: thread t owns score row t (tcgen05.ld gives each thread its own row, so the running max and
+//               sum need no cross-thread reduction), writes P back over S in TMEM (tcgen05.st) and rescales the
+//               32-column O accumulator when the running maximum moves (online softmax, fp32 statistics)
+// TMEM columns: [0, NK) scores / probabilities, [128, 160) output accumulator.
+#include "spe_internal.h"
+#include "profile.h"
+#include "spe_ptx.cuh"
+
+namespace spe {
+
+namespace {
+
+constexpr int kQRows = 128;
+constexpr int kOCol = 128;          // first TMEM column of the O accumulator
+constexpr int kTmemCols = 256;
+constexpr int kThreads = 192;
+
+struct AttnTcParams {
+  float* out;
+  int ldo;
+  int Lq, Lk;
+  float scale_log2e;
+  int exact_out;
+};
+
+template <int NK> struct AttnSmem {
+  static constexpr int Q_BYTES = kQRows * 128;
+  static constexpr int KV_BYTES = NK * 128;
+  static constexpr int STAGE_BYTES = 2 * KV_BYTES;
+  static constexpr int STAGES = 2;
+  static constexpr int BYTES = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t rna_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+template <int NK>
+__global__ void __launch_bounds__(kThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  using SM = AttnSmem<NK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + SM::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + SM::STAGES * SM::STAGE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * kQRows;
+  const int nchunks = (p.Lk + NK - 1) / NK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, SM::Q_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, h * 32, b * p.Lq + q0);
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j & 1;
+        const uint32_t u = static_cast<uint32_t>(j >> 1);
+        mbar_wait(&kv_empty[st], (u & 1u) ^ 1u, 11);
+        mbar_expect_tx(&kv_full[st], SM::STAGE_BYTES);
+        uint8_t* sk = sKV + st * SM::STAGE_BYTES;
+        tma_load_2d(sk, &tmK, &kv_full[st], h * 32, b * p.Lk + j * NK);
+        tma_load_2d(sk + SM::KV_BYTES, &tmV, &kv_full[st], h * 32, b * p.Lk + j * NK);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(2, kQRows, NK);
+      constexpr uint32_t idesc_pv = umma_idesc(2, kQRows, 32) | (1u << 16);   // B (= V tile) is MN-major
+      mbar_wait(q_full, 0, 12);
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+      for (int j = 0; j < nchunks; ++j) {
+        const int st = j & 1;
+        const uint32_t u = static_cast<uint32_t>(j >> 1);
+        mbar_wait(&kv_full[st], u & 1u, 13);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(sKV + st * SM::STAGE_BYTES);
+        const uint64_t kdesc = umma_desc_sw128(sk);
+        // S = Q K^T : K dimension = head_dim 32 = four K=8 steps inside one 128-byte swizzle atom.
+        // (tensor-pipe instructions retire in issue order, so this overwrites P_{j-1} only after P V_{j-1} read it)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_base, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(s_full);
+        mbar_wait(p_full, static_cast<uint32_t>(j) & 1u, 14);   // softmax wrote P_j (and rescaled O)
+        tc_fence_after();
+        const uint64_t vdesc = umma_desc_mn_sw128(sk + SM::KV_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < NK / 8; ++kk)                     // 8 keys per MMA = one 1024-byte row group of V
+          umma_ts_tf32(tmem_base + kOCol, tmem_base + static_cast<uint32_t>(kk * 8), vdesc + 64u * kk, idesc_pv,
+                       (j | kk) != 0 ? 1u : 0u);
+        tc_commit(&kv_empty[st]);
+        tc_commit(pv_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float c = p.scale_log2e;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nchunks; ++j) {
+      mbar_wait(s_full, static_cast<uint32_t>(j) & 1u, 15);
+      tc_fence_after();
+      const int key0 = j * NK;
+      // ---- pass 1: row maximum of this chunk
+      float mx = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < NK / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (key0 + cc * 32 + i < p.Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      if constexpr (NK % 32 != 0) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + static_cast<uint32_t>((NK / 32) * 32), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (key0 + (NK / 32) * 32 + i < p.Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m, mx);                    // finite: every chunk holds at least one valid key
+      const float alpha = ex2((m - m_new) * c);            // 0 on the first chunk (m = -inf)
+      const float mc = m_new * c;
+      // ---- pass 2: probabilities, written back over the scores as TF32
+      float sum = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < NK / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float pr = (key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          sum += pr;
+          v[i] = rna_bits(pr);
+        }
+        tmem_st_32x32(trow + static_cast<uint32_t>(cc * 32), v);
+      }
+      if constexpr (NK % 32 != 0) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + static_cast<uint32_t>((NK / 32) * 32), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pr = (key0 + (NK / 32) * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          sum += pr;
+          v[i] = rna_bits(pr);
+        }
+        tmem_st_32x16(trow + static_cast<uint32_t>((NK / 32) * 32), v);
+      }
+      l = l * alpha + sum;
+      m = m_new;
+      // ---- rescale the running output when this warp's maxima moved (needs P V_{j-1} to have landed)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u, 16);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld_32x32(trow + kOCol, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32(trow + kOCol, o);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> global
+    mbar_wait(pv_done, static_cast<uint32_t>(nchunks - 1) & 1u, 17);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld_32x32(trow + kOCol, o);
+    tmem_wait_ld();
+    if (q0 + row < p.Lq) {
+      const float inv = 1.0f / l;
+      float* op = p.out + (static_cast<long long>(b) * p.Lq + q0 + row) * p.ldo + h * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 r4 = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
+                                __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+        if (!p.exact_out)
+          r4 = make_float4(__uint_as_float(rna_bits(r4.x)), __uint_as_float(rna_bits(r4.y)),
+                           __uint_as_float(rna_bits(r4.z)), __uint_as_float(rna_bits(r4.w)));
+        *reinterpret_cast<float4*>(op + i) = r4;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int NK>
+std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
+  using SM = AttnSmem<NK>;
+  static bool attr_set = false;
+  auto kfn = attention_tc_kernel<NK>;
+  if (!attr_set) {
+    SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  const int hd = d.heads * 32;
+  std::string e;
+  e = encode_tmap_2d(&tmQ, kTF32, d.q, hd, static_cast<long long>(d.B) * d.Lq, static_cast<long long>(d.ldq) * 4, 32, kQRows);
+  if (!e.empty()) return e;
+  e = encode_tmap_2d(&tmK, kTF32, d.k, hd, static_cast<long long>(d.B) * d.Lk, static_cast<long long>(d.ldk) * 4, 32, NK);
+  if (!e.empty()) return e;
+  e = encode_tmap_2d(&tmV, kTF32, d.v, hd, static_cast<long long>(d.B) * d.Lk, static_cast<long long>(d.ldv) * 4, 32, NK);
+  if (!e.empty()) return e;
+  AttnTcParams p;
+  p.out = reinterpret_cast<float*>(d.out);
+  p.ldo = d.ldo;
+  p.Lq = d.Lq;
+  p.Lk = d.Lk;
+  p.scale_log2e = d.scale * 1.4426950408889634f;
+  p.exact_out = d.exact_out;
+  dim3 grid((d.Lq + kQRows - 1) / kQRows, d.heads, d.B);
+  ProfScope ps(kFamAttention, s);
+  kfn<<<grid, kThreads, SM::BYTES, s>>>(tmQ, tmK, tmV, p);
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
+}  // namespace
+
+// fp32 storage only; Q/K/V/O must be batch-contiguous (batch stride = rows * row stride)
+bool attention_tc_supported(Dtype dt, const AttnDesc& d) {
+  if (dt != kTF32) return false;
+  if (d.Lq < 96) return false;   // tiny query sets (decoder) waste most of a 128-row tile: keep the register kernel
+  if (d.bsq != static_cast<long long>(d.Lq) * d.ldq || d.bsk != static_cast<long long>(d.Lk) * d.ldk ||
+      d.bsv != static_cast<long long>(d.Lk) * d.ldv || d.bso != static_cast<long long>(d.Lq) * d.ldo)
+    return false;
+  if (d.ldq % 4 || d.ldk % 4 || d.ldv % 4 || d.ldo % 4) return false;
+  return true;
+}
+
+std::string launch_attention_tc(const AttnDesc& d, cudaStream_t s) {
+  if (d.Lk % 112 == 0) return launch_tc<112>(d, s);
+  return launch_tc<128>(d, s);
+}
+
+}  // namespace spe

@@ -514,6 +514,14 @@ std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap
 
 }  // namespace
 
+std::string encode_tmap_2d(void* map, Dtype dt, const void* base, long long dim0, long long dim1,
+                           long long stride1_bytes, int box0, int box1) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(dim0), static_cast<cuuint64_t>(dim1)};
+  cuuint64_t str[1] = {static_cast<cuuint64_t>(stride1_bytes)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
+  return encode_map(reinterpret_cast<CUtensorMap*>(map), dt, 2, base, dims, str, box);
+}
+
 std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t stream) {
   const int es = static_cast<int>(dtype_size(dt));
   const int BK = 128 / es;

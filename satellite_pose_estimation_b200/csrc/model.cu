@@ -177,6 +177,7 @@ struct spe_ctx {
   double *p_quat = nullptr, *p_tvec = nullptr;
   int32_t *p_assign = nullptr, *p_status = nullptr;
   const float *ov_logits = nullptr, *ov_points = nullptr;   // bench hook, see spe_debug_set_pnp_override
+  long long last_h2d = 0;            // bytes uploaded by the last spe_run_batch_host
 
   // forward schedule
   bool use_graphs = true;
@@ -1032,14 +1033,16 @@ namespace spe {
 struct PipelineBuffers {
   uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
   float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
-  int has_sigma; const float* ov_logits; const float* ov_points;
+  int has_sigma; const float* ov_logits; const float* ov_points; long long* last_h2d_bytes;
 };
 PipelineBuffers pipeline_buffers(spe_ctx* ctx) {
   return PipelineBuffers{&ctx->frames_dev, &ctx->frames_cap, ctx->boxes_dev, ctx->images_dev, ctx->p_logits,
                          ctx->p_points,    ctx->p_logsig,    ctx->p_quat,    ctx->p_tvec,     ctx->p_assign,
                          ctx->p_status,    ctx->device,      ctx->cfg.max_batch, ctx->cfg.input_size,
-                         ctx->cfg.num_queries, ctx->cfg.has_sigma, ctx->ov_logits, ctx->ov_points};
+                         ctx->cfg.num_queries, ctx->cfg.has_sigma, ctx->ov_logits, ctx->ov_points,
+                         &ctx->last_h2d};
 }
+long long last_h2d_bytes(spe_ctx* ctx) { return ctx->last_h2d; }
 void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points) {
   ctx->ov_logits = logits;
   ctx->ov_points = points;

@@ -197,7 +197,8 @@ class Engine:
                                           quat.ctypes.data_as(C.c_void_p), tvec.ctypes.data_as(C.c_void_p),
                                           status.ctypes.data_as(C.c_void_p), boxes.ctypes.data_as(C.c_void_p),
                                           _stream(self.device)), self._ctx)
-        return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes}
+        return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes,
+                "h2d_bytes": int(self.lib.spe_last_h2d_bytes(self._ctx))}
 
     # ---- measurement hooks (bench.py) ------------------------------------------------------------------------------
     FAMILIES = ("gemm", "attention", "elementwise", "heads", "crop", "pnp")
