@@ -1,0 +1,81 @@
+"""Per-GEMM roofline table for one step at C* (B = 64, fp32 storage / TF32): pairs the launch order of the forward
+schedule with an ncu launch list.  ideal = max(FLOPs / tf32_peak, unique HBM bytes / hbm_bw).
+Usage: python profiles/gemm_roofline.py launches.csv"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from summarize_launches import load, short  # noqa: E402
+
+B, ES = 64, 4
+PK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else \
+    {"bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
+TF32 = PK["bf16_tflops_sustained"] / 2 * 1e12
+HBM = PK["hbm_gbs"] * 1e9
+
+
+def schedule():
+    g = []  # (name, M, N, K, extra_read_elems)
+
+    def add(name, M, N, K, res=0, x3=False):
+        g.append((name, M, N, K, res, x3))
+    add("stem 7x7/s2", B * 112 * 112, 64, 147)
+    inpl, H = 64, 56
+    for li, (pl, nb) in enumerate(((64, 3), (128, 4), (256, 6))):
+        for bi in range(nb):
+            s = 2 if (bi == 0 and li > 0) else 1
+            Ho = H // s
+            add(f"l{li + 1}.{bi}.conv1", B * H * H, pl, inpl)
+            add(f"l{li + 1}.{bi}.conv2 3x3", B * Ho * Ho, pl, 9 * pl)
+            if bi == 0:
+                add(f"l{li + 1}.{bi}.down", B * Ho * Ho, 4 * pl, inpl)
+            add(f"l{li + 1}.{bi}.conv3+res", B * Ho * Ho, 4 * pl, pl, res=B * Ho * Ho * 4 * pl)
+            inpl, H = 4 * pl, Ho
+    T = 784
+    add("s8_latern", B * T, 256, 512)
+    add("s16_latern 3x3", B * T, 256, 9 * 1024)
+    add("output_conv 3x3", B * T, 512, 9 * 512)
+    add("input_proj", B * T, 256, 512)
+    for i in range(4):
+        add(f"enc{i}.qkv", B * T, 768, 256)
+        add(f"enc{i}.out+res", B * T, 256, 256, res=B * T * 256)
+        add(f"enc{i}.ff1", B * T, 2048, 256)
+        add(f"enc{i}.ff2+res", B * T, 256, 2048, res=B * T * 256)
+    add("dec.kv_all (3xTF32)", B * T, 2048, 256, x3=True)
+    Q = 40
+    for i in range(4):
+        add(f"dec{i}.sa_qkv x3", B * Q, 768, 256, x3=True)
+        add(f"dec{i}.sa_out x3", B * Q, 256, 256, x3=True)
+        add(f"dec{i}.ca_q x3", B * Q, 256, 256, x3=True)
+        add(f"dec{i}.ca_out x3", B * Q, 256, 256, x3=True)
+        add(f"dec{i}.ff1 x3", B * Q, 2048, 256, x3=True)
+        add(f"dec{i}.ff2 x3", B * Q, 256, 2048, x3=True)
+    add("pt0 x3", B * Q, 256, 256, x3=True)
+    add("pt1 x3", B * Q, 256, 256, x3=True)
+    return g
+
+
+def main(path):
+    seq = load(path)
+    starts = [i for i, s in enumerate(seq) if "crop_resize" in s[1]]
+    ends = [i for i, s in enumerate(seq) if "assign_pnp" in s[1] or "PnpDesc" in s[1]]
+    a = starts[-1] if ends and ends[-1] > starts[-1] else starts[-2]
+    b = min(e for e in ends if e > a)
+    gem = [s for s in seq[a:b + 1] if short(s[1]) == "gemm_tc_kernel"]
+    sch = schedule()
+    assert len(gem) == len(sch), (len(gem), len(sch))
+    print("| GEMM | M | N | K | us | ideal us | TFLOP/s | x ideal |\n|---|---:|---:|---:|---:|---:|---:|---:|")
+    tot = tot_ideal = 0
+    for (name, M, N, K, res, x3), s in zip(sch, gem):
+        fl = 2 * M * N * K
+        by = (M * K + M * N + res) * ES if "3x3" not in name else (M * K // 9 + M * N) * ES
+        ideal = max(fl * (3 if x3 else 1) / TF32, by / HBM) * 1e6
+        tot += s[2]; tot_ideal += ideal
+        print(f"| {name} | {M} | {N} | {K} | {s[2]:.1f} | {ideal:.1f} | {fl / s[2] / 1e6:.0f} | {s[2] / ideal:.1f} |")
+    print(f"\nGEMM total {tot:.0f} us, sum of per-GEMM ideals {tot_ideal:.0f} us")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -6,7 +6,8 @@
 // One CTA = 128 query rows of one head (two CTAs co-reside per SM and overlap each other's phases), 192 threads:
 //   warp 0      TMA producer: Q tile once, then K / V tiles of NK keys through a 2-stage mbarrier ring
 //   warp 1      owns TMEM, one lane issues   S = Q K^T   (tcgen05.mma kind::tf32, A and B from shared memory)
-//                                  and       O += P V     (A = P read straight from TMEM, B = V tile, MN-major)
+//                                  and       O += P V     (A = P read straight from TMEM, B = V tile, MN-major,
+//                                                          which for TF32 means the 32-byte-granule swizzle)
 //   warps 2..5  softmax: thread t owns score row t (tcgen05.ld gives each thread its own row, so the running max and
 //               sum need no cross-thread reduction), writes P back over S in TMEM (tcgen05.st) and rescales the
 //               32-column O accumulator when the running maximum moves (online softmax, fp32 statistics)
@@ -14,6 +15,8 @@
 #include "spe_internal.h"
 #include "profile.h"
 #include "spe_ptx.cuh"
+
+#include <stdlib.h>
 
 namespace spe {
 
@@ -30,6 +33,7 @@ struct AttnTcParams {
   int Lq, Lk;
   float scale_log2e;
   int exact_out;
+  int debug;
 };
 
 template <int NK> struct AttnSmem {
@@ -129,7 +133,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_commit(s_full);
         mbar_wait(p_full, static_cast<uint32_t>(j) & 1u, 14);   // softmax wrote P_j (and rescaled O)
         tc_fence_after();
-        const uint64_t vdesc = umma_desc_mn_sw128(sk + SM::KV_BYTES);
+        const uint64_t vdesc = umma_desc_mn_tf32(sk + SM::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < NK / 8; ++kk)                     // 8 keys per MMA = one 1024-byte row group of V
           umma_ts_tf32(tmem_base + kOCol, tmem_base + static_cast<uint32_t>(kk * 8), vdesc + 64u * kk, idesc_pv,
@@ -167,6 +171,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (key0 + (NK / 32) * 32 + i < p.Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      if (p.debug && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {   // warp-uniform: .sync.aligned ld
+        uint32_t v[16];
+        tmem_ld_32x16(trow, v);
+        tmem_wait_ld();
+        if (row < 2) printf("[attn dbg] chunk %d row %d S[0..3] = %f %f %f %f  mx %f\n", j, row, __uint_as_float(v[0]),
+               __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]), mx);
       }
       const float m_new = fmaxf(m, mx);                    // finite: every chunk holds at least one valid key
       const float alpha = ex2((m - m_new) * c);            // 0 on the first chunk (m = -inf)
@@ -222,6 +233,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t o[32];
     tmem_ld_32x32(trow + kOCol, o);
     tmem_wait_ld();
+    if (p.debug && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row < 2)
+      printf("[attn dbg] row %d m %f l %f O[0..3] = %f %f %f %f\n", row, m, l, __uint_as_float(o[0]),
+             __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
     if (q0 + row < p.Lq) {
       const float inv = 1.0f / l;
       float* op = p.out + (static_cast<long long>(b) * p.Lq + q0 + row) * p.ldo + h * 32;
@@ -261,7 +275,8 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
   if (!e.empty()) return e;
   e = encode_tmap_2d(&tmK, kTF32, d.k, hd, static_cast<long long>(d.B) * d.Lk, static_cast<long long>(d.ldk) * 4, 32, NK);
   if (!e.empty()) return e;
-  e = encode_tmap_2d(&tmV, kTF32, d.v, hd, static_cast<long long>(d.B) * d.Lk, static_cast<long long>(d.ldv) * 4, 32, NK);
+  e = encode_tmap_2d(&tmV, kTF32, d.v, hd, static_cast<long long>(d.B) * d.Lk, static_cast<long long>(d.ldv) * 4, 32, NK,
+                     /*swizzle_atom32=*/true);
   if (!e.empty()) return e;
   AttnTcParams p;
   p.out = reinterpret_cast<float*>(d.out);
@@ -270,6 +285,8 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
   p.Lk = d.Lk;
   p.scale_log2e = d.scale * 1.4426950408889634f;
   p.exact_out = d.exact_out;
+  static const bool dbg = getenv("SPE_ATTN_DEBUG") != nullptr;
+  p.debug = dbg ? 1 : 0;
   dim3 grid((d.Lq + kQRows - 1) / kQRows, d.heads, d.B);
   ProfScope ps(kFamAttention, s);
   kfn<<<grid, kThreads, SM::BYTES, s>>>(tmQ, tmK, tmV, p);

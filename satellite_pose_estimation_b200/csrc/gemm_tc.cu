@@ -467,7 +467,8 @@ EncodeTiledFn get_encode_fn(std::string* err) {
 }
 
 std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, const cuuint64_t* dims,
-                       const cuuint64_t* strides_bytes, const cuuint32_t* box, int spatial_stride = 1) {
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box, int spatial_stride = 1,
+                       bool swizzle_atom32 = false) {
   std::string err;
   EncodeTiledFn fn = get_encode_fn(&err);
   if (!fn) return err;
@@ -477,7 +478,9 @@ std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, con
   if (rank < 4) estr[1] = estr[2] = 1;
   CUresult r = fn(m, dt == kTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -515,11 +518,11 @@ std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap
 }  // namespace
 
 std::string encode_tmap_2d(void* map, Dtype dt, const void* base, long long dim0, long long dim1,
-                           long long stride1_bytes, int box0, int box1) {
+                           long long stride1_bytes, int box0, int box1, bool swizzle_atom32) {
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(dim0), static_cast<cuuint64_t>(dim1)};
   cuuint64_t str[1] = {static_cast<cuuint64_t>(stride1_bytes)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
-  return encode_map(reinterpret_cast<CUtensorMap*>(map), dt, 2, base, dims, str, box);
+  return encode_map(reinterpret_cast<CUtensorMap*>(map), dt, 2, base, dims, str, box, 1, swizzle_atom32);
 }
 
 std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t stream) {

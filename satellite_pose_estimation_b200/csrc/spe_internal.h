@@ -70,9 +70,10 @@ std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s);
 // tcgen05 / TMEM path (attention_tc.cu); launch_attention dispatches to it when supported
 bool attention_tc_supported(Dtype dt, const AttnDesc& d);
 std::string launch_attention_tc(const AttnDesc& d, cudaStream_t s);
-// 2-D row-major tensor map (dim0 contiguous, SWIZZLE_128B); `map` points at a CUtensorMap
+// 2-D row-major tensor map (dim0 contiguous); SWIZZLE_128B, or SWIZZLE_128B_ATOM_32B (32-byte swizzle granules: the
+// only layout the tensor core accepts for MN-major TF32 operands); `map` points at a CUtensorMap
 std::string encode_tmap_2d(void* map, Dtype dt, const void* base, long long dim0, long long dim1,
-                           long long stride1_bytes, int box0, int box1);
+                           long long stride1_bytes, int box0, int box1, bool swizzle_atom32 = false);
 
 // ---- heads (heads.cu) ----
 std::string launch_head_final(Dtype dt, const void* hs, const void* h2, const void* s2, long long rows,

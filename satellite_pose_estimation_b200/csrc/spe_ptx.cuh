@@ -210,15 +210,17 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-// MN-major operand tile (rows = K index, 128-byte rows of the contiguous M/N dimension, SWIZZLE_128B):
-// canonical ((T,8,m),(8,k)) : ((1,T,LBO),(8T,SBO)); one 128-byte atom along M/N (m = 1), 8-row K groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+// MN-major TF32 operand tile (rows = K index, each row = 128 contiguous bytes of the M/N dimension).  32-bit
+// MN-major operands only exist in the SWIZZLE_128B_BASE32B layout (32-byte swizzle granules, written by TMA mode
+// SWIZZLE_128B_ATOM_32B): canonical ((8,n),(4,k)) : ((1,LBO),(8,SBO)) in 16-byte units, i.e. swizzle atoms of 4 K-rows
+// (512 B); one atom along M/N here.
+__device__ __forceinline__ uint64_t umma_desc_mn_tf32(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>(1024 >> 4) << 16;   // LBO: stride between M/N atoms (single atom here)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;   // SBO: stride between 8-row K groups
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(512 >> 4) << 16;    // LBO: stride between M/N atoms (single atom: unused)
+  d |= static_cast<uint64_t>(512 >> 4) << 32;    // SBO: stride between 4-row K atoms
+  d |= static_cast<uint64_t>(1) << 46;           // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(1) << 61;           // SWIZZLE_128B_BASE32B
   return d;
 }
 

@@ -15,6 +15,11 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _rna_tf32(x):
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def _rel(got, ref):
     return ((got.double() - ref).abs().max() / ref.abs().max()).item()
 
@@ -87,13 +92,16 @@ def test_implicit_conv_stride2(lib, cuda_dev, dt, NB, H, Cin, Cout, R):
 
 
 @pytest.mark.parametrize("dt", [0, 1])
-@pytest.mark.parametrize("B,Lq,Lk", [(2, 784, 784), (3, 40, 40), (2, 40, 784), (1, 100, 1024), (1, 1, 5)])
+@pytest.mark.parametrize("B,Lq,Lk", [(2, 784, 784), (3, 40, 40), (2, 40, 784), (1, 100, 1024), (1, 1, 5), (3, 1024, 1024),
+                                     (2, 200, 300)])
 def test_attention(lib, cuda_dev, dt, B, Lq, Lk):
     torch.manual_seed(Lq + Lk)
     tdt = DT[dt]
     q = torch.randn(B, Lq, 256, device=cuda_dev).to(tdt)
     k = torch.randn(B, Lk, 256, device=cuda_dev).to(tdt)
     v = torch.randn(B, Lk, 256, device=cuda_dev).to(tdt)
+    if dt == 0:   # in the pipeline Q/K/V are GEMM outputs already rounded to TF32 (what the tensor core consumes)
+        q, k, v = _rna_tf32(q), _rna_tf32(k), _rna_tf32(v)
     out = torch.full((B, Lq, 256), float("nan"), device=cuda_dev).to(tdt)
     assert lib.spe_debug_attention(dt, _p(q), _p(k), _p(v), _p(out), B, 8, Lq, Lk, 256, 256, 256, 256, None) == 0
     torch.cuda.synchronize()
@@ -103,11 +111,6 @@ def test_attention(lib, cuda_dev, dt, B, Lq, Lk):
     ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 32 ** 0.5, -1) @ vh).transpose(1, 2).reshape(B, Lq, 256)
     assert not torch.isnan(out.float()).any()
     assert _rel(out, ref) < (2e-3 if dt == 0 else 8e-3)
-
-
-def _rna_tf32(x):
-    i = x.contiguous().view(torch.int32)
-    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 @pytest.mark.parametrize("M,N,K,relu,res_mod", [(40, 256, 256, 0, 0), (2560, 768, 256, 0, 40), (2560, 2048, 256, 1, 0),
