@@ -153,16 +153,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(s_full, static_cast<uint32_t>(j) & 1u, 15);
       tc_fence_after();
       const int key0 = j * NK;
-      // ---- pass 1: row maximum of this chunk
-      float mx = -INFINITY;
+      const bool full = key0 + NK <= p.Lk;                 // no ragged tail inside this chunk (the common case)
+      // ---- pass 1: row maximum of this chunk (four independent chains: a thread owns a whole row, so latency,
+      //      not bandwidth, is what this loop fights)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int cc = 0; cc < NK / 32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
         tmem_wait_ld();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (key0 + cc * 32 + i < p.Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + cc * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        }
       }
       if constexpr (NK % 32 != 0) {
         uint32_t v[16];
@@ -170,30 +177,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (key0 + (NK / 32) * 32 + i < p.Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+          if (full || key0 + (NK / 32) * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
       }
-      if (p.debug && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {   // warp-uniform: .sync.aligned ld
-        uint32_t v[16];
-        tmem_ld_32x16(trow, v);
-        tmem_wait_ld();
-        if (row < 2) printf("[attn dbg] chunk %d row %d S[0..3] = %f %f %f %f  mx %f\n", j, row, __uint_as_float(v[0]),
-               __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]), mx);
-      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m, mx);                    // finite: every chunk holds at least one valid key
       const float alpha = ex2((m - m_new) * c);            // 0 on the first chunk (m = -inf)
       const float mc = m_new * c;
       // ---- pass 2: probabilities, written back over the scores as TF32
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int cc = 0; cc < NK / 32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
         tmem_wait_ld();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pr = (key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-          sum += pr;
-          v[i] = rna_bits(pr);
+          for (int i = 0; i < 32; ++i) {
+            const float pr = ex2(fmaf(__uint_as_float(v[i]), c, -mc));
+            sum4[i & 3] += pr;
+            v[i] = rna_bits(pr);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float pr = (key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+            sum4[i & 3] += pr;
+            v[i] = rna_bits(pr);
+          }
         }
         tmem_st_32x32(trow + static_cast<uint32_t>(cc * 32), v);
       }
@@ -203,12 +213,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float pr = (key0 + (NK / 32) * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-          sum += pr;
+          const float pr = (full || key0 + (NK / 32) * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          sum4[i & 3] += pr;
           v[i] = rna_bits(pr);
         }
         tmem_st_32x16(trow + static_cast<uint32_t>((NK / 32) * 32), v);
       }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       l = l * alpha + sum;
       m = m_new;
       // ---- rescale the running output when this warp's maxima moved (needs P V_{j-1} to have landed)

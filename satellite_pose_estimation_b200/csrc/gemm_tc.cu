@@ -20,6 +20,7 @@
 #include "spe_ptx.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace spe {
 
@@ -42,14 +43,20 @@ template <> struct GemmTraits<__nv_bfloat16> {
 // X3 = error-compensated "3xTF32": A = A_hi + A_lo (split in shared memory by dedicated warps), W = W_hi + W_lo
 // (split once at weight load, stored as [N, 2K] = [W_hi | W_lo]); D = A_hi W_hi + A_lo W_hi + A_hi W_lo in one TMEM
 // accumulator.  Used where TF32's 10-bit mantissa is not enough (decoder + heads).
-template <int BN, bool X3> struct StageCfg {
+// EPI8 = eight epilogue warps instead of four (two per TMEM lane quarter, interleaved over the 32-column chunks).
+// Small-K GEMMs are bound by the epilogue's instruction latency and by how many residual loads it keeps in flight,
+// not by the tensor pipe; they trade smem stages for the wider epilogue.
+template <int BN, bool X3, bool EPI8> struct StageCfg {
+  static_assert(!(X3 && EPI8), "the 3xTF32 variant already spends its extra warps on the operand split");
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = X3 ? 2 * (A_BYTES + B_BYTES) : (A_BYTES + B_BYTES);
-  static constexpr int STAGES = X3 ? (BN <= 64 ? 4 : 3) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4));
-  static constexpr int THREADS = X3 ? 320 : 192;
+  static constexpr int EPI_WARPS = EPI8 ? 8 : 4;
+  static constexpr int STAGES = X3 ? (BN <= 64 ? 4 : 3)
+                                   : (EPI8 ? (BN <= 64 ? 7 : (BN <= 128 ? 5 : 3)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
+  static constexpr int THREADS = (X3 || EPI8) ? 320 : 192;
   static constexpr int TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
-  static constexpr int STAGING_BYTES = 4 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
+  static constexpr int STAGING_BYTES = EPI_WARPS * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 2 * 2 * BN * 4 /*scale,bias x2*/ +
                                     (3 * STAGES + 4) * 8 /*barriers*/ + 16 /*tmem ptr*/ + 1024 /*align slack*/;
 };
@@ -81,12 +88,14 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <typename T, int BN, bool X3>
-__global__ void __launch_bounds__((StageCfg<BN, X3>::THREADS), 1)
+template <typename T, int BN, bool X3, bool EPI8>
+__global__ void __launch_bounds__((StageCfg<BN, X3, EPI8>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKParams p) {
   using Tr = GemmTraits<T>;
-  using Cfg = StageCfg<BN, X3>;
+  using Cfg = StageCfg<BN, X3, EPI8>;
+  constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+  constexpr int CSTEP = EPI_WARPS / 4;   // chunk stride of one epilogue warp
   static_assert(!X3 || sizeof(T) == 4, "3xTF32 needs fp32 storage");
   constexpr int BK = Tr::BK;
   constexpr int STAGES = Cfg::STAGES;
@@ -120,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -241,7 +250,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // row inside the 128-row tile
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = threadIdx.x - 64;        // 0 .. 32 * EPI_WARPS - 1
+    const int half = (warp - 2) >> 2;       // which interleaved set of column chunks this warp handles
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -270,12 +280,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       float* s_scale = sm_scale + buf * BN;
       float* s_bias = sm_bias + buf * BN;
-      for (int j = et; j < BN; j += 128) {
+      for (int j = et; j < BN; j += 32 * EPI_WARPS) {
         const bool ok = (n0 + j) < p.N;
         s_scale[j] = (p.scale != nullptr && ok) ? p.scale[n0 + j] : 1.0f;
         s_bias[j] = (p.bias != nullptr && ok) ? p.bias[n0 + j] : 0.0f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 32 * EPI_WARPS);
       mbar_wait(&tfull_bar[buf], use_par, 4);
       tc_fence_after();
 
@@ -313,9 +323,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       };
-      if (coop_res) fetch_residual(n0);
+      if (coop_res) fetch_residual(n0 + half * 32);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += CSTEP) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
         const int ncol = n0 + c * 32;
@@ -366,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
           }
         }
-        if (coop_res && c + 1 < BN / 32) fetch_residual(ncol + 32);   // next chunk's tile, in flight during the stores
+        if (coop_res && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next tile, in flight during the stores
         tmem_wait_ld();
         if (col_ok && rows_here > 0) {
 #pragma unroll
@@ -494,12 +504,12 @@ std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, con
   return "";
 }
 
-template <typename T, int BN, bool X3>
+template <typename T, int BN, bool X3, bool EPI8>
 std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap& tmA, const CUtensorMap& tmB,
                      int num_sms, cudaStream_t stream) {
-  using Cfg = StageCfg<BN, X3>;
+  using Cfg = StageCfg<BN, X3, EPI8>;
   static bool attr_set = false;
-  auto kfn = gemm_tc_kernel<T, BN, X3>;
+  auto kfn = gemm_tc_kernel<T, BN, X3, EPI8>;
   if (!attr_set) {
     SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
@@ -635,19 +645,34 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     if (!err.empty()) return err;
   }
 
+  // short K loops cannot hide a 4-warp epilogue: give those GEMMs the 8-warp epilogue (and fewer smem stages)
+  static const int epi_force = getenv("SPE_GEMM_EPI8") ? atoi(getenv("SPE_GEMM_EPI8")) : -1;
+  const bool epi8 = !d.x3 && (epi_force >= 0 ? epi_force != 0 : kp.num_kb <= 16);
+#define SPE_LAUNCH(TT, BNV, X3V, E8V) return launch_t<TT, BNV, X3V, E8V>(d, kp, tmA, tmB, num_sms, stream)
   if (dt == kTF32) {
     if (d.x3) {
-      if (BN == 64) return launch_t<float, 64, true>(d, kp, tmA, tmB, num_sms, stream);
-      return launch_t<float, 128, true>(d, kp, tmA, tmB, num_sms, stream);
+      if (BN == 64) SPE_LAUNCH(float, 64, true, false);
+      SPE_LAUNCH(float, 128, true, false);
     }
-    if (BN == 64) return launch_t<float, 64, false>(d, kp, tmA, tmB, num_sms, stream);
-    if (BN == 128) return launch_t<float, 128, false>(d, kp, tmA, tmB, num_sms, stream);
-    return launch_t<float, 256, false>(d, kp, tmA, tmB, num_sms, stream);
+    if (epi8) {
+      if (BN == 64) SPE_LAUNCH(float, 64, false, true);
+      if (BN == 128) SPE_LAUNCH(float, 128, false, true);
+      SPE_LAUNCH(float, 256, false, true);
+    }
+    if (BN == 64) SPE_LAUNCH(float, 64, false, false);
+    if (BN == 128) SPE_LAUNCH(float, 128, false, false);
+    SPE_LAUNCH(float, 256, false, false);
   } else {
-    if (BN == 64) return launch_t<__nv_bfloat16, 64, false>(d, kp, tmA, tmB, num_sms, stream);
-    if (BN == 128) return launch_t<__nv_bfloat16, 128, false>(d, kp, tmA, tmB, num_sms, stream);
-    return launch_t<__nv_bfloat16, 256, false>(d, kp, tmA, tmB, num_sms, stream);
+    if (epi8) {
+      if (BN == 64) SPE_LAUNCH(__nv_bfloat16, 64, false, true);
+      if (BN == 128) SPE_LAUNCH(__nv_bfloat16, 128, false, true);
+      SPE_LAUNCH(__nv_bfloat16, 256, false, true);
+    }
+    if (BN == 64) SPE_LAUNCH(__nv_bfloat16, 64, false, false);
+    if (BN == 128) SPE_LAUNCH(__nv_bfloat16, 128, false, false);
+    SPE_LAUNCH(__nv_bfloat16, 256, false, false);
   }
+#undef SPE_LAUNCH
 }
 
 }  // namespace spe
