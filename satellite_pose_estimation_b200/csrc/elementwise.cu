@@ -253,6 +253,23 @@ layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, c
     const int c = (i * 32 + lane) * VN;
     Vec<T> r;
 #pragma unroll
+    if (exact == 2) {
+      // 3xTF32 operand layout [hi | lo | hi] (row stride 768): the consumer is a plain K = 768 GEMM against
+      // [W_hi | W_hi | W_lo], i.e. A_hi W_hi + A_lo W_hi + A_hi W_lo without any in-kernel operand split
+      Vec<T> hi, lo;
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        const float y = (x[i * VN + e] - mean) * rstd * gamma[c + e] + beta[c + e];
+        const float h = rna_tf32(y);
+        hi.set_exact(e, h);
+        lo.set(e, y - h);
+      }
+      vstore(out + row * 768 + c, hi);
+      vstore(out + row * 768 + 256 + c, lo);
+      vstore(out + row * 768 + 512 + c, hi);
+      continue;
+    }
+#pragma unroll
     for (int e = 0; e < VN; ++e) {
       const float y = (x[i * VN + e] - mean) * rstd * gamma[c + e] + beta[c + e];
       if (exact) r.set_exact(e, y); else r.set(e, y);

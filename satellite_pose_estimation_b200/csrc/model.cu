@@ -73,6 +73,16 @@ __global__ void addend_kernel(const float* __restrict__ X, int T, int K, const f
   out[static_cast<long long>(t) * out_ld + ncol0 + n] = acc + (b ? b[n] : 0.f);
 }
 
+// round-to-nearest (ties away) fp32 -> TF32, the host twin of cvt.rna.tf32.f32
+inline float host_rna_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
 struct HostTensor {
   const float* data;
   std::vector<long long> shape;
@@ -154,7 +164,9 @@ struct spe_ctx {
   GemmW s8_lat, s16_lat, out_conv, input_proj;
   std::vector<EncLayer> enc;
   std::vector<DecLayer> dec;
-  GemmW ca_kv_all;             // [L*512, 256]
+  GemmW ca_kv_all;             // [L*512, 256]  (TF32 mode: [L*512, 768] = [W_hi | W_hi | W_lo])
+  bool kv_split3 = false;
+  void* XS = nullptr;          // last encoder output as [hi | lo | hi], [B*tokens, 768]
   float* ca_kv_addend = nullptr;  // [tokens, L*512]
   float *dn_g = nullptr, *dn_b = nullptr;
   GemmW pt0, pt1, sg0, sg1;
@@ -495,7 +507,23 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(load_vec(ctx, ws, p + ".norm3.weight", E, &L.n3g));
       TRY_S(load_vec(ctx, ws, p + ".norm3.bias", E, &L.n3b));
     }
-    TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all, true));
+    if (ctx->dt == kTF32) {
+      // 3xTF32 with the operand split hoisted out of the GEMM: the last encoder LayerNorm emits [x_hi | x_lo | x_hi]
+      // and the weights are stored as [W_hi | W_hi | W_lo], so a plain K = 3E GEMM yields the compensated product
+      std::vector<float> w3(static_cast<size_t>(LD) * 2 * E * 3 * E);
+      for (int n = 0; n < LD * 2 * E; ++n)
+        for (int k = 0; k < E; ++k) {
+          const float w = kv_w[static_cast<size_t>(n) * E + k];
+          const float hi = host_rna_tf32(w), lo = host_rna_tf32(w - hi);
+          float* row = w3.data() + static_cast<size_t>(n) * 3 * E;
+          row[k] = hi; row[E + k] = hi; row[2 * E + k] = lo;
+        }
+      TRY_S(upload_gemm_w(ctx, w3, LD * 2 * E, 3 * E, &ctx->ca_kv_all));
+      ctx->kv_split3 = true;
+    } else {
+      TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all));
+      ctx->kv_split3 = false;
+    }
     TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.weight", E, &ctx->dn_g));
     TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.bias", E, &ctx->dn_b));
     // ---- heads
@@ -554,6 +582,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
   }
   TRY_S(A(&ctx->X, B * T * 256));
   TRY_S(A(&ctx->X2, B * T * 256));
+  if (ctx->dt == kTF32) TRY_S(A(&ctx->XS, B * T * 768));
   TRY_S(A(&ctx->QKV, B * T * 768));
   TRY_S(A(&ctx->ATT, B * T * 256));
   TRY_S(A(&ctx->HID, B * T * FF));
@@ -759,8 +788,15 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
     TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc));
     TRY_S(f.gemm(Xc, Bl * T, L.ff1, ctx->HID, c.dim_feedforward, true));
     TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, Xc, 256));
-    // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: keep it unrounded
-    TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, i == c.enc_layers - 1 ? 1 : 0));
+    // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: emit it pre-split
+    const bool last = i == c.enc_layers - 1;
+    if (last && ctx->kv_split3) {
+      void* XSc = static_cast<uint8_t*>(ctx->XS) + (static_cast<uint8_t*>(Xc) - static_cast<uint8_t*>(ctx->X)) * 3;
+      TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, XSc, 2));
+      if (ctx->taps_enabled) TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, 1));
+    } else {
+      TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, last ? 1 : 0));
+    }
     const std::string nm = "enc" + std::to_string(i);
     TRY_S(f.tap(nm.c_str(), Xc, Bl * T * 256));
   }
@@ -781,7 +817,17 @@ static std::string forward_tail(spe_ctx* ctx, int B, float* logits, float* point
   const int Q = c.num_queries, LD = c.dec_layers;
   const long long MQ = Bl * Q;
   const int kvld = LD * 512;
-  TRY_S(f.gemm(ctx->X, Bl * T, ctx->ca_kv_all, ctx->KV, kvld, false, ctx->ca_kv_addend, kvld, Ti, 1));
+  {
+    GemmDesc d;   // K/V of all decoder layers from the encoder memory
+    d.mode = 0;
+    d.A = ctx->kv_split3 ? ctx->XS : ctx->X;
+    d.M = Bl * T; d.K = ctx->ca_kv_all.K; d.lda = ctx->ca_kv_all.K;
+    d.Wt = ctx->ca_kv_all.w; d.N = ctx->ca_kv_all.N;
+    d.residual = ctx->ca_kv_addend; d.res_ld = kvld; d.res_mod = Ti; d.res_f32 = 1;
+    d.out = ctx->KV; d.out_ld = kvld;
+    d.round_out = ctx->kv_split3 ? 0 : 1;   // the decoder attention rounds its own operands
+    TRY_S(launch_gemm(f.dt, d, ctx->num_sms, st));
+  }
   SPE_CUDA_TRY(cudaMemsetAsync(ctx->TGT, 0, static_cast<size_t>(MQ * 256 * f.es), st));
   for (int i = 0; i < LD; ++i) {
     const DecLayer& L = ctx->dec[i];

@@ -52,7 +52,7 @@ std::string launch_im2col_nhwc(Dtype dt, const void* in, int NB, int H, int W, i
                                int pad, void* out, cudaStream_t s);
 std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s);
 std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s);
-// exact != 0: keep the full fp32 result (outputs read by the fp32 heads); otherwise fp32 storage is TF32-rounded
+// exact = 0: fp32 storage is TF32-rounded; 1: full fp32 result; 2: 3xTF32 operand layout [hi | lo | hi], row stride 768
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
                              int dim, void* out, cudaStream_t s, int exact = 0);
 
