@@ -289,152 +289,140 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[buf], use_par, 4);
       tc_fence_after();
 
-      // Thread t of the warp owns accumulator row t (that is how tcgen05.ld hands the data out), but a warp-wide
-      // access "32 rows x 16 bytes" touches 32 different 128-byte lines.  Residual loads and output stores therefore
-      // go through a per-warp 32 x 128-byte staging tile in shared memory (XOR-swizzled 16-byte chunks, conflict
-      // free both row-wise and in the cooperative pattern): global memory only ever sees "4 rows x 128 contiguous
-      // bytes" per instruction.
-      constexpr int ROWB = 32 * static_cast<int>(sizeof(T));   // bytes of one 32-column row chunk: 128 (fp32) / 64 (bf16)
-      constexpr int CPR = ROWB / 16;                            // 16-byte chunks per row: 8 / 4
-      constexpr int RPI = 32 / CPR;                             // rows covered by one cooperative instruction: 4 / 8
+      // tcgen05.ld hands thread t accumulator row t, but a warp-wide access "32 rows x 16 bytes" touches 32 different
+      // 128-byte lines.  So each 32x32 fp32 accumulator chunk is transposed ONCE through a per-warp XOR-swizzled
+      // 32 x 128-byte staging tile (raw accumulators in, conflict-free both ways), and everything else -- BN
+      // scale/bias, residual add, ReLU, rounding, store -- happens in the coalesced domain where a warp instruction
+      // covers RPI whole rows x 16 bytes per lane: global memory only sees full contiguous row segments, the
+      // residual needs no staging at all, and each thread keeps one fixed group of G columns (one scale/bias fetch).
+      constexpr int G = 16 / static_cast<int>(sizeof(T));        // columns per lane: 4 (fp32) / 8 (bf16)
+      constexpr int CPR = 32 / G;                                // lanes per row: 8 / 4
+      constexpr int RPI = 32 / CPR;                              // rows per warp instruction: 4 / 8
+      constexpr int NIT = 32 / RPI;                              // instructions per chunk: 8 / 4
       uint8_t* stg = sm_staging + (warp - 2) * 4096;
-      const int crow = lane / CPR, cseg = lane % CPR;           // cooperative role of this lane
+      const int crow = lane / CPR, cseg = lane % CPR;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-      const int rows_here = valid_rows - q * 32;                // valid rows in this warp's 32-row slab (may be <= 0)
-      const long long slab0 = m_base + q * 32;                  // first global row of the slab
-      const bool resid = p.residual != nullptr;
-      const bool res32 = (sizeof(T) == 4) || p.res_f32;         // residual element size (fp32 addends in bf16 mode)
-      const bool coop_res = resid && rows_here > 0 && !(res32 && sizeof(T) == 2);
-      // residual tile of one 32-column chunk, fetched one chunk ahead so its latency hides behind the stores
-      uint4 rx[32 / RPI];
+      const int rows_here = valid_rows - q * 32;                 // valid rows in this warp's 32-row slab (may be <= 0)
+      const long long slab0 = m_base + q * 32;                   // first global row of the slab
+      const bool resid = p.residual != nullptr && rows_here > 0;
+      const int res_es = (sizeof(T) == 4 || p.res_f32) ? 4 : 2;  // residual element size (fp32 addends in bf16 mode)
+      // per-thread row pointers advance by a constant stride; the batch-broadcast addend wraps with one compare
+      const long long out_step = static_cast<long long>(RPI) * p.out_ld * static_cast<long long>(sizeof(T));
+      uint8_t* out0 = reinterpret_cast<uint8_t*>(p.out) +
+                      ((slab0 + crow) * p.out_ld) * static_cast<long long>(sizeof(T)) + cseg * 16;
+      int rr0 = 0;
+      if (resid) rr0 = p.res_mod > 0 ? static_cast<int>(static_cast<unsigned>(slab0 + crow) % static_cast<unsigned>(p.res_mod))
+                                     : 0;
+      const uint8_t* res_base = reinterpret_cast<const uint8_t*>(p.residual);
+
+      // residual values of this lane for one chunk: NIT rows x G columns (prefetched one chunk ahead)
+      uint4 rx[NIT][2];
       auto fetch_residual = [&](int ncol_) {
 #pragma unroll
-        for (int i = 0; i < 32 / RPI; ++i) {
+        for (int i = 0; i < NIT; ++i) {
+          rx[i][0] = make_uint4(0u, 0u, 0u, 0u);
+          rx[i][1] = make_uint4(0u, 0u, 0u, 0u);
           const int r = i * RPI + crow;
-          rx[i] = make_uint4(0u, 0u, 0u, 0u);
           if (r < rows_here && ncol_ < p.N) {
-            const long long grow = slab0 + r;
-            const long long rr = (p.res_mod > 0) ? static_cast<long long>(static_cast<unsigned>(grow) %
-                                                                          static_cast<unsigned>(p.res_mod))
-                                                 : grow;
-            const uint8_t* gp = reinterpret_cast<const uint8_t*>(p.residual) +
-                                (rr * p.res_ld + ncol_) * static_cast<long long>(sizeof(T)) + cseg * 16;
-            rx[i] = *reinterpret_cast<const uint4*>(gp);
+            long long rr;
+            if (p.res_mod > 0) {
+              int w = rr0 + i * RPI;
+              if (w >= p.res_mod) w -= p.res_mod;
+              rr = w;
+            } else {
+              rr = slab0 + r;
+            }
+            const uint8_t* gp = res_base + (rr * p.res_ld + ncol_ + cseg * G) * static_cast<long long>(res_es);
+            rx[i][0] = *reinterpret_cast<const uint4*>(gp);
+            if (res_es * G > 16) rx[i][1] = *reinterpret_cast<const uint4*>(gp + 16);   // 8 fp32 addends (bf16 mode)
           }
         }
       };
-      if (coop_res) fetch_residual(n0 + half * 32);
+      if (resid) fetch_residual(n0 + half * 32);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += CSTEP) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
         const int ncol = n0 + c * 32;
         const bool col_ok = ncol < p.N;
-        float f[32];
-        float radd[32];
-        if (resid && col_ok && rows_here > 0) {
-          if (!coop_res) {
-            // fp32 addend while storage is bf16: 128-byte rows do not fit the 64-byte-row staging; these tensors
-            // are tiny and L2-resident, read them directly
-            const long long grow = slab0 + lane;
-            const long long rr = (p.res_mod > 0) ? static_cast<long long>(static_cast<unsigned>(grow) %
-                                                                          static_cast<unsigned>(p.res_mod))
-                                                 : grow;
-            if (lane < rows_here) {
-              const float* rp = reinterpret_cast<const float*>(p.residual) + rr * p.res_ld + ncol;
+        tmem_wait_ld();
+        // own row -> staging (raw fp32 accumulators)
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = ld_f4(rp + j);
-                radd[j] = r4.x; radd[j + 1] = r4.y; radd[j + 2] = r4.z; radd[j + 3] = r4.w;
-              }
-            }
-          } else {
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((k ^ (lane & 7)) * 16)) =
+              make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        __syncwarp();
+        // this lane's fixed column group: scale / bias
+        float sc[G], bi[G];
 #pragma unroll
-            for (int i = 0; i < 32 / RPI; ++i) {
-              const int r = i * RPI + crow;
-              *reinterpret_cast<uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16)) = rx[i];
-            }
-            __syncwarp();
-            if (lane < rows_here) {
+        for (int u = 0; u < G; u += 4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(s_scale + c * 32 + cseg * G + u);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cseg * G + u);
+          sc[u] = s4.x; sc[u + 1] = s4.y; sc[u + 2] = s4.z; sc[u + 3] = s4.w;
+          bi[u] = b4.x; bi[u + 1] = b4.y; bi[u + 2] = b4.z; bi[u + 3] = b4.w;
+        }
+        float f[NIT][G];
 #pragma unroll
-              for (int j = 0; j < CPR; ++j) {
-                const uint4 x = *reinterpret_cast<const uint4*>(stg + lane * ROWB + ((j ^ (lane % CPR)) * 16));
-                if (sizeof(T) == 4) {
-                  radd[4 * j] = __uint_as_float(x.x); radd[4 * j + 1] = __uint_as_float(x.y);
-                  radd[4 * j + 2] = __uint_as_float(x.z); radd[4 * j + 3] = __uint_as_float(x.w);
-                } else {
-                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+        for (int i = 0; i < NIT; ++i) {
+          const int r = i * RPI + crow;
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const float2 ff = __bfloat1622float2(h[u]);
-                    radd[8 * j + 2 * u] = ff.x;
-                    radd[8 * j + 2 * u + 1] = ff.y;
-                  }
-                }
-              }
-            }
-            __syncwarp();
+          for (int u = 0; u < G; u += 4) {
+            const int k = cseg * (G / 4) + u / 4;                  // 16-byte chunk of the staging row
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((k ^ (r & 7)) * 16));
+            f[i][u] = fmaf(a4.x, sc[u], bi[u]);
+            f[i][u + 1] = fmaf(a4.y, sc[u + 1], bi[u + 1]);
+            f[i][u + 2] = fmaf(a4.z, sc[u + 2], bi[u + 2]);
+            f[i][u + 3] = fmaf(a4.w, sc[u + 3], bi[u + 3]);
           }
         }
-        if (coop_res && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next tile, in flight during the stores
-        tmem_wait_ld();
-        if (col_ok && rows_here > 0) {
+        __syncwarp();   // staging free for the next chunk
+        if (resid && col_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c * 32 + j);
-            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c * 32 + j);
-            f[j + 0] = fmaf(__uint_as_float(v[j + 0]), sc.x, bi.x);
-            f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y);
-            f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z);
-            f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w);
-          }
-          if (resid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += radd[j];
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          // ---- output: own row -> staging -> coalesced global
-          if (lane < rows_here) {
-            if (sizeof(T) == 4) {
-              // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here so
-              // the next layer's products are exact and the error stays unbiased
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 o4 = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                if (p.round_out) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
-                *reinterpret_cast<float4*>(stg + lane * ROWB + ((j ^ (lane % CPR)) * 16)) = o4;
+          for (int i = 0; i < NIT; ++i) {
+            if (res_es == 4) {
+              f[i][0] += __uint_as_float(rx[i][0].x); f[i][1] += __uint_as_float(rx[i][0].y);
+              f[i][2] += __uint_as_float(rx[i][0].z); f[i][3] += __uint_as_float(rx[i][0].w);
+              if (G == 8) {
+                f[i][G - 4] += __uint_as_float(rx[i][1].x); f[i][G - 3] += __uint_as_float(rx[i][1].y);
+                f[i][G - 2] += __uint_as_float(rx[i][1].z); f[i][G - 1] += __uint_as_float(rx[i][1].w);
               }
             } else {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rx[i][0]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int u = 0; u < 4; ++u) {
+                const float2 ff = __bfloat1622float2(h[u]);
+                f[i][(2 * u) % G] += ff.x;
+                f[i][(2 * u + 1) % G] += ff.y;
+              }
+            }
+          }
+        }
+        if (resid && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next chunk, in flight during the stores
+        if (col_ok) {
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int r = i * RPI + crow;
+            if (p.relu) {
+#pragma unroll
+              for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
+            }
+            if (r < rows_here) {
+              uint8_t* gp = out0 + i * out_step + static_cast<long long>(ncol) * static_cast<long long>(sizeof(T));
+              if (sizeof(T) == 4) {
+                // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here
+                // so the next layer's products are exact and the error stays unbiased
+                float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
+                if (p.round_out) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
+                *reinterpret_cast<float4*>(gp) = o4;
+              } else {
                 uint4 o8;
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[8 * j + 2 * u], f[8 * j + 2 * u + 1]);
-                *reinterpret_cast<uint4*>(stg + lane * ROWB + ((j ^ (lane % CPR)) * 16)) = o8;
+                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[i][(2 * u) % G], f[i][(2 * u + 1) % G]);
+                *reinterpret_cast<uint4*>(gp) = o8;
               }
             }
           }
-          __syncwarp();
-          uint4 ox[32 / RPI];
-#pragma unroll
-          for (int i = 0; i < 32 / RPI; ++i) {
-            const int r = i * RPI + crow;
-            ox[i] = *reinterpret_cast<const uint4*>(stg + r * ROWB + ((cseg ^ (r % CPR)) * 16));
-          }
-#pragma unroll
-          for (int i = 0; i < 32 / RPI; ++i) {
-            const int r = i * RPI + crow;
-            if (r < rows_here) {
-              uint8_t* gp = reinterpret_cast<uint8_t*>(p.out) +
-                            ((slab0 + r) * p.out_ld + ncol) * static_cast<long long>(sizeof(T)) + cseg * 16;
-              *reinterpret_cast<uint4*>(gp) = ox[i];
-            }
-          }
-          __syncwarp();
         }
       }
       tc_fence_before();
