@@ -11,7 +11,8 @@
 //   warps 2..5  softmax: thread t owns score row t (tcgen05.ld gives each thread its own row, so the running max and
 //               sum need no cross-thread reduction), writes P back over S in TMEM (tcgen05.st) and rescales the
 //               32-column O accumulator when the running maximum moves (online softmax, fp32 statistics)
-// TMEM columns: [0, NK) scores / probabilities, [128, 160) output accumulator.
+// TMEM columns: two score / probability buffers [0, NK) and [NK, 2 NK) (QK^T of chunk j+1 is issued while the softmax
+// of chunk j runs), output accumulator at [2 NK, 2 NK + 32).
 #include "spe_internal.h"
 #include "profile.h"
 #include "spe_ptx.cuh"
@@ -23,7 +24,6 @@ namespace spe {
 namespace {
 
 constexpr int kQRows = 128;
-constexpr int kOCol = 128;          // first TMEM column of the O accumulator
 constexpr int kTmemCols = 256;
 constexpr int kThreads = 192;
 
@@ -40,7 +40,7 @@ template <int NK> struct AttnSmem {
   static constexpr int Q_BYTES = kQRows * 128;
   static constexpr int KV_BYTES = NK * 128;
   static constexpr int STAGE_BYTES = 2 * KV_BYTES;
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = 3;
   static constexpr int BYTES = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 16 + 1024;
 };
 
@@ -67,11 +67,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sKV = smem + SM::Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + SM::STAGES * SM::STAGE_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* pv_done = bars + 7;
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* pv_done = bars + 10;
+  constexpr uint32_t kOCol = 2 * NK;
+  static_assert(2 * NK + 32 <= kTmemCols, "two score buffers and the output accumulator must fit the TMEM allocation");
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,8 +86,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
     fence_mbar_init();
@@ -104,8 +107,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_expect_tx(q_full, SM::Q_BYTES);
       tma_load_2d(sQ, &tmQ, q_full, h * 32, b * p.Lq + q0);
       for (int j = 0; j < nchunks; ++j) {
-        const int st = j & 1;
-        const uint32_t u = static_cast<uint32_t>(j >> 1);
+        const int st = j % 3;
+        const uint32_t u = static_cast<uint32_t>(j / 3);
         mbar_wait(&kv_empty[st], (u & 1u) ^ 1u, 11);
         mbar_expect_tx(&kv_full[st], SM::STAGE_BYTES);
         uint8_t* sk = sKV + st * SM::STAGE_BYTES;
@@ -119,24 +122,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_pv = umma_idesc(2, kQRows, 32) | (1u << 16);   // B (= V tile) is MN-major
       mbar_wait(q_full, 0, 12);
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
-      for (int j = 0; j < nchunks; ++j) {
-        const int st = j & 1;
-        const uint32_t u = static_cast<uint32_t>(j >> 1);
-        mbar_wait(&kv_full[st], u & 1u, 13);
+      // S_i = Q K_i^T into score buffer i & 1.  K dimension = head_dim 32 = four K=8 steps inside one 128-byte
+      // swizzle atom.  Tensor-pipe instructions retire in issue order, so this overwrites P_{i-2} only after
+      // P V_{i-2} (issued earlier) has read it.
+      auto issue_s = [&](int i) {
+        const int st = i % 3;
+        mbar_wait(&kv_full[st], static_cast<uint32_t>(i / 3) & 1u, 13);
         tc_fence_after();
-        const uint32_t sk = smem_u32(sKV + st * SM::STAGE_BYTES);
-        const uint64_t kdesc = umma_desc_sw128(sk);
-        // S = Q K^T : K dimension = head_dim 32 = four K=8 steps inside one 128-byte swizzle atom.
-        // (tensor-pipe instructions retire in issue order, so this overwrites P_{j-1} only after P V_{j-1} read it)
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * SM::STAGE_BYTES));
+        const uint32_t sbuf = tmem_base + static_cast<uint32_t>((i & 1) * NK);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_base, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-        tc_commit(s_full);
+        for (int k = 0; k < 4; ++k) umma_ss<true>(sbuf, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(&s_full[i & 1]);
+      };
+      issue_s(0);
+      for (int j = 0; j < nchunks; ++j) {
+        if (j + 1 < nchunks) issue_s(j + 1);                    // scores of the next chunk while softmax_j runs
         mbar_wait(p_full, static_cast<uint32_t>(j) & 1u, 14);   // softmax wrote P_j (and rescaled O)
         tc_fence_after();
-        const uint64_t vdesc = umma_desc_mn_tf32(sk + SM::KV_BYTES);
+        const int st = j % 3;
+        const uint64_t vdesc = umma_desc_mn_tf32(smem_u32(sKV + st * SM::STAGE_BYTES) + SM::KV_BYTES);
+        const uint32_t pbuf = tmem_base + static_cast<uint32_t>((j & 1) * NK);
 #pragma unroll
-        for (int kk = 0; kk < NK / 8; ++kk)                     // 8 keys per MMA = one 1024-byte row group of V
-          umma_ts_tf32(tmem_base + kOCol, tmem_base + static_cast<uint32_t>(kk * 8), vdesc + 64u * kk, idesc_pv,
+        for (int kk = 0; kk < NK / 8; ++kk)                     // 8 keys per MMA = two 4-row K atoms (1024 B) of V
+          umma_ts_tf32(tmem_base + kOCol, pbuf + static_cast<uint32_t>(kk * 8), vdesc + 64u * kk, idesc_pv,
                        (j | kk) != 0 ? 1u : 0u);
         tc_commit(&kv_empty[st]);
         tc_commit(pv_done);
@@ -146,12 +155,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t trow0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float c = p.scale_log2e;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nchunks; ++j) {
-      mbar_wait(s_full, static_cast<uint32_t>(j) & 1u, 15);
+      mbar_wait(&s_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u, 15);
       tc_fence_after();
+      const uint32_t trow = trow0 + static_cast<uint32_t>((j & 1) * NK);   // this chunk's score buffer
       const int key0 = j * NK;
       const bool full = key0 + NK <= p.Lk;                 // no ragged tail inside this chunk (the common case)
       // ---- pass 1: row maximum of this chunk (four independent chains: a thread owns a whole row, so latency,
@@ -222,16 +232,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       l = l * alpha + sum;
       m = m_new;
-      // ---- rescale the running output when this warp's maxima moved (needs P V_{j-1} to have landed)
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      // ---- P V_{j-1} must have landed before O may be touched; waiting for it on EVERY chunk also keeps this warp
+      //      exactly one phase behind the pv_done barrier (a parity wait two phases late would alias and fall through)
+      if (j > 0) {
         mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u, 16);
         tc_fence_after();
-        uint32_t o[32];
-        tmem_ld_32x32(trow + kOCol, o);
-        tmem_wait_ld();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale the running output when a row maximum moved
+          uint32_t o[32];
+          tmem_ld_32x32(trow0 + kOCol, o);
+          tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32(trow + kOCol, o);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32(trow0 + kOCol, o);
+        }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -242,7 +255,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_wait(pv_done, static_cast<uint32_t>(nchunks - 1) & 1u, 17);
     tc_fence_after();
     uint32_t o[32];
-    tmem_ld_32x32(trow + kOCol, o);
+    tmem_ld_32x32(trow0 + kOCol, o);
     tmem_wait_ld();
     if (p.debug && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row < 2)
       printf("[attn dbg] row %d m %f l %f O[0..3] = %f %f %f %f\n", row, m, l, __uint_as_float(o[0]),
@@ -319,8 +332,8 @@ bool attention_tc_supported(Dtype dt, const AttnDesc& d) {
 }
 
 std::string launch_attention_tc(const AttnDesc& d, cudaStream_t s) {
-  if (d.Lk % 112 == 0) return launch_tc<112>(d, s);
-  return launch_tc<128>(d, s);
+  if (d.Lk % 112 == 0) return launch_tc<112>(d, s);   // 784 = 7 x 112: no ragged chunk at the 224^2 / stride-8 size
+  return launch_tc<64>(d, s);
 }
 
 }  // namespace spe
