@@ -8,9 +8,11 @@
 //   warp 1      owns TMEM, one lane issues   S = Q K^T   (tcgen05.mma kind::tf32, A and B from shared memory)
 //                                  and       O += P V     (A = P read straight from TMEM, B = V tile, MN-major,
 //                                                          which for TF32 means the 32-byte-granule swizzle)
-//   warps 2..5  softmax: thread t owns score row t (tcgen05.ld gives each thread its own row, so the running max and
-//               sum need no cross-thread reduction), writes P back over S in TMEM (tcgen05.st) and rescales the
-//               32-column O accumulator when the running maximum moves (online softmax, fp32 statistics)
+//   warps 2..9  softmax: tcgen05.ld gives thread t of a warp score row t of its TMEM lane quarter; two warps share a
+//               quarter and split the chunk's columns (twice the warps to hide MUFU / TMEM latency), exchanging only
+//               their partial row maxima through shared memory.  P is written back over S in TMEM (tcgen05.st); the
+//               32-column O accumulator (16 columns per warp) is rescaled when the running maximum moves
+//               (online softmax, fp32 statistics)
 // TMEM columns: two score / probability buffers [0, NK) and [NK, 2 NK) (QK^T of chunk j+1 is issued while the softmax
 // of chunk j runs), output accumulator at [2 NK, 2 NK + 32).
 #include "spe_internal.h"
@@ -25,7 +27,7 @@ namespace {
 
 constexpr int kQRows = 128;
 constexpr int kTmemCols = 256;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // TMA warp, MMA warp, 8 softmax warps
 
 struct AttnTcParams {
   float* out;
@@ -41,7 +43,8 @@ template <int NK> struct AttnSmem {
   static constexpr int KV_BYTES = NK * 128;
   static constexpr int STAGE_BYTES = 2 * KV_BYTES;
   static constexpr int STAGES = 3;
-  static constexpr int BYTES = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 16 + 1024;
+  static constexpr int XCHG_BYTES = 2 * 2 * kQRows * 4 + 2 * kQRows * 4;   // partial maxima [2][2][128] + sums [2][128]
+  static constexpr int BYTES = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 16 + XCHG_BYTES + 1024;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -75,6 +78,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t kOCol = 2 * NK;
   static_assert(2 * NK + 32 <= kTmemCols, "two score buffers and the output accumulator must fit the TMEM allocation");
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  float* sm_max = reinterpret_cast<float*>(bars + 18);        // [2 chunk parities][2 halves][128 rows]
+  float* sm_sum = sm_max + 2 * 2 * kQRows;                    // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -89,7 +94,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -153,84 +158,78 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int half = (warp - 2) >> 2;        // which part of the chunk's columns / of O's columns this warp owns
     const int row = q * 32 + lane;
+    // column split of a chunk: NK = 112 -> [0,64) | [64,112) ; NK = 64 -> [0,32) | [32,64)
+    constexpr int C0 = (NK == 112) ? 64 : NK / 2;
+    const int cbeg = half == 0 ? 0 : C0;
+    const int n32 = half == 0 ? C0 / 32 : (NK - C0) / 32;          // full 32-column pieces
+    const bool tail16 = (half == 1) && ((NK - C0) % 32 != 0);      // plus one 16-column piece (NK = 112, upper half)
     const uint32_t trow0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t ocol = 2 * NK + half * 16;                      // this warp's 16 columns of the O accumulator
     const float c = p.scale_log2e;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nchunks; ++j) {
       mbar_wait(&s_full[j & 1], static_cast<uint32_t>(j >> 1) & 1u, 15);
       tc_fence_after();
-      const uint32_t trow = trow0 + static_cast<uint32_t>((j & 1) * NK);   // this chunk's score buffer
-      const int key0 = j * NK;
-      const bool full = key0 + NK <= p.Lk;                 // no ragged tail inside this chunk (the common case)
-      // ---- pass 1: row maximum of this chunk (four independent chains: a thread owns a whole row, so latency,
-      //      not bandwidth, is what this loop fights)
+      const uint32_t trow = trow0 + static_cast<uint32_t>((j & 1) * NK + cbeg);   // this warp's score columns
+      const int key0 = j * NK + cbeg;
+      const bool full = j * NK + NK <= p.Lk;               // no ragged tail inside this chunk (the common case)
+      // ---- pass 1: partial row maximum (four independent chains)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int cc = 0; cc < NK / 32; ++cc) {
+      for (int cc = 0; cc < n32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
         tmem_wait_ld();
-        if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + cc * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
-        }
+        for (int i = 0; i < 32; ++i)
+          if (full || key0 + cc * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
       }
-      if constexpr (NK % 32 != 0) {
+      if (tail16) {
         uint32_t v[16];
-        tmem_ld_32x16(trow + static_cast<uint32_t>((NK / 32) * 32), v);
+        tmem_ld_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (full || key0 + (NK / 32) * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+          if (full || key0 + n32 * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // exchange with the warp that owns the other columns of the same rows
+      float* xm = sm_max + (j & 1) * 2 * kQRows;
+      xm[half * kQRows + row] = mx;
+      named_bar_sync(1 + q, 64);
+      mx = fmaxf(mx, xm[(half ^ 1) * kQRows + row]);
       const float m_new = fmaxf(m, mx);                    // finite: every chunk holds at least one valid key
       const float alpha = ex2((m - m_new) * c);            // 0 on the first chunk (m = -inf)
       const float mc = m_new * c;
       // ---- pass 2: probabilities, written back over the scores as TF32
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int cc = 0; cc < NK / 32; ++cc) {
+      for (int cc = 0; cc < n32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
         tmem_wait_ld();
-        if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float pr = ex2(fmaf(__uint_as_float(v[i]), c, -mc));
-            sum4[i & 3] += pr;
-            v[i] = rna_bits(pr);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float pr = (key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-            sum4[i & 3] += pr;
-            v[i] = rna_bits(pr);
-          }
-        }
-        tmem_st_32x32(trow + static_cast<uint32_t>(cc * 32), v);
-      }
-      if constexpr (NK % 32 != 0) {
-        uint32_t v[16];
-        tmem_ld_32x16(trow + static_cast<uint32_t>((NK / 32) * 32), v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pr = (full || key0 + (NK / 32) * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+        for (int i = 0; i < 32; ++i) {
+          const float pr = (full || key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
           sum4[i & 3] += pr;
           v[i] = rna_bits(pr);
         }
-        tmem_st_32x16(trow + static_cast<uint32_t>((NK / 32) * 32), v);
+        tmem_st_32x32(trow + static_cast<uint32_t>(cc * 32), v);
       }
-      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      l = l * alpha + sum;
+      if (tail16) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pr = (full || key0 + n32 * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          sum4[i & 3] += pr;
+          v[i] = rna_bits(pr);
+        }
+        tmem_st_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
+      }
+      l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));   // partial sum over this warp's columns
       m = m_new;
       // ---- P V_{j-1} must have landed before O may be touched; waiting for it on EVERY chunk also keeps this warp
       //      exactly one phase behind the pv_done barrier (a parity wait two phases late would alias and fall through)
@@ -238,12 +237,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u, 16);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale the running output when a row maximum moved
-          uint32_t o[32];
-          tmem_ld_32x32(trow0 + kOCol, o);
+          uint32_t o[16];
+          tmem_ld_32x16(trow0 + ocol, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(trow0 + kOCol, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x16(trow0 + ocol, o);
         }
       }
       tmem_wait_st();
@@ -251,20 +250,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // ---- epilogue: O / l -> global
+    // ---- epilogue: O / l -> global (each warp its 16 columns; l = sum of the two partial sums)
+    sm_sum[half * kQRows + row] = l;
+    named_bar_sync(1 + q, 64);
+    l += sm_sum[(half ^ 1) * kQRows + row];
     mbar_wait(pv_done, static_cast<uint32_t>(nchunks - 1) & 1u, 17);
     tc_fence_after();
-    uint32_t o[32];
-    tmem_ld_32x32(trow0 + kOCol, o);
+    uint32_t o[16];
+    tmem_ld_32x16(trow0 + ocol, o);
     tmem_wait_ld();
-    if (p.debug && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row < 2)
-      printf("[attn dbg] row %d m %f l %f O[0..3] = %f %f %f %f\n", row, m, l, __uint_as_float(o[0]),
-             __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
     if (q0 + row < p.Lq) {
       const float inv = 1.0f / l;
-      float* op = p.out + (static_cast<long long>(b) * p.Lq + q0 + row) * p.ldo + h * 32;
+      float* op = p.out + (static_cast<long long>(b) * p.Lq + q0 + row) * p.ldo + h * 32 + half * 16;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < 16; i += 4) {
         float4 r4 = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv,
                                 __uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
         if (!p.exact_out)
