@@ -119,6 +119,14 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
                        const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
                        int32_t* boxes_host /*[B,4] or NULL*/, void* stream);
 
+/* Double-buffered form of the same loop: submit enqueues upload + compute + download of one batch on an internal
+ * stream of `slot` (0 or 1) and returns at once; collect waits for that slot and hands out the poses.  Submitting
+ * batch i+1 before collecting batch i overlaps its upload with batch i's kernels.  frames_host must be pinned and stay
+ * valid until the slot is collected. */
+int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, int H, int W,
+                          const double* det_boxes_host, int B, const spe_pnp_params* params);
+int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tvec_host, int32_t* status_host,
+                           int32_t* boxes_host /*[B,4] or NULL*/);
 /* bytes spe_run_batch_host uploaded on its last call (only the crop-box/frame intersections travel) */
 long long spe_last_h2d_bytes(spe_ctx* ctx);
 

@@ -45,6 +45,8 @@ SYMBOLS = {
     "spe_debug_attention": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "spe_debug_enable_taps": (_i, [_vp, _i]),
     "spe_debug_read_tap": (_ll, [_vp, C.c_char_p, _vp, _ll]),
+    "spe_submit_batch_host": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, C.POINTER(SpePnpParams)]),
+    "spe_collect_batch_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "spe_last_h2d_bytes": (_ll, [_vp]),
     "spe_profile_enable": (_i, [_i]),
     "spe_profile_collect": (_i, [_vp, _vp]),

@@ -4,6 +4,9 @@
 #include "profile.h"
 #include "../../include/spe.h"
 
+#include <string.h>
+
+#include <map>
 #include <string>
 #include <vector>
 
@@ -21,6 +24,57 @@ int set_error(spe_ctx* ctx, int code, const std::string& msg);
 }  // namespace spe
 
 using namespace spe;
+
+namespace {
+constexpr int kPipeSlots = 2;
+struct PipeSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t compute_done = nullptr;
+  uint8_t* frames_dev = nullptr;
+  long long frames_cap = 0;
+  int32_t *boxes_dev = nullptr, *status_dev = nullptr, *assign_dev = nullptr;
+  double *quat_dev = nullptr, *tvec_dev = nullptr;
+  int32_t *boxes_h = nullptr, *status_h = nullptr;   // pinned
+  double *quat_h = nullptr, *tvec_h = nullptr;       // pinned
+  bool busy = false;
+  int B = 0;
+};
+struct Pipe {
+  PipeSlot slot[kPipeSlots];
+  cudaEvent_t prev_compute_done = nullptr;
+  bool have_prev = false;
+};
+std::map<spe_ctx*, Pipe*> g_pipes;
+Pipe& pipe_of(spe_ctx* ctx) {
+  auto it = g_pipes.find(ctx);
+  if (it == g_pipes.end()) it = g_pipes.emplace(ctx, new Pipe()).first;
+  return *it->second;
+}
+}  // namespace
+
+namespace spe {
+void pipeline_release(spe_ctx* ctx) {   // called by spe_destroy
+  auto it = g_pipes.find(ctx);
+  if (it == g_pipes.end()) return;
+  for (PipeSlot& S : it->second->slot) {
+    if (S.stream) cudaStreamSynchronize(S.stream);
+    if (S.frames_dev) cudaFree(S.frames_dev);
+    if (S.boxes_dev) cudaFree(S.boxes_dev);
+    if (S.status_dev) cudaFree(S.status_dev);
+    if (S.assign_dev) cudaFree(S.assign_dev);
+    if (S.quat_dev) cudaFree(S.quat_dev);
+    if (S.tvec_dev) cudaFree(S.tvec_dev);
+    if (S.boxes_h) cudaFreeHost(S.boxes_h);
+    if (S.status_h) cudaFreeHost(S.status_h);
+    if (S.quat_h) cudaFreeHost(S.quat_h);
+    if (S.tvec_h) cudaFreeHost(S.tvec_h);
+    if (S.compute_done) cudaEventDestroy(S.compute_done);
+    if (S.stream) cudaStreamDestroy(S.stream);
+  }
+  delete it->second;
+  g_pipes.erase(it);
+}
+}  // namespace spe
 
 extern "C" {
 
@@ -141,6 +195,104 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
 }
 
 long long spe_last_h2d_bytes(spe_ctx* ctx) { return ctx ? last_h2d_bytes(ctx) : -1; }
+
+// ---- double-buffered host pipeline: the upload of batch i+1 overlaps the compute of batch i -----------------------
+int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, int H, int W,
+                          const double* det_boxes_host, int B, const spe_pnp_params* params) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_submit_batch_host: null ctx");
+  if (slot < 0 || slot >= kPipeSlots) return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_host: slot must be 0 or 1");
+  if (!frames_host || !det_boxes_host || !params) return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_host: null buffer");
+  PipelineBuffers pb = pipeline_buffers(ctx);
+  if (B <= 0 || B > pb.max_batch) return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_host: batch outside [1, max_batch]");
+  cudaSetDevice(pb.device);
+  Pipe& P = pipe_of(ctx);
+  PipeSlot& S = P.slot[slot];
+  if (S.busy) return set_error(ctx, SPE_ERR_STATE, "spe_submit_batch_host: slot still in flight (collect it first)");
+  cudaError_t e = cudaSuccess;
+  if (!S.stream) {
+    e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.compute_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&S.boxes_dev, sizeof(int32_t) * 4 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&S.quat_dev, sizeof(double) * 4 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&S.tvec_dev, sizeof(double) * 3 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&S.status_dev, sizeof(int32_t) * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&S.assign_dev, sizeof(int32_t) * 11 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMallocHost(&S.boxes_h, sizeof(int32_t) * 4 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMallocHost(&S.quat_h, sizeof(double) * 4 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMallocHost(&S.tvec_h, sizeof(double) * 3 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMallocHost(&S.status_h, sizeof(int32_t) * pb.max_batch);
+    if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline slot: ") + cudaGetErrorString(e));
+  }
+  const long long need = static_cast<long long>(B) * H * W;
+  if (S.frames_cap < need) {
+    if (S.frames_dev) cudaFree(S.frames_dev);
+    S.frames_dev = nullptr;
+    S.frames_cap = 0;
+    const long long cap = static_cast<long long>(pb.max_batch) * H * W;
+    e = cudaMalloc(reinterpret_cast<void**>(&S.frames_dev), static_cast<size_t>(cap));
+    if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("frame buffer: ") + cudaGetErrorString(e));
+    S.frames_cap = cap;
+  }
+  spe_clip_boxes(det_boxes_host, B, S.boxes_h);
+  long long h2d = 0;
+  for (int i = 0; i < B && e == cudaSuccess; ++i) {
+    const int32_t* bx = S.boxes_h + 4 * i;
+    const int x0 = bx[0] < 0 ? 0 : bx[0], y0 = bx[1] < 0 ? 0 : bx[1];
+    const int x1 = bx[2] > W ? W : bx[2], y1 = bx[3] > H ? H : bx[3];
+    if (x1 <= x0 || y1 <= y0) continue;
+    const long long off = static_cast<long long>(i) * H * W + static_cast<long long>(y0) * W + x0;
+    e = cudaMemcpy2DAsync(S.frames_dev + off, W, frames_host + off, W, static_cast<size_t>(x1 - x0),
+                          static_cast<size_t>(y1 - y0), cudaMemcpyHostToDevice, S.stream);
+    h2d += static_cast<long long>(x1 - x0) * (y1 - y0);
+  }
+  *pb.last_h2d_bytes = h2d + static_cast<long long>(sizeof(int32_t)) * 4 * B;
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(S.boxes_dev, S.boxes_h, sizeof(int32_t) * 4 * B, cudaMemcpyHostToDevice, S.stream);
+  // the activations workspace is shared: this batch's kernels queue behind the previous batch's kernels, while
+  // its upload (above) already overlaps them
+  if (e == cudaSuccess && P.have_prev) e = cudaStreamWaitEvent(S.stream, P.prev_compute_done, 0);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_submit_batch_host: ") + cudaGetErrorString(e));
+  int rc = spe_crop_resize_norm(ctx, S.frames_dev, H, W, W, static_cast<long long>(H) * W, S.boxes_dev, B, pb.R,
+                                pb.images_dev, S.stream);
+  if (rc != SPE_OK) return rc;
+  const bool sig = pb.has_sigma != 0;
+  rc = spe_forward(ctx, pb.images_dev, B, pb.logits, pb.points, sig ? pb.logsig : nullptr, nullptr, nullptr, S.stream);
+  if (rc != SPE_OK) return rc;
+  spe_pnp_params pp = *params;
+  if (!sig) pp.weighted = 0;
+  const float* pl = pb.ov_logits ? pb.ov_logits : pb.logits;
+  const float* pp_pts = pb.ov_points ? pb.ov_points : pb.points;
+  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? pb.logsig : nullptr, S.boxes_dev, B, pb.Q, &pp, S.quat_dev, S.tvec_dev,
+                      S.assign_dev, S.status_dev, nullptr, nullptr, nullptr, nullptr, S.stream);
+  if (rc != SPE_OK) return rc;
+  e = cudaEventRecord(S.compute_done, S.stream);
+  P.prev_compute_done = S.compute_done;
+  P.have_prev = true;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.quat_h, S.quat_dev, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, S.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.tvec_h, S.tvec_dev, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, S.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.status_h, S.status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, S.stream);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_submit_batch_host: ") + cudaGetErrorString(e));
+  S.busy = true;
+  S.B = B;
+  return SPE_OK;
+}
+
+int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tvec_host, int32_t* status_host,
+                           int32_t* boxes_host) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_collect_batch_host: null ctx");
+  if (slot < 0 || slot >= kPipeSlots) return set_error(ctx, SPE_ERR_INVALID, "spe_collect_batch_host: slot must be 0 or 1");
+  if (!quat_host || !tvec_host || !status_host) return set_error(ctx, SPE_ERR_INVALID, "spe_collect_batch_host: null buffer");
+  PipeSlot& S = pipe_of(ctx).slot[slot];
+  if (!S.busy) return set_error(ctx, SPE_ERR_STATE, "spe_collect_batch_host: nothing submitted on this slot");
+  cudaError_t e = cudaStreamSynchronize(S.stream);
+  S.busy = false;
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_collect_batch_host: ") + cudaGetErrorString(e));
+  memcpy(quat_host, S.quat_h, sizeof(double) * 4 * S.B);
+  memcpy(tvec_host, S.tvec_h, sizeof(double) * 3 * S.B);
+  memcpy(status_host, S.status_h, sizeof(int32_t) * S.B);
+  if (boxes_host) memcpy(boxes_host, S.boxes_h, sizeof(int32_t) * 4 * S.B);
+  return SPE_OK;
+}
 
 int spe_profile_enable(int on) {
   profile_enable(on != 0);

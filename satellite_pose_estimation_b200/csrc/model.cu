@@ -204,6 +204,8 @@ struct spe_ctx {
 
 namespace spe {
 
+void pipeline_release(spe_ctx* ctx);   // api.cu
+
 static std::string g_last_error;
 
 static int fail(spe_ctx* ctx, int code, const std::string& msg) {
@@ -1002,6 +1004,7 @@ int spe_create(const spe_config* cfg, int device, spe_ctx** out) {
 void spe_destroy(spe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  pipeline_release(ctx);
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   for (void* p : ctx->allocs) cudaFree(p);

@@ -44,6 +44,7 @@ class Engine:
             check(self.lib.spe_create(C.byref(self.cfg), self.device.index, C.byref(self._ctx)))
         self.weights_loaded = False
         self._fwd_bufs = {}
+        self._inflight = {}
         self._stable_inputs = set()
 
     def close(self):
@@ -199,6 +200,27 @@ class Engine:
                                           _stream(self.device)), self._ctx)
         return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes,
                 "h2d_bytes": int(self.lib.spe_last_h2d_bytes(self._ctx))}
+
+    def submit_batch_host(self, slot, frames_host, det_boxes, reproj=20.0, weighted=False, reject=False):
+        """Asynchronous half of ``run_batch_host`` (slot 0 or 1): returns as soon as the work is enqueued.
+        ``frames_host`` must be a pinned uint8 torch tensor [B,H,W] that stays alive until ``collect_batch_host``."""
+        assert isinstance(frames_host, torch.Tensor) and frames_host.is_pinned() and frames_host.dtype == torch.uint8
+        B, H, W = frames_host.shape
+        det = np.ascontiguousarray(np.asarray(det_boxes, dtype=np.float64).reshape(-1, 4))
+        p = SpePnpParams(reproj_thresh=float(reproj), weighted=int(weighted), reject=int(reject),
+                         reject_rms_px=5.0, reject_sigma_px=12.0)
+        check(self.lib.spe_submit_batch_host(self._ctx, slot, C.c_void_p(frames_host.data_ptr()), H, W,
+                                             det.ctypes.data_as(C.c_void_p), B, C.byref(p)), self._ctx)
+        self._inflight[slot] = (frames_host, B, int(self.lib.spe_last_h2d_bytes(self._ctx)))
+
+    def collect_batch_host(self, slot):
+        frames_host, B, h2d = self._inflight.pop(slot)
+        quat = np.empty((B, 4), dtype=np.float64); tvec = np.empty((B, 3), dtype=np.float64)
+        status = np.empty((B,), dtype=np.int32); boxes = np.empty((B, 4), dtype=np.int32)
+        check(self.lib.spe_collect_batch_host(self._ctx, slot, quat.ctypes.data_as(C.c_void_p),
+                                              tvec.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
+                                              boxes.ctypes.data_as(C.c_void_p)), self._ctx)
+        return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes, "h2d_bytes": h2d}
 
     # ---- measurement hooks (bench.py) ------------------------------------------------------------------------------
     FAMILIES = ("gemm", "attention", "elementwise", "heads", "crop", "pnp")

@@ -152,6 +152,17 @@ def test_host_pipeline_matches_stagewise(lib, cuda_dev):
     p = eng.assign_pnp(out["pred_logits"], out["pred_points"], torch.from_numpy(clip).cuda())
     assert np.array_equal(r["status"], p["status"].cpu().numpy())
     assert np.allclose(r["quat"], p["quat"].cpu().numpy()) and np.allclose(r["tvec"], p["tvec"].cpu().numpy())
+    # double-buffered form: two batches in flight give the same answers as the synchronous call
+    fh = [torch.from_numpy(frames).pin_memory(), torch.from_numpy(frames[::-1].copy()).pin_memory()]
+    dets = [det, det[::-1].copy()]
+    eng.submit_batch_host(0, fh[0], dets[0])
+    eng.submit_batch_host(1, fh[1], dets[1])
+    a, b = eng.collect_batch_host(0), eng.collect_batch_host(1)
+    assert np.array_equal(a["status"], r["status"]) and np.allclose(a["quat"], r["quat"])
+    assert np.array_equal(b["boxes"], clip[::-1]) and np.array_equal(b["status"], r["status"][::-1])
+    assert 0 < a["h2d_bytes"] < frames.size          # only the crop-box / frame intersections are uploaded
+    with pytest.raises(Exception):
+        eng.collect_batch_host(0)                    # nothing in flight any more
     eng.close()
 
 
