@@ -176,33 +176,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t trow = trow0 + static_cast<uint32_t>((j & 1) * NK + cbeg);   // this warp's score columns
       const int key0 = j * NK + cbeg;
       const bool full = j * NK + NK <= p.Lk;               // no ragged tail inside this chunk (the common case)
-      // ---- scores of this warp's columns are read from TMEM ONCE and kept in registers (TMEM reads run at only
-      //      ~64 B/clk/SM, a second pass over S was the kernel's bottleneck); max with four independent chains
-      constexpr int MAXC = (NK == 112) ? 64 : NK / 2;     // columns held per thread
-      uint32_t v[MAXC];
+      // ---- pass 1: partial row maximum (four independent chains)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int cc = 0; cc < MAXC / 32; ++cc) {
-        if (cc < n32) {
-          uint32_t t32[32];
-          tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), t32);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[cc * 32 + i] = t32[i];
-            if (full || key0 + cc * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(t32[i]));
-          }
-        }
-      }
-      if (tail16) {   // NK = 112, upper half: columns [32, 48) of this warp's slice
-        uint32_t t16[16];
-        tmem_ld_32x16(trow + 32u, t16);
+      for (int cc = 0; cc < n32; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v[32 + i] = t16[i];
-          if (full || key0 + 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(t16[i]));
-        }
+        for (int i = 0; i < 32; ++i)
+          if (full || key0 + cc * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+      }
+      if (tail16) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (full || key0 + n32 * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
       }
       float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // exchange with the warp that owns the other columns of the same rows
@@ -213,30 +203,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_new = fmaxf(m, mx);                    // finite: every chunk holds at least one valid key
       const float alpha = ex2((m - m_new) * c);            // 0 on the first chunk (m = -inf)
       const float mc = m_new * c;
-      // ---- probabilities from the registers, written back over the scores as TF32
+      // ---- pass 2: probabilities, written back over the scores as TF32
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int cc = 0; cc < n32; ++cc) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
+        tmem_wait_ld();
 #pragma unroll
-      for (int cc = 0; cc < MAXC / 32; ++cc) {
-        if (cc < n32) {
-          uint32_t t32[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float pr = (full || key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[cc * 32 + i]), c, -mc)) : 0.f;
-            sum4[i & 3] += pr;
-            t32[i] = rna_bits(pr);
-          }
-          tmem_st_32x32(trow + static_cast<uint32_t>(cc * 32), t32);
+        for (int i = 0; i < 32; ++i) {
+          const float pr = (full || key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          sum4[i & 3] += pr;
+          v[i] = rna_bits(pr);
         }
+        tmem_st_32x32(trow + static_cast<uint32_t>(cc * 32), v);
       }
       if (tail16) {
-        uint32_t t16[16];
+        uint32_t v[16];
+        tmem_ld_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
+        tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float pr = (full || key0 + 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[32 + i]), c, -mc)) : 0.f;
+          const float pr = (full || key0 + n32 * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
           sum4[i & 3] += pr;
-          t16[i] = rna_bits(pr);
+          v[i] = rna_bits(pr);
         }
-        tmem_st_32x16(trow + 32u, t16);
+        tmem_st_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
       }
       l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));   // partial sum over this warp's columns
       m = m_new;
