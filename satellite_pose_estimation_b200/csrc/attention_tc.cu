@@ -176,23 +176,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t trow = trow0 + static_cast<uint32_t>((j & 1) * NK + cbeg);   // this warp's score columns
       const int key0 = j * NK + cbeg;
       const bool full = j * NK + NK <= p.Lk;               // no ragged tail inside this chunk (the common case)
-      // ---- pass 1: partial row maximum (four independent chains)
+      // ---- pass 1: partial row maximum (four independent chains; the ragged-tail predicate is hoisted out of the
+      //      per-element loops -- ncu showed 11 issued instructions per score element with it inside)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       for (int cc = 0; cc < n32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
         tmem_wait_ld();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (full || key0 + cc * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + cc * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        }
       }
       if (tail16) {
         uint32_t v[16];
         tmem_ld_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
         tmem_wait_ld();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (full || key0 + n32 * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+          for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (key0 + n32 * 32 + i < p.Lk) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        }
       }
       float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // exchange with the warp that owns the other columns of the same rows
@@ -203,17 +214,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_new = fmaxf(m, mx);                    // finite: every chunk holds at least one valid key
       const float alpha = ex2((m - m_new) * c);            // 0 on the first chunk (m = -inf)
       const float mc = m_new * c;
-      // ---- pass 2: probabilities, written back over the scores as TF32
+      // ---- pass 2: probabilities, written back over the scores.  P is cut to TF32 with one LOP3 (the conversion
+      //      instruction shares the MUFU pipe with ex2) and the row sum is taken over the SAME cut values the tensor
+      //      core will multiply, so the normalisation stays consistent (no truncation bias in O / l).
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int cc = 0; cc < n32; ++cc) {
         uint32_t v[32];
         tmem_ld_32x32(trow + static_cast<uint32_t>(cc * 32), v);
         tmem_wait_ld();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pr = (full || key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-          sum4[i & 3] += pr;
-          v[i] = rna_bits(pr);
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __float_as_uint(ex2(fmaf(__uint_as_float(v[i]), c, -mc))) & 0xffffe000u;
+            sum4[i & 3] += __uint_as_float(v[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float pr = (key0 + cc * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+            v[i] = __float_as_uint(pr) & 0xffffe000u;
+            sum4[i & 3] += __uint_as_float(v[i]);
+          }
         }
         tmem_st_32x32(trow + static_cast<uint32_t>(cc * 32), v);
       }
@@ -224,8 +245,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float pr = (full || key0 + n32 * 32 + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
-          sum4[i & 3] += pr;
-          v[i] = rna_bits(pr);
+          v[i] = __float_as_uint(pr) & 0xffffe000u;
+          sum4[i & 3] += __uint_as_float(v[i]);
         }
         tmem_st_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
       }
