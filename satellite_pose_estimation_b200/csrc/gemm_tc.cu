@@ -88,6 +88,149 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// One 128 x BN accumulator tile of one epilogue warp: rows [q*32, q*32+32) of the tile (its TMEM lane quarter), column
+// chunks half, half + CSTEP, ...  `taddr` = TMEM address of the warp's lane quarter in the accumulator buffer.
+template <typename T, int BN, int CSTEP>
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, const int lane, const int q,
+                                              const int half, const uint32_t taddr, const int valid_rows,
+                                              const long long m_base, const int n0, const float* s_scale,
+                                              const float* s_bias) {
+  // tcgen05.ld hands thread t accumulator row t, but a warp-wide access "32 rows x 16 bytes" touches 32 different
+  // 128-byte lines.  So each 32x32 fp32 accumulator chunk is transposed ONCE through a per-warp XOR-swizzled
+  // 32 x 128-byte staging tile (raw accumulators in, conflict-free both ways), and everything else -- BN
+  // scale/bias, residual add, ReLU, rounding, store -- happens in the coalesced domain where a warp instruction
+  // covers RPI whole rows x 16 bytes per lane: global memory only sees full contiguous row segments, the
+  // residual needs no staging at all, and each thread keeps one fixed group of G columns (one scale/bias fetch).
+  constexpr int G = 16 / static_cast<int>(sizeof(T));        // columns per lane: 4 (fp32) / 8 (bf16)
+  constexpr int CPR = 32 / G;                                // lanes per row: 8 / 4
+  constexpr int RPI = 32 / CPR;                              // rows per warp instruction: 4 / 8
+  constexpr int NIT = 32 / RPI;                              // instructions per chunk: 8 / 4
+  const int crow = lane / CPR, cseg = lane % CPR;
+  const int rows_here = valid_rows - q * 32;                 // valid rows in this warp's 32-row slab (may be <= 0)
+  const long long slab0 = m_base + q * 32;                   // first global row of the slab
+  const bool resid = p.residual != nullptr && rows_here > 0;
+  const int res_es = (sizeof(T) == 4 || p.res_f32) ? 4 : 2;  // residual element size (fp32 addends in bf16 mode)
+  // per-thread row pointers advance by a constant stride; the batch-broadcast addend wraps with one compare
+  const long long out_step = static_cast<long long>(RPI) * p.out_ld * static_cast<long long>(sizeof(T));
+  uint8_t* out0 = reinterpret_cast<uint8_t*>(p.out) +
+                  ((slab0 + crow) * p.out_ld) * static_cast<long long>(sizeof(T)) + cseg * 16;
+  int rr0 = 0;
+  if (resid) rr0 = p.res_mod > 0 ? static_cast<int>(static_cast<unsigned>(slab0 + crow) % static_cast<unsigned>(p.res_mod))
+                                 : 0;
+  const uint8_t* res_base = reinterpret_cast<const uint8_t*>(p.residual);
+
+  // residual values of this lane for one chunk: NIT rows x G columns (prefetched one chunk ahead)
+  uint4 rx[NIT][2];
+  auto fetch_residual = [&](int ncol_) {
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      rx[i][0] = make_uint4(0u, 0u, 0u, 0u);
+      rx[i][1] = make_uint4(0u, 0u, 0u, 0u);
+      const int r = i * RPI + crow;
+      if (r < rows_here && ncol_ < p.N) {
+        long long rr;
+        if (p.res_mod > 0) {
+          int w = rr0 + i * RPI;
+          if (w >= p.res_mod) w -= p.res_mod;
+          rr = w;
+        } else {
+          rr = slab0 + r;
+        }
+        const uint8_t* gp = res_base + (rr * p.res_ld + ncol_ + cseg * G) * static_cast<long long>(res_es);
+        rx[i][0] = *reinterpret_cast<const uint4*>(gp);
+        if (res_es * G > 16) rx[i][1] = *reinterpret_cast<const uint4*>(gp + 16);   // 8 fp32 addends (bf16 mode)
+      }
+    }
+  };
+  if (resid) fetch_residual(n0 + half * 32);
+#pragma unroll 1
+  for (int c = half; c < BN / 32; c += CSTEP) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+    const int ncol = n0 + c * 32;
+    const bool col_ok = ncol < p.N;
+    tmem_wait_ld();
+    // own row -> staging (raw fp32 accumulators)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      *reinterpret_cast<uint4*>(stg + lane * 128 + ((k ^ (lane & 7)) * 16)) =
+          make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    __syncwarp();
+    // this lane's fixed column group: scale / bias
+    float sc[G], bi[G];
+#pragma unroll
+    for (int u = 0; u < G; u += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(s_scale + c * 32 + cseg * G + u);
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cseg * G + u);
+      sc[u] = s4.x; sc[u + 1] = s4.y; sc[u + 2] = s4.z; sc[u + 3] = s4.w;
+      bi[u] = b4.x; bi[u + 1] = b4.y; bi[u + 2] = b4.z; bi[u + 3] = b4.w;
+    }
+    float f[NIT][G];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int r = i * RPI + crow;
+#pragma unroll
+      for (int u = 0; u < G; u += 4) {
+        const int k = cseg * (G / 4) + u / 4;                  // 16-byte chunk of the staging row
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((k ^ (r & 7)) * 16));
+        f[i][u] = fmaf(a4.x, sc[u], bi[u]);
+        f[i][u + 1] = fmaf(a4.y, sc[u + 1], bi[u + 1]);
+        f[i][u + 2] = fmaf(a4.z, sc[u + 2], bi[u + 2]);
+        f[i][u + 3] = fmaf(a4.w, sc[u + 3], bi[u + 3]);
+      }
+    }
+    __syncwarp();   // staging free for the next chunk
+    if (resid && col_ok) {
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        if (res_es == 4) {
+          f[i][0] += __uint_as_float(rx[i][0].x); f[i][1] += __uint_as_float(rx[i][0].y);
+          f[i][2] += __uint_as_float(rx[i][0].z); f[i][3] += __uint_as_float(rx[i][0].w);
+          if (G == 8) {
+            f[i][G - 4] += __uint_as_float(rx[i][1].x); f[i][G - 3] += __uint_as_float(rx[i][1].y);
+            f[i][G - 2] += __uint_as_float(rx[i][1].z); f[i][G - 1] += __uint_as_float(rx[i][1].w);
+          }
+        } else {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rx[i][0]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 ff = __bfloat1622float2(h[u]);
+            f[i][(2 * u) % G] += ff.x;
+            f[i][(2 * u + 1) % G] += ff.y;
+          }
+        }
+      }
+    }
+    if (resid && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next chunk, in flight during the stores
+    if (col_ok) {
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int r = i * RPI + crow;
+        if (p.relu) {
+#pragma unroll
+          for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
+        }
+        if (r < rows_here) {
+          uint8_t* gp = out0 + i * out_step + static_cast<long long>(ncol) * static_cast<long long>(sizeof(T));
+          if (sizeof(T) == 4) {
+            // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here
+            // so the next layer's products are exact and the error stays unbiased
+            float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
+            if (p.round_out) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
+            *reinterpret_cast<float4*>(gp) = o4;
+          } else {
+            uint4 o8;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[i][(2 * u) % G], f[i][(2 * u + 1) % G]);
+            *reinterpret_cast<uint4*>(gp) = o8;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <typename T, int BN, bool X3, bool EPI8>
 __global__ void __launch_bounds__((StageCfg<BN, X3, EPI8>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -289,142 +432,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[buf], use_par, 4);
       tc_fence_after();
 
-      // tcgen05.ld hands thread t accumulator row t, but a warp-wide access "32 rows x 16 bytes" touches 32 different
-      // 128-byte lines.  So each 32x32 fp32 accumulator chunk is transposed ONCE through a per-warp XOR-swizzled
-      // 32 x 128-byte staging tile (raw accumulators in, conflict-free both ways), and everything else -- BN
-      // scale/bias, residual add, ReLU, rounding, store -- happens in the coalesced domain where a warp instruction
-      // covers RPI whole rows x 16 bytes per lane: global memory only sees full contiguous row segments, the
-      // residual needs no staging at all, and each thread keeps one fixed group of G columns (one scale/bias fetch).
-      constexpr int G = 16 / static_cast<int>(sizeof(T));        // columns per lane: 4 (fp32) / 8 (bf16)
-      constexpr int CPR = 32 / G;                                // lanes per row: 8 / 4
-      constexpr int RPI = 32 / CPR;                              // rows per warp instruction: 4 / 8
-      constexpr int NIT = 32 / RPI;                              // instructions per chunk: 8 / 4
-      uint8_t* stg = sm_staging + (warp - 2) * 4096;
-      const int crow = lane / CPR, cseg = lane % CPR;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-      const int rows_here = valid_rows - q * 32;                 // valid rows in this warp's 32-row slab (may be <= 0)
-      const long long slab0 = m_base + q * 32;                   // first global row of the slab
-      const bool resid = p.residual != nullptr && rows_here > 0;
-      const int res_es = (sizeof(T) == 4 || p.res_f32) ? 4 : 2;  // residual element size (fp32 addends in bf16 mode)
-      // per-thread row pointers advance by a constant stride; the batch-broadcast addend wraps with one compare
-      const long long out_step = static_cast<long long>(RPI) * p.out_ld * static_cast<long long>(sizeof(T));
-      uint8_t* out0 = reinterpret_cast<uint8_t*>(p.out) +
-                      ((slab0 + crow) * p.out_ld) * static_cast<long long>(sizeof(T)) + cseg * 16;
-      int rr0 = 0;
-      if (resid) rr0 = p.res_mod > 0 ? static_cast<int>(static_cast<unsigned>(slab0 + crow) % static_cast<unsigned>(p.res_mod))
-                                     : 0;
-      const uint8_t* res_base = reinterpret_cast<const uint8_t*>(p.residual);
-
-      // residual values of this lane for one chunk: NIT rows x G columns (prefetched one chunk ahead)
-      uint4 rx[NIT][2];
-      auto fetch_residual = [&](int ncol_) {
-#pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-          rx[i][0] = make_uint4(0u, 0u, 0u, 0u);
-          rx[i][1] = make_uint4(0u, 0u, 0u, 0u);
-          const int r = i * RPI + crow;
-          if (r < rows_here && ncol_ < p.N) {
-            long long rr;
-            if (p.res_mod > 0) {
-              int w = rr0 + i * RPI;
-              if (w >= p.res_mod) w -= p.res_mod;
-              rr = w;
-            } else {
-              rr = slab0 + r;
-            }
-            const uint8_t* gp = res_base + (rr * p.res_ld + ncol_ + cseg * G) * static_cast<long long>(res_es);
-            rx[i][0] = *reinterpret_cast<const uint4*>(gp);
-            if (res_es * G > 16) rx[i][1] = *reinterpret_cast<const uint4*>(gp + 16);   // 8 fp32 addends (bf16 mode)
-          }
-        }
-      };
-      if (resid) fetch_residual(n0 + half * 32);
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += CSTEP) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
-        const int ncol = n0 + c * 32;
-        const bool col_ok = ncol < p.N;
-        tmem_wait_ld();
-        // own row -> staging (raw fp32 accumulators)
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((k ^ (lane & 7)) * 16)) =
-              make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        __syncwarp();
-        // this lane's fixed column group: scale / bias
-        float sc[G], bi[G];
-#pragma unroll
-        for (int u = 0; u < G; u += 4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(s_scale + c * 32 + cseg * G + u);
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + cseg * G + u);
-          sc[u] = s4.x; sc[u + 1] = s4.y; sc[u + 2] = s4.z; sc[u + 3] = s4.w;
-          bi[u] = b4.x; bi[u + 1] = b4.y; bi[u + 2] = b4.z; bi[u + 3] = b4.w;
-        }
-        float f[NIT][G];
-#pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-          const int r = i * RPI + crow;
-#pragma unroll
-          for (int u = 0; u < G; u += 4) {
-            const int k = cseg * (G / 4) + u / 4;                  // 16-byte chunk of the staging row
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((k ^ (r & 7)) * 16));
-            f[i][u] = fmaf(a4.x, sc[u], bi[u]);
-            f[i][u + 1] = fmaf(a4.y, sc[u + 1], bi[u + 1]);
-            f[i][u + 2] = fmaf(a4.z, sc[u + 2], bi[u + 2]);
-            f[i][u + 3] = fmaf(a4.w, sc[u + 3], bi[u + 3]);
-          }
-        }
-        __syncwarp();   // staging free for the next chunk
-        if (resid && col_ok) {
-#pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            if (res_es == 4) {
-              f[i][0] += __uint_as_float(rx[i][0].x); f[i][1] += __uint_as_float(rx[i][0].y);
-              f[i][2] += __uint_as_float(rx[i][0].z); f[i][3] += __uint_as_float(rx[i][0].w);
-              if (G == 8) {
-                f[i][G - 4] += __uint_as_float(rx[i][1].x); f[i][G - 3] += __uint_as_float(rx[i][1].y);
-                f[i][G - 2] += __uint_as_float(rx[i][1].z); f[i][G - 1] += __uint_as_float(rx[i][1].w);
-              }
-            } else {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rx[i][0]);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float2 ff = __bfloat1622float2(h[u]);
-                f[i][(2 * u) % G] += ff.x;
-                f[i][(2 * u + 1) % G] += ff.y;
-              }
-            }
-          }
-        }
-        if (resid && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next chunk, in flight during the stores
-        if (col_ok) {
-#pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            const int r = i * RPI + crow;
-            if (p.relu) {
-#pragma unroll
-              for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
-            }
-            if (r < rows_here) {
-              uint8_t* gp = out0 + i * out_step + static_cast<long long>(ncol) * static_cast<long long>(sizeof(T));
-              if (sizeof(T) == 4) {
-                // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here
-                // so the next layer's products are exact and the error stays unbiased
-                float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
-                if (p.round_out) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
-                *reinterpret_cast<float4*>(gp) = o4;
-              } else {
-                uint4 o8;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[i][(2 * u) % G], f[i][(2 * u + 1) % G]);
-                *reinterpret_cast<uint4*>(gp) = o8;
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<T, BN, CSTEP>(p, sm_staging + (warp - 2) * 4096, lane, q, half,
+                                  tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN),
+                                  valid_rows, m_base, n0, s_scale, s_bias);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
@@ -437,6 +447,213 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x 256 tile per cluster of two CTAs.  Each CTA loads its own 128 rows of A
+// and HALF of the 256-row weight tile; a single tcgen05.mma.cta_group::2 (M = 256, issued by the leader CTA) reads
+// both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Per 128x256x32 MACs a CTA now
+// pulls 32 KB through L2 instead of 48 KB -- fp32 operands make L2->SM bandwidth (~13 TB/s measured) the ceiling of
+// the big-K layers, not the tensor pipe.
+// ------------------------------------------------------------------------------------------------------------------
+struct Cg2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = (BN / 2) * 128;       // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int EPI_WARPS = 4;
+  static constexpr int THREADS = 192;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 2 * 2 * BN * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cg2Cfg::THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmKParams p) {
+  using Tr = GemmTraits<T>;
+  using Cfg = Cg2Cfg;
+  constexpr int BK = Tr::BK;
+  constexpr int BN = Cfg::BN;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // same offset in both CTAs of the pair
+  uint8_t* sm_staging = smem + STAGES * Cfg::STAGE_BYTES;
+  float* sm_scale = reinterpret_cast<float*>(sm_staging + Cfg::STAGING_BYTES);
+  float* sm_bias = sm_scale + 2 * BN;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_bias + 2 * BN);   // used in the leader CTA only
+  uint64_t* empty_bar = full_bar + STAGES;                              // per CTA (multicast commit)
+  uint64_t* tfull_bar = empty_bar + STAGES;                             // per CTA (multicast commit)
+  uint64_t* tempty_bar = tfull_bar + 2;                                 // leader CTA only: both epilogues arrive
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int num_tiles = ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles;     // 256-row pair tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits and the TMEM allocation are visible in both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs) {
+        const int pm = tile / p.num_n_tiles;
+        const int n0 = (tile - pm * p.num_n_tiles) * BN;
+        const int m_tile = 2 * pm + static_cast<int>(rank);    // may be one past the end: TMA zero-fills, nothing stored
+        int img = 0, h0 = 0;
+        if (p.mode == 1) {
+          img = m_tile / p.tiles_per_img;
+          h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 21);
+          // both CTAs' bytes are accounted on the leader's barrier
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (p.a_bytes + Cfg::B_BYTES));
+          const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (p.mode == 0) {
+            tma_load_2d_cg2(sa, &tmA, lead_bar, kb * BK, m_tile * BM);
+          } else {
+            const int tap = kb / p.kb_per_tap;
+            const int c0 = (kb - tap * p.kb_per_tap) * BK;
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            tma_load_4d_cg2(sa, &tmA, lead_bar, c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
+          }
+          tma_load_2d_cg2(sb, &tmB, lead_bar, kb * BK, n0 + static_cast<int>(rank) * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: one lane of the leader CTA
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(Tr::kFmt, 2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[buf], use_par ^ 1u, 22);   // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 23);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss_cg2<Tr::kTf32>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_cg2(&empty_bar[stage], 3);                        // frees the slot in both CTAs
+          if (kb == p.num_kb - 1) tc_commit_cg2(&tfull_bar[buf], 3);  // accumulator complete in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (each CTA its own 128 rows)
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
+      const int buf = it & 1;
+      const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
+      const int pm = tile / p.num_n_tiles;
+      const int n0 = (tile - pm * p.num_n_tiles) * BN;
+      const int m_tile = 2 * pm + static_cast<int>(rank);
+      long long m_base = 0;
+      int valid_rows = 0;
+      if (m_tile < p.num_m_tiles) {
+        if (p.mode == 0) {
+          m_base = static_cast<long long>(m_tile) * BM;
+          const long long rem = static_cast<long long>(p.M) - m_base;
+          valid_rows = rem < BM ? static_cast<int>(rem) : BM;
+        } else {
+          const int img = m_tile / p.tiles_per_img;
+          const int h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
+          m_base = static_cast<long long>(img) * p.HW + static_cast<long long>(h0) * p.W;
+          const int hr = (p.H - h0) < p.hrows ? (p.H - h0) : p.hrows;
+          valid_rows = hr * p.W;
+        }
+      }
+      float* s_scale = sm_scale + buf * BN;
+      float* s_bias = sm_bias + buf * BN;
+      for (int j = et; j < BN; j += 32 * Cfg::EPI_WARPS) {
+        const bool ok = (n0 + j) < p.N;
+        s_scale[j] = (p.scale != nullptr && ok) ? p.scale[n0 + j] : 1.0f;
+        s_bias[j] = (p.bias != nullptr && ok) ? p.bias[n0 + j] : 0.0f;
+      }
+      named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+      mbar_wait(&tfull_bar[buf], use_par, 24);
+      tc_fence_after();
+      epilogue_tile<T, BN, 1>(p, sm_staging + (warp - 2) * 4096, lane, q, 0,
+                              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN),
+                              valid_rows, m_base, n0, s_scale, s_bias);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // leader's barrier
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // no CTA of the pair may exit (or free TMEM) while its partner still uses it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <typename T>
+std::string launch_cg2(const GemmKParams& kp, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+                       cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kfn = gemm_tc2_kernel<T>;
+  if (!attr_set) {
+    SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cg2Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int pair_tiles = ((kp.num_m_tiles + 1) / 2) * kp.num_n_tiles;
+  int pairs = num_sms / 2;
+  if (pairs > pair_tiles) pairs = pair_tiles;
+  {
+    ProfScope ps(kFamGemm, stream);
+    kfn<<<2 * pairs, Cg2Cfg::THREADS, Cg2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+  }
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -538,6 +755,12 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   // wide tiles halve the A re-reads (L2 -> SM bandwidth is what bounds fp32-operand GEMMs) when there are still
   // enough tiles to fill the machine
   if (!d.x3 && d.N % 256 == 0 && m_tiles_est * (d.N / 256) >= num_sms) BN = 256;
+  // CTA pairs (256 x 256 tiles) for the deep-K layers, where operand traffic through L2 is the limiter
+  static const int cg2_force = getenv("SPE_GEMM_CG2") ? atoi(getenv("SPE_GEMM_CG2")) : -1;
+  const int k_est = d.mode == 0 ? d.K : d.R * d.S * d.C;
+  bool cg2 = !d.x3 && d.mode != 2 && d.N % 256 == 0 && k_est / BK >= 16 && ((m_tiles_est + 1) / 2) * (d.N / 256) >= 48;
+  if (cg2_force >= 0) cg2 = cg2 && cg2_force != 0;
+  if (cg2) BN = 256;
 
   GemmKParams kp{};
   kp.round_out = d.round_out;
@@ -628,11 +851,13 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     const int kw = d.x3 ? 2 * K : K;   // X3 weights: [N, 2K] = [W_hi | W_lo]
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(kw), static_cast<cuuint64_t>(d.N)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(kw) * es};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(BN)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(cg2 ? BN / 2 : BN)};
     err = encode_map(&tmB, dt, 2, d.Wt, dims, str, box);
     if (!err.empty()) return err;
   }
 
+  if (cg2) return dt == kTF32 ? launch_cg2<float>(kp, tmA, tmB, num_sms, stream)
+                              : launch_cg2<__nv_bfloat16>(kp, tmA, tmB, num_sms, stream);
   // short K loops cannot hide a 4-warp epilogue: give those GEMMs the 8-warp epilogue (and fewer smem stages)
   static const int epi_force = getenv("SPE_GEMM_EPI8") ? atoi(getenv("SPE_GEMM_EPI8")) : -1;
   const bool epi8 = !d.x3 && (epi_force >= 0 ? epi_force != 0 : kp.num_kb <= 16);

@@ -28,7 +28,9 @@ def _rel(got, ref):
 @pytest.mark.parametrize("M,N,K,relu,res,res_mod", [
     (128, 64, 64, 0, 0, 0), (1, 64, 64, 0, 0, 0), (300, 256, 512, 1, 1, 0), (6272, 64, 256, 1, 0, 0),
     (2352, 768, 256, 0, 1, 784), (40, 256, 2048, 0, 1, 0), (12544, 64, 192, 1, 0, 0), (1000, 2048, 256, 1, 0, 0),
-    (784 * 16, 128, 1152, 1, 0, 0)])
+    (784 * 16, 128, 1152, 1, 0, 0),
+    # CTA-pair (cta_group::2) path: N % 256 == 0, deep K; odd number of 128-row tiles, ragged tail, wrapped residual
+    (12837, 512, 1024, 1, 1, 0), (12288, 256, 2048, 0, 1, 784), (784 * 9, 256, 512, 1, 0, 0)])
 def test_gemm(lib, cuda_dev, dt, M, N, K, relu, res, res_mod):
     torch.manual_seed(M + N + K)
     tdt = DT[dt]
@@ -53,7 +55,7 @@ def test_gemm(lib, cuda_dev, dt, M, N, K, relu, res, res_mod):
 
 @pytest.mark.parametrize("dt", [0, 1])
 @pytest.mark.parametrize("NB,H,Cin,Cout", [(2, 28, 64, 64), (3, 56, 64, 64), (2, 14, 256, 256), (1, 28, 1024, 256),
-                                            (1, 7, 64, 128), (5, 32, 128, 128)])
+                                            (1, 7, 64, 128), (5, 32, 128, 128), (16, 28, 256, 256), (15, 25, 512, 256)])
 def test_implicit_conv3x3(lib, cuda_dev, dt, NB, H, Cin, Cout):
     """TMA out-of-bounds zero fill == the convolution's zero padding; ragged last row-tile (H % hrows != 0)."""
     torch.manual_seed(H * Cin)
@@ -73,7 +75,8 @@ def test_implicit_conv3x3(lib, cuda_dev, dt, NB, H, Cin, Cout):
 
 @pytest.mark.parametrize("dt", [0, 1])
 @pytest.mark.parametrize("NB,H,Cin,Cout,R", [(2, 56, 128, 128, 3), (3, 28, 256, 256, 3), (2, 56, 256, 512, 1),
-                                              (2, 28, 512, 1024, 1), (1, 64, 128, 128, 3)])
+                                              (2, 28, 512, 1024, 1), (1, 64, 128, 128, 3), (16, 56, 256, 256, 3),
+                                              (13, 50, 512, 1024, 1)])
 def test_implicit_conv_stride2(lib, cuda_dev, dt, NB, H, Cin, Cout, R):
     """Stride-2 convolutions (layerN.0.conv2, downsample) through the TMA traversal stride: no im2col buffer."""
     torch.manual_seed(H * Cin + R)
