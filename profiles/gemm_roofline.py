@@ -63,7 +63,7 @@ def main(path):
     ends = [i for i, s in enumerate(seq) if "assign_pnp" in s[1] or "PnpDesc" in s[1]]
     a = starts[-1] if ends and ends[-1] > starts[-1] else starts[-2]
     b = min(e for e in ends if e > a)
-    gem = [s for s in seq[a:b + 1] if short(s[1]) == "gemm_tc_kernel"]
+    gem = [s for s in seq[a:b + 1] if short(s[1]) in ("gemm_tc_kernel", "gemm_tc2_kernel")]
     sch = schedule()
     assert len(gem) == len(sch), (len(gem), len(sch))
     print("| GEMM | M | N | K | us | ideal us | TFLOP/s | x ideal |\n|---|---:|---:|---:|---:|---:|---:|---:|")
@@ -73,7 +73,7 @@ def main(path):
         by = (M * K + M * N + res) * ES if "3x3" not in name else (M * K // 9 + M * N) * ES
         ideal = max(fl * (3 if x3 else 1) / TF32, by / HBM) * 1e6
         tot += s[2]; tot_ideal += ideal
-        print(f"| {name} | {M} | {N} | {K} | {s[2]:.1f} | {ideal:.1f} | {fl / s[2] / 1e6:.0f} | {s[2] / ideal:.1f} |")
+        print(f"| {name}{" (pair)" if "tc2" in s[1] else ""} | {M} | {N} | {K} | {s[2]:.1f} | {ideal:.1f} | {fl / s[2] / 1e6:.0f} | {s[2] / ideal:.1f} |")
     print(f"\nGEMM total {tot:.0f} us, sum of per-GEMM ideals {tot_ideal:.0f} us")
 
 

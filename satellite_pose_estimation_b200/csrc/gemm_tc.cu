@@ -79,6 +79,7 @@ struct GemmKParams {
   int out_ld;
   int round_out;       // fp32 storage: round results to TF32 (consumer is a kind::tf32 MMA)
   int K;               // X3: column offset of W_lo inside the [N, 2K] weight matrix
+  int dbg;             // SPE_GEMM_DBG bit 0: skip the output stores (profiling experiments only)
 };
 
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -86,6 +87,37 @@ __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// Last step of one 32-column chunk in the coalesced domain: ReLU, rounding, 16-byte stores.  RELU / ROUND / FULL are
+// compile-time so the per-row loop carries no uniform branches or predicate reloads (they were a third of the
+// epilogue's issue slots, and the epilogue's issue rate is what bounds the short-K GEMMs).
+template <typename T, bool RELU, bool ROUND, bool FULL, int NIT, int G>
+__device__ __forceinline__ void store_chunk(float (&f)[NIT][G], uint8_t* gp, const long long out_step, const int crow,
+                                            const int rows_here, const int rpi) {
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    if (RELU) {
+#pragma unroll
+      for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
+    }
+    if (FULL || i * rpi + crow < rows_here) {
+      if (sizeof(T) == 4) {
+        // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here
+        // so the next layer's products are exact and the error stays unbiased
+        float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
+        if (ROUND) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
+        *reinterpret_cast<float4*>(gp) = o4;
+      } else {
+        uint4 o8;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[i][(2 * u) % G], f[i][(2 * u + 1) % G]);
+        *reinterpret_cast<uint4*>(gp) = o8;
+      }
+    }
+    gp += out_step;
+  }
 }
 
 // One 128 x BN accumulator tile of one epilogue warp: rows [q*32, q*32+32) of the tile (its TMEM lane quarter), column
@@ -118,6 +150,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   if (resid) rr0 = p.res_mod > 0 ? static_cast<int>(static_cast<unsigned>(slab0 + crow) % static_cast<unsigned>(p.res_mod))
                                  : 0;
   const uint8_t* res_base = reinterpret_cast<const uint8_t*>(p.residual);
+  // which store_chunk instance this tile uses (uniform over the warp)
+  const int variant = (p.relu ? 1 : 0) | ((sizeof(T) == 4 && p.round_out) ? 2 : 0) | (rows_here >= 32 ? 4 : 0);
+  // this lane's staging addresses (byte offsets): its own row for the transposing write, its column group for reads
+  const uint32_t stg_w = smem_u32(stg) + lane * 128;
+  const int wsw = lane & 7;
 
   // residual values of this lane for one chunk: NIT rows x G columns (prefetched one chunk ahead)
   uint4 rx[NIT][2];
@@ -143,18 +180,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     }
   };
   if (resid) fetch_residual(n0 + half * 32);
+  uint32_t v[32];
+  if (!(p.dbg & 4)) tmem_ld_32x32(taddr + static_cast<uint32_t>(half * 32), v);
+  else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = lane + k;
+  }
 #pragma unroll 1
   for (int c = half; c < BN / 32; c += CSTEP) {
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
     const int ncol = n0 + c * 32;
     const bool col_ok = ncol < p.N;
     tmem_wait_ld();
     // own row -> staging (raw fp32 accumulators)
+    if (!(p.dbg & 2))
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      *reinterpret_cast<uint4*>(stg + lane * 128 + ((k ^ (lane & 7)) * 16)) =
-          make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + ((k ^ wsw) * 16)), "r"(v[4 * k]),
+                   "r"(v[4 * k + 1]), "r"(v[4 * k + 2]), "r"(v[4 * k + 3])
+                   : "memory");
+    // the next chunk's accumulators travel TMEM -> registers while this one is finished below
+    if (c + CSTEP < BN / 32 && !(p.dbg & 4)) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + CSTEP) * 32), v);
     __syncwarp();
     // this lane's fixed column group: scale / bias
     float sc[G], bi[G];
@@ -172,7 +217,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 #pragma unroll
       for (int u = 0; u < G; u += 4) {
         const int k = cseg * (G / 4) + u / 4;                  // 16-byte chunk of the staging row
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((k ^ (r & 7)) * 16));
+        float4 a4;
+        if (!(p.dbg & 2)) a4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((k ^ (r & 7)) * 16));
+        else a4 = make_float4(__uint_as_float(v[i * 4]), __uint_as_float(v[i * 4 + 1]), __uint_as_float(v[i * 4 + 2]), __uint_as_float(v[i * 4 + 3]));
         f[i][u] = fmaf(a4.x, sc[u], bi[u]);
         f[i][u + 1] = fmaf(a4.y, sc[u + 1], bi[u + 1]);
         f[i][u + 2] = fmaf(a4.z, sc[u + 2], bi[u + 2]);
@@ -202,30 +249,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       }
     }
     if (resid && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next chunk, in flight during the stores
-    if (col_ok) {
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int r = i * RPI + crow;
-        if (p.relu) {
-#pragma unroll
-          for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
-        }
-        if (r < rows_here) {
-          uint8_t* gp = out0 + i * out_step + static_cast<long long>(ncol) * static_cast<long long>(sizeof(T));
-          if (sizeof(T) == 4) {
-            // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here
-            // so the next layer's products are exact and the error stays unbiased
-            float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
-            if (p.round_out) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
-            *reinterpret_cast<float4*>(gp) = o4;
-          } else {
-            uint4 o8;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[i][(2 * u) % G], f[i][(2 * u + 1) % G]);
-            *reinterpret_cast<uint4*>(gp) = o8;
-          }
-        }
+    if (col_ok && rows_here > 0 && !(p.dbg & 1)) {
+      uint8_t* gp = out0 + static_cast<long long>(ncol) * static_cast<long long>(sizeof(T));
+      switch (variant) {
+        case 0: store_chunk<T, false, false, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        case 1: store_chunk<T, true, false, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        case 2: store_chunk<T, false, true, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        case 3: store_chunk<T, true, true, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        case 4: store_chunk<T, false, false, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        case 5: store_chunk<T, true, false, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        case 6: store_chunk<T, false, true, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        default: store_chunk<T, true, true, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
       }
     }
   }
@@ -456,25 +490,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // pulls 32 KB through L2 instead of 48 KB -- fp32 operands make L2->SM bandwidth (~13 TB/s measured) the ceiling of
 // the big-K layers, not the tensor pipe.
 // ------------------------------------------------------------------------------------------------------------------
+template <bool EPI8>
 struct Cg2Cfg {
   static constexpr int BN = 256;
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = (BN / 2) * 128;       // this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
-  static constexpr int EPI_WARPS = 4;
-  static constexpr int THREADS = 192;
+  static constexpr int EPI_WARPS = EPI8 ? 8 : 4;
+  static constexpr int STAGES = EPI8 ? 5 : 6;   // the 8-warp epilogue needs 32 KB of staging
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS = 512;
   static constexpr int STAGING_BYTES = EPI_WARPS * 4096;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 2 * 2 * BN * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-template <typename T>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cg2Cfg::THREADS, 1)
+template <typename T, bool EPI8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cg2Cfg<EPI8>::THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmKParams p) {
   using Tr = GemmTraits<T>;
-  using Cfg = Cg2Cfg;
+  using Cfg = Cg2Cfg<EPI8>;
+  constexpr int CSTEP = EPI8 ? 2 : 1;
   constexpr int BK = Tr::BK;
   constexpr int BN = Cfg::BN;
   constexpr int STAGES = Cfg::STAGES;
@@ -586,6 +622,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ epilogue warps (each CTA its own 128 rows)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;   // with 8 warps the two halves take alternate column chunks
     const int et = threadIdx.x - 64;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
@@ -619,7 +656,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       named_bar_sync(1, 32 * Cfg::EPI_WARPS);
       mbar_wait(&tfull_bar[buf], use_par, 24);
       tc_fence_after();
-      epilogue_tile<T, BN, 1>(p, sm_staging + (warp - 2) * 4096, lane, q, 0,
+      epilogue_tile<T, BN, CSTEP>(p, sm_staging + (warp - 2) * 4096, lane, q, half,
                               tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN),
                               valid_rows, m_base, n0, s_scale, s_bias);
       tc_fence_before();
@@ -636,13 +673,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <typename T>
+template <typename T, bool EPI8>
 std::string launch_cg2(const GemmKParams& kp, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                        cudaStream_t stream) {
   static bool attr_set = false;
-  auto kfn = gemm_tc2_kernel<T>;
+  using Cfg = Cg2Cfg<EPI8>;
+  auto kfn = gemm_tc2_kernel<T, EPI8>;
   if (!attr_set) {
-    SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cg2Cfg::SMEM_BYTES));
+    SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int pair_tiles = ((kp.num_m_tiles + 1) / 2) * kp.num_n_tiles;
@@ -650,7 +688,7 @@ std::string launch_cg2(const GemmKParams& kp, const CUtensorMap& tmA, const CUte
   if (pairs > pair_tiles) pairs = pair_tiles;
   {
     ProfScope ps(kFamGemm, stream);
-    kfn<<<2 * pairs, Cg2Cfg::THREADS, Cg2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+    kfn<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
   }
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
@@ -757,13 +795,18 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (!d.x3 && d.N % 256 == 0 && m_tiles_est * (d.N / 256) >= num_sms) BN = 256;
   // CTA pairs (256 x 256 tiles) for the deep-K layers, where operand traffic through L2 is the limiter
   static const int cg2_force = getenv("SPE_GEMM_CG2") ? atoi(getenv("SPE_GEMM_CG2")) : -1;
+  static const int cg2_min_kb = getenv("SPE_GEMM_CG2_MINKB") ? atoi(getenv("SPE_GEMM_CG2_MINKB")) : 16;
   const int k_est = d.mode == 0 ? d.K : d.R * d.S * d.C;
-  bool cg2 = !d.x3 && d.mode != 2 && d.N % 256 == 0 && k_est / BK >= 16 && ((m_tiles_est + 1) / 2) * (d.N / 256) >= 48;
+  bool cg2 = !d.x3 && d.mode != 2 && d.N % 256 == 0 && k_est / BK >= cg2_min_kb && ((m_tiles_est + 1) / 2) * (d.N / 256) >= 48;
   if (cg2_force >= 0) cg2 = cg2 && cg2_force != 0;
   if (cg2) BN = 256;
+  static const int bn_force = getenv("SPE_GEMM_BN") ? atoi(getenv("SPE_GEMM_BN")) : 0;   // experiments only
+  if (!cg2 && (bn_force == 64 || bn_force == 128) && bn_force <= d.N) BN = bn_force;
 
   GemmKParams kp{};
   kp.round_out = d.round_out;
+  static const int dbg_flags = getenv("SPE_GEMM_DBG") ? atoi(getenv("SPE_GEMM_DBG")) : 0;
+  kp.dbg = dbg_flags;
   kp.mode = d.mode;
   kp.N = d.N;
   kp.scale = d.scale;
@@ -856,8 +899,13 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     if (!err.empty()) return err;
   }
 
-  if (cg2) return dt == kTF32 ? launch_cg2<float>(kp, tmA, tmB, num_sms, stream)
-                              : launch_cg2<__nv_bfloat16>(kp, tmA, tmB, num_sms, stream);
+  if (cg2) {
+    const bool e8 = kp.num_kb <= 16;   // short K: the epilogue is the long pole, give it 8 warps
+    if (dt == kTF32) return e8 ? launch_cg2<float, true>(kp, tmA, tmB, num_sms, stream)
+                               : launch_cg2<float, false>(kp, tmA, tmB, num_sms, stream);
+    return e8 ? launch_cg2<__nv_bfloat16, true>(kp, tmA, tmB, num_sms, stream)
+              : launch_cg2<__nv_bfloat16, false>(kp, tmA, tmB, num_sms, stream);
+  }
   // short K loops cannot hide a 4-warp epilogue: give those GEMMs the 8-warp epilogue (and fewer smem stages)
   static const int epi_force = getenv("SPE_GEMM_EPI8") ? atoi(getenv("SPE_GEMM_EPI8")) : -1;
   const bool epi8 = !d.x3 && (epi_force >= 0 ? epi_force != 0 : kp.num_kb <= 16);

@@ -18,6 +18,10 @@ cases = [  # name, M, N, K, relu, residual rows (0 = none, -1 = full), res_mod
     ("l1.conv3+res", 200704, 256, 64, 1, -1, 0),
     ("enc.ff1", 50176, 2048, 256, 1, 0, 0),
     ("enc.qkv+addend", 50176, 768, 256, 0, 784, 784),
+    ("ff1 K=32", 50176, 2048, 32, 1, 0, 0),
+    ("qkv K=32", 50176, 768, 32, 0, 0, 0),
+    ("N256 K=32", 401408, 256, 32, 1, 0, 0),
+    ("N64 K=32", 1605632, 64, 32, 1, 0, 0),
 ]
 bufs = []
 for name, M, N, K, relu, rrows, rmod in cases:
