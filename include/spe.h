@@ -119,14 +119,24 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
                        const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
                        int32_t* boxes_host /*[B,4] or NULL*/, void* stream);
 
-/* Double-buffered form of the same loop: submit enqueues upload + compute + download of one batch on an internal
- * stream of `slot` (0 or 1) and returns at once; collect waits for that slot and hands out the poses.  Submitting
- * batch i+1 before collecting batch i overlaps its upload with batch i's kernels.  frames_host must be pinned and stay
- * valid until the slot is collected. */
+/* Double-buffered form of the same loop: submit enqueues upload + compute + download of one batch on internal
+ * streams and returns at once; collect waits for that slot (0 or 1) and hands out the poses.  Submitting batch i+1
+ * before collecting batch i overlaps three things: the upload of i+1, the trunk of i+1 (crop, backbone, neck, encoder,
+ * decoder K/V -- fills the machine) and the tail of i (decoder, heads, assignment + PnP, download -- ~100 small
+ * latency-bound launches that run in the gaps of the trunk; each slot owns its K/V set).  frames_host must be pinned
+ * and stay valid until the slot is collected. */
 int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, int H, int W,
                           const double* det_boxes_host, int B, const spe_pnp_params* params);
 int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tvec_host, int32_t* status_host,
                            int32_t* boxes_host /*[B,4] or NULL*/);
+
+/* Same pipeline for frames that are already resident in device memory (a decoder / camera stack that delivers into
+ * HBM): frames_dev uint8 [B] frames of H x W with row pitch `pitch` and frame stride `frame_stride` bytes, boxes_dev
+ * int32 [B,4] clip boxes (spe_clip_boxes), both complete on `stream` at the time of the call and untouched until
+ * the slot is collected.  Collect with spe_collect_batch_host (boxes_host is not filled). */
+int spe_submit_batch_dev(spe_ctx* ctx, int slot, const uint8_t* frames_dev, int H, int W, long long pitch,
+                         long long frame_stride, const int32_t* boxes_dev, int B, const spe_pnp_params* params,
+                         void* stream);
 /* bytes spe_run_batch_host uploaded on its last call (only the crop-box/frame intersections travel) */
 long long spe_last_h2d_bytes(spe_ctx* ctx);
 
@@ -152,9 +162,13 @@ const char* spe_global_last_error(void);
  * launches since the last collect and, while enabled, their CUDA-event-timed device milliseconds */
 int spe_profile_enable(int on);
 int spe_profile_collect(double* ms_by_family /*[6]*/, long long* launches_by_family /*[6]*/);
-/* bench hook: spe_run_batch_host feeds these resident [B,Q,12] / [B,Q,2] tensors to the pose stage instead of the
- * network outputs (random-init weights collapse to one label, which would make the solve exit early); NULL resets */
-int spe_debug_set_pnp_override(spe_ctx* ctx, const float* logits_dev, const float* points_dev);
+/* bench hook: the batch pipelines (run / submit) feed these resident [B,Q,12] / [B,Q,2] tensors -- and, if given, the
+ * int32 [B,4] crop boxes they were generated for -- to the pose stage instead of the network outputs (random-init
+ * weights collapse to one label, which would make the solve exit early); NULL resets */
+int spe_debug_set_pnp_override(spe_ctx* ctx, const float* logits_dev, const float* points_dev,
+                               const int32_t* boxes_dev);
+/* test hook: network outputs (logits [B,Q,12], points [B,Q,2]) of the batch last collected from pipeline `slot` */
+int spe_debug_read_slot_outputs(spe_ctx* ctx, int slot, float* logits_host, float* points_host);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -47,10 +47,12 @@ SYMBOLS = {
     "spe_debug_read_tap": (_ll, [_vp, C.c_char_p, _vp, _ll]),
     "spe_submit_batch_host": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, C.POINTER(SpePnpParams)]),
     "spe_collect_batch_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "spe_submit_batch_dev": (_i, [_vp, _i, _vp, _i, _i, _ll, _ll, _vp, _i, C.POINTER(SpePnpParams), _vp]),
     "spe_last_h2d_bytes": (_ll, [_vp]),
     "spe_profile_enable": (_i, [_i]),
     "spe_profile_collect": (_i, [_vp, _vp]),
-    "spe_debug_set_pnp_override": (_i, [_vp, _vp, _vp]),
+    "spe_debug_set_pnp_override": (_i, [_vp, _vp, _vp, _vp]),
+    "spe_debug_read_slot_outputs": (_i, [_vp, _i, _vp, _vp]),
 }
 
 _lib = None

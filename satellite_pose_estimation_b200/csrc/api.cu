@@ -16,11 +16,14 @@ struct PipelineBuffers {
   uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
   float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
   int has_sigma; const float* ov_logits; const float* ov_points; long long* last_h2d_bytes;
+  const int32_t* ov_boxes;
 };
 PipelineBuffers pipeline_buffers(spe_ctx* ctx);
 long long last_h2d_bytes(spe_ctx* ctx);
-void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points);
+void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points, const int32_t* boxes);
 int set_error(spe_ctx* ctx, int code, const std::string& msg);
+int forward_half(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits, float* points,
+                 float* logsig, cudaStream_t st);
 }  // namespace spe
 
 using namespace spe;
@@ -28,21 +31,25 @@ using namespace spe;
 namespace {
 constexpr int kPipeSlots = 2;
 struct PipeSlot {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t compute_done = nullptr;
+  cudaStream_t stream = nullptr;          // upload stream of this slot
+  cudaEvent_t upload_done = nullptr, trunk_done = nullptr, done = nullptr;
   uint8_t* frames_dev = nullptr;
   long long frames_cap = 0;
   int32_t *boxes_dev = nullptr, *status_dev = nullptr, *assign_dev = nullptr;
   double *quat_dev = nullptr, *tvec_dev = nullptr;
+  float *logits_dev = nullptr, *points_dev = nullptr, *logsig_dev = nullptr;   // network outputs of this slot's batch
   int32_t *boxes_h = nullptr, *status_h = nullptr;   // pinned
   double *quat_h = nullptr, *tvec_h = nullptr;       // pinned
   bool busy = false;
   int B = 0;
 };
+// Two compute lanes shared by both slots: the trunk (crop, backbone, neck, encoder, decoder K/V -- throughput-bound,
+// fills the machine) and the tail (decoder, heads, assignment + PnP, result download -- ~100 small latency-bound
+// launches).  They only share the slot's K/V set, so the tail of batch i runs in the gaps of the trunk of batch i+1.
 struct Pipe {
   PipeSlot slot[kPipeSlots];
-  cudaEvent_t prev_compute_done = nullptr;
-  bool have_prev = false;
+  cudaStream_t trunk = nullptr, tail = nullptr;
+  cudaEvent_t caller_ready = nullptr;
 };
 std::map<spe_ctx*, Pipe*> g_pipes;
 Pipe& pipe_of(spe_ctx* ctx) {
@@ -58,19 +65,29 @@ void pipeline_release(spe_ctx* ctx) {   // called by spe_destroy
   if (it == g_pipes.end()) return;
   for (PipeSlot& S : it->second->slot) {
     if (S.stream) cudaStreamSynchronize(S.stream);
+    if (S.done && S.busy) cudaEventSynchronize(S.done);
     if (S.frames_dev) cudaFree(S.frames_dev);
     if (S.boxes_dev) cudaFree(S.boxes_dev);
     if (S.status_dev) cudaFree(S.status_dev);
     if (S.assign_dev) cudaFree(S.assign_dev);
     if (S.quat_dev) cudaFree(S.quat_dev);
     if (S.tvec_dev) cudaFree(S.tvec_dev);
+    if (S.logits_dev) cudaFree(S.logits_dev);
+    if (S.points_dev) cudaFree(S.points_dev);
+    if (S.logsig_dev) cudaFree(S.logsig_dev);
     if (S.boxes_h) cudaFreeHost(S.boxes_h);
     if (S.status_h) cudaFreeHost(S.status_h);
     if (S.quat_h) cudaFreeHost(S.quat_h);
     if (S.tvec_h) cudaFreeHost(S.tvec_h);
-    if (S.compute_done) cudaEventDestroy(S.compute_done);
+    if (S.upload_done) cudaEventDestroy(S.upload_done);
+    if (S.trunk_done) cudaEventDestroy(S.trunk_done);
+    if (S.done) cudaEventDestroy(S.done);
     if (S.stream) cudaStreamDestroy(S.stream);
   }
+  Pipe* P = it->second;
+  if (P->trunk) { cudaStreamSynchronize(P->trunk); cudaStreamDestroy(P->trunk); }
+  if (P->tail) { cudaStreamSynchronize(P->tail); cudaStreamDestroy(P->tail); }
+  if (P->caller_ready) cudaEventDestroy(P->caller_ready);
   delete it->second;
   g_pipes.erase(it);
 }
@@ -183,7 +200,7 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
   // benchmark may substitute resident synthetic keypoint sets for the pose stage (spe_debug_set_pnp_override)
   const float* pl = pb.ov_logits ? pb.ov_logits : pb.logits;
   const float* pp_pts = pb.ov_points ? pb.ov_points : pb.points;
-  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? pb.logsig : nullptr, pb.boxes_dev, B, pb.Q, &pp, pb.quat,
+  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? pb.logsig : nullptr, pb.ov_boxes ? pb.ov_boxes : pb.boxes_dev, B, pb.Q, &pp, pb.quat,
                       pb.tvec, pb.assign, pb.status, nullptr, nullptr, nullptr, nullptr, stream);
   if (rc != SPE_OK) return rc;
   e = cudaMemcpyAsync(quat_host, pb.quat, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st);
@@ -196,33 +213,93 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
 
 long long spe_last_h2d_bytes(spe_ctx* ctx) { return ctx ? last_h2d_bytes(ctx) : -1; }
 
-// ---- double-buffered host pipeline: the upload of batch i+1 overlaps the compute of batch i -----------------------
-int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, int H, int W,
-                          const double* det_boxes_host, int B, const spe_pnp_params* params) {
-  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_submit_batch_host: null ctx");
-  if (slot < 0 || slot >= kPipeSlots) return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_host: slot must be 0 or 1");
-  if (!frames_host || !det_boxes_host || !params) return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_host: null buffer");
-  PipelineBuffers pb = pipeline_buffers(ctx);
-  if (B <= 0 || B > pb.max_batch) return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_host: batch outside [1, max_batch]");
+// ---- double-buffered pipeline: upload of batch i+1 || trunk of batch i+1 || decoder + pose + download of batch i ----
+static int pipe_prepare(spe_ctx* ctx, const char* who, int slot, int B, PipelineBuffers& pb, Pipe** Pp, PipeSlot** Sp) {
+  if (slot < 0 || slot >= kPipeSlots) return set_error(ctx, SPE_ERR_INVALID, std::string(who) + ": slot must be 0 or 1");
+  pb = pipeline_buffers(ctx);
+  if (B <= 0 || B > pb.max_batch) return set_error(ctx, SPE_ERR_INVALID, std::string(who) + ": batch outside [1, max_batch]");
   cudaSetDevice(pb.device);
   Pipe& P = pipe_of(ctx);
   PipeSlot& S = P.slot[slot];
-  if (S.busy) return set_error(ctx, SPE_ERR_STATE, "spe_submit_batch_host: slot still in flight (collect it first)");
+  if (S.busy) return set_error(ctx, SPE_ERR_STATE, std::string(who) + ": slot still in flight (collect it first)");
   cudaError_t e = cudaSuccess;
+  if (!P.trunk) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
+    e = cudaStreamCreateWithPriority(&P.trunk, cudaStreamNonBlocking, lo);
+    // the small tail kernels take the SMs a finishing trunk kernel frees before the next trunk kernel does
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&P.tail, cudaStreamNonBlocking, hi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.caller_ready, cudaEventDisableTiming);
+    if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline streams: ") + cudaGetErrorString(e));
+  }
   if (!S.stream) {
     e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.compute_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.upload_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.trunk_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&S.boxes_dev, sizeof(int32_t) * 4 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMalloc(&S.quat_dev, sizeof(double) * 4 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMalloc(&S.tvec_dev, sizeof(double) * 3 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMalloc(&S.status_dev, sizeof(int32_t) * pb.max_batch);
     if (e == cudaSuccess) e = cudaMalloc(&S.assign_dev, sizeof(int32_t) * 11 * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&S.logits_dev, sizeof(float) * 12 * pb.Q * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&S.points_dev, sizeof(float) * 2 * pb.Q * pb.max_batch);
+    if (e == cudaSuccess) e = cudaMalloc(&S.logsig_dev, sizeof(float) * 2 * pb.Q * pb.max_batch);
     if (e == cudaSuccess) e = cudaMallocHost(&S.boxes_h, sizeof(int32_t) * 4 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMallocHost(&S.quat_h, sizeof(double) * 4 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMallocHost(&S.tvec_h, sizeof(double) * 3 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMallocHost(&S.status_h, sizeof(int32_t) * pb.max_batch);
     if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline slot: ") + cudaGetErrorString(e));
   }
+  *Pp = &P;
+  *Sp = &S;
+  return SPE_OK;
+}
+
+// crop + trunk on the trunk lane (after `ready`), decoder + pose + download on the tail lane
+static int pipe_enqueue(spe_ctx* ctx, const char* who, int slot, const PipelineBuffers& pb, Pipe& P, PipeSlot& S,
+                        cudaEvent_t ready, const uint8_t* frames_dev, int H, int W, long long pitch,
+                        long long frame_stride, const int32_t* boxes_dev, int B, const spe_pnp_params* params) {
+  cudaError_t e = cudaStreamWaitEvent(P.trunk, ready, 0);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  int rc = spe_crop_resize_norm(ctx, frames_dev, H, W, pitch, frame_stride, boxes_dev, B, pb.R, pb.images_dev, P.trunk);
+  if (rc != SPE_OK) return rc;
+  const bool sig = pb.has_sigma != 0;
+  rc = forward_half(ctx, 1, slot, pb.images_dev, B, nullptr, nullptr, nullptr, P.trunk);
+  if (rc != SPE_OK) return rc;
+  e = cudaEventRecord(S.trunk_done, P.trunk);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(P.tail, S.trunk_done, 0);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  rc = forward_half(ctx, 2, slot, nullptr, B, S.logits_dev, S.points_dev, sig ? S.logsig_dev : nullptr, P.tail);
+  if (rc != SPE_OK) return rc;
+  spe_pnp_params pp = *params;
+  if (!sig) pp.weighted = 0;
+  const float* pl = pb.ov_logits ? pb.ov_logits : S.logits_dev;
+  const float* pp_pts = pb.ov_points ? pb.ov_points : S.points_dev;
+  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? S.logsig_dev : nullptr, pb.ov_boxes ? pb.ov_boxes : boxes_dev, B, pb.Q, &pp, S.quat_dev, S.tvec_dev,
+                      S.assign_dev, S.status_dev, nullptr, nullptr, nullptr, nullptr, P.tail);
+  if (rc != SPE_OK) return rc;
+  e = cudaMemcpyAsync(S.quat_h, S.quat_dev, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, P.tail);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.tvec_h, S.tvec_dev, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, P.tail);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.status_h, S.status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, P.tail);
+  if (e == cudaSuccess) e = cudaEventRecord(S.done, P.tail);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  S.busy = true;
+  S.B = B;
+  return SPE_OK;
+}
+
+int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, int H, int W,
+                          const double* det_boxes_host, int B, const spe_pnp_params* params) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_submit_batch_host: null ctx");
+  if (!frames_host || !det_boxes_host || !params) return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_host: null buffer");
+  PipelineBuffers pb;
+  Pipe* P = nullptr;
+  PipeSlot* Sp = nullptr;
+  int rc = pipe_prepare(ctx, "spe_submit_batch_host", slot, B, pb, &P, &Sp);
+  if (rc != SPE_OK) return rc;
+  PipeSlot& S = *Sp;
+  cudaError_t e = cudaSuccess;
   const long long need = static_cast<long long>(B) * H * W;
   if (S.frames_cap < need) {
     if (S.frames_dev) cudaFree(S.frames_dev);
@@ -234,6 +311,7 @@ int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, in
     S.frames_cap = cap;
   }
   spe_clip_boxes(det_boxes_host, B, S.boxes_h);
+  // upload only the intersection of each crop box with its frame (see spe_run_batch_host)
   long long h2d = 0;
   for (int i = 0; i < B && e == cudaSuccess; ++i) {
     const int32_t* bx = S.boxes_h + 4 * i;
@@ -248,33 +326,29 @@ int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, in
   *pb.last_h2d_bytes = h2d + static_cast<long long>(sizeof(int32_t)) * 4 * B;
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(S.boxes_dev, S.boxes_h, sizeof(int32_t) * 4 * B, cudaMemcpyHostToDevice, S.stream);
-  // the activations workspace is shared: this batch's kernels queue behind the previous batch's kernels, while
-  // its upload (above) already overlaps them
-  if (e == cudaSuccess && P.have_prev) e = cudaStreamWaitEvent(S.stream, P.prev_compute_done, 0);
+  if (e == cudaSuccess) e = cudaEventRecord(S.upload_done, S.stream);
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_submit_batch_host: ") + cudaGetErrorString(e));
-  int rc = spe_crop_resize_norm(ctx, S.frames_dev, H, W, W, static_cast<long long>(H) * W, S.boxes_dev, B, pb.R,
-                                pb.images_dev, S.stream);
+  return pipe_enqueue(ctx, "spe_submit_batch_host", slot, pb, *P, S, S.upload_done, S.frames_dev, H, W, W,
+                      static_cast<long long>(H) * W, S.boxes_dev, B, params);
+}
+
+int spe_submit_batch_dev(spe_ctx* ctx, int slot, const uint8_t* frames_dev, int H, int W, long long pitch,
+                         long long frame_stride, const int32_t* boxes_dev, int B, const spe_pnp_params* params,
+                         void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_submit_batch_dev: null ctx");
+  if (!frames_dev || !boxes_dev || !params || H <= 0 || W <= 0 || pitch < W)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_submit_batch_dev: bad argument");
+  PipelineBuffers pb;
+  Pipe* P = nullptr;
+  PipeSlot* Sp = nullptr;
+  int rc = pipe_prepare(ctx, "spe_submit_batch_dev", slot, B, pb, &P, &Sp);
   if (rc != SPE_OK) return rc;
-  const bool sig = pb.has_sigma != 0;
-  rc = spe_forward(ctx, pb.images_dev, B, pb.logits, pb.points, sig ? pb.logsig : nullptr, nullptr, nullptr, S.stream);
-  if (rc != SPE_OK) return rc;
-  spe_pnp_params pp = *params;
-  if (!sig) pp.weighted = 0;
-  const float* pl = pb.ov_logits ? pb.ov_logits : pb.logits;
-  const float* pp_pts = pb.ov_points ? pb.ov_points : pb.points;
-  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? pb.logsig : nullptr, S.boxes_dev, B, pb.Q, &pp, S.quat_dev, S.tvec_dev,
-                      S.assign_dev, S.status_dev, nullptr, nullptr, nullptr, nullptr, S.stream);
-  if (rc != SPE_OK) return rc;
-  e = cudaEventRecord(S.compute_done, S.stream);
-  P.prev_compute_done = S.compute_done;
-  P.have_prev = true;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(S.quat_h, S.quat_dev, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, S.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(S.tvec_h, S.tvec_dev, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, S.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(S.status_h, S.status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, S.stream);
-  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_submit_batch_host: ") + cudaGetErrorString(e));
-  S.busy = true;
-  S.B = B;
-  return SPE_OK;
+  // the frames and boxes are whatever `stream` has produced up to this call
+  cudaError_t e = cudaEventRecord(P->caller_ready, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_submit_batch_dev: ") + cudaGetErrorString(e));
+  *pb.last_h2d_bytes = 0;
+  return pipe_enqueue(ctx, "spe_submit_batch_dev", slot, pb, *P, *Sp, P->caller_ready, frames_dev, H, W, pitch,
+                      frame_stride, boxes_dev, B, params);
 }
 
 int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tvec_host, int32_t* status_host,
@@ -284,13 +358,27 @@ int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tv
   if (!quat_host || !tvec_host || !status_host) return set_error(ctx, SPE_ERR_INVALID, "spe_collect_batch_host: null buffer");
   PipeSlot& S = pipe_of(ctx).slot[slot];
   if (!S.busy) return set_error(ctx, SPE_ERR_STATE, "spe_collect_batch_host: nothing submitted on this slot");
-  cudaError_t e = cudaStreamSynchronize(S.stream);
+  cudaError_t e = cudaEventSynchronize(S.done);
   S.busy = false;
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_collect_batch_host: ") + cudaGetErrorString(e));
   memcpy(quat_host, S.quat_h, sizeof(double) * 4 * S.B);
   memcpy(tvec_host, S.tvec_h, sizeof(double) * 3 * S.B);
   memcpy(status_host, S.status_h, sizeof(int32_t) * S.B);
-  if (boxes_host) memcpy(boxes_host, S.boxes_h, sizeof(int32_t) * 4 * S.B);
+  if (boxes_host) memcpy(boxes_host, S.boxes_h, sizeof(int32_t) * 4 * S.B);   // host submits only (clip boxes)
+  return SPE_OK;
+}
+
+int spe_debug_read_slot_outputs(spe_ctx* ctx, int slot, float* logits_host, float* points_host) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_debug_read_slot_outputs: null ctx");
+  if (slot < 0 || slot >= kPipeSlots || !logits_host || !points_host)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_debug_read_slot_outputs: bad argument");
+  PipeSlot& S = pipe_of(ctx).slot[slot];
+  if (S.busy || S.B <= 0 || !S.logits_dev)
+    return set_error(ctx, SPE_ERR_STATE, "spe_debug_read_slot_outputs: collect the slot first");
+  const PipelineBuffers pb = pipeline_buffers(ctx);
+  cudaError_t e = cudaMemcpy(logits_host, S.logits_dev, sizeof(float) * 12 * pb.Q * S.B, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(points_host, S.points_dev, sizeof(float) * 2 * pb.Q * S.B, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_debug_read_slot_outputs: ") + cudaGetErrorString(e));
   return SPE_OK;
 }
 
@@ -305,9 +393,10 @@ int spe_profile_collect(double* ms_by_family, long long* launches_by_family) {
   return SPE_OK;
 }
 
-int spe_debug_set_pnp_override(spe_ctx* ctx, const float* logits_dev, const float* points_dev) {
+int spe_debug_set_pnp_override(spe_ctx* ctx, const float* logits_dev, const float* points_dev,
+                               const int32_t* boxes_dev) {
   if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_debug_set_pnp_override: null ctx");
-  set_pnp_override(ctx, logits_dev, points_dev);
+  set_pnp_override(ctx, logits_dev, points_dev, boxes_dev);
   return SPE_OK;
 }
 

@@ -132,8 +132,9 @@ using namespace spe;
 struct GraphKey {
   int B;
   const void *images, *logits, *points, *logsig, *aux_l, *aux_p;
+  int parts = 3, kv_slot = 0;   // 1 = trunk (+ decoder K/V), 2 = decoder + heads, 3 = both
   bool operator==(const GraphKey& o) const {
-    return B == o.B && images == o.images && logits == o.logits && points == o.points && logsig == o.logsig &&
+    return parts == o.parts && kv_slot == o.kv_slot && B == o.B && images == o.images && logits == o.logits && points == o.points && logsig == o.logsig &&
            aux_l == o.aux_l && aux_p == o.aux_p;
   }
 };
@@ -175,7 +176,8 @@ struct spe_ctx {
   // workspace (storage dtype unless noted)
   void *S0 = nullptr, *S1 = nullptr, *P0 = nullptr, *P1 = nullptr, *T1 = nullptr, *T2 = nullptr, *DS = nullptr,
        *COL = nullptr, *L2OUT = nullptr, *L3OUT = nullptr, *UP = nullptr, *CAT = nullptr, *FEAT = nullptr,
-       *X = nullptr, *X2 = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr, *KV = nullptr;
+       *X = nullptr, *X2 = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr, *KV = nullptr,
+       *KV2 = nullptr;   // second K/V set: the decoder of batch i reads one while the trunk of batch i+1 fills the other
   void *TGT = nullptr, *TGT2 = nullptr, *DQKV = nullptr, *DQ = nullptr, *DATT = nullptr, *DHID = nullptr,
        *HS = nullptr, *H1 = nullptr, *H2 = nullptr, *G1 = nullptr, *G2 = nullptr;
   float *logits_all = nullptr, *points_all = nullptr;
@@ -189,6 +191,7 @@ struct spe_ctx {
   double *p_quat = nullptr, *p_tvec = nullptr;
   int32_t *p_assign = nullptr, *p_status = nullptr;
   const float *ov_logits = nullptr, *ov_points = nullptr;   // bench hook, see spe_debug_set_pnp_override
+  const int32_t* ov_boxes = nullptr;
   long long last_h2d = 0;            // bytes uploaded by the last spe_run_batch_host
 
   // forward schedule
@@ -806,9 +809,25 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   return "";
 }
 
-// cross-attention K/V of all layers, decoder, heads for the whole batch
-static std::string forward_tail(spe_ctx* ctx, int B, float* logits, float* points, float* logsig, float* aux_logits,
-                                float* aux_points, cudaStream_t st) {
+// cross-attention K/V of all decoder layers from the encoder memory (last step of the trunk)
+static std::string forward_kv(spe_ctx* ctx, int B, void* kv, cudaStream_t st) {
+  Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
+  const long long T = ctx->tokens;
+  const int kvld = ctx->cfg.dec_layers * 512;
+  GemmDesc d;
+  d.mode = 0;
+  d.A = ctx->kv_split3 ? ctx->XS : ctx->X;
+  d.M = static_cast<long long>(B) * T; d.K = ctx->ca_kv_all.K; d.lda = ctx->ca_kv_all.K;
+  d.Wt = ctx->ca_kv_all.w; d.N = ctx->ca_kv_all.N;
+  d.residual = ctx->ca_kv_addend; d.res_ld = kvld; d.res_mod = static_cast<int>(T); d.res_f32 = 1;
+  d.out = kv; d.out_ld = kvld;
+  d.round_out = ctx->kv_split3 ? 0 : 1;   // the decoder attention rounds its own operands
+  return launch_gemm(f.dt, d, ctx->num_sms, st);
+}
+
+// decoder and heads for the whole batch
+static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, float* points, float* logsig,
+                                float* aux_logits, float* aux_points, cudaStream_t st) {
   const spe_config& c = ctx->cfg;
   Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
   const long long Bl = B;
@@ -819,17 +838,6 @@ static std::string forward_tail(spe_ctx* ctx, int B, float* logits, float* point
   const int Q = c.num_queries, LD = c.dec_layers;
   const long long MQ = Bl * Q;
   const int kvld = LD * 512;
-  {
-    GemmDesc d;   // K/V of all decoder layers from the encoder memory
-    d.mode = 0;
-    d.A = ctx->kv_split3 ? ctx->XS : ctx->X;
-    d.M = Bl * T; d.K = ctx->ca_kv_all.K; d.lda = ctx->ca_kv_all.K;
-    d.Wt = ctx->ca_kv_all.w; d.N = ctx->ca_kv_all.N;
-    d.residual = ctx->ca_kv_addend; d.res_ld = kvld; d.res_mod = Ti; d.res_f32 = 1;
-    d.out = ctx->KV; d.out_ld = kvld;
-    d.round_out = ctx->kv_split3 ? 0 : 1;   // the decoder attention rounds its own operands
-    TRY_S(launch_gemm(f.dt, d, ctx->num_sms, st));
-  }
   SPE_CUDA_TRY(cudaMemsetAsync(ctx->TGT, 0, static_cast<size_t>(MQ * 256 * f.es), st));
   for (int i = 0; i < LD; ++i) {
     const DecLayer& L = ctx->dec[i];
@@ -838,7 +846,7 @@ static std::string forward_tail(spe_ctx* ctx, int B, float* logits, float* point
     TRY_S(f.gemm(ctx->DATT, MQ, L.sa_out, ctx->TGT2, 256, false, ctx->TGT, 256));
     TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT, 1));
     TRY_S(f.gemm(ctx->TGT, MQ, L.ca_q, ctx->DQ, 256, false, L.ca_q_addend, 256, Q, 1));
-    TRY_S(f.attn(ctx->DQ, 256, f.col(ctx->KV, i * 512), kvld, f.col(ctx->KV, i * 512 + 256), kvld, ctx->DATT, Q, Ti, 1));
+    TRY_S(f.attn(ctx->DQ, 256, f.col(kv, i * 512), kvld, f.col(kv, i * 512 + 256), kvld, ctx->DATT, Q, Ti, 1));
     TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, ctx->TGT, 256));
     TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT, 1));
     TRY_S(f.gemm(ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
@@ -880,26 +888,52 @@ static int chunk_images(const spe_ctx* ctx, int B) {
   return ctx->sub_batch < B ? ctx->sub_batch : B;
 }
 
-static std::string forward_schedule(spe_ctx* ctx, const float* images, int B, float* logits, float* points,
-                                    float* logsig, float* aux_logits, float* aux_points, cudaStream_t st) {
-  const long long es = static_cast<long long>(dtype_size(ctx->dt));
-  const long long img_elems = 3ll * ctx->cfg.input_size * ctx->cfg.input_size;
-  const int SB = chunk_images(ctx, B);
-  for (int c0 = 0; c0 < B; c0 += SB) {
-    const int nb = (B - c0) < SB ? (B - c0) : SB;
-    void* Xc = static_cast<uint8_t*>(ctx->X) + static_cast<long long>(c0) * ctx->tokens * 256 * es;
-    TRY_S(forward_trunk(ctx, images + c0 * img_elems, nb, Xc, st));
+static std::string kv_buffer(spe_ctx* ctx, int kv_slot, void** kv) {
+  if (kv_slot == 0) { *kv = ctx->KV; return ""; }
+  if (!ctx->KV2) {
+    const size_t bytes = static_cast<size_t>(ctx->cfg.max_batch) * ctx->tokens * ctx->cfg.dec_layers * 512 *
+                         dtype_size(ctx->dt);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return "out of device memory (second K/V set)"; }
+    ctx->allocs.push_back(p);
+    ctx->KV2 = p;
   }
-  return forward_tail(ctx, B, logits, points, logsig, aux_logits, aux_points, st);
+  *kv = ctx->KV2;
+  return "";
+}
+
+// parts: bit 0 = trunk (backbone, neck, encoder, decoder K/V), bit 1 = decoder + heads.  The two halves only share
+// the K/V set `kv_slot`, so the pipeline can run the decoder of one batch next to the trunk of the next.
+static std::string forward_schedule(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits,
+                                    float* points, float* logsig, float* aux_logits, float* aux_points,
+                                    cudaStream_t st) {
+  void* kv = nullptr;
+  TRY_S(kv_buffer(ctx, kv_slot, &kv));
+  if (parts & 1) {
+    const long long es = static_cast<long long>(dtype_size(ctx->dt));
+    const long long img_elems = 3ll * ctx->cfg.input_size * ctx->cfg.input_size;
+    const int SB = chunk_images(ctx, B);
+    for (int c0 = 0; c0 < B; c0 += SB) {
+      const int nb = (B - c0) < SB ? (B - c0) : SB;
+      void* Xc = static_cast<uint8_t*>(ctx->X) + static_cast<long long>(c0) * ctx->tokens * 256 * es;
+      TRY_S(forward_trunk(ctx, images + c0 * img_elems, nb, Xc, st));
+    }
+    TRY_S(forward_kv(ctx, B, kv, st));
+  }
+  if (parts & 2) TRY_S(forward_tail(ctx, B, kv, logits, points, logsig, aux_logits, aux_points, st));
+  return "";
 }
 
 // The schedule is a fixed sequence of ~150-600 launches: after one eager run per (batch, buffer set) it is captured
 // into a CUDA graph and replayed, which removes the per-launch CPU cost (tensor-map encodes, launch calls).
-std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits, float* points, float* logsig,
-                         float* aux_logits, float* aux_points, cudaStream_t st) {
+std::string forward_parts(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits,
+                          float* points, float* logsig, float* aux_logits, float* aux_points, cudaStream_t st) {
   const bool graphs_ok = ctx->use_graphs && !ctx->taps_enabled && !profile_timing_enabled();
-  if (!graphs_ok) return forward_schedule(ctx, images, B, logits, points, logsig, aux_logits, aux_points, st);
-  GraphKey key{B, images, logits, points, logsig, aux_logits, aux_points};
+  if (!graphs_ok)
+    return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
+  GraphKey key{B, images, logits, points, logsig, aux_logits, aux_points, parts, kv_slot};
+  if (!(parts & 1)) key.images = nullptr;
+  if (!(parts & 2)) key.logits = key.points = key.logsig = key.aux_l = key.aux_p = nullptr;
   for (auto& g : ctx->graphs) {
     if (!(g.key == key)) continue;
     if (g.exec == nullptr) {
@@ -908,7 +942,7 @@ std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits
       profile_peek_launches(before);
       cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
       if (e != cudaSuccess) { ctx->use_graphs = false; cudaGetLastError(); break; }
-      std::string s = forward_schedule(ctx, images, B, logits, points, logsig, aux_logits, aux_points, st);
+      std::string s = forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
       cudaGraph_t graph = nullptr;
       e = cudaStreamEndCapture(st, &graph);
       if (!s.empty() || e != cudaSuccess || graph == nullptr) {
@@ -931,7 +965,7 @@ std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits
     return "";
   }
   if (ctx->use_graphs) {
-    if (ctx->graphs.size() >= 8) {               // bounded cache: drop the oldest
+    if (ctx->graphs.size() >= 12) {              // bounded cache: drop the oldest
       if (ctx->graphs.front().exec) cudaGraphExecDestroy(ctx->graphs.front().exec);
       ctx->graphs.erase(ctx->graphs.begin());
     }
@@ -939,7 +973,13 @@ std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits
     ge.key = key;
     ctx->graphs.push_back(ge);
   }
-  return forward_schedule(ctx, images, B, logits, points, logsig, aux_logits, aux_points, st);   // first call: eager
+  // first call: eager
+  return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
+}
+
+std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits, float* points, float* logsig,
+                         float* aux_logits, float* aux_points, cudaStream_t st) {
+  return forward_parts(ctx, 3, 0, images, B, logits, points, logsig, aux_logits, aux_points, st);
 }
 
 }  // namespace spe
@@ -1083,18 +1123,28 @@ struct PipelineBuffers {
   uint8_t** frames_dev; long long* frames_cap; int32_t* boxes_dev; float* images_dev; float* logits; float* points;
   float* logsig; double* quat; double* tvec; int32_t* assign; int32_t* status; int device; int max_batch; int R; int Q;
   int has_sigma; const float* ov_logits; const float* ov_points; long long* last_h2d_bytes;
+  const int32_t* ov_boxes;
 };
 PipelineBuffers pipeline_buffers(spe_ctx* ctx) {
   return PipelineBuffers{&ctx->frames_dev, &ctx->frames_cap, ctx->boxes_dev, ctx->images_dev, ctx->p_logits,
                          ctx->p_points,    ctx->p_logsig,    ctx->p_quat,    ctx->p_tvec,     ctx->p_assign,
                          ctx->p_status,    ctx->device,      ctx->cfg.max_batch, ctx->cfg.input_size,
                          ctx->cfg.num_queries, ctx->cfg.has_sigma, ctx->ov_logits, ctx->ov_points,
-                         &ctx->last_h2d};
+                         &ctx->last_h2d, ctx->ov_boxes};
 }
 long long last_h2d_bytes(spe_ctx* ctx) { return ctx->last_h2d; }
-void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points) {
+void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points, const int32_t* boxes) {
   ctx->ov_logits = logits;
   ctx->ov_points = points;
+  ctx->ov_boxes = boxes;
 }
 int set_error(spe_ctx* ctx, int code, const std::string& msg) { return fail(ctx, code, msg); }
+// one half of the forward on `st` (parts: 1 = trunk + decoder K/V into set kv_slot, 2 = decoder + heads from it)
+int forward_half(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits, float* points,
+                 float* logsig, cudaStream_t st) {
+  if (!ctx->weights_loaded) return fail(ctx, SPE_ERR_STATE, "pipeline: call spe_load_weights first");
+  std::string s = forward_parts(ctx, parts, kv_slot, images, B, logits, points, logsig, nullptr, nullptr, st);
+  if (!s.empty()) return fail(ctx, SPE_ERR_CUDA, "pipeline forward: " + s);
+  return SPE_OK;
+}
 }  // namespace spe

@@ -213,6 +213,19 @@ class Engine:
                                              det.ctypes.data_as(C.c_void_p), B, C.byref(p)), self._ctx)
         self._inflight[slot] = (frames_host, B, int(self.lib.spe_last_h2d_bytes(self._ctx)))
 
+    def submit_batch_dev(self, slot, frames_dev, boxes_dev, reproj=20.0, weighted=False, reject=False):
+        """``submit_batch_host`` for frames already resident in HBM: uint8 CUDA tensor [B,H,W] (contiguous) and the
+        int32 clip boxes [B,4] (``clip_boxes``), both produced on the current torch stream.  Collect with
+        ``collect_batch_host``; the tensors must stay untouched until then."""
+        assert frames_dev.is_cuda and frames_dev.dtype == torch.uint8 and frames_dev.is_contiguous()
+        assert boxes_dev.is_cuda and boxes_dev.dtype == torch.int32 and boxes_dev.is_contiguous()
+        B, H, W = frames_dev.shape
+        p = SpePnpParams(reproj_thresh=float(reproj), weighted=int(weighted), reject=int(reject),
+                         reject_rms_px=5.0, reject_sigma_px=12.0)
+        check(self.lib.spe_submit_batch_dev(self._ctx, slot, C.c_void_p(frames_dev.data_ptr()), H, W, W, H * W,
+                                            C.c_void_p(boxes_dev.data_ptr()), B, C.byref(p), _stream(frames_dev.device)), self._ctx)
+        self._inflight[slot] = ((frames_dev, boxes_dev), B, 0)
+
     def collect_batch_host(self, slot):
         frames_host, B, h2d = self._inflight.pop(slot)
         quat = np.empty((B, 4), dtype=np.float64); tvec = np.empty((B, 3), dtype=np.float64)
@@ -221,6 +234,14 @@ class Engine:
                                               tvec.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
                                               boxes.ctypes.data_as(C.c_void_p)), self._ctx)
         return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes, "h2d_bytes": h2d}
+
+    def read_slot_outputs(self, slot, B):
+        """Test hook: (logits [B,Q,12], points [B,Q,2]) the network produced for the batch last collected from `slot`."""
+        Q = self.cfg.num_queries
+        logits = np.empty((B, Q, 12), dtype=np.float32); points = np.empty((B, Q, 2), dtype=np.float32)
+        check(self.lib.spe_debug_read_slot_outputs(self._ctx, slot, logits.ctypes.data_as(C.c_void_p),
+                                                   points.ctypes.data_as(C.c_void_p)), self._ctx)
+        return logits, points
 
     # ---- measurement hooks (bench.py) ------------------------------------------------------------------------------
     FAMILIES = ("gemm", "attention", "elementwise", "heads", "crop", "pnp")
@@ -235,10 +256,10 @@ class Engine:
         check(self.lib.spe_profile_collect(ms, n))
         return dict(zip(self.FAMILIES, list(ms))), dict(zip(self.FAMILIES, list(n)))
 
-    def set_pnp_override(self, logits=None, points=None):
-        """Bench hook: run_batch_host feeds these resident tensors to the pose stage (None resets)."""
-        self._override = (logits, points)   # keep alive
-        check(self.lib.spe_debug_set_pnp_override(self._ctx, _ptr(logits), _ptr(points)), self._ctx)
+    def set_pnp_override(self, logits=None, points=None, boxes=None):
+        """Bench hook: the batch pipelines feed these resident tensors to the pose stage (None resets)."""
+        self._override = (logits, points, boxes)   # keep alive
+        check(self.lib.spe_debug_set_pnp_override(self._ctx, _ptr(logits), _ptr(points), _ptr(boxes)), self._ctx)
 
     # ---- bring-up -----------------------------------------------------------------------------------------------
     def enable_taps(self, on=True):

@@ -166,6 +166,43 @@ def test_host_pipeline_matches_stagewise(lib, cuda_dev):
     eng.close()
 
 
+def test_two_lane_pipeline_matches_serial(lib, cuda_dev):
+    """Decoder/pose of batch i running next to the trunk of batch i+1 (own K/V set per slot) changes nothing:
+    network outputs and poses of every batch are bit-identical to the one-stream stage calls."""
+    cfg = model_ref.ModelCfg()
+    B = 8
+    eng = _engine(cfg, 224, B, "tf32")
+    eng.load_state_dict(synth.make_state_dict(cfg, seed=0))
+    det_all = synth.load_detector_boxes()
+    preds = synth.make_predictions(B, Q=cfg.num_queries, seed=5)
+    syn = [torch.from_numpy(preds[k]).cuda() for k in ("logits", "points")]
+    syn_boxes = torch.from_numpy(preds["boxes"]).to(torch.int32).cuda()
+    sets = []
+    for k in range(5):
+        det = det_all[k * B:(k + 1) * B]
+        frames = torch.from_numpy(synth.make_frames(B, det, seed=10 + k)).cuda()
+        boxes = torch.from_numpy(eng.clip_boxes(det)).cuda()
+        out = eng.forward(eng.crop_resize_norm(frames, boxes))
+        ref = (out["pred_logits"].cpu().numpy().copy(), out["pred_points"].cpu().numpy().copy())
+        sets.append((frames, boxes, ref))
+    pose_ref = eng.assign_pnp(syn[0], syn[1], syn_boxes)
+    assert int((pose_ref["status"] == 0).sum()) >= B // 2
+    eng.set_pnp_override(syn[0], syn[1], syn_boxes)
+    for rep in range(2):                                 # second round replays the captured graphs
+        eng.submit_batch_dev(0, sets[0][0], sets[0][1])
+        for i in range(len(sets)):
+            if i + 1 < len(sets):
+                eng.submit_batch_dev((i + 1) & 1, sets[i + 1][0], sets[i + 1][1])
+            r = eng.collect_batch_host(i & 1)
+            logits, points = eng.read_slot_outputs(i & 1, B)
+            assert np.array_equal(logits, sets[i][2][0]) and np.array_equal(points, sets[i][2][1]), (rep, i)
+            assert np.array_equal(r["status"], pose_ref["status"].cpu().numpy())
+            assert np.array_equal(r["quat"], pose_ref["quat"].cpu().numpy())
+            assert np.array_equal(r["tvec"], pose_ref["tvec"].cpu().numpy())
+    eng.set_pnp_override(None, None, None)
+    eng.close()
+
+
 def test_errors_are_loud(lib, cuda_dev):
     cfg = model_ref.ModelCfg()
     eng = _engine(cfg, 224, 2, "tf32")
