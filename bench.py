@@ -217,25 +217,26 @@ def run_b200(args):
         # label, which would let the solver exit early and under-count its cost)
         return eng.assign_pnp(syn_logits, syn_points, syn_boxes, reproj=20.0)
 
-    # The throughput loop runs the same three stages through the two-lane batch pipeline (spe_submit_batch_dev):
-    # every step is one full batch, but the latency-bound tail of step i (decoder, heads, PnP, result download) runs
-    # next to the machine-filling trunk of step i+1.  SPE_BENCH_SERIAL=1 times the one-stream loop instead.
-    serial = os.environ.get("SPE_BENCH_SERIAL", "0") == "1"
+    # The throughput loop runs the same three stages through the multi-slot batch pipeline (spe_submit_batch_dev):
+    # every step is one full batch on its own slot (streams + activation set); with SLOTS batches in flight the GPU
+    # fills one batch's latency-bound decoder / pose stage and GEMM tail waves with another batch's work.
+    # SPE_BENCH_SLOTS=1 times strictly one batch at a time.
+    SLOTS = max(1, min(4, int(os.environ.get("SPE_BENCH_SLOTS", "3"))))
     eng.set_pnp_override(syn_logits, syn_points, syn_boxes)
 
-    def run_steps(n, first):
-        if serial:
-            out = None
-            for i in range(first, first + n):
-                out = step(i)
-            return out
+    def pipelined(n, first, submit):
+        """n batches through the pipeline, SLOTS in flight; returns the last batch's result"""
         out = None
-        eng.submit_batch_dev(first & 1, frames_dev[first % n_sets], boxes_dev[first % n_sets])
+        for i in range(first, min(first + SLOTS, first + n)):
+            submit(i % SLOTS, i)
         for i in range(first, first + n):
-            if i + 1 < first + n:
-                eng.submit_batch_dev((i + 1) & 1, frames_dev[(i + 1) % n_sets], boxes_dev[(i + 1) % n_sets])
-            out = eng.collect_batch_host(i & 1)     # poses of step i are in host memory
+            out = eng.collect_batch_host(i % SLOTS)       # poses of batch i are in host memory
+            if i + SLOTS < first + n:
+                submit(i % SLOTS, i + SLOTS)
         return out
+
+    def run_steps(n, first):
+        return pipelined(n, first, lambda slot, i: eng.submit_batch_dev(slot, frames_dev[i % n_sets], boxes_dev[i % n_sets]))
 
     def barrier():
         if world > 1:
@@ -275,17 +276,14 @@ def run_b200(args):
 
     # ---- end to end through the C ABI with host buffers (H2D of the frames + D2H of the poses inside the region)
     eng.set_pnp_override(syn_logits, syn_points, syn_boxes)
-    # double-buffered host pipeline: the ROI upload of batch i+1 overlaps the kernels of batch i; every batch's poses
-    # are read back to host memory inside the timed region
+    # same pipeline fed from pinned host frames: the ROI upload of a batch hides behind the kernels of the batches in
+    # flight; every batch's poses are read back to host memory inside the timed region
     for i in range(max(args.warmup, 1)):
         eng.run_batch_host(frames_host[i % n_sets], det_sets[i % n_sets])
+    pipelined(SLOTS, 0, lambda slot, i: eng.submit_batch_host(slot, frames_host[i % n_sets], det_sets[i % n_sets]))
     barrier()
     t0 = time.perf_counter()
-    eng.submit_batch_host(0, frames_host[0], det_sets[0])
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            eng.submit_batch_host((i + 1) & 1, frames_host[(i + 1) % n_sets], det_sets[(i + 1) % n_sets])
-        r = eng.collect_batch_host(i & 1)
+    r = pipelined(args.steps, 0, lambda slot, i: eng.submit_batch_host(slot, frames_host[i % n_sets], det_sets[i % n_sets]))
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -347,6 +345,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "parallelism": f"image-sharded x{world}, no collective",
+                       "batches_in_flight": SLOTS,
                        "l2_policy": f"inputs larger than L2: {n_sets} alternating frame sets of {frames_dev[0].numel() / 1e6:.0f} MB",
                        "pnp_inputs": "resident synthetic keypoint sets (random-init weights collapse to one label)",
                        "poses_solved_per_batch": solved},

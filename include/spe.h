@@ -119,12 +119,16 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
                        const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
                        int32_t* boxes_host /*[B,4] or NULL*/, void* stream);
 
-/* Double-buffered form of the same loop: submit enqueues upload + compute + download of one batch on internal
- * streams and returns at once; collect waits for that slot (0 or 1) and hands out the poses.  Submitting batch i+1
- * before collecting batch i overlaps three things: the upload of i+1, the trunk of i+1 (crop, backbone, neck, encoder,
- * decoder K/V -- fills the machine) and the tail of i (decoder, heads, assignment + PnP, download -- ~100 small
- * latency-bound launches that run in the gaps of the trunk; each slot owns its K/V set).  frames_host must be pinned
- * and stay valid until the slot is collected. */
+/* Pipelined form of the same loop.  A slot (0 .. SPE_PIPELINE_SLOTS-1) is a complete, independent instance of the
+ * path: own streams, frame / result buffers and activation set (allocated on first use, ~3.5 GB at B=64).  submit
+ * enqueues upload + compute + download of one batch on the slot and returns at once; collect waits for that slot and
+ * hands out the poses.  Keeping several slots in flight lets the GPU run whole batches next to each other: the upload
+ * of one hides behind the kernels of the others, and the small latency-bound launches of a batch's decoder / pose
+ * stage and the drained last wave of every persistent GEMM are filled with another batch's work (B=64 on B200:
+ * 6.7 ms/batch one at a time, 5.9 ms with three in flight).  Results are bit-identical to the one-stream calls.
+ * frames_host must be pinned and stay valid until the slot is collected.  Do not mix with spe_forward /
+ * spe_run_batch_host while slots are in flight (slot 0 shares their activation set). */
+#define SPE_PIPELINE_SLOTS 4
 int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, int H, int W,
                           const double* det_boxes_host, int B, const spe_pnp_params* params);
 int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tvec_host, int32_t* status_host,

@@ -29,10 +29,12 @@ int forward_half(spe_ctx* ctx, int parts, int kv_slot, const float* images, int 
 using namespace spe;
 
 namespace {
-constexpr int kPipeSlots = 2;
+constexpr int kPipeSlots = SPE_PIPELINE_SLOTS;
 struct PipeSlot {
   cudaStream_t stream = nullptr;          // upload stream of this slot
-  cudaEvent_t upload_done = nullptr, trunk_done = nullptr, done = nullptr;
+  cudaStream_t compute = nullptr;         // crop -> forward -> assignment + PnP -> result download of this slot
+  cudaEvent_t upload_done = nullptr, done = nullptr;
+  float* images_dev = nullptr;
   uint8_t* frames_dev = nullptr;
   long long frames_cap = 0;
   int32_t *boxes_dev = nullptr, *status_dev = nullptr, *assign_dev = nullptr;
@@ -43,12 +45,12 @@ struct PipeSlot {
   bool busy = false;
   int B = 0;
 };
-// Two compute lanes shared by both slots: the trunk (crop, backbone, neck, encoder, decoder K/V -- throughput-bound,
-// fills the machine) and the tail (decoder, heads, assignment + PnP, result download -- ~100 small latency-bound
-// launches).  They only share the slot's K/V set, so the tail of batch i runs in the gaps of the trunk of batch i+1.
+// Every slot is a complete, independent instance of the path: its own streams, frame / result buffers and activation
+// set (model.cu: use_workspace).  Batches submitted on different slots share nothing but the weights, so the GPU runs
+// them next to each other: the ~100 small latency-bound launches of one batch's decoder / pose stage and the drained
+// last wave of every persistent GEMM are filled with another batch's tiles.
 struct Pipe {
   PipeSlot slot[kPipeSlots];
-  cudaStream_t trunk = nullptr, tail = nullptr;
   cudaEvent_t caller_ready = nullptr;
 };
 std::map<spe_ctx*, Pipe*> g_pipes;
@@ -65,7 +67,7 @@ void pipeline_release(spe_ctx* ctx) {   // called by spe_destroy
   if (it == g_pipes.end()) return;
   for (PipeSlot& S : it->second->slot) {
     if (S.stream) cudaStreamSynchronize(S.stream);
-    if (S.done && S.busy) cudaEventSynchronize(S.done);
+    if (S.compute) cudaStreamSynchronize(S.compute);
     if (S.frames_dev) cudaFree(S.frames_dev);
     if (S.boxes_dev) cudaFree(S.boxes_dev);
     if (S.status_dev) cudaFree(S.status_dev);
@@ -79,14 +81,13 @@ void pipeline_release(spe_ctx* ctx) {   // called by spe_destroy
     if (S.status_h) cudaFreeHost(S.status_h);
     if (S.quat_h) cudaFreeHost(S.quat_h);
     if (S.tvec_h) cudaFreeHost(S.tvec_h);
+    if (S.images_dev) cudaFree(S.images_dev);
     if (S.upload_done) cudaEventDestroy(S.upload_done);
-    if (S.trunk_done) cudaEventDestroy(S.trunk_done);
     if (S.done) cudaEventDestroy(S.done);
     if (S.stream) cudaStreamDestroy(S.stream);
+    if (S.compute) cudaStreamDestroy(S.compute);
   }
   Pipe* P = it->second;
-  if (P->trunk) { cudaStreamSynchronize(P->trunk); cudaStreamDestroy(P->trunk); }
-  if (P->tail) { cudaStreamSynchronize(P->tail); cudaStreamDestroy(P->tail); }
   if (P->caller_ready) cudaEventDestroy(P->caller_ready);
   delete it->second;
   g_pipes.erase(it);
@@ -213,9 +214,10 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
 
 long long spe_last_h2d_bytes(spe_ctx* ctx) { return ctx ? last_h2d_bytes(ctx) : -1; }
 
-// ---- double-buffered pipeline: upload of batch i+1 || trunk of batch i+1 || decoder + pose + download of batch i ----
+// ---- multi-slot pipeline: whole batches in flight next to each other ------------------------------------------
 static int pipe_prepare(spe_ctx* ctx, const char* who, int slot, int B, PipelineBuffers& pb, Pipe** Pp, PipeSlot** Sp) {
-  if (slot < 0 || slot >= kPipeSlots) return set_error(ctx, SPE_ERR_INVALID, std::string(who) + ": slot must be 0 or 1");
+  if (slot < 0 || slot >= kPipeSlots)
+    return set_error(ctx, SPE_ERR_INVALID, std::string(who) + ": slot outside [0, SPE_PIPELINE_SLOTS)");
   pb = pipeline_buffers(ctx);
   if (B <= 0 || B > pb.max_batch) return set_error(ctx, SPE_ERR_INVALID, std::string(who) + ": batch outside [1, max_batch]");
   cudaSetDevice(pb.device);
@@ -223,20 +225,16 @@ static int pipe_prepare(spe_ctx* ctx, const char* who, int slot, int B, Pipeline
   PipeSlot& S = P.slot[slot];
   if (S.busy) return set_error(ctx, SPE_ERR_STATE, std::string(who) + ": slot still in flight (collect it first)");
   cudaError_t e = cudaSuccess;
-  if (!P.trunk) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
-    e = cudaStreamCreateWithPriority(&P.trunk, cudaStreamNonBlocking, lo);
-    // the small tail kernels take the SMs a finishing trunk kernel frees before the next trunk kernel does
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&P.tail, cudaStreamNonBlocking, hi);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.caller_ready, cudaEventDisableTiming);
-    if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline streams: ") + cudaGetErrorString(e));
+  if (!P.caller_ready) {
+    e = cudaEventCreateWithFlags(&P.caller_ready, cudaEventDisableTiming);
+    if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline: ") + cudaGetErrorString(e));
   }
   if (!S.stream) {
     e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S.compute, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.upload_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.trunk_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&S.images_dev, sizeof(float) * 3 * pb.R * pb.R * pb.max_batch);
     if (e == cudaSuccess) e = cudaMalloc(&S.boxes_dev, sizeof(int32_t) * 4 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMalloc(&S.quat_dev, sizeof(double) * 4 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMalloc(&S.tvec_dev, sizeof(double) * 3 * pb.max_batch);
@@ -256,33 +254,30 @@ static int pipe_prepare(spe_ctx* ctx, const char* who, int slot, int B, Pipeline
   return SPE_OK;
 }
 
-// crop + trunk on the trunk lane (after `ready`), decoder + pose + download on the tail lane
+// the whole path of one batch on the slot's compute stream (after `ready`), on the slot's activation set
 static int pipe_enqueue(spe_ctx* ctx, const char* who, int slot, const PipelineBuffers& pb, Pipe& P, PipeSlot& S,
                         cudaEvent_t ready, const uint8_t* frames_dev, int H, int W, long long pitch,
                         long long frame_stride, const int32_t* boxes_dev, int B, const spe_pnp_params* params) {
-  cudaError_t e = cudaStreamWaitEvent(P.trunk, ready, 0);
+  (void)P;
+  cudaStream_t st = S.compute;
+  cudaError_t e = cudaStreamWaitEvent(st, ready, 0);
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
-  int rc = spe_crop_resize_norm(ctx, frames_dev, H, W, pitch, frame_stride, boxes_dev, B, pb.R, pb.images_dev, P.trunk);
+  int rc = spe_crop_resize_norm(ctx, frames_dev, H, W, pitch, frame_stride, boxes_dev, B, pb.R, S.images_dev, st);
   if (rc != SPE_OK) return rc;
   const bool sig = pb.has_sigma != 0;
-  rc = forward_half(ctx, 1, slot, pb.images_dev, B, nullptr, nullptr, nullptr, P.trunk);
-  if (rc != SPE_OK) return rc;
-  e = cudaEventRecord(S.trunk_done, P.trunk);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(P.tail, S.trunk_done, 0);
-  if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
-  rc = forward_half(ctx, 2, slot, nullptr, B, S.logits_dev, S.points_dev, sig ? S.logsig_dev : nullptr, P.tail);
+  rc = forward_half(ctx, 3, slot, S.images_dev, B, S.logits_dev, S.points_dev, sig ? S.logsig_dev : nullptr, st);
   if (rc != SPE_OK) return rc;
   spe_pnp_params pp = *params;
   if (!sig) pp.weighted = 0;
   const float* pl = pb.ov_logits ? pb.ov_logits : S.logits_dev;
   const float* pp_pts = pb.ov_points ? pb.ov_points : S.points_dev;
-  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? S.logsig_dev : nullptr, pb.ov_boxes ? pb.ov_boxes : boxes_dev, B, pb.Q, &pp, S.quat_dev, S.tvec_dev,
-                      S.assign_dev, S.status_dev, nullptr, nullptr, nullptr, nullptr, P.tail);
+  rc = spe_assign_pnp(ctx, pl, pp_pts, sig ? S.logsig_dev : nullptr, pb.ov_boxes ? pb.ov_boxes : boxes_dev, B, pb.Q,
+                      &pp, S.quat_dev, S.tvec_dev, S.assign_dev, S.status_dev, nullptr, nullptr, nullptr, nullptr, st);
   if (rc != SPE_OK) return rc;
-  e = cudaMemcpyAsync(S.quat_h, S.quat_dev, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, P.tail);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(S.tvec_h, S.tvec_dev, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, P.tail);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(S.status_h, S.status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, P.tail);
-  if (e == cudaSuccess) e = cudaEventRecord(S.done, P.tail);
+  e = cudaMemcpyAsync(S.quat_h, S.quat_dev, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.tvec_h, S.tvec_dev, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S.status_h, S.status_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaEventRecord(S.done, st);
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
   S.busy = true;
   S.B = B;
@@ -354,7 +349,8 @@ int spe_submit_batch_dev(spe_ctx* ctx, int slot, const uint8_t* frames_dev, int 
 int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tvec_host, int32_t* status_host,
                            int32_t* boxes_host) {
   if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_collect_batch_host: null ctx");
-  if (slot < 0 || slot >= kPipeSlots) return set_error(ctx, SPE_ERR_INVALID, "spe_collect_batch_host: slot must be 0 or 1");
+  if (slot < 0 || slot >= kPipeSlots)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_collect_batch_host: slot outside [0, SPE_PIPELINE_SLOTS)");
   if (!quat_host || !tvec_host || !status_host) return set_error(ctx, SPE_ERR_INVALID, "spe_collect_batch_host: null buffer");
   PipeSlot& S = pipe_of(ctx).slot[slot];
   if (!S.busy) return set_error(ctx, SPE_ERR_STATE, "spe_collect_batch_host: nothing submitted on this slot");

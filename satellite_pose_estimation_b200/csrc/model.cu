@@ -176,11 +176,17 @@ struct spe_ctx {
   // workspace (storage dtype unless noted)
   void *S0 = nullptr, *S1 = nullptr, *P0 = nullptr, *P1 = nullptr, *T1 = nullptr, *T2 = nullptr, *DS = nullptr,
        *COL = nullptr, *L2OUT = nullptr, *L3OUT = nullptr, *UP = nullptr, *CAT = nullptr, *FEAT = nullptr,
-       *X = nullptr, *X2 = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr, *KV = nullptr,
-       *KV2 = nullptr;   // second K/V set: the decoder of batch i reads one while the trunk of batch i+1 fills the other
+       *X = nullptr, *X2 = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr, *KV = nullptr;
   void *TGT = nullptr, *TGT2 = nullptr, *DQKV = nullptr, *DQ = nullptr, *DATT = nullptr, *DHID = nullptr,
        *HS = nullptr, *H1 = nullptr, *H2 = nullptr, *G1 = nullptr, *G2 = nullptr;
   float *logits_all = nullptr, *points_all = nullptr;
+  // Activation sets: every pipeline slot owns a full copy of the workspace above, so whole batches can be in flight
+  // next to each other.  The named pointers always hold the set selected by use_workspace() (enqueue is host-serial;
+  // launched kernels keep the pointers they were given).
+  struct WsField { void** field; long long bytes; };
+  std::vector<WsField> ws_fields;
+  std::vector<std::vector<void*>> ws_sets;
+  int ws_current = 0;
 
   // pipeline buffers for spe_run_batch_host
   uint8_t* frames_dev = nullptr;
@@ -568,9 +574,14 @@ std::string alloc_workspace(spe_ctx* ctx) {
   const long long R = c.input_size;
   const long long h2 = R / 2, h4 = R / 4, h8 = R / 8, h16 = R / 16;
   const long long T = ctx->tokens, Q = c.num_queries, LD = c.dec_layers, FF = c.dim_feedforward;
-  auto A = [&](void** p, long long elems) { return dmalloc_bytes(ctx, p, elems * es); };
+  auto AB = [&](void** p, long long bytes) {
+    std::string e = dmalloc_bytes(ctx, p, bytes);
+    if (e.empty()) ctx->ws_fields.push_back({p, bytes});
+    return e;
+  };
+  auto A = [&](void** p, long long elems) { return AB(p, elems * es); };
   TRY_S(A(&ctx->S0, B * h2 * h2 * 192));
-  TRY_S(dmalloc_bytes(ctx, &ctx->SP, B * (R + 6) * (R + 6) * 16));
+  TRY_S(AB(&ctx->SP, B * (R + 6) * (R + 6) * 16));
   TRY_S(A(&ctx->S1, B * h2 * h2 * 64));
   TRY_S(A(&ctx->P0, B * h4 * h4 * 256));
   TRY_S(A(&ctx->P1, B * h4 * h4 * 256));
@@ -603,6 +614,12 @@ std::string alloc_workspace(spe_ctx* ctx) {
   TRY_S(A(&ctx->H2, LD * B * Q * 256));
   TRY_S(A(&ctx->G1, B * Q * 256));
   TRY_S(A(&ctx->G2, B * Q * 256));
+  {
+    std::vector<void*> set0;
+    for (const auto& f : ctx->ws_fields) set0.push_back(*f.field);
+    ctx->ws_sets.assign(1, set0);
+    ctx->ws_current = 0;
+  }
   // pipeline buffers
   TRY_S(dmalloc(ctx, &ctx->boxes_dev, B * 4));
   TRY_S(dmalloc(ctx, &ctx->images_dev, B * 3 * R * R));
@@ -888,27 +905,37 @@ static int chunk_images(const spe_ctx* ctx, int B) {
   return ctx->sub_batch < B ? ctx->sub_batch : B;
 }
 
-static std::string kv_buffer(spe_ctx* ctx, int kv_slot, void** kv) {
-  if (kv_slot == 0) { *kv = ctx->KV; return ""; }
-  if (!ctx->KV2) {
-    const size_t bytes = static_cast<size_t>(ctx->cfg.max_batch) * ctx->tokens * ctx->cfg.dec_layers * 512 *
-                         dtype_size(ctx->dt);
-    void* p = nullptr;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return "out of device memory (second K/V set)"; }
-    ctx->allocs.push_back(p);
-    ctx->KV2 = p;
+// select activation set `set` (allocated on first use -- never during a graph capture: the first call with any
+// graph key runs eagerly)
+static std::string use_workspace(spe_ctx* ctx, int set) {
+  if (set < 0 || set >= 8) return "workspace set out of range";
+  while (static_cast<int>(ctx->ws_sets.size()) <= set) {
+    std::vector<void*> ns;
+    for (const auto& f : ctx->ws_fields) {
+      void* p = nullptr;
+      if (cudaMalloc(&p, static_cast<size_t>(f.bytes > 0 ? f.bytes : 16)) != cudaSuccess) {
+        cudaGetLastError();
+        for (void* q : ns) cudaFree(q);
+        return "out of device memory (activation set " + std::to_string(ctx->ws_sets.size()) + ")";
+      }
+      ns.push_back(p);
+    }
+    for (void* q : ns) ctx->allocs.push_back(q);
+    ctx->ws_sets.push_back(ns);
   }
-  *kv = ctx->KV2;
+  if (set != ctx->ws_current) {
+    for (size_t i = 0; i < ctx->ws_fields.size(); ++i) *ctx->ws_fields[i].field = ctx->ws_sets[set][i];
+    ctx->ws_current = set;
+  }
   return "";
 }
 
-// parts: bit 0 = trunk (backbone, neck, encoder, decoder K/V), bit 1 = decoder + heads.  The two halves only share
-// the K/V set `kv_slot`, so the pipeline can run the decoder of one batch next to the trunk of the next.
+// parts: bit 0 = trunk (backbone, neck, encoder, decoder K/V), bit 1 = decoder + heads, on activation set `kv_slot`.
 static std::string forward_schedule(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits,
                                     float* points, float* logsig, float* aux_logits, float* aux_points,
                                     cudaStream_t st) {
-  void* kv = nullptr;
-  TRY_S(kv_buffer(ctx, kv_slot, &kv));
+  TRY_S(use_workspace(ctx, kv_slot));
+  void* kv = ctx->KV;
   if (parts & 1) {
     const long long es = static_cast<long long>(dtype_size(ctx->dt));
     const long long img_elems = 3ll * ctx->cfg.input_size * ctx->cfg.input_size;
@@ -1139,7 +1166,7 @@ void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points, co
   ctx->ov_boxes = boxes;
 }
 int set_error(spe_ctx* ctx, int code, const std::string& msg) { return fail(ctx, code, msg); }
-// one half of the forward on `st` (parts: 1 = trunk + decoder K/V into set kv_slot, 2 = decoder + heads from it)
+// the forward (parts: 1 = trunk + decoder K/V, 2 = decoder + heads, 3 = both) on activation set `kv_slot`
 int forward_half(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits, float* points,
                  float* logsig, cudaStream_t st) {
   if (!ctx->weights_loaded) return fail(ctx, SPE_ERR_STATE, "pipeline: call spe_load_weights first");

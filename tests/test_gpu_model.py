@@ -166,9 +166,10 @@ def test_host_pipeline_matches_stagewise(lib, cuda_dev):
     eng.close()
 
 
-def test_two_lane_pipeline_matches_serial(lib, cuda_dev):
-    """Decoder/pose of batch i running next to the trunk of batch i+1 (own K/V set per slot) changes nothing:
-    network outputs and poses of every batch are bit-identical to the one-stream stage calls."""
+@pytest.mark.parametrize("slots", [2, 4])
+def test_multi_slot_pipeline_matches_serial(lib, cuda_dev, slots):
+    """Whole batches in flight next to each other (own streams + activation set per slot) change nothing: network
+    outputs and poses of every batch are bit-identical to the one-stream stage calls."""
     cfg = model_ref.ModelCfg()
     B = 8
     eng = _engine(cfg, 224, B, "tf32")
@@ -178,7 +179,7 @@ def test_two_lane_pipeline_matches_serial(lib, cuda_dev):
     syn = [torch.from_numpy(preds[k]).cuda() for k in ("logits", "points")]
     syn_boxes = torch.from_numpy(preds["boxes"]).to(torch.int32).cuda()
     sets = []
-    for k in range(5):
+    for k in range(7):
         det = det_all[k * B:(k + 1) * B]
         frames = torch.from_numpy(synth.make_frames(B, det, seed=10 + k)).cuda()
         boxes = torch.from_numpy(eng.clip_boxes(det)).cuda()
@@ -188,17 +189,24 @@ def test_two_lane_pipeline_matches_serial(lib, cuda_dev):
     pose_ref = eng.assign_pnp(syn[0], syn[1], syn_boxes)
     assert int((pose_ref["status"] == 0).sum()) >= B // 2
     eng.set_pnp_override(syn[0], syn[1], syn_boxes)
+    n = len(sets)
     for rep in range(2):                                 # second round replays the captured graphs
-        eng.submit_batch_dev(0, sets[0][0], sets[0][1])
-        for i in range(len(sets)):
-            if i + 1 < len(sets):
-                eng.submit_batch_dev((i + 1) & 1, sets[i + 1][0], sets[i + 1][1])
-            r = eng.collect_batch_host(i & 1)
-            logits, points = eng.read_slot_outputs(i & 1, B)
+        for i in range(min(slots, n)):
+            eng.submit_batch_dev(i % slots, sets[i][0], sets[i][1])
+        for i in range(n):
+            r = eng.collect_batch_host(i % slots)
+            logits, points = eng.read_slot_outputs(i % slots, B)
             assert np.array_equal(logits, sets[i][2][0]) and np.array_equal(points, sets[i][2][1]), (rep, i)
             assert np.array_equal(r["status"], pose_ref["status"].cpu().numpy())
             assert np.array_equal(r["quat"], pose_ref["quat"].cpu().numpy())
             assert np.array_equal(r["tvec"], pose_ref["tvec"].cpu().numpy())
+            if i + slots < n:
+                eng.submit_batch_dev(i % slots, sets[i + slots][0], sets[i + slots][1])
+    # the one-stream call still works afterwards (activation set 0 is selected again)
+    out = eng.forward(eng.crop_resize_norm(sets[3][0], sets[3][1]))
+    assert np.array_equal(out["pred_points"].cpu().numpy(), sets[3][2][1])
+    with pytest.raises(Exception):
+        eng.submit_batch_dev(4, sets[0][0], sets[0][1])   # no such slot
     eng.set_pnp_override(None, None, None)
     eng.close()
 
