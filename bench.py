@@ -76,27 +76,40 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip().split(", "))
+            self.rows.append((time.perf_counter(), line.strip().split(", ")))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
+        # nvidia-smi is started before the warm-up (it needs ~0.3 s to deliver its first row); only rows that arrived
+        # inside the timed region count, unless the region was too short to catch two of them
+        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1]
+        window = "timed region"
+        if len(rows) < 2:
+            rows = [r for t, r in self.rows if self.t1 is None or t <= self.t1 + 0.02]
+            window = "warm-up + timed region (timed region shorter than two sampling periods)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -106,7 +119,7 @@ class ClockSampler:
                 pass
         load = [c for c in sm if mx and c > 0.5 * mx] or sm
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -243,18 +256,26 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    run_steps(args.warmup, 0)
-    barrier()
-    eng.profile_collect()                                 # reset launch counters
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    run_steps(args.warmup, 0)
+    if sampler and not sampler.rows:                      # keep the GPU under the same load until nvidia-smi reports
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 2.0:
+            run_steps(SLOTS, 0)
+    barrier()
+    eng.profile_collect()                                 # reset launch counters
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark_begin()
     e0.record()
     out = run_steps(args.steps, args.warmup)
     e1.record()                                           # after the last collect: every batch's poses are on the host
     barrier()
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     _, launches = eng.profile_collect()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -362,7 +383,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true",
