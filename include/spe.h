@@ -155,6 +155,10 @@ int spe_debug_gemm(int dtype, const void* A_dev, const void* W_dev, long long M,
 int spe_debug_conv(int dtype, const void* x_dev, const void* w_dev, int NB, int H, int W, int C, int Cout, int R,
                    int S, int pad, int stride, const float* scale_dev, const float* bias_dev, int relu, void* out_dev,
                    void* stream);
+/* fused encoder feed-forward block, fp32/TF32: out = LayerNorm(X + relu(X W1^T + b1) W2^T + b2); X [M,256], W1
+ * [hidden,256], W2 [256,hidden]; out_mode 0 rounded / 1 exact [M,256], 2 = [M,768] 3xTF32 operand form */
+int spe_debug_ffn(const float* X, long long M, const float* W1, const float* b1, const float* W2, const float* b2,
+                  const float* gamma, const float* beta, int hidden, int out_mode, float* out, void* stream);
 int spe_debug_attention(int dtype, const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int B,
                         int heads, int Lq, int Lk, int ldq, int ldk, int ldv, int ldo, void* stream);
 /* keep copies of intermediate activations during spe_forward (names: stem, layer1, layer2, layer3, neck,

@@ -43,6 +43,7 @@ SYMBOLS = {
     "spe_debug_gemm": (_i, [_i, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "spe_debug_conv": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "spe_debug_attention": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "spe_debug_ffn": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "spe_debug_enable_taps": (_i, [_vp, _i]),
     "spe_debug_read_tap": (_ll, [_vp, C.c_char_p, _vp, _ll]),
     "spe_submit_batch_host": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, C.POINTER(SpePnpParams)]),

@@ -427,6 +427,17 @@ int spe_debug_conv(int dtype, const void* x, const void* w, int NB, int H, int W
   return SPE_OK;
 }
 
+int spe_debug_ffn(const float* X, long long M, const float* W1, const float* b1, const float* W2, const float* b2,
+                  const float* gamma, const float* beta, int hidden, int out_mode, float* out, void* stream) {
+  FfnDesc d;
+  d.X = X; d.M = M; d.W1 = W1; d.b1 = b1; d.W2 = W2; d.b2 = b2; d.gamma = gamma; d.beta = beta;
+  d.hidden = hidden; d.out_mode = out_mode; d.out = out;
+  if (!ffn_fused_supported(kTF32, 256, hidden)) return set_error(nullptr, SPE_ERR_INVALID, "spe_debug_ffn: unsupported shape");
+  std::string s = launch_ffn_fused(d, sm_count(), static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_ffn: " + s);
+  return SPE_OK;
+}
+
 int spe_debug_attention(int dtype, const void* q, const void* k, const void* v, void* out, int B, int heads, int Lq,
                         int Lk, int ldq, int ldk, int ldv, int ldo, void* stream) {
   AttnDesc a;

@@ -808,16 +808,31 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
     TRY_S(f.attn(ctx->QKV, 768, f.col(ctx->QKV, 256), 768, f.col(ctx->QKV, 512), 768, ctx->ATT, Ti, Ti));
     TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256));
     TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc));
-    TRY_S(f.gemm(Xc, Bl * T, L.ff1, ctx->HID, c.dim_feedforward, true));
-    TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, Xc, 256));
     // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: emit it pre-split
     const bool last = i == c.enc_layers - 1;
-    if (last && ctx->kv_split3) {
-      void* XSc = static_cast<uint8_t*>(ctx->XS) + (static_cast<uint8_t*>(Xc) - static_cast<uint8_t*>(ctx->X)) * 3;
-      TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, XSc, 2));
-      if (ctx->taps_enabled) TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, 1));
+    const bool split = last && ctx->kv_split3;
+    void* XSc = split ? static_cast<uint8_t*>(ctx->XS) + (static_cast<uint8_t*>(Xc) - static_cast<uint8_t*>(ctx->X)) * 3
+                      : nullptr;
+    // feed-forward block + norm2 in one kernel (the 2048-wide hidden activation stays in tensor memory); the tap of
+    // the last layer needs both output forms, so bring-up runs take the unfused path there
+    if (ffn_fused_supported(f.dt, 256, c.dim_feedforward) && !(split && ctx->taps_enabled)) {
+      FfnDesc d;
+      d.X = Xc; d.M = Bl * T;
+      d.W1 = L.ff1.w; d.b1 = L.ff1.bias; d.W2 = L.ff2.w; d.b2 = L.ff2.bias;
+      d.gamma = L.n2g; d.beta = L.n2b;
+      d.hidden = c.dim_feedforward;
+      d.out = split ? XSc : Xc;
+      d.out_mode = split ? 2 : (last ? 1 : 0);
+      TRY_S(launch_ffn_fused(d, ctx->num_sms, st));
     } else {
-      TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, last ? 1 : 0));
+      TRY_S(f.gemm(Xc, Bl * T, L.ff1, ctx->HID, c.dim_feedforward, true));
+      TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, Xc, 256));
+      if (split) {
+        TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, XSc, 2));
+        if (ctx->taps_enabled) TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, 1));
+      } else {
+        TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, last ? 1 : 0));
+      }
     }
     const std::string nm = "enc" + std::to_string(i);
     TRY_S(f.tap(nm.c_str(), Xc, Bl * T * 256));

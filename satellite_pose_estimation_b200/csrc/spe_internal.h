@@ -75,6 +75,23 @@ std::string launch_attention_tc(const AttnDesc& d, cudaStream_t s);
 std::string encode_tmap_2d(void* map, Dtype dt, const void* base, long long dim0, long long dim1,
                            long long stride1_bytes, int box0, int box1, bool swizzle_atom32 = false);
 
+// ---- fused encoder feed-forward block (ffn_tc.cu): out = LayerNorm(X + relu(X W1^T + b1) W2^T + b2) ----
+struct FfnDesc {
+  const void* X = nullptr;      // [M, 256] fp32 (TF32 values)
+  long long M = 0;
+  const void* W1 = nullptr;     // [hidden, 256]
+  const float* b1 = nullptr;
+  const void* W2 = nullptr;     // [256, hidden]
+  const float* b2 = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  void* out = nullptr;          // may alias X (each tile is read completely before it is written)
+  int out_mode = 0;             // 0: rounded to TF32, 1: exact fp32, 2: [M, 768] = [hi | lo | hi]
+  int hidden = 0;
+};
+bool ffn_fused_supported(Dtype dt, int d_model, int hidden);
+std::string launch_ffn_fused(const FfnDesc& d, int num_sms, cudaStream_t stream);
+
 // ---- heads (heads.cu) ----
 std::string launch_head_final(Dtype dt, const void* hs, const void* h2, const void* s2, long long rows,
                               const float* Wc, const float* bc, const float* W3, const float* b3,

@@ -138,6 +138,41 @@ def test_gemm_3xtf32_reaches_fp32_accuracy(lib, cuda_dev, M, N, K, relu, res_mod
     assert _rel(out, ref) < 2e-5      # fp32 accumulation over up to 3 x 2048 products; plain TF32 sits at ~5e-4
 
 
+@pytest.mark.parametrize("M,hidden,mode", [(128, 256, 0), (784, 2048, 0), (3 * 784, 2048, 2), (1000, 512, 1),
+                                           (50176, 2048, 0)])
+def test_fused_ffn_layernorm(lib, cuda_dev, M, hidden, mode):
+    """LayerNorm(X + relu(X W1^T + b1) W2^T + b2) in one kernel (hidden tile in tensor memory) vs fp64 on the same
+    TF32-rounded operands; ragged last tile, several tiles per CTA, in-place output, 3xTF32 operand form."""
+    torch.manual_seed(M + hidden)
+    X = _rna_tf32(torch.randn(M, 256, device=cuda_dev))
+    W1 = _rna_tf32(torch.randn(hidden, 256, device=cuda_dev) / 16)
+    W2 = _rna_tf32(torch.randn(256, hidden, device=cuda_dev) / hidden ** 0.5)
+    b1, b2 = torch.randn(hidden, device=cuda_dev) * 0.5, torch.randn(256, device=cuda_dev)
+    g, be = torch.rand(256, device=cuda_dev) + 0.5, torch.randn(256, device=cuda_dev)
+    h = _rna_tf32(torch.relu(X.double() @ W1.double().t() + b1.double()).float()).double()
+    v = X.double() + h @ W2.double().t() + b2.double()
+    ref = (v - v.mean(1, keepdim=True)) / torch.sqrt(v.var(1, unbiased=False, keepdim=True) + 1e-5) * g.double() + be.double()
+    if mode == 2:
+        out = torch.full((M, 768), float("nan"), device=cuda_dev)
+    else:
+        out = X.clone()                                   # in place, like the encoder schedule
+    src = X if mode == 2 else out
+    assert lib.spe_debug_ffn(_p(src), M, _p(W1), _p(b1), _p(W2), _p(b2), _p(g), _p(be), hidden, mode, _p(out), None) == 0
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    if mode == 2:
+        hi, lo, hi2 = out[:, :256], out[:, 256:512], out[:, 512:]
+        assert torch.equal(hi, hi2) and torch.equal(hi, _rna_tf32(hi))
+        got = hi.double() + lo.double()
+    else:
+        got = out.double()
+        if mode == 0:
+            assert torch.equal(out, _rna_tf32(out))
+    # H is rounded to TF32 (rel 2^-11) once, everything else is fp32; mode 0 also rounds the result itself
+    bound = 1e-3 + (6e-4 if mode == 0 else 0.0) * ref.abs()
+    assert ((got - ref).abs() <= bound).all(), ((got - ref).abs() - bound).max().item()
+
+
 def test_gemm_rejects_bad_shapes(lib, cuda_dev):
     a = torch.zeros(8, 48, device=cuda_dev)
     assert lib.spe_debug_gemm(0, _p(a), _p(a), 8, 8, 48, None, None, None, 0, 0, _p(a), None) != 0
