@@ -17,6 +17,8 @@
 //   warps 2-5  thread t owns row t (tcgen05.ld layout):  H_j = rna_tf32(relu(S_j + b1_j)) written back over S_j; after
 //            the last chunk: v = O + b2 + X (X from the resident smem tile), two-pass LayerNorm statistics over the
 //            thread's own row (no cross-thread reduction), normalise, round / split, store.
+// A cta_group::2 variant (each CTA keeps half of every weight k-block) was built and measured 5 % slower (258 vs
+// 246 us at M = 50176): the kernel is bound by the tensor pipe's sustained TF32 rate, not by its weight stream.
 // TMEM: S0 [0,128)  S1 [128,256)  O [256,512).  Tensor-pipe instructions retire in issue order, so S_{j+2} overwrites
 // H_j only after O += H_j W2_j^T has read it.
 #include "spe_internal.h"

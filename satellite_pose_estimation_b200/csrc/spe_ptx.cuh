@@ -301,6 +301,16 @@ __device__ __forceinline__ void umma_ss_cg2(uint32_t tmem_d, uint64_t adesc, uin
   }
 }
 
+// D[tmem] (+)= A[tmem] * B[smem] on a CTA pair: each CTA's 128 A rows come from its own tensor memory
+__device__ __forceinline__ void umma_ts_cg2_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
