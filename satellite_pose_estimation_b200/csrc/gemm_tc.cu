@@ -16,6 +16,7 @@
 // {BK channels, W, hrows, 1 image} shifted by (s - pad, r - pad); TMA zero-fills outside the image, which is
 // exactly the convolution's zero padding, so no im2col buffer is ever materialised.
 #include "spe_internal.h"
+#include <algorithm>
 #include "profile.h"
 #include "spe_ptx.cuh"
 
@@ -79,6 +80,9 @@ struct GemmKParams {
   int out_ld;
   int round_out;       // fp32 storage: round results to TF32 (consumer is a kind::tf32 MMA)
   int K;               // X3: column offset of W_lo inside the [N, 2K] weight matrix
+  int remap_wp;        // tap-reuse 3x3 kernel: accumulator row m' = h * remap_wp + w of a (W + 2)-wide padded grid
+  int sub_rows;        // ... image rows per 128-row accumulator
+  uint32_t a_stage;    // ... bytes of one halo-tile stage
   int dbg;             // SPE_GEMM_DBG bit 0: skip the output stores (profiling experiments only)
 };
 
@@ -122,7 +126,7 @@ __device__ __forceinline__ void store_chunk(float (&f)[NIT][G], uint8_t* gp, con
 
 // One 128 x BN accumulator tile of one epilogue warp: rows [q*32, q*32+32) of the tile (its TMEM lane quarter), column
 // chunks half, half + CSTEP, ...  `taddr` = TMEM address of the warp's lane quarter in the accumulator buffer.
-template <typename T, int BN, int CSTEP>
+template <typename T, int BN, int CSTEP, bool REMAP = false>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, const int lane, const int q,
                                               const int half, const uint32_t taddr, const int valid_rows,
                                               const long long m_base, const int n0, const float* s_scale,
@@ -249,6 +253,39 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       }
     }
     if (resid && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next chunk, in flight during the stores
+    if constexpr (REMAP) {
+      // accumulator row r is pixel (h, w) = (r / Wp, r % Wp) of the padded grid; columns w >= W are the halo (their
+      // values are meaningless) and valid_rows counts the image rows of this sub-tile that exist
+      if (col_ok) {
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          const int r = q * 32 + i * RPI + crow;
+          const int hl = r / p.remap_wp;
+          const int w = r - hl * p.remap_wp;
+          if (w < p.W && hl < valid_rows) {
+            if (p.relu) {
+#pragma unroll
+              for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
+            }
+            uint8_t* gp = reinterpret_cast<uint8_t*>(p.out) +
+                          ((m_base + static_cast<long long>(hl) * p.W + w) * p.out_ld + ncol) *
+                              static_cast<long long>(sizeof(T)) + cseg * 16;
+            if (sizeof(T) == 4) {
+              float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
+              if (p.round_out) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
+              *reinterpret_cast<float4*>(gp) = o4;
+            } else {
+              uint4 o8;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(f[i][(2 * u) % G], f[i][(2 * u + 1) % G]);
+              *reinterpret_cast<uint4*>(gp) = o8;
+            }
+          }
+        }
+      }
+      continue;
+    }
     if (col_ok && rows_here > 0 && !(p.dbg & 1)) {
       uint8_t* gp = out0 + static_cast<long long>(ncol) * static_cast<long long>(sizeof(T));
       switch (variant) {
@@ -695,6 +732,190 @@ std::string launch_cg2(const GemmKParams& kp, const CUtensorMap& tmA, const CUte
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 convolution with tap reuse (Cout = BN <= 128).  The generic implicit GEMM above fetches the
+// shifted input window once per filter tap: nine TMA loads of (almost) the same pixels per channel block, and with
+// N <= 128 also one pass over the whole filter bank per 112 output pixels -- the 3x3 layers of layer1 / layer2 ran at
+// 2.7-4.3x their ideal, bound by L2 -> SM traffic.  Here a CTA loads, per 32-channel block, ONE halo tile of
+// (2 * hrows + 2) x (W + 2) pixels and feeds the tensor core nine row-shifted views of it: in the flattened padded grid
+// output pixel m' = h * (W + 2) + w needs input pixel m' + r * (W + 2) + s for tap (r, s), i.e. the same 128-byte rows of
+// shared memory starting r * (W + 2) + s rows further down (the descriptor's start address may be any 128-byte row:
+// the swizzle is a function of absolute address bits).  The two halo columns per image row become two meaningless accumulator rows that are simply not stored.  Each
+// filter k-block is used for two 128-row accumulators (2 * hrows image rows), which halves the filter traffic too.
+// L2 -> SM bytes per 112 output pixels: 396 KB -> 118 KB (64 -> 64 channels at 56 x 56), 1080 KB -> 365 KB (128 -> 128
+// channels at 28 x 28).
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN> struct Conv3Cfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int A_STAGES = 2;
+  static constexpr int THREADS = 192;
+  static constexpr int TMEM_COLS = 4 * BN;        // two accumulators per tile, double-buffered
+  static constexpr int STAGING_BYTES = 4 * 4096;
+  static constexpr int FIXED_BYTES = STAGING_BYTES + 2 * 2 * BN * 4 + 64 * 8 + 16 + 1024;
+};
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(Conv3Cfg<BN>::THREADS, 1)
+conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmKParams p, const int b_stages) {
+  using Tr = GemmTraits<T>;
+  using Cfg = Conv3Cfg<BN>;
+  constexpr int BK = Tr::BK;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sA = smem;                                               // [2][a_stage] halo tiles
+  uint8_t* sB = sA + Cfg::A_STAGES * p.a_stage;                     // [b_stages][BN x 128 B]
+  uint8_t* sm_staging = sB + b_stages * Cfg::B_BYTES;
+  float* sm_scale = reinterpret_cast<float*>(sm_staging + Cfg::STAGING_BYTES);
+  float* sm_bias = sm_scale + 2 * BN;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sm_bias + 2 * BN);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* tfull_bar = a_empty + 2;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* b_full = tempty_bar + 2;                                // [b_stages]
+  uint64_t* b_empty = b_full + 24;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_empty + 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Wp = p.remap_wp;
+  const int hrows = p.sub_rows;                // image rows per 128-row accumulator
+  const int CB = p.kb_per_tap;                 // 32-channel blocks
+  const int num_tiles = p.num_m_tiles;         // tiles of 2 * hrows image rows
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    for (int i = 0; i < b_stages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int img = tile / p.tiles_per_img;
+        const int h0 = (tile - img * p.tiles_per_img) * (2 * hrows);
+        for (int cb = 0; cb < CB; ++cb) {
+          mbar_wait(&a_empty[as], aph ^ 1u, 41);
+          mbar_expect_tx(&a_full[as], p.a_bytes);
+          // halo tile: image rows h0-1 .. h0+2*hrows, columns -1 .. W (out-of-bounds = zero = the padding)
+          tma_load_4d(sA + as * p.a_stage, &tmA, &a_full[as], cb * BK, -1, h0 - 1, img);
+          if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1u, 42);
+            mbar_expect_tx(&b_full[bs], Cfg::B_BYTES);
+            tma_load_2d(sB + bs * Cfg::B_BYTES, &tmB, &b_full[bs], (tap * CB + cb) * BK, 0);
+            if (++bs == b_stages) { bs = 0; bph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(Tr::kFmt, BM, BN);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[buf], use_par ^ 1u, 43);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 2 * BN);
+        for (int cb = 0; cb < CB; ++cb) {
+          mbar_wait(&a_full[as], aph, 44);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + as * p.a_stage);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph, 45);
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + bs * Cfg::B_BYTES));
+            const int r = tap / 3, sx = tap - 3 * r;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint64_t adesc = umma_desc_sw128(a0 + static_cast<uint32_t>(((u * hrows + r) * Wp + sx) * 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_ss<Tr::kTf32>(tmem_d + static_cast<uint32_t>(u * BN), adesc + 2u * k, bdesc + 2u * k, idesc,
+                                   (cb | tap | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(&b_empty[bs]);
+            if (++bs == b_stages) { bs = 0; bph ^= 1u; }
+          }
+          tc_commit(&a_empty[as]);
+          if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
+        }
+        tc_commit(&tfull_bar[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
+      const int img = tile / p.tiles_per_img;
+      const int h0 = (tile - img * p.tiles_per_img) * (2 * hrows);
+      float* s_scale = sm_scale + buf * BN;
+      float* s_bias = sm_bias + buf * BN;
+      for (int j = et; j < BN; j += 128) {
+        s_scale[j] = p.scale != nullptr ? p.scale[j] : 1.0f;
+        s_bias[j] = p.bias != nullptr ? p.bias[j] : 0.0f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&tfull_bar[buf], use_par, 46);
+      tc_fence_after();
+#pragma unroll 1
+      for (int u = 0; u < 2; ++u) {
+        const int hu = h0 + u * hrows;                                   // first image row of this accumulator
+        int hv = p.H - hu;
+        hv = hv < 0 ? 0 : (hv > hrows ? hrows : hv);
+        const long long m_base = static_cast<long long>(img) * p.HW + static_cast<long long>(hu) * p.W;
+        epilogue_tile<T, BN, 1, true>(p, sm_staging + (warp - 2) * 4096, lane, q, 0,
+                                      tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                          static_cast<uint32_t>(buf * 2 * BN + u * BN),
+                                      hv, m_base, 0, s_scale, s_bias);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -778,6 +999,84 @@ std::string encode_tmap_2d(void* map, Dtype dt, const void* base, long long dim0
   return encode_map(reinterpret_cast<CUtensorMap*>(map), dt, 2, base, dims, str, box, 1, swizzle_atom32);
 }
 
+// tap-reuse 3x3 / stride 1 / pad 1 convolution (conv3_tc_kernel); returns "skip" when the shape does not qualify
+static std::string launch_conv3(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t stream) {
+  static const int env_on = getenv("SPE_CONV3_REUSE") ? atoi(getenv("SPE_CONV3_REUSE")) : 1;
+  const int es = static_cast<int>(dtype_size(dt));
+  const int BK = 128 / es;
+  const int cs = d.conv_stride > 0 ? d.conv_stride : 1;
+  if (!env_on || d.mode != 1 || d.R != 3 || d.S != 3 || d.pad != 1 || cs != 1 || d.x3 || d.residual != nullptr)
+    return "skip";
+  if ((d.N != 64 && d.N != 128) || d.C % BK != 0 || d.W + 2 > 128 || d.H < 1) return "skip";
+  const int Wp = d.W + 2;
+  const int hrows = BM / Wp;
+  const int dbl = 2 * hrows;
+  if (dbl + 2 > 256) return "skip";
+  const int need_rows = std::max(Wp * (dbl + 2), (hrows + 2) * Wp + 2 + BM);
+  const uint32_t a_stage = (static_cast<uint32_t>(need_rows) * 128u + 1023u) & ~1023u;
+  const int b_bytes = d.N * 128;
+  const int fixed = d.N == 64 ? Conv3Cfg<64>::FIXED_BYTES : Conv3Cfg<128>::FIXED_BYTES;
+  int b_stages = (232448 - fixed - 2 * static_cast<int>(a_stage)) / b_bytes;
+  if (b_stages > 12) b_stages = 12;
+  if (b_stages < 3) return "skip";
+  const int smem_bytes = fixed + 2 * static_cast<int>(a_stage) + b_stages * b_bytes;
+
+  GemmKParams kp{};
+  kp.mode = 1;
+  kp.M = d.NB * d.H * d.W;
+  kp.N = d.N;
+  kp.tiles_per_img = (d.H + dbl - 1) / dbl;
+  kp.num_m_tiles = kp.tiles_per_img * d.NB;
+  kp.num_n_tiles = 1;
+  kp.HW = d.H * d.W;
+  kp.H = d.H;
+  kp.W = d.W;
+  kp.kb_per_tap = d.C / BK;
+  kp.a_bytes = static_cast<uint32_t>(Wp * (dbl + 2) * 128);
+  kp.remap_wp = Wp;
+  kp.sub_rows = hrows;
+  kp.a_stage = a_stage;
+  kp.scale = d.scale; kp.bias = d.bias; kp.residual = nullptr; kp.relu = d.relu;
+  kp.out = d.out; kp.out_ld = d.out_ld; kp.round_out = d.round_out;
+  static const int dbg_flags = getenv("SPE_GEMM_DBG") ? atoi(getenv("SPE_GEMM_DBG")) : 0;
+  kp.dbg = dbg_flags;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.C), static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H),
+                          static_cast<cuuint64_t>(d.NB)};
+    cuuint64_t str[3] = {static_cast<cuuint64_t>(d.C) * es, static_cast<cuuint64_t>(d.W) * d.C * es,
+                         static_cast<cuuint64_t>(d.H) * d.W * d.C * es};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(Wp), static_cast<cuuint32_t>(dbl + 2), 1};
+    std::string err = encode_map(&tmA, dt, 4, d.A, dims, str, box);
+    if (!err.empty()) return "conv3: " + err;
+  }
+  {
+    const int K = 9 * d.C;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.N)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(K) * es};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(d.N)};
+    std::string err = encode_map(&tmB, dt, 2, d.Wt, dims, str, box);
+    if (!err.empty()) return "conv3: " + err;
+  }
+  const int grid = kp.num_m_tiles < num_sms ? kp.num_m_tiles : num_sms;
+#define SPE_CONV3(TT, BNV)                                                                                        \
+  do {                                                                                                            \
+    auto kfn = conv3_tc_kernel<TT, BNV>;                                                                          \
+    SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));                 \
+    ProfScope ps(kFamGemm, stream);                                                                               \
+    kfn<<<grid, Conv3Cfg<BNV>::THREADS, smem_bytes, stream>>>(tmA, tmB, kp, b_stages);                            \
+  } while (0)
+  if (dt == kTF32) {
+    if (d.N == 64) SPE_CONV3(float, 64); else SPE_CONV3(float, 128);
+  } else {
+    if (d.N == 64) SPE_CONV3(__nv_bfloat16, 64); else SPE_CONV3(__nv_bfloat16, 128);
+  }
+#undef SPE_CONV3
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
 std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t stream) {
   const int es = static_cast<int>(dtype_size(dt));
   const int BK = 128 / es;
@@ -786,6 +1085,10 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
   if (d.x3 && d.mode != 0) return "gemm: 3xTF32 is only built for plain matrices";
   if (d.mode < 0 || d.mode > 2) return "gemm: bad mode";
+  if (d.mode == 1) {
+    const std::string c3 = launch_conv3(dt, d, num_sms, stream);
+    if (c3 != "skip") return c3;
+  }
   const int cs_est = d.conv_stride > 1 ? d.conv_stride : 1;
   const long long m_tiles_est = d.mode == 0 ? (d.M + BM - 1) / BM
                                             : static_cast<long long>(d.NB) * (((d.H / cs_est) * (d.W / cs_est) + BM - 1) / BM);

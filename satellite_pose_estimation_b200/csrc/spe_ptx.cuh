@@ -130,6 +130,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Note: the start address may be ANY 128-byte row of a larger 1024-byte-aligned swizzled buffer (a row-shifted window
+// of a halo tile, see conv3_tc_kernel).  The tensor core applies the 128B swizzle to absolute shared-memory address bits
+// [7,10) -- exactly like TMA wrote them -- so the descriptor's "matrix base offset" field stays 0; setting it to the
+// start row's phase ((addr >> 7) & 7) double-counts and reads the wrong 16-byte chunks (measured on B200).
+
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, A and B K-major.
 // fmt: 0 = f16, 1 = bf16, 2 = tf32.
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int m, int n) {
