@@ -333,8 +333,14 @@ def run_b200(args):
             peak, peak_src = pk["bf16_tflops_sustained"] / 2, "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense = half of bf16)"
         else:
             peak, peak_src = 1400.0 / 2, "fallback 1.4 PFLOP/s sustained bf16 / 2"
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32, all convolutions and linear layers)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tpath):          # DRAM bytes per GEMM launch from the committed ncu capture (not measured live)
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["bytes_per_launch"], tj["source"]
+        roofline = {"bound": "tensor", "kernel": "gemm_tc / gemm_tc2 / conv3_tc / ffn_tc kernels (tcgen05 kind::tf32: all convolutions and linear layers)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+                    "traffic_source": traffic_src,
                     "peak_source": peak_src, "launches_per_step": fam_n["gemm"] // prof_steps,
                     "kernel_ms_per_step": gemm_ms,
                     "family_ms_per_step": {k: v / prof_steps for k, v in fam_ms.items()},

@@ -20,7 +20,7 @@ def schedule():
     g = []  # (name, M, N, K, extra_read_elems)
 
     def add(name, M, N, K, res=0, x3=False):
-        g.append((name, M, N, K, res, x3))
+        g.append((name, M, N, K, res, x3, 1))
     add("stem 7x7/s2", B * 112 * 112, 64, 147)
     inpl, H = 64, 56
     for li, (pl, nb) in enumerate(((64, 3), (128, 4), (256, 6))):
@@ -41,8 +41,8 @@ def schedule():
     for i in range(4):
         add(f"enc{i}.qkv", B * T, 768, 256)
         add(f"enc{i}.out+res", B * T, 256, 256, res=B * T * 256)
-        add(f"enc{i}.ff1", B * T, 2048, 256)
-        add(f"enc{i}.ff2+res", B * T, 256, 2048, res=B * T * 256)
+        # linear1 + ReLU + linear2 + residual + norm2 in one kernel: 2 x (M x 2048 x 256) MACs, X in, Y out
+        g.append((f"enc{i}.ffn fused (+LN)", B * T, 2048, 256, 0, False, 2))
     add("dec.kv_all (3xTF32)", B * T, 2048, 256, x3=True)
     Q = 40
     for i in range(4):
@@ -63,17 +63,22 @@ def main(path):
     ends = [i for i, s in enumerate(seq) if "assign_pnp" in s[1] or "PnpDesc" in s[1]]
     a = starts[-1] if ends and ends[-1] > starts[-1] else starts[-2]
     b = min(e for e in ends if e > a)
-    gem = [s for s in seq[a:b + 1] if short(s[1]) in ("gemm_tc_kernel", "gemm_tc2_kernel")]
+    FAM = ("gemm_tc_kernel", "gemm_tc2_kernel", "conv3_tc_kernel", "ffn_tc_kernel")
+    gem = [s for s in seq[a:b + 1] if short(s[1]) in FAM]
     sch = schedule()
     assert len(gem) == len(sch), (len(gem), len(sch))
     print("| GEMM | M | N | K | us | ideal us | TFLOP/s | x ideal |\n|---|---:|---:|---:|---:|---:|---:|---:|")
     tot = tot_ideal = 0
-    for (name, M, N, K, res, x3), s in zip(sch, gem):
-        fl = 2 * M * N * K
+    tag = {"gemm_tc2_kernel": " (pair)", "conv3_tc_kernel": " (tap reuse)", "ffn_tc_kernel": ""}
+    for (name, M, N, K, res, x3, nmm), s in zip(sch, gem):
+        fl = 2 * M * N * K * nmm
         by = (M * K + M * N + res) * ES if "3x3" not in name else (M * K // 9 + M * N) * ES
+        if nmm == 2:
+            by = 2 * M * K * ES
+        name = name + tag.get(short(s[1]), "")
         ideal = max(fl * (3 if x3 else 1) / TF32, by / HBM) * 1e6
         tot += s[2]; tot_ideal += ideal
-        print(f"| {name}{" (pair)" if "tc2" in s[1] else ""} | {M} | {N} | {K} | {s[2]:.1f} | {ideal:.1f} | {fl / s[2] / 1e6:.0f} | {s[2] / ideal:.1f} |")
+        print(f"| {name} | {M} | {N} | {K} | {s[2]:.1f} | {ideal:.1f} | {fl / s[2] / 1e6:.0f} | {s[2] / ideal:.1f} |")
     print(f"\nGEMM total {tot:.0f} us, sum of per-GEMM ideals {tot_ideal:.0f} us")
 
 

@@ -6,21 +6,33 @@ import re
 import sys
 
 
-def load(path):
+def load(path, extra=None):
+    """-> [(id, kernel name, us, grid)] in launch order; `extra` (dict) receives {id: {metric: value}} for any other
+    metrics the capture holds (e.g. dram__bytes_read.sum, in bytes)."""
     lines = [l for l in open(path) if not l.startswith("==")]
-    seq = []
+    seq, seen = [], {}
     for row in csv.DictReader(lines):
         v = float(row["Metric Value"].replace(",", ""))
         u = row["Metric Unit"]
-        v = v / 1000 if u in ("ns", "nsecond") else (v * 1000 if u in ("ms", "msecond") else v)
-        seq.append((int(row["ID"]), row["Kernel Name"], v, row.get("Grid Size", "")))
+        kid = int(row["ID"])
+        name = row.get("Metric Name", "gpu__time_duration.sum")
+        if name.startswith("gpu__time_duration"):
+            v = v / 1000 if u in ("ns", "nsecond") else (v * 1000 if u in ("ms", "msecond") else v)
+            seen[kid] = len(seq)
+            seq.append((kid, row["Kernel Name"], v, row.get("Grid Size", "")))
+        elif extra is not None:
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            extra.setdefault(kid, {})[name] = v * scale
     return seq
 
 
 def short(name):
     n = re.sub(r"\(.*", "", name)
     n = re.sub(r"^.*::", "", n)
-    return "gemm_tc_kernel" if n.strip().startswith("GemmKParams") or "gemm_tc" in name else n.strip()
+    for fam in ("gemm_tc2_kernel", "gemm_tc_kernel", "conv3_tc_kernel", "ffn_tc_kernel"):
+        if fam in name:
+            return fam
+    return "gemm_tc_kernel" if n.strip().startswith("GemmKParams") else n.strip()
 
 
 def main(path):

@@ -815,7 +815,9 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
                       : nullptr;
     // feed-forward block + norm2 in one kernel (the 2048-wide hidden activation stays in tensor memory); the tap of
     // the last layer needs both output forms, so bring-up runs take the unfused path there
-    if (ffn_fused_supported(f.dt, 256, c.dim_feedforward) && !(split && ctx->taps_enabled)) {
+    // (small batches keep the two-GEMM path: one 128-row tile per CTA cannot fill the machine below ~74 tiles)
+    if (ffn_fused_supported(f.dt, 256, c.dim_feedforward) && !(split && ctx->taps_enabled) &&
+        (Bl * T + 127) / 128 >= ctx->num_sms / 2) {
       FfnDesc d;
       d.X = Xc; d.M = Bl * T;
       d.W1 = L.ff1.w; d.b1 = L.ff1.bias; d.W2 = L.ff2.w; d.b2 = L.ff2.bias;
