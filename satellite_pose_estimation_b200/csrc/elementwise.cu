@@ -185,19 +185,15 @@ maxpool3x3s2_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int W
 // ---------------------------------------------------------------------------------------------------------------
 // bilinear x2 upsample, align_corners=True (torch upsample_bilinear2d arithmetic: fp32 scale = (in-1)/(out-1))
 // ---------------------------------------------------------------------------------------------------------------
+// One CTA per output pixel (all index math and the four bilinear weights are block-uniform); threads walk the channel
+// vectors, so every load and store is a contiguous 16 bytes per lane.
 template <typename T>
 __global__ void __launch_bounds__(256)
-upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, long long total_vec, T* __restrict__ out) {
+upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, T* __restrict__ out) {
   constexpr int VN = Vec<T>::N;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total_vec) return;
   const int Ho = 2 * H, Wo = 2 * W;
-  const int cv = C / VN;
-  const int c0 = static_cast<int>(idx % cv) * VN;
-  const long long pix = idx / cv;
-  const int ox = static_cast<int>(pix % Wo);
-  const int oy = static_cast<int>((pix / Wo) % Ho);
-  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const int ox = blockIdx.x, oy = blockIdx.y;
+  const long long n = blockIdx.z;
   const float sh = Ho > 1 ? static_cast<float>(H - 1) / static_cast<float>(Ho - 1) : 0.f;
   const float sw = Wo > 1 ? static_cast<float>(W - 1) / static_cast<float>(Wo - 1) : 0.f;
   const float fy = sh * oy, fx = sw * ox;
@@ -205,16 +201,20 @@ upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, long long total
   const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
   const float ly1 = fy - y0, lx1 = fx - x0;
   const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-  const T* base = in + n * H * W * C + c0;
-  const Vec<T> a = vload(base + (static_cast<long long>(y0) * W + x0) * C);
-  const Vec<T> b = vload(base + (static_cast<long long>(y0) * W + x1) * C);
-  const Vec<T> c = vload(base + (static_cast<long long>(y1) * W + x0) * C);
-  const Vec<T> d = vload(base + (static_cast<long long>(y1) * W + x1) * C);
-  Vec<T> r;
+  const T* base = in + n * H * W * C;
+  const T* pa = base + (static_cast<long long>(y0) * W + x0) * C;
+  const T* pb = base + (static_cast<long long>(y0) * W + x1) * C;
+  const T* pc = base + (static_cast<long long>(y1) * W + x0) * C;
+  const T* pd = base + (static_cast<long long>(y1) * W + x1) * C;
+  T* po = out + ((n * Ho + oy) * Wo + ox) * C;
+  for (int c0 = threadIdx.x * VN; c0 < C; c0 += blockDim.x * VN) {
+    const Vec<T> a = vload(pa + c0), b = vload(pb + c0), c = vload(pc + c0), d = vload(pd + c0);
+    Vec<T> r;
 #pragma unroll
-  for (int e = 0; e < VN; ++e)
-    r.set(e, ly0 * (lx0 * a.get(e) + lx1 * b.get(e)) + ly1 * (lx0 * c.get(e) + lx1 * d.get(e)));
-  vstore(out + pix * C + c0, r);
+    for (int e = 0; e < VN; ++e)
+      r.set(e, ly0 * (lx0 * a.get(e) + lx1 * b.get(e)) + ly1 * (lx0 * c.get(e) + lx1 * d.get(e)));
+    vstore(po + c0, r);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -338,9 +338,10 @@ std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, 
 std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s) {
   ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
-    const long long total = static_cast<long long>(NB) * 4 * H * W * (C / Vec<T>::N);
-    upsample2x_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C, total,
-                                                                reinterpret_cast<T*>(out));
+    const int nvec = C / Vec<T>::N;
+    const int threads = nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32;
+    upsample2x_kernel<T><<<dim3(2 * W, 2 * H, NB), threads, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C,
+                                                                   reinterpret_cast<T*>(out));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

@@ -106,6 +106,25 @@ def test_batch_invariance_and_chunking(lib, cuda_dev):
     assert torch.allclose(lst["pred_points"], full["pred_points"][:2], atol=1e-6)
 
 
+def test_large_batch_kernels_agree_with_small_batch_path(lib, cuda_dev):
+    """At B = 16 the schedule switches to the machine-filling kernels (fused feed-forward block + norm2, wide / paired
+    GEMM tiles); an image's keypoints must stay within a fraction of the 0.5 px budget of its batch-1 result
+    (which the golden tests pin against the reference).  1748 px = the largest crop side of the box distribution."""
+    cfg = model_ref.ModelCfg()
+    eng = _engine(cfg, 224, 16, "tf32")
+    eng.load_state_dict(synth.make_state_dict(cfg, seed=0))
+    x = model_inputs(16, 224, 11).cuda()
+    big = eng.forward(x)
+    pts_big = big["pred_points"].cpu().numpy().copy()
+    log_big = big["pred_logits"].cpu().numpy().copy()
+    for i in (0, 7, 15):
+        one = eng.forward(x[i:i + 1])
+        d_px = np.abs(one["pred_points"].cpu().numpy()[0] - pts_big[i]).max() * 1748
+        assert d_px < 0.1, (i, d_px)
+        assert np.abs(one["pred_logits"].cpu().numpy()[0] - log_big[i]).max() < 5e-3
+    eng.close()
+
+
 def test_drop_in_loop_like_gen_submission(lib, cuda_dev):
     """The reference's hot loop (RV/gen_submission_single.py:136-181) with the drop-in objects, on seeded inputs;
     outputs are compared with the oracle chain (restated forward + PostProcess + cv2 solver)."""
