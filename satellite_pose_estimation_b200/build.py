@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("SPE_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs, log = [], []
     for s, obj, p in procs:

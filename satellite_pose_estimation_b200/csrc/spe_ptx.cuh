@@ -68,6 +68,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// One lane of a fully converged warp.  Issue TMA / tcgen05 instructions as  `if (elect_one_sync()) { ... }`  inside
+// WARP-UNIFORM control flow (every lane runs the loops and the mbarrier waits): the operands then live in uniform
+// registers and the SASS is a straight run of UTCHMMA / UTMALDG.  Under `if (lane == 0)` the compiler cannot prove the
+// operands uniform and wraps EVERY such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop -- ~13
+// dependent instructions, ~90 cycles per MMA measured on B200, more than a 128 x 128 x 8 TF32 MMA takes to execute.
+// The same lane is elected every time, which tcgen05.commit needs (it tracks the MMAs of the executing thread).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> shared, completion on an mbarrier)
 // ----------------------------------------------------------------------------------------------
