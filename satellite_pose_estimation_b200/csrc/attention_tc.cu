@@ -107,22 +107,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // Producer and MMA warps run warp-uniform loops; one elected lane issues (spe_ptx.cuh: elect_one_sync) -- under
+  // `if (lane == 0)` every one of the 18 MMAs of a chunk was wrapped in a ~90-cycle waterfall loop, 3.6 x their 450
+  // tensor-pipe cycles.
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, SM::Q_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, h * 32, b * p.Lq + q0);
+    {
+      if (elect_one_sync()) {
+        mbar_expect_tx(q_full, SM::Q_BYTES);
+        tma_load_2d(sQ, &tmQ, q_full, h * 32, b * p.Lq + q0);
+      }
+      __syncwarp();
       for (int j = 0; j < nchunks; ++j) {
         const int st = j % 3;
         const uint32_t u = static_cast<uint32_t>(j / 3);
         mbar_wait(&kv_empty[st], (u & 1u) ^ 1u, 11);
-        mbar_expect_tx(&kv_full[st], SM::STAGE_BYTES);
-        uint8_t* sk = sKV + st * SM::STAGE_BYTES;
-        tma_load_2d(sk, &tmK, &kv_full[st], h * 32, b * p.Lk + j * NK);
-        tma_load_2d(sk + SM::KV_BYTES, &tmV, &kv_full[st], h * 32, b * p.Lk + j * NK);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&kv_full[st], SM::STAGE_BYTES);
+          uint8_t* sk = sKV + st * SM::STAGE_BYTES;
+          tma_load_2d(sk, &tmK, &kv_full[st], h * 32, b * p.Lk + j * NK);
+          tma_load_2d(sk + SM::KV_BYTES, &tmV, &kv_full[st], h * 32, b * p.Lk + j * NK);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = umma_idesc(2, kQRows, NK);
       constexpr uint32_t idesc_pv = umma_idesc(2, kQRows, 32) | (1u << 16);   // B (= V tile) is MN-major
       mbar_wait(q_full, 0, 12);
@@ -134,11 +143,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int st = i % 3;
         mbar_wait(&kv_full[st], static_cast<uint32_t>(i / 3) & 1u, 13);
         tc_fence_after();
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * SM::STAGE_BYTES));
-        const uint32_t sbuf = tmem_base + static_cast<uint32_t>((i & 1) * NK);
+        if (elect_one_sync()) {
+          const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * SM::STAGE_BYTES));
+          const uint32_t sbuf = tmem_base + static_cast<uint32_t>((i & 1) * NK);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss<true>(sbuf, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[i & 1]);
+          for (int k = 0; k < 4; ++k) umma_ss<true>(sbuf, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          tc_commit(&s_full[i & 1]);
+        }
+        __syncwarp();
       };
       issue_s(0);
       for (int j = 0; j < nchunks; ++j) {
@@ -146,14 +158,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(p_full, static_cast<uint32_t>(j) & 1u, 14);   // softmax wrote P_j (and rescaled O)
         tc_fence_after();
         const int st = j % 3;
-        const uint64_t vdesc = umma_desc_mn_tf32(smem_u32(sKV + st * SM::STAGE_BYTES) + SM::KV_BYTES);
-        const uint32_t pbuf = tmem_base + static_cast<uint32_t>((j & 1) * NK);
+        if (elect_one_sync()) {
+          const uint64_t vdesc = umma_desc_mn_tf32(smem_u32(sKV + st * SM::STAGE_BYTES) + SM::KV_BYTES);
+          const uint32_t pbuf = tmem_base + static_cast<uint32_t>((j & 1) * NK);
 #pragma unroll
-        for (int kk = 0; kk < NK / 8; ++kk)                     // 8 keys per MMA = two 4-row K atoms (1024 B) of V
-          umma_ts_tf32(tmem_base + kOCol, pbuf + static_cast<uint32_t>(kk * 8), vdesc + 64u * kk, idesc_pv,
-                       (j | kk) != 0 ? 1u : 0u);
-        tc_commit(&kv_empty[st]);
-        tc_commit(pv_done);
+          for (int kk = 0; kk < NK / 8; ++kk)                     // 8 keys per MMA = two 4-row K atoms (1024 B) of V
+            umma_ts_tf32(tmem_base + kOCol, pbuf + static_cast<uint32_t>(kk * 8), vdesc + 64u * kk, idesc_pv,
+                         (j | kk) != 0 ? 1u : 0u);
+          tc_commit(&kv_empty[st]);
+          tc_commit(pv_done);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();

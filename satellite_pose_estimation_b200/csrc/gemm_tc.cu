@@ -358,7 +358,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (warp-uniform loops, one elected lane issues: see elect_one_sync in spe_ptx.cuh)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -376,31 +377,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-          mbar_expect_tx(&full_bar[stage], p.a_bytes + (X3 ? 2 : 1) * Cfg::B_BYTES);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + (X3 ? 2 : 1) * Cfg::A_BYTES;
-          if (p.mode == 0) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
-          } else if (p.mode == 2) {
-            // k-block kb = filter row kb: 8 consecutive padded pixels x Cp channels per output pixel, windows of
-            // neighbouring output pixels overlap (dim-1 stride = 2 pixels)
-            tma_load_4d(sa, &tmA, &full_bar[stage], 0, x0, 2 * h0 + kb, img);
-          } else {
-            const int tap = kb / p.kb_per_tap;
-            const int c0 = (kb - tap * p.kb_per_tap) * BK;
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full_bar[stage], p.a_bytes + (X3 ? 2 : 1) * Cfg::B_BYTES);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + (X3 ? 2 : 1) * Cfg::A_BYTES;
+            if (p.mode == 0) {
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
+            } else if (p.mode == 2) {
+              // k-block kb = filter row kb: 8 consecutive padded pixels x Cp channels per output pixel, windows of
+              // neighbouring output pixels overlap (dim-1 stride = 2 pixels)
+              tma_load_4d(sa, &tmA, &full_bar[stage], 0, x0, 2 * h0 + kb, img);
+            } else {
+              const int tap = kb / p.kb_per_tap;
+              const int c0 = (kb - tap * p.kb_per_tap) * BK;
+              const int r = tap / p.S;
+              const int s = tap - r * p.S;
+              tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
+            }
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+            if constexpr (X3) tma_load_2d(sb + Cfg::B_BYTES, &tmB, &full_bar[stage], p.K + kb * BK, n0);
           }
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
-          if constexpr (X3) tma_load_2d(sb + Cfg::B_BYTES, &tmB, &full_bar[stage], p.K + kb * BK, n0);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
+    {
       constexpr uint32_t idesc = umma_idesc(Tr::kFmt, BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -414,24 +418,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase, 3);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + (X3 ? 2 : 1) * Cfg::A_BYTES);
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t adesc = umma_desc_sw128(sa);
+            const uint64_t bdesc = umma_desc_sw128(sa + (X3 ? 2 : 1) * Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_ss<Tr::kTf32>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              umma_ss<Tr::kTf32>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (X3) {
+              const uint64_t alo = umma_desc_sw128(sa + Cfg::A_BYTES);
+              const uint64_t blo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_d, alo + 2u * k, bdesc + 2u * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_d, adesc + 2u * k, blo + 2u * k, idesc, 1u);
+            }
+            tc_commit(&empty_bar[stage]);                        // smem slot reusable once these MMAs retire
+            if (kb == p.num_kb - 1) tc_commit(&tfull_bar[buf]);  // accumulator complete
           }
-          if constexpr (X3) {
-            const uint64_t alo = umma_desc_sw128(sa + Cfg::A_BYTES);
-            const uint64_t blo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_d, alo + 2u * k, bdesc + 2u * k, idesc, 1u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss<true>(tmem_d, adesc + 2u * k, blo + 2u * k, idesc, 1u);
-          }
-          tc_commit(&empty_bar[stage]);                        // smem slot reusable once these MMAs retire
-          if (kb == p.num_kb - 1) tc_commit(&tfull_bar[buf]);  // accumulator complete
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -593,8 +600,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; warp-uniform)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
@@ -608,28 +615,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 21);
-          // both CTAs' bytes are accounted on the leader's barrier
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (p.a_bytes + Cfg::B_BYTES));
-          const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          if (p.mode == 0) {
-            tma_load_2d_cg2(sa, &tmA, lead_bar, kb * BK, m_tile * BM);
-          } else {
-            const int tap = kb / p.kb_per_tap;
-            const int c0 = (kb - tap * p.kb_per_tap) * BK;
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            tma_load_4d_cg2(sa, &tmA, lead_bar, c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
+          if (elect_one_sync()) {
+            // both CTAs' bytes are accounted on the leader's barrier
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (p.a_bytes + Cfg::B_BYTES));
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            if (p.mode == 0) {
+              tma_load_2d_cg2(sa, &tmA, lead_bar, kb * BK, m_tile * BM);
+            } else {
+              const int tap = kb / p.kb_per_tap;
+              const int c0 = (kb - tap * p.kb_per_tap) * BK;
+              const int r = tap / p.S;
+              const int s = tap - r * p.S;
+              tma_load_4d_cg2(sa, &tmA, lead_bar, c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
+            }
+            tma_load_2d_cg2(sb, &tmB, lead_bar, kb * BK, n0 + static_cast<int>(rank) * (BN / 2));
           }
-          tma_load_2d_cg2(sb, &tmB, lead_bar, kb * BK, n0 + static_cast<int>(rank) * (BN / 2));
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer: one lane of the leader CTA
-    if (lane == 0 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer: leader CTA, one elected lane
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc(Tr::kFmt, 2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -643,14 +653,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 23);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t adesc = umma_desc_sw128(sa);
+            const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss_cg2<Tr::kTf32>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit_cg2(&empty_bar[stage], 3);                        // frees the slot in both CTAs
-          if (kb == p.num_kb - 1) tc_commit_cg2(&tfull_bar[buf], 3);  // accumulator complete in both CTAs
+            for (int k = 0; k < 4; ++k)
+              umma_ss_cg2<Tr::kTf32>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_cg2(&empty_bar[stage], 3);                        // frees the slot in both CTAs
+            if (kb == p.num_kb - 1) tc_commit_cg2(&tfull_bar[buf], 3);  // accumulator complete in both CTAs
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -809,8 +822,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
+    {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -818,22 +831,28 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int h0 = (tile - img * p.tiles_per_img) * (2 * hrows);
         for (int cb = 0; cb < CB; ++cb) {
           mbar_wait(&a_empty[as], aph ^ 1u, 41);
-          mbar_expect_tx(&a_full[as], p.a_bytes);
-          // halo tile: image rows h0-1 .. h0+2*hrows, columns -1 .. W (out-of-bounds = zero = the padding)
-          tma_load_4d(sA + as * p.a_stage, &tmA, &a_full[as], cb * BK, -1, h0 - 1, img);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&a_full[as], p.a_bytes);
+            // halo tile: image rows h0-1 .. h0+2*hrows, columns -1 .. W (out-of-bounds = zero = the padding)
+            tma_load_4d(sA + as * p.a_stage, &tmA, &a_full[as], cb * BK, -1, h0 - 1, img);
+          }
+          __syncwarp();
           if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bs], bph ^ 1u, 42);
-            mbar_expect_tx(&b_full[bs], Cfg::B_BYTES);
-            tma_load_2d(sB + bs * Cfg::B_BYTES, &tmB, &b_full[bs], (tap * CB + cb) * BK, 0);
+            if (elect_one_sync()) {
+              mbar_expect_tx(&b_full[bs], Cfg::B_BYTES);
+              tma_load_2d(sB + bs * Cfg::B_BYTES, &tmB, &b_full[bs], (tap * CB + cb) * BK, 0);
+            }
+            __syncwarp();
             if (++bs == b_stages) { bs = 0; bph ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
+    {
       constexpr uint32_t idesc = umma_idesc(Tr::kFmt, BM, BN);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -851,23 +870,28 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_full[bs], bph, 45);
             tc_fence_after();
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + bs * Cfg::B_BYTES));
-            const int r = tap / 3, sx = tap - 3 * r;
+            if (elect_one_sync()) {
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + bs * Cfg::B_BYTES));
+              const int r = tap / 3, sx = tap - 3 * r;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint64_t adesc = umma_desc_sw128(a0 + static_cast<uint32_t>(((u * hrows + r) * Wp + sx) * 128));
+              for (int u = 0; u < 2; ++u) {
+                const uint64_t adesc = umma_desc_sw128(a0 + static_cast<uint32_t>(((u * hrows + r) * Wp + sx) * 128));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_ss<Tr::kTf32>(tmem_d + static_cast<uint32_t>(u * BN), adesc + 2u * k, bdesc + 2u * k, idesc,
-                                   (cb | tap | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  umma_ss<Tr::kTf32>(tmem_d + static_cast<uint32_t>(u * BN), adesc + 2u * k, bdesc + 2u * k, idesc,
+                                     (cb | tap | k) != 0 ? 1u : 0u);
+              }
+              tc_commit(&b_empty[bs]);
+              if (tap == 8) {
+                tc_commit(&a_empty[as]);
+                if (cb == CB - 1) tc_commit(&tfull_bar[buf]);
+              }
             }
-            tc_commit(&b_empty[bs]);
+            __syncwarp();
             if (++bs == b_stages) { bs = 0; bph ^= 1u; }
           }
-          tc_commit(&a_empty[as]);
           if (++as == Cfg::A_STAGES) { as = 0; aph ^= 1u; }
         }
-        tc_commit(&tfull_bar[buf]);
       }
     }
     __syncwarp();
