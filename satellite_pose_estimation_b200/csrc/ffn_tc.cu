@@ -310,12 +310,14 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 16; ++k) bb[k] = __ldg(reinterpret_cast<const float4*>(b1 + 4 * k));   // warp-uniform
         mbar_wait_t(&s_full[j & 1], (g >> 1) & 1u, 39, w_s);
+        const long long a0 = FFN_CLOCK();
         tc_fence_after();
         const uint32_t tb = trow + static_cast<uint32_t>((j & 1) * kChunk + half * 64);
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(tb, v0);
         tmem_ld_32x32(tb + 32u, v1);
         tmem_wait_ld();
+        const long long a1 = FFN_CLOCK();
         // relu() has already mapped NaN to 0 and the values are >= 0, so round-to-nearest (ties away) to TF32 is an
         // integer add + mask on the bit pattern
 #pragma unroll
@@ -330,12 +332,20 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           v1[4 * k + 2] = (__float_as_uint(fmaxf(__uint_as_float(v1[4 * k + 2]) + c4.z, 0.f)) + 0x1000u) & 0xffffe000u;
           v1[4 * k + 3] = (__float_as_uint(fmaxf(__uint_as_float(v1[4 * k + 3]) + c4.w, 0.f)) + 0x1000u) & 0xffffe000u;
         }
+        const long long a2 = FFN_CLOCK();
         tmem_st_32x32(tb, v0);
         tmem_st_32x32(tb + 32u, v1);
         tmem_wait_st();
+        const long long a3 = FFN_CLOCK();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&h_ready[j & 1]), 0));   // leader's barrier
+#ifdef SPE_FFN_TIMING_ACT
+        const long long a4 = FFN_CLOCK();
+        t_p1 += a1 - a0; t_p2 += a2 - a1; t_p3 += a3 - a2; t_epi += a4 - a3;
+#else
+        (void)a0; (void)a1; (void)a2; (void)a3;
+#endif
       }
       if (half != 0) continue;   // the epilogue is done by one warp per lane quarter
 
@@ -443,7 +453,7 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(o_empty), 0));
-#ifdef SPE_FFN_TIMING
+#if defined(SPE_FFN_TIMING) && !defined(SPE_FFN_TIMING_ACT)
       const long long e3 = FFN_CLOCK();
       t_p1 += e1 - e0; t_p2 += e2 - e1; t_p3 += e3 - e2; t_epi += e3 - e0;
 #else

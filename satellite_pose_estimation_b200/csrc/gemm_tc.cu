@@ -1129,6 +1129,12 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (cg2) BN = 256;
   static const int bn_force = getenv("SPE_GEMM_BN") ? atoi(getenv("SPE_GEMM_BN")) : 0;   // experiments only
   if (!cg2 && (bn_force == 64 || bn_force == 128) && bn_force <= d.N) BN = bn_force;
+  // few-row GEMMs (the decoder: M = 40 queries x batch): 128-wide tiles leave most SMs without a tile while every CTA
+  // serialises the whole K loop -- 64-wide tiles double the CTAs that share it
+  static const int small_bn = getenv("SPE_GEMM_SMALL_BN") ? atoi(getenv("SPE_GEMM_SMALL_BN")) : 1;
+  if (small_bn && !cg2 && bn_force == 0 && BN == 128 && d.N % 64 == 0 &&
+      m_tiles_est * ((d.N + 127) / 128) * 2 <= num_sms)
+    BN = 64;
 
   GemmKParams kp{};
   kp.round_out = d.round_out;
