@@ -111,6 +111,17 @@ int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_de
                    float* points_px_dev /*[B,Q,2] or NULL*/, float* sigmas_dev /*[B,Q,2] or NULL*/,
                    int32_t* inlier_mask_dev /*[B] or NULL*/, void* stream);
 
+/* replaces: Multi_Mean_PoseSolver.__call__ (RV/utils/speed_eval.py:42-140) over a batch, fed with the per-model network
+ * outputs that gen_prediction collects (RV/gen_submission_multi.py:122-141): logits [num_models,B,Q,12] and points
+ * [num_models,B,Q,2] (normalised; the PostProcess de-normalisation with `boxes` happens inside).  Every foreground
+ * query of every model is pooled per keypoint label (mean -> drop predictions farther than 3 std of the distances
+ * -> mean), then the same RANSAC-P3P consensus + LM refinement as spe_assign_pnp.  count [B,11] receives the number of
+ * predictions each label's mean was taken over (0 = label absent), pooled_px [B,11,2] the pooled keypoints. */
+int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_dev, const int32_t* boxes_dev,
+                     int num_models, int B, int Q, const spe_pnp_params* params, double* quat_dev /*[B,4]*/,
+                     double* tvec_dev /*[B,3]*/, int32_t* count_dev /*[B,11]*/, int32_t* status_dev /*[B]*/,
+                     float* pooled_px_dev /*[B,11,2] or NULL*/, int32_t* inlier_mask_dev /*[B] or NULL*/, void* stream);
+
 /* ---- whole path, host buffers in, host buffers out ---------------------------------------------------------- */
 /* replaces the hot loop of gen_submission (RV/gen_submission_single.py:136-181): frames + detector boxes in
  * host memory -> poses in host memory.  Uploads, runs crop -> forward -> assign/PnP on `stream`, downloads and

@@ -198,6 +198,58 @@ def write_pnp(rv_eval, n=400):
     print("pnp cases", n, "solved", int(ok.sum()))
 
 
+def write_pnp_multi(rv_eval, n=200, num_models=5):
+    """Ensemble solver: the reference's own PostProcess per member + its own Multi_Mean_PoseSolver."""
+    import cv2
+    import io
+    import contextlib
+    d = synth.make_multi_predictions(n, num_models=num_models, seed=7)
+    args = synth.reference_args(ModelCfg())
+    args.repro = 25                                                         # RV/gen_submission_multi.py:106
+    solver = rv_eval.Multi_Mean_PoseSolver(args)                            # the reference's own ensemble solver
+    post = sys.modules["models"].PostProcess()
+    boxes = [torch.from_numpy(b) for b in d["boxes"]]
+    per_model = [post({"pred_logits": torch.from_numpy(d["logits"][m]),
+                       "pred_points": torch.from_numpy(d["points"][m]).clone()}, boxes) for m in range(num_models)]
+    quat = np.zeros((n, 4)); tvec = np.zeros((n, 3)); ok = np.zeros(n, dtype=np.int32)
+    pooled = np.zeros((n, 11, 2), dtype=np.float32); count = np.zeros((n, 11), dtype=np.int32)
+    oracle = pnp_ref.MultiMeanPoseSolver(25, return_details=True)
+    nan_cases = 0
+    for i in range(n):
+        mp = [per_model[m][i]["points"] for m in range(num_models)]
+        ml = [per_model[m][i]["logits"] for m in range(num_models)]
+        # the restatement's pooling must equal the reference's own mean_and_filter bit for bit
+        mean_o, cnt_o = oracle.pool(mp, ml)
+        from collections import defaultdict
+        orig = defaultdict(list)
+        for points, logits in zip(mp, ml):
+            labels, scores = solver.find_index(logits)
+            fg = labels != logits.shape[1] - 1
+            for pt_, l_ in zip(points[fg], labels[fg]):
+                orig[l_].append(pt_)
+        import warnings
+        with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+            warnings.simplefilter("ignore")
+            mean_r = solver.mean_and_filter(orig)
+        assert list(mean_r.keys()) == list(mean_o.keys())
+        for l_ in mean_r:
+            assert np.array_equal(mean_r[l_], mean_o[l_], equal_nan=True), (i, l_)
+        if any(np.isnan(v).any() for v in mean_r.values()):
+            nan_cases += 1
+        pooled[i], count[i] = pnp_ref.pooled_table(mean_o, cnt_o)
+        try:                                                                # RV/gen_submission_multi.py:166-171
+            with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+                warnings.simplefilter("ignore")
+                q, t = solver(mp, ml)
+            if np.all(np.isfinite(q)) and np.all(np.isfinite(t)):
+                quat[i], tvec[i], ok[i] = q, t, 1
+        except (IndexError, cv2.error):
+            pass
+    np.savez_compressed(os.path.join(GOLDEN, "pnp_multi_golden.npz"), quat=quat, tvec=tvec, ok=ok, pooled_px=pooled,
+                        count=count, n=n, num_models=num_models, seed=7)
+    print("ensemble pnp cases", n, "solved", int(ok.sum()), "with an emptied label", nan_cases)
+
+
 def main():
     if not ref_import.available():
         raise SystemExit("/root/reference is not mounted: golden vectors can only be regenerated in the build container")
@@ -207,6 +259,7 @@ def main():
     write_crop(rv_speed)
     write_model()
     write_pnp(rv_eval)
+    write_pnp_multi(rv_eval)
 
 
 if __name__ == "__main__":

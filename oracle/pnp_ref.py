@@ -4,6 +4,7 @@
                           (+ sigmas = exp(pred_sigmas)         SA/src/zoo/rtdetr/rtdetr_postprocessor.py:53)
 * ``assign``              find_index + per-label best query    RV/utils/speed_eval.py:152-162, :184-200
 * ``SimplePoseSolver``    cv2 RANSAC-P3P -> ITERATIVE refine   RV/utils/speed_eval.py:143-242
+* ``MultiMeanPoseSolver`` ensemble pooling + the same chain    RV/utils/speed_eval.py:42-140
 * ``sigma_pnp``           sigma-weighted Huber LM              SA/utils/speed_eval.py:269-319 (ceres_pnp) -- the
                           cost functor is a private PyCeres build (absent): restated with scipy, PARITY UNPINNED
 * ``self_assessment``     reject filter                        no reference code exists:
@@ -123,6 +124,84 @@ class SimplePoseSolver:
         if self.return_inliers:
             return quat.flatten(), np.asarray(tvec).flatten(), used
         return quat.flatten(), np.asarray(tvec).flatten()
+
+
+class MultiMeanPoseSolver:
+    """Multi_Mean_PoseSolver, RV/utils/speed_eval.py:42-140 (the ensemble solver of gen_submission_multi.py).
+    ``solver(multi_points, multi_probs)``: one [Q,2] pixel array and one [Q,12] probability array per member."""
+
+    def __init__(self, repro=25, return_details=False):
+        self.W_Pt = TANGO_POINTS
+        self.reprojectionError = repro
+        self.return_details = return_details
+
+    @staticmethod
+    def mean_and_filter(obj_pts):
+        """:57-75 -- per label: mean of all pooled predictions; with >= 3 of them, drop those whose distance to the
+        mean is not below 3 std of the distances, and average the rest (an empty rest gives NaN, as in the reference)."""
+        from scipy.spatial.distance import cdist
+        result, counts = {}, {}
+        for label, points in obj_pts.items():
+            num_points = len(points)
+            points = np.vstack(points)
+            points_mean = np.mean(points, axis=0, keepdims=True)
+            if num_points < 3:
+                result[label] = points_mean.flatten()
+                counts[label] = num_points
+            else:
+                distances = cdist(points, points_mean).flatten()
+                std_dist = np.std(distances)
+                inlier_index = distances < std_dist * 3
+                with np.errstate(all="ignore"):
+                    import warnings
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        result[label] = np.mean(points[inlier_index], axis=0).flatten()
+                counts[label] = int(inlier_index.sum())
+        return result, counts
+
+    def pool(self, multi_points, multi_logits):
+        """:77-92 -- every foreground query of every member, appended per label in (member, query) order."""
+        from collections import defaultdict
+        obj_pts_original = defaultdict(list)
+        for points, logits in zip(multi_points, multi_logits):
+            points = np.asarray(points); logits = np.asarray(logits)
+            labels = logits.argmax(1)
+            fg = labels != logits.shape[1] - 1
+            for pt_, l_ in zip(points[fg], labels[fg]):
+                obj_pts_original[int(l_)].append(pt_)
+        return self.mean_and_filter(obj_pts_original)
+
+    def __call__(self, multi_points, multi_logits):
+        assert len(multi_points) == len(multi_logits)
+        obj_pts_mean, counts = self.pool(multi_points, multi_logits)
+        order = list(obj_pts_mean.keys())
+        obj_pts = np.asarray([obj_pts_mean[l_][:2] for l_ in order])[:, np.newaxis, :].astype(np.float32)   # :94-102
+        wld_pts = np.asarray([self.W_Pt[l_] for l_ in order])[:, np.newaxis, :].astype(np.float32)
+        retval, rvec, tvec, inliers = cv2.solvePnPRansac(                                                   # :105-110
+            wld_pts, obj_pts, CAMERA_K, CAMERA_DIST, useExtrinsicGuess=False, flags=cv2.SOLVEPNP_P3P,
+            reprojectionError=self.reprojectionError)
+        used = None
+        if inliers is not None:                                                                             # :115-126
+            idx = inliers.flatten()
+            retval, rvecs, tvecs, _ = cv2.solvePnPGeneric(
+                wld_pts[idx], obj_pts[idx], CAMERA_K, CAMERA_DIST, useExtrinsicGuess=True, rvec=rvec, tvec=tvec,
+                flags=cv2.SOLVEPNP_ITERATIVE)
+            assert len(rvecs) == 1
+            rvec, tvec = rvecs[0], tvecs[0]
+            used = sorted(order[i] for i in idx)
+        quat = rot_to_quat(cv2.Rodrigues(rvec)[0])                                                          # :128-131
+        if self.return_details:
+            return quat.flatten(), np.asarray(tvec).flatten(), obj_pts_mean, counts, used
+        return quat.flatten(), np.asarray(tvec).flatten()
+
+
+def pooled_table(obj_pts_mean, counts):
+    """pooled keypoints as float32 [11,2] (0 where absent) and the per-label counts int32 [11]."""
+    pts = np.zeros((11, 2), dtype=np.float32); cnt = np.zeros(11, dtype=np.int32)
+    for l_, p in obj_pts_mean.items():
+        pts[l_] = p[:2]; cnt[l_] = counts[l_]
+    return pts, cnt
 
 
 def solve_or_zero(solver, points, probs):

@@ -260,3 +260,55 @@ def make_predictions(n, Q=40, seed=1, noise_px=1.0, outlier_frac=0.10, few_frac=
     if with_sigma:
         out["logsig"] = logsig
     return out
+
+
+def make_multi_predictions(n, num_models=5, Q=40, seed=7, noise_px=1.0, outlier_frac=0.08, miss_frac=0.05,
+                           few_frac=0.05):
+    """Ensemble-shaped PnP inputs (RV/gen_submission_multi.py): ``num_models`` members predict the same ``n`` crops.
+
+    Every member finds each visible keypoint with independent N(0, noise_px) noise (one query per label in a random
+    slot, occasionally a second lower-score query nearby: the ensemble solver pools EVERY foreground query), misses a
+    label with probability ``miss_frac`` and puts it grossly wrong (50..200 px) with probability ``outlier_frac`` --
+    the 3-sigma filter's job.  Returns dict: logits [Nm,n,Q,12] f32 raw logits, points [Nm,n,Q,2] f32 normalised,
+    boxes [n,4] int64, q_gt [n,4], t_gt [n,3]."""
+    rng = np.random.default_rng(seed)
+    logits = np.zeros((num_models, n, Q, 12), dtype=np.float32)
+    points = rng.uniform(0.05, 0.95, (num_models, n, Q, 2)).astype(np.float32)
+    boxes = np.zeros((n, 4), dtype=np.int64)
+    q_gt = np.zeros((n, 4)); t_gt = np.zeros((n, 3))
+    for i in range(n):
+        q = _random_quat(rng)
+        t = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3), rng.uniform(3.0, 20.0)])
+        pc = TANGO_POINTS @ quat_to_rot(q).T + t
+        uv = pc[:, :2] / pc[:, 2:3] * np.array([CAMERA_K[0, 0], CAMERA_K[1, 1]]) + CAMERA_K[:2, 2]
+        q_gt[i], t_gt[i] = q, t
+        lo, hi = uv.min(0), uv.max(0)
+        side = int(max(hi - lo) * 1.2) + 8
+        cx, cy = (lo + hi) / 2
+        x1, y1 = int(cx - side / 2), int(cy - side / 2)
+        boxes[i] = (x1, y1, x1 + side, y1 + side)
+        visible = np.arange(11)
+        if rng.random() < few_frac:
+            visible = rng.permutation(11)[: rng.integers(0, 4)]            # < 4 keypoints: failure path
+        for m in range(num_models):
+            slots = rng.permutation(Q)
+            used = 0
+            for l_ in rng.permutation(visible):                            # label order differs between members
+                if rng.random() < miss_frac:
+                    continue
+                p = uv[l_] + rng.normal(0, noise_px, 2)
+                if len(visible) >= 6 and rng.random() < outlier_frac:
+                    ang, mag = rng.uniform(0, 2 * np.pi), rng.uniform(50, 200)
+                    p = p + mag * np.array([np.cos(ang), np.sin(ang)])
+                reps = 2 if rng.random() < 0.15 else 1                     # a second, weaker query on the same keypoint
+                for r in range(reps):
+                    s = slots[used]; used += 1
+                    top = rng.uniform(0.5, 0.99) if r == 0 else rng.uniform(0.3, 0.45)
+                    logits[m, i, s, :] = np.log((1 - top) / 11)
+                    logits[m, i, s, l_] = np.log(top)
+                    points[m, i, s] = (p + (rng.normal(0, 2.0, 2) if r else 0.0) - boxes[i, :2]) / side
+            for s in slots[used:]:
+                top = rng.uniform(0.6, 0.99)
+                logits[m, i, s, :] = np.log((1 - top) / 11)
+                logits[m, i, s, 11] = np.log(top)
+    return {"logits": logits, "points": points, "boxes": boxes, "q_gt": q_gt, "t_gt": t_gt}

@@ -7,5 +7,6 @@
 All compute runs in ``libspe.so`` (hand-written sm_100a CUDA, C ABI in include/spe.h).  No CPU fallback.
 """
 from .models import B200DETR, PostProcess, build_model  # noqa: F401
-from .solver import BatchedPoseSolver, build_solver  # noqa: F401
+from .solver import BatchedPoseSolver, MultiMeanPoseSolver, build_solver  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .submission import SubmissionWriter, gen_prediction, gen_submission, run_image_set, save_prediction  # noqa: F401

@@ -148,6 +148,29 @@ int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_de
   return SPE_OK;
 }
 
+int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_dev, const int32_t* boxes_dev,
+                     int num_models, int B, int Q, const spe_pnp_params* params, double* quat_dev, double* tvec_dev,
+                     int32_t* count_dev, int32_t* status_dev, float* pooled_px_dev, int32_t* inlier_mask_dev,
+                     void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_ensemble_pnp: null ctx");
+  if (!logits_dev || !points_dev || !boxes_dev || !quat_dev || !tvec_dev || !count_dev || !status_dev || !params)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_ensemble_pnp: null buffer");
+  if (num_models < 1) return set_error(ctx, SPE_ERR_INVALID, "spe_ensemble_pnp: needs at least one model");
+  if (params->weighted) return set_error(ctx, SPE_ERR_INVALID, "spe_ensemble_pnp: the ensemble solver has no sigma-weighted form");
+  PnpDesc d{};
+  d.logits = logits_dev; d.points = points_dev; d.logsig = nullptr; d.boxes = boxes_dev;
+  d.B = B; d.Q = Q; d.num_models = num_models;
+  d.reproj_thresh = params->reproj_thresh;
+  d.reject = params->reject;
+  d.reject_rms_px = params->reject_rms_px > 0 ? params->reject_rms_px : 5.0f;
+  d.reject_sigma = params->reject_sigma_px > 0 ? params->reject_sigma_px : 12.0f;
+  d.quat = quat_dev; d.tvec = tvec_dev; d.assign = count_dev; d.status = status_dev;
+  d.pooled_px = pooled_px_dev; d.inlier_mask = inlier_mask_dev;
+  std::string s = launch_assign_pnp(d, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(ctx, SPE_ERR_CUDA, "spe_ensemble_pnp: " + s);
+  return SPE_OK;
+}
+
 int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, const double* det_boxes_host, int B,
                        const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
                        int32_t* boxes_host, void* stream) {

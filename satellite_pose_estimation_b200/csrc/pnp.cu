@@ -9,6 +9,9 @@
 //                                  Rodrigues -> quaternion (w,x,y,z)
 //   SimplePoseSolverSigma          same with sigma-weighted Huber LM in normalised     SA/utils/speed_eval.py:269-420
 //                                  image coordinates, w = 1/(sqrt(sigma)+1e-6) / sum
+//   Multi_Mean_PoseSolver          ensemble of N checkpoints: every foreground query   RV/utils/speed_eval.py:42-140
+//                                  of every model is pooled per label, mean -> 3-sigma
+//                                  distance filter -> mean, then the same PnP chain
 //
 // cv2's RANSAC draws random 4-point samples; the warp instead evaluates EVERY 3-point minimal sample (<= 165 for 11
 // keypoints; Grunert's P3P, closed-form quartic) against all correspondences and keeps the hypothesis with the most
@@ -416,6 +419,7 @@ __device__ void rot_to_quat(const double (&R)[9], double (&q)[4]) {
 }
 
 constexpr int kPnpThreads = 128;
+constexpr int kMaxPooled = 4096;     // ensemble: models x queries per image
 
 __global__ void __launch_bounds__(kPnpThreads)
 assign_pnp_kernel(const PnpDesc d) {
@@ -434,6 +438,7 @@ assign_pnp_kernel(const PnpDesc d) {
   __shared__ double s_bpose[4][12];
   __shared__ double s_J[16 * 14];
   __shared__ double s_A[27];
+  __shared__ unsigned char s_elab[kMaxPooled];   // ensemble: label of every pooled prediction
 
   const float* lg = d.logits + static_cast<long long>(img) * Q * 12;
   const float* pt = d.points + static_cast<long long>(img) * Q * 2;
@@ -442,7 +447,113 @@ assign_pnp_kernel(const PnpDesc d) {
   const float bh = static_cast<float>(d.boxes[img * 4 + 3] - by1);
 
   const long long t_start = clock64();
-  if (warp == 0) {
+  if (warp == 0 && d.num_models > 0) {
+    // ---- ensemble: Multi_Mean_PoseSolver.__call__ / mean_and_filter (RV/utils/speed_eval.py:57-96)
+    // pooled prediction e = model * Q + query, i.e. the order in which the reference appends to obj_pts_original
+    const int NQ = d.num_models * Q;
+    auto pixel = [&](int e, float& px, float& py) {
+      const int m = e / Q, q = e - m * Q;
+      const float* p2 = d.points + ((static_cast<long long>(m) * d.B + img) * Q + q) * 2;
+      px = __fadd_rn(__fmul_rn(p2[0], bw), static_cast<float>(bx1));     // PostProcess, fp32, unfused
+      py = __fadd_rn(__fmul_rn(p2[1], bh), static_cast<float>(by1));
+    };
+    for (int e = lane; e < NQ; e += 32) {
+      const int m = e / Q, q = e - m * Q;
+      const float* x = d.logits + ((static_cast<long long>(m) * d.B + img) * Q + q) * 12;
+      float mx = -INFINITY;
+      int am = 0;
+#pragma unroll
+      for (int c = 0; c < 12; ++c) {
+        const float v = x[c];
+        if (v > mx) { mx = v; am = c; }     // first maximum, like np.argmax
+      }
+      s_elab[e] = static_cast<unsigned char>(am);
+    }
+    __syncwarp();
+    float mx = 0.f, my = 0.f;
+    int cnt = 0, first = 0x7fffffff;
+    if (lane < 11) {
+      // np.mean over float32 rows: sequential fp32 sums in pooling order, one fp32 division
+      float sx = 0.f, sy = 0.f;
+      int n = 0;
+      for (int e = 0; e < NQ; ++e) {
+        if (s_elab[e] != lane) continue;
+        float px, py;
+        pixel(e, px, py);
+        sx = __fadd_rn(sx, px); sy = __fadd_rn(sy, py);
+        if (n == 0) first = e;
+        ++n;
+      }
+      if (n > 0) {
+        const float m0x = __fdiv_rn(sx, static_cast<float>(n)), m0y = __fdiv_rn(sy, static_cast<float>(n));
+        if (n < 3) {
+          mx = m0x; my = m0y; cnt = n;
+        } else {
+          // cdist(points, mean) in float64, np.std of the distances, keep distances < 3 std, mean again
+          double sd = 0.0;
+          for (int e = 0; e < NQ; ++e) {
+            if (s_elab[e] != lane) continue;
+            float px, py;
+            pixel(e, px, py);
+            const double dx = static_cast<double>(px) - static_cast<double>(m0x);
+            const double dy = static_cast<double>(py) - static_cast<double>(m0y);
+            sd += sqrt(dx * dx + dy * dy);
+          }
+          const double md = sd / n;
+          double var = 0.0;
+          for (int e = 0; e < NQ; ++e) {
+            if (s_elab[e] != lane) continue;
+            float px, py;
+            pixel(e, px, py);
+            const double dx = static_cast<double>(px) - static_cast<double>(m0x);
+            const double dy = static_cast<double>(py) - static_cast<double>(m0y);
+            const double dd = sqrt(dx * dx + dy * dy) - md;
+            var += dd * dd;
+          }
+          const double thr = 3.0 * sqrt(var / n);
+          float s2x = 0.f, s2y = 0.f;
+          int k = 0;
+          for (int e = 0; e < NQ; ++e) {
+            if (s_elab[e] != lane) continue;
+            float px, py;
+            pixel(e, px, py);
+            const double dx = static_cast<double>(px) - static_cast<double>(m0x);
+            const double dy = static_cast<double>(py) - static_cast<double>(m0y);
+            if (sqrt(dx * dx + dy * dy) < thr) { s2x = __fadd_rn(s2x, px); s2y = __fadd_rn(s2y, py); ++k; }
+          }
+          // k == 0 (all distances equal, e.g. coincident predictions): the reference averages an empty set -> NaN
+          // image point, which its RANSAC can never count as an inlier; here the label is dropped instead
+          if (k > 0) { mx = __fdiv_rn(s2x, static_cast<float>(k)); my = __fdiv_rn(s2y, static_cast<float>(k)); cnt = k; }
+        }
+      }
+    }
+    const bool present = lane < 11 && cnt > 0;
+    // correspondence order = order of first appearance of each label in the pooled list (dict insertion order)
+    int rank = 0;
+    for (int l = 0; l < 11; ++l) {
+      const int f2 = __shfl_sync(FULL, first, l);
+      const int c2 = __shfl_sync(FULL, cnt, l);
+      if (c2 > 0 && f2 < first) ++rank;
+    }
+    const unsigned pm = __ballot_sync(FULL, present);
+    if (lane < 11) {
+      d.assign[img * 11 + lane] = cnt;
+      if (d.pooled_px) {
+        d.pooled_px[(img * 11 + lane) * 2 + 0] = present ? mx : 0.f;
+        d.pooled_px[(img * 11 + lane) * 2 + 1] = present ? my : 0.f;
+      }
+    }
+    if (present) {
+      s_lab[rank] = lane;
+      s_uv[2 * rank] = static_cast<double>(mx);
+      s_uv[2 * rank + 1] = static_cast<double>(my);
+      const double bx = (static_cast<double>(mx) - kCx) / kFx, by = (static_cast<double>(my) - kCy) / kFy;
+      const double inv = 1.0 / sqrt(bx * bx + by * by + 1.0);
+      s_bear[3 * rank] = bx * inv; s_bear[3 * rank + 1] = by * inv; s_bear[3 * rank + 2] = inv;
+      s_sig[2 * rank] = 1.0; s_sig[2 * rank + 1] = 1.0;
+    }
+    if (lane == 0) s_n = __popc(pm);
+  } else if (warp == 0) {
     // ---- PostProcess + find_index, one query per lane per pass; per-label running best (score desc, query asc)
     float best_s[11];
     int best_q[11];
@@ -655,6 +766,8 @@ assign_pnp_kernel(const PnpDesc d) {
 std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s) {
   if (d.B <= 0) return "";
   if (d.Q <= 0 || d.Q > 4096) return "assign_pnp: bad query count";
+  if (d.num_models < 0 || static_cast<long long>(d.num_models) * d.Q > kMaxPooled)
+    return "ensemble_pnp: models x queries must not exceed 4096";
   ProfScope ps(kFamPnp, s);
   PnpDesc dd = d;
   static const bool timing = getenv("SPE_PNP_TIMING") != nullptr;

@@ -123,6 +123,11 @@ struct PnpDesc {
   float* sigmas;         // [B,Q,2] or null: exp(logsig)
   int32_t* inlier_mask;  // [B] bit i = label i used in the final refinement, or null
   int debug_timing;      // print per-phase cycle counts of the first images (SPE_PNP_TIMING)
+  // ensemble form (Multi_Mean_PoseSolver): num_models > 0 -> logits / points are [num_models,B,Q,*], every foreground
+  // query of every model is pooled per label (mean -> 3-sigma filter -> mean); `assign` then receives the number of
+  // predictions each label's mean was taken over (0 = label absent)
+  int num_models;
+  float* pooled_px;      // [B,11,2] or null: the pooled keypoints in original-image pixels (0 where absent)
 };
 std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s);
 

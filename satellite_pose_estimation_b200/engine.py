@@ -180,6 +180,32 @@ class Engine:
                 out["sigmas"] = sig
         return out
 
+    def ensemble_pnp(self, logits, points, boxes, reproj=25.0, reject=False, want_pooled=False):
+        """Batched ``Multi_Mean_PoseSolver`` (RV/utils/speed_eval.py:42-140): ``logits`` [Nm,B,Q,12] and ``points``
+        [Nm,B,Q,2] are the raw outputs of the Nm ensemble members for the same B crops (cuda), ``boxes`` int [B,4]
+        the crop boxes.  Returns dict of cuda tensors: quat, tvec, status, count [B,11] (predictions pooled per
+        keypoint after the 3-sigma filter), inlier_mask, and with ``want_pooled`` the pooled keypoints [B,11,2] px."""
+        logits = logits.contiguous().float(); points = points.contiguous().float()
+        boxes = boxes.to(torch.int32).contiguous()
+        Nm, B, Q = logits.shape[0], logits.shape[1], logits.shape[2]
+        assert points.shape[:3] == (Nm, B, Q) and boxes.shape == (B, 4)
+        dev = logits.device
+        quat = torch.empty((B, 4), dtype=torch.float64, device=dev)
+        tvec = torch.empty((B, 3), dtype=torch.float64, device=dev)
+        count = torch.empty((B, 11), dtype=torch.int32, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        inl = torch.empty((B,), dtype=torch.int32, device=dev)
+        pooled = torch.empty((B, 11, 2), dtype=torch.float32, device=dev) if want_pooled else None
+        p = SpePnpParams(reproj_thresh=float(reproj), weighted=0, reject=int(reject), reject_rms_px=5.0,
+                         reject_sigma_px=12.0)
+        check(self.lib.spe_ensemble_pnp(self._ctx, _ptr(logits), _ptr(points), _ptr(boxes), Nm, B, Q, C.byref(p),
+                                        _ptr(quat), _ptr(tvec), _ptr(count), _ptr(status), _ptr(pooled), _ptr(inl),
+                                        _stream(dev)), self._ctx)
+        out = {"quat": quat, "tvec": tvec, "count": count, "status": status, "inlier_mask": inl}
+        if want_pooled:
+            out["pooled_px"] = pooled
+        return out
+
     # ---- whole path, host in / host out -----------------------------------------------------------------------
     def run_batch_host(self, frames_host, det_boxes, reproj=20.0, weighted=False, reject=False):
         """frames_host: uint8 (pinned) torch/numpy [B,H,W]; det_boxes: float64 [B,4] -> numpy quat/tvec/status/boxes."""

@@ -67,6 +67,49 @@ class BatchedPoseSolver:
         return r["quat"][0].cpu().numpy(), r["tvec"][0].cpu().numpy()
 
 
+class MultiMeanPoseSolver:
+    """Mirror of ``Multi_Mean_PoseSolver`` (RV/utils/speed_eval.py:42-140), the ensemble solver of
+    ``gen_submission_multi.py``: ``solver(multi_points, multi_logits) -> (quat, tvec)`` with one [Q,2] pixel-point
+    array and one [Q,12] probability array per ensemble member; raises ``IndexError`` where the reference's callers
+    expect a failure (RV/gen_submission_multi.py:166-171).  ``solve_batch`` is the fast path: all images of a batch and
+    all members in one kernel launch, straight from the members' raw outputs."""
+
+    def __init__(self, args=None, engine=None, reproj=None, device=0, model=None):
+        self._engine = engine
+        self._model = model
+        self._device = device
+        self.reprojectionError = float(reproj if reproj is not None else getattr(args, "repro", 25))
+
+    @property
+    def engine(self):
+        if self._model is not None and self._model.engine is not None:
+            return self._model.engine
+        if self._engine is None:
+            self._engine = Engine(max_batch=1, device=self._device)
+        return self._engine
+
+    def solve_batch(self, multi_logits, multi_points, boxes, want_pooled=False):
+        """cuda tensors [Nm,B,Q,12] raw logits, [Nm,B,Q,2] normalised points, int [B,4] crop boxes."""
+        return self.engine.ensemble_pnp(multi_logits, multi_points, boxes, reproj=self.reprojectionError,
+                                        want_pooled=want_pooled)
+
+    def __call__(self, multi_points, multi_logits):
+        assert isinstance(multi_points, list) and isinstance(multi_logits, list)
+        assert len(multi_points) == len(multi_logits)
+        dev = self.engine.device
+        pts = np.stack([np.asarray(p, dtype=np.float32) for p in multi_points])[:, None]       # [Nm,1,Q,2] pixels
+        prb = np.stack([np.asarray(l, dtype=np.float32) for l in multi_logits])[:, None]       # [Nm,1,Q,12] probabilities
+        # pixel coordinates pass through the kernel's de-normalisation unchanged with box (0,0,1,1); the arg-max of
+        # log-probabilities is the arg-max of the probabilities
+        lg = torch.from_numpy(np.log(np.maximum(prb, 1e-38))).to(dev)
+        box = torch.tensor([[0, 0, 1, 1]], dtype=torch.int32, device=dev)
+        r = self.engine.ensemble_pnp(lg, torch.from_numpy(pts).to(dev), box, reproj=self.reprojectionError)
+        status = int(r["status"].item())
+        if status != 0:
+            raise IndexError(f"pose solve failed (status {status})")
+        return r["quat"][0].cpu().numpy(), r["tvec"][0].cpu().numpy()
+
+
 def build_solver(args, model=None, postprocessors=None):
     """Reference contract ``build_solver(args)`` (RV/utils/speed_eval.py:21-22).  Passing the ``model`` /
     ``postprocessors`` returned by ``build_model`` lets the solver share their context and batched results."""

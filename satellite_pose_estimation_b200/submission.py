@@ -1,0 +1,173 @@
+"""Callers and wire formats either side of the hot path, mirrored from the reference:
+
+* ``SubmissionWriter``                      RV/utils/submission.py:6-56 (CSV: filename, q0..q3, r0..r2; test rows sorted by
+                                            filename, then the real-test rows)
+* ``gen_prediction`` / ``gen_submission`` / ``save_prediction``
+                                            RV/gen_submission_multi.py:122-199 -- the ensemble ("multi") submission loop:
+                                            collect every checkpoint's PostProcess results per file, then solve each
+                                            file with ``Multi_Mean_PoseSolver``; log values rounded to 6 decimals
+* ``run_image_set``                         the single-model loop of RV/gen_submission_single.py:113-187 over a whole
+                                            image set, sharded by image across ranks (BASELINE.json configs[4]) and fed
+                                            through the multi-slot batch pipeline of libspe.so
+
+Nothing here computes on the CPU: poses come from libspe.so (``Engine``); this module only moves results around.
+"""
+import csv
+import json
+import os
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from .sharding import batches, gather_results, shard_range
+
+
+class SubmissionWriter:
+    """Collects pose estimates and exports the SPEED submission CSV (same API as the reference class)."""
+
+    def __init__(self):
+        self.test_results = []
+        self.real_test_results = []
+
+    def _append(self, filename, q, r, real):
+        (self.real_test_results if real else self.test_results).append(
+            {"filename": filename, "q": list(q), "r": list(r)})
+
+    def append_test(self, filename, q, r):
+        self._append(filename, q, r, real=False)
+
+    def append_real_test(self, filename, q, r):
+        self._append(filename, q, r, real=True)
+
+    def export(self, out_dir="", suffix=None):
+        sorted_test = sorted(self.test_results, key=lambda k: k["filename"])
+        sorted_real_test = sorted(self.real_test_results, key=lambda k: k["filename"])
+        if suffix is None:
+            suffix = datetime.now().strftime("%Y%m%d-%H%M")
+        path = os.path.join(out_dir, "submission_{}.csv".format(suffix))
+        with open(path, "w") as f:
+            w = csv.writer(f, lineterminator="\n")
+            for result in sorted_test + sorted_real_test:
+                w.writerow([result["filename"], *(result["q"] + result["r"])])
+        return path
+
+
+def log_entry(quat, tvec):
+    """The reference's log record (RV/gen_submission_single.py:176-179): values rounded to 6 decimals, as lists."""
+    return {"quat_pr": np.around(np.asarray(quat, dtype=np.float64), decimals=6).tolist(),
+            "tvec_pr": np.around(np.asarray(tvec, dtype=np.float64), decimals=6).tolist()}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ensemble ("multi") submission loop
+# ---------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def gen_prediction(model, postprocessors, device, data_loader, prediction):
+    """RV/gen_submission_multi.py:122-141: run one checkpoint over the loader and append its PostProcess result to
+    ``prediction[filename]`` (a ``defaultdict(list)``)."""
+    model.eval()
+    for samples, targets in data_loader:
+        samples = samples.to(device)
+        filenames = [item.pop("filename") for item in targets]
+        clip_bbox = [item.pop("clip_bbox") for item in targets]
+        outputs = model(samples)
+        results = postprocessors["points"](outputs, clip_bbox)
+        for filename, ret in zip(filenames, results):
+            prediction[filename].append(ret)
+
+
+def gen_submission(prediction, solver, chunk=256):
+    """RV/gen_submission_multi.py:145-186: ``prediction`` = {filename: [{'logits': [Q,12] probabilities, 'points':
+    [Q,2] pixels} per checkpoint]} -> {filename: {'quat_pr', 'tvec_pr'}} (zero pose where the solve fails).
+
+    With a ``MultiMeanPoseSolver`` all files are solved ``chunk`` at a time by one ensemble kernel launch each (files
+    with the same number of members and queries share a launch); any other solver object is called per file exactly
+    like the reference does."""
+    from .solver import MultiMeanPoseSolver
+    log = {}
+    if not isinstance(solver, MultiMeanPoseSolver):
+        for filename, pre_list in prediction.items():
+            try:
+                quat_pr, tvec_pr = solver([it["points"] for it in pre_list], [it["logits"] for it in pre_list])
+            except IndexError:
+                quat_pr, tvec_pr = np.zeros(4), np.zeros(3)
+            log[filename] = log_entry(quat_pr, tvec_pr)
+        return log
+    groups = {}
+    for filename, pre_list in prediction.items():
+        key = (len(pre_list), np.asarray(pre_list[0]["logits"]).shape[0])
+        groups.setdefault(key, []).append(filename)
+    eng = solver.engine
+    dev = eng.device
+    for (nm, q), names in groups.items():
+        for a in range(0, len(names), chunk):
+            part = names[a:a + chunk]
+            probs = np.stack([[np.asarray(prediction[f][m]["logits"], dtype=np.float32) for f in part] for m in range(nm)])
+            pts = np.stack([[np.asarray(prediction[f][m]["points"], dtype=np.float32) for f in part] for m in range(nm)])
+            # pixel coordinates pass through the kernel's de-normalisation unchanged with box (0,0,1,1)
+            box = torch.tensor([[0, 0, 1, 1]], dtype=torch.int32, device=dev).repeat(len(part), 1)
+            r = eng.ensemble_pnp(torch.from_numpy(np.log(np.maximum(probs, 1e-38))).to(dev), torch.from_numpy(pts).to(dev),
+                                 box, reproj=solver.reprojectionError)
+            quat, tvec, status = r["quat"].cpu().numpy(), r["tvec"].cpu().numpy(), r["status"].cpu().numpy()
+            for i, f in enumerate(part):
+                ok = status[i] == 0
+                log[f] = log_entry(quat[i] if ok else np.zeros(4), tvec[i] if ok else np.zeros(3))
+    return {f: log[f] for f in prediction}     # the reference's dict order: order of first prediction
+
+
+def save_prediction(prediction, save_path):
+    """RV/gen_submission_multi.py:189-199."""
+    log = {}
+    for filename, pre_list in prediction.items():
+        log[filename] = [{"points": np.around(item["points"], decimals=6).tolist(),
+                          "logits": np.around(item["logits"], decimals=6).tolist()} for item in pre_list]
+    with open(save_path, "w") as f:
+        json.dump(log, f)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole image set, one model, sharded by image
+# ---------------------------------------------------------------------------------------------------------------
+def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, rank=0, world_size=1, slots=3,
+                  reproj=20.0, weighted=False, reject=False, gather=True):
+    """crop -> predictor -> PnP for every image of a set (RV/gen_submission_single.py:136-181).
+
+    ``get_frames(i0, i1)`` returns the frames ``i0 .. i1-1`` as a uint8 array / tensor [n,H,W] (decoded by the
+    caller); ``det_boxes`` float64 [N,4] detector boxes, ``filenames`` their keys.  The rank's contiguous shard is
+    cut into batches (ragged tail = short last batch, nothing padded or dropped) that go through the multi-slot
+    pipeline with ``slots`` batches in flight.  Returns {filename: {'quat_pr', 'tvec_pr', 'status'}}; with ``gather``
+    and an initialised process group, rank 0 gets the merged, filename-sorted dict of all ranks (others ``None``)."""
+    n = len(filenames)
+    det_boxes = np.asarray(det_boxes, dtype=np.float64).reshape(n, 4)
+    batch_size = batch_size or engine.max_batch
+    if batch_size > engine.max_batch:
+        raise ValueError(f"batch_size {batch_size} exceeds the engine's max_batch {engine.max_batch}")
+    slots = max(1, min(4, slots))
+    a, b = shard_range(n, rank, world_size)
+    todo = batches(a, b, batch_size)
+    local = {}
+    staged = [None] * slots
+
+    def submit(k):
+        i0, i1 = todo[k]
+        fr = get_frames(i0, i1)
+        fr = fr if isinstance(fr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fr, dtype=np.uint8))
+        if not fr.is_pinned():
+            fr = fr.contiguous().pin_memory()
+        staged[k % slots] = fr                      # must stay alive until the slot is collected
+        engine.submit_batch_host(k % slots, fr, det_boxes[i0:i1], reproj=reproj, weighted=weighted, reject=reject)
+
+    for k in range(min(slots, len(todo))):
+        submit(k)
+    for k in range(len(todo)):
+        r = engine.collect_batch_host(k % slots)
+        i0, i1 = todo[k]
+        for j, i in enumerate(range(i0, i1)):
+            ok = r["status"][j] in (0, 3)           # 3 = solved but flagged by the self-assessment filter
+            e = log_entry(r["quat"][j] if ok else np.zeros(4), r["tvec"][j] if ok else np.zeros(3))
+            e["status"] = int(r["status"][j])
+            local[filenames[i]] = e
+        if k + slots < len(todo):
+            submit(k + slots)
+    return gather_results(local) if gather else local

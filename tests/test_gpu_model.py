@@ -247,3 +247,68 @@ def test_errors_are_loud(lib, cuda_dev):
     with pytest.raises(SpeError, match="max_batch"):
         eng.forward(torch.zeros(3, 3, 224, 224, device="cuda"))
     eng.close()
+
+
+def test_image_set_runner_shards_and_matches_batch_calls(lib, cuda_dev):
+    """BASELINE configs[4] in miniature: a 150-image set through run_image_set (three batches in flight, ragged last
+    batch, two emulated ranks) gives exactly what one spe_run_batch_host call per batch gives, keyed by filename."""
+    from satellite_pose_estimation_b200.submission import run_image_set
+    cfg = model_ref.ModelCfg()
+    eng = Engine(max_batch=64)
+    eng.load_state_dict(synth.make_state_dict(cfg, seed=0))
+    n = 150
+    det = synth.load_detector_boxes()[:n]
+    base = synth.make_frames(8, det, seed=3)
+    frames = np.stack([np.roll(base[i % 8], 11 * i, axis=1) for i in range(n)])
+    names = [f"img{(7 * i) % n:06d}.jpg" for i in range(n)]                          # not in filename order
+    preds = synth.make_predictions(64, seed=5)
+    eng.set_pnp_override(torch.from_numpy(preds["logits"]).cuda(), torch.from_numpy(preds["points"]).cuda(),
+                         torch.from_numpy(preds["boxes"]).to(torch.int32).cuda())     # so that poses are non-trivial
+    get = lambda a, b: frames[a:b]
+    merged = {}
+    for rank in range(2):
+        part = run_image_set(eng, get, det, names, batch_size=64, rank=rank, world_size=2, slots=3, gather=False)
+        assert not (set(part) & set(merged))
+        merged.update(part)
+    assert sorted(merged) == sorted(names)
+    from satellite_pose_estimation_b200.sharding import shard_range, batches
+    from satellite_pose_estimation_b200.submission import log_entry
+    for rank in range(2):
+        a, b = shard_range(n, rank, 2)
+        for i0, i1 in batches(a, b, 64):
+            r = eng.run_batch_host(torch.from_numpy(frames[i0:i1]).pin_memory(), det[i0:i1])
+            for j, i in enumerate(range(i0, i1)):
+                ok = r["status"][j] == 0
+                want = log_entry(r["quat"][j] if ok else np.zeros(4), r["tvec"][j] if ok else np.zeros(3))
+                got = merged[names[i]]
+                assert got["status"] == int(r["status"][j]) and got["quat_pr"] == want["quat_pr"] and \
+                    got["tvec_pr"] == want["tvec_pr"], (i, got, want)
+    assert sum(1 for v in merged.values() if v["status"] == 0) > 100
+    eng.set_pnp_override(None, None, None)
+    eng.close()
+
+
+def test_ensemble_submission_loop(lib, cuda_dev):
+    """gen_submission of the ensemble path (RV/gen_submission_multi.py:145-186): the batched kernel path equals the
+    per-file solver calls, failures become the zero pose, values are rounded to 6 decimals."""
+    from collections import defaultdict
+    from satellite_pose_estimation_b200 import MultiMeanPoseSolver, gen_submission
+    nm, n = 3, 40
+    d = synth.make_multi_predictions(n, num_models=nm, seed=11)
+    prediction = defaultdict(list)
+    for m in range(nm):
+        for i, r in enumerate(pnp_ref.post_process(d["logits"][m], d["points"][m], d["boxes"])):
+            prediction[f"img{i:06d}.jpg"].append(r)
+    eng = Engine(max_batch=1)
+    solver = MultiMeanPoseSolver(reproj=25, engine=eng)
+    log = gen_submission(prediction, solver)
+    assert list(log) == list(prediction)
+
+    class PerFile:                       # any non-batched solver object goes through the reference's per-file loop
+        def __call__(self, mp, ml):
+            return solver(mp, ml)
+    log2 = gen_submission(prediction, PerFile())
+    assert log == log2
+    zero = [f for f, v in log.items() if not any(v["quat_pr"])]
+    assert 0 < len(zero) < n // 2 and all(log[f]["tvec_pr"] == [0.0, 0.0, 0.0] for f in zero)
+    eng.close()

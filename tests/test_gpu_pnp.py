@@ -7,7 +7,7 @@ import torch
 
 from oracle import pnp_ref, synth
 from oracle.constants import TANGO_POINTS
-from satellite_pose_estimation_b200 import Engine
+from satellite_pose_estimation_b200 import Engine, MultiMeanPoseSolver
 
 pytestmark = pytest.mark.gpu
 ROT_TOL_DEG, TRA_TOL = 0.01, 1e-4        # north_star: "poses match cv2 within 0.01 deg rotation and 1e-4 relative t"
@@ -142,6 +142,52 @@ def test_sigma_weighted_solve_and_reject_filter(eng):
     # a confident-but-wrong set is rejected: tiny threshold forces status 3 with the pose still reported
     r3 = _solve(eng, d, reproj=25.0, weighted=True, reject=True, reject_rms_px=1e-3)
     assert ((r3["status"] == 3) | (r3["status"] == 1)).all() and (r3["status"] == 3).sum() > 100
+
+
+def test_ensemble_solver_matches_reference(eng):
+    """spe_ensemble_pnp vs the reference's Multi_Mean_PoseSolver (golden) and the cv2 chain of the oracle: pooled
+    keypoints and their counts bit-exact, success / failure identical, poses within tolerance whenever the consensus
+    set is the one cv2's RANSAC drew; otherwise the exhaustive consensus is never smaller than cv2's."""
+    import warnings
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "pnp_multi_golden.npz"))
+    n, nm = int(g["n"]), int(g["num_models"])
+    d = synth.make_multi_predictions(n, num_models=nm, seed=int(g["seed"]))
+    r = eng.ensemble_pnp(torch.from_numpy(d["logits"]).cuda(), torch.from_numpy(d["points"]).cuda(),
+                         torch.from_numpy(d["boxes"]).cuda(), reproj=25.0, want_pooled=True)
+    torch.cuda.synchronize()
+    r = {k: v.cpu().numpy() for k, v in r.items()}
+    assert np.array_equal(r["count"], g["count"])
+    have = g["count"] > 0
+    assert np.array_equal(r["pooled_px"][have], g["pooled_px"][have])            # fp32 bit-exact with numpy's means
+    assert not r["pooled_px"][~have].any()
+    assert np.array_equal(r["status"] == 0, g["ok"] == 1)
+    per_model = [pnp_ref.post_process(d["logits"][m], d["points"][m], d["boxes"]) for m in range(nm)]
+    solver = pnp_ref.MultiMeanPoseSolver(25, return_details=True)
+    compared = off = 0
+    for i in np.nonzero(g["ok"])[0]:
+        mp = [per_model[m][i]["points"] for m in range(nm)]
+        ml = [per_model[m][i]["logits"] for m in range(nm)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            q_ref, t_ref, mean, cnt, used = solver(mp, ml)
+        order = [l for l in mean.keys() if cnt[l] > 0]      # an emptied label is a NaN point for cv2, dropped by the kernel
+        mine = sorted(order[j] for j in range(len(order)) if (int(r["inlier_mask"][i]) >> j) & 1)
+        if mine != used:
+            off += 1
+            assert len(mine) >= len(used), (i, mine, used)   # every hypothesis cv2 can draw is also evaluated here
+            continue
+        s_t, s_q = pnp_ref.speed_score(r["quat"][i], r["tvec"][i], q_ref, t_ref)
+        assert np.degrees(s_q) < ROT_TOL_DEG and s_t < TRA_TOL, (i, np.degrees(s_q), s_t)
+        compared += 1
+    assert compared >= 0.85 * g["ok"].sum(), (compared, off)
+    # the reference's per-image signature: lists of per-member PostProcess results
+    sol = MultiMeanPoseSolver(reproj=25, engine=eng)
+    i = int(np.nonzero(g["ok"])[0][0])
+    q, t = sol([per_model[m][i]["points"] for m in range(nm)], [per_model[m][i]["logits"] for m in range(nm)])
+    assert np.allclose(q, r["quat"][i], atol=1e-9) and np.allclose(t, r["tvec"][i], atol=1e-9)
+    j = int(np.nonzero(g["ok"] == 0)[0][0])
+    with pytest.raises(IndexError):
+        sol([per_model[m][j]["points"] for m in range(nm)], [per_model[m][j]["logits"] for m in range(nm)])
 
 
 def test_single_image_solver_interface(eng):

@@ -117,3 +117,32 @@ def test_two_rank_gloo_gather(tmp_path):
            "127.0.0.1", "--master-port", "29533", str(script)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "GATHER_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_submission_writer_matches_reference_format(tmp_path):
+    """CSV wire format of RV/utils/submission.py:36-56: test rows sorted by filename, then real-test rows; one line
+    per image: filename, q0..q3, r0..r2 with Python's float repr; '\n' line ends."""
+    from satellite_pose_estimation_b200.submission import SubmissionWriter, log_entry
+    w = SubmissionWriter()
+    w.append_test("img000002.jpg", [1.0, 0.0, 0.0, 0.0], [0.1, -0.2, 10.5])
+    w.append_real_test("img000001real.jpg", [0.5, 0.5, 0.5, 0.5], [0.0, 0.0, 3.0])
+    w.append_test("img000001.jpg", np.array([0.7071068, 0.0, 0.7071068, 0.0]).tolist(), [1.0, 2.0, 3.0])
+    path = w.export(str(tmp_path), suffix="t")
+    assert os.path.basename(path) == "submission_t.csv"
+    assert open(path).read() == ("img000001.jpg,0.7071068,0.0,0.7071068,0.0,1.0,2.0,3.0\n"
+                                 "img000002.jpg,1.0,0.0,0.0,0.0,0.1,-0.2,10.5\n"
+                                 "img000001real.jpg,0.5,0.5,0.5,0.5,0.0,0.0,3.0\n")
+    ref_dir = os.path.join("/root/reference", "Revisiting Monocular Satellite Pose Estimation With Transformer", "utils")
+    if os.path.isdir(ref_dir):       # build container only: the reference's own writer produces the same bytes
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("rv_submission", os.path.join(ref_dir, "submission.py"))
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        r = mod.SubmissionWriter()
+        r.append_test("img000002.jpg", [1.0, 0.0, 0.0, 0.0], [0.1, -0.2, 10.5])
+        r.append_real_test("img000001real.jpg", [0.5, 0.5, 0.5, 0.5], [0.0, 0.0, 3.0])
+        r.append_test("img000001.jpg", [0.7071068, 0.0, 0.7071068, 0.0], [1.0, 2.0, 3.0])
+        os.makedirs(tmp_path / "ref")
+        r.export(str(tmp_path / "ref"), suffix="t")
+        assert open(tmp_path / "ref" / "submission_t.csv").read() == open(path).read()
+    e = log_entry([0.12345678, 1, 0, 0], [1e-7, 2.5, 3.0000004])       # RV/gen_submission_single.py:176-179
+    assert e == {"quat_pr": [0.123457, 1.0, 0.0, 0.0], "tvec_pr": [0.0, 2.5, 3.0]}

@@ -1,6 +1,7 @@
 """The CPU oracle against the golden vectors produced by running the real reference (oracle/make_golden.py)."""
 import os
 
+import cv2
 import numpy as np
 import pytest
 import torch
@@ -111,6 +112,38 @@ def test_pnp_oracle_matches_reference_golden():
     # cv2's RANSAC sampling is not bit-reproducible between calls; the refined optimum is
     assert worst_q < 1e-3 and worst_t < 1e-5
     assert (g["ok"] == 0).sum() > 0 and (d["n_outliers"] > 0).sum() > 0   # failure + outlier paths are covered
+
+
+def test_ensemble_oracle_matches_reference_golden():
+    """MultiMeanPoseSolver restatement vs the reference's own Multi_Mean_PoseSolver (golden made by make_golden.py):
+    pooled keypoints bit-exact (NaN where the reference's 3-sigma filter empties a label), poses to 1e-3 degrees."""
+    import warnings
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "pnp_multi_golden.npz"))
+    n, nm = int(g["n"]), int(g["num_models"])
+    d = synth.make_multi_predictions(n, num_models=nm, seed=int(g["seed"]))
+    per_model = [pnp_ref.post_process(d["logits"][m], d["points"][m], d["boxes"]) for m in range(nm)]
+    solver = pnp_ref.MultiMeanPoseSolver(25, return_details=True)
+    emptied = 0
+    for i in range(n):
+        mp = [per_model[m][i]["points"] for m in range(nm)]
+        ml = [per_model[m][i]["logits"] for m in range(nm)]
+        mean, cnt = solver.pool(mp, ml)
+        pts, c = pnp_ref.pooled_table(mean, cnt)
+        assert np.array_equal(c, g["count"][i])
+        assert np.array_equal(pts, g["pooled_px"][i], equal_nan=True)
+        emptied += int(np.isnan(pts).any())
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                q, t = solver(mp, ml)[:2]
+            ok = bool(np.all(np.isfinite(q)) and np.all(np.isfinite(t)))
+        except (IndexError, cv2.error):
+            ok = False
+        assert ok == bool(g["ok"][i]), i
+        if ok:
+            s_t, s_q = pnp_ref.speed_score(q, t, g["quat"][i], g["tvec"][i])
+            assert np.degrees(s_q) < 1e-3 and s_t < 1e-5, (i, np.degrees(s_q), s_t)
+    assert emptied > 10 and (g["ok"] == 0).sum() > 3          # the filter quirk and the failure path are exercised
 
 
 def test_pnp_oracle_recovers_ground_truth():
