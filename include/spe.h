@@ -79,7 +79,14 @@ int spe_sync(spe_ctx* ctx, void* stream);
 /* replaces: SpeedSubmission.generate_clip_bbox               (RV/datasets/speed.py:92-108)
  * host-side, float64, int() truncation toward zero; det_boxes [B,4] = x1,y1,x2,y2 ; boxes [B,4] int32 */
 int spe_clip_boxes(const double* det_boxes_host, int B, int32_t* boxes_host);
-/* replaces: canvas copy + cv2.resize(INTER_CUBIC) + to_tensor + Normalize   (RV/datasets/speed.py:113-160)
+/* replaces: SpeedTrain.generate_clip_bbox_val + the box rounding of PIL.Image.crop   (RV/datasets/speed.py:246-260,
+ * :223; the main.py --eval path).  float_boxes [B,4] = centre +- 0.6 max(w,h) clipped to the W x H frame (float64, the
+ * box PostProcess later de-normalises with); crop_boxes [B,4] int32 = each coordinate rounded half-to-even like
+ * Python's round(): the (generally non-square) pixel rectangle that spe_crop_resize_norm squashes to R x R */
+int spe_clip_boxes_val(const double* det_boxes_host, int B, int W, int H, double* float_boxes_host,
+                       int32_t* crop_boxes_host);
+/* replaces: canvas copy + cv2.resize(INTER_CUBIC) + to_tensor + Normalize   (RV/datasets/speed.py:113-160), and
+ * PIL crop + A.Resize + to_tensor + Normalize of the eval path (:219-236): boxes may be any pixel rectangle
  * frames: uint8 grayscale, image b at frames + b*frame_stride, rows `pitch` bytes apart; out: fp32 [B,3,R,R] */
 int spe_crop_resize_norm(spe_ctx* ctx, const uint8_t* frames_dev, int H, int W, long long pitch,
                          long long frame_stride, const int32_t* boxes_dev, int B, int R, float* out_nchw_dev,
@@ -102,6 +109,9 @@ typedef struct {
   int reject;            /* 1: apply the self-assessment reject filter (status SPE_POSE_REJECTED)          */
   float reject_rms_px;   /* reject when inlier RMS reprojection error exceeds this (default 5)            */
   float reject_sigma_px; /* reject when mean predicted sigma (pixels) exceeds this (default 12)           */
+  const float* float_boxes_dev; /* optional [B,4] fp32 (x1, y1, width, height): de-normalise the keypoints with
+                                   these instead of the int32 boxes -- the main.py --eval path hands PostProcess the
+                                   UNROUNDED crop box (RV/datasets/speed.py:246-260, spe_clip_boxes_val)        */
 } spe_pnp_params;
 
 int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_dev, const float* log_sigma_dev,
@@ -121,6 +131,11 @@ int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_
                      int num_models, int B, int Q, const spe_pnp_params* params, double* quat_dev /*[B,4]*/,
                      double* tvec_dev /*[B,3]*/, int32_t* count_dev /*[B,11]*/, int32_t* status_dev /*[B]*/,
                      float* pooled_px_dev /*[B,11,2] or NULL*/, int32_t* inlier_mask_dev /*[B] or NULL*/, void* stream);
+
+/* replaces: speed_score (RV/utils/speed_eval.py:245-262) for a batch that stays on the device: score_t = |t^ - t| / |t|,
+ * score_q = 2 acos(min(|q^ . q|, 1)); all arrays float64, quaternions (w,x,y,z) */
+int spe_speed_score(spe_ctx* ctx, const double* quat_pr_dev, const double* tvec_pr_dev, const double* quat_gt_dev,
+                    const double* tvec_gt_dev, int B, double* score_t_dev, double* score_q_dev, void* stream);
 
 /* ---- whole path, host buffers in, host buffers out ---------------------------------------------------------- */
 /* replaces the hot loop of gen_submission (RV/gen_submission_single.py:136-181): frames + detector boxes in

@@ -92,3 +92,34 @@ def bicubic_f64(canvas_gray, R):
     hz = (im[:, idx] * w[None]).sum(-1)
     out = (hz[idx] * w[:, :, None]).sum(1)
     return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# main.py --eval path (SpeedTrain with train=False), RV/datasets/speed.py:209-260
+# ----------------------------------------------------------------------------------------------------------
+def generate_clip_bbox_val(bbox, image_size):
+    """RV/datasets/speed.py:246-260: centre +- 0.6 max(w, h), clipped to the frame; float64[4], generally not square."""
+    x1, y1, x2, y2 = [float(v) for v in bbox]
+    bbox_width, bbox_height = x2 - x1, y2 - y1
+    scale = max(bbox_width, bbox_height) * 1.2
+    x_center, y_center = (x1 + x2) / 2, (y1 + y2) / 2
+    half_scale = scale / 2
+    bbox_clip = np.asarray([x_center - half_scale, y_center - half_scale, x_center + half_scale, y_center + half_scale])
+    bbox_clip[0::2] = bbox_clip[0::2].clip(min=0, max=image_size[0])
+    bbox_clip[1::2] = bbox_clip[1::2].clip(min=0, max=image_size[1])
+    return bbox_clip
+
+
+def eval_crop_resize_u8(gray, bbox_clip, R):
+    """:219-230: ``np.array(img.crop(bbox_clip))`` (PIL rounds every coordinate with ``round``) then
+    ``A.Resize(R, R, cv2.INTER_CUBIC)``.  The random ``img_trunc`` (:230, applied even in eval) is left out: it
+    depends on numpy's global RNG state."""
+    from PIL import Image
+    img = Image.fromarray(gray).convert("RGB")
+    crop = np.array(img.crop(bbox_clip))
+    return cv2.resize(crop, (R, R), interpolation=cv2.INTER_CUBIC)
+
+
+def eval_crop_resize_normalize(gray, det_bbox, R):
+    bbox_clip = generate_clip_bbox_val(det_bbox, (gray.shape[1], gray.shape[0]))
+    return normalize_u8(eval_crop_resize_u8(gray, bbox_clip, R)), bbox_clip

@@ -155,6 +155,46 @@ def write_crop(rv_speed):
     print("crop cases", len(idx), "sides", [int(c[2] - c[0]) for c in clips])
 
 
+def write_crop_eval(rv_speed):
+    """main.py --eval crop: the reference's own SpeedTrain(train=False).__getitem__ (RV/datasets/speed.py:209-244) with
+    its random ``img_trunc`` switched off, against the oracle restatement; uint8 crops + boxes are committed."""
+    from PIL import Image
+    idx, det = crop_case_boxes()
+    idx, det = idx[:10], det[:10]
+    frames = synth.make_frames(len(idx), det, seed=0)
+    R = 224
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "annos")); os.makedirs(os.path.join(tmp, "images"))
+        anns = []
+        for i in range(len(idx)):
+            fn = f"img{i:06d}.png"
+            Image.fromarray(frames[i]).save(os.path.join(tmp, "images", fn))
+            anns.append({"filename": fn, "landmarks": np.zeros((11, 3)).tolist(), "bbox_xxyy": list(det[i])})
+        with open(os.path.join(tmp, "annos", "a.json"), "w") as f:
+            json.dump(anns, f)
+        np.savetxt(os.path.join(tmp, "annos", "idx.txt"), np.arange(len(idx)), fmt="%d")
+        rv_speed.DATA_ROOT = tmp
+        rv_speed.img_trunc = lambda img, **kw: img            # np.random-driven blackout, applied even in eval (:230)
+
+        class T:                                              # make_transforms(False): A.Resize only (keypoints pass through)
+            def __call__(self, image, keypoints):
+                import cv2
+                return {"image": cv2.resize(image, (R, R), interpolation=cv2.INTER_CUBIC), "keypoints": keypoints}
+        ds = rv_speed.SpeedTrain("a.json", "idx.txt", "images", resize=R, train=False, transforms=T())
+        u8s, fboxes = [], []
+        for i in range(len(ds)):
+            img, target = ds[i]
+            fbox = target["clip_bbox"].numpy()
+            want = crop_ref.generate_clip_bbox_val(det[i], (1920, 1200))
+            assert np.array_equal(fbox, want), (fbox, want)
+            u8 = crop_ref.eval_crop_resize_u8(frames[i], fbox, R)
+            assert torch.equal(img, crop_ref.normalize_u8(u8)), f"oracle eval crop != reference for case {i}"
+            u8s.append(u8[:, :, 0]); fboxes.append(fbox)
+    np.savez_compressed(os.path.join(GOLDEN, "crop_eval_golden.npz"), box_index=idx, det_boxes=det,
+                        float_boxes=np.stack(fboxes), crops_u8=np.stack(u8s), input_size=R, frame_seed=0)
+    print("eval crop cases", len(idx), "sizes", [(int(round(b[2]) - round(b[0])), int(round(b[3]) - round(b[1]))) for b in fboxes])
+
+
 def write_model():
     out = {}
     for name, (kw, B, R, seed) in MODEL_CASES.items():
@@ -257,6 +297,7 @@ def main():
     write_boxes()
     rv_speed, rv_eval = import_rv_dataset_and_solver()
     write_crop(rv_speed)
+    write_crop_eval(rv_speed)
     write_model()
     write_pnp(rv_eval)
     write_pnp_multi(rv_eval)

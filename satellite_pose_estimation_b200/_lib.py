@@ -22,7 +22,7 @@ class SpeTensorDesc(C.Structure):
 
 class SpePnpParams(C.Structure):
     _fields_ = [("reproj_thresh", C.c_float), ("weighted", C.c_int), ("reject", C.c_int),
-                ("reject_rms_px", C.c_float), ("reject_sigma_px", C.c_float)]
+                ("reject_rms_px", C.c_float), ("reject_sigma_px", C.c_float), ("float_boxes_dev", C.c_void_p)]
 
 
 # every symbol include/spe.h declares: (restype, argtypes)
@@ -35,6 +35,8 @@ SYMBOLS = {
     "spe_load_weights": (_i, [_vp, C.POINTER(SpeTensorDesc), _i]),
     "spe_sync": (_i, [_vp, _vp]),
     "spe_clip_boxes": (_i, [_vp, _i, _vp]),
+    "spe_clip_boxes_val": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "spe_speed_score": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "spe_crop_resize_norm": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _i, _i, _vp, _vp]),
     "spe_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spe_assign_pnp": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp, _vp,

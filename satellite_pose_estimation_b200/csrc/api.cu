@@ -1,3 +1,4 @@
+#include <cmath>
 // C-ABI entry points for the crop and pose stages, the host-buffer pipeline and the bring-up hooks.
 // (ctx lifetime, weights and spe_forward live in model.cu.)
 #include "spe_internal.h"
@@ -112,6 +113,27 @@ int spe_clip_boxes(const double* det, int B, int32_t* boxes) {
   return SPE_OK;
 }
 
+int spe_clip_boxes_val(const double* det, int B, int W, int H, double* fbox, int32_t* ibox) {
+  if (!det || !fbox || !ibox || B < 0) return set_error(nullptr, SPE_ERR_INVALID, "spe_clip_boxes_val: null argument");
+  for (int i = 0; i < B; ++i) {
+    // SpeedTrain.generate_clip_bbox_val, RV/datasets/speed.py:246-260 (float64; x clipped to [0,W], y to [0,H])
+    const double x1 = det[4 * i + 0], y1 = det[4 * i + 1], x2 = det[4 * i + 2], y2 = det[4 * i + 3];
+    const double bw = x2 - x1, bh = y2 - y1;
+    const double scale = (bw > bh ? bw : bh) * 1.2;
+    const double xc = (x1 + x2) / 2, yc = (y1 + y2) / 2;
+    const double half = scale / 2;
+    double b[4] = {xc - half, yc - half, xc + half, yc + half};
+    for (int k = 0; k < 4; ++k) {
+      const double hi = (k & 1) ? static_cast<double>(H) : static_cast<double>(W);
+      b[k] = b[k] < 0.0 ? 0.0 : (b[k] > hi ? hi : b[k]);
+      fbox[4 * i + k] = b[k];
+      // PIL.Image.crop: int(round(v)) -- Python's round() is round-half-to-even, like nearbyint in the default mode
+      ibox[4 * i + k] = static_cast<int32_t>(nearbyint(b[k]));
+    }
+  }
+  return SPE_OK;
+}
+
 int spe_crop_resize_norm(spe_ctx* ctx, const uint8_t* frames_dev, int H, int W, long long pitch,
                          long long frame_stride, const int32_t* boxes_dev, int B, int R, float* out_nchw_dev,
                          void* stream) {
@@ -135,6 +157,7 @@ int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_de
     return set_error(ctx, SPE_ERR_INVALID, "spe_assign_pnp: weighted solve needs log_sigma");
   PnpDesc d{};
   d.logits = logits_dev; d.points = points_dev; d.logsig = log_sigma_dev; d.boxes = boxes_dev;
+  d.boxes_f = params->float_boxes_dev;
   d.B = B; d.Q = Q;
   d.reproj_thresh = params->reproj_thresh;
   d.weighted = params->weighted;
@@ -145,6 +168,17 @@ int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_de
   d.probs = probs_dev; d.points_px = points_px_dev; d.sigmas = sigmas_dev; d.inlier_mask = inlier_mask_dev;
   std::string s = launch_assign_pnp(d, static_cast<cudaStream_t>(stream));
   if (!s.empty()) return set_error(ctx, SPE_ERR_CUDA, "spe_assign_pnp: " + s);
+  return SPE_OK;
+}
+
+int spe_speed_score(spe_ctx* ctx, const double* quat_pr_dev, const double* tvec_pr_dev, const double* quat_gt_dev,
+                    const double* tvec_gt_dev, int B, double* score_t_dev, double* score_q_dev, void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_speed_score: null ctx");
+  if (!quat_pr_dev || !tvec_pr_dev || !quat_gt_dev || !tvec_gt_dev || !score_t_dev || !score_q_dev)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_speed_score: null buffer");
+  std::string s = launch_speed_score(quat_pr_dev, tvec_pr_dev, quat_gt_dev, tvec_gt_dev, B, score_t_dev, score_q_dev,
+                                     static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(ctx, SPE_ERR_CUDA, "spe_speed_score: " + s);
   return SPE_OK;
 }
 
@@ -159,6 +193,7 @@ int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_
   if (params->weighted) return set_error(ctx, SPE_ERR_INVALID, "spe_ensemble_pnp: the ensemble solver has no sigma-weighted form");
   PnpDesc d{};
   d.logits = logits_dev; d.points = points_dev; d.logsig = nullptr; d.boxes = boxes_dev;
+  d.boxes_f = params->float_boxes_dev;
   d.B = B; d.Q = Q; d.num_models = num_models;
   d.reproj_thresh = params->reproj_thresh;
   d.reject = params->reject;

@@ -38,14 +38,15 @@ crop_resize_norm_kernel(const uint8_t* __restrict__ frames, int H, int W, long l
 
   const int x1 = boxes[b * 4 + 0];
   const int y1 = boxes[b * 4 + 1];
-  const int S = boxes[b * 4 + 2] - x1;  // square canvas side (reference: clip_size)
+  // canvas extent: square (clip_size) on the submission path, any rectangle on the eval path (PIL crop squashed to R x R)
+  const int S = boxes[b * 4 + 2] - x1;
+  const int Sy = boxes[b * 4 + 3] - y1;
   const uint8_t* frame = frames + static_cast<long long>(b) * frame_stride;
 
   float v = 0.0f;
-  if (S > 0) {
-    const double scale = static_cast<double>(S) / static_cast<double>(R);
-    const double fx = (ox + 0.5) * scale - 0.5;
-    const double fy = (oy + 0.5) * scale - 0.5;
+  if (S > 0 && Sy > 0) {
+    const double fx = (ox + 0.5) * (static_cast<double>(S) / static_cast<double>(R)) - 0.5;
+    const double fy = (oy + 0.5) * (static_cast<double>(Sy) / static_cast<double>(R)) - 0.5;
     const double flx = floor(fx), fly = floor(fy);
     const int sx = static_cast<int>(flx), sy = static_cast<int>(fly);
     double wx[4], wy[4];
@@ -66,7 +67,7 @@ crop_resize_norm_kernel(const uint8_t* __restrict__ frames, int H, int W, long l
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int c = sy - 1 + j;
-      c = c < 0 ? 0 : (c > S - 1 ? S - 1 : c);
+      c = c < 0 ? 0 : (c > Sy - 1 ? Sy - 1 : c);
       const int gy = y1 + c;
       double row = 0.0;
       if (gy >= 0 && gy < H) {

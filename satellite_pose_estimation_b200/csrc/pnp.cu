@@ -442,9 +442,19 @@ assign_pnp_kernel(const PnpDesc d) {
 
   const float* lg = d.logits + static_cast<long long>(img) * Q * 12;
   const float* pt = d.points + static_cast<long long>(img) * Q * 2;
-  const int bx1 = d.boxes[img * 4 + 0], by1 = d.boxes[img * 4 + 1];
-  const float bw = static_cast<float>(d.boxes[img * 4 + 2] - bx1);
-  const float bh = static_cast<float>(d.boxes[img * 4 + 3] - by1);
+  // PostProcess multiplies the fp32 points by the box extent and adds the box origin, all in fp32 (a 0-dim int64 or
+  // float64 box tensor is cast to the points' dtype first): the int boxes of the submission path, or the unrounded
+  // float box of the eval path
+  float bx1, by1, bw, bh;
+  if (d.boxes_f) {
+    bx1 = d.boxes_f[img * 4 + 0]; by1 = d.boxes_f[img * 4 + 1];
+    bw = d.boxes_f[img * 4 + 2]; bh = d.boxes_f[img * 4 + 3];
+  } else {
+    const int ix1 = d.boxes[img * 4 + 0], iy1 = d.boxes[img * 4 + 1];
+    bx1 = static_cast<float>(ix1); by1 = static_cast<float>(iy1);
+    bw = static_cast<float>(d.boxes[img * 4 + 2] - ix1);
+    bh = static_cast<float>(d.boxes[img * 4 + 3] - iy1);
+  }
 
   const long long t_start = clock64();
   if (warp == 0 && d.num_models > 0) {
@@ -454,8 +464,8 @@ assign_pnp_kernel(const PnpDesc d) {
     auto pixel = [&](int e, float& px, float& py) {
       const int m = e / Q, q = e - m * Q;
       const float* p2 = d.points + ((static_cast<long long>(m) * d.B + img) * Q + q) * 2;
-      px = __fadd_rn(__fmul_rn(p2[0], bw), static_cast<float>(bx1));     // PostProcess, fp32, unfused
-      py = __fadd_rn(__fmul_rn(p2[1], bh), static_cast<float>(by1));
+      px = __fadd_rn(__fmul_rn(p2[0], bw), bx1);     // PostProcess, fp32, unfused
+      py = __fadd_rn(__fmul_rn(p2[1], bh), by1);
     };
     for (int e = lane; e < NQ; e += 32) {
       const int m = e / Q, q = e - m * Q;
@@ -580,8 +590,8 @@ assign_pnp_kernel(const PnpDesc d) {
       }
       if (d.points_px) {
         // fp32 multiply then add, unfused, exactly like `pt[:, 0] * width + x1` on float32 tensors
-        d.points_px[gq * 2 + 0] = __fadd_rn(__fmul_rn(pt[q * 2 + 0], bw), static_cast<float>(bx1));
-        d.points_px[gq * 2 + 1] = __fadd_rn(__fmul_rn(pt[q * 2 + 1], bh), static_cast<float>(by1));
+        d.points_px[gq * 2 + 0] = __fadd_rn(__fmul_rn(pt[q * 2 + 0], bw), bx1);
+        d.points_px[gq * 2 + 1] = __fadd_rn(__fmul_rn(pt[q * 2 + 1], bh), by1);
       }
       if (d.sigmas && d.logsig) {
         d.sigmas[gq * 2 + 0] = expf(d.logsig[gq * 2 + 0]);
@@ -610,8 +620,8 @@ assign_pnp_kernel(const PnpDesc d) {
         d.assign[img * 11 + l] = present ? qi : -1;
         if (present) {
           s_lab[n] = l;
-          const float px = __fadd_rn(__fmul_rn(pt[qi * 2 + 0], bw), static_cast<float>(bx1));
-          const float py = __fadd_rn(__fmul_rn(pt[qi * 2 + 1], bh), static_cast<float>(by1));
+          const float px = __fadd_rn(__fmul_rn(pt[qi * 2 + 0], bw), bx1);
+          const float py = __fadd_rn(__fmul_rn(pt[qi * 2 + 1], bh), by1);
           s_uv[2 * n] = static_cast<double>(px);
           s_uv[2 * n + 1] = static_cast<double>(py);
           // bearing of the correspondence
@@ -761,7 +771,34 @@ assign_pnp_kernel(const PnpDesc d) {
   write_out(st);
 }
 
+// speed_score, RV/utils/speed_eval.py:245-262
+__global__ void speed_score_kernel(const double* __restrict__ q_pr, const double* __restrict__ t_pr,
+                                   const double* __restrict__ q_gt, const double* __restrict__ t_gt, int B,
+                                   double* __restrict__ s_t, double* __restrict__ s_q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const double sp = q_pr[4 * i] < 0 ? -1.0 : 1.0, sg = q_gt[4 * i] < 0 ? -1.0 : 1.0;
+  double dot = 0.0, dn = 0.0, gn = 0.0;
+  for (int k = 0; k < 4; ++k) dot += (sp * q_pr[4 * i + k]) * (sg * q_gt[4 * i + k]);
+  for (int k = 0; k < 3; ++k) {
+    const double e = t_pr[3 * i + k] - t_gt[3 * i + k];
+    dn += e * e;
+    gn += t_gt[3 * i + k] * t_gt[3 * i + k];
+  }
+  s_t[i] = sqrt(dn) / sqrt(gn);
+  s_q[i] = 2.0 * acos(fmin(fabs(dot), 1.0));
+}
+
 }  // namespace
+
+std::string launch_speed_score(const double* q_pr, const double* t_pr, const double* q_gt, const double* t_gt, int B,
+                               double* s_t, double* s_q, cudaStream_t s) {
+  if (B <= 0) return "";
+  ProfScope ps(kFamPnp, s);
+  speed_score_kernel<<<(B + 127) / 128, 128, 0, s>>>(q_pr, t_pr, q_gt, t_gt, B, s_t, s_q);
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
 
 std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s) {
   if (d.B <= 0) return "";

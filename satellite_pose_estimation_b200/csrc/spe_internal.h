@@ -108,6 +108,7 @@ struct PnpDesc {
   const float* points;   // [B,Q,2] normalised crop coordinates
   const float* logsig;   // [B,Q,2] or null
   const int32_t* boxes;  // [B,4] crop boxes x1,y1,x2,y2
+  const float* boxes_f;  // or [B,4] fp32 x1,y1,width,height (eval path: unrounded box); takes precedence when set
   int B, Q;
   float reproj_thresh;
   int weighted;
@@ -130,6 +131,8 @@ struct PnpDesc {
   float* pooled_px;      // [B,11,2] or null: the pooled keypoints in original-image pixels (0 where absent)
 };
 std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s);
+std::string launch_speed_score(const double* q_pr, const double* t_pr, const double* q_gt, const double* t_gt, int B,
+                               double* s_t, double* s_q, cudaStream_t s);
 
 #define SPE_CUDA_TRY(expr)                                                                     \
   do {                                                                                         \

@@ -88,6 +88,26 @@ class Engine:
         check(self.lib.spe_clip_boxes(det.ctypes.data_as(C.c_void_p), det.shape[0], out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def clip_boxes_val(self, det_boxes, W=1920, H=1200):
+        """``main.py --eval`` crop boxes (RV/datasets/speed.py:246-260 + PIL's rounding): returns (float64 [B,4] unrounded
+        boxes -- what PostProcess de-normalises with --, int32 [B,4] pixel rectangles for ``crop_resize_norm``)."""
+        det = np.ascontiguousarray(np.asarray(det_boxes, dtype=np.float64).reshape(-1, 4))
+        fbox = np.empty((det.shape[0], 4), dtype=np.float64)
+        ibox = np.empty((det.shape[0], 4), dtype=np.int32)
+        check(self.lib.spe_clip_boxes_val(det.ctypes.data_as(C.c_void_p), det.shape[0], int(W), int(H),
+                                          fbox.ctypes.data_as(C.c_void_p), ibox.ctypes.data_as(C.c_void_p)))
+        return fbox, ibox
+
+    def speed_score(self, quat_pr, tvec_pr, quat_gt, tvec_gt):
+        """Batched ``speed_score`` (RV/utils/speed_eval.py:245-262) on device: float64 cuda [B,4] / [B,3] -> (s_t, s_q)."""
+        q, t, qg, tg = (x.to(torch.float64).contiguous() for x in (quat_pr, tvec_pr, quat_gt, tvec_gt))
+        B = q.shape[0]
+        s_t = torch.empty((B,), dtype=torch.float64, device=q.device)
+        s_q = torch.empty((B,), dtype=torch.float64, device=q.device)
+        check(self.lib.spe_speed_score(self._ctx, _ptr(q), _ptr(t), _ptr(qg), _ptr(tg), B, _ptr(s_t), _ptr(s_q),
+                                       _stream(q.device)), self._ctx)
+        return s_t, s_q
+
     def crop_resize_norm(self, frames, boxes, out=None, R=None):
         """frames: uint8 cuda [B,H,W]; boxes: int32 cuda [B,4] -> float32 cuda [B,3,R,R]."""
         R = R or self.R
@@ -150,8 +170,14 @@ class Engine:
     # ---- stage 3 ---------------------------------------------------------------------------------------------
     def assign_pnp(self, logits, points, boxes, log_sigma=None, reproj=20.0, weighted=False, reject=False,
                    reject_rms_px=5.0, reject_sigma_px=12.0, want_post=False):
-        """Batched PostProcess + assignment + PnP.  All inputs cuda; returns dict of cuda tensors."""
+        """Batched PostProcess + assignment + PnP.  All inputs cuda; returns dict of cuda tensors.  Integer ``boxes``
+        are the submission path's crop boxes; floating-point ``boxes`` [B,4] (x1,y1,x2,y2) are the eval path's
+        unrounded boxes (``clip_boxes_val``), applied like PostProcess applies a float64 ``clip_bbox``."""
         logits = logits.contiguous().float(); points = points.contiguous().float()
+        fbox = None
+        if boxes.is_floating_point():
+            b64 = boxes.to(torch.float64)
+            fbox = torch.stack([b64[:, 0], b64[:, 1], b64[:, 2] - b64[:, 0], b64[:, 3] - b64[:, 1]], 1).float().contiguous()
         boxes = boxes.to(torch.int32).contiguous()
         B, Q = logits.shape[0], logits.shape[1]
         dev = logits.device
@@ -169,7 +195,8 @@ class Engine:
         if log_sigma is not None:
             log_sigma = log_sigma.contiguous().float()
         p = SpePnpParams(reproj_thresh=float(reproj), weighted=int(weighted), reject=int(reject),
-                         reject_rms_px=float(reject_rms_px), reject_sigma_px=float(reject_sigma_px))
+                         reject_rms_px=float(reject_rms_px), reject_sigma_px=float(reject_sigma_px),
+                         float_boxes_dev=fbox.data_ptr() if fbox is not None else None)
         check(self.lib.spe_assign_pnp(self._ctx, _ptr(logits), _ptr(points), _ptr(log_sigma), _ptr(boxes), B, Q,
                                       C.byref(p), _ptr(quat), _ptr(tvec), _ptr(assign), _ptr(status), _ptr(probs),
                                       _ptr(pts_px), _ptr(sig), _ptr(inl), _stream(dev)), self._ctx)

@@ -60,6 +60,25 @@ def test_clip_boxes_bit_exact_on_every_reference_box(lib):
     assert (out == np.stack([crop_ref.generate_clip_bbox(b) for b in neg])).all()
 
 
+def test_eval_path_boxes_bit_exact_on_every_reference_box(lib):
+    """main.py --eval crop boxes (RV/datasets/speed.py:246-260): the float64 box and its PIL rounding
+    (``int(round(v))``, half to even) for every detector box the reference ships."""
+    from oracle import crop_ref, synth
+    for name in ("wz_synt_test_boxes.npy", "wz_real_test_boxes.npy"):
+        det = np.load(os.path.join(synth.GOLDEN_DIR, name))
+        fb = np.empty((len(det), 4), dtype=np.float64); ib = np.empty((len(det), 4), dtype=np.int32)
+        assert lib.spe_clip_boxes_val(det.ctypes.data_as(C.c_void_p), len(det), 1920, 1200,
+                                      fb.ctypes.data_as(C.c_void_p), ib.ctypes.data_as(C.c_void_p)) == 0
+        ref = np.stack([crop_ref.generate_clip_bbox_val(b, (1920, 1200)) for b in det])
+        assert np.array_equal(fb, ref)
+        assert np.array_equal(ib, np.asarray([[int(round(v)) for v in r] for r in ref]))
+    half = np.array([[100.0, 100.0, 105.0, 105.0], [0.5, 0.5, 3.0, 3.0]])      # x.5 coordinates: ties go to even
+    fb = np.empty((2, 4)); ib = np.empty((2, 4), dtype=np.int32)
+    lib.spe_clip_boxes_val(half.ctypes.data_as(C.c_void_p), 2, 1920, 1200, fb.ctypes.data_as(C.c_void_p),
+                           ib.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(ib, np.asarray([[int(round(v)) for v in r] for r in fb])) and ib[0].tolist() == [100, 100, 106, 106]
+
+
 def test_no_cpu_fallback(lib):
     """Without a GPU the product path fails loudly instead of computing on the CPU."""
     if torch.cuda.is_available():

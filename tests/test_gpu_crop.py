@@ -88,3 +88,24 @@ def test_crop_other_input_size(eng):
         ref, _ = crop_ref.crop_resize_normalize(frames[i], det[i], 256)
         d = (out[i] - ref).abs()
         assert d.max() <= LSB * 1.001 and (d > 1e-6).float().mean() <= 2e-4
+
+
+def test_eval_path_crop_matches_reference_golden(eng):
+    """main.py --eval crop (non-square PIL rectangle squashed to R x R, RV/datasets/speed.py:219-236) against the
+    reference's own SpeedTrain(train=False) output."""
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "crop_eval_golden.npz"))
+    det = g["det_boxes"]
+    frames = synth.make_frames(len(det), det, seed=int(g["frame_seed"]))
+    fbox, ibox = eng.clip_boxes_val(det)
+    assert np.array_equal(fbox, g["float_boxes"])
+    out = eng.crop_resize_norm(torch.from_numpy(frames).cuda(), torch.from_numpy(ibox).cuda(), R=int(g["input_size"]))
+    torch.cuda.synchronize()
+    out = out.cpu()
+    bad = tot = 0
+    for i in range(len(det)):
+        gold = crop_ref.normalize_u8(np.repeat(g["crops_u8"][i][:, :, None], 3, 2))
+        d = (out[i] - gold).abs()
+        assert d.max() <= LSB * 1.001, f"case {i}: more than one uint8 step off"
+        bad += int((d > 1e-6).sum()); tot += d.numel()
+    assert bad / tot <= 1e-4, f"{bad}/{tot} values differ from cv2"
+    assert any(ibox[i, 2] - ibox[i, 0] != ibox[i, 3] - ibox[i, 1] for i in range(len(det)))   # non-square cases present

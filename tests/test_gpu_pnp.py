@@ -204,3 +204,28 @@ def test_single_image_solver_interface(eng):
         assert np.degrees(s_q) < ROT_TOL_DEG and s_t < TRA_TOL
     with pytest.raises(IndexError):
         s(res[0]["points"][:2], res[0]["logits"][:2])
+
+
+def test_eval_path_float_boxes_and_speed_score(eng):
+    """main.py --eval hands PostProcess the UNROUNDED float64 crop box: fp32 `pt * width + x1` with the box cast to
+    fp32 first (bit-exact with the torch ops of RV/models/detr_speed.py:275-291); plus the batched speed_score."""
+    d = synth.make_predictions(300, seed=21)
+    rng = np.random.default_rng(3)
+    fb = d["boxes"].astype(np.float64) + rng.uniform(-0.49, 0.49, d["boxes"].shape)      # unrounded boxes
+    r = eng.assign_pnp(torch.from_numpy(d["logits"]).cuda(), torch.from_numpy(d["points"]).cuda(),
+                       torch.from_numpy(fb).cuda(), want_post=True)
+    torch.cuda.synchronize()
+    r = {k: v.cpu().numpy() for k, v in r.items()}
+    res = pnp_ref.post_process(d["logits"], d["points"], [torch.from_numpy(b) for b in fb])
+    solver = pnp_ref.SimplePoseSolver(20)
+    for i in range(300):
+        assert np.array_equal(r["points_px"][i], res[i]["points"])
+        assert np.array_equal(r["assign"][i], pnp_ref.assign_table(res[i]["points"], res[i]["logits"]))
+    ok = r["status"] == 0
+    q_gt, t_gt = torch.from_numpy(d["q_gt"]).cuda(), torch.from_numpy(d["t_gt"]).cuda()
+    s_t, s_q = eng.speed_score(torch.from_numpy(r["quat"]).cuda(), torch.from_numpy(r["tvec"]).cuda(), q_gt, t_gt)
+    s_t, s_q = s_t.cpu().numpy(), s_q.cpu().numpy()
+    for i in np.nonzero(ok)[0][:100]:
+        rt, rq = pnp_ref.speed_score(r["quat"][i], r["tvec"][i], d["q_gt"][i], d["t_gt"][i])
+        assert abs(s_t[i] - rt) < 1e-14 and abs(s_q[i] - rq) < 1e-9, (i, s_t[i], rt, s_q[i], rq)
+    assert np.median(s_t[ok]) < 0.01 and np.median(s_q[ok]) < 0.02            # the synthetic poses are recovered

@@ -51,6 +51,24 @@ def test_crop_out_of_frame_is_black_before_normalise():
 
 
 # --------------------------------------------------------------------------------------------------------- model
+def test_eval_crop_oracle_matches_reference_golden():
+    """main.py --eval crop restatement vs the reference's own SpeedTrain(train=False) output (golden)."""
+    from oracle.make_golden import crop_case_boxes
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "crop_eval_golden.npz"))
+    idx, det = crop_case_boxes()
+    idx, det = idx[:len(g["box_index"])], det[:len(g["box_index"])]
+    assert np.array_equal(idx, g["box_index"])
+    frames = synth.make_frames(len(idx), det, seed=int(g["frame_seed"]))
+    shapes = set()
+    for i in range(len(idx)):
+        fbox = crop_ref.generate_clip_bbox_val(det[i], (1920, 1200))
+        assert np.array_equal(fbox, g["float_boxes"][i])
+        u8 = crop_ref.eval_crop_resize_u8(frames[i], fbox, int(g["input_size"]))
+        assert np.array_equal(u8[:, :, 0], g["crops_u8"][i]) and np.array_equal(u8[:, :, 0], u8[:, :, 2])
+        shapes.add(round(fbox[2]) - round(fbox[0]) == round(fbox[3]) - round(fbox[1]))
+    assert shapes == {True, False}                      # square and non-square (clipped / rounded) crops both covered
+
+
 @pytest.mark.parametrize("case", list(MODEL_CASES))
 def test_model_oracle_matches_reference_golden(case):
     g = np.load(os.path.join(G, "model_golden.npz"))
