@@ -338,7 +338,7 @@ def run_b200(args):
         if os.path.exists(tpath):          # DRAM bytes per GEMM launch from the committed ncu capture (not measured live)
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["bytes_per_launch"], tj["source"]
-        roofline = {"bound": "tensor", "kernel": "gemm_tc / gemm_tc2 / conv3_tc / ffn_tc kernels (tcgen05 kind::tf32: all convolutions and linear layers)",
+        roofline = {"bound": "tensor", "kernel": "gemm_tc / gemm_tc2 / conv3_tc / ffn_tc2 kernels (tcgen05 kind::tf32: all convolutions and linear layers)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
                     "traffic_source": traffic_src,
                     "peak_source": peak_src, "launches_per_step": fam_n["gemm"] // prof_steps,
@@ -360,12 +360,15 @@ def run_b200(args):
                 lat.append(a.elapsed_time(b))
         p50 = statistics.median(lat)
 
-        # ---- CPU baseline: bounded sample of the same workload on this box's host cores
-        n_cpu = 32
-        cpu_path = CpuPath(n_cpu)
-        cpu_v, cores = n_cpu / cpu_path.run(8), cpu_path.threads
-        cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} images (4 batches of 8) through cv2 crop + PyTorch-CPU forward + cv2 PnP"}
+        # ---- CPU baseline: bounded sample of the same workload on this box's host cores (N = 1 only: with more ranks
+        # the other processes spin in their NCCL barrier on the same cores and the number means nothing)
+        cpu = None
+        if world == 1:
+            n_cpu = 32
+            cpu_path = CpuPath(n_cpu)
+            cpu_v, cores = n_cpu / cpu_path.run(8), cpu_path.threads
+            cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n_cpu} images (4 batches of 8) through cv2 crop + PyTorch-CPU forward + cv2 PnP"}
 
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -63,13 +63,13 @@ def main(path):
     ends = [i for i, s in enumerate(seq) if "assign_pnp" in s[1] or "PnpDesc" in s[1]]
     a = starts[-1] if ends and ends[-1] > starts[-1] else starts[-2]
     b = min(e for e in ends if e > a)
-    FAM = ("gemm_tc_kernel", "gemm_tc2_kernel", "conv3_tc_kernel", "ffn_tc_kernel")
+    FAM = ("gemm_tc_kernel", "gemm_tc2_kernel", "conv3_tc_kernel", "ffn_tc2_kernel", "ffn_tc_kernel")
     gem = [s for s in seq[a:b + 1] if short(s[1]) in FAM]
     sch = schedule()
     assert len(gem) == len(sch), (len(gem), len(sch))
     print("| GEMM | M | N | K | us | ideal us | TFLOP/s | x ideal |\n|---|---:|---:|---:|---:|---:|---:|---:|")
     tot = tot_ideal = 0
-    tag = {"gemm_tc2_kernel": " (pair)", "conv3_tc_kernel": " (tap reuse)", "ffn_tc_kernel": ""}
+    tag = {"gemm_tc2_kernel": " (pair)", "conv3_tc_kernel": " (tap reuse)", "ffn_tc_kernel": "", "ffn_tc2_kernel": " (pair)"}
     for (name, M, N, K, res, x3, nmm), s in zip(sch, gem):
         fl = 2 * M * N * K * nmm
         by = (M * K + M * N + res) * ES if "3x3" not in name else (M * K // 9 + M * N) * ES

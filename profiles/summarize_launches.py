@@ -29,7 +29,7 @@ def load(path, extra=None):
 def short(name):
     n = re.sub(r"\(.*", "", name)
     n = re.sub(r"^.*::", "", n)
-    for fam in ("gemm_tc2_kernel", "gemm_tc_kernel", "conv3_tc_kernel", "ffn_tc_kernel"):
+    for fam in ("gemm_tc2_kernel", "gemm_tc_kernel", "conv3_tc_kernel", "ffn_tc2_kernel", "ffn_tc_kernel"):
         if fam in name:
             return fam
     return "gemm_tc_kernel" if n.strip().startswith("GemmKParams") else n.strip()
