@@ -18,6 +18,7 @@ cases = [  # name, M, N, K, relu, residual rows (0 = none, -1 = full), res_mod
     ("l1.conv3+res", 200704, 256, 64, 1, -1, 0),
     ("enc.ff1", 50176, 2048, 256, 1, 0, 0),
     ("enc.qkv+addend", 50176, 768, 256, 0, 784, 784),
+    ("enc.out+res", 50176, 256, 256, 0, -1, 0),
     ("ff1 K=32", 50176, 2048, 32, 1, 0, 0),
     ("qkv K=32", 50176, 768, 32, 0, 0, 0),
     ("N256 K=32", 401408, 256, 32, 1, 0, 0),

@@ -30,7 +30,10 @@ def _rel(got, ref):
     (2352, 768, 256, 0, 1, 784), (40, 256, 2048, 0, 1, 0), (12544, 64, 192, 1, 0, 0), (1000, 2048, 256, 1, 0, 0),
     (784 * 16, 128, 1152, 1, 0, 0),
     # CTA-pair (cta_group::2) path: N % 256 == 0, deep K; odd number of 128-row tiles, ragged tail, wrapped residual
-    (12837, 512, 1024, 1, 1, 0), (12288, 256, 2048, 0, 1, 784), (784 * 9, 256, 512, 1, 0, 0)])
+    (12837, 512, 1024, 1, 1, 0), (12288, 256, 2048, 0, 1, 784), (784 * 9, 256, 512, 1, 0, 0),
+    # A-resident CTA-pair path (K = 256, N % 256 == 0, >= 74 pair tiles): three column blocks with a wrapped addend
+    # and a ragged, odd tile count; one column block with a plain residual + ReLU; many tiles per pair
+    (19001, 768, 256, 0, 1, 784), (18944, 256, 256, 1, 1, 0), (50176, 768, 256, 0, 1, 784), (50176, 256, 256, 0, 1, 0)])
 def test_gemm(lib, cuda_dev, dt, M, N, K, relu, res, res_mod):
     torch.manual_seed(M + N + K)
     tdt = DT[dt]
