@@ -25,6 +25,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH = 64
+# --quick side measurements only (the headline line is always configs[1]: batch 64, TF32): SPE_BENCH_BATCH=256
+# SPE_BENCH_PRECISION=bf16 times BASELINE.json configs[2], SPE_BENCH_SIGMA=1 the self-assessment variant of configs[3]
+if "--quick" in sys.argv:
+    BATCH = int(os.environ.get("SPE_BENCH_BATCH", BATCH))
+PRECISION = os.environ.get("SPE_BENCH_PRECISION", "tf32") if "--quick" in sys.argv else "tf32"
+SIGMA = bool(int(os.environ.get("SPE_BENCH_SIGMA", "0"))) if "--quick" in sys.argv else False
 R = 224
 Q = 40
 WORKLOAD = ("Revisiting-Transformer ResNet-50 s8 keypoint-set predictor (224^2, Q=40, enc4/dec4, d_ff 2048), "
@@ -199,9 +205,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    eng = Engine(input_size=R, num_queries=Q, enc_layers=4, dec_layers=4, backbone="resnet50s8", precision="tf32",
-                 max_batch=BATCH, device=local)
-    eng.load_state_dict(synth.make_state_dict(model_ref.ModelCfg(), seed=0))
+    eng = Engine(input_size=R, num_queries=Q, enc_layers=4, dec_layers=4, backbone="resnet50s8", precision=PRECISION,
+                 has_sigma=SIGMA, max_batch=BATCH, device=local)
+    eng.load_state_dict(synth.make_state_dict(model_ref.ModelCfg(sigma_head=SIGMA), seed=0))
 
     # ---- synthetic inputs: each rank owns a different shard of frames / boxes (weak scaling, no collective)
     det_all = synth.load_detector_boxes()
@@ -288,7 +294,8 @@ def run_b200(args):
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms_total / args.steps, "quick": True,
+                              "ms_per_step": ms_total / args.steps, "quick": True, "batch": BATCH,
+                              "precision": PRECISION, "sigma_head": SIGMA,
                               "gpu_launches_by_family": launches}))
         if world > 1:
             dist.barrier()
