@@ -608,10 +608,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int pm = tile / p.num_n_tiles;
         const int n0 = (tile - pm * p.num_n_tiles) * BN;
         const int m_tile = 2 * pm + static_cast<int>(rank);    // may be one past the end: TMA zero-fills, nothing stored
-        int img = 0, h0 = 0;
+        int img = 0, h0 = 0, w0 = 0;
         if (p.mode == 1) {
           img = m_tile / p.tiles_per_img;
           h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
+        } else if (p.mode == 3) {
+          // im2col map: the tile is 128 CONSECUTIVE output pixels (rows and images wrap inside the TMA unit), no padded
+          // rows; a tile past the end re-reads tile 0 (nothing of it is stored)
+          const int m0 = m_tile < p.num_m_tiles ? m_tile * BM : 0;
+          img = m0 / p.HW;
+          const int rem = m0 - img * p.HW;
+          h0 = rem / p.W;
+          w0 = rem - h0 * p.W;
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, 21);
@@ -628,7 +636,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const int c0 = (kb - tap * p.kb_per_tap) * BK;
               const int r = tap / p.S;
               const int s = tap - r * p.S;
-              tma_load_4d_cg2(sa, &tmA, lead_bar, c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
+              if (p.mode == 3)
+                tma_load_im2col_4d_cg2(sa, &tmA, lead_bar, c0, w0 - p.pad, h0 - p.pad, img, static_cast<uint16_t>(s),
+                                       static_cast<uint16_t>(r));
+              else
+                tma_load_4d_cg2(sa, &tmA, lead_bar, c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
             }
             tma_load_2d_cg2(sb, &tmB, lead_bar, kb * BK, n0 + static_cast<int>(rank) * (BN / 2));
           }
@@ -684,7 +696,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       long long m_base = 0;
       int valid_rows = 0;
       if (m_tile < p.num_m_tiles) {
-        if (p.mode == 0) {
+        if (p.mode == 0 || p.mode == 3) {
           m_base = static_cast<long long>(m_tile) * BM;
           const long long rem = static_cast<long long>(p.M) - m_base;
           valid_rows = rem < BM ? static_cast<int>(rem) : BM;
@@ -964,6 +976,43 @@ EncodeTiledFn get_encode_fn(std::string* err) {
   return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+// NHWC activation as an im2col tensor map for an R x S / stride 1 convolution with symmetric padding: the bounding box of
+// base pixels is [-pad, W - 1 + pad - (S - 1)] x [-pad, H - 1 + pad - (R - 1)], i.e. exactly the output grid; one load
+// delivers `pixels` consecutive output pixels x `channels` channels, shifted by the tap offset given at issue time
+std::string encode_map_im2col(CUtensorMap* m, Dtype dt, const void* base, int C, int W, int H, int NB, int R, int S,
+                              int pad, int channels, int pixels) {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  if (!fn) return "cuTensorMapEncodeIm2col not available";
+  const long long es = static_cast<long long>(dtype_size(dt));
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(NB)};
+  cuuint64_t str[3] = {static_cast<cuuint64_t>(C * es), static_cast<cuuint64_t>(W * C * es),
+                       static_cast<cuuint64_t>(static_cast<long long>(H) * W * C * es)};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (S - 1), pad - (R - 1)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, dt == kTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                  const_cast<void*>(base), dims, str, lower, upper, static_cast<cuuint32_t>(channels),
+                  static_cast<cuuint32_t>(pixels), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeIm2col failed (" + std::to_string(static_cast<int>(r)) + ")";
+  return "";
+}
+
 std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box, int spatial_stride = 1,
                        bool swizzle_atom32 = false) {
@@ -1200,6 +1249,22 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     int hrows = BM / Wo;
     if (hrows > Ho) hrows = Ho;
     if (hrows * cs > 256 || Wo * cs > 256) return "conv: TMA box too large";
+    // CTA-pair stride-1 convolutions whose row blocks leave accumulator rows empty (28-wide maps: 4 x 28 = 112 of 128)
+    // read their A tiles through an im2col tensor map instead: 128 consecutive output pixels per tile, 12.5 % fewer
+    // tiles and, at B = 64, three waves of pair tiles instead of three and a bit
+    static const int im2col_on = getenv("SPE_CONV_IM2COL") ? atoi(getenv("SPE_CONV_IM2COL")) : 1;
+    const bool im2col = im2col_on && cg2 && cs == 1 && Ho == d.H && Wo == d.W && (hrows * Wo) % BM != 0 &&
+                        d.R <= 128 && d.S <= 128;
+    if (im2col) {
+      kp.mode = 3;
+      kp.M = d.NB * Ho * Wo;
+      kp.num_m_tiles = (kp.M + BM - 1) / BM;
+      kp.HW = Ho * Wo; kp.H = Ho; kp.W = Wo; kp.S = d.S; kp.pad = d.pad; kp.cstride = 1;
+      kp.kb_per_tap = d.C / BK;
+      kp.a_bytes = BM * 128;
+      err = encode_map_im2col(&tmA, dt, d.A, d.C, d.W, d.H, d.NB, d.R, d.S, d.pad, BK, BM);
+      if (!err.empty()) return err;
+    } else {
     kp.hrows = hrows;
     kp.tiles_per_img = (Ho + hrows - 1) / hrows;
     kp.num_m_tiles = kp.tiles_per_img * d.NB;
@@ -1220,6 +1285,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
                          static_cast<cuuint32_t>(hrows * cs), 1};
     err = encode_map(&tmA, dt, 4, d.A, dims, str, box, cs);
     if (!err.empty()) return err;
+    }
   }
   kp.num_kb = K / BK;
   kp.K = K;

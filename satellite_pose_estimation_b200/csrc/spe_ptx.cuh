@@ -286,6 +286,18 @@ __device__ __forceinline__ void tma_load_4d_cg2(void* smem_dst, const CUtensorMa
       "r"(c2), "r"(c3)
       : "memory");
 }
+// im2col-mode TMA load (tensor map from cuTensorMapEncodeIm2col): `pixelsPerColumn` consecutive OUTPUT pixels starting at
+// base pixel (w, h) of image n -- the traversal wraps over rows and images inside the map's bounding box -- each shifted
+// by the filter tap offset (off_w, off_h); out-of-tensor pixels are zero-filled (= the convolution padding)
+__device__ __forceinline__ void tma_load_im2col_4d_cg2(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr,
+                                                       int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h),
+      "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)

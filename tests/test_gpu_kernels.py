@@ -61,6 +61,9 @@ def test_gemm(lib, cuda_dev, dt, M, N, K, relu, res, res_mod):
                                             (1, 7, 64, 128), (5, 32, 128, 128), (16, 28, 256, 256), (15, 25, 512, 256),
                                             # tap-reuse kernel (Cout <= 128): odd extents, widest grid, many tiles per CTA
                                             (3, 28, 128, 128), (2, 30, 64, 128), (1, 126, 64, 64), (40, 56, 64, 64),
+                                            # im2col-TMA pair path (tiles of 128 consecutive output pixels that wrap over
+                                            # rows and images): ragged last tile, odd tile count, two column blocks
+                                            (20, 30, 256, 256), (33, 28, 256, 512), (64, 28, 512, 512),
                                             (2, 13, 128, 64)])
 def test_implicit_conv3x3(lib, cuda_dev, dt, NB, H, Cin, Cout):
     """TMA out-of-bounds zero fill == the convolution's zero padding; ragged last row-tile (H % hrows != 0)."""
