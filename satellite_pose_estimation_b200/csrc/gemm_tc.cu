@@ -369,6 +369,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.mode == 1) {
           img = m_tile / p.tiles_per_img;
           h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
+        } else if (p.mode == 3) {   // im2col map: 128 consecutive output pixels
+          const int m0 = m_tile * BM;
+          img = m0 / p.HW;
+          const int rem = m0 - img * p.HW;
+          h0 = rem / p.W;
+          x0 = rem - h0 * p.W;
         } else if (p.mode == 2) {
           img = m_tile / p.tiles_per_img;
           const int rem = m_tile - img * p.tiles_per_img;
@@ -392,7 +398,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int c0 = (kb - tap * p.kb_per_tap) * BK;
               const int r = tap / p.S;
               const int s = tap - r * p.S;
-              tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
+              if (p.mode == 3)
+                tma_load_im2col_4d(sa, &tmA, &full_bar[stage], c0, x0 * p.cstride - p.pad, h0 * p.cstride - p.pad, img,
+                                   static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+              else
+                tma_load_4d(sa, &tmA, &full_bar[stage], c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
             }
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
             if constexpr (X3) tma_load_2d(sb + Cfg::B_BYTES, &tmB, &full_bar[stage], p.K + kb * BK, n0);
@@ -481,7 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
       long long m_base;
       int valid_rows;
-      if (p.mode == 0) {
+      if (p.mode == 0 || p.mode == 3) {
         m_base = static_cast<long long>(m_tile) * BM;
         const long long rem = static_cast<long long>(p.M) - m_base;
         valid_rows = rem < BM ? static_cast<int>(rem) : BM;
@@ -637,8 +647,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const int r = tap / p.S;
               const int s = tap - r * p.S;
               if (p.mode == 3)
-                tma_load_im2col_4d_cg2(sa, &tmA, lead_bar, c0, w0 - p.pad, h0 - p.pad, img, static_cast<uint16_t>(s),
-                                       static_cast<uint16_t>(r));
+                tma_load_im2col_4d_cg2(sa, &tmA, lead_bar, c0, w0 * p.cstride - p.pad, h0 * p.cstride - p.pad, img,
+                                       static_cast<uint16_t>(s), static_cast<uint16_t>(r));
               else
                 tma_load_4d_cg2(sa, &tmA, lead_bar, c0, s - p.pad, h0 * p.cstride + r - p.pad, img);
             }
@@ -981,11 +991,12 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 
-// NHWC activation as an im2col tensor map for an R x S / stride 1 convolution with symmetric padding: the bounding box of
-// base pixels is [-pad, W - 1 + pad - (S - 1)] x [-pad, H - 1 + pad - (R - 1)], i.e. exactly the output grid; one load
-// delivers `pixels` consecutive output pixels x `channels` channels, shifted by the tap offset given at issue time
+// NHWC activation as an im2col tensor map for an R x S convolution with symmetric padding: the bounding box of base pixels
+// is [-pad, W - 1 + pad - (S - 1)] x [-pad, H - 1 + pad - (R - 1)], walked with the convolution stride, i.e. exactly the
+// output grid; one load delivers `pixels` consecutive output pixels x `channels` channels, shifted by the tap offset
+// given at issue time
 std::string encode_map_im2col(CUtensorMap* m, Dtype dt, const void* base, int C, int W, int H, int NB, int R, int S,
-                              int pad, int channels, int pixels) {
+                              int pad, int stride, int channels, int pixels) {
   static EncodeIm2colFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -1004,7 +1015,8 @@ std::string encode_map_im2col(CUtensorMap* m, Dtype dt, const void* base, int C,
                        static_cast<cuuint64_t>(static_cast<long long>(H) * W * C * es)};
   int lower[2] = {-pad, -pad};
   int upper[2] = {pad - (S - 1), pad - (R - 1)};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // traversal stride of the base pixel = convolution stride
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
   CUresult r = fn(m, dt == kTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                   const_cast<void*>(base), dims, str, lower, upper, static_cast<cuuint32_t>(channels),
                   static_cast<cuuint32_t>(pixels), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1249,20 +1261,19 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     int hrows = BM / Wo;
     if (hrows > Ho) hrows = Ho;
     if (hrows * cs > 256 || Wo * cs > 256) return "conv: TMA box too large";
-    // CTA-pair stride-1 convolutions whose row blocks leave accumulator rows empty (28-wide maps: 4 x 28 = 112 of 128)
-    // read their A tiles through an im2col tensor map instead: 128 consecutive output pixels per tile, 12.5 % fewer
-    // tiles and, at B = 64, three waves of pair tiles instead of three and a bit
+    // convolutions whose row blocks leave accumulator rows empty (28-wide maps: 4 x 28 = 112 of 128; 14-wide: 9 + 5 rows)
+    // read their A tiles through an im2col tensor map instead: 128 consecutive output pixels per tile -- 12.5 % fewer
+    // tiles at 28 x 28 (and, at B = 64, three waves of pair tiles instead of three and a bit), 23 % fewer at 14 x 14
     static const int im2col_on = getenv("SPE_CONV_IM2COL") ? atoi(getenv("SPE_CONV_IM2COL")) : 1;
-    const bool im2col = im2col_on && cg2 && cs == 1 && Ho == d.H && Wo == d.W && (hrows * Wo) % BM != 0 &&
-                        d.R <= 128 && d.S <= 128;
+    const bool im2col = im2col_on && (hrows * Wo) % BM != 0 && d.R <= 128 && d.S <= 128;
     if (im2col) {
       kp.mode = 3;
       kp.M = d.NB * Ho * Wo;
       kp.num_m_tiles = (kp.M + BM - 1) / BM;
-      kp.HW = Ho * Wo; kp.H = Ho; kp.W = Wo; kp.S = d.S; kp.pad = d.pad; kp.cstride = 1;
+      kp.HW = Ho * Wo; kp.H = Ho; kp.W = Wo; kp.S = d.S; kp.pad = d.pad; kp.cstride = cs;
       kp.kb_per_tap = d.C / BK;
       kp.a_bytes = BM * 128;
-      err = encode_map_im2col(&tmA, dt, d.A, d.C, d.W, d.H, d.NB, d.R, d.S, d.pad, BK, BM);
+      err = encode_map_im2col(&tmA, dt, d.A, d.C, d.W, d.H, d.NB, d.R, d.S, d.pad, cs, BK, BM);
       if (!err.empty()) return err;
     } else {
     kp.hrows = hrows;

@@ -289,6 +289,15 @@ __device__ __forceinline__ void tma_load_4d_cg2(void* smem_dst, const CUtensorMa
 // im2col-mode TMA load (tensor map from cuTensorMapEncodeIm2col): `pixelsPerColumn` consecutive OUTPUT pixels starting at
 // base pixel (w, h) of image n -- the traversal wraps over rows and images inside the map's bounding box -- each shifted
 // by the filter tap offset (off_w, off_h); out-of-tensor pixels are zero-filled (= the convolution padding)
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
+      "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d_cg2(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr,
                                                        int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
