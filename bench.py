@@ -324,8 +324,11 @@ def run_b200(args):
     if rank == 0:
         # ---- per-family device time of one step (CUDA events on the launch stream) -> roofline of the GEMM kernel
         eng.profile_enable(True)
+        for i in range(2):                 # the serial event-timed path has its own graph / clock state: settle first
+            step(i)
+        torch.cuda.synchronize()
         eng.profile_collect()
-        prof_steps = 3
+        prof_steps = 8
         for i in range(prof_steps):
             step(i)
         torch.cuda.synchronize()
