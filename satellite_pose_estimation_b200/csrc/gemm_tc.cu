@@ -82,6 +82,7 @@ struct GemmKParams {
   int K;               // X3: column offset of W_lo inside the [N, 2K] weight matrix
   int remap_wp;        // tap-reuse 3x3 kernel: accumulator row m' = h * remap_wp + w of a (W + 2)-wide padded grid
   int sub_rows;        // ... image rows per 128-row accumulator
+  int stem_im2col;     // mode 2 through an im2col map: tile = 128 consecutive output pixels
   uint32_t a_stage;    // ... bytes of one halo-tile stage
   int dbg;             // SPE_GEMM_DBG bit 0: skip the output stores (profiling experiments only)
 };
@@ -375,6 +376,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int rem = m0 - img * p.HW;
           h0 = rem / p.W;
           x0 = rem - h0 * p.W;
+        } else if (p.mode == 2 && p.stem_im2col) {
+          const int m0 = m_tile * BM;
+          img = m0 / p.HW;
+          const int rem = m0 - img * p.HW;
+          h0 = rem / p.W;
+          x0 = rem - h0 * p.W;
         } else if (p.mode == 2) {
           img = m_tile / p.tiles_per_img;
           const int rem = m_tile - img * p.tiles_per_img;
@@ -392,7 +399,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (p.mode == 2) {
               // k-block kb = filter row kb: 8 consecutive padded pixels x Cp channels per output pixel, windows of
               // neighbouring output pixels overlap (dim-1 stride = 2 pixels)
-              tma_load_4d(sa, &tmA, &full_bar[stage], 0, x0, 2 * h0 + kb, img);
+              if (p.stem_im2col)
+                tma_load_im2col_4d(sa, &tmA, &full_bar[stage], 0, x0, 2 * h0, img, 0, static_cast<uint16_t>(kb));
+              else
+                tma_load_4d(sa, &tmA, &full_bar[stage], 0, x0, 2 * h0 + kb, img);
             } else {
               const int tap = kb / p.kb_per_tap;
               const int c0 = (kb - tap * p.kb_per_tap) * BK;
@@ -491,7 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
       long long m_base;
       int valid_rows;
-      if (p.mode == 0 || p.mode == 3) {
+      if (p.mode == 0 || p.mode == 3 || (p.mode == 2 && p.stem_im2col)) {
         m_base = static_cast<long long>(m_tile) * BM;
         const long long rem = static_cast<long long>(p.M) - m_base;
         valid_rows = rem < BM ? static_cast<int>(rem) : BM;
@@ -995,18 +1005,33 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 // is [-pad, W - 1 + pad - (S - 1)] x [-pad, H - 1 + pad - (R - 1)], walked with the convolution stride, i.e. exactly the
 // output grid; one load delivers `pixels` consecutive output pixels x `channels` channels, shifted by the tap offset
 // given at issue time
+EncodeIm2colFn get_im2col_fn();
+
+// stem: the overlapping-window view of the padded image ({8 pixels x 4 channels} per output pixel, W stride = 2 input
+// pixels) as an im2col map: base rows 0, 2, 4, ... (traversal stride 2 in H), filter row = im2col offset in H
+std::string encode_map_im2col_stem(CUtensorMap* m, Dtype dt, const void* base, int BKe, int Wo, int Hp, int Wp, int Cp,
+                                   int NB, int pixels) {
+  EncodeIm2colFn fn = get_im2col_fn();
+  if (!fn) return "cuTensorMapEncodeIm2col not available";
+  const long long es = static_cast<long long>(dtype_size(dt));
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(BKe), static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Hp),
+                        static_cast<cuuint64_t>(NB)};
+  cuuint64_t str[3] = {static_cast<cuuint64_t>(2 * Cp * es), static_cast<cuuint64_t>(static_cast<long long>(Wp) * Cp * es),
+                       static_cast<cuuint64_t>(static_cast<long long>(Hp) * Wp * Cp * es)};
+  int lower[2] = {0, 0};
+  int upper[2] = {0, -6};
+  cuuint32_t estr[4] = {1, 1, 2, 1};
+  CUresult r = fn(m, dt == kTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                  const_cast<void*>(base), dims, str, lower, upper, static_cast<cuuint32_t>(BKe),
+                  static_cast<cuuint32_t>(pixels), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeIm2col (stem) failed (" + std::to_string(static_cast<int>(r)) + ")";
+  return "";
+}
+
 std::string encode_map_im2col(CUtensorMap* m, Dtype dt, const void* base, int C, int W, int H, int NB, int R, int S,
                               int pad, int stride, int channels, int pixels) {
-  static EncodeIm2colFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeIm2colFn>(p);
-  }
+  EncodeIm2colFn fn = get_im2col_fn();
   if (!fn) return "cuTensorMapEncodeIm2col not available";
   const long long es = static_cast<long long>(dtype_size(dt));
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
@@ -1023,6 +1048,19 @@ std::string encode_map_im2col(CUtensorMap* m, Dtype dt, const void* base, int C,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return "cuTensorMapEncodeIm2col failed (" + std::to_string(static_cast<int>(r)) + ")";
   return "";
+}
+
+EncodeIm2colFn get_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  });
+  return fn;
 }
 
 std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, const cuuint64_t* dims,
@@ -1249,8 +1287,23 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     cuuint64_t str[3] = {static_cast<cuuint64_t>(2 * Cp) * es, static_cast<cuuint64_t>(Wp) * Cp * es,
                          static_cast<cuuint64_t>(Hp) * Wp * Cp * es};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(bw), 1, 1};
-    err = encode_map(&tmA, dt, 4, d.A, dims, str, box);
-    if (!err.empty()) return "stem: " + err;
+    // output rows shorter than the tile (112 of 128): 128 consecutive output pixels per tile through an im2col view
+    static const int stem_im2col_on = getenv("SPE_STEM_IM2COL") ? atoi(getenv("SPE_STEM_IM2COL")) : 1;
+    bool stem_i2c = stem_im2col_on && Wo % BM != 0;
+    if (stem_i2c) {
+      err = encode_map_im2col_stem(&tmA, dt, d.A, BK, Wo, Hp, Wp, Cp, d.NB, BM);
+      if (err.empty()) {
+        kp.stem_im2col = 1;
+        kp.num_m_tiles = (kp.M + BM - 1) / BM;
+        kp.a_bytes = BM * 128;
+      } else {
+        stem_i2c = false;
+      }
+    }
+    if (!stem_i2c) {
+      err = encode_map(&tmA, dt, 4, d.A, dims, str, box);
+      if (!err.empty()) return "stem: " + err;
+    }
   } else {
     if (d.C % BK != 0) return "conv: C must be a multiple of the 128-byte k-block";
     const int cs = d.conv_stride > 0 ? d.conv_stride : 1;
