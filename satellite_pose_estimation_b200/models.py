@@ -93,6 +93,55 @@ class _Holder(nn.Module):
             "sub-modules of B200DETR only hold parameters; the forward pass runs as one fused schedule in libspe.so")
 
 
+def position_embedding_sine(B, H, W, hidden_dim=256, device="cpu"):
+    """``PositionEmbeddingSine.forward`` for an all-False mask (RV/models/position_encoding.py:30-53): normalised
+    cumulative coordinates x 2 pi / 10000^(2 floor(k/2)/128), sin on even / cos on odd channels, cat(y, x)."""
+    npf = hidden_dim // 2
+    ones = torch.ones((B, H, W), dtype=torch.float32, device=device)
+    y_embed, x_embed = ones.cumsum(1), ones.cumsum(2)
+    eps, scale = 1e-6, 2 * math.pi
+    y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
+    x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(npf, dtype=torch.float32, device=device)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / npf)
+    pos_x, pos_y = x_embed[:, :, :, None] / dim_t, y_embed[:, :, :, None] / dim_t
+    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+class _BackboneView(_Holder):
+    """``model.backbone(samples)`` as the reference's ``Joiner`` answers it (RV/models/backbone.py:156-165; called
+    directly by RV/get_backbone_time.py:110): ``([NestedTensor-like features], [position embedding])``.  The features are
+    read back from the fused schedule's activation taps -- a compatibility / inspection accessor, not the hot path."""
+
+    def forward(self, samples):
+        root = self.__dict__["_root"]()
+        x = root._as_batch(samples)
+        dev = root.query_embed.weight.device
+        x = x.to(device=dev, dtype=torch.float32)
+        B, R = x.shape[0], x.shape[-1]
+        eng = root._get_engine(dev, R, B)
+        if B > eng.max_batch:
+            raise ValueError(f"backbone view: batch {B} exceeds max_batch {eng.max_batch}")
+        eng.enable_taps(True)
+        try:
+            eng.forward(x)
+            torch.cuda.synchronize(dev)
+            if is_stride8(root.cfg.backbone):
+                h = R // 8
+                feat = eng.read_tap("neck", (B, h, h, 512))
+            else:
+                h = R // 16
+                feat = eng.read_tap("layer3", (B, h, h, 1024))
+        finally:
+            eng.enable_taps(False)
+        feat = feat.permute(0, 3, 1, 2).contiguous().to(dev)
+        mask = torch.zeros((B, h, h), dtype=torch.bool, device=dev)
+        pos = position_embedding_sine(B, h, h, root.cfg.hidden_dim, device=dev)
+        return [SimpleNamespace(tensors=feat, mask=mask, decompose=lambda: (feat, mask))], [pos]
+
+
 def _register(root, name, tensor, is_buffer):
     parts = name.split(".")
     mod = root
@@ -128,6 +177,9 @@ class B200DETR(nn.Module):
         self._engine = None
         self._engine_key = None
         self._weights_dirty = True
+        import weakref
+        self._modules["backbone"].__class__ = _BackboneView          # same parameters, plus the Joiner-style call
+        self._modules["backbone"].__dict__["_root"] = weakref.ref(self)
 
     @staticmethod
     def _init_tensor(name, shape, gen):

@@ -352,3 +352,26 @@ def test_baseline_configs_at_batch_256(lib, cuda_dev, precision, sigma):
     out = eng.run_batch_host(frames, det, reproj=25.0 if sigma else 20.0, weighted=sigma, reject=sigma)
     assert out["status"].shape == (B,) and np.isfinite(out["quat"]).all() and np.isfinite(out["tvec"]).all()
     eng.close()
+
+
+def test_backbone_view_like_get_backbone_time(lib, cuda_dev):
+    """``model.backbone(sample)`` (RV/get_backbone_time.py:110): features + sine position embedding as the reference's
+    Joiner returns them, against the oracle's backbone and position embedding."""
+    cfg = model_ref.ModelCfg()
+    sd = synth.make_state_dict(cfg, seed=0)
+    args = SimpleNamespace(backbone="resnet50s8", num_queries=40, enc_layers=4, dec_layers=4, hidden_dim=256, nheads=8,
+                           dim_feedforward=2048, aux_loss=False, device="cuda", repro=20, max_batch=4)
+    model, _, _ = build_model(args)
+    model.to("cuda")
+    model.load_state_dict(sd, strict=True)
+    x = model_inputs(2, 224, 3)
+    feats, pos = model.backbone(x.cuda())
+    assert len(feats) == 1 and len(pos) == 1
+    taps = {}
+    model_ref.forward(sd, cfg, x, taps)
+    f = feats[0].tensors.cpu()
+    assert f.shape == (2, 512, 28, 28) and not feats[0].mask.any()
+    assert (f - taps["neck"]).abs().max().item() / taps["neck"].abs().max().item() < 6e-3
+    assert torch.allclose(pos[0].cpu(), model_ref.position_embedding_sine(2, 28, 28), atol=1e-6)
+    out = model(x.cuda())                     # the fused forward still works after the tap round trip
+    assert out["pred_points"].shape == (2, 40, 2)
