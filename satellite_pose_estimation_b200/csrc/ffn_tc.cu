@@ -21,10 +21,10 @@
 //            multicast to both CTAs
 //   warps 2-9  thread t owns row t (tcgen05.ld layout; two warps per lane quarter split a chunk's columns):
 //            H_j = rna_tf32(relu(S_j + b1_j)) written back over S_j, reported to the leader's barrier; after the last
-//            chunk warps 2-5 run the epilogue: v = O + b2 + X (X from the resident smem tile), two-pass LayerNorm
-//            statistics over the thread's own row (no cross-thread reduction), normalise, round / split, and store
-//            through a per-warp 32 x 128-byte XOR-swizzled staging tile so that every store instruction writes four
-//            complete 128-byte lines.
+//            chunk the same eight warps run the epilogue, 128 of the 256 columns each: v = O + b2 + X (X from the
+//            resident smem tile), two-pass LayerNorm statistics (the two warps of a lane quarter exchange their partial
+//            sums through shared memory), normalise, round / split, and store through a per-warp 32 x 64-byte
+//            XOR-swizzled staging tile so that every store instruction writes eight rows x 64 contiguous bytes.
 // TMEM: S0 [0,128)  S1 [128,256)  O [256,512).  Tensor-pipe instructions retire in issue order, so S_{j+2} overwrites
 // H_j only after O += H_j W2_j^T has read it.
 //
@@ -34,7 +34,8 @@
 //   + CTA pairs, half the weight stream per SM and twice the ring depth            203 us
 //   + coalesced epilogue stores (SPE_FFN_TIMING counters: the 64 row-per-thread STG.128 of a tile -- 32 distinct lines
 //     per instruction -- took 32 k cycles, half of the tile's tensor time, during which the activation warps of the
-//     next tile's first chunks were not served)                                    see profiles/
+//     next tile's first chunks were not served)                                    170 us  (ncu r01i: tensor pipe 73 %)
+//   + epilogue on all eight row warps (half the columns each)                      165 us
 #include "spe_internal.h"
 #include "spe_ptx.cuh"
 #include "profile.h"
@@ -51,9 +52,10 @@ constexpr int kChunk = 128;         // hidden units per chunk
 constexpr int kSlab = 16384;        // 128 rows x 128 bytes
 constexpr int kEntry = 16384;       // ring entry: two W1 half k-blocks (64 x 32 each) or one W2 half k-block (128 x 32)
 constexpr int kEntries = 5;
-constexpr int kStage = 4096;        // per epilogue warp: 32 rows x 128 bytes
+constexpr int kStage = 2048;        // per row warp: 32 rows x 64 bytes (16 output columns at a time)
 constexpr int kThreads = 320;       // TMA warp, MMA warp, 8 row warps (two per TMEM lane quarter)
-constexpr int kSmemBytes = 8 * kSlab + kEntries * kEntry + 4 * kStage + 256 + 1024;
+constexpr int kXchg = 2 * kRows * 4;   // partial LayerNorm sums exchanged between the two warps of a lane quarter
+constexpr int kSmemBytes = 8 * kSlab + kEntries * kEntry + 8 * kStage + kXchg + 256 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 struct FfnParams {
@@ -97,20 +99,25 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-// One 32-row x 32-column block of the output through the warp's staging tile: thread `lane` holds row `lane` (eight
-// float4 = 128 bytes); afterwards lane l stores chunk (l & 7) of rows 4 i + (l >> 3): four whole 128-byte lines per
-// instruction.  `dst` points at (first row of the warp, first column of the block); `ld` is the row pitch in floats.
-__device__ __forceinline__ void store_block_coalesced(uint32_t stage, int lane, const float4 (&y)[8], float* dst,
-                                                      long long ld, int rows_ok) {
+// One 32-row x 16-column block of the output through the warp's 2 KB staging tile: thread `lane` holds row `lane` (four
+// float4 = 64 bytes); afterwards lane l stores chunk (l & 3) of rows 8 i + (l >> 2): eight rows x 64 contiguous bytes per
+// instruction (whole 32-byte sectors).  The 16-byte chunks are XOR-swizzled with bits 1..2 of the row so that both the
+// row-wise writes and the transposed reads are bank-conflict free.  `dst` points at (first row of the warp, first column
+// of the block), `dst2` optionally at a second copy; `ld` is the row pitch in floats.
+__device__ __forceinline__ void store_half_block(uint32_t stage, int lane, const float4* y, float* dst, float* dst2,
+                                                 long long ld, int rows_ok) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) st_shared_v4(stage + lane * 128 + ((k ^ (lane & 7)) * 16), y[k]);
+  for (int k = 0; k < 4; ++k) st_shared_v4(stage + lane * 64 + ((k ^ ((lane >> 1) & 3)) * 16), y[k]);
   __syncwarp();
-  const int kk = lane & 7;
+  const int kk = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + (lane >> 3);
-    const float4 v = ld_shared_v4(stage + r * 128 + ((kk ^ (r & 7)) * 16));
-    if (r < rows_ok) *reinterpret_cast<float4*>(dst + r * ld + kk * 4) = v;
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    const float4 v = ld_shared_v4(stage + r * 64 + ((kk ^ ((r >> 1) & 3)) * 16));
+    if (r < rows_ok) {
+      *reinterpret_cast<float4*>(dst + r * ld + kk * 4) = v;
+      if (dst2 != nullptr) *reinterpret_cast<float4*>(dst2 + r * ld + kk * 4) = v;
+    }
   }
   __syncwarp();
 }
@@ -123,16 +130,17 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // same offset in both CTAs of the pair
   uint8_t* sX = smem;                                   // [8 slabs][128 rows][128 B], SWIZZLE_128B: this CTA's rows
   uint8_t* sRing = smem + 8 * kSlab;                    // [5][16 KB]
-  uint8_t* sStage = sRing + kEntries * kEntry;          // [4][4 KB] epilogue staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 4 * kStage);
+  uint8_t* sStage = sRing + kEntries * kEntry;          // [8][2 KB] epilogue staging, one per row warp
+  float* sXchg = reinterpret_cast<float*>(sStage + 8 * kStage);   // [2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sXchg) + kXchg);
   uint64_t* x_full = bars;                              // leader only: both CTAs' X tiles landed
-  uint64_t* x_empty = bars + 1;                         // per CTA: last S MMA retired (multicast commit) + own 4 epilogue warps
+  uint64_t* x_empty = bars + 1;                         // per CTA: last S MMA retired (multicast commit) + own 8 row warps
   uint64_t* full = bars + 2;                            // [5] leader only: both halves of the entry landed
   uint64_t* empty = bars + 8;                           // [5] per CTA (multicast commit)
   uint64_t* s_full = bars + 14;                         // [2] per CTA (multicast commit)
   uint64_t* h_ready = bars + 16;                        // [2] leader only: 8 activation warps of each CTA
   uint64_t* o_full = bars + 18;                         // per CTA (multicast commit)
-  uint64_t* o_empty = bars + 19;                        // leader only: 4 epilogue warps of each CTA
+  uint64_t* o_empty = bars + 19;                        // leader only: 8 row warps of each CTA
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5;
@@ -146,11 +154,11 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     mbar_init(x_full, 1);
-    mbar_init(x_empty, 5);
+    mbar_init(x_empty, 9);
     for (int i = 0; i < kEntries; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&h_ready[i], 16); }
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 8);
+    mbar_init(o_empty, 16);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -295,7 +303,7 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int row = q * 32 + lane;                  // row of the tile this thread owns
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t xrow = smem_u32(sX) + row * 128;
-    const uint32_t stage = smem_u32(sStage) + q * kStage;
+    const uint32_t stage = smem_u32(sStage) + (warp - 2) * kStage;
     const int sw = row & 7;
     long long w_s = 0, w_of = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0, t_epi = 0;
     const long long t_begin = FFN_CLOCK();
@@ -347,23 +355,24 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         (void)a0; (void)a1; (void)a2; (void)a3;
 #endif
       }
-      if (half != 0) continue;   // the epilogue is done by one warp per lane quarter
-
-      // ---- epilogue of the tile: v = O + b2 + X, LayerNorm over the thread's own row
+      // ---- epilogue of the tile: v = O + b2 + X, LayerNorm over the row.  All eight row warps take part: the two warps
+      //      of a lane quarter split the 256 columns (128 each) and exchange their partial sums through shared memory,
+      //      which halves the time the tensor pipe waits for the O accumulator and the X tile to be released.
       mbar_wait_t(o_full, static_cast<uint32_t>(it) & 1u, 40, w_of);
       const long long e0 = FFN_CLOCK();
       tc_fence_after();
-      const uint32_t to = trow + 256u;
+      const uint32_t to = trow + 256u + static_cast<uint32_t>(half * 128);
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
+        const int cb = half * 4 + c;                 // 32-column block of the row
         uint32_t v[32];
         tmem_ld_32x32(to + static_cast<uint32_t>(c * 32), v);
         tmem_wait_ld();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float4 x4 = ld_shared_v4(xrow + c * kSlab + ((k ^ sw) * 16));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32 + 4 * k));
+          const float4 x4 = ld_shared_v4(xrow + cb * kSlab + ((k ^ sw) * 16));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + cb * 32 + 4 * k));
           const float a0 = __uint_as_float(v[4 * k]) + b4.x + x4.x;
           const float a1 = __uint_as_float(v[4 * k + 1]) + b4.y + x4.y;
           const float a2 = __uint_as_float(v[4 * k + 2]) + b4.z + x4.z;
@@ -377,11 +386,15 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tmem_wait_st();
       __syncwarp();
       if (lane == 0) mbar_arrive(x_empty);          // residual read: the producer may load the next X tile
+      sXchg[half * kRows + row] = sum;
+      named_bar_sync(1 + q, 64);                    // the two warps of this lane quarter
+      sum += sXchg[(half ^ 1) * kRows + row];
+      named_bar_sync(1 + q, 64);                    // both have read before the array is reused
       const long long e1 = FFN_CLOCK();
       const float mean = sum * (1.f / 256.f);
       float qs = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(to + static_cast<uint32_t>(c * 32), v);
         tmem_wait_ld();
@@ -394,6 +407,9 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         qs += (q0 + q1) + (q2 + q3);
       }
+      sXchg[half * kRows + row] = qs;
+      named_bar_sync(1 + q, 64);
+      qs += sXchg[(half ^ 1) * kRows + row];
       const float rstd = rsqrtf(qs * (1.f / 256.f) + 1e-5f);
       const long long e2 = FFN_CLOCK();
       const long long row0 = static_cast<long long>(tile) * kRows + q * 32;      // first row of this warp
@@ -402,15 +418,16 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const long long ld = p.out_mode == 2 ? 768 : 256;
       float* obase = p.out + row0 * ld;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = (half * 4 + c) * 32;
         uint32_t v[32];
         tmem_ld_32x32(to + static_cast<uint32_t>(c * 32), v);
         tmem_wait_ld();
         float4 y[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c * 32 + 4 * k));
-          const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.beta + c * 32 + 4 * k));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + 4 * k));
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + 4 * k));
           y[k].x = (__uint_as_float(v[4 * k]) - mean) * rstd * g4.x + e4.x;
           y[k].y = (__uint_as_float(v[4 * k + 1]) - mean) * rstd * g4.y + e4.y;
           y[k].z = (__uint_as_float(v[4 * k + 2]) - mean) * rstd * g4.z + e4.z;
@@ -424,30 +441,19 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             y[k] = make_float4(rna_tf32(y[k].x - hi[k].x), rna_tf32(y[k].y - hi[k].y), rna_tf32(y[k].z - hi[k].z),
                                rna_tf32(y[k].w - hi[k].w));
           }
-          // hi goes to columns [0,256) and [512,768): stage once, read back once, store twice
-#pragma unroll
-          for (int k = 0; k < 8; ++k) st_shared_v4(stage + lane * 128 + ((k ^ (lane & 7)) * 16), hi[k]);
-          __syncwarp();
-          const int kk = lane & 7;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
-            const float4 h = ld_shared_v4(stage + r * 128 + ((kk ^ (r & 7)) * 16));
-            if (r < rows_ok) {
-              float* o = obase + r * ld + c * 32 + kk * 4;
-              *reinterpret_cast<float4*>(o) = h;
-              *reinterpret_cast<float4*>(o + 512) = h;
-            }
-          }
-          __syncwarp();
-          store_block_coalesced(stage, lane, y, obase + 256 + c * 32, ld, rows_ok);
+          // [hi | lo | hi]: hi goes to columns [0,256) and [512,768), lo to [256,512)
+          store_half_block(stage, lane, hi, obase + col0, obase + 512 + col0, ld, rows_ok);
+          store_half_block(stage, lane, hi + 4, obase + col0 + 16, obase + 512 + col0 + 16, ld, rows_ok);
+          store_half_block(stage, lane, y, obase + 256 + col0, nullptr, ld, rows_ok);
+          store_half_block(stage, lane, y + 4, obase + 256 + col0 + 16, nullptr, ld, rows_ok);
         } else {
           if (p.out_mode == 0) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               y[k] = make_float4(rna_tf32(y[k].x), rna_tf32(y[k].y), rna_tf32(y[k].z), rna_tf32(y[k].w));
           }
-          store_block_coalesced(stage, lane, y, obase + c * 32, ld, rows_ok);
+          store_half_block(stage, lane, y, obase + col0, nullptr, ld, rows_ok);
+          store_half_block(stage, lane, y + 4, obase + col0 + 16, nullptr, ld, rows_ok);
         }
       }
       tc_fence_before();
