@@ -175,11 +175,15 @@ def run_reference(args):
         path.run(batch)
     dt = sum(path.run(batch) for _ in range(args.steps))
     v = per_step * args.steps / dt
+    # second half of the headline metric: p50 latency of ONE image through the same CPU path (BASELINE configs[0])
+    one = CpuPath(1)
+    lat = sorted(one.run(1) for _ in range(9))
+    p50_ms = lat[len(lat) // 2] * 1e3
     sample = f"{per_step} images per step (one batch of {batch}) through cv2 crop + PyTorch-CPU forward + cv2 PnP"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "p50_ms_batch1": p50_ms,
         "config": {"workload": WORKLOAD, "reference_kind": "oracle port of the reference's Python path (the Python "
                    "reference cannot travel to the GPU box)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": path.threads, "kind": "port", "sample": sample},
