@@ -229,3 +229,37 @@ def test_eval_path_float_boxes_and_speed_score(eng):
         rt, rq = pnp_ref.speed_score(r["quat"][i], r["tvec"][i], d["q_gt"][i], d["t_gt"][i])
         assert abs(s_t[i] - rt) < 1e-14 and abs(s_q[i] - rq) < 1e-9, (i, s_t[i], rt, s_q[i], rq)
     assert np.median(s_t[ok]) < 0.01 and np.median(s_q[ok]) < 0.02            # the synthetic poses are recovered
+
+
+def test_ensemble_edge_cases(eng):
+    """One member = the pooled mean of a single prediction per label; members that see nothing -> zero pose;
+    too many pooled predictions and the sigma-weighted form are refused loudly."""
+    from satellite_pose_estimation_b200._lib import SpeError
+    d = synth.make_predictions(32, seed=41, outlier_frac=0.0)
+    lg, pt, bx = (torch.from_numpy(d[k]).cuda() for k in ("logits", "points", "boxes"))
+    one = eng.ensemble_pnp(lg[None], pt[None], bx, reproj=20.0, want_pooled=True)
+    ref = eng.assign_pnp(lg, pt, bx, reproj=20.0, want_post=True)
+    # with a single member every label is the mean of its own foreground queries (>= 1): where a label has exactly one
+    # query the pooled point is that query's pixel position
+    cnt = one["count"].cpu().numpy(); pooled = one["pooled_px"].cpu().numpy()
+    px = ref["points_px"].cpu().numpy(); asg = ref["assign"].cpu().numpy()
+    labels = d["logits"].argmax(-1)                                    # [32, Q]
+    hit = 0
+    for i in range(32):
+        for l in range(11):
+            raw = int((labels[i] == l).sum())                            # foreground queries of this label
+            if raw == 1:
+                assert cnt[i, l] == 1 and np.array_equal(pooled[i, l], px[i, asg[i, l]]); hit += 1
+            elif raw == 2:
+                qs = np.nonzero(labels[i] == l)[0]
+                assert cnt[i, l] == 2 and np.allclose(pooled[i, l], (px[i, qs[0]] + px[i, qs[1]]) / 2, atol=1e-3)
+            elif raw == 0:
+                assert cnt[i, l] == 0 and asg[i, l] < 0 and not pooled[i, l].any()
+            else:
+                assert cnt[i, l] <= raw                                  # >= 3: the 3-sigma filter may drop some (or all)
+    assert hit > 100
+    bg = torch.full((3, 4, 40, 12), -4.0, device="cuda"); bg[..., 11] = 4.0           # every query background
+    r = eng.ensemble_pnp(bg, torch.rand(3, 4, 40, 2, device="cuda"), bx[:4], reproj=25.0)
+    assert (r["status"].cpu().numpy() == 1).all() and not r["quat"].cpu().numpy().any() and not r["count"].cpu().numpy().any()
+    with pytest.raises(SpeError):                                                        # 41 x 100 > 4096 pooled predictions
+        eng.ensemble_pnp(torch.zeros(41, 1, 100, 12, device="cuda"), torch.zeros(41, 1, 100, 2, device="cuda"), bx[:1])
