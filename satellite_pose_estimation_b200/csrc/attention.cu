@@ -222,6 +222,7 @@ std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s) {
   if (d.ldk % vec || d.ldv % vec || d.ldq % 1) return "attention: K/V row strides must be multiples of 8 elements";
   static const bool no_tc = getenv("SPE_ATTN_LEGACY") != nullptr;
   if (!no_tc && attention_tc_supported(dt, d)) return launch_attention_tc(d, s);
+  if (d.mixed) return "attention: fp32 Q/K/V with bf16 output needs the tcgen05 kernel (shape not supported)";
   if (dt == kTF32) return launch_attn_t<float>(d, s);
   return launch_attn_t<__nv_bfloat16>(d, s);
 }

@@ -18,6 +18,7 @@
 #include "spe_internal.h"
 #include "profile.h"
 #include "spe_ptx.cuh"
+#include <cuda_bf16.h>
 
 #include <stdlib.h>
 
@@ -36,6 +37,7 @@ struct AttnTcParams {
   float scale_log2e;
   int exact_out;
   int debug;
+  int out_bf16;     // bf16-storage models: Q / K / V arrive as fp32 (TF32 values), the output is written as bf16
 };
 
 template <int NK> struct AttnSmem {
@@ -295,7 +297,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t o[16];
     tmem_ld_32x16(trow0 + ocol, o);
     tmem_wait_ld();
-    if (q0 + row < p.Lq) {
+    if (q0 + row < p.Lq && p.out_bf16) {
+      const float inv = 1.0f / l;
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                          (static_cast<long long>(b) * p.Lq + q0 + row) * p.ldo + h * 32 + half * 16;
+#pragma unroll
+      for (int i = 0; i < 16; i += 8) {
+        uint4 o8;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&o8);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          hh[u] = __floats2bfloat162_rn(__uint_as_float(o[i + 2 * u]) * inv, __uint_as_float(o[i + 2 * u + 1]) * inv);
+        *reinterpret_cast<uint4*>(op + i) = o8;
+      }
+    } else if (q0 + row < p.Lq) {
       const float inv = 1.0f / l;
       float* op = p.out + (static_cast<long long>(b) * p.Lq + q0 + row) * p.ldo + h * 32 + half * 16;
 #pragma unroll
@@ -344,6 +359,7 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
   p.Lk = d.Lk;
   p.scale_log2e = d.scale * 1.4426950408889634f;
   p.exact_out = d.exact_out;
+  p.out_bf16 = d.mixed;
   static const bool dbg = getenv("SPE_ATTN_DEBUG") != nullptr;
   p.debug = dbg ? 1 : 0;
   dim3 grid((d.Lq + kQRows - 1) / kQRows, d.heads, d.B);
@@ -357,7 +373,7 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
 
 // fp32 storage only; Q/K/V/O must be batch-contiguous (batch stride = rows * row stride)
 bool attention_tc_supported(Dtype dt, const AttnDesc& d) {
-  if (dt != kTF32) return false;
+  if (dt != kTF32 && !d.mixed) return false;   // bf16 storage: only with fp32 Q / K / V (AttnDesc::mixed)
   // small problems (decoder self-attention, 40 x 40) stay on the register kernel; decoder cross-attention (40 queries
   // x 784 keys) is worth a 128-row tile even at 31 % row occupancy (28 us vs 45 us per layer at B = 64)
   if (d.Lq < 32 || d.Lk < 128) return false;

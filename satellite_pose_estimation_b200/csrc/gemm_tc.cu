@@ -79,6 +79,8 @@ struct GemmKParams {
   void* out;
   int out_ld;
   int round_out;       // fp32 storage: round results to TF32 (consumer is a kind::tf32 MMA)
+  int out_f32;         // bf16 storage: write this GEMM's output as fp32 (rounded to TF32), e.g. Q|K|V for the tcgen05
+                       // attention kernel, which takes fp32 / TF32 operands
   int K;               // X3: column offset of W_lo inside the [N, 2K] weight matrix
   int remap_wp;        // tap-reuse 3x3 kernel: accumulator row m' = h * remap_wp + w of a (W + 2)-wide padded grid
   int sub_rows;        // ... image rows per 128-row accumulator
@@ -99,7 +101,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // epilogue's issue slots, and the epilogue's issue rate is what bounds the short-K GEMMs).
 template <typename T, bool RELU, bool ROUND, bool FULL, int NIT, int G>
 __device__ __forceinline__ void store_chunk(float (&f)[NIT][G], uint8_t* gp, const long long out_step, const int crow,
-                                            const int rows_here, const int rpi) {
+                                            const int rows_here, const int rpi, const bool out_f32 = false) {
 #pragma unroll
   for (int i = 0; i < NIT; ++i) {
     if (RELU) {
@@ -113,6 +115,12 @@ __device__ __forceinline__ void store_chunk(float (&f)[NIT][G], uint8_t* gp, con
         float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
         if (ROUND) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
         *reinterpret_cast<float4*>(gp) = o4;
+      } else if (out_f32) {
+        // bf16 storage, fp32 output (TF32-rounded): this lane's eight columns are 32 contiguous bytes
+        *reinterpret_cast<float4*>(gp) = make_float4(rna_tf32(f[i][0]), rna_tf32(f[i][1]), rna_tf32(f[i][2]),
+                                                     rna_tf32(f[i][3]));
+        *reinterpret_cast<float4*>(gp + 16) = make_float4(rna_tf32(f[i][4 % G]), rna_tf32(f[i][5 % G]),
+                                                          rna_tf32(f[i][6 % G]), rna_tf32(f[i][7 % G]));
       } else {
         uint4 o8;
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
@@ -148,9 +156,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   const bool resid = p.residual != nullptr && rows_here > 0;
   const int res_es = (sizeof(T) == 4 || p.res_f32) ? 4 : 2;  // residual element size (fp32 addends in bf16 mode)
   // per-thread row pointers advance by a constant stride; the batch-broadcast addend wraps with one compare
-  const long long out_step = static_cast<long long>(RPI) * p.out_ld * static_cast<long long>(sizeof(T));
-  uint8_t* out0 = reinterpret_cast<uint8_t*>(p.out) +
-                  ((slab0 + crow) * p.out_ld) * static_cast<long long>(sizeof(T)) + cseg * 16;
+  const bool out_f32 = sizeof(T) == 2 && p.out_f32;             // bf16 storage, fp32 output
+  const long long oes = out_f32 ? 4 : static_cast<long long>(sizeof(T));   // output element size
+  const long long out_step = static_cast<long long>(RPI) * p.out_ld * oes;
+  uint8_t* out0 = reinterpret_cast<uint8_t*>(p.out) + ((slab0 + crow) * p.out_ld) * oes + cseg * G * oes;
   int rr0 = 0;
   if (resid) rr0 = p.res_mod > 0 ? static_cast<int>(static_cast<unsigned>(slab0 + crow) % static_cast<unsigned>(p.res_mod))
                                  : 0;
@@ -288,16 +297,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       continue;
     }
     if (col_ok && rows_here > 0 && !(p.dbg & 1)) {
-      uint8_t* gp = out0 + static_cast<long long>(ncol) * static_cast<long long>(sizeof(T));
+      uint8_t* gp = out0 + static_cast<long long>(ncol) * oes;
       switch (variant) {
-        case 0: store_chunk<T, false, false, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
-        case 1: store_chunk<T, true, false, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
-        case 2: store_chunk<T, false, true, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
-        case 3: store_chunk<T, true, true, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
-        case 4: store_chunk<T, false, false, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
-        case 5: store_chunk<T, true, false, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
-        case 6: store_chunk<T, false, true, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
-        default: store_chunk<T, true, true, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI); break;
+        case 0: store_chunk<T, false, false, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
+        case 1: store_chunk<T, true, false, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
+        case 2: store_chunk<T, false, true, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
+        case 3: store_chunk<T, true, true, false, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
+        case 4: store_chunk<T, false, false, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
+        case 5: store_chunk<T, true, false, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
+        case 6: store_chunk<T, false, true, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
+        default: store_chunk<T, true, true, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
       }
     }
   }
@@ -1204,7 +1213,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   const int es = static_cast<int>(dtype_size(dt));
   const int BK = 128 / es;
   if (d.N % 32 != 0) return "gemm: N must be a multiple of 32";
-  if (d.out_ld % (16 / es) != 0) return "gemm: out_ld must keep rows 16-byte aligned";
+  if (d.out_ld % (16 / es) != 0 && !d.out_f32) return "gemm: out_ld must keep rows 16-byte aligned";
   if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
   if (d.x3 && d.mode != 0) return "gemm: 3xTF32 is only built for plain matrices";
   if (d.mode < 0 || d.mode > 2) return "gemm: bad mode";
@@ -1250,6 +1259,8 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   kp.relu = d.relu;
   kp.out = d.out;
   kp.out_ld = d.out_ld;
+  kp.out_f32 = (dt != kTF32 && d.out_f32) ? 1 : 0;
+  if (kp.out_f32 && d.mode != 0) return "gemm: fp32 output from bf16 storage is only built for plain matrices";
   kp.num_n_tiles = (d.N + BN - 1) / BN;
 
   CUtensorMap tmA, tmB;

@@ -177,6 +177,7 @@ struct spe_ctx {
   void *S0 = nullptr, *S1 = nullptr, *P0 = nullptr, *P1 = nullptr, *T1 = nullptr, *T2 = nullptr, *DS = nullptr,
        *COL = nullptr, *L2OUT = nullptr, *L3OUT = nullptr, *UP = nullptr, *CAT = nullptr, *FEAT = nullptr,
        *X = nullptr, *X2 = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr, *KV = nullptr;
+  bool mixed_attention = getenv("SPE_MIXED_ATTN") ? atoi(getenv("SPE_MIXED_ATTN")) != 0 : true;
   void *TGT = nullptr, *TGT2 = nullptr, *DQKV = nullptr, *DQ = nullptr, *DATT = nullptr, *DHID = nullptr,
        *HS = nullptr, *H1 = nullptr, *H2 = nullptr, *G1 = nullptr, *G2 = nullptr;
   float *logits_all = nullptr, *points_all = nullptr;
@@ -599,7 +600,8 @@ std::string alloc_workspace(spe_ctx* ctx) {
   TRY_S(A(&ctx->X, B * T * 256));
   TRY_S(A(&ctx->X2, B * T * 256));
   if (ctx->dt == kTF32) TRY_S(A(&ctx->XS, B * T * 768));
-  TRY_S(A(&ctx->QKV, B * T * 768));
+  // bf16 storage: the encoder's Q|K|V are written as fp32 (TF32 values) for the tcgen05 attention kernel -> 4 B/element
+  TRY_S(A(&ctx->QKV, B * T * 768 * (ctx->dt == kTF32 ? 1 : 2)));
   TRY_S(A(&ctx->ATT, B * T * 256));
   TRY_S(A(&ctx->HID, B * T * FF));
   TRY_S(A(&ctx->KV, B * T * LD * 512));
@@ -666,7 +668,7 @@ struct Fwd {
   // out[M, N] = act(scale * A W^T + bias (+ residual))
   std::string gemm(const void* A, long long M, const GemmW& w, void* out, int out_ld, bool relu,
                    const void* residual = nullptr, int res_ld = 0, int res_mod = 0, int res_f32 = 0,
-                   bool use_scale_bias = true) {
+                   bool use_scale_bias = true, int out_f32 = 0) {
     GemmDesc d;
     d.mode = 0;
     d.A = A; d.M = M; d.K = w.K; d.lda = w.K;
@@ -678,6 +680,7 @@ struct Fwd {
     d.out = out; d.out_ld = out_ld;
     d.x3 = w.x3;
     d.round_out = w.x3 ? 0 : 1;   // 3xTF32 chains keep full fp32 activations
+    d.out_f32 = out_f32;
     return launch_gemm(dt, d, ctx->num_sms, st);
   }
   // R x R convolution (pad = R/2, stride 1 or 2) as implicit GEMM; H = input extent
@@ -696,9 +699,10 @@ struct Fwd {
     return conv(x, H, C, 3, 1, w, out, out_ld, relu);
   }
   std::string attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int Lq,
-                   int Lk, int exact_out = 0) {
+                   int Lk, int exact_out = 0, int mixed = 0) {
     AttnDesc a;
     a.exact_out = exact_out;
+    a.mixed = mixed;
     a.q = q; a.k = k; a.v = v; a.out = out;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = 256;
     a.bsq = static_cast<long long>(Lq) * ldq; a.bsk = static_cast<long long>(Lk) * ldk;
@@ -804,8 +808,16 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   const int Ti = static_cast<int>(T);
   for (int i = 0; i < c.enc_layers; ++i) {
     const EncLayer& L = ctx->enc[i];
-    TRY_S(f.gemm(Xc, Bl * T, L.qkv, ctx->QKV, 768, false, L.addend, 768, Ti, 1));
-    TRY_S(f.attn(ctx->QKV, 768, f.col(ctx->QKV, 256), 768, f.col(ctx->QKV, 512), 768, ctx->ATT, Ti, Ti));
+    if (f.dt == kTF32 || !ctx->mixed_attention) {
+      TRY_S(f.gemm(Xc, Bl * T, L.qkv, ctx->QKV, 768, false, L.addend, 768, Ti, 1));
+      TRY_S(f.attn(ctx->QKV, 768, f.col(ctx->QKV, 256), 768, f.col(ctx->QKV, 512), 768, ctx->ATT, Ti, Ti));
+    } else {
+      // bf16 storage: Q|K|V leave the GEMM as fp32 (TF32 values) so that the encoder attention can run on the tcgen05 /
+      // TMEM kernel (184 us per layer at B = 64) instead of the mma.sync register kernel (445 us); its output is bf16
+      float* q32 = static_cast<float*>(ctx->QKV);
+      TRY_S(f.gemm(Xc, Bl * T, L.qkv, q32, 768, false, L.addend, 768, Ti, 1, true, 1));
+      TRY_S(f.attn(q32, 768, q32 + 256, 768, q32 + 512, 768, ctx->ATT, Ti, Ti, 0, 1));
+    }
     TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256));
     TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc));
     // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: emit it pre-split

@@ -38,6 +38,7 @@ struct GemmDesc {
   int out_ld = 0;
   int round_out = 1;              // fp32 storage: round the result to TF32 (its consumer is a kind::tf32 MMA)
   int x3 = 0;                     // error-compensated 3xTF32: Wt is [N, 2K] = [W_hi | W_lo]; fp32-grade accuracy
+  int out_f32 = 0;                // bf16 storage only: `out` is fp32 [M, out_ld] (values rounded to TF32)
 };
 
 // returns empty string on success, else an error message
@@ -65,6 +66,7 @@ struct AttnDesc {
   int B, heads, Lq, Lk;                         // head_dim fixed at 32
   float scale;                                  // 1/sqrt(head_dim)
   int exact_out = 0;                            // fp32 storage: do not round the output to TF32
+  int mixed = 0;                                // bf16 storage, tcgen05 path: q / k / v are fp32 (TF32 values), out is bf16
 };
 std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s);
 // tcgen05 / TMEM path (attention_tc.cu); launch_attention dispatches to it when supported
