@@ -1,5 +1,5 @@
 """Standalone launches of the fused feed-forward kernel at the encoder's shape (for timing / ncu captures).
-   python tests/ffn_probe.py [reps]"""
+   python tools/ffn_probe.py [reps]"""
 import ctypes as C
 import os
 import sys

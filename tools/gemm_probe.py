@@ -1,5 +1,5 @@
 """Standalone launches of the three epilogue-heavy GEMM shapes of the forward (for ncu --set full captures).
-   python tests/gemm_probe.py [reps]"""
+   python tools/gemm_probe.py [reps]"""
 import ctypes as C
 import os
 import sys

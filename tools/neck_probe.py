@@ -1,5 +1,5 @@
 """Standalone launches of the two neck 3x3 convolutions at B = 64 (the largest GEMM launches of the step), for ncu
-captures.   python tests/neck_probe.py [reps]"""
+captures.   python tools/neck_probe.py [reps]"""
 import ctypes as C, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
