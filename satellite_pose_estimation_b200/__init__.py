@@ -9,4 +9,5 @@ All compute runs in ``libspe.so`` (hand-written sm_100a CUDA, C ABI in include/s
 from .models import B200DETR, PostProcess, build_model  # noqa: F401
 from .solver import BatchedPoseSolver, MultiMeanPoseSolver, build_solver  # noqa: F401
 from .engine import Engine  # noqa: F401
-from .submission import SubmissionWriter, gen_prediction, gen_submission, run_image_set, save_prediction  # noqa: F401
+from .submission import (SpeedEval, SubmissionWriter, gen_prediction, gen_submission, run_image_set,  # noqa: F401
+                         save_prediction, speed_score)

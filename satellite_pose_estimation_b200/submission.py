@@ -6,6 +6,8 @@
                                             RV/gen_submission_multi.py:122-199 -- the ensemble ("multi") submission loop:
                                             collect every checkpoint's PostProcess results per file, then solve each
                                             file with ``Multi_Mean_PoseSolver``; log values rounded to 6 decimals
+* ``SpeedEval`` / ``speed_score``           RV/datasets/speed.py:337-425, RV/utils/speed_eval.py:245-262 -- the ``main.py --eval``
+                                            bookkeeping: per-file log with the reference's rounding, summary string
 * ``run_image_set``                         the single-model loop of RV/gen_submission_single.py:113-187 over a whole
                                             image set, sharded by image across ranks (BASELINE.json configs[4]) and fed
                                             through the multi-slot batch pipeline of libspe.so
@@ -57,6 +59,82 @@ def log_entry(quat, tvec):
     """The reference's log record (RV/gen_submission_single.py:176-179): values rounded to 6 decimals, as lists."""
     return {"quat_pr": np.around(np.asarray(quat, dtype=np.float64), decimals=6).tolist(),
             "tvec_pr": np.around(np.asarray(tvec, dtype=np.float64), decimals=6).tolist()}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# evaluation bookkeeping (main.py --eval)
+# ---------------------------------------------------------------------------------------------------------------
+def speed_score(q_pr, t_pr, q_gt, t_gt):
+    """RV/utils/speed_eval.py:245-262 for one image on the host (``Engine.speed_score`` is the batched device form)."""
+    q_pr = np.asarray(q_pr, dtype=np.float64).flatten(); t_pr = np.asarray(t_pr, dtype=np.float64).flatten()
+    q_gt = np.asarray(q_gt, dtype=np.float64).flatten(); t_gt = np.asarray(t_gt, dtype=np.float64).flatten()
+    assert q_pr.shape[0] == q_gt.shape[0] == 4 and t_pr.shape[0] == t_gt.shape[0] == 3
+    if q_pr[0] < 0:
+        q_pr = q_pr * -1
+    if q_gt[0] < 0:
+        q_gt = q_gt * -1
+    s_t = np.linalg.norm(t_pr - t_gt, ord=2) / np.linalg.norm(t_gt, ord=2)
+    s_q = 2 * np.arccos(min(np.abs(np.dot(q_pr, q_gt)), 1))
+    return s_t, s_q
+
+
+class SpeedEval:
+    """Mirror of ``SpeedEval`` (RV/datasets/speed.py:337-425): ``update({filename: PostProcess result})`` solves each
+    file with ``solver(points, logits)`` (failures -> zero pose, :351-362), scores it against the ground truth and logs
+    it with the reference's rounding (points 2, logits / poses 6, scores 8 decimals); ``summarize()`` builds the same
+    ``stats`` string.  ``ground_truth`` is the reference's JSON list (``filename``, ``q_vbs2tango``,
+    ``r_Vo2To_vbs_true``) -- a path or the parsed list."""
+
+    def __init__(self, ground_truth, solver):
+        self.solver = solver
+        if isinstance(ground_truth, (str, os.PathLike)):
+            with open(ground_truth, "r") as f:
+                ground_truth = json.load(f)
+        self.ground_truth = {item["filename"]: {"quat": item["q_vbs2tango"], "tvec": item["r_Vo2To_vbs_true"]}
+                             for item in ground_truth}
+        self.log = {}
+        self.stats = ""
+
+    def update(self, predictions):
+        for filename, ret in predictions.items():
+            try:
+                quat_pr, tvec_pr = self.solver(ret["points"], ret["logits"])
+            except IndexError:
+                quat_pr, tvec_pr = np.zeros(4), np.zeros(3)
+            quat_gt = self.ground_truth[filename]["quat"]
+            tvec_gt = self.ground_truth[filename]["tvec"]
+            score_tvec, score_quat = speed_score(quat_pr, tvec_pr, quat_gt, tvec_gt)
+            self.log[filename] = {
+                "points": np.around(ret["points"], decimals=2).tolist(),
+                "logits": np.around(ret["logits"], decimals=6).tolist(),
+                "quat_gt": quat_gt,
+                "tvec_gt": tvec_gt,
+                "quat_pr": np.around(quat_pr, decimals=6).tolist(),
+                "tvec_pr": np.around(tvec_pr, decimals=6).tolist(),
+                "score_tvec": np.around(score_tvec, decimals=8).item(),
+                "score_quat": np.around(score_quat, decimals=8).item(),
+                "score": np.around(score_quat + score_tvec, decimals=8).item(),
+            }
+
+    def summarize(self):
+        scores = np.asarray([item["score"] for item in self.log.values()])
+        tvec_score = np.asarray([item["score_tvec"] for item in self.log.values()])
+        quat_score = np.asarray([item["score_quat"] for item in self.log.values()])
+        tvec_abs = np.stack([np.abs(np.asarray(item["tvec_pr"]) - np.asarray(item["tvec_gt"]))
+                             for item in self.log.values()])
+        scores = np.mean(scores).item()
+        tvec_score = np.mean(tvec_score).item()
+        quat_score = np.mean(quat_score).item()
+        self.stats = "tvec score: {:.6f}, quat score: {:.6f}, final score: {:.6f}; ".format(
+            tvec_score, quat_score, scores)
+        # the reference takes these "medians" of the already averaged scalars (:407-411); kept so that the string matches
+        self.stats = self.stats + "median tvec: {:.6f}, median quat: {:.6f}; ".format(
+            np.median(tvec_score).item(), np.median(quat_score).item())
+        tvec_abs_mean = np.mean(tvec_abs, 0).tolist()
+        tvec_abs_median = np.median(tvec_abs, 0).tolist()
+        self.stats = self.stats + "mean tvec abs: [{:.6f}, {:.6f}, {:.6f}], median tvec abs:[{:.6f}, {:.6f}, {:.6f}]".format(
+            *(tvec_abs_mean + tvec_abs_median))
+        return self.stats
 
 
 # ---------------------------------------------------------------------------------------------------------------

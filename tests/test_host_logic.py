@@ -146,3 +146,53 @@ def test_submission_writer_matches_reference_format(tmp_path):
         assert open(tmp_path / "ref" / "submission_t.csv").read() == open(path).read()
     e = log_entry([0.12345678, 1, 0, 0], [1e-7, 2.5, 3.0000004])       # RV/gen_submission_single.py:176-179
     assert e == {"quat_pr": [0.123457, 1.0, 0.0, 0.0], "tvec_pr": [0.0, 2.5, 3.0]}
+
+
+def test_speed_eval_matches_reference(tmp_path):
+    """SpeedEval bookkeeping (RV/datasets/speed.py:337-425): log rounding, failure -> zero pose, summary string; in
+    the build container the reference's own class is run on the same inputs and must produce the same log and string."""
+    import json
+    from satellite_pose_estimation_b200.submission import SpeedEval, speed_score
+    from oracle import pnp_ref, synth
+    rng = np.random.default_rng(4)
+    n = 12
+    d = synth.make_predictions(n, seed=17)
+    res = pnp_ref.post_process(d["logits"], d["points"], d["boxes"])
+    gt = [{"filename": f"img{i:06d}.jpg", "q_vbs2tango": d["q_gt"][i].tolist(), "r_Vo2To_vbs_true": d["t_gt"][i].tolist()}
+          for i in range(n)]
+    poses = {}
+    for i in range(n):      # a deterministic stand-in solver: ground truth plus a small perturbation, two failures
+        q = d["q_gt"][i] + rng.normal(0, 1e-3, 4); q /= np.linalg.norm(q)
+        poses[id(res[i]["points"])] = (q * (-1 if i % 3 == 0 else 1), d["t_gt"][i] + rng.normal(0, 1e-2, 3))
+
+    def solver(points, logits):
+        if id(points) in (id(res[2]["points"]), id(res[7]["points"])):
+            raise IndexError("too few keypoints")
+        return poses[id(points)]
+    ev = SpeedEval(gt, solver)
+    preds = {g["filename"]: res[i] for i, g in enumerate(gt)}
+    ev.update(dict(list(preds.items())[:5])); ev.update(dict(list(preds.items())[5:]))
+    stats = ev.summarize()
+    assert list(ev.log) == [g["filename"] for g in gt]
+    e2 = ev.log["img000002.jpg"]
+    assert e2["quat_pr"] == [0.0] * 4 and e2["tvec_pr"] == [0.0] * 3 and abs(e2["score_tvec"] - 1.0) < 1e-12
+    e1 = ev.log["img000001.jpg"]
+    s_t, s_q = pnp_ref.speed_score(*poses[id(res[1]["points"])], d["q_gt"][1], d["t_gt"][1])
+    assert e1["score_tvec"] == round(float(s_t), 8) and e1["score_quat"] == round(float(s_q), 8)
+    assert e1["points"] == np.around(res[1]["points"], 2).tolist()
+    assert stats.startswith("tvec score: ") and "median tvec abs:[" in stats
+    a = speed_score([1, 0, 0, 0], [0, 0, 10], [-1, 0, 0, 0], [0, 0, 5])
+    assert a[0] == 1.0 and a[1] == 0.0
+    ref_root = os.path.join("/root/reference", "Revisiting Monocular Satellite Pose Estimation With Transformer")
+    if os.path.isdir(ref_root):
+        from oracle import make_golden
+        rv_speed, _ = make_golden.import_rv_dataset_and_solver()
+        os.makedirs(tmp_path / "gt")
+        with open(tmp_path / "gt" / "gt.json", "w") as f:
+            json.dump(gt, f)
+        rv_speed.DATA_ROOT = str(tmp_path / "gt")
+        ref = rv_speed.SpeedEval("gt.json", solver)
+        ref.update(preds)
+        ref.summarize()
+        assert ref.log == ev.log
+        assert ref.stats == ev.stats
