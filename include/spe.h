@@ -112,6 +112,9 @@ typedef struct {
   const float* float_boxes_dev; /* optional [B,4] fp32 (x1, y1, width, height): de-normalise the keypoints with
                                    these instead of the int32 boxes -- the main.py --eval path hands PostProcess the
                                    UNROUNDED crop box (RV/datasets/speed.py:246-260, spe_clip_boxes_val)        */
+  const float* reproj_thresh_dev; /* optional [B] fp32: per-image RANSAC threshold instead of reproj_thresh -- the SA solver
+                                     derives it from the detection area, int(area / input_size * 10) clamped to [1.5, 20]
+                                     (SA/utils/speed_eval_ceres.py:53-58)                                          */
 } spe_pnp_params;
 
 int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_dev, const float* log_sigma_dev,

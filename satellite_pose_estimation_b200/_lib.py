@@ -22,7 +22,8 @@ class SpeTensorDesc(C.Structure):
 
 class SpePnpParams(C.Structure):
     _fields_ = [("reproj_thresh", C.c_float), ("weighted", C.c_int), ("reject", C.c_int),
-                ("reject_rms_px", C.c_float), ("reject_sigma_px", C.c_float), ("float_boxes_dev", C.c_void_p)]
+                ("reject_rms_px", C.c_float), ("reject_sigma_px", C.c_float), ("float_boxes_dev", C.c_void_p),
+                ("reproj_thresh_dev", C.c_void_p)]
 
 
 # every symbol include/spe.h declares: (restype, argtypes)

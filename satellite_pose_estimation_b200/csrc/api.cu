@@ -160,6 +160,7 @@ int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_de
   d.boxes_f = params->float_boxes_dev;
   d.B = B; d.Q = Q;
   d.reproj_thresh = params->reproj_thresh;
+  d.reproj_dev = params->reproj_thresh_dev;
   d.weighted = params->weighted;
   d.reject = params->reject;
   d.reject_rms_px = params->reject_rms_px > 0 ? params->reject_rms_px : 5.0f;
@@ -196,6 +197,7 @@ int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_
   d.boxes_f = params->float_boxes_dev;
   d.B = B; d.Q = Q; d.num_models = num_models;
   d.reproj_thresh = params->reproj_thresh;
+  d.reproj_dev = params->reproj_thresh_dev;
   d.reject = params->reject;
   d.reject_rms_px = params->reject_rms_px > 0 ? params->reject_rms_px : 5.0f;
   d.reject_sigma = params->reject_sigma_px > 0 ? params->reject_sigma_px : 12.0f;

@@ -662,7 +662,8 @@ assign_pnp_kernel(const PnpDesc d) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) best.R[i] = 0.0;
   best.t[0] = best.t[1] = best.t[2] = 0.0;
-  const double thr2 = static_cast<double>(d.reproj_thresh) * static_cast<double>(d.reproj_thresh);
+  const double thr = static_cast<double>(d.reproj_dev ? d.reproj_dev[img] : d.reproj_thresh);
+  const double thr2 = thr * thr;
   // Every thread first decodes its own triple index, then all lanes run the solver together: calling it from inside
   // the enumeration loop would serialise the warp (one active lane per iteration).
   const int ntriples = n * (n - 1) * (n - 2) / 6;

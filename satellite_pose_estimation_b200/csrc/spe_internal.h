@@ -113,6 +113,7 @@ struct PnpDesc {
   const float* boxes_f;  // or [B,4] fp32 x1,y1,width,height (eval path: unrounded box); takes precedence when set
   int B, Q;
   float reproj_thresh;
+  const float* reproj_dev;   // optional [B]: per-image threshold (area-adaptive RANSAC threshold of the SA solver)
   int weighted;
   int reject;            // apply the self-assessment reject filter
   float reject_rms_px;   // filter thresholds

@@ -167,6 +167,20 @@ class Engine:
         copy), keeping the CUDA-graph key stable."""
         self._stable_inputs.add(tensor.data_ptr())
 
+    @staticmethod
+    def sa_detection_area(det_boxes):
+        """The "area" the SA dataset hands its solver (SA/src/data/speed/speed_dataset.py:370-373), reproduced with its
+        parenthesisation: ``sqrt((x2 - x1) * y2 - y1)`` of the detector box -- a length in pixels, not an area."""
+        b = np.asarray(det_boxes, dtype=np.float64).reshape(-1, 4)
+        return np.sqrt((b[:, 2] - b[:, 0]) * b[:, 3] - b[:, 1])
+
+    @staticmethod
+    def area_repro_threshold(areas, input_size):
+        """``EPnPCeresSolver.get_repro_th`` (SA/utils/speed_eval_ceres.py:53-58): RANSAC threshold from the detection
+        area, ``int(area / input_size * 10)`` clamped to [1.5, 20]; float32 numpy [B] for ``assign_pnp(reproj=...)``."""
+        a = np.asarray(areas, dtype=np.float64).reshape(-1)
+        return np.clip(np.trunc(a / float(input_size) * 10), 1.5, 20).astype(np.float32)
+
     # ---- stage 3 ---------------------------------------------------------------------------------------------
     def assign_pnp(self, logits, points, boxes, log_sigma=None, reproj=20.0, weighted=False, reject=False,
                    reject_rms_px=5.0, reject_sigma_px=12.0, want_post=False):
@@ -194,9 +208,14 @@ class Engine:
                 sig = torch.empty((B, Q, 2), dtype=torch.float32, device=dev)
         if log_sigma is not None:
             log_sigma = log_sigma.contiguous().float()
-        p = SpePnpParams(reproj_thresh=float(reproj), weighted=int(weighted), reject=int(reject),
-                         reject_rms_px=float(reject_rms_px), reject_sigma_px=float(reject_sigma_px),
-                         float_boxes_dev=fbox.data_ptr() if fbox is not None else None)
+        thr = None
+        if torch.is_tensor(reproj):          # per-image thresholds (e.g. area_repro_threshold), cuda float [B]
+            thr = reproj.to(device=dev, dtype=torch.float32).contiguous()
+            assert thr.shape == (B,)
+        p = SpePnpParams(reproj_thresh=0.0 if thr is not None else float(reproj), weighted=int(weighted),
+                         reject=int(reject), reject_rms_px=float(reject_rms_px), reject_sigma_px=float(reject_sigma_px),
+                         float_boxes_dev=fbox.data_ptr() if fbox is not None else None,
+                         reproj_thresh_dev=thr.data_ptr() if thr is not None else None)
         check(self.lib.spe_assign_pnp(self._ctx, _ptr(logits), _ptr(points), _ptr(log_sigma), _ptr(boxes), B, Q,
                                       C.byref(p), _ptr(quat), _ptr(tvec), _ptr(assign), _ptr(status), _ptr(probs),
                                       _ptr(pts_px), _ptr(sig), _ptr(inl), _stream(dev)), self._ctx)

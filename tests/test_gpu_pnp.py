@@ -263,3 +263,27 @@ def test_ensemble_edge_cases(eng):
     assert (r["status"].cpu().numpy() == 1).all() and not r["quat"].cpu().numpy().any() and not r["count"].cpu().numpy().any()
     with pytest.raises(SpeError):                                                        # 41 x 100 > 4096 pooled predictions
         eng.ensemble_pnp(torch.zeros(41, 1, 100, 12, device="cuda"), torch.zeros(41, 1, 100, 2, device="cuda"), bx[:1])
+
+
+def test_per_image_reprojection_threshold(eng):
+    """SA's area-adaptive RANSAC threshold (SA/utils/speed_eval_ceres.py:53-58) as a per-image array: each image solved
+    with its own threshold equals the same image solved alone with that threshold as the scalar."""
+    d = synth.make_predictions(48, seed=51, outlier_frac=0.5)
+    lg, pt, bx = (torch.from_numpy(d[k]).cuda() for k in ("logits", "points", "boxes"))
+    det = synth.load_detector_boxes()[:480:10]
+    area = Engine.sa_detection_area(det)
+    assert np.allclose(area, [np.sqrt((b[2] - b[0]) * b[3] - b[1]) for b in det])
+    thr = Engine.area_repro_threshold(area, 224)                     # a spread of thresholds between 1.5 and 20
+    assert thr.min() >= 1.5 and thr.max() <= 20 and len(np.unique(thr)) > 3
+    for a, want in ((224 * 0.16, 1.5), (224 * 1.0, 10.0), (224 * 9.99, 20.0), (224 * 0.77, 7.0)):
+        assert Engine.area_repro_threshold([a], 224)[0] == want       # int() truncation, then the clamp
+    r = eng.assign_pnp(lg, pt, bx, reproj=torch.from_numpy(thr).cuda())
+    for i in range(48):
+        one = eng.assign_pnp(lg[i:i + 1], pt[i:i + 1], bx[i:i + 1], reproj=float(thr[i]))
+        assert int(one["status"][0]) == int(r["status"][i]) and int(one["inlier_mask"][0]) == int(r["inlier_mask"][i])
+        assert torch.equal(one["quat"][0], r["quat"][i]) and torch.equal(one["tvec"][0], r["tvec"][i])
+    # the array is really used: tight thresholds on the odd images only change exactly (some of) those images
+    mix = torch.from_numpy(np.where(np.arange(48) % 2 == 1, 1.5, 20.0).astype(np.float32)).cuda()
+    loose = eng.assign_pnp(lg, pt, bx, reproj=20.0)["inlier_mask"].cpu().numpy()
+    mixed = eng.assign_pnp(lg, pt, bx, reproj=mix)["inlier_mask"].cpu().numpy()
+    assert np.array_equal(mixed[0::2], loose[0::2]) and (mixed[1::2] != loose[1::2]).any()
