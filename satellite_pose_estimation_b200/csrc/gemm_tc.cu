@@ -87,13 +87,33 @@ struct GemmKParams {
   int stem_im2col;     // mode 2 through an im2col map: tile = 128 consecutive output pixels
   uint32_t a_stage;    // ... bytes of one halo-tile stage
   int dbg;             // SPE_GEMM_DBG bit 0: skip the output stores (profiling experiments only)
+  long long* tdbg;     // -DSPE_GEMM_TIMING + SPE_GEMM_TDBG=1: per-CTA wait-cycle counters of gemm_tc_kernel (bring-up only)
 };
 
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// fp32 -> TF32, round to nearest, ties away from zero: what cvt.rna.tf32.f32 computes, on the integer ALUs.  The
+// conversion instruction runs on the 16-lane XU pipe (8 issue cycles per warp, 32 of them per 32-column chunk of the
+// epilogue); IEEE floats are sign-magnitude, so adding half a TF32 ulp to the bit pattern and clearing the low 13 bits
+// rounds the magnitude for either sign (carries into the exponent, up to infinity, like the instruction).  NaNs pass.
 __device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  const uint32_t u = __float_as_uint(x);
+  const uint32_t r = (u + 0x1000u) & 0xffffe000u;
+  return __uint_as_float((u & 0x7fffffffu) > 0x7f800000u ? u : r);
+}
+
+#ifdef SPE_GEMM_TIMING
+#define GEMM_CLOCK() clock64()
+#else
+#define GEMM_CLOCK() 0ll
+#endif
+__device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity, int tag, long long& acc) {
+#ifdef SPE_GEMM_TIMING
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, tag);
+  acc += clock64() - t0;
+#else
+  mbar_wait(bar, parity, tag);
+#endif
 }
 
 // Last step of one 32-column chunk in the coalesced domain: ReLU, rounding, 16-byte stores.  RELU / ROUND / FULL are
@@ -139,7 +159,7 @@ template <typename T, int BN, int CSTEP, bool REMAP = false>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, const int lane, const int q,
                                               const int half, const uint32_t taddr, const int valid_rows,
                                               const long long m_base, const int n0, const float* s_scale,
-                                              const float* s_bias) {
+                                              const float* s_bias, long long* tc = nullptr) {
   // tcgen05.ld hands thread t accumulator row t, but a warp-wide access "32 rows x 16 bytes" touches 32 different
   // 128-byte lines.  So each 32x32 fp32 accumulator chunk is transposed ONCE through a per-warp XOR-swizzled
   // 32 x 128-byte staging tile (raw accumulators in, conflict-free both ways), and everything else -- BN
@@ -204,7 +224,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   for (int c = half; c < BN / 32; c += CSTEP) {
     const int ncol = n0 + c * 32;
     const bool col_ok = ncol < p.N;
+    const long long k0 = GEMM_CLOCK();
     tmem_wait_ld();
+    const long long k1 = GEMM_CLOCK();
     // own row -> staging (raw fp32 accumulators)
     if (!(p.dbg & 2))
 #pragma unroll
@@ -215,6 +237,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     // the next chunk's accumulators travel TMEM -> registers while this one is finished below
     if (c + CSTEP < BN / 32 && !(p.dbg & 4)) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + CSTEP) * 32), v);
     __syncwarp();
+    const long long k2 = GEMM_CLOCK();
     // this lane's fixed column group: scale / bias
     float sc[G], bi[G];
 #pragma unroll
@@ -241,6 +264,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       }
     }
     __syncwarp();   // staging free for the next chunk
+    const long long k3 = GEMM_CLOCK();
     if (resid && col_ok) {
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
@@ -262,7 +286,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
         }
       }
     }
+    const long long k4 = GEMM_CLOCK();
     if (resid && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next chunk, in flight during the stores
+    const long long k5 = GEMM_CLOCK();
     if constexpr (REMAP) {
       // accumulator row r is pixel (h, w) = (r / Wp, r % Wp) of the padded grid; columns w >= W are the halo (their
       // values are meaningless) and valid_rows counts the image rows of this sub-tile that exist
@@ -309,6 +335,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
         default: store_chunk<T, true, true, true, NIT, G>(f, gp, out_step, crow, rows_here, RPI, out_f32); break;
       }
     }
+#ifdef SPE_GEMM_TIMING
+    if (tc) {
+      const long long k6 = GEMM_CLOCK();
+      tc[0] += k1 - k0; tc[1] += k2 - k1; tc[2] += k3 - k2; tc[3] += k4 - k3; tc[4] += k5 - k4; tc[5] += k6 - k5;
+    }
+#else
+    (void)k0; (void)k1; (void)k2; (void)k3; (void)k4; (void)k5; (void)tc;
+#endif
   }
 }
 
@@ -372,6 +406,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
+      const long long t_begin = GEMM_CLOCK();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n0 = (tile - m_tile * p.num_n_tiles) * BN;
@@ -398,7 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           x0 = (rem - h0 * p.tiles_per_row) * BM;        // first output column of the tile
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          mbar_wait_g(&empty_bar[stage], phase ^ 1u, 1, w_empty);
           if (elect_one_sync()) {
             mbar_expect_tx(&full_bar[stage], p.a_bytes + (X3 ? 2 : 1) * Cfg::B_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -430,6 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (p.tdbg && lane == 0) { p.tdbg[blockIdx.x * 16 + 0] = GEMM_CLOCK() - t_begin; p.tdbg[blockIdx.x * 16 + 1] = w_empty; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
@@ -438,14 +475,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_begin = GEMM_CLOCK();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
-        mbar_wait(&tempty_bar[buf], use_par ^ 1u, 2);  // epilogue has drained this accumulator
+        mbar_wait_g(&tempty_bar[buf], use_par ^ 1u, 2, w_tempty);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase, 3);
+          mbar_wait_g(X3 ? &split_bar[stage] : &full_bar[stage], phase, 3, w_full);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -470,6 +509,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (p.tdbg && lane == 0) {
+        p.tdbg[blockIdx.x * 16 + 2] = GEMM_CLOCK() - t_begin; p.tdbg[blockIdx.x * 16 + 3] = w_full;
+        p.tdbg[blockIdx.x * 16 + 4] = w_tempty;
       }
     }
     __syncwarp();
@@ -503,7 +546,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 64;        // 0 .. 32 * EPI_WARPS - 1
     const int half = (warp - 2) >> 2;       // which interleaved set of column chunks this warp handles
     int it = 0;
+    long long w_tfull = 0, t_epi = 0, t_pre = 0;
+    long long tcs[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = GEMM_CLOCK();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const long long c0 = GEMM_CLOCK();
       const int buf = it & 1;
       const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
       const int m_tile = tile / p.num_n_tiles;
@@ -536,15 +583,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         s_bias[j] = (p.bias != nullptr && ok) ? p.bias[n0 + j] : 0.0f;
       }
       named_bar_sync(1, 32 * EPI_WARPS);
-      mbar_wait(&tfull_bar[buf], use_par, 4);
+      const long long c1 = GEMM_CLOCK();
+      mbar_wait_g(&tfull_bar[buf], use_par, 4, w_tfull);
+      const long long c2 = GEMM_CLOCK();
       tc_fence_after();
 
       epilogue_tile<T, BN, CSTEP>(p, sm_staging + (warp - 2) * 4096, lane, q, half,
                                   tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN),
-                                  valid_rows, m_base, n0, s_scale, s_bias);
+                                  valid_rows, m_base, n0, s_scale, s_bias, tcs);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      t_pre += c1 - c0; t_epi += GEMM_CLOCK() - c2;
+    }
+    if (p.tdbg && warp == 2 && lane == 0) {
+      p.tdbg[blockIdx.x * 16 + 5] = GEMM_CLOCK() - t_begin; p.tdbg[blockIdx.x * 16 + 6] = w_tfull;
+      p.tdbg[blockIdx.x * 16 + 7] = t_epi; p.tdbg[blockIdx.x * 16 + 8] = t_pre; p.tdbg[blockIdx.x * 16 + 9] = it;
+      for (int k = 0; k < 6; ++k) p.tdbg[blockIdx.x * 16 + 10 + k] = tcs[k];
     }
   }
 
@@ -1101,8 +1156,14 @@ std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, con
 }
 
 template <typename T, int BN, bool X3, bool EPI8>
-std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap& tmA, const CUtensorMap& tmB,
+std::string launch_t(const GemmDesc& d, const GemmKParams& kp_in, const CUtensorMap& tmA, const CUtensorMap& tmB,
                      int num_sms, cudaStream_t stream) {
+  GemmKParams kp = kp_in;
+  static const bool tdbg_on = getenv("SPE_GEMM_TDBG") != nullptr;
+  static long long* tdbg_dev = nullptr;
+  if (tdbg_on && tdbg_dev == nullptr) SPE_CUDA_TRY(cudaMalloc(&tdbg_dev, 256 * 16 * sizeof(long long)));
+  if (tdbg_on) SPE_CUDA_TRY(cudaMemsetAsync(tdbg_dev, 0, 256 * 16 * sizeof(long long), stream));
+  kp.tdbg = tdbg_on ? tdbg_dev : nullptr;
   using Cfg = StageCfg<BN, X3, EPI8>;
   static bool attr_set = false;
   auto kfn = gemm_tc_kernel<T, BN, X3, EPI8>;
@@ -1118,6 +1179,19 @@ std::string launch_t(const GemmDesc& d, const GemmKParams& kp, const CUtensorMap
   }
   SPE_CUDA_TRY(cudaGetLastError());
   (void)d;
+  if (tdbg_on) {   // only meaningful in a -DSPE_GEMM_TIMING build
+    static long long host[256 * 16];
+    SPE_CUDA_TRY(cudaStreamSynchronize(stream));
+    SPE_CUDA_TRY(cudaMemcpy(host, tdbg_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    for (int cta : {0, 73, 147}) {
+      const long long* h = host + cta * 16;
+      fprintf(stderr, "[gemm dbg] BN %d epi8 %d cta %3d: prod.total=%lld prod.wait_empty=%lld mma.total=%lld mma.wait_full=%lld "
+              "mma.wait_tempty=%lld epi.total=%lld epi.wait_tfull=%lld epi.work=%lld epi.pre=%lld tiles=%lld\n", BN,
+              static_cast<int>(EPI8), cta, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+      fprintf(stderr, "[gemm dbg]   per-chunk phases (sum): wait_ld=%lld sts+ldtm=%lld lds+fma=%lld residual_add=%lld "
+              "fetch_next=%lld store=%lld\n", h[10], h[11], h[12], h[13], h[14], h[15]);
+    }
+  }
   return "";
 }
 
