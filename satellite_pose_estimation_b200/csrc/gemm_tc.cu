@@ -740,14 +740,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_begin = GEMM_CLOCK();
       for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
         const int buf = it & 1;
         const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
-        mbar_wait(&tempty_bar[buf], use_par ^ 1u, 22);   // both CTAs' epilogues have drained this accumulator
+        mbar_wait_g(&tempty_bar[buf], use_par ^ 1u, 22, w_tempty);   // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 23);
+          mbar_wait_g(&full_bar[stage], phase, 23, w_full);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -763,6 +765,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (p.tdbg && lane == 0) {
+        p.tdbg[blockIdx.x * 16 + 2] = GEMM_CLOCK() - t_begin; p.tdbg[blockIdx.x * 16 + 3] = w_full;
+        p.tdbg[blockIdx.x * 16 + 4] = w_tempty;
+      }
     }
     __syncwarp();
   } else {
@@ -771,6 +777,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half = (warp - 2) >> 2;   // with 8 warps the two halves take alternate column chunks
     const int et = threadIdx.x - 64;
     int it = 0;
+    long long w_tfull = 0, t_epi = 0, t_arr = 0;
+    long long tcs[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = GEMM_CLOCK();
     for (int tile = pair; tile < num_tiles; tile += npairs, ++it) {
       const int buf = it & 1;
       const uint32_t use_par = static_cast<uint32_t>(it >> 1) & 1u;
@@ -800,14 +809,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         s_bias[j] = (p.bias != nullptr && ok) ? p.bias[n0 + j] : 0.0f;
       }
       named_bar_sync(1, 32 * Cfg::EPI_WARPS);
-      mbar_wait(&tfull_bar[buf], use_par, 24);
+      mbar_wait_g(&tfull_bar[buf], use_par, 24, w_tfull);
+      const long long c2 = GEMM_CLOCK();
       tc_fence_after();
       epilogue_tile<T, BN, CSTEP>(p, sm_staging + (warp - 2) * 4096, lane, q, half,
                               tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN),
-                              valid_rows, m_base, n0, s_scale, s_bias);
+                              valid_rows, m_base, n0, s_scale, s_bias, tcs);
+      const long long c3 = GEMM_CLOCK();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // leader's barrier
+      t_epi += c3 - c2; t_arr += GEMM_CLOCK() - c3;
+    }
+    if (p.tdbg && warp == 2 && lane == 0) {
+      p.tdbg[blockIdx.x * 16 + 5] = GEMM_CLOCK() - t_begin; p.tdbg[blockIdx.x * 16 + 6] = w_tfull;
+      p.tdbg[blockIdx.x * 16 + 7] = t_epi; p.tdbg[blockIdx.x * 16 + 8] = t_arr; p.tdbg[blockIdx.x * 16 + 9] = it;
+      for (int kq = 0; kq < 6; ++kq) p.tdbg[blockIdx.x * 16 + 10 + kq] = tcs[kq];
     }
   }
 
@@ -820,8 +837,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <typename T, bool EPI8>
-std::string launch_cg2(const GemmKParams& kp, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
+std::string launch_cg2(const GemmKParams& kp_in, const CUtensorMap& tmA, const CUtensorMap& tmB, int num_sms,
                        cudaStream_t stream) {
+  GemmKParams kp = kp_in;
+  static const bool tdbg_on = getenv("SPE_GEMM_TDBG") != nullptr;
+  static long long* tdbg_dev = nullptr;
+  if (tdbg_on && tdbg_dev == nullptr) SPE_CUDA_TRY(cudaMalloc(&tdbg_dev, 256 * 16 * sizeof(long long)));
+  if (tdbg_on) SPE_CUDA_TRY(cudaMemsetAsync(tdbg_dev, 0, 256 * 16 * sizeof(long long), stream));
+  kp.tdbg = tdbg_on ? tdbg_dev : nullptr;
   static bool attr_set = false;
   using Cfg = Cg2Cfg<EPI8>;
   auto kfn = gemm_tc2_kernel<T, EPI8>;
@@ -837,6 +860,18 @@ std::string launch_cg2(const GemmKParams& kp, const CUtensorMap& tmA, const CUte
     kfn<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
   }
   SPE_CUDA_TRY(cudaGetLastError());
+  if (tdbg_on) {   // only meaningful in a -DSPE_GEMM_TIMING build
+    static long long host[256 * 16];
+    SPE_CUDA_TRY(cudaStreamSynchronize(stream));
+    SPE_CUDA_TRY(cudaMemcpy(host, tdbg_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    for (int cta : {0, 1, 146}) {
+      const long long* h = host + cta * 16;
+      fprintf(stderr, "[gemm2 dbg] epi8 %d cta %3d: mma.total=%lld mma.wait_full=%lld mma.wait_tempty=%lld epi.total=%lld "
+              "epi.wait_tfull=%lld epi.work=%lld epi.arrive=%lld tiles=%lld | wait_ld=%lld sts=%lld lds=%lld res=%lld fetch=%lld "
+              "store=%lld\n", static_cast<int>(EPI8), cta, h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12],
+              h[13], h[14], h[15]);
+    }
+  }
   return "";
 }
 
