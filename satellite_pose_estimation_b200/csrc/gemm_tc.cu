@@ -96,9 +96,12 @@ __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_ca
 // epilogue); IEEE floats are sign-magnitude, so adding half a TF32 ulp to the bit pattern and clearing the low 13 bits
 // rounds the magnitude for either sign (carries into the exponent, up to infinity, like the instruction).  NaNs pass.
 __device__ __forceinline__ float rna_tf32(float x) {
-  const uint32_t u = __float_as_uint(x);
-  const uint32_t r = (u + 0x1000u) & 0xffffe000u;
-  return __uint_as_float((u & 0x7fffffffu) > 0x7f800000u ? u : r);
+  const uint32_t r = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  return x != x ? x : __uint_as_float(r);     // one FSETP + a predicated LOP3
+}
+// the same for a value that cannot be NaN (fmaxf(x, 0) never is): add + mask only
+__device__ __forceinline__ float rna_tf32_finite(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 #ifdef SPE_GEMM_TIMING
@@ -128,12 +131,14 @@ __device__ __forceinline__ void store_chunk(float (&f)[NIT][G], uint8_t* gp, con
 #pragma unroll
       for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
     }
-    if (FULL || i * rpi + crow < rows_here) {
+    if (FULL || i * rpi < rows_here - crow) {
       if (sizeof(T) == 4) {
         // fp32 storage feeds kind::tf32 MMAs, which drop the low 13 mantissa bits: round to nearest here
         // so the next layer's products are exact and the error stays unbiased
         float4 o4 = make_float4(f[i][0], f[i][1], f[i][2], f[i][3]);
-        if (ROUND) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
+        if (ROUND && RELU)
+          o4 = make_float4(rna_tf32_finite(o4.x), rna_tf32_finite(o4.y), rna_tf32_finite(o4.z), rna_tf32_finite(o4.w));
+        else if (ROUND) o4 = make_float4(rna_tf32(o4.x), rna_tf32(o4.y), rna_tf32(o4.z), rna_tf32(o4.w));
         *reinterpret_cast<float4*>(gp) = o4;
       } else if (out_f32) {
         // bf16 storage, fp32 output (TF32-rounded): this lane's eight columns are 32 contiguous bytes
@@ -189,37 +194,42 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
   // this lane's staging addresses (byte offsets): its own row for the transposing write, its column group for reads
   const uint32_t stg_w = smem_u32(stg) + lane * 128;
   const int wsw = lane & 7;
+  // coalesced-domain reads: row r = i * RPI + crow, 16-byte chunk k of it sits at (k ^ (r & 7)).  fp32: k = cseg and
+  // r & 7 alternates between crow and crow + 4 with i; bf16: k = 2 * cseg + {0, 1} and r & 7 = crow.  Two base
+  // addresses either way, the rest is an immediate offset.
+  const uint8_t* stg_r0 = stg + crow * 128 + (sizeof(T) == 4 ? ((cseg ^ crow) * 16) : (((2 * cseg) ^ crow) * 16));
+  const uint8_t* stg_r1 = stg + crow * 128 + (sizeof(T) == 4 ? ((cseg ^ (crow + 4)) * 16) : (((2 * cseg + 1) ^ crow) * 16));
 
-  // residual values of this lane for one chunk: NIT rows x G columns (prefetched one chunk ahead)
+  // residual values of this lane for one chunk: NIT rows x G columns (prefetched one chunk ahead).  The row pointer
+  // advances by a constant stride and the batch-broadcast addend wraps with one compare: the epilogue warp's issue
+  // rate is what bounds the short-K GEMMs, and a 64-bit multiply per row was 22 instructions per load.
   uint4 rx[NIT][2];
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) rx[i][0] = rx[i][1] = make_uint4(0u, 0u, 0u, 0u);
+  const long long res_step = static_cast<long long>(RPI) * p.res_ld * res_es;
+  const long long res_wrap = static_cast<long long>(p.res_mod) * p.res_ld * res_es;
+  const int wrap_at = p.res_mod > 0 ? p.res_mod : 0x7fffffff;
+  const uint8_t* res0 = res_base + ((p.res_mod > 0 ? static_cast<long long>(rr0) : slab0 + crow) * p.res_ld + cseg * G) *
+                                       static_cast<long long>(res_es);
+  const int rows_left = rows_here - crow;                    // row i * RPI + crow exists iff i * RPI < rows_left
   auto fetch_residual = [&](int ncol_) {
+    const uint8_t* gp = res0 + static_cast<long long>(ncol_) * res_es;
+    const int lim = ncol_ < p.N ? rows_left : 0;
+    int w = rr0;
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
-      rx[i][0] = make_uint4(0u, 0u, 0u, 0u);
-      rx[i][1] = make_uint4(0u, 0u, 0u, 0u);
-      const int r = i * RPI + crow;
-      if (r < rows_here && ncol_ < p.N) {
-        long long rr;
-        if (p.res_mod > 0) {
-          int w = rr0 + i * RPI;
-          if (w >= p.res_mod) w -= p.res_mod;
-          rr = w;
-        } else {
-          rr = slab0 + r;
-        }
-        const uint8_t* gp = res_base + (rr * p.res_ld + ncol_ + cseg * G) * static_cast<long long>(res_es);
+      if (i * RPI < lim) {
         rx[i][0] = *reinterpret_cast<const uint4*>(gp);
         if (res_es * G > 16) rx[i][1] = *reinterpret_cast<const uint4*>(gp + 16);   // 8 fp32 addends (bf16 mode)
       }
+      gp += res_step;
+      w += RPI;
+      if (w >= wrap_at) { w -= wrap_at; gp -= res_wrap; }
     }
   };
   if (resid) fetch_residual(n0 + half * 32);
   uint32_t v[32];
-  if (!(p.dbg & 4)) tmem_ld_32x32(taddr + static_cast<uint32_t>(half * 32), v);
-  else {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = lane + k;
-  }
+  tmem_ld_32x32(taddr + static_cast<uint32_t>(half * 32), v);
 #pragma unroll 1
   for (int c = half; c < BN / 32; c += CSTEP) {
     const int ncol = n0 + c * 32;
@@ -228,14 +238,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     tmem_wait_ld();
     const long long k1 = GEMM_CLOCK();
     // own row -> staging (raw fp32 accumulators)
-    if (!(p.dbg & 2))
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + ((k ^ wsw) * 16)), "r"(v[4 * k]),
                    "r"(v[4 * k + 1]), "r"(v[4 * k + 2]), "r"(v[4 * k + 3])
                    : "memory");
     // the next chunk's accumulators travel TMEM -> registers while this one is finished below
-    if (c + CSTEP < BN / 32 && !(p.dbg & 4)) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + CSTEP) * 32), v);
+    if (c + CSTEP < BN / 32) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + CSTEP) * 32), v);
     __syncwarp();
     const long long k2 = GEMM_CLOCK();
     // this lane's fixed column group: scale / bias
@@ -250,13 +259,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     float f[NIT][G];
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
-      const int r = i * RPI + crow;
 #pragma unroll
       for (int u = 0; u < G; u += 4) {
-        const int k = cseg * (G / 4) + u / 4;                  // 16-byte chunk of the staging row
-        float4 a4;
-        if (!(p.dbg & 2)) a4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((k ^ (r & 7)) * 16));
-        else a4 = make_float4(__uint_as_float(v[i * 4]), __uint_as_float(v[i * 4 + 1]), __uint_as_float(v[i * 4 + 2]), __uint_as_float(v[i * 4 + 3]));
+        const uint8_t* sp = (sizeof(T) == 4 ? ((i & 1) ? stg_r1 : stg_r0) : (u ? stg_r1 : stg_r0)) + i * RPI * 128;
+        const float4 a4 = *reinterpret_cast<const float4*>(sp);
         f[i][u] = fmaf(a4.x, sc[u], bi[u]);
         f[i][u + 1] = fmaf(a4.y, sc[u + 1], bi[u + 1]);
         f[i][u + 2] = fmaf(a4.z, sc[u + 2], bi[u + 2]);
