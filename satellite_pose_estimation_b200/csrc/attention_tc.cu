@@ -108,6 +108,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();     // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_launch();
 
   // Producer and MMA warps run warp-uniform loops; one elected lane issues (spe_ptx.cuh: elect_one_sync) -- under
   // `if (lane == 0)` every one of the 18 MMAs of a chunk was wrapped in a ~90-cycle waterfall loop, 3.6 x their 450
@@ -364,7 +366,7 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
   p.debug = dbg ? 1 : 0;
   dim3 grid((d.Lq + kQRows - 1) / kQRows, d.heads, d.B);
   ProfScope ps(kFamAttention, s);
-  kfn<<<grid, kThreads, SM::BYTES, s>>>(tmQ, tmK, tmV, p);
+  SPE_CUDA_TRY(launch_pdl(kfn, grid, dim3(kThreads), SM::BYTES, s, tmQ, tmK, tmV, p));
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
 }

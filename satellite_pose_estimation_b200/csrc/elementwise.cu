@@ -9,6 +9,7 @@
 //   layernorm        nn.LayerNorm(256), eps 1e-5, fp32 statistics (RV/models/transformer.py:159-166)
 #include "spe_internal.h"
 #include "profile.h"
+#include "spe_ptx.cuh"
 #include <cuda_bf16.h>
 
 namespace spe {
@@ -238,6 +239,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
                     long long rows, T* __restrict__ out, int exact) {
+  pdl_wait();
+  pdl_launch();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -367,8 +370,8 @@ std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const
   if (rows <= 0) return "";
   ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
-    layernorm256_kernel<T><<<blocks_for(rows, 8), 256, 0, s>>>(reinterpret_cast<const T*>(in), gamma, beta, rows,
-                                                               reinterpret_cast<T*>(out), exact);
+    SPE_CUDA_TRY(launch_pdl(layernorm256_kernel<T>, dim3(blocks_for(rows, 8)), dim3(256), 0, s,
+                            reinterpret_cast<const T*>(in), gamma, beta, rows, reinterpret_cast<T*>(out), exact));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

@@ -169,6 +169,8 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   cluster_sync_all();   // barrier inits and the TMEM allocation are visible in both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();     // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_launch();
   const int NC = p.num_chunks;
 
   if (warp == 0) {
@@ -519,7 +521,7 @@ std::string launch_ffn_fused(const FfnDesc& d, int num_sms, cudaStream_t stream)
   const int pairs = num_pt < num_sms / 2 ? num_pt : num_sms / 2;
   {
     ProfScope ps(kFamGemm, stream);
-    ffn_tc2_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(tmX, tmW1, tmW2, p);
+    SPE_CUDA_TRY(launch_pdl(ffn_tc2_kernel, dim3(2 * pairs), dim3(kThreads), kSmemBytes, stream, tmX, tmW1, tmW2, p));
   }
   SPE_CUDA_TRY(cudaGetLastError());
   if (dbg_on) {   // only meaningful in a -DSPE_FFN_TIMING build

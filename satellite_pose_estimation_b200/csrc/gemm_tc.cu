@@ -405,6 +405,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();     // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -688,6 +690,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();   // barrier inits and the TMEM allocation are visible in both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();     // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs; warp-uniform)
@@ -863,7 +867,7 @@ std::string launch_cg2(const GemmKParams& kp_in, const CUtensorMap& tmA, const C
   if (pairs > pair_tiles) pairs = pair_tiles;
   {
     ProfScope ps(kFamGemm, stream);
-    kfn<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+    SPE_CUDA_TRY(launch_pdl(kfn, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, kp));
   }
   SPE_CUDA_TRY(cudaGetLastError());
   if (tdbg_on) {   // only meaningful in a -DSPE_GEMM_TIMING build
@@ -957,6 +961,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();     // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform, one lane issues)
@@ -1216,7 +1222,7 @@ std::string launch_t(const GemmDesc& d, const GemmKParams& kp_in, const CUtensor
   const int grid = tiles < num_sms ? tiles : num_sms;
   {
     ProfScope ps(kFamGemm, stream);
-    kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, kp);
+    SPE_CUDA_TRY(launch_pdl(kfn, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, kp));
   }
   SPE_CUDA_TRY(cudaGetLastError());
   (void)d;
@@ -1312,7 +1318,8 @@ static std::string launch_conv3(Dtype dt, const GemmDesc& d, int num_sms, cudaSt
     auto kfn = conv3_tc_kernel<TT, BNV>;                                                                          \
     SPE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));                 \
     ProfScope ps(kFamGemm, stream);                                                                               \
-    kfn<<<grid, Conv3Cfg<BNV>::THREADS, smem_bytes, stream>>>(tmA, tmB, kp, b_stages);                            \
+    SPE_CUDA_TRY(launch_pdl(kfn, dim3(grid), dim3(Conv3Cfg<BNV>::THREADS), smem_bytes, stream, tmA, tmB, kp,      \
+                            b_stages));                                                                           \
   } while (0)
   if (dt == kTF32) {
     if (d.N == 64) SPE_CONV3(float, 64); else SPE_CONV3(float, 128);

@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace spe {
 
@@ -82,6 +83,34 @@ __device__ __forceinline__ bool elect_one_sync() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched through launch_pdl() may become resident while the previous kernel
+// of the stream is still draining: its prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps that
+// tail instead of following the completion + launch gap (~3 us x 120 launches per batch).  pdl_wait() returns once
+// the previous kernel has completed and its writes are visible; NOTHING that touches global memory may precede it.
+// pdl_launch() lets the next kernel of the stream start arriving; it sits right after the wait so at most two
+// kernels are ever in flight.  Both are no-ops in a kernel launched the ordinary way.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  static const int pdl_on = getenv("SPE_PDL") ? atoi(getenv("SPE_PDL")) : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ----------------------------------------------------------------------------------------------
