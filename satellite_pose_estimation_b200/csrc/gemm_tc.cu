@@ -243,8 +243,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + ((k ^ wsw) * 16)), "r"(v[4 * k]),
                    "r"(v[4 * k + 1]), "r"(v[4 * k + 2]), "r"(v[4 * k + 3])
                    : "memory");
-    // the next chunk's accumulators travel TMEM -> registers while this one is finished below
-    if (c + CSTEP < BN / 32) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + CSTEP) * 32), v);
     __syncwarp();
     const long long k2 = GEMM_CLOCK();
     // this lane's fixed column group: scale / bias
@@ -270,6 +268,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
       }
     }
     __syncwarp();   // staging free for the next chunk
+    // The next chunk's accumulators travel TMEM -> registers while this one is finished below.  Issued here and not
+    // right behind the staging writes: tcgen05.ld overwrites the registers those st.shared still read, and waiting
+    // for them to drain was the largest single stall of the loop (ncu source view, r01n).
+    if (c + CSTEP < BN / 32) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + CSTEP) * 32), v);
     const long long k3 = GEMM_CLOCK();
     if (resid && col_ok) {
 #pragma unroll
@@ -557,6 +559,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     long long w_tfull = 0, t_epi = 0, t_pre = 0;
     long long tcs[6] = {0, 0, 0, 0, 0, 0};
     const long long t_begin = GEMM_CLOCK();
+    constexpr int NJ = (BN + 32 * EPI_WARPS - 1) / (32 * EPI_WARPS);   // scale / bias columns per thread and tile
+    float nsc[NJ], nbi[NJ];
+    auto fetch_scale_bias = [&](int tile_) {
+      const int n0_ = (tile_ % p.num_n_tiles) * BN;
+#pragma unroll
+      for (int u = 0; u < NJ; ++u) {
+        const int j = et + u * 32 * EPI_WARPS;
+        const bool ok = j < BN && (n0_ + j) < p.N;
+        nsc[u] = (p.scale != nullptr && ok) ? p.scale[n0_ + j] : 1.0f;
+        nbi[u] = (p.bias != nullptr && ok) ? p.bias[n0_ + j] : 0.0f;
+      }
+    };
+    if (static_cast<int>(blockIdx.x) < num_tiles) fetch_scale_bias(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const long long c0 = GEMM_CLOCK();
       const int buf = it & 1;
@@ -585,12 +600,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       float* s_scale = sm_scale + buf * BN;
       float* s_bias = sm_bias + buf * BN;
-      for (int j = et; j < BN; j += 32 * EPI_WARPS) {
-        const bool ok = (n0 + j) < p.N;
-        s_scale[j] = (p.scale != nullptr && ok) ? p.scale[n0 + j] : 1.0f;
-        s_bias[j] = (p.bias != nullptr && ok) ? p.bias[n0 + j] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < NJ; ++u) {
+        const int j = et + u * 32 * EPI_WARPS;
+        if (j < BN) { s_scale[j] = nsc[u]; s_bias[j] = nbi[u]; }
       }
       named_bar_sync(1, 32 * EPI_WARPS);
+      // the next tile's scale / bias travel to registers while this tile is drained (their L2 round trip used to sit
+      // in front of every tile of the warps that bound the short-K GEMMs)
+      if (tile + static_cast<int>(gridDim.x) < num_tiles) fetch_scale_bias(tile + gridDim.x);
       const long long c1 = GEMM_CLOCK();
       mbar_wait_g(&tfull_bar[buf], use_par, 4, w_tfull);
       const long long c2 = GEMM_CLOCK();
