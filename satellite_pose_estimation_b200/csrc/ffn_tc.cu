@@ -460,7 +460,7 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(o_empty), 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(o_empty), 0));
 #if defined(SPE_FFN_TIMING) && !defined(SPE_FFN_TIMING_ACT)
       const long long e3 = FFN_CLOCK();
       t_p1 += e1 - e0; t_p2 += e2 - e1; t_p3 += e3 - e2; t_epi += e3 - e0;

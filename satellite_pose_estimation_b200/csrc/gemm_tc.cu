@@ -846,7 +846,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long long c3 = GEMM_CLOCK();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // leader's barrier
+      if (lane == 0) {   // leader's barrier; relaxed: only TMEM reads are handed over (SPE_GEMM_RELEASE_ARRIVE for A/B)
+#ifdef SPE_GEMM_RELEASE_ARRIVE
+        mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+#else
+        mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+#endif
+      }
       t_epi += c3 - c2; t_arr += GEMM_CLOCK() - c3;
     }
     if (p.tdbg && warp == 2 && lane == 0) {

@@ -296,6 +296,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same without release semantics, for hand-overs that publish NO memory writes: "this accumulator has been read
+// out of TMEM" is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.  The release form first drains every
+// outstanding global store of the thread to cluster scope -- 1.4 k cycles behind an epilogue's stores (clock64, r01m).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads issued by either CTA of a pair: data lands in the issuing CTA's smem, the transaction bytes are
 // signalled on `bar_cluster_addr` (the leader CTA's mbarrier)
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr,
