@@ -539,7 +539,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < Cfg::A_BYTES / 16 / 128; ++i) {
           const float4 v = a[st + i * 128];
-          const float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+          // (no NaN guard on the rounding: for a NaN input the remainder v - h below is NaN whatever h came out as,
+          // and the product sum carries it)
+          const float4 h = make_float4(rna_tf32_finite(v.x), rna_tf32_finite(v.y), rna_tf32_finite(v.z),
+                                       rna_tf32_finite(v.w));
           a[st + i * 128] = h;                                                   // A_hi: exactly TF32
           lo[st + i * 128] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);  // A_lo: the remainder
         }
