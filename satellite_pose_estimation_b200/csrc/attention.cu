@@ -12,6 +12,7 @@
 // through this kernel; ragged tails are masked.
 #include "spe_internal.h"
 #include "profile.h"
+#include "spe_ptx.cuh"
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -78,6 +79,8 @@ __global__ void __launch_bounds__(128)
 attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ out,
                  int ldq, int ldk, int ldv, int ldo, long long bsq, long long bsk, long long bsv, long long bso,
                  int Lq, int Lk, float scale_log2e, int exact_out) {
+  pdl_wait();
+  pdl_launch();
   __shared__ __align__(16) float Ks[KT * KLD];
   __shared__ __align__(16) float Vs[KT * KLD];
 
@@ -204,11 +207,11 @@ std::string launch_attn_t(const AttnDesc& d, cudaStream_t s) {
   T* o = reinterpret_cast<T*>(d.out);
   ProfScope ps(kFamAttention, s);
   if (d.Lk % 112 == 0) {
-    attention_kernel<T, 112><<<grid, 128, 0, s>>>(q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq, d.bsk, d.bsv,
-                                                 d.bso, d.Lq, d.Lk, sl2, d.exact_out);
+    SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 112>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq,
+                            d.bsk, d.bsv, d.bso, d.Lq, d.Lk, sl2, d.exact_out));
   } else {
-    attention_kernel<T, 64><<<grid, 128, 0, s>>>(q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq, d.bsk, d.bsv,
-                                                d.bso, d.Lq, d.Lk, sl2, d.exact_out);
+    SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 64>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq,
+                            d.bsk, d.bsv, d.bso, d.Lq, d.Lk, sl2, d.exact_out));
   }
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

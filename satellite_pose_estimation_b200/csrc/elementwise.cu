@@ -95,6 +95,8 @@ stem_im2col_kernel(const float* __restrict__ in, int Hin, int Win, int Ho, int W
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_pad_kernel(const float* __restrict__ in, int H, int W, long long total_px, T* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   constexpr int VN = Vec<T>::N;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total_px) return;
@@ -152,6 +154,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int Wo, long long total_vec,
                     T* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   constexpr int VN = Vec<T>::N;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total_vec) return;
@@ -195,6 +199,8 @@ constexpr int kUpTile = 4;
 template <typename T>
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, T* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
   constexpr int VN = Vec<T>::N;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long n = blockIdx.z;
@@ -319,7 +325,8 @@ std::string launch_stem_pad(Dtype dt, const float* nchw, int NB, int Hin, int Wi
   ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     const long long total = static_cast<long long>(NB) * (Hin + 6) * (Win + 6);
-    stem_pad_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(nchw, Hin, Win, total, reinterpret_cast<T*>(out));
+    SPE_CUDA_TRY(launch_pdl(stem_pad_kernel<T>, dim3(blocks_for(total, 256)), dim3(256), 0, s, nchw, Hin, Win, total,
+                            reinterpret_cast<T*>(out)));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
@@ -345,8 +352,8 @@ std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, 
   ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     const long long total = static_cast<long long>(NB) * Ho * Wo * (C / Vec<T>::N);
-    maxpool3x3s2_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C, Ho, Wo,
-                                                                  total, reinterpret_cast<T*>(out));
+    SPE_CUDA_TRY(launch_pdl(maxpool3x3s2_kernel<T>, dim3(blocks_for(total, 256)), dim3(256), 0, s,
+                            reinterpret_cast<const T*>(in), H, W, C, Ho, Wo, total, reinterpret_cast<T*>(out)));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
@@ -357,8 +364,9 @@ std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, in
   DISPATCH_T(dt, {
     const int nvec = C / Vec<T>::N;
     const int threads = nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32;
-    upsample2x_kernel<T><<<dim3((2 * W + kUpTile - 1) / kUpTile, (2 * H + kUpTile - 1) / kUpTile, NB), threads, 0, s>>>(reinterpret_cast<const T*>(in), H, W, C,
-                                                                   reinterpret_cast<T*>(out));
+    SPE_CUDA_TRY(launch_pdl(upsample2x_kernel<T>,
+                            dim3((2 * W + kUpTile - 1) / kUpTile, (2 * H + kUpTile - 1) / kUpTile, NB), dim3(threads), 0, s,
+                            reinterpret_cast<const T*>(in), H, W, C, reinterpret_cast<T*>(out)));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

@@ -7,6 +7,7 @@
 // The two hidden 256 -> 256 layers of each MLP run on the tensor-core GEMM; this kernel is one warp per query row.
 #include "spe_internal.h"
 #include "profile.h"
+#include "spe_ptx.cuh"
 #include <cuda_bf16.h>
 
 namespace spe {
@@ -47,6 +48,8 @@ head_final_kernel(const T* __restrict__ hs, const T* __restrict__ h2, const T* _
                   const float* __restrict__ Wc, const float* __restrict__ bc, const float* __restrict__ W3,
                   const float* __restrict__ b3, const float* __restrict__ Ws3, const float* __restrict__ bs3,
                   float* __restrict__ logits, float* __restrict__ points, float* __restrict__ logsig) {
+  pdl_wait();
+  pdl_launch();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -78,14 +81,15 @@ std::string launch_head_final(Dtype dt, const void* hs, const void* h2, const vo
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   ProfScope ps(kFamHeads, s);
   if (dt == kTF32) {
-    head_final_kernel<float><<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(hs),
-                                                     reinterpret_cast<const float*>(h2),
-                                                     reinterpret_cast<const float*>(s2), rows, Wc, bc, W3, b3, Ws3,
-                                                     bs3, logits, points, logsig);
+    SPE_CUDA_TRY(launch_pdl(head_final_kernel<float>, dim3(blocks), dim3(256), 0, s,
+                            reinterpret_cast<const float*>(hs), reinterpret_cast<const float*>(h2),
+                            reinterpret_cast<const float*>(s2), rows, Wc, bc, W3, b3, Ws3, bs3, logits, points,
+                            logsig));
   } else {
-    head_final_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(hs), reinterpret_cast<const __nv_bfloat16*>(h2),
-        reinterpret_cast<const __nv_bfloat16*>(s2), rows, Wc, bc, W3, b3, Ws3, bs3, logits, points, logsig);
+    SPE_CUDA_TRY(launch_pdl(head_final_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, s,
+                            reinterpret_cast<const __nv_bfloat16*>(hs), reinterpret_cast<const __nv_bfloat16*>(h2),
+                            reinterpret_cast<const __nv_bfloat16*>(s2), rows, Wc, bc, W3, b3, Ws3, bs3, logits, points,
+                            logsig));
   }
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

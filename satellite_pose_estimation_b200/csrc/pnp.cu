@@ -21,6 +21,7 @@
 // Failures reproduce the reference's observable contract: < 4 correspondences / no valid pose -> zero pose + status.
 #include "spe_internal.h"
 #include "profile.h"
+#include "spe_ptx.cuh"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -423,6 +424,8 @@ constexpr int kMaxPooled = 4096;     // ensemble: models x queries per image
 
 __global__ void __launch_bounds__(kPnpThreads)
 assign_pnp_kernel(const PnpDesc d) {
+  pdl_wait();
+  pdl_launch();
   const int img = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -810,7 +813,7 @@ std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s) {
   PnpDesc dd = d;
   static const bool timing = getenv("SPE_PNP_TIMING") != nullptr;
   dd.debug_timing = timing ? 1 : 0;
-  assign_pnp_kernel<<<d.B, kPnpThreads, 0, s>>>(dd);
+  SPE_CUDA_TRY(launch_pdl(assign_pnp_kernel, dim3(d.B), dim3(kPnpThreads), 0, s, dd));
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
 }
