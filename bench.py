@@ -244,7 +244,7 @@ def run_b200(args):
     # every step is one full batch on its own slot (streams + activation set); with SLOTS batches in flight the GPU
     # fills one batch's latency-bound decoder / pose stage and GEMM tail waves with another batch's work.
     # SPE_BENCH_SLOTS=1 times strictly one batch at a time.
-    SLOTS = max(1, min(4, int(os.environ.get("SPE_BENCH_SLOTS", "3"))))
+    SLOTS = max(1, min(8, int(os.environ.get("SPE_BENCH_SLOTS", "4"))))
     eng.set_pnp_override(syn_logits, syn_points, syn_boxes)
 
     def pipelined(n, first, submit):

@@ -154,10 +154,11 @@ int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, c
  * hands out the poses.  Keeping several slots in flight lets the GPU run whole batches next to each other: the upload
  * of one hides behind the kernels of the others, and the small latency-bound launches of a batch's decoder / pose
  * stage and the drained last wave of every persistent GEMM are filled with another batch's work (B=64 on B200:
- * 6.7 ms/batch one at a time, 5.9 ms with three in flight).  Results are bit-identical to the one-stream calls.
+ * 6.7 ms/batch one at a time, 5.9 ms with three in flight when the pipeline was built; four is the measured optimum
+ * with host frames).  Results are bit-identical to the one-stream calls.
  * frames_host must be pinned and stay valid until the slot is collected.  Do not mix with spe_forward /
  * spe_run_batch_host while slots are in flight (slot 0 shares their activation set). */
-#define SPE_PIPELINE_SLOTS 4
+#define SPE_PIPELINE_SLOTS 8
 int spe_submit_batch_host(spe_ctx* ctx, int slot, const uint8_t* frames_host, int H, int W,
                           const double* det_boxes_host, int B, const spe_pnp_params* params);
 int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tvec_host, int32_t* status_host,

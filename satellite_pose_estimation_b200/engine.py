@@ -274,7 +274,7 @@ class Engine:
                 "h2d_bytes": int(self.lib.spe_last_h2d_bytes(self._ctx))}
 
     def submit_batch_host(self, slot, frames_host, det_boxes, reproj=20.0, weighted=False, reject=False):
-        """Asynchronous half of ``run_batch_host`` (slot 0 .. 3): returns as soon as the work is enqueued.
+        """Asynchronous half of ``run_batch_host`` (slot 0 .. SPE_PIPELINE_SLOTS - 1 = 7): returns as soon as the work is enqueued.
         ``frames_host`` must be a pinned uint8 torch tensor [B,H,W] that stays alive until ``collect_batch_host``."""
         assert isinstance(frames_host, torch.Tensor) and frames_host.is_pinned() and frames_host.dtype == torch.uint8
         B, H, W = frames_host.shape
