@@ -28,6 +28,8 @@ class SpePnpParams(C.Structure):
 
 # every symbol include/spe.h declares: (restype, argtypes)
 _vp, _i, _ll = C.c_void_p, C.c_int, C.c_longlong
+PIPELINE_SLOTS = 8   # include/spe.h: SPE_PIPELINE_SLOTS
+
 SYMBOLS = {
     "spe_create": (_i, [C.POINTER(SpeConfig), _i, C.POINTER(_vp)]),
     "spe_destroy": (None, [_vp]),

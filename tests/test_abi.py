@@ -23,6 +23,8 @@ def test_header_symbols_all_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"include/spe.h declares {n} but libspe.so does not export it"
     assert set(names) == set(_lib.SYMBOLS), "ctypes prototypes out of sync with include/spe.h"
+    slots = int(re.search(r"#define SPE_PIPELINE_SLOTS (\d+)", open(os.path.join(ROOT, "include", "spe.h")).read()).group(1))
+    assert slots == _lib.PIPELINE_SLOTS
 
 
 def test_only_abi_symbols_are_exported():

@@ -9,7 +9,7 @@ import torch
 
 from oracle import model_ref, pnp_ref, synth
 from oracle.make_golden import MODEL_CASES, model_inputs
-from satellite_pose_estimation_b200 import Engine, build_model, build_solver
+from satellite_pose_estimation_b200 import Engine, _lib, build_model, build_solver
 
 pytestmark = pytest.mark.gpu
 
@@ -225,7 +225,7 @@ def test_multi_slot_pipeline_matches_serial(lib, cuda_dev, slots):
     out = eng.forward(eng.crop_resize_norm(sets[3][0], sets[3][1]))
     assert np.array_equal(out["pred_points"].cpu().numpy(), sets[3][2][1])
     with pytest.raises(Exception):
-        eng.submit_batch_dev(4, sets[0][0], sets[0][1])   # no such slot
+        eng.submit_batch_dev(_lib.PIPELINE_SLOTS, sets[0][0], sets[0][1])   # no such slot
     eng.set_pnp_override(None, None, None)
     eng.close()
 
