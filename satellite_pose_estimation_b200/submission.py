@@ -22,6 +22,7 @@ from datetime import datetime
 import numpy as np
 import torch
 
+from ._lib import PIPELINE_SLOTS
 from .sharding import batches, gather_results, shard_range
 
 
@@ -207,7 +208,7 @@ def save_prediction(prediction, save_path):
 # ---------------------------------------------------------------------------------------------------------------
 # whole image set, one model, sharded by image
 # ---------------------------------------------------------------------------------------------------------------
-def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, rank=0, world_size=1, slots=3,
+def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, rank=0, world_size=1, slots=4,
                   reproj=20.0, weighted=False, reject=False, gather=True):
     """crop -> predictor -> PnP for every image of a set (RV/gen_submission_single.py:136-181).
 
@@ -221,7 +222,7 @@ def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, ran
     batch_size = batch_size or engine.max_batch
     if batch_size > engine.max_batch:
         raise ValueError(f"batch_size {batch_size} exceeds the engine's max_batch {engine.max_batch}")
-    slots = max(1, min(4, slots))
+    slots = max(1, min(PIPELINE_SLOTS, slots))
     a, b = shard_range(n, rank, world_size)
     todo = batches(a, b, batch_size)
     local = {}
