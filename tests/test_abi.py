@@ -45,6 +45,10 @@ def test_kernels_are_blackwell_native():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, f"{mnemonic} missing from libspe.so SASS"
+    # issue loops are warp-uniform (elect_one_sync): no per-instruction waterfall loops around UTCHMMA / UTMALDG
+    assert "BRA.U.ANY" not in sass
+    # programmatic dependent launch: griddepcontrol.wait / .launch_dependents compiled into the step's kernels
+    assert sass.count("ACQBULK") >= 20 and sass.count("PREEXIT") >= 20
 
 
 def test_clip_boxes_bit_exact_on_every_reference_box(lib):
