@@ -99,6 +99,17 @@ int spe_crop_resize_norm(spe_ctx* ctx, const uint8_t* frames_dev, int H, int W, 
 int spe_forward(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev, float* points_dev,
                 float* log_sigma_dev, float* aux_logits_dev, float* aux_points_dev, void* stream);
 
+/* Optional accuracy step with no counterpart in the reference (whose fp32 weights need none).  The tensor cores read
+ * TF32 / BF16 weights; what the rounded weights lose, (W - round(W)) . x, is to first order the same for every image:
+ * (W - round(W)) . mean(x).  spe_calibrate runs one forward over `images` ([B,3,R,R] fp32, e.g. the first batch of
+ * crops), measures each layer's per-channel input mean and folds that term into the layer's bias (FrozenBN bias,
+ * linear bias or positional addend), once, at no inference cost.  Measured on the benchmarked frames: TF32 keypoint
+ * error 0.18 -> 0.05 px rms at the largest crop.  Results of later forwards depend on the calibration
+ * batch only through this correction, which is itself below the TF32 rounding noise it removes.  Must not be called
+ * while pipeline slots are in flight; synchronises `stream`.  Re-calibration replaces the previous correction. */
+int spe_calibrate(spe_ctx* ctx, const float* images_dev, int B, void* stream);
+int spe_is_calibrated(const spe_ctx* ctx);
+
 /* ---- stage 3: set post-processing + pose -------------------------------------------------------------------- */
 /* replaces: PostProcess.forward (RV/models/detr_speed.py:264-293), SimplePoseSolver.__call__
  * (RV/utils/speed_eval.py:164-242), SimplePoseSolverSigma (SA/utils/speed_eval.py:322-420).
@@ -115,6 +126,12 @@ typedef struct {
   const float* reproj_thresh_dev; /* optional [B] fp32: per-image RANSAC threshold instead of reproj_thresh -- the SA solver
                                      derives it from the detection area, int(area / input_size * 10) clamped to [1.5, 20]
                                      (SA/utils/speed_eval_ceres.py:53-58)                                          */
+  int inputs_post_processed; /* 1: `logits` are PostProcess OUTPUTS -- class probabilities, used as scores without another
+                                softmax, so the assignment sees exactly the numbers the reference's solver sees -- and
+                                `points` original-image pixels (pass boxes (0,0,1,1)): the reference's per-image
+                                solver(points, logits) signature (RV/utils/speed_eval.py:164-200)                     */
+  float sigma_px_scale;      /* with inputs_post_processed: crop side in pixels for the reject filter's sigma criterion
+                                (sigmas are in normalised crop units); 0 = criterion skipped                        */
 } spe_pnp_params;
 
 int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_dev, const float* log_sigma_dev,
@@ -205,6 +222,9 @@ int spe_profile_collect(double* ms_by_family /*[6]*/, long long* launches_by_fam
  * weights collapse to one label, which would make the solve exit early); NULL resets */
 int spe_debug_set_pnp_override(spe_ctx* ctx, const float* logits_dev, const float* points_dev,
                                const int32_t* boxes_dev);
+/* test hook: how many (batch size, buffer set) keys of the forward schedule replay a captured CUDA graph, and for how
+ * many the capture failed (those keep running kernel by kernel) */
+int spe_debug_graph_stats(const spe_ctx* ctx, int* captured, int* failed);
 /* test hook: network outputs (logits [B,Q,12], points [B,Q,2]) of the batch last collected from pipeline `slot` */
 int spe_debug_read_slot_outputs(spe_ctx* ctx, int slot, float* logits_host, float* points_host);
 

@@ -15,6 +15,8 @@ Fixtures written:
   crop_golden.npz     reference crop boxes + uint8 resized crops for a spread of boxes
   model_golden.npz    reference model outputs for seeded weights/inputs (weights are regenerated, never stored)
   pnp_golden.npz      reference SimplePoseSolver poses for seeded synthetic predictions
+  model_b256_golden.npz  reference model (calibrated heads, oracle/make_chain_fixture.py) + PostProcess + solver on the
+                      256 crops of the benchmarked frame sets; sigma head through the SA drop's own MLP class
 """
 import json
 import os
@@ -216,6 +218,88 @@ def write_model():
     np.savez_compressed(os.path.join(GOLDEN, "model_golden.npz"), **out)
 
 
+B256_SETS = 4                     # synth.bench_set(0..3): the frames bench.py times (sets 0, 1) + two more
+
+
+def b256_inputs():
+    """The 256 crops of the batch-64 / batch-256 parity goldens: oracle crops (cv2) of synth.bench_set(0..3)."""
+    crops, clips = [], []
+    for s in range(B256_SETS):
+        frames, det = synth.bench_set(s)
+        for i in range(len(frames)):
+            t, c = crop_ref.crop_resize_normalize(frames[i], det[i], 224)
+            crops.append(t); clips.append(c)
+    return torch.stack(crops), np.stack(clips)
+
+
+def write_model_b256(rv_eval):
+    """The benchmarked configurations end to end: the LIVE reference model (calibrated heads, so its queries emit 11
+    distinct labels) on 256 crops, the reference's own PostProcess + SimplePoseSolver behind it, and the sigma head
+    evaluated by the SA drop's own ``MLP`` class (SA/src/zoo/rtdetr/rtdetr_decoder.py:24-37, :295-297, :367)."""
+    import cv2
+    cfg = ModelCfg(sigma_head=True)
+    sd = synth.make_state_dict(cfg, seed=0, spread_labels=True)
+    rv_sd = {k: v for k, v in sd.items() if not k.startswith("sigma_embed.")}
+    model, _, _ = ref_import.build_reference_model(ModelCfg(), rv_sd)
+    hs_store = {}
+    model.transformer.register_forward_hook(lambda m, i, o: hs_store.__setitem__("hs", o[0]))
+    x, clips = b256_inputs()
+    logits, points, hs_last = [], [], []
+    with torch.no_grad():
+        for i in range(0, len(x), 32):
+            ref = model(x[i:i + 32])
+            logits.append(ref["pred_logits"]); points.append(ref["pred_points"]); hs_last.append(hs_store["hs"][-1])
+    logits, points, hs_last = torch.cat(logits), torch.cat(points), torch.cat(hs_last)
+    port = model_ref.forward(sd, cfg, x[:16])
+    err = max((port["pred_logits"] - logits[:16]).abs().max().item(), (port["pred_points"] - points[:16]).abs().max().item())
+    print("b256: restatement vs live reference max|d|", err)
+    assert err < 1e-4
+    # sigma head through the SA drop's own MLP module
+    sa = ref_import.import_sa_rtdetr()
+    from src.zoo.rtdetr.rtdetr_decoder import MLP as SA_MLP
+    mlp = SA_MLP(256, 256, 1, num_layers=3)
+    mlp.load_state_dict({k[len("sigma_embed."):]: v for k, v in sd.items() if k.startswith("sigma_embed.")}, strict=True)
+    with torch.no_grad():
+        sig = mlp(hs_last).repeat(1, 1, 2)                                   # rtdetr_decoder.py:367
+    assert (sig[:16] - port["pred_sigmas"]).abs().max().item() < 1e-5
+    # the reference's own post-processing + solver on the reference's own network outputs
+    post = sys.modules["models"].PostProcess()
+    res = post({"pred_logits": logits, "pred_points": points.clone()}, [torch.from_numpy(c) for c in clips])
+    solver = rv_eval.SimplePoseSolver(synth.reference_args(ModelCfg()))
+    n = len(res)
+    quat = np.zeros((n, 4)); tvec = np.zeros((n, 3)); ok = np.zeros(n, dtype=np.int32)
+    for i, r in enumerate(res):
+        try:
+            q, t = solver(r["points"], r["logits"])
+            quat[i], tvec[i], ok[i] = q, t, 1
+        except (IndexError, cv2.error):
+            pass
+    assign = np.stack([pnp_ref.assign_table(r["points"], r["logits"]) for r in res])
+    np.savez_compressed(os.path.join(GOLDEN, "model_b256_golden.npz"),
+                        checksum=np.frombuffer(synth.weights_checksum(sd).encode(), dtype=np.uint8),
+                        pred_logits=logits.numpy(), pred_points=points.numpy(), pred_sigmas=sig.numpy(),
+                        clip_boxes=clips, quat=quat, tvec=tvec, ok=ok, assign=assign)
+    print("b256: reference chain solved", int(ok.sum()), "of", n, "; distinct labels per image",
+          np.unique((assign >= 0).sum(1)))
+
+
+def write_model_b64_random():
+    """BASELINE configs[1] as specified (random-init weights, batch 64): the live reference on the 64 crops of frame
+    set 0.  Every query collapses to one label with these weights, so only the network outputs are pinned here."""
+    cfg = ModelCfg()
+    sd = synth.make_state_dict(cfg, seed=0)
+    model, _, _ = ref_import.build_reference_model(cfg, sd)
+    x, _ = b256_inputs()
+    x = x[:64]
+    with torch.no_grad():
+        ref = [model(x[i:i + 32]) for i in range(0, 64, 32)]
+    np.savez_compressed(os.path.join(GOLDEN, "model_b64_random_golden.npz"),
+                        checksum=np.frombuffer(synth.weights_checksum(sd).encode(), dtype=np.uint8),
+                        pred_logits=torch.cat([r["pred_logits"] for r in ref]).numpy(),
+                        pred_points=torch.cat([r["pred_points"] for r in ref]).numpy())
+    print("b64 random-init golden written")
+
+
 def write_pnp(rv_eval, n=400):
     import cv2
     d = synth.make_predictions(n, seed=1)
@@ -299,6 +383,8 @@ def main():
     write_crop(rv_speed)
     write_crop_eval(rv_speed)
     write_model()
+    write_model_b256(rv_eval)
+    write_model_b64_random()
     write_pnp(rv_eval)
     write_pnp_multi(rv_eval)
 

@@ -59,3 +59,29 @@ def build_reference_model(cfg, state_dict=None):
     if state_dict is not None:
         model.load_state_dict(state_dict, strict=True)
     return model, criterion, postprocessors
+
+
+SA_ROOT = os.path.join(REFERENCE_ROOT, "Monocular Satellite Pose Estimation Based on Uncertainty Estimation and Self-Assessment")
+
+
+def import_sa_rtdetr():
+    """The SA drop's ``src.zoo.rtdetr`` package (``rtdetr_decoder.MLP`` / ``TransformerDecoder.sigma_embed``,
+    ``utils.deformable_attention_core_func``, ...).  The tree is not importable as shipped (SURVEY.md section 2b:
+    ``src/__init__.py`` expects ``nn`` / ``optim`` / ``solver`` under ``src/`` but they sit at the project root, and
+    ``nn/backbone/__init__.py`` needs ``timm``): a synthetic ``src`` namespace package spanning both directories is
+    registered instead -- no reference file is edited."""
+    import types
+    if "src.zoo.rtdetr" not in sys.modules:
+        src = types.ModuleType("src")
+        src.__path__ = [os.path.join(SA_ROOT, "src"), SA_ROOT]
+        sys.modules["src"] = src
+        nn_ = types.ModuleType("src.nn")
+        nn_.__path__ = [os.path.join(SA_ROOT, "nn")]
+        sys.modules["src.nn"] = nn_
+        bb = types.ModuleType("src.nn.backbone")
+        bb.__path__ = [os.path.join(SA_ROOT, "nn", "backbone")]
+        sys.modules["src.nn.backbone"] = bb
+        import src.core  # noqa: F401
+        import src.nn.backbone.presnet  # noqa: F401
+        import src.zoo.rtdetr  # noqa: F401
+    return sys.modules["src.zoo.rtdetr"]

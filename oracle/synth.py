@@ -65,8 +65,11 @@ def _ln(rng, sd, prefix, e):
 
 
 def make_state_dict(cfg: ModelCfg, seed=0, spread_labels=False):
-    """Random weights in the reference ``state_dict`` layout.  ``spread_labels`` biases ``cls_embed`` so that the
-    first 11 queries emit distinct foreground labels (random init collapses to one label)."""
+    """Random weights in the reference ``state_dict`` layout.  ``spread_labels`` swaps in the calibrated heads of
+    ``tests/golden/chain_heads.npz`` (oracle/make_chain_fixture.py): query embeddings x16, ``cls_embed`` and
+    ``point_embed`` fitted so that queries 0..10 emit the 11 keypoint labels at a PnP-consistent layout and the other
+    queries background -- random init collapses every query to one label, which would leave the
+    crop -> predictor -> PnP chain untestable on the network's own output."""
     rng = np.random.default_rng(seed)
     sd = {}
     b = "backbone.0.body"
@@ -122,7 +125,40 @@ def make_state_dict(cfg: ModelCfg, seed=0, spread_labels=False):
         _linear(rng, sd, "sigma_embed.layers.0", e, e)
         _linear(rng, sd, "sigma_embed.layers.1", e, e)
         _linear(rng, sd, "sigma_embed.layers.2", 1, e)
-    return {k: torch.from_numpy(v) for k, v in sd.items()}
+    sd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    if spread_labels:
+        apply_chain_heads(sd, cfg, seed)
+    return sd
+
+
+CHAIN_QUERY_SCALE = 16.0
+
+
+def apply_chain_heads(sd, cfg, seed):
+    """Overwrite the heads of the C* seed-0 weights with the calibrated ones (see ``make_state_dict``)."""
+    assert seed == 0 and cfg.stride8 and (cfg.num_queries, cfg.enc_layers, cfg.dec_layers) == (40, 4, 4), \
+        "the calibrated heads exist for the canonical config C* with seed 0 only"
+    fx = np.load(os.path.join(GOLDEN_DIR, "chain_heads.npz"))
+    sd["query_embed.weight"] = sd["query_embed.weight"] * float(fx["query_embed_scale"])
+    for k in fx.files:
+        if k.startswith(("cls_embed.", "point_embed.")):
+            sd[k] = torch.from_numpy(fx[k].astype(np.float32))
+    if cfg.sigma_head:
+        # log-sigma around log(2 px / 430 px): random init would predict sigma ~ 1 crop side and reject every pose
+        sd["sigma_embed.layers.2.weight"] = sd["sigma_embed.layers.2.weight"] * 0.1
+        sd["sigma_embed.layers.2.bias"] = torch.full((1,), float(np.log(2.0 / 430.0)), dtype=torch.float32)
+    return sd
+
+
+def canonical_layout():
+    """Normalised (crop-relative) positions of the 11 Tango keypoints for one fixed attitude, target centred and
+    filling 1/1.2 of the crop like the detector boxes do: the layout the calibrated point head is fitted to."""
+    q = np.array([0.8, 0.3, -0.4, 0.33])
+    q /= np.linalg.norm(q)
+    pc = TANGO_POINTS @ quat_to_rot(q).T + np.array([0.0, 0.0, 8.0])
+    uv = pc[:, :2] / pc[:, 2:3]
+    lo, hi = uv.min(0), uv.max(0)
+    return (uv - (lo + hi) / 2) / ((hi - lo).max() * 1.2) + 0.5
 
 
 def weights_checksum(sd):
@@ -170,6 +206,21 @@ def make_frames(n, boxes, seed=0, H=IMG_H, W=IMG_W):
         noise = rng.integers(-6, 7, (H, W))
         frames[i] = np.clip(bg + noise, 0, 255).astype(np.uint8)
     return frames
+
+
+_BENCH_BASE = {}
+
+
+def bench_set(s, batch=64):
+    """Frame set ``s`` of bench.py (and of the B = 64 / 256 parity goldens): uint8 frames [batch, H, W] built from 8
+    seeded base frames shifted horizontally, with detector boxes ``s*batch .. (s+1)*batch`` of the real distribution."""
+    det_all = load_detector_boxes()
+    if "base" not in _BENCH_BASE:
+        _BENCH_BASE["base"] = make_frames(8, det_all, seed=100)
+    base = _BENCH_BASE["base"]
+    det = det_all[s * batch:(s + 1) * batch]
+    frames = np.concatenate([np.roll(base, 37 * (s * 8 + k), axis=2) for k in range(batch // 8)])
+    return frames, det
 
 
 # -------------------------------------------------------------------------------------------------------------

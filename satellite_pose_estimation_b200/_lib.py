@@ -23,7 +23,8 @@ class SpeTensorDesc(C.Structure):
 class SpePnpParams(C.Structure):
     _fields_ = [("reproj_thresh", C.c_float), ("weighted", C.c_int), ("reject", C.c_int),
                 ("reject_rms_px", C.c_float), ("reject_sigma_px", C.c_float), ("float_boxes_dev", C.c_void_p),
-                ("reproj_thresh_dev", C.c_void_p)]
+                ("reproj_thresh_dev", C.c_void_p), ("inputs_post_processed", C.c_int),
+                ("sigma_px_scale", C.c_float)]
 
 
 # every symbol include/spe.h declares: (restype, argtypes)
@@ -42,6 +43,8 @@ SYMBOLS = {
     "spe_speed_score": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "spe_crop_resize_norm": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _i, _i, _vp, _vp]),
     "spe_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spe_calibrate": (_i, [_vp, _vp, _i, _vp]),
+    "spe_is_calibrated": (_i, [_vp]),
     "spe_assign_pnp": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp]),
     "spe_ensemble_pnp": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -59,6 +62,7 @@ SYMBOLS = {
     "spe_profile_enable": (_i, [_i]),
     "spe_profile_collect": (_i, [_vp, _vp]),
     "spe_debug_set_pnp_override": (_i, [_vp, _vp, _vp, _vp]),
+    "spe_debug_graph_stats": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "spe_debug_read_slot_outputs": (_i, [_vp, _i, _vp, _vp]),
 }
 

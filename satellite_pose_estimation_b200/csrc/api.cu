@@ -44,6 +44,8 @@ struct PipeSlot {
   int32_t *boxes_h = nullptr, *status_h = nullptr;   // pinned
   double *quat_h = nullptr, *tvec_h = nullptr;       // pinned
   bool busy = false;
+  bool ready = false;                                // every buffer below was allocated
+  bool host_boxes = false;                           // boxes_h holds this batch's crop boxes (host submissions only)
   int B = 0;
 };
 // Every slot is a complete, independent instance of the path: its own streams, frame / result buffers and activation
@@ -62,32 +64,42 @@ Pipe& pipe_of(spe_ctx* ctx) {
 }
 }  // namespace
 
+static void slot_free(PipeSlot& S) {
+  if (S.stream) cudaStreamSynchronize(S.stream);
+  if (S.compute) cudaStreamSynchronize(S.compute);
+  if (S.frames_dev) cudaFree(S.frames_dev);
+  if (S.boxes_dev) cudaFree(S.boxes_dev);
+  if (S.status_dev) cudaFree(S.status_dev);
+  if (S.assign_dev) cudaFree(S.assign_dev);
+  if (S.quat_dev) cudaFree(S.quat_dev);
+  if (S.tvec_dev) cudaFree(S.tvec_dev);
+  if (S.logits_dev) cudaFree(S.logits_dev);
+  if (S.points_dev) cudaFree(S.points_dev);
+  if (S.logsig_dev) cudaFree(S.logsig_dev);
+  if (S.boxes_h) cudaFreeHost(S.boxes_h);
+  if (S.status_h) cudaFreeHost(S.status_h);
+  if (S.quat_h) cudaFreeHost(S.quat_h);
+  if (S.tvec_h) cudaFreeHost(S.tvec_h);
+  if (S.images_dev) cudaFree(S.images_dev);
+  if (S.upload_done) cudaEventDestroy(S.upload_done);
+  if (S.done) cudaEventDestroy(S.done);
+  if (S.stream) cudaStreamDestroy(S.stream);
+  if (S.compute) cudaStreamDestroy(S.compute);
+  S = PipeSlot();
+}
+
 namespace spe {
+bool pipeline_busy(spe_ctx* ctx) {
+  auto it = g_pipes.find(ctx);
+  if (it == g_pipes.end()) return false;
+  for (const PipeSlot& S : it->second->slot)
+    if (S.busy) return true;
+  return false;
+}
 void pipeline_release(spe_ctx* ctx) {   // called by spe_destroy
   auto it = g_pipes.find(ctx);
   if (it == g_pipes.end()) return;
-  for (PipeSlot& S : it->second->slot) {
-    if (S.stream) cudaStreamSynchronize(S.stream);
-    if (S.compute) cudaStreamSynchronize(S.compute);
-    if (S.frames_dev) cudaFree(S.frames_dev);
-    if (S.boxes_dev) cudaFree(S.boxes_dev);
-    if (S.status_dev) cudaFree(S.status_dev);
-    if (S.assign_dev) cudaFree(S.assign_dev);
-    if (S.quat_dev) cudaFree(S.quat_dev);
-    if (S.tvec_dev) cudaFree(S.tvec_dev);
-    if (S.logits_dev) cudaFree(S.logits_dev);
-    if (S.points_dev) cudaFree(S.points_dev);
-    if (S.logsig_dev) cudaFree(S.logsig_dev);
-    if (S.boxes_h) cudaFreeHost(S.boxes_h);
-    if (S.status_h) cudaFreeHost(S.status_h);
-    if (S.quat_h) cudaFreeHost(S.quat_h);
-    if (S.tvec_h) cudaFreeHost(S.tvec_h);
-    if (S.images_dev) cudaFree(S.images_dev);
-    if (S.upload_done) cudaEventDestroy(S.upload_done);
-    if (S.done) cudaEventDestroy(S.done);
-    if (S.stream) cudaStreamDestroy(S.stream);
-    if (S.compute) cudaStreamDestroy(S.compute);
-  }
+  for (PipeSlot& S : it->second->slot) slot_free(S);
   Pipe* P = it->second;
   if (P->caller_ready) cudaEventDestroy(P->caller_ready);
   delete it->second;
@@ -99,6 +111,9 @@ extern "C" {
 
 int spe_clip_boxes(const double* det, int B, int32_t* boxes) {
   if (!det || !boxes || B < 0) return set_error(nullptr, SPE_ERR_INVALID, "spe_clip_boxes: null argument");
+  for (int i = 0; i < 4 * B; ++i)     // int() of NaN / inf / 1e300 is undefined behaviour: refuse instead
+    if (!std::isfinite(det[i]) || std::fabs(det[i]) > 1e8)
+      return set_error(nullptr, SPE_ERR_INVALID, "spe_clip_boxes: non-finite or absurd detector box");
   for (int i = 0; i < B; ++i) {
     // SpeedSubmission.generate_clip_bbox, RV/datasets/speed.py:92-108 (float64; int() truncates toward zero)
     const double x1 = det[4 * i + 0], y1 = det[4 * i + 1], x2 = det[4 * i + 2], y2 = det[4 * i + 3];
@@ -115,6 +130,9 @@ int spe_clip_boxes(const double* det, int B, int32_t* boxes) {
 
 int spe_clip_boxes_val(const double* det, int B, int W, int H, double* fbox, int32_t* ibox) {
   if (!det || !fbox || !ibox || B < 0) return set_error(nullptr, SPE_ERR_INVALID, "spe_clip_boxes_val: null argument");
+  for (int i = 0; i < 4 * B; ++i)
+    if (!std::isfinite(det[i]) || std::fabs(det[i]) > 1e8)
+      return set_error(nullptr, SPE_ERR_INVALID, "spe_clip_boxes_val: non-finite or absurd detector box");
   for (int i = 0; i < B; ++i) {
     // SpeedTrain.generate_clip_bbox_val, RV/datasets/speed.py:246-260 (float64; x clipped to [0,W], y to [0,H])
     const double x1 = det[4 * i + 0], y1 = det[4 * i + 1], x2 = det[4 * i + 2], y2 = det[4 * i + 3];
@@ -165,6 +183,7 @@ int spe_assign_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_de
   d.reject = params->reject;
   d.reject_rms_px = params->reject_rms_px > 0 ? params->reject_rms_px : 5.0f;
   d.reject_sigma = params->reject_sigma_px > 0 ? params->reject_sigma_px : 12.0f;
+  d.post_processed = params->inputs_post_processed; d.sigma_px_scale = params->sigma_px_scale;
   d.quat = quat_dev; d.tvec = tvec_dev; d.assign = assign_dev; d.status = status_dev;
   d.probs = probs_dev; d.points_px = points_px_dev; d.sigmas = sigmas_dev; d.inlier_mask = inlier_mask_dev;
   std::string s = launch_assign_pnp(d, static_cast<cudaStream_t>(stream));
@@ -201,6 +220,7 @@ int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_
   d.reject = params->reject;
   d.reject_rms_px = params->reject_rms_px > 0 ? params->reject_rms_px : 5.0f;
   d.reject_sigma = params->reject_sigma_px > 0 ? params->reject_sigma_px : 12.0f;
+  d.post_processed = params->inputs_post_processed; d.sigma_px_scale = params->sigma_px_scale;
   d.quat = quat_dev; d.tvec = tvec_dev; d.assign = count_dev; d.status = status_dev;
   d.pooled_px = pooled_px_dev; d.inlier_mask = inlier_mask_dev;
   std::string s = launch_assign_pnp(d, static_cast<cudaStream_t>(stream));
@@ -289,7 +309,7 @@ static int pipe_prepare(spe_ctx* ctx, const char* who, int slot, int B, Pipeline
     e = cudaEventCreateWithFlags(&P.caller_ready, cudaEventDisableTiming);
     if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline: ") + cudaGetErrorString(e));
   }
-  if (!S.stream) {
+  if (!S.ready) {
     e = cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S.compute, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.upload_done, cudaEventDisableTiming);
@@ -307,7 +327,13 @@ static int pipe_prepare(spe_ctx* ctx, const char* who, int slot, int B, Pipeline
     if (e == cudaSuccess) e = cudaMallocHost(&S.quat_h, sizeof(double) * 4 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMallocHost(&S.tvec_h, sizeof(double) * 3 * pb.max_batch);
     if (e == cudaSuccess) e = cudaMallocHost(&S.status_h, sizeof(int32_t) * pb.max_batch);
-    if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline slot: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      // a half-built slot must not look initialised to the next submit: release what was allocated
+      cudaGetLastError();
+      slot_free(S);
+      return set_error(ctx, SPE_ERR_CUDA, std::string("pipeline slot: ") + cudaGetErrorString(e));
+    }
+    S.ready = true;
   }
   *Pp = &P;
   *Sp = &S;
@@ -341,6 +367,7 @@ static int pipe_enqueue(spe_ctx* ctx, const char* who, int slot, const PipelineB
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
   S.busy = true;
   S.B = B;
+  S.host_boxes = (boxes_dev == S.boxes_dev);   // spe_submit_batch_host computed S.boxes_h for this batch
   return SPE_OK;
 }
 
@@ -420,7 +447,10 @@ int spe_collect_batch_host(spe_ctx* ctx, int slot, double* quat_host, double* tv
   memcpy(quat_host, S.quat_h, sizeof(double) * 4 * S.B);
   memcpy(tvec_host, S.tvec_h, sizeof(double) * 3 * S.B);
   memcpy(status_host, S.status_h, sizeof(int32_t) * S.B);
-  if (boxes_host) memcpy(boxes_host, S.boxes_h, sizeof(int32_t) * 4 * S.B);   // host submits only (clip boxes)
+  if (boxes_host) {   // the crop boxes libspe computed: host submissions only (device submissions brought their own)
+    if (S.host_boxes) memcpy(boxes_host, S.boxes_h, sizeof(int32_t) * 4 * S.B);
+    else memset(boxes_host, 0, sizeof(int32_t) * 4 * S.B);
+  }
   return SPE_OK;
 }
 

@@ -74,7 +74,11 @@ template <> __device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-template <typename T, int KT>
+// X3 (fp32 storage only): error-compensated products, S = Q_hi K_hi + Q_lo K_hi + Q_hi K_lo and likewise P V, with
+// x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi): fp32-grade scores whatever their magnitude.  Used by the decoder, whose
+// learned query embeddings can drive the self-attention logits into the hundreds, where plain TF32 operands are off by
+// tenths of a logit.
+template <typename T, int KT, bool X3>
 __global__ void __launch_bounds__(128)
 attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ out,
                  int ldq, int ldk, int ldv, int ldo, long long bsq, long long bsk, long long bsv, long long bso,
@@ -83,6 +87,8 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   pdl_launch();
   __shared__ __align__(16) float Ks[KT * KLD];
   __shared__ __align__(16) float Vs[KT * KLD];
+  __shared__ __align__(16) float Kl[X3 ? KT * KLD : 4];   // low parts
+  __shared__ __align__(16) float Vl[X3 ? KT * KLD : 4];
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * QT;
@@ -97,13 +103,20 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   const int r0 = q0 + warp * 16 + g;
   const int r1 = r0 + 8;
   float qa[4][4];
+  float ql[X3 ? 4 : 1][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     const int c = ks * 8 + t;
-    qa[ks][0] = r0 < Lq ? to_tf32(load1(qb + static_cast<long long>(r0) * ldq + c) * scale_log2e) : 0.f;
-    qa[ks][1] = r1 < Lq ? to_tf32(load1(qb + static_cast<long long>(r1) * ldq + c) * scale_log2e) : 0.f;
-    qa[ks][2] = r0 < Lq ? to_tf32(load1(qb + static_cast<long long>(r0) * ldq + c + 4) * scale_log2e) : 0.f;
-    qa[ks][3] = r1 < Lq ? to_tf32(load1(qb + static_cast<long long>(r1) * ldq + c + 4) * scale_log2e) : 0.f;
+    float x[4];
+    x[0] = r0 < Lq ? load1(qb + static_cast<long long>(r0) * ldq + c) * scale_log2e : 0.f;
+    x[1] = r1 < Lq ? load1(qb + static_cast<long long>(r1) * ldq + c) * scale_log2e : 0.f;
+    x[2] = r0 < Lq ? load1(qb + static_cast<long long>(r0) * ldq + c + 4) * scale_log2e : 0.f;
+    x[3] = r1 < Lq ? load1(qb + static_cast<long long>(r1) * ldq + c + 4) * scale_log2e : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      qa[ks][e] = to_tf32(x[e]);
+      if constexpr (X3) ql[ks][e] = to_tf32(x[e] - qa[ks][e]);
+    }
   }
 
   float o[4][4];
@@ -125,10 +138,21 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       }
       float* kd = Ks + row * KLD + c8;
       float* vd = Vs + row * KLD + c8;
-      *reinterpret_cast<float4*>(kd) = make_float4(to_tf32(kk[0]), to_tf32(kk[1]), to_tf32(kk[2]), to_tf32(kk[3]));
-      *reinterpret_cast<float4*>(kd + 4) = make_float4(to_tf32(kk[4]), to_tf32(kk[5]), to_tf32(kk[6]), to_tf32(kk[7]));
-      *reinterpret_cast<float4*>(vd) = make_float4(to_tf32(vv[0]), to_tf32(vv[1]), to_tf32(vv[2]), to_tf32(vv[3]));
-      *reinterpret_cast<float4*>(vd + 4) = make_float4(to_tf32(vv[4]), to_tf32(vv[5]), to_tf32(vv[6]), to_tf32(vv[7]));
+      float kh[8], vh[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { kh[e] = to_tf32(kk[e]); vh[e] = to_tf32(vv[e]); }
+      *reinterpret_cast<float4*>(kd) = make_float4(kh[0], kh[1], kh[2], kh[3]);
+      *reinterpret_cast<float4*>(kd + 4) = make_float4(kh[4], kh[5], kh[6], kh[7]);
+      *reinterpret_cast<float4*>(vd) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+      *reinterpret_cast<float4*>(vd + 4) = make_float4(vh[4], vh[5], vh[6], vh[7]);
+      if constexpr (X3) {
+        float* kld = Kl + row * KLD + c8;
+        float* vld = Vl + row * KLD + c8;
+        *reinterpret_cast<float4*>(kld) = make_float4(to_tf32(kk[0] - kh[0]), to_tf32(kk[1] - kh[1]), to_tf32(kk[2] - kh[2]), to_tf32(kk[3] - kh[3]));
+        *reinterpret_cast<float4*>(kld + 4) = make_float4(to_tf32(kk[4] - kh[4]), to_tf32(kk[5] - kh[5]), to_tf32(kk[6] - kh[6]), to_tf32(kk[7] - kh[7]));
+        *reinterpret_cast<float4*>(vld) = make_float4(to_tf32(vv[0] - vh[0]), to_tf32(vv[1] - vh[1]), to_tf32(vv[2] - vh[2]), to_tf32(vv[3] - vh[3]));
+        *reinterpret_cast<float4*>(vld + 4) = make_float4(to_tf32(vv[4] - vh[4]), to_tf32(vv[5] - vh[5]), to_tf32(vv[6] - vh[6]), to_tf32(vv[7] - vh[7]));
+      }
     }
     __syncthreads();
 
@@ -138,6 +162,14 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     for (int j = 0; j < KT / 8; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       const float* kr = Ks + (j * 8 + g) * KLD + t;
+      if constexpr (X3) {
+        const float* kl = Kl + (j * 8 + g) * KLD + t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {     // small terms first
+          mma_tf32(s[j], ql[ks], kr[ks * 8], kr[ks * 8 + 4]);
+          mma_tf32(s[j], qa[ks], kl[ks * 8], kl[ks * 8 + 4]);
+        }
+      }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) mma_tf32(s[j], qa[ks], kr[ks * 8], kr[ks * 8 + 4]);
     }
@@ -178,6 +210,18 @@ attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       pa[0] = to_tf32(s[j][0]); pa[1] = to_tf32(s[j][2]); pa[2] = to_tf32(s[j][1]); pa[3] = to_tf32(s[j][3]);
       const float* vr0 = Vs + (j * 8 + 2 * t) * KLD + g;
       const float* vr1 = vr0 + KLD;
+      if constexpr (X3) {
+        float pl[4];
+        pl[0] = to_tf32(s[j][0] - pa[0]); pl[1] = to_tf32(s[j][2] - pa[1]);
+        pl[2] = to_tf32(s[j][1] - pa[2]); pl[3] = to_tf32(s[j][3] - pa[3]);
+        const float* vl0 = Vl + (j * 8 + 2 * t) * KLD + g;
+        const float* vl1 = vl0 + KLD;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          mma_tf32(o[d], pl, vr0[d * 8], vr1[d * 8]);
+          mma_tf32(o[d], pa, vl0[d * 8], vl1[d * 8]);
+        }
+      }
 #pragma unroll
       for (int d = 0; d < 4; ++d) mma_tf32(o[d], pa, vr0[d * 8], vr1[d * 8]);
     }
@@ -206,11 +250,26 @@ std::string launch_attn_t(const AttnDesc& d, cudaStream_t s) {
   const T* v = reinterpret_cast<const T*>(d.v);
   T* o = reinterpret_cast<T*>(d.out);
   ProfScope ps(kFamAttention, s);
+  if constexpr (sizeof(T) == 4) {
+    if (d.exact_out) {
+      // the decoder's attention (its GEMMs are 3xTF32): compensated products; half-size tiles keep the four operand
+      // tiles within the 48 KB of static shared memory
+      if (d.Lk % 56 == 0) {
+        SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 56, true>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo,
+                                d.bsq, d.bsk, d.bsv, d.bso, d.Lq, d.Lk, sl2, d.exact_out));
+      } else {
+        SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 64, true>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo,
+                                d.bsq, d.bsk, d.bsv, d.bso, d.Lq, d.Lk, sl2, d.exact_out));
+      }
+      SPE_CUDA_TRY(cudaGetLastError());
+      return "";
+    }
+  }
   if (d.Lk % 112 == 0) {
-    SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 112>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq,
+    SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 112, false>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq,
                             d.bsk, d.bsv, d.bso, d.Lq, d.Lk, sl2, d.exact_out));
   } else {
-    SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 64>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq,
+    SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 64, false>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo, d.bsq,
                             d.bsk, d.bsv, d.bso, d.Lq, d.Lk, sl2, d.exact_out));
   }
   SPE_CUDA_TRY(cudaGetLastError());

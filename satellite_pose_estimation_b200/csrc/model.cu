@@ -73,6 +73,77 @@ __global__ void addend_kernel(const float* __restrict__ X, int T, int K, const f
   out[static_cast<long long>(t) * out_ld + ncol0 + n] = acc + (b ? b[n] : 0.f);
 }
 
+// ---- calibration (spe_calibrate): per-column sums of a GEMM's A operand, and the bias correction they imply ----
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// what the tensor core makes of a stored operand: kind::tf32 ignores the low 13 mantissa bits (truncation); bf16 is exact
+__device__ __forceinline__ float as_mma_operand(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ float as_mma_operand(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// sum[c] += sum over rows of A[r, c], sum_mma[c] += the same over the values the tensor core reads
+// (A [M, C], row stride lda elements; both pre-zeroed)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ A, long long M, int C, long long lda, float* __restrict__ sum,
+                              float* __restrict__ sum_mma) {
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = rows_per_block * blockIdx.x;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f, acc_t = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      const T v = A[r * lda + c];
+      acc += to_f32(v);
+      acc_t += as_mma_operand(v);
+    }
+    atomicAdd(sum + c, acc);
+    atomicAdd(sum_mma + c, acc_t);
+  }
+}
+// channel sums of an NCHW fp32 image batch: sum[c] += sum over (n, h, w); C channels, HW pixels per plane
+__global__ void nchw_chansum_kernel(const float* __restrict__ x, int NB, int C, long long HW, float* __restrict__ sum) {
+  const int plane = blockIdx.x;                 // n * C + c
+  if (plane >= NB * C) return;
+  const float* p = x + static_cast<long long>(plane) * HW;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < HW; i += blockDim.x) acc += p[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sum + plane % C, acc);
+}
+// One warp per output channel n: delta = scale[n] * sum_k (W32[n,k] * mean[k % C] - W[n,k] * mean_mma[k % C]) -- what
+// the product of the stored (rounded) weights and the operand as the tensor core reads it (fp32 activations that were
+// left unrounded are truncated to TF32) loses on the mean activation -- folded into the layer's bias (or, for the
+// projections whose bias lives in a batch-broadcast addend, into every row of that addend).  `applied` remembers the
+// correction so that a second calibration replaces the first instead of stacking on it.
+template <typename T>
+__global__ void bias_correction_kernel(const float* __restrict__ w32, const T* __restrict__ w, const float* __restrict__ colsum,
+                                       const float* __restrict__ colsum_mma,
+                                       float inv_rows, int N, int K, int C, const float* __restrict__ scale,
+                                       float* __restrict__ bias, float* __restrict__ applied, float* __restrict__ addend,
+                                       int addend_rows, int addend_ld) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* a = w32 + static_cast<long long>(n) * K;
+  const T* b = w + static_cast<long long>(n) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const int c = k % C;
+    acc += (a[k] * colsum[c] - to_f32(b[k]) * colsum_mma[c]) * inv_rows;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const float delta = (scale ? scale[n] : 1.0f) * acc;
+  const float d = delta - applied[n];
+  __syncwarp();
+  if (bias != nullptr) {
+    if (lane == 0) bias[n] += d;
+  } else if (addend != nullptr) {
+    for (int t = lane; t < addend_rows; t += 32) addend[static_cast<long long>(t) * addend_ld + n] += d;
+  }
+  __syncwarp();
+  if (lane == 0) applied[n] = delta;
+}
+
 // round-to-nearest (ties away) fp32 -> TF32, the host twin of cvt.rna.tf32.f32
 inline float host_rna_tf32(float x) {
   uint32_t u;
@@ -104,6 +175,12 @@ struct GemmW {          // one GEMM's parameters on the device
   float* bias = nullptr;
   int N = 0, K = 0;
   int x3 = 0;           // weights stored as [N, 2K] = [W_hi | W_lo] (3xTF32)
+  // calibration (spe_calibrate): the unrounded fp32 weights in the stored layout, the correction currently folded
+  // into `bias`, and -- for projections without a bias vector -- the batch-broadcast addend that takes it instead
+  float* w32 = nullptr;
+  float* applied = nullptr;
+  float* addend = nullptr;
+  int addend_rows = 0, addend_ld = 0;
 };
 
 struct Bottleneck {
@@ -141,6 +218,7 @@ struct GraphKey {
 struct GraphEntry {
   GraphKey key{};
   cudaGraphExec_t exec = nullptr;
+  bool failed = false;          // capture / instantiation failed for THIS key: it keeps running eagerly
   long long launches[kNumFamilies] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -201,6 +279,24 @@ struct spe_ctx {
   const int32_t* ov_boxes = nullptr;
   long long last_h2d = 0;            // bytes uploaded by the last spe_run_batch_host
 
+  // calibration state (spe_calibrate)
+  bool calibrating = false, calibrated = false;
+  float* colsum = nullptr;           // [2][4096] scratch: column sums of a layer's input as stored / as the MMA reads it
+  // fp32 storage: tensors that are both a GEMM operand and a residual (block outputs of the backbone, the encoder
+  // stream) stay UNROUNDED in HBM.  The tensor core truncates them on the fly -- same noise as rounding them, plus a
+  // small bias that spe_calibrate measures and folds into the biases -- while the skip path adds the exact values, so
+  // rounding noise no longer accumulates along the residual stream.  MEASURED AND LEFT OFF (SPE_EXACT_STREAM=1 enables
+  // it): the per-element error of the encoder memory drops (5.6e-4 -> 4.2e-4 relative) but the keypoints get WORSE
+  // (0.16 -> 0.21 px rms at S = 1748): truncation shrinks every operand by ~3.5e-4, a coherent gain error on every
+  // GEMM branch that a bias cannot absorb.
+  bool exact_stream = getenv("SPE_EXACT_STREAM") ? atoi(getenv("SPE_EXACT_STREAM")) != 0 : false;
+
+  // Stream capture is illegal on the legacy default stream (and on cudaStreamPerThread a capture would swallow
+  // unrelated work): calls that arrive on one of those run on this private non-blocking stream instead, ordered against
+  // the caller's stream by a pair of events, so they too replay their captured graph.
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+
   // forward schedule
   bool use_graphs = true;
   int sub_batch = 0;                 // 0 = automatic (L2-sized chunks)
@@ -215,6 +311,7 @@ struct spe_ctx {
 namespace spe {
 
 void pipeline_release(spe_ctx* ctx);   // api.cu
+bool pipeline_busy(spe_ctx* ctx);      // api.cu
 
 static std::string g_last_error;
 
@@ -255,7 +352,7 @@ static std::string upload_f32(spe_ctx* ctx, const float* host, long long n, floa
 
 // upload a host fp32 [N,K] matrix as GEMM weights in the storage dtype (tf32-rounded fp32 or bf16)
 static std::string upload_gemm_w(spe_ctx* ctx, const std::vector<float>& host, int N, int K, GemmW* g,
-                                 bool x3 = false) {
+                                 bool x3 = false, bool keep32 = true) {
   float* tmp = nullptr;
   const long long n = static_cast<long long>(N) * K;
   x3 = x3 && ctx->dt == kTF32;   // bf16 storage has its own (looser) accuracy contract
@@ -270,10 +367,18 @@ static std::string upload_gemm_w(spe_ctx* ctx, const std::vector<float>& host, i
   else if (ctx->dt == kTF32) f32_to_tf32_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<float*>(g->w), n);
   else f32_to_bf16_kernel<<<blocks, 256>>>(tmp, reinterpret_cast<__nv_bfloat16*>(g->w), n);
   e = cudaDeviceSynchronize();
-  cudaFree(tmp);
-  if (e != cudaSuccess) return std::string("convert weights: ") + cudaGetErrorString(e);
+  if (e != cudaSuccess) { cudaFree(tmp); return std::string("convert weights: ") + cudaGetErrorString(e); }
   g->N = N;
   g->K = K;
+  if (keep32 && !x3) {
+    // the unrounded weights stay on the device: spe_calibrate folds (W - round(W)) . mean(activation) into the bias
+    ctx->allocs.push_back(tmp);
+    g->w32 = tmp;
+    TRY_S(dmalloc(ctx, &g->applied, N));
+    SPE_CUDA_TRY(cudaMemset(g->applied, 0, sizeof(float) * N));
+  } else {
+    cudaFree(tmp);
+  }
   return "";
 }
 
@@ -405,6 +510,7 @@ static std::string load_mha_self(spe_ctx* ctx, WeightSource& ws, const std::stri
   // q and k see (x + pos); v sees x only
   TRY_S(make_addend(ctx, posX_dev, T, E, w->data, b->data, 2 * E, *addend, 3 * E, 0));
   TRY_S(make_addend(ctx, nullptr, T, E, w->data + 2 * E * E, b->data + 2 * E, E, *addend, 3 * E, 2 * E));
+  qkv->addend = *addend; qkv->addend_rows = T; qkv->addend_ld = 3 * E;
   TRY_S(load_linear(ctx, ws, p + ".out_proj", E, E, out, x3));
   return "";
 }
@@ -426,7 +532,7 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
         for (int r = 0; r < 7; ++r)
           for (int t = 0; t < 7; ++t)
             w2[static_cast<size_t>(o) * Kw + (r * 8 + t) * Cp + ch] = w->data[((o * 3 + ch) * 7 + r) * 7 + t];
-    TRY_S(upload_gemm_w(ctx, w2, 64, Kw, &ctx->stem2));
+    TRY_S(upload_gemm_w(ctx, w2, 64, Kw, &ctx->stem2, false, false));
     ctx->stem2.scale = ctx->stem.scale;
     ctx->stem2.bias = ctx->stem.bias;
   }
@@ -454,6 +560,12 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
   if (c.backbone == 0) {
     TRY_S(load_conv_bn(ctx, ws, "backbone.0.s8_latern", "", 256, 512, 1, &ctx->s8_lat));
     TRY_S(load_conv_bn(ctx, ws, "backbone.0.s16_latern", "", 256, 1024, 3, &ctx->s16_lat));
+    {
+      // both lateral convolutions are bias-free in the reference; a zero bias gives spe_calibrate a place for its correction
+      const std::vector<float> zeros(256, 0.f);
+      TRY_S(upload_f32(ctx, zeros.data(), 256, &ctx->s8_lat.bias));
+      TRY_S(upload_f32(ctx, zeros.data(), 256, &ctx->s16_lat.bias));
+    }
     TRY_S(load_conv_bn(ctx, ws, "backbone.0.output_conv", "", 512, 512, 3, &ctx->out_conv));
     TRY_S(load_vec(ctx, ws, "backbone.0.output_conv.bias", 512, &ctx->out_conv.bias));
   }
@@ -503,6 +615,7 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + E * E), E, E, &L.ca_q, true));
       TRY_S(dmalloc(ctx, &L.ca_q_addend, static_cast<long long>(Q) * E));
       TRY_S(make_addend(ctx, qe_dev, Q, E, w->data, bb->data, E, L.ca_q_addend, E, 0));
+      L.ca_q.addend = L.ca_q_addend; L.ca_q.addend_rows = Q; L.ca_q.addend_ld = E;
       // key/value projections of every layer share the encoder memory: stack them into one GEMM
       memcpy(kv_w.data() + static_cast<size_t>(i) * 2 * E * E, w->data + E * E, sizeof(float) * 2 * E * E);
       TRY_S(make_addend(ctx, pos_dev, T, E, w->data + E * E, bb->data + E, E, ctx->ca_kv_addend, LD * 2 * E,
@@ -530,10 +643,11 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
           float* row = w3.data() + static_cast<size_t>(n) * 3 * E;
           row[k] = hi; row[E + k] = hi; row[2 * E + k] = lo;
         }
-      TRY_S(upload_gemm_w(ctx, w3, LD * 2 * E, 3 * E, &ctx->ca_kv_all));
+      TRY_S(upload_gemm_w(ctx, w3, LD * 2 * E, 3 * E, &ctx->ca_kv_all, false, false));   // already error-compensated
       ctx->kv_split3 = true;
     } else {
       TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all));
+      ctx->ca_kv_all.addend = ctx->ca_kv_addend; ctx->ca_kv_all.addend_rows = T; ctx->ca_kv_all.addend_ld = LD * 2 * E;
       ctx->kv_split3 = false;
     }
     TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.weight", E, &ctx->dn_g));
@@ -622,6 +736,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
     ctx->ws_sets.assign(1, set0);
     ctx->ws_current = 0;
   }
+  TRY_S(dmalloc(ctx, &ctx->colsum, 8192));
   // pipeline buffers
   TRY_S(dmalloc(ctx, &ctx->boxes_dev, B * 4));
   TRY_S(dmalloc(ctx, &ctx->images_dev, B * 3 * R * R));
@@ -665,10 +780,37 @@ struct Fwd {
     return "";
   }
 
+  // spe_calibrate: measure the column means of this layer's input ([rows, C], row stride ld) and fold what the rounded
+  // weights lose on them into the layer's bias (see bias_correction_kernel)
+  std::string calibrate_layer(const void* A, long long rows, int C, long long ld, const GemmW& w) {
+    if (!ctx->calibrating || w.w32 == nullptr || w.x3 || rows <= 0) return "";
+    if (C > 4096) return "calibration: more than 4096 input channels";
+    if (w.bias == nullptr && w.addend == nullptr) return "";
+    SPE_CUDA_TRY(cudaMemsetAsync(ctx->colsum, 0, sizeof(float) * 8192, st));
+    float* cs = ctx->colsum;
+    float* cs_mma = ctx->colsum + 4096;
+    const unsigned blocks = static_cast<unsigned>(rows < 2048 ? rows : 2048);
+    const unsigned cgrid = static_cast<unsigned>((w.N + 7) / 8);
+    const float inv = 1.0f / static_cast<float>(rows);
+    if (dt == kTF32) {
+      colsum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(A), rows, C, ld, cs, cs_mma);
+      bias_correction_kernel<float><<<cgrid, 256, 0, st>>>(w.w32, static_cast<const float*>(w.w), cs, cs_mma, inv, w.N, w.K, C,
+                                                           w.scale, w.bias, w.applied, w.addend, w.addend_rows, w.addend_ld);
+    } else {
+      colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(A), rows, C, ld, cs, cs_mma);
+      bias_correction_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>(w.w32, static_cast<const __nv_bfloat16*>(w.w), cs, cs_mma, inv,
+                                                                   w.N, w.K, C, w.scale, w.bias, w.applied, w.addend,
+                                                                   w.addend_rows, w.addend_ld);
+    }
+    SPE_CUDA_TRY(cudaGetLastError());
+    return "";
+  }
+
   // out[M, N] = act(scale * A W^T + bias (+ residual))
   std::string gemm(const void* A, long long M, const GemmW& w, void* out, int out_ld, bool relu,
                    const void* residual = nullptr, int res_ld = 0, int res_mod = 0, int res_f32 = 0,
-                   bool use_scale_bias = true, int out_f32 = 0) {
+                   bool use_scale_bias = true, int out_f32 = 0, bool exact_out = false) {
+    TRY_S(calibrate_layer(A, M, w.K, w.K, w));
     GemmDesc d;
     d.mode = 0;
     d.A = A; d.M = M; d.K = w.K; d.lda = w.K;
@@ -679,13 +821,17 @@ struct Fwd {
     d.relu = relu ? 1 : 0;
     d.out = out; d.out_ld = out_ld;
     d.x3 = w.x3;
-    d.round_out = w.x3 ? 0 : 1;   // 3xTF32 chains keep full fp32 activations
+    // 3xTF32 chains keep full fp32 activations; so do outputs that no tensor-core GEMM reads (`exact_out`: values that
+    // only feed a residual add or a LayerNorm -- rounding them would add noise to the residual stream for nothing)
+    d.round_out = (w.x3 || exact_out) ? 0 : 1;
     d.out_f32 = out_f32;
     return launch_gemm(dt, d, ctx->num_sms, st);
   }
   // R x R convolution (pad = R/2, stride 1 or 2) as implicit GEMM; H = input extent
   std::string conv(const void* x, int H, int C, int R, int stride, const GemmW& w, void* out, int out_ld,
-                   bool relu) {
+                   bool relu, bool exact_out = false) {
+    // the mean is taken over every input position; the zero padding at the border is ignored (second-order)
+    TRY_S(calibrate_layer(x, static_cast<long long>(B) * H * H, C, C, w));
     GemmDesc d;
     d.mode = 1;
     d.A = x; d.NB = B; d.H = H; d.W = H; d.C = C; d.R = R; d.S = R; d.pad = R / 2; d.conv_stride = stride;
@@ -693,6 +839,7 @@ struct Fwd {
     d.scale = w.scale; d.bias = w.bias;
     d.relu = relu ? 1 : 0;
     d.out = out; d.out_ld = out_ld;
+    d.round_out = exact_out ? 0 : 1;
     return launch_gemm(dt, d, ctx->num_sms, st);
   }
   std::string conv3x3(const void* x, int H, int C, const GemmW& w, void* out, int out_ld, bool relu) {
@@ -718,6 +865,12 @@ struct Fwd {
 
 }  // namespace
 
+// Unrounded residual stream (see spe_ctx::exact_stream): only together with the calibration that removes the bias of the
+// tensor core's operand truncation -- an uncalibrated context keeps rounding every store.
+static bool exact_stream_on(const spe_ctx* ctx) {
+  return ctx->exact_stream && ctx->dt == kTF32 && (ctx->calibrated || ctx->calibrating);
+}
+
 // backbone + neck + input_proj + encoder for `B` images starting at `images`; the encoder output (memory) of those
 // images is left in Xc ([B * tokens, 256]).  Every other buffer is the shared scratch region, so consecutive chunks
 // reuse the same cache lines (the whole working set of a chunk is sized to stay L2-resident).
@@ -729,6 +882,21 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   const long long Bl = B;
 
   // ---- stem
+  if (ctx->calibrating && ctx->stem.w32 != nullptr) {
+    // channel means of the normalised image; the filter in im2col layout [64, 192] has k % 3 = channel
+    SPE_CUDA_TRY(cudaMemsetAsync(ctx->colsum, 0, sizeof(float) * 3, st));
+    nchw_chansum_kernel<<<B * 3, 256, 0, st>>>(images, B, 3, static_cast<long long>(R) * R, ctx->colsum);
+    const GemmW& w = ctx->stem;
+    const float inv = 1.0f / (static_cast<float>(B) * R * R);
+    if (f.dt == kTF32)
+      bias_correction_kernel<float><<<(w.N + 7) / 8, 256, 0, st>>>(w.w32, static_cast<const float*>(w.w), ctx->colsum, ctx->colsum,
+                                                                  inv, w.N, w.K, 3, w.scale, w.bias, w.applied, nullptr, 0, 0);
+    else
+      bias_correction_kernel<__nv_bfloat16><<<(w.N + 7) / 8, 256, 0, st>>>(w.w32, static_cast<const __nv_bfloat16*>(w.w),
+                                                                          ctx->colsum, ctx->colsum, inv, w.N, w.K, 3, w.scale,
+                                                                          w.bias, w.applied, nullptr, 0, 0);
+    SPE_CUDA_TRY(cudaGetLastError());
+  }
   bool stem_done = false;
   if (ctx->stem_windowed) {
     TRY_S(launch_stem_pad(f.dt, images, B, R, R, ctx->SP, st));
@@ -744,7 +912,13 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   }
   if (!stem_done) {
     TRY_S(launch_stem_im2col(f.dt, images, B, R, R, ctx->S0, st));
-    TRY_S(f.gemm(ctx->S0, Bl * h2 * h2, ctx->stem, ctx->S1, 64, true));
+    {
+      const bool cal = ctx->calibrating;
+      ctx->calibrating = false;                 // the stem was calibrated from the image channel means above
+      const std::string e = f.gemm(ctx->S0, Bl * h2 * h2, ctx->stem, ctx->S1, 64, true);
+      ctx->calibrating = cal;
+      if (!e.empty()) return e;
+    }
   }
   TRY_S(f.tap("stem", ctx->S1, Bl * h2 * h2 * 64));
   TRY_S(launch_maxpool3x3s2(f.dt, ctx->S1, B, h2, h2, 64, ctx->P0, st));
@@ -772,13 +946,13 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
       const void* identity = cur;
       if (bk.has_down) {
         if (bk.stride == 1) {
-          TRY_S(f.gemm(cur, Min, bk.down, ctx->DS, bk.planes * 4, false));
+          TRY_S(f.gemm(cur, Min, bk.down, ctx->DS, bk.planes * 4, false, nullptr, 0, 0, 0, true, 0, true));
         } else {
-          TRY_S(f.conv(cur, H, bk.inplanes, 1, 2, bk.down, ctx->DS, bk.planes * 4, false));  // 1x1 / stride 2
+          TRY_S(f.conv(cur, H, bk.inplanes, 1, 2, bk.down, ctx->DS, bk.planes * 4, false, true));  // 1x1 / stride 2
         }
         identity = ctx->DS;
       }
-      TRY_S(f.gemm(ctx->T2, Mout, bk.c3, nxt, bk.planes * 4, true, identity, bk.planes * 4));
+      TRY_S(f.gemm(ctx->T2, Mout, bk.c3, nxt, bk.planes * 4, true, identity, bk.planes * 4, 0, 0, true, 0, exact_stream_on(ctx)));
       cur = nxt;
       H = Ho;
     }
@@ -801,7 +975,7 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   } else {
     feat = ctx->L3OUT;
   }
-  TRY_S(f.gemm(feat, Bl * T, ctx->input_proj, Xc, 256, false));
+  TRY_S(f.gemm(feat, Bl * T, ctx->input_proj, Xc, 256, false, nullptr, 0, 0, 0, true, 0, exact_stream_on(ctx)));
   TRY_S(f.tap("input_proj", Xc, Bl * T * 256));
 
   // ---- encoder
@@ -818,8 +992,8 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
       TRY_S(f.gemm(Xc, Bl * T, L.qkv, q32, 768, false, L.addend, 768, Ti, 1, true, 1));
       TRY_S(f.attn(q32, 768, q32 + 256, 768, q32 + 512, 768, ctx->ATT, Ti, Ti, 0, 1));
     }
-    TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256));
-    TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc));
+    TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
+    TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc, exact_stream_on(ctx) ? 1 : 0));
     // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: emit it pre-split
     const bool last = i == c.enc_layers - 1;
     const bool split = last && ctx->kv_split3;
@@ -828,7 +1002,7 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
     // feed-forward block + norm2 in one kernel (the 2048-wide hidden activation stays in tensor memory); the tap of
     // the last layer needs both output forms, so bring-up runs take the unfused path there
     // (small batches keep the two-GEMM path: one 128-row tile per CTA cannot fill the machine below ~74 tiles)
-    if (ffn_fused_supported(f.dt, 256, c.dim_feedforward) && !(split && ctx->taps_enabled) &&
+    if (ffn_fused_supported(f.dt, 256, c.dim_feedforward) && !(split && ctx->taps_enabled) && !ctx->calibrating &&
         (Bl * T + 127) / 128 >= ctx->num_sms / 2) {
       FfnDesc d;
       d.X = Xc; d.M = Bl * T;
@@ -836,16 +1010,16 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
       d.gamma = L.n2g; d.beta = L.n2b;
       d.hidden = c.dim_feedforward;
       d.out = split ? XSc : Xc;
-      d.out_mode = split ? 2 : (last ? 1 : 0);
+      d.out_mode = split ? 2 : ((last || exact_stream_on(ctx)) ? 1 : 0);
       TRY_S(launch_ffn_fused(d, ctx->num_sms, st));
     } else {
       TRY_S(f.gemm(Xc, Bl * T, L.ff1, ctx->HID, c.dim_feedforward, true));
-      TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, Xc, 256));
+      TRY_S(f.gemm(ctx->HID, Bl * T, L.ff2, ctx->X2, 256, false, Xc, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
       if (split) {
         TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, XSc, 2));
         if (ctx->taps_enabled) TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, 1));
       } else {
-        TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, last ? 1 : 0));
+        TRY_S(f.ln(ctx->X2, L.n2g, L.n2b, Bl * T, Xc, (last || exact_stream_on(ctx)) ? 1 : 0));
       }
     }
     const std::string nm = "enc" + std::to_string(i);
@@ -860,6 +1034,7 @@ static std::string forward_kv(spe_ctx* ctx, int B, void* kv, cudaStream_t st) {
   Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
   const long long T = ctx->tokens;
   const int kvld = ctx->cfg.dec_layers * 512;
+  if (!ctx->kv_split3) TRY_S(f.calibrate_layer(ctx->X, static_cast<long long>(B) * T, 256, 256, ctx->ca_kv_all));
   GemmDesc d;
   d.mode = 0;
   d.A = ctx->kv_split3 ? ctx->XS : ctx->X;
@@ -982,35 +1157,67 @@ static std::string forward_schedule(spe_ctx* ctx, int parts, int kv_slot, const 
 
 // The schedule is a fixed sequence of ~150-600 launches: after one eager run per (batch, buffer set) it is captured
 // into a CUDA graph and replayed, which removes the per-launch CPU cost (tensor-map encodes, launch calls).
+static std::string forward_parts_on(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits,
+                                    float* points, float* logsig, float* aux_logits, float* aux_points, cudaStream_t st);
+
 std::string forward_parts(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits,
                           float* points, float* logsig, float* aux_logits, float* aux_points, cudaStream_t st) {
   const bool graphs_ok = ctx->use_graphs && !ctx->taps_enabled && !profile_timing_enabled();
   if (!graphs_ok)
     return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
+  const bool default_stream = st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
+  if (!default_stream)
+    return forward_parts_on(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
+  if (ctx->own_stream == nullptr) {
+    SPE_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    SPE_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+    SPE_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
+  }
+  SPE_CUDA_TRY(cudaEventRecord(ctx->ev_in, st));                       // everything the caller enqueued so far ...
+  SPE_CUDA_TRY(cudaStreamWaitEvent(ctx->own_stream, ctx->ev_in, 0));   // ... precedes the forward
+  std::string s = forward_parts_on(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points,
+                                   ctx->own_stream);
+  SPE_CUDA_TRY(cudaEventRecord(ctx->ev_out, ctx->own_stream));
+  SPE_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out, 0));               // and whatever the caller enqueues next follows it
+  return s;
+}
+
+static std::string forward_parts_on(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits,
+                                    float* points, float* logsig, float* aux_logits, float* aux_points, cudaStream_t st) {
   GraphKey key{B, images, logits, points, logsig, aux_logits, aux_points, parts, kv_slot};
   if (!(parts & 1)) key.images = nullptr;
   if (!(parts & 2)) key.logits = key.points = key.logsig = key.aux_l = key.aux_p = nullptr;
   for (auto& g : ctx->graphs) {
     if (!(g.key == key)) continue;
+    if (g.failed)       // this key could not be captured: eager, without giving up on the other keys
+      return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
     if (g.exec == nullptr) {
       // second call with this key: capture
       long long before[kNumFamilies];
       profile_peek_launches(before);
       cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
-      if (e != cudaSuccess) { ctx->use_graphs = false; cudaGetLastError(); break; }
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        g.failed = true;
+        return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
+      }
       std::string s = forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
       cudaGraph_t graph = nullptr;
       e = cudaStreamEndCapture(st, &graph);
       if (!s.empty() || e != cudaSuccess || graph == nullptr) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
-        ctx->use_graphs = false;
+        g.failed = true;
         if (!s.empty()) return s;
-        break;
+        // nothing ran during the broken capture: run this call eagerly
+        return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
       }
       e = cudaGraphInstantiate(&g.exec, graph, 0);
       cudaGraphDestroy(graph);
-      if (e != cudaSuccess) { g.exec = nullptr; ctx->use_graphs = false; cudaGetLastError(); break; }
+      if (e != cudaSuccess) {
+        g.exec = nullptr; g.failed = true; cudaGetLastError();
+        return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
+      }
       long long after[kNumFamilies];
       profile_peek_launches(after);
       for (int i = 0; i < kNumFamilies; ++i) g.launches[i] = after[i] - before[i];
@@ -1031,6 +1238,28 @@ std::string forward_parts(spe_ctx* ctx, int parts, int kv_slot, const float* ima
   }
   // first call: eager
   return forward_schedule(ctx, parts, kv_slot, images, B, logits, points, logsig, aux_logits, aux_points, st);
+}
+
+// One eager pass of the whole forward with the per-layer measurement switched on (see Fwd::calibrate_layer): layers are
+// corrected in schedule order, so every layer is measured on the already-corrected output of its predecessors.
+std::string calibrate_impl(spe_ctx* ctx, const float* images, int B, cudaStream_t st) {
+  const bool taps = ctx->taps_enabled;
+  ctx->taps_enabled = false;
+  ctx->calibrating = true;
+  std::string s = forward_schedule(ctx, 3, 0, images, B, ctx->p_logits, ctx->p_points,
+                                   ctx->cfg.has_sigma ? ctx->p_logsig : nullptr, nullptr, nullptr, st);
+  ctx->calibrating = false;
+  ctx->taps_enabled = taps;
+  if (!s.empty()) return s;
+  SPE_CUDA_TRY(cudaStreamSynchronize(st));
+  if (!ctx->calibrated) {
+    // the schedule changes with the first calibration (unrounded residual stream): drop the graphs captured before it
+    for (auto& g : ctx->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+  }
+  ctx->calibrated = true;
+  return "";
 }
 
 std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits, float* points, float* logsig,
@@ -1103,6 +1332,9 @@ void spe_destroy(spe_ctx* ctx) {
   pipeline_release(ctx);
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->frames_dev) cudaFree(ctx->frames_dev);
   delete ctx;
@@ -1124,6 +1356,7 @@ int spe_load_weights(spe_ctx* ctx, const spe_tensor_desc* tensors, int n) {
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   ctx->graphs.clear();               // captured launches point at the previous weights
+  ctx->calibrated = false;
   std::string s = load_weights_impl(ctx, ws);
   if (!s.empty()) return fail(ctx, SPE_ERR_WEIGHTS, "spe_load_weights: " + s);
   ctx->weights_loaded = true;
@@ -1151,6 +1384,27 @@ int spe_forward(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev,
   std::string s = forward_impl(ctx, images_dev, B, logits_dev, points_dev, log_sigma_dev, aux_logits_dev,
                                aux_points_dev, static_cast<cudaStream_t>(stream));
   if (!s.empty()) return fail(ctx, SPE_ERR_CUDA, "spe_forward: " + s);
+  return SPE_OK;
+}
+
+int spe_calibrate(spe_ctx* ctx, const float* images_dev, int B, void* stream) {
+  if (!ctx) return fail(nullptr, SPE_ERR_INVALID, "spe_calibrate: null ctx");
+  if (!ctx->weights_loaded) return fail(ctx, SPE_ERR_STATE, "spe_calibrate: call spe_load_weights first");
+  if (!images_dev) return fail(ctx, SPE_ERR_INVALID, "spe_calibrate: null buffer");
+  if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, SPE_ERR_INVALID, "spe_calibrate: batch outside [1, max_batch]");
+  if (pipeline_busy(ctx)) return fail(ctx, SPE_ERR_STATE, "spe_calibrate: collect every pipeline slot first (the biases it rewrites are shared)");
+  cudaSetDevice(ctx->device);
+  std::string s = calibrate_impl(ctx, images_dev, B, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return fail(ctx, SPE_ERR_CUDA, "spe_calibrate: " + s);
+  return SPE_OK;
+}
+
+int spe_is_calibrated(const spe_ctx* ctx) { return ctx && ctx->calibrated ? 1 : 0; }
+
+int spe_debug_graph_stats(const spe_ctx* ctx, int* captured, int* failed) {
+  if (!ctx || !captured || !failed) return SPE_ERR_INVALID;
+  *captured = *failed = 0;
+  for (const auto& g : ctx->graphs) { if (g.exec) ++*captured; if (g.failed) ++*failed; }
   return SPE_OK;
 }
 

@@ -581,10 +581,13 @@ assign_pnp_kernel(const PnpDesc d) {
         x[c] = lg[q * 12 + c];
         if (x[c] > mx) { mx = x[c]; am = c; }  // first maximum, like np.argmax
       }
-      float sum = 0.f;
+      float inv = 1.0f;
+      if (!d.post_processed) {               // raw class logits: PostProcess' softmax
+        float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 12; ++c) { x[c] = expf(x[c] - mx); sum += x[c]; }
-      const float inv = 1.0f / sum;
+        for (int c = 0; c < 12; ++c) { x[c] = expf(x[c] - mx); sum += x[c]; }
+        inv = 1.0f / sum;
+      }                                       // else: PostProcess output, the probabilities ARE the scores
       const float score = x[am] * inv;
       const long long gq = static_cast<long long>(img) * Q + q;
       if (d.probs) {
@@ -666,7 +669,9 @@ assign_pnp_kernel(const PnpDesc d) {
   for (int i = 0; i < 9; ++i) best.R[i] = 0.0;
   best.t[0] = best.t[1] = best.t[2] = 0.0;
   const double thr = static_cast<double>(d.reproj_dev ? d.reproj_dev[img] : d.reproj_thresh);
-  const double thr2 = thr * thr;
+  // exactly four correspondences: cv2.solvePnPRansac skips RANSAC (model_points == npoints), takes the P3P pose the
+  // fourth point selects and reports all four as inliers -- no threshold is applied
+  const double thr2 = n == 4 ? INFINITY : thr * thr;
   // Every thread first decodes its own triple index, then all lanes run the solver together: calling it from inside
   // the enumeration loop would serialise the warp (one active lane per iteration).
   const int ntriples = n * (n - 1) * (n - 2) / 6;
@@ -763,11 +768,14 @@ assign_pnp_kernel(const PnpDesc d) {
   }
   const int ninl = __popc(inl_mask);
   const double rms = sqrt(wsum(e2) / ninl);
-  const double mean_sigma_px = wsum(sg) / ninl * static_cast<double>(bw);  // sigma is in normalised crop units
+  // sigma is in normalised crop units: the crop side converts it to pixels (callers that hand over pixel keypoints
+  // pass the side separately; without it the sigma criterion cannot be evaluated and is skipped)
+  const double side = d.post_processed ? static_cast<double>(d.sigma_px_scale) : static_cast<double>(bw);
+  const double mean_sigma_px = wsum(sg) / ninl * side;
   int st = 0;
   if (d.reject) {
     const bool rej = (ninl < 4) || (rms > static_cast<double>(d.reject_rms_px)) ||
-                     (d.logsig != nullptr && mean_sigma_px > static_cast<double>(d.reject_sigma));
+                     (d.logsig != nullptr && side > 0.0 && mean_sigma_px > static_cast<double>(d.reject_sigma));
     if (rej) st = 3;
   }
   rot_to_quat(R, quat);

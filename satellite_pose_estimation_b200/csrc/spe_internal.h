@@ -131,6 +131,11 @@ struct PnpDesc {
   // query of every model is pooled per label (mean -> 3-sigma filter -> mean); `assign` then receives the number of
   // predictions each label's mean was taken over (0 = label absent)
   int num_models;
+  // inputs are PostProcess OUTPUTS: `logits` holds class probabilities (no softmax is applied: scores are compared bit
+  // for bit as the reference's solver sees them) and `points` original-image pixels (boxes must be (0,0,1,1));
+  // sigma_px_scale = crop side for the reject filter's sigma criterion (0: criterion skipped)
+  int post_processed;
+  float sigma_px_scale;
   float* pooled_px;      // [B,11,2] or null: the pooled keypoints in original-image pixels (0 where absent)
 };
 std::string launch_assign_pnp(const PnpDesc& d, cudaStream_t s);

@@ -162,6 +162,18 @@ class Engine:
             out["aux_outputs"] = [{"pred_logits": aux_l[i], "pred_points": aux_p[i]} for i in range(self.L - 1)]
         return out
 
+    def calibrate(self, images, max_images=16):
+        """Fold the mean effect of the TF32 / BF16 weight rounding into the layer biases, measured on ``images``
+        (float32 cuda [B,3,R,R], typically the first batch of crops; at most ``max_images`` are used).  See
+        ``spe_calibrate`` in include/spe.h.  Not while pipeline slots are in flight."""
+        assert images.is_cuda and images.dtype == torch.float32 and images.shape[1:] == (3, self.R, self.R)
+        x = images[:min(images.shape[0], max_images, self.max_batch)].contiguous()
+        check(self.lib.spe_calibrate(self._ctx, _ptr(x), x.shape[0], _stream(x.device)), self._ctx)
+
+    @property
+    def calibrated(self):
+        return bool(self.lib.spe_is_calibrated(self._ctx))
+
     def register_stable_input(self, tensor):
         """Declare a caller-owned, persistent, contiguous input buffer: ``forward`` reads it in place (no staging
         copy), keeping the CUDA-graph key stable."""
@@ -183,10 +195,13 @@ class Engine:
 
     # ---- stage 3 ---------------------------------------------------------------------------------------------
     def assign_pnp(self, logits, points, boxes, log_sigma=None, reproj=20.0, weighted=False, reject=False,
-                   reject_rms_px=5.0, reject_sigma_px=12.0, want_post=False):
+                   reject_rms_px=5.0, reject_sigma_px=12.0, want_post=False, post_processed=False, sigma_px_scale=0.0):
         """Batched PostProcess + assignment + PnP.  All inputs cuda; returns dict of cuda tensors.  Integer ``boxes``
         are the submission path's crop boxes; floating-point ``boxes`` [B,4] (x1,y1,x2,y2) are the eval path's
-        unrounded boxes (``clip_boxes_val``), applied like PostProcess applies a float64 ``clip_bbox``."""
+        unrounded boxes (``clip_boxes_val``), applied like PostProcess applies a float64 ``clip_bbox``.
+        ``post_processed``: ``logits`` are PostProcess outputs (class probabilities, used as scores as they are) and
+        ``points`` original-image pixels (``boxes`` must then be (0,0,1,1)); ``sigma_px_scale`` = crop side for the
+        reject filter's sigma criterion in that mode (0 skips the criterion)."""
         logits = logits.contiguous().float(); points = points.contiguous().float()
         fbox = None
         if boxes.is_floating_point():
@@ -215,7 +230,8 @@ class Engine:
         p = SpePnpParams(reproj_thresh=0.0 if thr is not None else float(reproj), weighted=int(weighted),
                          reject=int(reject), reject_rms_px=float(reject_rms_px), reject_sigma_px=float(reject_sigma_px),
                          float_boxes_dev=fbox.data_ptr() if fbox is not None else None,
-                         reproj_thresh_dev=thr.data_ptr() if thr is not None else None)
+                         reproj_thresh_dev=thr.data_ptr() if thr is not None else None,
+                         inputs_post_processed=int(bool(post_processed)), sigma_px_scale=float(sigma_px_scale))
         check(self.lib.spe_assign_pnp(self._ctx, _ptr(logits), _ptr(points), _ptr(log_sigma), _ptr(boxes), B, Q,
                                       C.byref(p), _ptr(quat), _ptr(tvec), _ptr(assign), _ptr(status), _ptr(probs),
                                       _ptr(pts_px), _ptr(sig), _ptr(inl), _stream(dev)), self._ctx)
@@ -226,7 +242,7 @@ class Engine:
                 out["sigmas"] = sig
         return out
 
-    def ensemble_pnp(self, logits, points, boxes, reproj=25.0, reject=False, want_pooled=False):
+    def ensemble_pnp(self, logits, points, boxes, reproj=25.0, reject=False, want_pooled=False, post_processed=False):
         """Batched ``Multi_Mean_PoseSolver`` (RV/utils/speed_eval.py:42-140): ``logits`` [Nm,B,Q,12] and ``points``
         [Nm,B,Q,2] are the raw outputs of the Nm ensemble members for the same B crops (cuda), ``boxes`` int [B,4]
         the crop boxes.  Returns dict of cuda tensors: quat, tvec, status, count [B,11] (predictions pooled per
@@ -243,7 +259,7 @@ class Engine:
         inl = torch.empty((B,), dtype=torch.int32, device=dev)
         pooled = torch.empty((B, 11, 2), dtype=torch.float32, device=dev) if want_pooled else None
         p = SpePnpParams(reproj_thresh=float(reproj), weighted=0, reject=int(reject), reject_rms_px=5.0,
-                         reject_sigma_px=12.0)
+                         reject_sigma_px=12.0, inputs_post_processed=int(bool(post_processed)))
         check(self.lib.spe_ensemble_pnp(self._ctx, _ptr(logits), _ptr(points), _ptr(boxes), Nm, B, Q, C.byref(p),
                                         _ptr(quat), _ptr(tvec), _ptr(count), _ptr(status), _ptr(pooled), _ptr(inl),
                                         _stream(dev)), self._ctx)
@@ -305,7 +321,16 @@ class Engine:
         check(self.lib.spe_collect_batch_host(self._ctx, slot, quat.ctypes.data_as(C.c_void_p),
                                               tvec.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
                                               boxes.ctypes.data_as(C.c_void_p)), self._ctx)
-        return {"quat": quat, "tvec": tvec, "status": status, "boxes": boxes, "h2d_bytes": h2d}
+        out = {"quat": quat, "tvec": tvec, "status": status, "h2d_bytes": h2d}
+        if not isinstance(frames_host, tuple):      # host submissions: the crop boxes libspe computed for this batch
+            out["boxes"] = boxes
+        return out
+
+    def graph_stats(self):
+        """Test hook: (keys of the forward schedule that replay a captured CUDA graph, keys whose capture failed)."""
+        a, b = C.c_int(0), C.c_int(0)
+        check(self.lib.spe_debug_graph_stats(self._ctx, C.byref(a), C.byref(b)), self._ctx)
+        return a.value, b.value
 
     def read_slot_outputs(self, slot, B):
         """Test hook: (logits [B,Q,12], points [B,Q,2]) the network produced for the batch last collected from `slot`."""

@@ -161,7 +161,7 @@ class B200DETR(nn.Module):
 
     def __init__(self, *, backbone="resnet50s8", num_queries=40, enc_layers=4, dec_layers=4, hidden_dim=256, nheads=8,
                  dim_feedforward=2048, aux_loss=True, input_size=None, precision="tf32", sigma_head=False,
-                 max_batch=64):
+                 max_batch=64, calibrate=True):
         super().__init__()
         if hidden_dim != 256 or nheads != 8:
             raise ValueError("libspe.so is built for hidden_dim=256, nheads=8 (every recipe of the reference)")
@@ -170,6 +170,9 @@ class B200DETR(nn.Module):
                                    dec_layers=dec_layers, hidden_dim=hidden_dim, nheads=nheads,
                                    dim_feedforward=dim_feedforward, sigma_head=sigma_head)
         self.input_size, self.precision, self.max_batch = input_size, precision, max_batch
+        # fold the mean effect of the TF32 / BF16 weight rounding into the biases, measured on the first batch this
+        # model sees after (re)loading weights (Engine.calibrate / spe_calibrate)
+        self.calibrate = bool(calibrate)
         gen = torch.Generator().manual_seed(0)
         for name, shape, is_buffer in param_specs(backbone, num_queries, enc_layers, dec_layers, hidden_dim,
                                                   dim_feedforward, sigma_head):
@@ -272,6 +275,9 @@ class B200DETR(nn.Module):
         if self.input_size is not None and R != self.input_size:
             raise ValueError(f"model was built for input_size={self.input_size}, got {R}")
         eng = self._get_engine(dev, R, x.shape[0])
+        if self.calibrate and not eng.calibrated:
+            eng.calibrate(x)
+
         def run(chunk):   # engine outputs live in persistent buffers: detach them from the next call
             o = eng.forward(chunk, want_aux=self.aux_loss)
             res = {k: v.clone() for k, v in o.items() if k != "aux_outputs"}
@@ -327,16 +333,34 @@ class PostProcess(nn.Module):
         return results
 
 
+class NoCriterion(nn.Module):
+    """Stand-in for ``SetCriterion`` (RV/models/detr_speed.py:103-261) on the inference path.  ``evaluate`` calls
+    ``criterion(outputs, targets)`` and reads ``criterion.weight_dict`` purely to log validation losses
+    (RV/engine.py:99-113); the training loss (Hungarian matching + set loss) is outside this path, so this returns
+    no weighted losses and ``class_error`` = NaN ("not computed" -- ``evaluate`` reads that key unconditionally), which
+    lets ``main.py --eval`` run unedited and log nothing misleading."""
+
+    def __init__(self):
+        super().__init__()
+        self.weight_dict = {}
+
+    def forward(self, outputs, targets):
+        dev = outputs["pred_logits"].device if isinstance(outputs, dict) and "pred_logits" in outputs else "cpu"
+        return {"class_error": torch.full((), float("nan"), device=dev)}
+
+
 def build_model(args):
     """Same contract as the reference's ``build_model(args)`` (RV/models/__init__.py:5-6 ->
     RV/models/detr_speed.py:296-336): returns ``(model, criterion, postprocessors)``.  ``criterion`` (training loss)
-    is outside this path and returned as ``None``.  Additive optional attributes on ``args``:
-    ``precision`` ('tf32' | 'bf16'), ``sigma_head`` (bool), ``max_batch`` (int), ``input_size``."""
+    is outside this path: a ``NoCriterion`` that yields no losses keeps ``engine.evaluate`` running unedited.  Additive optional attributes on ``args``:
+    ``precision`` ('tf32' | 'bf16'), ``sigma_head`` (bool), ``max_batch`` (int), ``input_size``, ``calibrate`` (bool,
+    default True: rounding-bias calibration on the first batch, see ``Engine.calibrate``)."""
     model = B200DETR(
         backbone=args.backbone, num_queries=args.num_queries, enc_layers=args.enc_layers, dec_layers=args.dec_layers,
         hidden_dim=args.hidden_dim, nheads=args.nheads, dim_feedforward=args.dim_feedforward,
         aux_loss=getattr(args, "aux_loss", True), input_size=getattr(args, "input_size", None),
         precision=getattr(args, "precision", "tf32"), sigma_head=getattr(args, "sigma_head", False),
+        calibrate=getattr(args, "calibrate", True),
         max_batch=getattr(args, "max_batch", None) or max(int(getattr(args, "batch_size", 64) or 64), 1))
     if is_stride8(args.backbone):
         args.backbone = "resnet50"   # the reference's build_backbone rewrites it too (RV/models/backbone.py:193)
@@ -344,4 +368,4 @@ def build_model(args):
                        weighted=bool(getattr(args, "sigma_head", False)),
                        reject=bool(getattr(args, "self_assessment", False)))
     model.eval()   # like the reference, the caller moves it: model.to(device)
-    return model, None, {"points": post}
+    return model, NoCriterion(), {"points": post}

@@ -37,9 +37,12 @@ class BatchedPoseSolver:
         return self.engine.assign_pnp(logits, points, boxes, log_sigma=log_sigma, reproj=self.reprojectionError,
                                       weighted=self.weighted and log_sigma is not None, reject=self.reject)
 
-    def __call__(self, points, logits, sigmas=None):
+    def __call__(self, points, logits, sigmas=None, crop_side=None):
         """Reference per-image signature: ``points`` [Q,2] in original-image pixels, ``logits`` [Q,12] class
-        probabilities (PostProcess output).  Answers from the batch solve PostProcess already did when possible."""
+        probabilities (PostProcess output).  Answers from the batch solve PostProcess already did when possible.
+        A pose flagged by the self-assessment filter (status 3) is treated like a failed solve everywhere (here:
+        ``IndexError``, i.e. the callers' zero pose).  ``crop_side`` (pixels) lets the filter's sigma criterion work on
+        this path too: the reference signature carries no crop box, and sigmas are in crop units."""
         if self._post is not None:
             hit = self._post.pose_cache.get(id(points))
             if hit is not None and hit[0] is points:
@@ -51,16 +54,17 @@ class BatchedPoseSolver:
         probs = np.asarray(logits, dtype=np.float32)
         assert points.shape[0] == probs.shape[0], "[Solver]: num_queries!"
         dev = self.engine.device
-        # the kernel de-normalises with box (0,0,1,1): pixel coordinates pass through unchanged (x*1+0); softmax is
-        # monotone, so feeding log-probabilities reproduces the same arg-max labels and the same scores
-        lg = torch.from_numpy(np.log(np.maximum(probs, 1e-38)))[None].to(dev)
+        # post_processed: the probabilities are the scores (no second softmax: the assignment compares exactly the
+        # numbers the reference's find_index compares) and the pixel points pass through box (0,0,1,1) unchanged
+        lg = torch.from_numpy(probs)[None].to(dev)
         pt = torch.from_numpy(points)[None].to(dev)
         box = torch.tensor([[0, 0, 1, 1]], dtype=torch.int32, device=dev)
         ls = None
         if sigmas is not None:
             ls = torch.from_numpy(np.log(np.asarray(sigmas, dtype=np.float32)))[None].to(dev)
         r = self.engine.assign_pnp(lg, pt, box, log_sigma=ls, reproj=self.reprojectionError,
-                                   weighted=self.weighted and ls is not None, reject=self.reject)
+                                   weighted=self.weighted and ls is not None, reject=self.reject, post_processed=True,
+                                   sigma_px_scale=float(crop_side or 0.0))
         status = int(r["status"].item())
         if status != 0:
             raise IndexError(f"pose solve failed (status {status})")
@@ -99,11 +103,12 @@ class MultiMeanPoseSolver:
         dev = self.engine.device
         pts = np.stack([np.asarray(p, dtype=np.float32) for p in multi_points])[:, None]       # [Nm,1,Q,2] pixels
         prb = np.stack([np.asarray(l, dtype=np.float32) for l in multi_logits])[:, None]       # [Nm,1,Q,12] probabilities
-        # pixel coordinates pass through the kernel's de-normalisation unchanged with box (0,0,1,1); the arg-max of
-        # log-probabilities is the arg-max of the probabilities
-        lg = torch.from_numpy(np.log(np.maximum(prb, 1e-38))).to(dev)
+        # pixel coordinates pass through the kernel's de-normalisation unchanged with box (0,0,1,1); the labels are the
+        # arg-max of the probabilities themselves
+        lg = torch.from_numpy(prb).to(dev)
         box = torch.tensor([[0, 0, 1, 1]], dtype=torch.int32, device=dev)
-        r = self.engine.ensemble_pnp(lg, torch.from_numpy(pts).to(dev), box, reproj=self.reprojectionError)
+        r = self.engine.ensemble_pnp(lg, torch.from_numpy(pts).to(dev), box, reproj=self.reprojectionError,
+                                     post_processed=True)
         status = int(r["status"].item())
         if status != 0:
             raise IndexError(f"pose solve failed (status {status})")

@@ -186,8 +186,8 @@ def gen_submission(prediction, solver, chunk=256):
             pts = np.stack([[np.asarray(prediction[f][m]["points"], dtype=np.float32) for f in part] for m in range(nm)])
             # pixel coordinates pass through the kernel's de-normalisation unchanged with box (0,0,1,1)
             box = torch.tensor([[0, 0, 1, 1]], dtype=torch.int32, device=dev).repeat(len(part), 1)
-            r = eng.ensemble_pnp(torch.from_numpy(np.log(np.maximum(probs, 1e-38))).to(dev), torch.from_numpy(pts).to(dev),
-                                 box, reproj=solver.reprojectionError)
+            r = eng.ensemble_pnp(torch.from_numpy(probs).to(dev), torch.from_numpy(pts).to(dev), box,
+                                 reproj=solver.reprojectionError, post_processed=True)
             quat, tvec, status = r["quat"].cpu().numpy(), r["tvec"].cpu().numpy(), r["status"].cpu().numpy()
             for i, f in enumerate(part):
                 ok = status[i] == 0
@@ -209,7 +209,7 @@ def save_prediction(prediction, save_path):
 # whole image set, one model, sharded by image
 # ---------------------------------------------------------------------------------------------------------------
 def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, rank=0, world_size=1, slots=4,
-                  reproj=20.0, weighted=False, reject=False, gather=True):
+                  reproj=20.0, weighted=False, reject=False, gather=True, calibrate=True):
     """crop -> predictor -> PnP for every image of a set (RV/gen_submission_single.py:136-181).
 
     ``get_frames(i0, i1)`` returns the frames ``i0 .. i1-1`` as a uint8 array / tensor [n,H,W] (decoded by the
@@ -227,6 +227,13 @@ def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, ran
     todo = batches(a, b, batch_size)
     local = {}
     staged = [None] * slots
+    if calibrate and not engine.calibrated and todo:
+        # rounding-bias calibration (Engine.calibrate) on the first crops of this shard, before anything is in flight
+        i0, i1 = todo[0][0], min(todo[0][1], todo[0][0] + 16)
+        fr = get_frames(i0, i1)
+        fr = fr if isinstance(fr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(fr, dtype=np.uint8))
+        boxes = torch.from_numpy(engine.clip_boxes(det_boxes[i0:i1])).to(engine.device)
+        engine.calibrate(engine.crop_resize_norm(fr.to(engine.device), boxes))
 
     def submit(k):
         i0, i1 = todo[k]
@@ -243,7 +250,7 @@ def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, ran
         r = engine.collect_batch_host(k % slots)
         i0, i1 = todo[k]
         for j, i in enumerate(range(i0, i1)):
-            ok = r["status"][j] in (0, 3)           # 3 = solved but flagged by the self-assessment filter
+            ok = r["status"][j] == 0                # 3 = flagged by the self-assessment filter: reported like a failure
             e = log_entry(r["quat"][j] if ok else np.zeros(4), r["tvec"][j] if ok else np.zeros(3))
             e["status"] = int(r["status"][j])
             local[filenames[i]] = e

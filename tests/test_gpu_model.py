@@ -315,42 +315,21 @@ def test_ensemble_submission_loop(lib, cuda_dev):
 
 
 @pytest.mark.parametrize("precision,sigma", [("bf16", False), ("tf32", True)])
-def test_baseline_configs_at_batch_256(lib, cuda_dev, precision, sigma):
-    """BASELINE.json configs[2] (bf16, batch 256) and configs[3] (self-assessment variant: sigma heads + sigma-weighted
-    PnP + reject filter, batch 256) at their stated batch size: every image of the 256-batch equals its own small-batch
-    result (which the golden / layer-wise tests pin against the reference), and the whole host pipeline runs at B = 256."""
+def test_host_pipeline_at_batch_256(lib, cuda_dev, precision, sigma):
+    """BASELINE.json configs[2] / configs[3] at their stated batch size through the whole host pipeline (crop ->
+    predictor -> PnP on 256 pinned frames); their numerics are pinned against the live reference in
+    tests/test_gpu_bench_configs.py::test_batch256_configs_vs_live_reference."""
     cfg = model_ref.ModelCfg(sigma_head=sigma)
     B = 256
     eng = _engine(cfg, 224, B, precision)
-    eng.load_state_dict(synth.make_state_dict(cfg, seed=0))
-    x = model_inputs(8, 224, 13).cuda()
-    xb = x.repeat(B // 8, 1, 1, 1).contiguous()
-    xb[100:108] = x.flip(0)                                            # not just a periodic batch
-    big = {k: v.clone() for k, v in eng.forward(xb).items() if torch.is_tensor(v)}
-    small = {k: v.clone() for k, v in eng.forward(x).items() if torch.is_tensor(v)}
-    ptol = 0.1 / 1748 if precision == "tf32" else 2e-3                 # a fraction of the 0.5 px budget (bf16: looser)
-    for i in (0, 5, 101, 255):
-        j = 7 - (i - 100) if 100 <= i < 108 else i % 8
-        assert (big["pred_points"][i] - small["pred_points"][j]).abs().max().item() <= ptol, i
-        assert (big["pred_logits"][i] - small["pred_logits"][j]).abs().max().item() <= (5e-3 if precision == "tf32" else 0.1)
-        if sigma:
-            assert (big["pred_sigmas"][i] - small["pred_sigmas"][j]).abs().max().item() <= 5e-3
-    # pose stage at B = 256 on keypoint sets with known poses (sigma-weighted + reject filter for the SA variant)
-    d = synth.make_predictions(B, seed=31, with_sigma=sigma)
-    r = eng.assign_pnp(torch.from_numpy(d["logits"]).cuda(), torch.from_numpy(d["points"]).cuda(),
-                       torch.from_numpy(d["boxes"]).cuda(), log_sigma=torch.from_numpy(d["logsig"]).cuda() if sigma else None,
-                       reproj=25.0 if sigma else 20.0, weighted=sigma, reject=sigma)
-    st = r["status"].cpu().numpy()
-    ok = st == 0
-    assert ok.sum() > 0.8 * B and set(np.unique(st)) <= {0, 1, 3}
-    s_t, s_q = eng.speed_score(r["quat"], r["tvec"], torch.from_numpy(d["q_gt"]).cuda(), torch.from_numpy(d["t_gt"]).cuda())
-    assert np.median(s_t.cpu().numpy()[ok]) < 0.01 and np.median(np.degrees(s_q.cpu().numpy()[ok])) < 1.0
-    # whole host pipeline (crop -> predictor -> PnP) on 256 frames
+    eng.load_state_dict(synth.make_state_dict(cfg, seed=0, spread_labels=True))
     det = synth.load_detector_boxes()[:B]
     base = synth.make_frames(8, det, seed=2)
     frames = torch.from_numpy(np.concatenate([base] * (B // 8))).pin_memory()
     out = eng.run_batch_host(frames, det, reproj=25.0 if sigma else 20.0, weighted=sigma, reject=sigma)
     assert out["status"].shape == (B,) and np.isfinite(out["quat"]).all() and np.isfinite(out["tvec"]).all()
+    # the sigma variant runs the reject filter: poses whose inlier RMS reprojection error exceeds 5 px are flagged (3)
+    assert (out["status"] == 0).mean() > (0.6 if sigma else 0.9) and set(np.unique(out["status"])) <= {0, 1, 3}
     eng.close()
 
 

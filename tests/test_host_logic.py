@@ -28,7 +28,11 @@ def test_state_dict_layout_is_the_references(backbone, nq, enc, dec):
     cfg = model_ref.ModelCfg(backbone=backbone, num_queries=nq, enc_layers=enc, dec_layers=dec)
     sd = synth.make_state_dict(cfg)
     model, criterion, post = build_model(_args(backbone=backbone, num_queries=nq, enc_layers=enc, dec_layers=dec))
-    assert criterion is None and callable(post["points"])
+    assert callable(post["points"])
+    # RV/engine.py:99-113 calls criterion(outputs, targets), reads criterion.weight_dict and loss_dict['class_error']
+    criterion.eval()
+    losses = criterion({"pred_logits": torch.zeros(1, 2, 12)}, [])
+    assert criterion.weight_dict == {} and set(losses) == {"class_error"} and torch.isnan(losses["class_error"])
     res = model.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}

@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Parity of the benchmarked configurations against the live-reference goldens (tests/golden/model_b256_golden.npz).
+
+Runs on the GPU box; prints one JSON object (also written to gpurun_out/parity_report.json).  For every configuration:
+keypoint error in pixels at crop sides 430 / 1147 / 1748 (normalised error x side), split into the keypoints the pose
+stage uses (assigned queries) and all queries, arg-max label flips, and -- through the pipelined C-ABI path on the
+network's own outputs -- pose error against the reference's own PostProcess + SimplePoseSolver.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import crop_ref, model_ref, pnp_ref, synth          # noqa: E402
+from satellite_pose_estimation_b200 import Engine              # noqa: E402
+
+G = np.load(os.path.join(synth.GOLDEN_DIR, "model_b256_golden.npz"))
+
+
+def crops_and_boxes(n_sets):
+    crops, frames_all, det_all = [], [], []
+    for s in range(n_sets):
+        frames, det = synth.bench_set(s)
+        frames_all.append(frames); det_all.append(det)
+        for i in range(len(frames)):
+            crops.append(crop_ref.crop_resize_normalize(frames[i], det[i], 224)[0])
+    return torch.stack(crops), np.concatenate(frames_all), np.concatenate(det_all)
+
+
+def point_stats(pts, n, assign):
+    d = np.abs(pts - G["pred_points"][:n])                      # [n,Q,2] normalised
+    fg = np.zeros(d.shape[:2], dtype=bool)
+    for i in range(n):
+        fg[i, assign[i][assign[i] >= 0]] = True
+    out = {}
+    for name, sel in (("assigned", d[fg]), ("all_queries", d.reshape(-1, 2))):
+        out[name] = {f"max_px_at_{S}": float(sel.max() * S) for S in (430, 1147, 1748)}
+        out[name]["rms_px_at_1748"] = float(np.sqrt((sel ** 2).mean()) * 1748)
+    side = (G["clip_boxes"][:n, 2] - G["clip_boxes"][:n, 0]).astype(np.float64)
+    out["max_px_at_own_crop_side"] = float((d.max((1, 2)) * side).max())
+    return out
+
+
+def run_config(precision, sigma, B, x, calibrate_x, report):
+    cfg = model_ref.ModelCfg(sigma_head=sigma)
+    sd = synth.make_state_dict(cfg, seed=0, spread_labels=True)
+    eng = Engine(max_batch=B, precision=precision, has_sigma=sigma)
+    eng.load_state_dict(sd)
+    xb = x[:B].cuda()
+    for cal in (False, True):
+        if cal:
+            eng.calibrate(calibrate_x.cuda())
+        out = eng.forward(xb)
+        torch.cuda.synchronize()
+        pts = out["pred_points"].cpu().numpy(); lg = out["pred_logits"].cpu().numpy()
+        r = point_stats(pts, B, G["assign"][:B])
+        flips = int((lg.argmax(-1) != G["pred_logits"][:B].argmax(-1)).sum())
+        r["argmax_flips"] = flips
+        r["argmax_flip_rate"] = flips / (B * lg.shape[1])
+        r["logits_max_abs_err"] = float(np.abs(lg - G["pred_logits"][:B]).max())
+        if sigma:
+            r["log_sigma_max_abs_err"] = float(np.abs(out["pred_sigmas"].cpu().numpy() - G["pred_sigmas"][:B]).max())
+        report[f"{precision}{'_sigma' if sigma else ''}_b{B}_{'calibrated' if cal else 'uncalibrated'}"] = r
+    return eng
+
+
+def chain(eng, B, frames, det, report, key):
+    """frames resident in HBM -> spe_submit_batch_dev (4 slots) -> poses on the host, on the network's own outputs"""
+    slots = 4
+    nb = len(frames) // B
+    fd = [torch.from_numpy(frames[i * B:(i + 1) * B]).cuda() for i in range(nb)]
+    bd = [torch.from_numpy(eng.clip_boxes(det[i * B:(i + 1) * B])).cuda() for i in range(nb)]
+    res = [None] * nb
+    for rep in range(2):                       # the second round replays the captured graphs
+        for i in range(min(slots, nb)):
+            eng.submit_batch_dev(i % slots, fd[i], bd[i])
+        for i in range(nb):
+            res[i] = eng.collect_batch_host(i % slots)
+            res[i]["net"] = eng.read_slot_outputs(i % slots, B)
+            if i + slots < nb:
+                eng.submit_batch_dev(i % slots, fd[i + slots], bd[i + slots])
+    n = nb * B
+    quat = np.concatenate([r["quat"] for r in res]); tvec = np.concatenate([r["tvec"] for r in res])
+    status = np.concatenate([r["status"] for r in res])
+    pts = np.concatenate([r["net"][1] for r in res]); lg = np.concatenate([r["net"][0] for r in res])
+    ok_ref = G["ok"][:n] == 1
+    rot, tr = [], []
+    for i in range(n):
+        if ok_ref[i] and status[i] == 0:
+            s_t, s_q = pnp_ref.speed_score(quat[i], tvec[i], G["quat"][i], G["tvec"][i])
+            rot.append(np.degrees(s_q)); tr.append(s_t)
+    r = point_stats(pts, n, G["assign"][:n])
+    r.update({"images": n, "solved": int((status == 0).sum()), "reference_solved": int(ok_ref.sum()),
+              "status_mismatch": int(((status == 0) != ok_ref).sum()),
+              "argmax_flips": int((lg.argmax(-1) != G["pred_logits"][:n].argmax(-1)).sum()),
+              "pose_rot_deg_max": float(max(rot)), "pose_rot_deg_median": float(np.median(rot)),
+              "pose_trans_rel_max": float(max(tr)), "pose_trans_rel_median": float(np.median(tr))})
+    report[key] = r
+
+
+def main():
+    report = {}
+    x, frames, det = crops_and_boxes(4)
+    cal_x = x[64:80]                                   # calibration images: 16 crops of frame set 1
+    eng = run_config("tf32", False, 64, x, cal_x, report)
+    chain(eng, 64, frames[:256], det[:256], report, "tf32_b64_chain_4slots_calibrated")
+    eng.close()
+    eng = run_config("bf16", False, 256, x, cal_x, report)
+    chain(eng, 256, frames[:256], det[:256], report, "bf16_b256_chain_calibrated")
+    eng.close()
+    eng = run_config("tf32", True, 256, x, cal_x, report)
+    eng.close()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps(report, indent=1))
+
+
+if __name__ == "__main__":
+    main()
