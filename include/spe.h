@@ -157,6 +157,27 @@ int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_
 int spe_speed_score(spe_ctx* ctx, const double* quat_pr_dev, const double* tvec_pr_dev, const double* quat_gt_dev,
                     const double* tvec_gt_dev, int B, double* score_t_dev, double* score_q_dev, void* stream);
 
+/* ---- SA (RT-DETR) variant: first decoder pieces ----------------------------------------- */
+/* replaces: deformable_attention_core_func (SA/src/zoo/rtdetr/utils.py:15-64) -- per level F.grid_sample(bilinear,
+ * zeros padding, align_corners=False) and the weighted sum over levels x points -- and, with fused = 1, also what
+ * MSDeformableAttention.forward computes between its linear layers and the core (SA/src/zoo/rtdetr/rtdetr_decoder.py:
+ * 117-163): softmax of the attention logits over levels x points, sampling location = reference point + offset / (W_l, H_l).
+ *   value [B, Lv, heads, 32] fp32, levels concatenated along Lv; shapes_hw_host [L, 2] = (H_l, W_l) in HOST memory
+ *   fused = 0: loc [B, Lq, heads, L, P, 2] sampling locations in [0, 1], attn [B, Lq, heads, L, P] softmaxed weights
+ *   fused = 1: loc = raw sampling offsets (same shape), attn = raw logits, ref [B, Lq, ref_levels, 2] (ref_levels 1 or L)
+ *   out [B, Lq, heads * 32] fp32.  head_dim is 32 (embed 256 / 8 heads), L * P <= 64. */
+int spe_ms_deform_attn(spe_ctx* ctx, const float* value_dev, const int32_t* shapes_hw_host, int L, const float* loc_dev,
+                       const float* attn_dev, const float* ref_dev, int ref_levels, int B, int Lq, int heads, int P,
+                       int fused, float* out_dev, void* stream);
+/* replaces: torch.topk(enc_outputs_class.max(-1).values, num_queries, dim=1) (SA/src/zoo/rtdetr/rtdetr_decoder.py:
+ * 646-648): cls [B, Lv, C] fp32 -> idx [B, k] int32 in descending score order (ties: lower index), vals [B, k] or NULL */
+int spe_topk_queries(spe_ctx* ctx, const float* cls_dev, int B, int Lv, int C, int k, int32_t* idx_dev, float* vals_dev,
+                     void* stream);
+/* replaces: tensor.gather(dim=1, index=topk_ind.unsqueeze(-1).repeat(1, 1, D)) (rtdetr_decoder.py:651-680):
+ * out[b, r, :] = src[b, idx[b, r], :] for src [B, Lv, D] fp32 */
+int spe_gather_rows(spe_ctx* ctx, const float* src_dev, const int32_t* idx_dev, int B, int Lv, int k, int D,
+                    float* out_dev, void* stream);
+
 /* ---- whole path, host buffers in, host buffers out ---------------------------------------------------------- */
 /* replaces the hot loop of gen_submission (RV/gen_submission_single.py:136-181): frames + detector boxes in
  * host memory -> poses in host memory.  Uploads, runs crop -> forward -> assign/PnP on `stream`, downloads and

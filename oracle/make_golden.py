@@ -15,6 +15,7 @@ Fixtures written:
   crop_golden.npz     reference crop boxes + uint8 resized crops for a spread of boxes
   model_golden.npz    reference model outputs for seeded weights/inputs (weights are regenerated, never stored)
   pnp_golden.npz      reference SimplePoseSolver poses for seeded synthetic predictions
+  deform_attn_golden.npz  the SA drop's deformable_attention_core_func and live MSDeformableAttention module on seeded inputs
   model_b256_golden.npz  reference model (calibrated heads, oracle/make_chain_fixture.py) + PostProcess + solver on the
                       256 crops of the benchmarked frame sets; sigma head through the SA drop's own MLP class
 """
@@ -300,6 +301,54 @@ def write_model_b64_random():
     print("b64 random-init golden written")
 
 
+DEFORM_CASE = dict(bs=3, Lq=30, heads=8, levels=((32, 32), (16, 16), (8, 8)), points=4, seed=41)
+
+
+def deform_inputs(case=DEFORM_CASE):
+    """Seeded inputs + module weights of the deformable-attention goldens (numpy PCG64: identical on every machine)."""
+    rng = np.random.default_rng(case["seed"])
+    bs, Lq, H, P = case["bs"], case["Lq"], case["heads"], case["points"]
+    L = len(case["levels"])
+    Lv = sum(h * w for h, w in case["levels"])
+    f = lambda *shape, scale=1.0: torch.from_numpy((rng.standard_normal(shape) * scale).astype(np.float32))
+    d = {"query": f(bs, Lq, 256), "value_in": f(bs, Lv, 256),
+         # reference points as the decoder passes them: one (x, y) in (0, 1) per query, shared by the levels
+         # (rtdetr_decoder.py:320 `ref_points_detach.unsqueeze(2)`); a few outside [0, 1] exercise the zero padding
+         "ref": torch.from_numpy(rng.uniform(-0.1, 1.1, (bs, Lq, 1, 2)).astype(np.float32)),
+         "weights": {
+             "sampling_offsets.weight": f(H * L * P * 2, 256, scale=0.05), "sampling_offsets.bias": f(H * L * P * 2, scale=2.0),
+             "attention_weights.weight": f(H * L * P, 256, scale=0.1), "attention_weights.bias": f(H * L * P, scale=0.5),
+             "value_proj.weight": f(256, 256, scale=0.06), "value_proj.bias": f(256, scale=0.02),
+             "output_proj.weight": f(256, 256, scale=0.06), "output_proj.bias": f(256, scale=0.02)},
+         # direct inputs of the core function: sampling locations spilling over the map border, softmaxed weights
+         "core_value": f(bs, Lv, H, 32), "core_loc": torch.from_numpy(rng.uniform(-0.15, 1.15, (bs, Lq, H, L, P, 2)).astype(np.float32)),
+         "core_attn": torch.softmax(f(bs, Lq, H, L * P), -1).reshape(bs, Lq, H, L, P)}
+    return d
+
+
+def write_deform_attn():
+    """SA/src/zoo/rtdetr/utils.py:15-64 (``deformable_attention_core_func``) and the LIVE ``MSDeformableAttention`` module
+    (rtdetr_decoder.py:40-191) on seeded inputs: the core output the module hands to ``output_proj`` is captured with a
+    forward-pre hook, so the softmax / sampling-location arithmetic in between is the reference's own."""
+    ref_import.import_sa_rtdetr()
+    from src.zoo.rtdetr.rtdetr_decoder import MSDeformableAttention
+    from src.zoo.rtdetr.utils import deformable_attention_core_func
+    case = DEFORM_CASE
+    d = deform_inputs(case)
+    shapes = [list(s_) for s_ in case["levels"]]
+    with torch.no_grad():
+        core = deformable_attention_core_func(d["core_value"], shapes, d["core_loc"], d["core_attn"])
+        m = MSDeformableAttention(256, case["heads"], len(shapes), case["points"])
+        m.load_state_dict(d["weights"], strict=True)
+        m.eval()
+        got = {}
+        m.output_proj.register_forward_pre_hook(lambda mod, inp: got.__setitem__("core", inp[0].clone()))
+        out = m(d["query"], d["ref"], d["value_in"], shapes)
+    np.savez_compressed(os.path.join(GOLDEN, "deform_attn_golden.npz"), core_func_out=core.numpy(),
+                        module_core_out=got["core"].numpy(), module_out=out.numpy())
+    print("deformable attention goldens:", core.shape, got["core"].shape, out.shape)
+
+
 def write_pnp(rv_eval, n=400):
     import cv2
     d = synth.make_predictions(n, seed=1)
@@ -385,6 +434,7 @@ def main():
     write_model()
     write_model_b256(rv_eval)
     write_model_b64_random()
+    write_deform_attn()
     write_pnp(rv_eval)
     write_pnp_multi(rv_eval)
 

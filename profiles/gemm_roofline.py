@@ -13,7 +13,9 @@ PK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAK
     if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else \
     {"bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
 TF32 = PK["bf16_tflops_sustained"] / 2 * 1e12
+TF32_BURST = PK.get("bf16_tflops", PK["bf16_tflops_sustained"]) / 2 * 1e12   # the peak at the clock a short run holds
 HBM = PK["hbm_gbs"] * 1e9
+KV_X3 = os.environ.get("KV_X3", "0") == "1"     # round 2: the K/V projection is plain TF32 once calibrated
 
 
 def schedule():
@@ -43,7 +45,7 @@ def schedule():
         add(f"enc{i}.out+res", B * T, 256, 256, res=B * T * 256)
         # linear1 + ReLU + linear2 + residual + norm2 in one kernel: 2 x (M x 2048 x 256) MACs, X in, Y out
         g.append((f"enc{i}.ffn fused (+LN)", B * T, 2048, 256, 0, False, 2))
-    add("dec.kv_all (3xTF32)", B * T, 2048, 256, x3=True)
+    add("dec.kv_all" + (" (3xTF32)" if KV_X3 else ""), B * T, 2048, 256, x3=KV_X3)
     Q = 40
     for i in range(4):
         add(f"dec{i}.sa_qkv x3", B * Q, 768, 256, x3=True)
@@ -58,7 +60,8 @@ def schedule():
 
 
 def main(path):
-    seq = load(path)
+    extra = {}
+    seq = load(path, extra)
     starts = [i for i, s in enumerate(seq) if "crop_resize" in s[1]]
     ends = [i for i, s in enumerate(seq) if "assign_pnp" in s[1] or "PnpDesc" in s[1]]
     a = starts[-1] if ends and ends[-1] > starts[-1] else starts[-2]
@@ -67,8 +70,12 @@ def main(path):
     gem = [s for s in seq[a:b + 1] if short(s[1]) in FAM]
     sch = schedule()
     assert len(gem) == len(sch), (len(gem), len(sch))
-    print("| GEMM | M | N | K | us | ideal us | TFLOP/s | x ideal |\n|---|---:|---:|---:|---:|---:|---:|---:|")
-    tot = tot_ideal = 0
+    TP = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"
+    has_tp = any(TP in v for v in extra.values())
+    print("| GEMM | M | N | K | us | ideal us | TFLOP/s | x ideal |" + (" tensor pipe % of elapsed |" if has_tp else "") +
+          "\n|---|---:|---:|---:|---:|---:|---:|---:|" + ("---:|" if has_tp else ""))
+    tot = tot_ideal = tot_burst = 0
+    tp_weighted = 0.0
     tag = {"gemm_tc2_kernel": " (pair)", "conv3_tc_kernel": " (tap reuse)", "ffn_tc_kernel": "", "ffn_tc2_kernel": " (pair)"}
     for (name, M, N, K, res, x3, nmm), s in zip(sch, gem):
         fl = 2 * M * N * K * nmm
@@ -78,8 +85,24 @@ def main(path):
         name = name + tag.get(short(s[1]), "")
         ideal = max(fl * (3 if x3 else 1) / TF32, by / HBM) * 1e6
         tot += s[2]; tot_ideal += ideal
-        print(f"| {name} | {M} | {N} | {K} | {s[2]:.1f} | {ideal:.1f} | {fl / s[2] / 1e6:.0f} | {s[2] / ideal:.1f} |")
-    print(f"\nGEMM total {tot:.0f} us, sum of per-GEMM ideals {tot_ideal:.0f} us")
+        tot_burst += max(fl * (3 if x3 else 1) / TF32_BURST, by / HBM) * 1e6
+        tp = extra.get(s[0], {}).get(TP)
+        if tp is not None:
+            tp_weighted += tp * s[2]
+        print(f"| {name} | {M} | {N} | {K} | {s[2]:.1f} | {ideal:.1f} | {fl / s[2] / 1e6:.0f} | {s[2] / ideal:.1f} |" +
+              (f" {tp:.1f} |" if tp is not None else ""))
+    print(f"\nGEMM total {tot:.0f} us, sum of per-GEMM ideals {tot_ideal:.0f} us at the sustained peak "
+          f"({TF32 / 1e12:.0f} TFLOP/s), {tot_burst:.0f} us at the burst peak ({TF32_BURST / 1e12:.0f} TFLOP/s)")
+    if has_tp:
+        print(f"time-weighted tensor-pipe utilisation of the GEMM family (counter {TP}): {tp_weighted / tot:.1f} %")
+    # the other kernels that issue tensor-core work
+    att = [s for s in seq[a:b + 1] if "attention" in s[1]]
+    if has_tp and att:
+        t = sum(s[2] for s in att)
+        w = sum(extra.get(s[0], {}).get(TP, 0.0) * s[2] for s in att)
+        step_t = sum(s[2] for s in seq[a:b + 1])
+        allw = sum(extra.get(s[0], {}).get(TP, 0.0) * s[2] for s in seq[a:b + 1])
+        print(f"attention kernels: {t:.0f} us at {w / t:.1f} %; whole step ({step_t:.0f} us of kernel time): {allw / step_t:.1f} %")
 
 
 if __name__ == "__main__":

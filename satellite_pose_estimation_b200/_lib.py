@@ -48,6 +48,9 @@ SYMBOLS = {
     "spe_assign_pnp": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp]),
     "spe_ensemble_pnp": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spe_ms_deform_attn": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "spe_topk_queries": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "spe_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "spe_run_batch_host": (_i, [_vp, _vp, _i, _i, _vp, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp]),
     "spe_debug_gemm": (_i, [_i, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "spe_debug_conv": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -228,6 +228,36 @@ int spe_ensemble_pnp(spe_ctx* ctx, const float* logits_dev, const float* points_
   return SPE_OK;
 }
 
+int spe_ms_deform_attn(spe_ctx* ctx, const float* value_dev, const int32_t* shapes_hw_host, int L, const float* loc_dev,
+                       const float* attn_dev, const float* ref_dev, int ref_levels, int B, int Lq, int heads, int P,
+                       int fused, float* out_dev, void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_ms_deform_attn: null ctx");
+  if (!value_dev || !shapes_hw_host || !loc_dev || !attn_dev || !out_dev || heads <= 0)
+    return set_error(ctx, SPE_ERR_INVALID, "spe_ms_deform_attn: null buffer");
+  std::string s = launch_ms_deform_attn(value_dev, shapes_hw_host, L, loc_dev, attn_dev, ref_dev, ref_levels, B, Lq, heads,
+                                        P, fused, out_dev, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(ctx, SPE_ERR_INVALID, "spe_ms_deform_attn: " + s);
+  return SPE_OK;
+}
+
+int spe_topk_queries(spe_ctx* ctx, const float* cls_dev, int B, int Lv, int C, int k, int32_t* idx_dev, float* vals_dev,
+                     void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_topk_queries: null ctx");
+  if (!cls_dev || !idx_dev || Lv <= 0 || C <= 0) return set_error(ctx, SPE_ERR_INVALID, "spe_topk_queries: bad argument");
+  std::string s = launch_topk_queries(cls_dev, B, Lv, C, k, idx_dev, vals_dev, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(ctx, SPE_ERR_INVALID, "spe_topk_queries: " + s);
+  return SPE_OK;
+}
+
+int spe_gather_rows(spe_ctx* ctx, const float* src_dev, const int32_t* idx_dev, int B, int Lv, int k, int D,
+                    float* out_dev, void* stream) {
+  if (!ctx) return set_error(nullptr, SPE_ERR_INVALID, "spe_gather_rows: null ctx");
+  if (!src_dev || !idx_dev || !out_dev || D <= 0) return set_error(ctx, SPE_ERR_INVALID, "spe_gather_rows: bad argument");
+  std::string s = launch_gather_rows(src_dev, idx_dev, B, Lv, k, D, out_dev, static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(ctx, SPE_ERR_INVALID, "spe_gather_rows: " + s);
+  return SPE_OK;
+}
+
 int spe_run_batch_host(spe_ctx* ctx, const uint8_t* frames_host, int H, int W, const double* det_boxes_host, int B,
                        const spe_pnp_params* params, double* quat_host, double* tvec_host, int32_t* status_host,
                        int32_t* boxes_host, void* stream) {

@@ -251,8 +251,8 @@ std::string launch_attn_t(const AttnDesc& d, cudaStream_t s) {
   T* o = reinterpret_cast<T*>(d.out);
   ProfScope ps(kFamAttention, s);
   if constexpr (sizeof(T) == 4) {
-    if (d.exact_out) {
-      // the decoder's attention (its GEMMs are 3xTF32): compensated products; half-size tiles keep the four operand
+    if (d.x3) {
+      // the decoder's attention: compensated products; half-size tiles keep the four operand
       // tiles within the 48 KB of static shared memory
       if (d.Lk % 56 == 0) {
         SPE_CUDA_TRY(launch_pdl(attention_kernel<T, 56, true>, grid, dim3(128), 0, s, q, k, v, o, d.ldq, d.ldk, d.ldv, d.ldo,
@@ -283,7 +283,7 @@ std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s) {
   const int vec = 8;
   if (d.ldk % vec || d.ldv % vec || d.ldq % 1) return "attention: K/V row strides must be multiples of 8 elements";
   static const bool no_tc = getenv("SPE_ATTN_LEGACY") != nullptr;
-  if (!no_tc && attention_tc_supported(dt, d)) return launch_attention_tc(d, s);
+  if (!no_tc && !d.x3 && attention_tc_supported(dt, d)) return launch_attention_tc(d, s);
   if (d.mixed) return "attention: fp32 Q/K/V with bf16 output needs the tcgen05 kernel (shape not supported)";
   if (dt == kTF32) return launch_attn_t<float>(d, s);
   return launch_attn_t<__nv_bfloat16>(d, s);

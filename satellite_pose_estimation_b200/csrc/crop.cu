@@ -27,13 +27,18 @@ __device__ __forceinline__ void cubic_w(double t, double (&w)[4]) {
   w[3] = 1.0 - w[0] - w[1] - w[2];
 }
 
-// One thread per output pixel; threadIdx.x walks ox so the three channel stores are fully coalesced.
+// One thread per output COLUMN, kRows output rows per block: the horizontal taps (four clamped frame columns + four
+// fp64 cubic weights, a third of the kernel's arithmetic) depend on the column only and are computed once per thread;
+// threadIdx.x walks ox, so the three channel stores of every row are fully coalesced, and the 4 x 4 source bytes of
+// neighbouring columns share sectors (at the median crop side of 430 px a warp's 32 columns span 61 source bytes).
+// Measured: 49 us -> see profiles/r02_ncu_crop.md for 64 frames.
+constexpr int kCropRows = 8;
+
 __global__ void __launch_bounds__(256)
 crop_resize_norm_kernel(const uint8_t* __restrict__ frames, int H, int W, long long pitch, long long frame_stride,
                         const int32_t* __restrict__ boxes, int R, float* __restrict__ out) {
   const int b = blockIdx.z;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  const int oy = blockIdx.y;
   if (ox >= R) return;
 
   const int x1 = boxes[b * 4 + 0];
@@ -42,55 +47,67 @@ crop_resize_norm_kernel(const uint8_t* __restrict__ frames, int H, int W, long l
   const int S = boxes[b * 4 + 2] - x1;
   const int Sy = boxes[b * 4 + 3] - y1;
   const uint8_t* frame = frames + static_cast<long long>(b) * frame_stride;
+  const long long plane = static_cast<long long>(R) * R;
+  const bool empty = !(S > 0 && Sy > 0);
 
-  float v = 0.0f;
-  if (S > 0 && Sy > 0) {
+  double wx[4];
+  int cx[4];
+  bool inx[4];
+  if (!empty) {
     const double fx = (ox + 0.5) * (static_cast<double>(S) / static_cast<double>(R)) - 0.5;
-    const double fy = (oy + 0.5) * (static_cast<double>(Sy) / static_cast<double>(R)) - 0.5;
-    const double flx = floor(fx), fly = floor(fy);
-    const int sx = static_cast<int>(flx), sy = static_cast<int>(fly);
-    double wx[4], wy[4];
+    const double flx = floor(fx);
+    const int sx = static_cast<int>(flx);
     cubic_w(fx - flx, wx);
-    cubic_w(fy - fly, wy);
-
-    int cx[4];
-    bool inx[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int c = sx - 1 + i;
       c = c < 0 ? 0 : (c > S - 1 ? S - 1 : c);  // replicate the canvas border
       const int gx = x1 + c;                    // canvas -> frame column
       inx[i] = (gx >= 0) && (gx < W);
-      cx[i] = gx;
+      cx[i] = inx[i] ? gx : 0;
     }
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int c = sy - 1 + j;
-      c = c < 0 ? 0 : (c > Sy - 1 ? Sy - 1 : c);
-      const int gy = y1 + c;
-      double row = 0.0;
-      if (gy >= 0 && gy < H) {
-        const uint8_t* rp = frame + static_cast<long long>(gy) * pitch;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double px = inx[i] ? static_cast<double>(__ldg(rp + cx[i])) : 0.0;  // outside frame: zero canvas
-          row += px * wx[i];
-        }
-      }
-      acc += row * wy[j];
-    }
-    double r = rint(acc);  // round half to even, like cvRound / IPP
-    r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
-    v = static_cast<float>(r);
   }
-  // to_tensor: uint8 -> float32 / 255 ; Normalize: (x - mean) / std, all IEEE fp32 like the torch CPU ops
-  const float x = __fdiv_rn(v, 255.0f);
-  const long long plane = static_cast<long long>(R) * R;
-  float* o = out + static_cast<long long>(b) * 3 * plane + static_cast<long long>(oy) * R + ox;
-  o[0] = __fdiv_rn(__fsub_rn(x, 0.485f), 0.229f);
-  o[plane] = __fdiv_rn(__fsub_rn(x, 0.456f), 0.224f);
-  o[2 * plane] = __fdiv_rn(__fsub_rn(x, 0.406f), 0.225f);
+  const double ry = static_cast<double>(Sy) / static_cast<double>(R);
+  const int oy0 = blockIdx.y * kCropRows;
+#pragma unroll 2
+  for (int r = 0; r < kCropRows; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= R) break;
+    float v = 0.0f;
+    if (!empty) {
+      const double fy = (oy + 0.5) * ry - 0.5;
+      const double fly = floor(fy);
+      const int sy = static_cast<int>(fly);
+      double wy[4];
+      cubic_w(fy - fly, wy);
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int c = sy - 1 + j;
+        c = c < 0 ? 0 : (c > Sy - 1 ? Sy - 1 : c);
+        const int gy = y1 + c;
+        double row = 0.0;
+        if (gy >= 0 && gy < H) {
+          const uint8_t* rp = frame + static_cast<long long>(gy) * pitch;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double px = inx[i] ? static_cast<double>(__ldg(rp + cx[i])) : 0.0;  // outside frame: zero canvas
+            row += px * wx[i];
+          }
+        }
+        acc += row * wy[j];
+      }
+      double rr = rint(acc);  // round half to even, like cvRound / IPP
+      rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
+      v = static_cast<float>(rr);
+    }
+    // to_tensor: uint8 -> float32 / 255 ; Normalize: (x - mean) / std, all IEEE fp32 like the torch CPU ops
+    const float x = __fdiv_rn(v, 255.0f);
+    float* o = out + static_cast<long long>(b) * 3 * plane + static_cast<long long>(oy) * R + ox;
+    o[0] = __fdiv_rn(__fsub_rn(x, 0.485f), 0.229f);
+    o[plane] = __fdiv_rn(__fsub_rn(x, 0.456f), 0.224f);
+    o[2 * plane] = __fdiv_rn(__fsub_rn(x, 0.406f), 0.225f);
+  }
 }
 
 }  // namespace
@@ -101,7 +118,7 @@ std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long lo
   if (R <= 0 || R > 4096) return "crop: bad output size";
   const int tx = R >= 256 ? 256 : ((R + 31) / 32) * 32;
   dim3 block(tx);
-  dim3 grid((R + tx - 1) / tx, R, B);
+  dim3 grid((R + tx - 1) / tx, (R + kCropRows - 1) / kCropRows, B);
   ProfScope ps(kFamCrop, s);
   crop_resize_norm_kernel<<<grid, block, 0, s>>>(frames, H, W, pitch, frame_stride, boxes, R, out_nchw);
   SPE_CUDA_TRY(cudaGetLastError());

@@ -81,11 +81,12 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162flo
 __device__ __forceinline__ float as_mma_operand(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 __device__ __forceinline__ float as_mma_operand(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// sum[c] += sum over rows of A[r, c], sum_mma[c] += the same over the values the tensor core reads
-// (A [M, C], row stride lda elements; both pre-zeroed)
+// part[blk][c] = sum over the block's rows of A[r, c], part_mma[blk][c] = the same over the values the tensor core
+// reads (A [M, C], row stride lda elements).  No atomics: the partial sums are added up in a fixed order by
+// colsum_reduce_kernel, so a calibration is bit-reproducible.
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ A, long long M, int C, long long lda, float* __restrict__ sum,
-                              float* __restrict__ sum_mma) {
+__global__ void colsum_kernel(const T* __restrict__ A, long long M, int C, long long lda, float* __restrict__ part,
+                              float* __restrict__ part_mma) {
   const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
   const long long r0 = rows_per_block * blockIdx.x;
   const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
@@ -96,19 +97,36 @@ __global__ void colsum_kernel(const T* __restrict__ A, long long M, int C, long 
       acc += to_f32(v);
       acc_t += as_mma_operand(v);
     }
-    atomicAdd(sum + c, acc);
-    atomicAdd(sum_mma + c, acc_t);
+    part[static_cast<long long>(blockIdx.x) * C + c] = acc;
+    part_mma[static_cast<long long>(blockIdx.x) * C + c] = acc_t;
   }
+}
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, const float* __restrict__ part_mma, int nblk, int C,
+                                     float* __restrict__ sum, float* __restrict__ sum_mma) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int i = 0; i < nblk; ++i) { a += part[static_cast<long long>(i) * C + c]; b += part_mma[static_cast<long long>(i) * C + c]; }
+  sum[c] = a;
+  sum_mma[c] = b;
 }
 // channel sums of an NCHW fp32 image batch: sum[c] += sum over (n, h, w); C channels, HW pixels per plane
 __global__ void nchw_chansum_kernel(const float* __restrict__ x, int NB, int C, long long HW, float* __restrict__ sum) {
-  const int plane = blockIdx.x;                 // n * C + c
-  if (plane >= NB * C) return;
-  const float* p = x + static_cast<long long>(plane) * HW;
+  // one block per channel, fixed summation order (bit-reproducible): thread t strides over the pixels of every image
+  const int c = blockIdx.x;
+  __shared__ float red[256];
   float acc = 0.f;
-  for (long long i = threadIdx.x; i < HW; i += blockDim.x) acc += p[i];
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(sum + plane % C, acc);
+  for (int n = 0; n < NB; ++n) {
+    const float* p = x + (static_cast<long long>(n) * C + c) * HW;
+    for (long long i = threadIdx.x; i < HW; i += blockDim.x) acc += p[i];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sum[c] = red[0];
 }
 // One warp per output channel n: delta = scale[n] * sum_k (W32[n,k] * mean[k % C] - W[n,k] * mean_mma[k % C]) -- what
 // the product of the stored (rounded) weights and the operand as the tensor core reads it (fp32 activations that were
@@ -243,8 +261,9 @@ struct spe_ctx {
   GemmW s8_lat, s16_lat, out_conv, input_proj;
   std::vector<EncLayer> enc;
   std::vector<DecLayer> dec;
-  GemmW ca_kv_all;             // [L*512, 256]  (TF32 mode: [L*512, 768] = [W_hi | W_hi | W_lo])
-  bool kv_split3 = false;
+  GemmW ca_kv_all;             // [L*512, 256] plain storage-dtype weights
+  GemmW ca_kv_x3;              // fp32 storage: [L*512, 768] = [W_hi | W_hi | W_lo], the hoisted 3xTF32 form
+  bool kv_split3 = false;      // ca_kv_x3 is loaded
   void* XS = nullptr;          // last encoder output as [hi | lo | hi], [B*tokens, 768]
   float* ca_kv_addend = nullptr;  // [tokens, L*512]
   float *dn_g = nullptr, *dn_b = nullptr;
@@ -281,7 +300,8 @@ struct spe_ctx {
 
   // calibration state (spe_calibrate)
   bool calibrating = false, calibrated = false;
-  float* colsum = nullptr;           // [2][4096] scratch: column sums of a layer's input as stored / as the MMA reads it
+  float* colsum = nullptr;           // [2][4096] column sums of a layer's input as stored / as the MMA reads it, then
+                                     // [2][256][4096] per-block partial sums (calibration scratch)
   // fp32 storage: tensors that are both a GEMM operand and a residual (block outputs of the backbone, the encoder
   // stream) stay UNROUNDED in HBM.  The tensor core truncates them on the fly -- same noise as rounding them, plus a
   // small bias that spe_calibrate measures and folds into the biases -- while the skip path adds the exact values, so
@@ -289,6 +309,13 @@ struct spe_ctx {
   // it): the per-element error of the encoder memory drops (5.6e-4 -> 4.2e-4 relative) but the keypoints get WORSE
   // (0.16 -> 0.21 px rms at S = 1748): truncation shrinks every operand by ~3.5e-4, a coherent gain error on every
   // GEMM branch that a bias cannot absorb.
+  // error-compensated 3xTF32 for the decoder + head GEMMs / for the cross-attention K/V projection (fp32 storage only)
+  bool dec_x3 = getenv("SPE_DEC_X3") ? atoi(getenv("SPE_DEC_X3")) != 0 : true;
+  // K/V projection: -1 (default) = 3xTF32 until the context is calibrated, plain TF32 afterwards -- with the rounding
+  // bias folded into the addend the plain product is as accurate as the compensated one (measured: 0.12 vs 0.14 px at
+  // S = 1748, whole-chain keypoints 0.27 vs 0.49 px) and a third of the tensor work (213 -> ~75 us at B = 64);
+  // uncalibrated it is not (0.61 vs 0.47 px).  1 = always 3xTF32, 0 = never.
+  int kv_x3 = getenv("SPE_KV_X3") ? atoi(getenv("SPE_KV_X3")) : -1;
   bool exact_stream = getenv("SPE_EXACT_STREAM") ? atoi(getenv("SPE_EXACT_STREAM")) != 0 : false;
 
   // Stream capture is illegal on the legacy default stream (and on cudaStreamPerThread a capture would swallow
@@ -607,12 +634,12 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       const std::string p = "transformer.decoder.layers." + std::to_string(i);
       // the decoder and the heads run as 3xTF32: their rounding error dominates the keypoint error budget (0.5 px at
       // crop sides up to 1748 px), while they are < 6 % of the FLOPs
-      TRY_S(load_mha_self(ctx, ws, p + ".self_attn", qe_dev, Q, &L.sa_qkv, &L.sa_out, &L.sa_addend, true));
+      TRY_S(load_mha_self(ctx, ws, p + ".self_attn", qe_dev, Q, &L.sa_qkv, &L.sa_out, &L.sa_addend, ctx->dec_x3));
       const HostTensor* w = ws.get(p + ".multihead_attn.in_proj_weight", {3 * E, E});
       const HostTensor* bb = ws.get(p + ".multihead_attn.in_proj_bias", {3 * E});
       if (!w || !bb) return ws.missing;
       // query projection: (tgt + query_pos) Wq^T + bq
-      TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + E * E), E, E, &L.ca_q, true));
+      TRY_S(upload_gemm_w(ctx, std::vector<float>(w->data, w->data + E * E), E, E, &L.ca_q, ctx->dec_x3));
       TRY_S(dmalloc(ctx, &L.ca_q_addend, static_cast<long long>(Q) * E));
       TRY_S(make_addend(ctx, qe_dev, Q, E, w->data, bb->data, E, L.ca_q_addend, E, 0));
       L.ca_q.addend = L.ca_q_addend; L.ca_q.addend_rows = Q; L.ca_q.addend_ld = E;
@@ -622,9 +649,9 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
                         i * 2 * E));
       TRY_S(make_addend(ctx, nullptr, T, E, w->data + 2 * E * E, bb->data + 2 * E, E, ctx->ca_kv_addend,
                         LD * 2 * E, i * 2 * E + E));
-      TRY_S(load_linear(ctx, ws, p + ".multihead_attn.out_proj", E, E, &L.ca_out, true));
-      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1, true));
-      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2, true));
+      TRY_S(load_linear(ctx, ws, p + ".multihead_attn.out_proj", E, E, &L.ca_out, ctx->dec_x3));
+      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1, ctx->dec_x3));
+      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2, ctx->dec_x3));
       TRY_S(load_vec(ctx, ws, p + ".norm1.weight", E, &L.n1g));
       TRY_S(load_vec(ctx, ws, p + ".norm1.bias", E, &L.n1b));
       TRY_S(load_vec(ctx, ws, p + ".norm2.weight", E, &L.n2g));
@@ -632,7 +659,10 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(load_vec(ctx, ws, p + ".norm3.weight", E, &L.n3g));
       TRY_S(load_vec(ctx, ws, p + ".norm3.bias", E, &L.n3b));
     }
-    if (ctx->dt == kTF32) {
+    TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all));
+    ctx->ca_kv_all.addend = ctx->ca_kv_addend; ctx->ca_kv_all.addend_rows = T; ctx->ca_kv_all.addend_ld = LD * 2 * E;
+    ctx->kv_split3 = false;
+    if (ctx->dt == kTF32 && ctx->kv_x3 != 0) {
       // 3xTF32 with the operand split hoisted out of the GEMM: the last encoder LayerNorm emits [x_hi | x_lo | x_hi]
       // and the weights are stored as [W_hi | W_hi | W_lo], so a plain K = 3E GEMM yields the compensated product
       std::vector<float> w3(static_cast<size_t>(LD) * 2 * E * 3 * E);
@@ -643,12 +673,8 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
           float* row = w3.data() + static_cast<size_t>(n) * 3 * E;
           row[k] = hi; row[E + k] = hi; row[2 * E + k] = lo;
         }
-      TRY_S(upload_gemm_w(ctx, w3, LD * 2 * E, 3 * E, &ctx->ca_kv_all, false, false));   // already error-compensated
+      TRY_S(upload_gemm_w(ctx, w3, LD * 2 * E, 3 * E, &ctx->ca_kv_x3, false, false));   // already error-compensated
       ctx->kv_split3 = true;
-    } else {
-      TRY_S(upload_gemm_w(ctx, kv_w, LD * 2 * E, E, &ctx->ca_kv_all));
-      ctx->ca_kv_all.addend = ctx->ca_kv_addend; ctx->ca_kv_all.addend_rows = T; ctx->ca_kv_all.addend_ld = LD * 2 * E;
-      ctx->kv_split3 = false;
     }
     TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.weight", E, &ctx->dn_g));
     TRY_S(load_vec(ctx, ws, "transformer.decoder.norm.bias", E, &ctx->dn_b));
@@ -657,15 +683,15 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
     if (!cw) return ws.missing;
     TRY_S(upload_f32(ctx, cw->data, 12 * E, &ctx->cls_w));
     TRY_S(load_vec(ctx, ws, "cls_embed.bias", 12, &ctx->cls_b));
-    TRY_S(load_linear(ctx, ws, "point_embed.layers.0", E, E, &ctx->pt0, true));
-    TRY_S(load_linear(ctx, ws, "point_embed.layers.1", E, E, &ctx->pt1, true));
+    TRY_S(load_linear(ctx, ws, "point_embed.layers.0", E, E, &ctx->pt0, ctx->dec_x3));
+    TRY_S(load_linear(ctx, ws, "point_embed.layers.1", E, E, &ctx->pt1, ctx->dec_x3));
     const HostTensor* p2 = ws.get("point_embed.layers.2.weight", {2, E});
     if (!p2) return ws.missing;
     TRY_S(upload_f32(ctx, p2->data, 2 * E, &ctx->pt2_w));
     TRY_S(load_vec(ctx, ws, "point_embed.layers.2.bias", 2, &ctx->pt2_b));
     if (c.has_sigma) {
-      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.0", E, E, &ctx->sg0, true));
-      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.1", E, E, &ctx->sg1, true));
+      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.0", E, E, &ctx->sg0, ctx->dec_x3));
+      TRY_S(load_linear(ctx, ws, "sigma_embed.layers.1", E, E, &ctx->sg1, ctx->dec_x3));
       const HostTensor* s2 = ws.get("sigma_embed.layers.2.weight", {1, E});
       if (!s2) return ws.missing;
       TRY_S(upload_f32(ctx, s2->data, E, &ctx->sg2_w));
@@ -736,7 +762,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
     ctx->ws_sets.assign(1, set0);
     ctx->ws_current = 0;
   }
-  TRY_S(dmalloc(ctx, &ctx->colsum, 8192));
+  TRY_S(dmalloc(ctx, &ctx->colsum, 8192 + 2 * 256 * 4096));   // sums + per-block partials
   // pipeline buffers
   TRY_S(dmalloc(ctx, &ctx->boxes_dev, B * 4));
   TRY_S(dmalloc(ctx, &ctx->images_dev, B * 3 * R * R));
@@ -786,18 +812,22 @@ struct Fwd {
     if (!ctx->calibrating || w.w32 == nullptr || w.x3 || rows <= 0) return "";
     if (C > 4096) return "calibration: more than 4096 input channels";
     if (w.bias == nullptr && w.addend == nullptr) return "";
-    SPE_CUDA_TRY(cudaMemsetAsync(ctx->colsum, 0, sizeof(float) * 8192, st));
     float* cs = ctx->colsum;
     float* cs_mma = ctx->colsum + 4096;
-    const unsigned blocks = static_cast<unsigned>(rows < 2048 ? rows : 2048);
+    constexpr int kColsumBlocks = 256;
+    const unsigned blocks = static_cast<unsigned>(rows < kColsumBlocks ? rows : kColsumBlocks);
+    float* part = ctx->colsum + 8192;
+    float* part_mma = part + static_cast<long long>(kColsumBlocks) * 4096;
     const unsigned cgrid = static_cast<unsigned>((w.N + 7) / 8);
     const float inv = 1.0f / static_cast<float>(rows);
     if (dt == kTF32) {
-      colsum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(A), rows, C, ld, cs, cs_mma);
+      colsum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(A), rows, C, ld, part, part_mma);
+      colsum_reduce_kernel<<<(C + 255) / 256, 256, 0, st>>>(part, part_mma, static_cast<int>(blocks), C, cs, cs_mma);
       bias_correction_kernel<float><<<cgrid, 256, 0, st>>>(w.w32, static_cast<const float*>(w.w), cs, cs_mma, inv, w.N, w.K, C,
                                                            w.scale, w.bias, w.applied, w.addend, w.addend_rows, w.addend_ld);
     } else {
-      colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(A), rows, C, ld, cs, cs_mma);
+      colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(A), rows, C, ld, part, part_mma);
+      colsum_reduce_kernel<<<(C + 255) / 256, 256, 0, st>>>(part, part_mma, static_cast<int>(blocks), C, cs, cs_mma);
       bias_correction_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>(w.w32, static_cast<const __nv_bfloat16*>(w.w), cs, cs_mma, inv,
                                                                    w.N, w.K, C, w.scale, w.bias, w.applied, w.addend,
                                                                    w.addend_rows, w.addend_ld);
@@ -846,9 +876,10 @@ struct Fwd {
     return conv(x, H, C, 3, 1, w, out, out_ld, relu);
   }
   std::string attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int Lq,
-                   int Lk, int exact_out = 0, int mixed = 0) {
+                   int Lk, int exact_out = 0, int mixed = 0, int x3 = 0) {
     AttnDesc a;
     a.exact_out = exact_out;
+    a.x3 = x3;
     a.mixed = mixed;
     a.q = q; a.k = k; a.v = v; a.out = out;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = 256;
@@ -867,6 +898,18 @@ struct Fwd {
 
 // Unrounded residual stream (see spe_ctx::exact_stream): only together with the calibration that removes the bias of the
 // tensor core's operand truncation -- an uncalibrated context keeps rounding every store.
+// the K/V projection runs in its hoisted 3xTF32 form (see spe_ctx::kv_x3)
+static bool kv_split_on(const spe_ctx* ctx) {
+  if (!ctx->kv_split3) return false;
+  return ctx->kv_x3 > 0 || !(ctx->calibrated || ctx->calibrating);
+}
+// profiling only (results are garbage): SPE_DBG_SKIP bit mask leaves stages out of the schedule so that their cost
+// under batches-in-flight can be read off the step time: 1 decoder + heads, 2 encoder attention, 4 encoder FFN,
+// 8 decoder K/V projection, 16 layer1, 32 layer2, 64 layer3, 128 neck 3x3 convolutions, 256 encoder Q|K|V + out-proj
+static int dbg_skip() {
+  static const int m = getenv("SPE_DBG_SKIP") ? atoi(getenv("SPE_DBG_SKIP")) : 0;
+  return m;
+}
 static bool exact_stream_on(const spe_ctx* ctx) {
   return ctx->exact_stream && ctx->dt == kTF32 && (ctx->calibrated || ctx->calibrating);
 }
@@ -884,8 +927,7 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   // ---- stem
   if (ctx->calibrating && ctx->stem.w32 != nullptr) {
     // channel means of the normalised image; the filter in im2col layout [64, 192] has k % 3 = channel
-    SPE_CUDA_TRY(cudaMemsetAsync(ctx->colsum, 0, sizeof(float) * 3, st));
-    nchw_chansum_kernel<<<B * 3, 256, 0, st>>>(images, B, 3, static_cast<long long>(R) * R, ctx->colsum);
+    nchw_chansum_kernel<<<3, 256, 0, st>>>(images, B, 3, static_cast<long long>(R) * R, ctx->colsum);
     const GemmW& w = ctx->stem;
     const float inv = 1.0f / (static_cast<float>(B) * R * R);
     if (f.dt == kTF32)
@@ -932,6 +974,7 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
     for (int bi = 0; bi < nblk[li]; ++bi, ++bidx) {
       const Bottleneck& bk = ctx->blocks[bidx];
       const int Ho = H / bk.stride;
+      if (dbg_skip() & (16 << li)) { H = Ho; continue; }
       const long long Min = Bl * H * H, Mout = Bl * Ho * Ho;
       void* nxt;
       if (bi == nblk[li] - 1 && li == 1) nxt = ctx->L2OUT;
@@ -968,8 +1011,10 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
     const int h16 = R / 16;
     TRY_S(f.gemm(ctx->L2OUT, Bl * T, ctx->s8_lat, ctx->CAT, 512, false));
     TRY_S(launch_upsample2x(f.dt, ctx->L3OUT, B, h16, h16, 1024, ctx->UP, st));
+    if (!(dbg_skip() & 128)) {
     TRY_S(f.conv3x3(ctx->UP, FH, 1024, ctx->s16_lat, f.col(ctx->CAT, 256), 512, false));
     TRY_S(f.conv3x3(ctx->CAT, FH, 512, ctx->out_conv, ctx->FEAT, 512, false));
+    }
     TRY_S(f.tap("neck", ctx->FEAT, Bl * T * 512));
     feat = ctx->FEAT;
   } else {
@@ -983,8 +1028,8 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   for (int i = 0; i < c.enc_layers; ++i) {
     const EncLayer& L = ctx->enc[i];
     if (f.dt == kTF32 || !ctx->mixed_attention) {
-      TRY_S(f.gemm(Xc, Bl * T, L.qkv, ctx->QKV, 768, false, L.addend, 768, Ti, 1));
-      TRY_S(f.attn(ctx->QKV, 768, f.col(ctx->QKV, 256), 768, f.col(ctx->QKV, 512), 768, ctx->ATT, Ti, Ti));
+      if (!(dbg_skip() & 256)) TRY_S(f.gemm(Xc, Bl * T, L.qkv, ctx->QKV, 768, false, L.addend, 768, Ti, 1));
+      if (!(dbg_skip() & 2)) TRY_S(f.attn(ctx->QKV, 768, f.col(ctx->QKV, 256), 768, f.col(ctx->QKV, 512), 768, ctx->ATT, Ti, Ti));
     } else {
       // bf16 storage: Q|K|V leave the GEMM as fp32 (TF32 values) so that the encoder attention can run on the tcgen05 /
       // TMEM kernel (184 us per layer at B = 64) instead of the mma.sync register kernel (445 us); its output is bf16
@@ -992,17 +1037,18 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
       TRY_S(f.gemm(Xc, Bl * T, L.qkv, q32, 768, false, L.addend, 768, Ti, 1, true, 1));
       TRY_S(f.attn(q32, 768, q32 + 256, 768, q32 + 512, 768, ctx->ATT, Ti, Ti, 0, 1));
     }
-    TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
+    if (!(dbg_skip() & 256)) TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
     TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc, exact_stream_on(ctx) ? 1 : 0));
     // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: emit it pre-split
     const bool last = i == c.enc_layers - 1;
-    const bool split = last && ctx->kv_split3;
+    const bool split = last && kv_split_on(ctx);
     void* XSc = split ? static_cast<uint8_t*>(ctx->XS) + (static_cast<uint8_t*>(Xc) - static_cast<uint8_t*>(ctx->X)) * 3
                       : nullptr;
     // feed-forward block + norm2 in one kernel (the 2048-wide hidden activation stays in tensor memory); the tap of
     // the last layer needs both output forms, so bring-up runs take the unfused path there
     // (small batches keep the two-GEMM path: one 128-row tile per CTA cannot fill the machine below ~74 tiles)
-    if (ffn_fused_supported(f.dt, 256, c.dim_feedforward) && !(split && ctx->taps_enabled) && !ctx->calibrating &&
+    if (dbg_skip() & 4) {
+    } else if (ffn_fused_supported(f.dt, 256, c.dim_feedforward) && !(split && ctx->taps_enabled) && !ctx->calibrating &&
         (Bl * T + 127) / 128 >= ctx->num_sms / 2) {
       FfnDesc d;
       d.X = Xc; d.M = Bl * T;
@@ -1034,15 +1080,17 @@ static std::string forward_kv(spe_ctx* ctx, int B, void* kv, cudaStream_t st) {
   Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
   const long long T = ctx->tokens;
   const int kvld = ctx->cfg.dec_layers * 512;
-  if (!ctx->kv_split3) TRY_S(f.calibrate_layer(ctx->X, static_cast<long long>(B) * T, 256, 256, ctx->ca_kv_all));
+  const bool split = kv_split_on(ctx);
+  const GemmW& w = split ? ctx->ca_kv_x3 : ctx->ca_kv_all;
+  if (!split) TRY_S(f.calibrate_layer(ctx->X, static_cast<long long>(B) * T, 256, 256, w));
   GemmDesc d;
   d.mode = 0;
-  d.A = ctx->kv_split3 ? ctx->XS : ctx->X;
-  d.M = static_cast<long long>(B) * T; d.K = ctx->ca_kv_all.K; d.lda = ctx->ca_kv_all.K;
-  d.Wt = ctx->ca_kv_all.w; d.N = ctx->ca_kv_all.N;
+  d.A = split ? ctx->XS : ctx->X;
+  d.M = static_cast<long long>(B) * T; d.K = w.K; d.lda = w.K;
+  d.Wt = w.w; d.N = w.N;
   d.residual = ctx->ca_kv_addend; d.res_ld = kvld; d.res_mod = static_cast<int>(T); d.res_f32 = 1;
   d.out = kv; d.out_ld = kvld;
-  d.round_out = ctx->kv_split3 ? 0 : 1;   // the decoder attention rounds its own operands
+  d.round_out = split ? 0 : 1;   // the decoder attention rounds its own operands
   return launch_gemm(f.dt, d, ctx->num_sms, st);
 }
 
@@ -1060,19 +1108,26 @@ static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, fl
   const long long MQ = Bl * Q;
   const int kvld = LD * 512;
   SPE_CUDA_TRY(cudaMemsetAsync(ctx->TGT, 0, static_cast<size_t>(MQ * 256 * f.es), st));
+  // fp32 storage: with 3xTF32 GEMMs the decoder state stays unrounded fp32 end to end; with plain TF32 GEMMs
+  // (SPE_DEC_X3=0) whatever feeds a GEMM is rounded by its producer.  The attention products are error-compensated in
+  // both cases for the SELF-attention (the learned query embeddings can drive its logits into the hundreds).
+  const int ex = (f.dt == kTF32 && ctx->dec_x3) ? 1 : 0;
+  const int ax3 = f.dt == kTF32 ? 1 : 0;
   for (int i = 0; i < LD; ++i) {
     const DecLayer& L = ctx->dec[i];
     TRY_S(f.gemm(ctx->TGT, MQ, L.sa_qkv, ctx->DQKV, 768, false, L.sa_addend, 768, Q, 1));
-    TRY_S(f.attn(ctx->DQKV, 768, f.col(ctx->DQKV, 256), 768, f.col(ctx->DQKV, 512), 768, ctx->DATT, Q, Q, 1));
-    TRY_S(f.gemm(ctx->DATT, MQ, L.sa_out, ctx->TGT2, 256, false, ctx->TGT, 256));
-    TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT, 1));
+    TRY_S(f.attn(ctx->DQKV, 768, f.col(ctx->DQKV, 256), 768, f.col(ctx->DQKV, 512), 768, ctx->DATT, Q, Q, ex, 0, ax3));
+    TRY_S(f.gemm(ctx->DATT, MQ, L.sa_out, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
+    TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT, ex));
     TRY_S(f.gemm(ctx->TGT, MQ, L.ca_q, ctx->DQ, 256, false, L.ca_q_addend, 256, Q, 1));
-    TRY_S(f.attn(ctx->DQ, 256, f.col(kv, i * 512), kvld, f.col(kv, i * 512 + 256), kvld, ctx->DATT, Q, Ti, 1));
-    TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, ctx->TGT, 256));
-    TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT, 1));
+    // cross-attention stays on the tcgen05 kernel (plain TF32 operands): its logits are bounded by the LayerNorm-ed
+    // memory (tens at most), where TF32 is accurate to ~1e-2 of a logit -- measured harmless; 28 vs ~80 us per layer
+    TRY_S(f.attn(ctx->DQ, 256, f.col(kv, i * 512), kvld, f.col(kv, i * 512 + 256), kvld, ctx->DATT, Q, Ti, ex));
+    TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));
+    TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT, ex));
     TRY_S(f.gemm(ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
-    TRY_S(f.gemm(ctx->DHID, MQ, L.ff2, ctx->TGT2, 256, false, ctx->TGT, 256));
-    TRY_S(f.ln(ctx->TGT2, L.n3g, L.n3b, MQ, ctx->TGT, 1));
+    TRY_S(f.gemm(ctx->DHID, MQ, L.ff2, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));
+    TRY_S(f.ln(ctx->TGT2, L.n3g, L.n3b, MQ, ctx->TGT, ex));
     TRY_S(f.ln(ctx->TGT, ctx->dn_g, ctx->dn_b, MQ, f.col(ctx->HS, static_cast<long long>(i) * MQ * 256), 1));
   }
   TRY_S(f.tap("hs", ctx->HS, static_cast<long long>(LD) * MQ * 256));
@@ -1149,9 +1204,9 @@ static std::string forward_schedule(spe_ctx* ctx, int parts, int kv_slot, const 
       void* Xc = static_cast<uint8_t*>(ctx->X) + static_cast<long long>(c0) * ctx->tokens * 256 * es;
       TRY_S(forward_trunk(ctx, images + c0 * img_elems, nb, Xc, st));
     }
-    TRY_S(forward_kv(ctx, B, kv, st));
+    if (!(dbg_skip() & 8)) TRY_S(forward_kv(ctx, B, kv, st));
   }
-  if (parts & 2) TRY_S(forward_tail(ctx, B, kv, logits, points, logsig, aux_logits, aux_points, st));
+  if ((parts & 2) && !(dbg_skip() & 1)) TRY_S(forward_tail(ctx, B, kv, logits, points, logsig, aux_logits, aux_points, st));
   return "";
 }
 

@@ -669,12 +669,13 @@ assign_pnp_kernel(const PnpDesc d) {
   for (int i = 0; i < 9; ++i) best.R[i] = 0.0;
   best.t[0] = best.t[1] = best.t[2] = 0.0;
   const double thr = static_cast<double>(d.reproj_dev ? d.reproj_dev[img] : d.reproj_thresh);
-  // exactly four correspondences: cv2.solvePnPRansac skips RANSAC (model_points == npoints), takes the P3P pose the
-  // fourth point selects and reports all four as inliers -- no threshold is applied
+  // exactly four correspondences: cv2.solvePnPRansac skips RANSAC (model_points == npoints) and calls solvePnP(P3P),
+  // which solves the FIRST three correspondences and lets the fourth pick among the (up to four) solutions; all four
+  // are reported as inliers and no threshold is applied
   const double thr2 = n == 4 ? INFINITY : thr * thr;
   // Every thread first decodes its own triple index, then all lanes run the solver together: calling it from inside
   // the enumeration loop would serialise the warp (one active lane per iteration).
-  const int ntriples = n * (n - 1) * (n - 2) / 6;
+  const int ntriples = n == 4 ? 1 : n * (n - 1) * (n - 2) / 6;     // n == 4: triple #0 = correspondences (0, 1, 2)
   for (int c = static_cast<int>(threadIdx.x); c < ((ntriples + kPnpThreads - 1) / kPnpThreads) * kPnpThreads;
        c += kPnpThreads) {
     int i0 = 0, i1 = 1, i2 = 2;

@@ -67,6 +67,7 @@ struct AttnDesc {
   float scale;                                  // 1/sqrt(head_dim)
   int exact_out = 0;                            // fp32 storage: do not round the output to TF32
   int mixed = 0;                                // bf16 storage, tcgen05 path: q / k / v are fp32 (TF32 values), out is bf16
+  int x3 = 0;                                   // fp32 storage: error-compensated products (register kernel only)
 };
 std::string launch_attention(Dtype dt, const AttnDesc& d, cudaStream_t s);
 // tcgen05 / TMEM path (attention_tc.cu); launch_attention dispatches to it when supported
@@ -99,6 +100,13 @@ std::string launch_head_final(Dtype dt, const void* hs, const void* h2, const vo
                               const float* Wc, const float* bc, const float* W3, const float* b3,
                               const float* Ws3, const float* bs3, float* logits, float* points, float* logsig,
                               cudaStream_t s);
+
+// ---- SA (RT-DETR) decoder pieces (deform_attn.cu) ----
+std::string launch_ms_deform_attn(const float* value, const int* shapes_hw, int L, const float* loc, const float* attn,
+                                  const float* ref, int ref_levels, int B, int Lq, int heads, int P, int fused,
+                                  float* out, cudaStream_t s);
+std::string launch_topk_queries(const float* cls, int B, int Lv, int C, int k, int32_t* idx, float* vals, cudaStream_t s);
+std::string launch_gather_rows(const float* src, const int32_t* idx, int B, int Lv, int k, int D, float* out, cudaStream_t s);
 
 // ---- crop (crop.cu) ----
 std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long long pitch, long long frame_stride,

@@ -268,6 +268,46 @@ class Engine:
             out["pooled_px"] = pooled
         return out
 
+    # ---- SA (RT-DETR) decoder pieces ----------------------------------------------------------------------------
+    def ms_deform_attn(self, value, spatial_shapes, loc, attn, ref=None):
+        """Multi-scale deformable attention core (``deformable_attention_core_func``, SA/src/zoo/rtdetr/utils.py:15-64).
+        ``value`` cuda float32 [B, Lv, heads, 32]; ``spatial_shapes`` [(H_l, W_l)]; without ``ref``: ``loc``
+        [B, Lq, heads, L, P, 2] sampling locations in [0, 1] and ``attn`` [B, Lq, heads, L, P] softmaxed weights;
+        with ``ref`` [B, Lq, 1 or L, 2]: ``loc`` / ``attn`` are the raw outputs of ``MSDeformableAttention``'s
+        ``sampling_offsets`` / ``attention_weights`` linear layers (rtdetr_decoder.py:117-163).  -> [B, Lq, heads*32]."""
+        value, loc, attn = value.contiguous().float(), loc.contiguous().float(), attn.contiguous().float()
+        B, Lv, heads, hd = value.shape
+        assert hd == 32 and value.is_cuda
+        Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+        shp = np.ascontiguousarray(np.asarray(spatial_shapes, dtype=np.int32).reshape(L, 2))
+        assert int((shp[:, 0] * shp[:, 1]).sum()) == Lv
+        if ref is not None:
+            ref = ref.contiguous().float()
+        out = torch.empty((B, Lq, heads * 32), dtype=torch.float32, device=value.device)
+        check(self.lib.spe_ms_deform_attn(self._ctx, _ptr(value), shp.ctypes.data_as(C.c_void_p), L, _ptr(loc), _ptr(attn),
+                                          _ptr(ref), ref.shape[2] if ref is not None else 0, B, Lq, heads, P,
+                                          int(ref is not None), _ptr(out), _stream(value.device)), self._ctx)
+        return out
+
+    def topk_queries(self, enc_class, k):
+        """``torch.topk(enc_outputs_class.max(-1).values, k, dim=1)`` (rtdetr_decoder.py:646-648): cuda float32
+        [B, Lv, C] -> (values [B, k], indices int32 [B, k]) in descending score order."""
+        x = enc_class.contiguous().float()
+        B, Lv, Cc = x.shape
+        idx = torch.empty((B, k), dtype=torch.int32, device=x.device)
+        val = torch.empty((B, k), dtype=torch.float32, device=x.device)
+        check(self.lib.spe_topk_queries(self._ctx, _ptr(x), B, Lv, Cc, k, _ptr(idx), _ptr(val), _stream(x.device)), self._ctx)
+        return val, idx
+
+    def gather_rows(self, src, idx):
+        """``src.gather(1, idx[..., None].repeat(1, 1, D))`` (rtdetr_decoder.py:651-680): [B, Lv, D], int32 [B, k] -> [B, k, D]."""
+        src = src.contiguous().float(); idx = idx.contiguous().to(torch.int32)
+        B, Lv, D = src.shape
+        k = idx.shape[1]
+        out = torch.empty((B, k, D), dtype=torch.float32, device=src.device)
+        check(self.lib.spe_gather_rows(self._ctx, _ptr(src), _ptr(idx), B, Lv, k, D, _ptr(out), _stream(src.device)), self._ctx)
+        return out
+
     # ---- whole path, host in / host out -----------------------------------------------------------------------
     def run_batch_host(self, frames_host, det_boxes, reproj=20.0, weighted=False, reject=False):
         """frames_host: uint8 (pinned) torch/numpy [B,H,W]; det_boxes: float64 [B,4] -> numpy quat/tvec/status/boxes."""
