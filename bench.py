@@ -138,7 +138,16 @@ class ClockSampler:
 CPU_BATCH = 8      # images per forward call of the CPU arm (batch 64 gains nothing on the host cores and takes 2.4 s a step)
 
 
+def _one_thread():
+    """a pool worker must not spawn its own thread pools (16 processes x 16 threads thrash the cores)"""
+    import cv2
+    import torch
+    cv2.setNumThreads(1)
+    torch.set_num_threads(1)
+
+
 def _pool_crop(job):
+    _one_thread()
     from oracle import crop_ref, synth
     frames, det = synth.bench_set(0)
     t0 = time.perf_counter()
@@ -148,6 +157,7 @@ def _pool_crop(job):
 
 
 def _pool_pnp(job):
+    _one_thread()
     from oracle import pnp_ref, synth
     d = synth.make_predictions(len(job), seed=1)
     res = pnp_ref.post_process(d["logits"], d["points"], d["boxes"])

@@ -13,6 +13,13 @@
 //               their partial row maxima through shared memory.  P is written back over S in TMEM (tcgen05.st); the
 //               32-column O accumulator (16 columns per warp) is rescaled when the running maximum moves
 //               (online softmax, fp32 statistics)
+// Softmax reference: the running row maximum is taken from the FIRST chunk only (two passes over it: maximum, then
+// exponentials) and kept for the whole row; later chunks run a single pass p = 2^((s - m_0) c).  Probabilities above 1
+// are as exact in floating point as those below, so O / l is the same softmax -- without the per-chunk maximum pass,
+// the partial-maximum exchange between the two warps of a row and the rescaling of O (a fifth of the softmax warps'
+// instructions, two barrier round trips per chunk).  A row whose later scores exceed m_0 by more than ~350 logits would
+// overflow: its row sum then fails the `l < 1e30` check at the end and the whole CTA repeats its tile with the
+// classical online softmax (every chunk two passes, O rescaled when the maximum moves) on a second set of barriers.
 // TMEM columns: two score / probability buffers [0, NK) and [NK, 2 NK) (QK^T of chunk j+1 is issued while the softmax
 // of chunk j runs), output accumulator at [2 NK, 2 NK + 32).
 #include "spe_internal.h"
@@ -38,6 +45,7 @@ struct AttnTcParams {
   int exact_out;
   int debug;
   int out_bf16;     // bf16-storage models: Q / K / V arrive as fp32 (TF32 values), the output is written as bf16
+  int safe_softmax; // 1: classical online softmax from the start (SPE_ATTN_SAFE=1; the fast path falls back to it by itself)
 };
 
 template <int NK> struct AttnSmem {
@@ -46,7 +54,7 @@ template <int NK> struct AttnSmem {
   static constexpr int STAGE_BYTES = 2 * KV_BYTES;
   static constexpr int STAGES = 3;
   static constexpr int XCHG_BYTES = 2 * 2 * kQRows * 4 + 2 * kQRows * 4;   // partial maxima [2][2][128] + sums [2][128]
-  static constexpr int BYTES = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 16 + XCHG_BYTES + 1024;
+  static constexpr int BYTES = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 16 + XCHG_BYTES + 16 * 8 + 1024;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -70,18 +78,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + SM::Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + SM::STAGES * SM::STAGE_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;
-  uint64_t* pv_done = bars + 10;
+  uint64_t* bars0 = reinterpret_cast<uint64_t*>(sKV + SM::STAGES * SM::STAGE_BYTES);
+  uint64_t* q_full = bars0 + 0;
   constexpr uint32_t kOCol = 2 * NK;
   static_assert(2 * NK + 32 <= kTmemCols, "two score buffers and the output accumulator must fit the TMEM allocation");
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
-  float* sm_max = reinterpret_cast<float*>(bars + 18);        // [2 chunk parities][2 halves][128 rows]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars0 + 16);
+  float* sm_max = reinterpret_cast<float*>(bars0 + 18);       // [2 chunk parities][2 halves][128 rows]
   float* sm_sum = sm_max + 2 * 2 * kQRows;                    // [2 halves][128 rows]
+  uint64_t* bars1 = reinterpret_cast<uint64_t*>(sm_sum + 2 * kQRows);   // barrier set of the repeat pass
+  volatile int* vote = reinterpret_cast<volatile int*>(bars1 + 14);     // set when a row sum overflowed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -93,11 +98,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 8);
-    mbar_init(pv_done, 1);
+    vote[0] = 0;
+    for (int a = 0; a < 2; ++a) {
+      uint64_t* bb = a == 0 ? bars0 : bars1;
+      for (int i = 0; i < 3; ++i) { mbar_init(&bb[1 + i], 1); mbar_init(&bb[4 + i], 1); }
+      mbar_init(&bb[7], 1);
+      mbar_init(&bb[8], 1);
+      mbar_init(&bb[9], 8);
+      mbar_init(&bb[10], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -114,9 +123,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // Producer and MMA warps run warp-uniform loops; one elected lane issues (spe_ptx.cuh: elect_one_sync) -- under
   // `if (lane == 0)` every one of the 18 MMAs of a chunk was wrapped in a ~90-cycle waterfall loop, 3.6 x their 450
   // tensor-pipe cycles.
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  const bool fast = attempt == 0 && !p.safe_softmax;     // fixed softmax reference (see the header); attempt 1 = classical
+  uint64_t* bars = attempt == 0 ? bars0 : bars1;
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* pv_done = bars + 10;
+  int bad = 0;
   if (warp == 0) {
     {
-      if (elect_one_sync()) {
+      if (attempt == 0 && elect_one_sync()) {
         mbar_expect_tx(q_full, SM::Q_BYTES);
         tma_load_2d(sQ, &tmQ, q_full, h * 32, b * p.Lq + q0);
       }
@@ -195,6 +213,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t trow = trow0 + static_cast<uint32_t>((j & 1) * NK + cbeg);   // this warp's score columns
       const int key0 = j * NK + cbeg;
       const bool full = j * NK + NK <= p.Lk;               // no ragged tail inside this chunk (the common case)
+      float alpha = 1.0f;
+      if (!fast || j == 0) {
       // ---- pass 1: partial row maximum (four independent chains; the ragged-tail predicate is hoisted out of the
       //      per-element loops -- ncu showed 11 issued instructions per score element with it inside)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -231,8 +251,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       named_bar_sync(1 + q, 64);
       mx = fmaxf(mx, xm[(half ^ 1) * kQRows + row]);
       const float m_new = fmaxf(m, mx);                    // finite: every chunk holds at least one valid key
-      const float alpha = ex2((m - m_new) * c);            // 0 on the first chunk (m = -inf)
-      const float mc = m_new * c;
+      alpha = ex2((m - m_new) * c);                        // 0 on the first chunk (m = -inf)
+      m = m_new;
+      }
+      const float mc = m * c;
+      bool done = false;
+      if constexpr (NK == 112) {
+        if (fast && j > 0) {
+          // ---- single pass, balanced split: each warp of a row owns 56 columns = pieces of 32 + 16 + 8, all three
+          //      loads in flight before the first exponential (one TMEM round trip per chunk instead of three)
+          const uint32_t t56 = trow0 + static_cast<uint32_t>((j & 1) * NK + half * 56);
+          uint32_t va[32], vb[16], vc[8];
+          tmem_ld_32x32(t56, va);
+          tmem_ld_32x16(t56 + 32u, vb);
+          tmem_ld_32x8(t56 + 48u, vc);
+          tmem_wait_ld();
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            va[i] = __float_as_uint(ex2(fmaf(__uint_as_float(va[i]), c, -mc))) & 0xffffe000u;
+            s4[i & 3] += __uint_as_float(va[i]);
+          }
+          tmem_st_32x32(t56, va);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            vb[i] = __float_as_uint(ex2(fmaf(__uint_as_float(vb[i]), c, -mc))) & 0xffffe000u;
+            s4[i & 3] += __uint_as_float(vb[i]);
+          }
+          tmem_st_32x16(t56 + 32u, vb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            vc[i] = __float_as_uint(ex2(fmaf(__uint_as_float(vc[i]), c, -mc))) & 0xffffe000u;
+            s4[i & 3] += __uint_as_float(vc[i]);
+          }
+          tmem_st_32x8(t56 + 48u, vc);
+          l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          done = true;
+        }
+      }
+      if (!done) {
       // ---- pass 2: probabilities, written back over the scores.  P is cut to TF32 with one LOP3 (the conversion
       //      instruction shares the MUFU pipe with ex2) and the row sum is taken over the SAME cut values the tensor
       //      core will multiply, so the normalisation stays consistent (no truncation bias in O / l).
@@ -270,13 +327,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_st_32x16(trow + static_cast<uint32_t>(n32 * 32), v);
       }
       l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));   // partial sum over this warp's columns
-      m = m_new;
+      }
       // ---- P V_{j-1} must have landed before O may be touched; waiting for it on EVERY chunk also keeps this warp
       //      exactly one phase behind the pv_done barrier (a parity wait two phases late would alias and fall through)
       if (j > 0) {
         mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u, 16);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale the running output when a row maximum moved
+        if (!fast && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale the running output when a row maximum moved
           uint32_t o[16];
           tmem_ld_32x16(trow0 + ocol, o);
           tmem_wait_ld();
@@ -296,10 +353,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     l += sm_sum[(half ^ 1) * kQRows + row];
     mbar_wait(pv_done, static_cast<uint32_t>(nchunks - 1) & 1u, 17);
     tc_fence_after();
+    bad = (fast && q0 + row < p.Lq && !(l < 1e30f)) ? 1 : 0;      // overflowed row (or NaN): repeat the tile classically
+    if (bad) vote[0] = 1;
+    named_bar_sync(9, 256);                                        // the eight softmax warps agree before anything is stored
+    const bool redo = fast && vote[0] != 0;
     uint32_t o[16];
     tmem_ld_32x16(trow0 + ocol, o);
     tmem_wait_ld();
-    if (q0 + row < p.Lq && p.out_bf16) {
+    if (redo) {
+      // nothing is stored; every warp meets at the barrier below and runs the tile again
+    } else if (q0 + row < p.Lq && p.out_bf16) {
       const float inv = 1.0f / l;
       __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) +
                           (static_cast<long long>(b) * p.Lq + q0 + row) * p.ldo + h * 32 + half * 16;
@@ -326,9 +389,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   }
-
+  (void)bad;
   tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  if (!fast || vote[0] == 0) break;       // done, unless a row overflowed the fixed-reference softmax: run the tile again
+  }
+
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -364,6 +431,8 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
   p.out_bf16 = d.mixed;
   static const bool dbg = getenv("SPE_ATTN_DEBUG") != nullptr;
   p.debug = dbg ? 1 : 0;
+  static const bool safe = getenv("SPE_ATTN_SAFE") != nullptr && atoi(getenv("SPE_ATTN_SAFE")) != 0;
+  p.safe_softmax = safe ? 1 : 0;
   dim3 grid((d.Lq + kQRows - 1) / kQRows, d.heads, d.B);
   ProfScope ps(kFamAttention, s);
   SPE_CUDA_TRY(launch_pdl(kfn, grid, dim3(kThreads), SM::BYTES, s, tmQ, tmK, tmV, p));

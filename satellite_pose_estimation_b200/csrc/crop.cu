@@ -27,32 +27,62 @@ __device__ __forceinline__ void cubic_w(double t, double (&w)[4]) {
   w[3] = 1.0 - w[0] - w[1] - w[2];
 }
 
-// One thread per output COLUMN, kRows output rows per block: the horizontal taps (four clamped frame columns + four
-// fp64 cubic weights, a third of the kernel's arithmetic) depend on the column only and are computed once per thread;
-// threadIdx.x walks ox, so the three channel stores of every row are fully coalesced, and the 4 x 4 source bytes of
-// neighbouring columns share sectors (at the median crop side of 430 px a warp's 32 columns span 61 source bytes).
-// Measured: 49 us -> see profiles/r02_ncu_crop.md for 64 frames.
+// One thread per output COLUMN, kCropRows output rows per block.
+//  * the horizontal taps (four clamped frame columns + four fp64 cubic weights) depend on the column only and are
+//    computed once per thread; the vertical taps (four clamped frame rows + weights) depend on the row only and are
+//    computed once per BLOCK by its first kCropRows threads and shared through shared memory
+//  * ncu on the first version (profiles/r02_ncu_crop.md) showed the kernel bound by the XU pipe (46 % busy: 16 uint8 ->
+//    fp64 conversions, floor, rint and fp64 -> int per pixel), not by memory.  Conversions now stay off that pipe: a byte
+//    becomes a double by OR-ing it into the mantissa of 2^52 and subtracting 2^52 (exact), and the final rounding is
+//    the classic add-and-subtract of 1.5 * 2^52 (round-half-even in the default rounding mode, exactly rint() for
+//    |x| < 2^51), the integer read straight from the low word of the sum
+//  * threadIdx.x walks ox, so the three channel stores of every row are fully coalesced, and the 4 x 4 source bytes of
+//    neighbouring columns share sectors (at the median crop side of 430 px a warp's 32 columns span 61 source bytes)
 constexpr int kCropRows = 8;
+
+__device__ __forceinline__ double u8_to_f64(unsigned v) {          // exact, no conversion instruction
+  return __hiloint2double(0x43300000, static_cast<int>(v)) - 4503599627370496.0;   // (2^52 + v) - 2^52
+}
 
 __global__ void __launch_bounds__(256)
 crop_resize_norm_kernel(const uint8_t* __restrict__ frames, int H, int W, long long pitch, long long frame_stride,
                         const int32_t* __restrict__ boxes, int R, float* __restrict__ out) {
+  __shared__ double s_wy[kCropRows][4];
+  __shared__ int s_gy[kCropRows][4];          // frame row of each vertical tap, -1 = outside the frame (zero canvas)
   const int b = blockIdx.z;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ox >= R) return;
+  const int oy0 = blockIdx.y * kCropRows;
 
   const int x1 = boxes[b * 4 + 0];
   const int y1 = boxes[b * 4 + 1];
   // canvas extent: square (clip_size) on the submission path, any rectangle on the eval path (PIL crop squashed to R x R)
   const int S = boxes[b * 4 + 2] - x1;
   const int Sy = boxes[b * 4 + 3] - y1;
-  const uint8_t* frame = frames + static_cast<long long>(b) * frame_stride;
-  const long long plane = static_cast<long long>(R) * R;
   const bool empty = !(S > 0 && Sy > 0);
 
+  if (threadIdx.x < kCropRows && !empty) {
+    const int oy = oy0 + threadIdx.x;
+    const double fy = (oy + 0.5) * (static_cast<double>(Sy) / static_cast<double>(R)) - 0.5;
+    const double fly = floor(fy);
+    const int sy = static_cast<int>(fly);
+    double wy[4];
+    cubic_w(fy - fly, wy);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = sy - 1 + j;
+      c = c < 0 ? 0 : (c > Sy - 1 ? Sy - 1 : c);   // replicate the canvas border
+      const int gy = y1 + c;                       // canvas -> frame row
+      s_wy[threadIdx.x][j] = wy[j];
+      s_gy[threadIdx.x][j] = (gy >= 0 && gy < H) ? gy : -1;
+    }
+  }
+  __syncthreads();
+  if (ox >= R) return;
+
+  const uint8_t* frame = frames + static_cast<long long>(b) * frame_stride;
+  const long long plane = static_cast<long long>(R) * R;
   double wx[4];
   int cx[4];
-  bool inx[4];
   if (!empty) {
     const double fx = (ox + 0.5) * (static_cast<double>(S) / static_cast<double>(R)) - 0.5;
     const double flx = floor(fx);
@@ -63,47 +93,37 @@ crop_resize_norm_kernel(const uint8_t* __restrict__ frames, int H, int W, long l
       int c = sx - 1 + i;
       c = c < 0 ? 0 : (c > S - 1 ? S - 1 : c);  // replicate the canvas border
       const int gx = x1 + c;                    // canvas -> frame column
-      inx[i] = (gx >= 0) && (gx < W);
-      cx[i] = inx[i] ? gx : 0;
+      const bool in = (gx >= 0) && (gx < W);
+      cx[i] = in ? gx : 0;
+      if (!in) wx[i] = 0.0;                     // outside the frame: zero canvas (0 * w contributes nothing)
     }
   }
-  const double ry = static_cast<double>(Sy) / static_cast<double>(R);
-  const int oy0 = blockIdx.y * kCropRows;
+  float* o = out + static_cast<long long>(b) * 3 * plane + static_cast<long long>(oy0) * R + ox;
 #pragma unroll 2
-  for (int r = 0; r < kCropRows; ++r) {
-    const int oy = oy0 + r;
-    if (oy >= R) break;
-    float v = 0.0f;
+  for (int r = 0; r < kCropRows; ++r, o += R) {
+    if (oy0 + r >= R) break;
+    int iv = 0;
     if (!empty) {
-      const double fy = (oy + 0.5) * ry - 0.5;
-      const double fly = floor(fy);
-      const int sy = static_cast<int>(fly);
-      double wy[4];
-      cubic_w(fy - fly, wy);
       double acc = 0.0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int c = sy - 1 + j;
-        c = c < 0 ? 0 : (c > Sy - 1 ? Sy - 1 : c);
-        const int gy = y1 + c;
-        double row = 0.0;
-        if (gy >= 0 && gy < H) {
+        const int gy = s_gy[r][j];
+        if (gy >= 0) {
           const uint8_t* rp = frame + static_cast<long long>(gy) * pitch;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double px = inx[i] ? static_cast<double>(__ldg(rp + cx[i])) : 0.0;  // outside frame: zero canvas
-            row += px * wx[i];
-          }
+          double row = u8_to_f64(__ldg(rp + cx[0])) * wx[0];
+          row += u8_to_f64(__ldg(rp + cx[1])) * wx[1];
+          row += u8_to_f64(__ldg(rp + cx[2])) * wx[2];
+          row += u8_to_f64(__ldg(rp + cx[3])) * wx[3];
+          acc += row * s_wy[r][j];
         }
-        acc += row * wy[j];
       }
-      double rr = rint(acc);  // round half to even, like cvRound / IPP
-      rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
-      v = static_cast<float>(rr);
+      // round half to even like cvRound / IPP, saturate to uint8
+      const double magic = acc + 6755399441055744.0;                 // 1.5 * 2^52: the integer sits in the low word
+      iv = __double2loint(magic);
+      iv = iv < 0 ? 0 : (iv > 255 ? 255 : iv);
     }
     // to_tensor: uint8 -> float32 / 255 ; Normalize: (x - mean) / std, all IEEE fp32 like the torch CPU ops
-    const float x = __fdiv_rn(v, 255.0f);
-    float* o = out + static_cast<long long>(b) * 3 * plane + static_cast<long long>(oy) * R + ox;
+    const float x = __fdiv_rn(static_cast<float>(iv), 255.0f);
     o[0] = __fdiv_rn(__fsub_rn(x, 0.485f), 0.229f);
     o[plane] = __fdiv_rn(__fsub_rn(x, 0.456f), 0.224f);
     o[2 * plane] = __fdiv_rn(__fsub_rn(x, 0.406f), 0.225f);

@@ -372,6 +372,97 @@ std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, in
   return "";
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// s16_latern at the resolution of its input.  The reference computes conv3x3(upsample2x(x)) (RV/models/backbone.py:
+// 140-141, bilinear, align_corners=True).  Both are linear and the channel mixing commutes with the spatial operators:
+//   conv3x3(U x)[p] = sum_taps W_tap (U x)[p + tap] = sum_taps (U (W_tap x))[p + tap]
+// so the nine 1024 -> 256 tap matrices are applied to the 14 x 14 map (one GEMM, M = 196 per image instead of 784:
+// a quarter of the multiply-adds) and this kernel gathers:  out[p, o] = sum over the taps that fall inside the 28 x 28
+// map (zero padding) of the bilinear interpolation of Y_tap at p + tap.
+// One CTA = one image x kTapCh output channels; its slice of Y ([196 positions][9 taps][kTapCh], 110 KB) is staged in
+// shared memory once and every output reads its 9 x 4 terms from there.
+constexpr int kTapCh = 16;
+template <typename TO>
+__global__ void __launch_bounds__(256)
+upsample_tapsum_kernel(const float* __restrict__ Y, int H, int W, int Cout, TO* __restrict__ out, int out_ld, int round_tf32) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ float sy[];                       // [H*W][9][kTapCh]
+  const int b = blockIdx.x, c0 = blockIdx.y * kTapCh;
+  const int HW = H * W, Ho = 2 * H, Wo = 2 * W;
+  const float* yb = Y + static_cast<long long>(b) * HW * 9 * Cout;
+  for (int u = threadIdx.x; u < HW * 9 * (kTapCh / 4); u += blockDim.x) {
+    const int seg = u / (kTapCh / 4), v4 = u % (kTapCh / 4);     // seg = position * 9 + tap
+    const float4 v = *reinterpret_cast<const float4*>(yb + static_cast<long long>(seg) * Cout + c0 + v4 * 4);
+    *reinterpret_cast<float4*>(sy + seg * kTapCh + v4 * 4) = v;
+  }
+  __syncthreads();
+  const float sh = static_cast<float>(H - 1) / static_cast<float>(Ho - 1);
+  const float sw = static_cast<float>(W - 1) / static_cast<float>(Wo - 1);
+  const int c = threadIdx.x % kTapCh;
+  for (int p = threadIdx.x / kTapCh; p < Ho * Wo; p += blockDim.x / kTapCh) {
+    const int i = p / Wo, j = p % Wo;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ii = i + r - 1;
+      if (ii < 0 || ii >= Ho) continue;               // zero padding of the 3x3 convolution
+      const float fy = sh * ii;
+      const int y0 = static_cast<int>(fy);
+      const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+      const float ly1 = fy - y0, ly0 = 1.f - ly1;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int jj = j + q - 1;
+        if (jj < 0 || jj >= Wo) continue;
+        const float fx = sw * jj;
+        const int x0 = static_cast<int>(fx);
+        const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float lx1 = fx - x0, lx0 = 1.f - lx1;
+        const int t = r * 3 + q;
+        const float a = sy[((y0 * W + x0) * 9 + t) * kTapCh + c], bq = sy[((y0 * W + x1) * 9 + t) * kTapCh + c];
+        const float cq = sy[((y1 * W + x0) * 9 + t) * kTapCh + c], d = sy[((y1 * W + x1) * 9 + t) * kTapCh + c];
+        acc += ly0 * (lx0 * a + lx1 * bq) + ly1 * (lx0 * cq + lx1 * d);   // nn.UpsamplingBilinear2d's expression
+      }
+    }
+    if (sizeof(TO) == 4) {
+      if (round_tf32) acc = __uint_as_float((__float_as_uint(acc) + 0x1000u) & 0xffffe000u);
+      reinterpret_cast<float*>(out)[(static_cast<long long>(b) * Ho * Wo + p) * out_ld + c0 + c] = acc;
+    } else {
+      reinterpret_cast<__nv_bfloat16*>(out)[(static_cast<long long>(b) * Ho * Wo + p) * out_ld + c0 + c] = __float2bfloat16_rn(acc);
+    }
+  }
+}
+
+std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int W, int Cout, void* out, int out_ld,
+                                   cudaStream_t s) {
+  if (NB <= 0) return "";
+  if (Cout % kTapCh) return "upsample_tapsum: output channels must be a multiple of 16";
+  const size_t smem = static_cast<size_t>(H) * W * 9 * kTapCh * sizeof(float);
+  if (smem > 200 * 1024) return "upsample_tapsum: feature map too large for the shared-memory slice";
+  ProfScope ps(kFamElementwise, s);
+  if (dt == kTF32) {
+    static bool attr = false;
+    if (!attr) {
+      SPE_CUDA_TRY(cudaFuncSetAttribute(upsample_tapsum_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    SPE_CUDA_TRY(launch_pdl(upsample_tapsum_kernel<float>, dim3(NB, Cout / kTapCh), dim3(256), smem, s, Y, H, W, Cout,
+                            reinterpret_cast<float*>(out), out_ld, 1));
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      SPE_CUDA_TRY(cudaFuncSetAttribute(upsample_tapsum_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+      attr = true;
+    }
+    SPE_CUDA_TRY(launch_pdl(upsample_tapsum_kernel<__nv_bfloat16>, dim3(NB, Cout / kTapCh), dim3(256), smem, s, Y, H, W, Cout,
+                            reinterpret_cast<__nv_bfloat16*>(out), out_ld, 0));
+  }
+  SPE_CUDA_TRY(cudaGetLastError());
+  return "";
+}
+
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
                              int dim, void* out, cudaStream_t s, int exact) {
   if (dim != 256) return "layernorm: only hidden_dim 256 is built";

@@ -259,6 +259,17 @@ struct spe_ctx {
   void* SP = nullptr;          // padded NHWC-Cp stem input
   std::vector<Bottleneck> blocks;
   GemmW s8_lat, s16_lat, out_conv, input_proj;
+  // output_conv (3x3, 512 -> 512, + bias) is followed by input_proj (1x1, 512 -> 256, + bias) with nothing in between
+  // (RV/models/backbone.py:142, RV/models/detr_speed.py:81): one 3x3 convolution 512 -> 256 with W' = W_ip . W_oc and
+  // b' = W_ip . b_oc + b_ip computes the same thing with half the multiply-adds of output_conv and no input_proj at all
+  // (-2.06 of 26.57 GFLOP per image, one rounding of the 512-channel feature map less).  SPE_FOLD_NECK=0 keeps the two.
+  GemmW out_conv_ip;
+  // s16_latern applied BEFORE the bilinear x2 upsampling (launch_upsample_tapsum, elementwise.cu): its nine tap matrices
+  // as one [9 * 256, 1024] GEMM on the 14 x 14 map, a quarter of the convolution's multiply-adds (-2.77 GFLOP per image),
+  // no 1024-channel upsampled tensor (205 MB at B = 64)
+  GemmW s16_lr;
+  float* YLR = nullptr;        // [B, 14, 14, 9 * 256] fp32
+  bool fold_neck = getenv("SPE_FOLD_NECK") ? atoi(getenv("SPE_FOLD_NECK")) != 0 : true;
   std::vector<EncLayer> enc;
   std::vector<DecLayer> dec;
   GemmW ca_kv_all;             // [L*512, 256] plain storage-dtype weights
@@ -593,11 +604,54 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(upload_f32(ctx, zeros.data(), 256, &ctx->s8_lat.bias));
       TRY_S(upload_f32(ctx, zeros.data(), 256, &ctx->s16_lat.bias));
     }
+    if (ctx->fold_neck) {
+      const HostTensor* w16 = ws.get("backbone.0.s16_latern.weight", {256, 1024, 3, 3});
+      if (!w16) return ws.missing;
+      std::vector<float> wlr(static_cast<size_t>(9) * 256 * 1024);           // row = tap * 256 + o, column = input channel
+      for (int o = 0; o < 256; ++o)
+        for (int ci = 0; ci < 1024; ++ci)
+          for (int t = 0; t < 9; ++t)
+            wlr[(static_cast<size_t>(t) * 256 + o) * 1024 + ci] = w16->data[(static_cast<size_t>(o) * 1024 + ci) * 9 + t];
+      TRY_S(upload_gemm_w(ctx, wlr, 9 * 256, 1024, &ctx->s16_lr));
+      const std::vector<float> z9(9 * 256, 0.f);
+      TRY_S(upload_f32(ctx, z9.data(), 9 * 256, &ctx->s16_lr.bias));
+    }
     TRY_S(load_conv_bn(ctx, ws, "backbone.0.output_conv", "", 512, 512, 3, &ctx->out_conv));
     TRY_S(load_vec(ctx, ws, "backbone.0.output_conv.bias", 512, &ctx->out_conv.bias));
   }
   TRY_S(load_conv_bn(ctx, ws, "input_proj", "", E, ctx->featC, 1, &ctx->input_proj));
   TRY_S(load_vec(ctx, ws, "input_proj.bias", E, &ctx->input_proj.bias));
+  if (c.backbone == 0 && ctx->fold_neck) {
+    const HostTensor* woc = ws.get("backbone.0.output_conv.weight", {512, 512, 3, 3});
+    const HostTensor* boc = ws.get("backbone.0.output_conv.bias", {512});
+    const HostTensor* wip = ws.get("input_proj.weight", {E, 512, 1, 1});
+    const HostTensor* bip = ws.get("input_proj.bias", {E});
+    if (!woc || !boc || !wip || !bip) return ws.missing;
+    const int Kc = 9 * 512;
+    const std::vector<float> oc = repack_conv(*woc);                 // [512][(r*3+s)*512 + c]
+    std::vector<float> ocT(static_cast<size_t>(Kc) * 512);           // [Kc][512]: addend_kernel computes X . W^T
+    for (int m = 0; m < 512; ++m)
+      for (int j = 0; j < Kc; ++j) ocT[static_cast<size_t>(j) * 512 + m] = oc[static_cast<size_t>(m) * Kc + j];
+    float *wip_dev = nullptr, *prod_dev = nullptr;
+    SPE_CUDA_TRY(cudaMalloc(&wip_dev, sizeof(float) * E * 512));
+    SPE_CUDA_TRY(cudaMalloc(&prod_dev, sizeof(float) * E * Kc));
+    cudaMemcpy(wip_dev, wip->data, sizeof(float) * E * 512, cudaMemcpyHostToDevice);
+    const std::vector<float> zeros(Kc, 0.f);
+    std::string e2 = make_addend(ctx, wip_dev, E, 512, ocT.data(), zeros.data(), Kc, prod_dev, Kc, 0);   // fp32 FMA
+    std::vector<float> prod(static_cast<size_t>(E) * Kc);
+    if (e2.empty()) cudaMemcpy(prod.data(), prod_dev, sizeof(float) * E * Kc, cudaMemcpyDeviceToHost);
+    cudaFree(wip_dev);
+    cudaFree(prod_dev);
+    if (!e2.empty()) return e2;
+    TRY_S(upload_gemm_w(ctx, prod, E, Kc, &ctx->out_conv_ip));
+    std::vector<float> bias(E);
+    for (int o = 0; o < E; ++o) {
+      double acc = bip->data[o];
+      for (int m = 0; m < 512; ++m) acc += static_cast<double>(wip->data[static_cast<size_t>(o) * 512 + m]) * boc->data[m];
+      bias[o] = static_cast<float>(acc);
+    }
+    TRY_S(upload_f32(ctx, bias.data(), E, &ctx->out_conv_ip.bias));
+  }
 
   // ---- positional embedding and query embedding on the device (fp32) for the addends
   std::vector<float> pos = make_pos(ctx->featH, ctx->featH, E);
@@ -733,6 +787,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
   TRY_S(A(&ctx->L2OUT, B * h8 * h8 * 512));
   TRY_S(A(&ctx->L3OUT, B * h16 * h16 * 1024));
   if (c.backbone == 0) {
+    TRY_S(AB(reinterpret_cast<void**>(&ctx->YLR), B * h16 * h16 * 9 * 256 * 4));
     TRY_S(A(&ctx->UP, B * h8 * h8 * 1024));
     TRY_S(A(&ctx->CAT, B * h8 * h8 * 512));
     TRY_S(A(&ctx->FEAT, B * h8 * h8 * 512));
@@ -1006,21 +1061,35 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   // ---- neck
   const int FH = ctx->featH;
   const long long T = ctx->tokens;
-  const void* feat;
+  const void* feat = c.backbone == 0 ? ctx->FEAT : ctx->L3OUT;
   if (c.backbone == 0) {
     const int h16 = R / 16;
     TRY_S(f.gemm(ctx->L2OUT, Bl * T, ctx->s8_lat, ctx->CAT, 512, false));
-    TRY_S(launch_upsample2x(f.dt, ctx->L3OUT, B, h16, h16, 1024, ctx->UP, st));
     if (!(dbg_skip() & 128)) {
-    TRY_S(f.conv3x3(ctx->UP, FH, 1024, ctx->s16_lat, f.col(ctx->CAT, 256), 512, false));
-    TRY_S(f.conv3x3(ctx->CAT, FH, 512, ctx->out_conv, ctx->FEAT, 512, false));
+    if (ctx->s16_lr.w != nullptr && !ctx->taps_enabled) {
+      // the nine taps of s16_latern on the 14 x 14 map, then upsample + shift + add (see spe_ctx::s16_lr)
+      TRY_S(f.gemm(ctx->L3OUT, Bl * h16 * h16, ctx->s16_lr, ctx->YLR, 9 * 256, false, nullptr, 0, 0, 0, true, 1, true));
+      TRY_S(launch_upsample_tapsum(f.dt, ctx->YLR, B, h16, h16, 256, f.col(ctx->CAT, 256), 512, st));
+    } else {
+      TRY_S(launch_upsample2x(f.dt, ctx->L3OUT, B, h16, h16, 1024, ctx->UP, st));
+      TRY_S(f.conv3x3(ctx->UP, FH, 1024, ctx->s16_lat, f.col(ctx->CAT, 256), 512, false));
     }
-    TRY_S(f.tap("neck", ctx->FEAT, Bl * T * 512));
-    feat = ctx->FEAT;
+    if (ctx->out_conv_ip.w != nullptr && !ctx->taps_enabled) {
+      // output_conv and input_proj as one 3x3 convolution (see spe_ctx::out_conv_ip); the 512-channel neck output only
+      // exists when the activation taps ask for it
+      TRY_S(f.conv(ctx->CAT, FH, 512, 3, 1, ctx->out_conv_ip, Xc, 256, false, exact_stream_on(ctx)));
+      feat = nullptr;
+    } else {
+      TRY_S(f.conv3x3(ctx->CAT, FH, 512, ctx->out_conv, ctx->FEAT, 512, false));
+      TRY_S(f.tap("neck", ctx->FEAT, Bl * T * 512));
+      feat = ctx->FEAT;
+    }
+    }
   } else {
     feat = ctx->L3OUT;
   }
-  TRY_S(f.gemm(feat, Bl * T, ctx->input_proj, Xc, 256, false, nullptr, 0, 0, 0, true, 0, exact_stream_on(ctx)));
+  if (feat != nullptr)
+    TRY_S(f.gemm(feat, Bl * T, ctx->input_proj, Xc, 256, false, nullptr, 0, 0, 0, true, 0, exact_stream_on(ctx)));
   TRY_S(f.tap("input_proj", Xc, Bl * T * 256));
 
   // ---- encoder

@@ -53,6 +53,10 @@ std::string launch_im2col_nhwc(Dtype dt, const void* in, int NB, int H, int W, i
                                int pad, void* out, cudaStream_t s);
 std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s);
 std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, int C, void* out, cudaStream_t s);
+// out[b, p, 0:Cout] (row stride out_ld, storage dtype) = sum over the 3x3 taps inside the 2H x 2W map of the bilinear
+// (align_corners=True) x2 upsampling of Y[b, :, :, tap * Cout + o]; Y fp32 [NB, H, W, 9 * Cout]
+std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int W, int Cout, void* out, int out_ld,
+                                   cudaStream_t s);
 // exact = 0: fp32 storage is TF32-rounded; 1: full fp32 result; 2: 3xTF32 operand layout [hi | lo | hi], row stride 768
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
                              int dim, void* out, cudaStream_t s, int exact = 0);

@@ -125,6 +125,34 @@ def test_attention(lib, cuda_dev, dt, B, Lq, Lk):
     assert _rel(out, ref) < (2e-3 if dt == 0 else 8e-3)
 
 
+@pytest.mark.parametrize("late_boost", [0.0, 40.0, 4000.0])
+def test_attention_fixed_reference_softmax_and_its_fallback(lib, cuda_dev, late_boost):
+    """The tcgen05 attention kernel takes its softmax reference from the first chunk of 112 keys and keeps it for the
+    row; scores far above it later in the row (here: keys 500.. boosted so that q.k grows by `late_boost`) make
+    probabilities > 1 -- still exact -- and, beyond ~350 logits, overflow a row sum, which the kernel detects and
+    answers by repeating the tile with the classical online softmax.  All three regimes must give the same softmax."""
+    torch.manual_seed(7)
+    B, L = 2, 784
+    q = torch.randn(B, L, 256, device=cuda_dev)
+    k = torch.randn(B, L, 256, device=cuda_dev)
+    v = torch.randn(B, L, 256, device=cuda_dev)
+    if late_boost:
+        # add a multiple of q's own direction to the late keys of head 0 and head 5 for the first 200 queries' mean
+        # direction: every query's score on those keys rises by roughly late_boost * |component|
+        d = torch.nn.functional.normalize(q[:, :, :32].mean(1, keepdim=True), dim=-1)
+        k[:, 500:, :32] += late_boost * d * 32 ** 0.5 / q[:, :, :32].norm(dim=-1).mean()
+    q, k, v = _rna_tf32(q), _rna_tf32(k), _rna_tf32(v)
+    out = torch.full((B, L, 256), float("nan"), device=cuda_dev)
+    assert lib.spe_debug_attention(0, _p(q), _p(k), _p(v), _p(out), B, 8, L, L, 256, 256, 256, 256, None) == 0
+    torch.cuda.synchronize()
+    qh = q.double().view(B, L, 8, 32).transpose(1, 2)
+    kh = k.double().view(B, L, 8, 32).transpose(1, 2)
+    vh = v.double().view(B, L, 8, 32).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 32 ** 0.5, -1) @ vh).transpose(1, 2).reshape(B, L, 256)
+    assert not torch.isnan(out).any() and not torch.isinf(out).any()
+    assert _rel(out, ref) < 2e-3
+
+
 @pytest.mark.parametrize("M,N,K,relu,res_mod", [(40, 256, 256, 0, 0), (2560, 768, 256, 0, 40), (2560, 2048, 256, 1, 0),
                                                 (300, 256, 2048, 0, 0), (784 * 8, 2048, 256, 0, 784)])
 def test_gemm_3xtf32_reaches_fp32_accuracy(lib, cuda_dev, M, N, K, relu, res_mod):
