@@ -15,6 +15,7 @@ PK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAK
 TF32 = PK["bf16_tflops_sustained"] / 2 * 1e12
 TF32_BURST = PK.get("bf16_tflops", PK["bf16_tflops_sustained"]) / 2 * 1e12   # the peak at the clock a short run holds
 HBM = PK["hbm_gbs"] * 1e9
+FOLD = os.environ.get("FOLD", "1") == "1"       # round 2: algebraically folded neck (SPE_FOLD_NECK, default on)
 KV_X3 = os.environ.get("KV_X3", "0") == "1"     # round 2: the K/V projection is plain TF32 once calibrated
 
 
@@ -37,9 +38,15 @@ def schedule():
             inpl, H = 4 * pl, Ho
     T = 784
     add("s8_latern", B * T, 256, 512)
-    add("s16_latern 3x3", B * T, 256, 9 * 1024)
-    add("output_conv 3x3", B * T, 512, 9 * 512)
-    add("input_proj", B * T, 256, 512)
+    if FOLD:
+        # round 2: s16_latern's nine tap matrices on the 14 x 14 map (then upsample_tapsum_kernel); output_conv and
+        # input_proj as ONE 3x3 convolution 512 -> 256
+        add("s16_latern taps @14x14", B * 196, 9 * 256, 1024)
+        add("output_conv.input_proj 3x3", B * T, 256, 9 * 512)
+    else:
+        add("s16_latern 3x3", B * T, 256, 9 * 1024)
+        add("output_conv 3x3", B * T, 512, 9 * 512)
+        add("input_proj", B * T, 256, 512)
     for i in range(4):
         add(f"enc{i}.qkv", B * T, 768, 256)
         add(f"enc{i}.out+res", B * T, 256, 256, res=B * T * 256)

@@ -45,6 +45,7 @@ struct AttnTcParams {
   int exact_out;
   int debug;
   int out_bf16;     // bf16-storage models: Q / K / V arrive as fp32 (TF32 values), the output is written as bf16
+  int q_rows_per_batch;   // Lq, or 0 when every image shares one [Lq, ldq] query block (AttnDesc::bsq == 0)
   int safe_softmax; // 1: classical online softmax from the start (SPE_ATTN_SAFE=1; the fast path falls back to it by itself)
 };
 
@@ -136,7 +137,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     {
       if (attempt == 0 && elect_one_sync()) {
         mbar_expect_tx(q_full, SM::Q_BYTES);
-        tma_load_2d(sQ, &tmQ, q_full, h * 32, b * p.Lq + q0);
+        tma_load_2d(sQ, &tmQ, q_full, h * 32, b * p.q_rows_per_batch + q0);
       }
       __syncwarp();
       for (int j = 0; j < nchunks; ++j) {
@@ -414,7 +415,8 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
   CUtensorMap tmQ, tmK, tmV;
   const int hd = d.heads * 32;
   std::string e;
-  e = encode_tmap_2d(&tmQ, kTF32, d.q, hd, static_cast<long long>(d.B) * d.Lq, static_cast<long long>(d.ldq) * 4, 32, kQRows);
+  e = encode_tmap_2d(&tmQ, kTF32, d.q, hd, (d.bsq == 0 ? 1ll : static_cast<long long>(d.B)) * d.Lq, static_cast<long long>(d.ldq) * 4, 32,
+                     kQRows);
   if (!e.empty()) return e;
   e = encode_tmap_2d(&tmK, kTF32, d.k, hd, static_cast<long long>(d.B) * d.Lk, static_cast<long long>(d.ldk) * 4, 32, NK);
   if (!e.empty()) return e;
@@ -426,6 +428,7 @@ std::string launch_tc(const AttnDesc& d, cudaStream_t s) {
   p.ldo = d.ldo;
   p.Lq = d.Lq;
   p.Lk = d.Lk;
+  p.q_rows_per_batch = d.bsq == 0 ? 0 : d.Lq;
   p.scale_log2e = d.scale * 1.4426950408889634f;
   p.exact_out = d.exact_out;
   p.out_bf16 = d.mixed;
@@ -448,7 +451,7 @@ bool attention_tc_supported(Dtype dt, const AttnDesc& d) {
   // small problems (decoder self-attention, 40 x 40) stay on the register kernel; decoder cross-attention (40 queries
   // x 784 keys) is worth a 128-row tile even at 31 % row occupancy (28 us vs 45 us per layer at B = 64)
   if (d.Lq < 32 || d.Lk < 128) return false;
-  if (d.bsq != static_cast<long long>(d.Lq) * d.ldq || d.bsk != static_cast<long long>(d.Lk) * d.ldk ||
+  if ((d.bsq != 0 && d.bsq != static_cast<long long>(d.Lq) * d.ldq) || d.bsk != static_cast<long long>(d.Lk) * d.ldk ||
       d.bsv != static_cast<long long>(d.Lk) * d.ldv || d.bso != static_cast<long long>(d.Lq) * d.ldo)
     return false;
   if (d.ldq % 4 || d.ldk % 4 || d.ldv % 4 || d.ldo % 4) return false;

@@ -244,7 +244,8 @@ upsample2x_kernel(const T* __restrict__ in, int H, int W, int C, T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    long long rows, T* __restrict__ out, int exact) {
+                    long long rows, T* __restrict__ out, int exact, const float* __restrict__ gamma2,
+                    const float* __restrict__ beta2, T* __restrict__ out2) {
   pdl_wait();
   pdl_launch();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -296,8 +297,32 @@ layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, c
     for (int e = 0; e < VN; ++e) {
       const float y = (x[i * VN + e] - mean) * rstd * gamma[c + e] + beta[c + e];
       if (exact) r.set_exact(e, y); else r.set(e, y);
+      x[i * VN + e] = r.get(e);          // what a second kernel would read back
     }
     vstore(out + row * 256 + c, r);
+  }
+  if (gamma2 == nullptr) return;
+  // chained second normalisation of the row just written (decoder: norm3 followed by the shared decoder norm,
+  // RV/models/transformer.py:116-118), stored unrounded -- one launch instead of two, same values
+  float s2 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s2 += x[e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const float mean2 = s2 * (1.f / 256.f);
+  float q2 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { const float d = x[e] - mean2; q2 += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+  const float rstd2 = rsqrtf(q2 * (1.f / 256.f) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * VN;
+    Vec<T> r;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) r.set_exact(e, (x[i * VN + e] - mean2) * rstd2 * gamma2[c + e] + beta2[c + e]);
+    vstore(out2 + row * 256 + c, r);
   }
 }
 
@@ -379,57 +404,112 @@ std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, in
 // so the nine 1024 -> 256 tap matrices are applied to the 14 x 14 map (one GEMM, M = 196 per image instead of 784:
 // a quarter of the multiply-adds) and this kernel gathers:  out[p, o] = sum over the taps that fall inside the 28 x 28
 // map (zero padding) of the bilinear interpolation of Y_tap at p + tap.
-// One CTA = one image x kTapCh output channels; its slice of Y ([196 positions][9 taps][kTapCh], 110 KB) is staged in
-// shared memory once and every output reads its 9 x 4 terms from there.
+// One CTA = one image x kTapCh output channels; its slice of Y ([196 positions][9 taps][kTapCh], 112 KB with padding) is
+// staged in shared memory once.  One THREAD = one output position x all kTapCh channels: the interpolation indices and
+// weights of the three tap rows / three tap columns are computed once per position (the first version did it per
+// channel and per tap: 269 us at B = 64, bound by its own index arithmetic -- profiles/r02b_launches_summary.md), the
+// shared-memory reads are 16-byte (four channels), and a position's row is padded to kTapStride words so that the
+// quarter-warps of an LDS.128 (eight different source positions at most) fall on different banks.
 constexpr int kTapCh = 16;
+constexpr int kTapStride = 9 * kTapCh + 2;            // 146 words: 2 CTAs of 196 positions still fit one SM (2 x 112 KB)
 template <typename TO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 upsample_tapsum_kernel(const float* __restrict__ Y, int H, int W, int Cout, TO* __restrict__ out, int out_ld, int round_tf32) {
   pdl_wait();
   pdl_launch();
-  extern __shared__ float sy[];                       // [H*W][9][kTapCh]
+  extern __shared__ float sy[];                       // [H*W][kTapStride]
   const int b = blockIdx.x, c0 = blockIdx.y * kTapCh;
   const int HW = H * W, Ho = 2 * H, Wo = 2 * W;
   const float* yb = Y + static_cast<long long>(b) * HW * 9 * Cout;
-  for (int u = threadIdx.x; u < HW * 9 * (kTapCh / 4); u += blockDim.x) {
-    const int seg = u / (kTapCh / 4), v4 = u % (kTapCh / 4);     // seg = position * 9 + tap
-    const float4 v = *reinterpret_cast<const float4*>(yb + static_cast<long long>(seg) * Cout + c0 + v4 * 4);
-    *reinterpret_cast<float4*>(sy + seg * kTapCh + v4 * 4) = v;
+  // eight independent 16-byte loads in flight per thread (the loop-carried form waited out one DRAM latency per element)
+  const int nvec = HW * 9 * (kTapCh / 4);
+  for (int u0 = threadIdx.x; u0 < nvec; u0 += 8 * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int u = u0 + k * blockDim.x;
+      if (u < nvec)
+        v[k] = __ldg(reinterpret_cast<const float4*>(yb + static_cast<long long>(u / (kTapCh / 4)) * Cout + c0 + (u % (kTapCh / 4)) * 4));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int u = u0 + k * blockDim.x;
+      if (u < nvec) {
+        const int seg = u / (kTapCh / 4), v4 = u % (kTapCh / 4);     // seg = position * 9 + tap
+        float* d = sy + (seg / 9) * kTapStride + (seg % 9) * kTapCh + v4 * 4;
+        *reinterpret_cast<float2*>(d) = make_float2(v[k].x, v[k].y);       // rows are 8-byte aligned only (146 words)
+        *reinterpret_cast<float2*>(d + 2) = make_float2(v[k].z, v[k].w);
+      }
+    }
   }
   __syncthreads();
   const float sh = static_cast<float>(H - 1) / static_cast<float>(Ho - 1);
   const float sw = static_cast<float>(W - 1) / static_cast<float>(Wo - 1);
-  const int c = threadIdx.x % kTapCh;
-  for (int p = threadIdx.x / kTapCh; p < Ho * Wo; p += blockDim.x / kTapCh) {
+  for (int p = threadIdx.x; p < Ho * Wo; p += blockDim.x) {
     const int i = p / Wo, j = p % Wo;
-    float acc = 0.f;
+    // the three tap rows / columns of this output: source index pair and the interpolation weight (0 = outside the
+    // 2H x 2W map, the convolution's zero padding)
+    int ro[3][2], co[3][2];
+    float rw[3][2], cw[3][2];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int ii = i + r - 1;
-      if (ii < 0 || ii >= Ho) continue;               // zero padding of the 3x3 convolution
-      const float fy = sh * ii;
-      const int y0 = static_cast<int>(fy);
-      const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
-      const float ly1 = fy - y0, ly0 = 1.f - ly1;
+      const int ii = i + r - 1, jj = j + r - 1;
+      const bool vi = ii >= 0 && ii < Ho, vj = jj >= 0 && jj < Wo;
+      const float fy = sh * (vi ? ii : 0), fx = sw * (vj ? jj : 0);
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      ro[r][0] = y0 * W; ro[r][1] = (y0 + (y0 < H - 1 ? 1 : 0)) * W;
+      co[r][0] = x0; co[r][1] = x0 + (x0 < W - 1 ? 1 : 0);
+      rw[r][1] = vi ? fy - y0 : 0.f; rw[r][0] = vi ? 1.f - (fy - y0) : 0.f;
+      cw[r][1] = vj ? fx - x0 : 0.f; cw[r][0] = vj ? 1.f - (fx - x0) : 0.f;
+    }
+    float acc[kTapCh];
+#pragma unroll
+    for (int c = 0; c < kTapCh; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const int jj = j + q - 1;
-        if (jj < 0 || jj >= Wo) continue;
-        const float fx = sw * jj;
-        const int x0 = static_cast<int>(fx);
-        const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
-        const float lx1 = fx - x0, lx0 = 1.f - lx1;
         const int t = r * 3 + q;
-        const float a = sy[((y0 * W + x0) * 9 + t) * kTapCh + c], bq = sy[((y0 * W + x1) * 9 + t) * kTapCh + c];
-        const float cq = sy[((y1 * W + x0) * 9 + t) * kTapCh + c], d = sy[((y1 * W + x1) * 9 + t) * kTapCh + c];
-        acc += ly0 * (lx0 * a + lx1 * bq) + ly1 * (lx0 * cq + lx1 * d);   // nn.UpsamplingBilinear2d's expression
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float w = rw[r][a] * cw[q][e];
+            const float* src = sy + (ro[r][a] + co[q][e]) * kTapStride + t * kTapCh;
+#pragma unroll
+            for (int c = 0; c < kTapCh; c += 2) {
+              const float2 v = *reinterpret_cast<const float2*>(src + c);
+              acc[c] = fmaf(w, v.x, acc[c]);
+              acc[c + 1] = fmaf(w, v.y, acc[c + 1]);
+            }
+          }
+        }
       }
     }
+    const long long o = (static_cast<long long>(b) * Ho * Wo + p) * out_ld + c0;
     if (sizeof(TO) == 4) {
-      if (round_tf32) acc = __uint_as_float((__float_as_uint(acc) + 0x1000u) & 0xffffe000u);
-      reinterpret_cast<float*>(out)[(static_cast<long long>(b) * Ho * Wo + p) * out_ld + c0 + c] = acc;
+      float* op = reinterpret_cast<float*>(out) + o;
+#pragma unroll
+      for (int c = 0; c < kTapCh; c += 4) {
+        float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        if (round_tf32) {
+          v.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u);
+          v.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u);
+          v.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u);
+          v.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u);
+        }
+        *reinterpret_cast<float4*>(op + c) = v;
+      }
     } else {
-      reinterpret_cast<__nv_bfloat16*>(out)[(static_cast<long long>(b) * Ho * Wo + p) * out_ld + c0 + c] = __float2bfloat16_rn(acc);
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + o;
+#pragma unroll
+      for (int c = 0; c < kTapCh; c += 8) {
+        uint4 o8;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(acc[c + 2 * u], acc[c + 2 * u + 1]);
+        *reinterpret_cast<uint4*>(op + c) = o8;
+      }
     }
   }
 }
@@ -438,7 +518,7 @@ std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int 
                                    cudaStream_t s) {
   if (NB <= 0) return "";
   if (Cout % kTapCh) return "upsample_tapsum: output channels must be a multiple of 16";
-  const size_t smem = static_cast<size_t>(H) * W * 9 * kTapCh * sizeof(float);
+  const size_t smem = static_cast<size_t>(H) * W * kTapStride * sizeof(float);
   if (smem > 200 * 1024) return "upsample_tapsum: feature map too large for the shared-memory slice";
   ProfScope ps(kFamElementwise, s);
   if (dt == kTF32) {
@@ -464,13 +544,15 @@ std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int 
 }
 
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
-                             int dim, void* out, cudaStream_t s, int exact) {
+                             int dim, void* out, cudaStream_t s, int exact, const float* gamma2, const float* beta2,
+                             void* out2) {
   if (dim != 256) return "layernorm: only hidden_dim 256 is built";
   if (rows <= 0) return "";
   ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     SPE_CUDA_TRY(launch_pdl(layernorm256_kernel<T>, dim3(blocks_for(rows, 8)), dim3(256), 0, s,
-                            reinterpret_cast<const T*>(in), gamma, beta, rows, reinterpret_cast<T*>(out), exact));
+                            reinterpret_cast<const T*>(in), gamma, beta, rows, reinterpret_cast<T*>(out), exact, gamma2,
+                            beta2, reinterpret_cast<T*>(out2)));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

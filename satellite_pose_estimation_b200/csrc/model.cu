@@ -269,6 +269,20 @@ struct spe_ctx {
   // no 1024-channel upsampled tensor (205 MB at B = 64)
   GemmW s16_lr;
   float* YLR = nullptr;        // [B, 14, 14, 9 * 256] fp32
+  // stem + max-pool + layer1 run in chunks of `head_chunk` images (0 = whole batch at once): at 112 x 112 x 64 and
+  // 56 x 56 x 256 fp32 these layers are HBM-bound (205 MB per tensor at B = 64, against 126 MB of L2); a chunk of 16
+  // images keeps producer -> consumer hand-overs inside L2, and because every chunk reuses the SAME scratch addresses
+  // the dirty lines of the stem output are overwritten in L2 instead of ever being written back.  SPE_HEAD_CHUNK.
+  // The first decoder layer starts from tgt = 0 (RV/models/transformer.py:59, :111): its self-attention block sees
+  // only the learned query embeddings, so norm1's output and the cross-attention query projection of layer 0 are the
+  // same [Q, 256] matrices for every image.  They are computed once (after a weight load and after every calibration,
+  // with the very kernels the per-batch path would run on one image) and broadcast: five launches per batch less.
+  void* dec0_tgt = nullptr;    // [Q, 256] storage dtype: tgt after norm1 of decoder layer 0
+  void* dec0_q = nullptr;      // [Q, 256] storage dtype: cross-attention query projection of decoder layer 0
+  bool dec0_valid = false;
+  bool dec0_fold = getenv("SPE_DEC0_FOLD") ? atoi(getenv("SPE_DEC0_FOLD")) != 0 : true;
+  void* L1OUT = nullptr;       // [B, 56, 56, 256] layer1 output of all chunks
+  int head_chunk = getenv("SPE_HEAD_CHUNK") ? atoi(getenv("SPE_HEAD_CHUNK")) : 0;
   bool fold_neck = getenv("SPE_FOLD_NECK") ? atoi(getenv("SPE_FOLD_NECK")) != 0 : true;
   std::vector<EncLayer> enc;
   std::vector<DecLayer> dec;
@@ -780,6 +794,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
   TRY_S(A(&ctx->S1, B * h2 * h2 * 64));
   TRY_S(A(&ctx->P0, B * h4 * h4 * 256));
   TRY_S(A(&ctx->P1, B * h4 * h4 * 256));
+  TRY_S(A(&ctx->L1OUT, ctx->head_chunk > 0 ? B * h4 * h4 * 256 : 4));
   TRY_S(A(&ctx->T1, B * h4 * h4 * 128));
   TRY_S(A(&ctx->T2, B * h4 * h4 * 128));
   TRY_S(A(&ctx->DS, B * h4 * h4 * 256));
@@ -818,6 +833,8 @@ std::string alloc_workspace(spe_ctx* ctx) {
     ctx->ws_current = 0;
   }
   TRY_S(dmalloc(ctx, &ctx->colsum, 8192 + 2 * 256 * 4096));   // sums + per-block partials
+  TRY_S(dmalloc_bytes(ctx, &ctx->dec0_tgt, Q * 256 * es));
+  TRY_S(dmalloc_bytes(ctx, &ctx->dec0_q, Q * 256 * es));
   // pipeline buffers
   TRY_S(dmalloc(ctx, &ctx->boxes_dev, B * 4));
   TRY_S(dmalloc(ctx, &ctx->images_dev, B * 3 * R * R));
@@ -931,14 +948,15 @@ struct Fwd {
     return conv(x, H, C, 3, 1, w, out, out_ld, relu);
   }
   std::string attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int Lq,
-                   int Lk, int exact_out = 0, int mixed = 0, int x3 = 0) {
+                   int Lk, int exact_out = 0, int mixed = 0, int x3 = 0, bool q_broadcast = false) {
     AttnDesc a;
     a.exact_out = exact_out;
     a.x3 = x3;
     a.mixed = mixed;
     a.q = q; a.k = k; a.v = v; a.out = out;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = 256;
-    a.bsq = static_cast<long long>(Lq) * ldq; a.bsk = static_cast<long long>(Lk) * ldk;
+    a.bsq = q_broadcast ? 0 : static_cast<long long>(Lq) * ldq;   // 0: one [Lq, ldq] query block shared by every image
+    a.bsk = static_cast<long long>(Lk) * ldk;
     a.bsv = static_cast<long long>(Lk) * ldv; a.bso = static_cast<long long>(Lq) * 256;
     a.B = B; a.heads = 8; a.Lq = Lq; a.Lk = Lk;
     a.scale = 1.0f / sqrtf(32.0f);
@@ -969,10 +987,32 @@ static bool exact_stream_on(const spe_ctx* ctx) {
   return ctx->exact_stream && ctx->dt == kTF32 && (ctx->calibrated || ctx->calibrating);
 }
 
-// backbone + neck + input_proj + encoder for `B` images starting at `images`; the encoder output (memory) of those
-// images is left in Xc ([B * tokens, 256]).  Every other buffer is the shared scratch region, so consecutive chunks
-// reuse the same cache lines (the whole working set of a chunk is sized to stay L2-resident).
-static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void* Xc, cudaStream_t st) {
+// One residual block of layer1..layer3 on `B` images: conv1 (1x1) -> conv2 (3x3, stride on it) -> conv3 (1x1) + identity / downsample
+static std::string run_bottleneck(spe_ctx* ctx, Fwd& f, const Bottleneck& bk, const void* cur, int H, void* nxt) {
+  const long long Bl = f.B;
+  const int Ho = H / bk.stride;
+  const long long Min = Bl * H * H, Mout = Bl * Ho * Ho;
+  TRY_S(f.gemm(cur, Min, bk.c1, ctx->T1, bk.planes, true));
+  if (bk.stride == 1) {
+    TRY_S(f.conv3x3(ctx->T1, H, bk.planes, bk.c2, ctx->T2, bk.planes, true));
+  } else {
+    TRY_S(f.conv(ctx->T1, H, bk.planes, 3, 2, bk.c2, ctx->T2, bk.planes, true));   // 3x3 / stride 2
+  }
+  const void* identity = cur;
+  if (bk.has_down) {
+    if (bk.stride == 1) {
+      TRY_S(f.gemm(cur, Min, bk.down, ctx->DS, bk.planes * 4, false, nullptr, 0, 0, 0, true, 0, true));
+    } else {
+      TRY_S(f.conv(cur, H, bk.inplanes, 1, 2, bk.down, ctx->DS, bk.planes * 4, false, true));  // 1x1 / stride 2
+    }
+    identity = ctx->DS;
+  }
+  return f.gemm(ctx->T2, Mout, bk.c3, nxt, bk.planes * 4, true, identity, bk.planes * 4, 0, 0, true, 0, exact_stream_on(ctx));
+}
+
+// stem + max-pool + layer1 for `B` images starting at `images`; the layer1 output goes to `l1dst` when given, else to
+// the ping-pong buffer the block sequence ends on.  *out = where it is.
+static std::string trunk_head(spe_ctx* ctx, const float* images, int B, void* l1dst, const void** out, cudaStream_t st) {
   const spe_config& c = ctx->cfg;
   Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
   const int R = c.input_size;
@@ -1020,37 +1060,59 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
   TRY_S(f.tap("stem", ctx->S1, Bl * h2 * h2 * 64));
   TRY_S(launch_maxpool3x3s2(f.dt, ctx->S1, B, h2, h2, 64, ctx->P0, st));
 
-  // ---- layer1..layer3
-  void* cur = ctx->P0;
+  // ---- layer1
+  const void* cur = ctx->P0;
+  if (!(dbg_skip() & 16)) {
+    for (int bi = 0; bi < 3; ++bi) {
+      void* nxt = (bi == 2 && l1dst != nullptr) ? l1dst : ((cur == ctx->P0) ? ctx->P1 : ctx->P0);
+      TRY_S(run_bottleneck(ctx, f, ctx->blocks[bi], cur, h4, nxt));
+      cur = nxt;
+    }
+  }
+  TRY_S(f.tap("layer1", cur, Bl * h4 * h4 * 256));
+  *out = cur;
+  return "";
+}
+
+// backbone + neck + input_proj + encoder for `B` images starting at `images`; the encoder output (memory) of those
+// images is left in Xc ([B * tokens, 256]).  Every other buffer is the shared scratch region, so consecutive chunks
+// reuse the same cache lines (the whole working set of a chunk is sized to stay L2-resident).
+static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void* Xc, cudaStream_t st) {
+  const spe_config& c = ctx->cfg;
+  Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
+  const int R = c.input_size;
+  const int h4 = R / 4;
+  const long long Bl = B;
+
+  // ---- stem, max-pool, layer1: whole batch, or chunk by chunk (see spe_ctx::head_chunk)
+  const void* cur = nullptr;
+  const int hc = ctx->head_chunk;
+  if (hc > 0 && hc < B && !ctx->taps_enabled && !ctx->calibrating) {
+    const long long img_elems = 3ll * R * R, l1_elems = static_cast<long long>(h4) * h4 * 256;
+    for (int c0 = 0; c0 < B; c0 += hc) {
+      const int nb = (B - c0) < hc ? (B - c0) : hc;
+      const void* dummy = nullptr;
+      TRY_S(trunk_head(ctx, images + c0 * img_elems, nb, f.col(ctx->L1OUT, c0 * l1_elems), &dummy, st));
+    }
+    cur = ctx->L1OUT;
+  } else {
+    TRY_S(trunk_head(ctx, images, B, nullptr, &cur, st));
+  }
+
+  // ---- layer2, layer3
   int H = h4;
-  int bidx = 0;
+  int bidx = 3;
   const int nblk[3] = {3, 4, 6};
-  for (int li = 0; li < 3; ++li) {
+  for (int li = 1; li < 3; ++li) {
     for (int bi = 0; bi < nblk[li]; ++bi, ++bidx) {
       const Bottleneck& bk = ctx->blocks[bidx];
       const int Ho = H / bk.stride;
       if (dbg_skip() & (16 << li)) { H = Ho; continue; }
-      const long long Min = Bl * H * H, Mout = Bl * Ho * Ho;
       void* nxt;
       if (bi == nblk[li] - 1 && li == 1) nxt = ctx->L2OUT;
       else if (bi == nblk[li] - 1 && li == 2) nxt = ctx->L3OUT;
       else nxt = (cur == ctx->P0) ? ctx->P1 : ctx->P0;
-      TRY_S(f.gemm(cur, Min, bk.c1, ctx->T1, bk.planes, true));
-      if (bk.stride == 1) {
-        TRY_S(f.conv3x3(ctx->T1, H, bk.planes, bk.c2, ctx->T2, bk.planes, true));
-      } else {
-        TRY_S(f.conv(ctx->T1, H, bk.planes, 3, 2, bk.c2, ctx->T2, bk.planes, true));   // 3x3 / stride 2
-      }
-      const void* identity = cur;
-      if (bk.has_down) {
-        if (bk.stride == 1) {
-          TRY_S(f.gemm(cur, Min, bk.down, ctx->DS, bk.planes * 4, false, nullptr, 0, 0, 0, true, 0, true));
-        } else {
-          TRY_S(f.conv(cur, H, bk.inplanes, 1, 2, bk.down, ctx->DS, bk.planes * 4, false, true));  // 1x1 / stride 2
-        }
-        identity = ctx->DS;
-      }
-      TRY_S(f.gemm(ctx->T2, Mout, bk.c3, nxt, bk.planes * 4, true, identity, bk.planes * 4, 0, 0, true, 0, exact_stream_on(ctx)));
+      TRY_S(run_bottleneck(ctx, f, bk, cur, H, nxt));
       cur = nxt;
       H = Ho;
     }
@@ -1165,7 +1227,7 @@ static std::string forward_kv(spe_ctx* ctx, int B, void* kv, cudaStream_t st) {
 
 // decoder and heads for the whole batch
 static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, float* points, float* logsig,
-                                float* aux_logits, float* aux_points, cudaStream_t st) {
+                                float* aux_logits, float* aux_points, cudaStream_t st, bool dec0_only = false) {
   const spe_config& c = ctx->cfg;
   Fwd f{ctx, st, B, ctx->dt, static_cast<long long>(dtype_size(ctx->dt))};
   const long long Bl = B;
@@ -1176,7 +1238,9 @@ static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, fl
   const int Q = c.num_queries, LD = c.dec_layers;
   const long long MQ = Bl * Q;
   const int kvld = LD * 512;
-  SPE_CUDA_TRY(cudaMemsetAsync(ctx->TGT, 0, static_cast<size_t>(MQ * 256 * f.es), st));
+  // layer 0's self-attention block and query projection are constants of the model (see spe_ctx::dec0_tgt)
+  const bool fold0 = ctx->dec0_fold && ctx->dec0_valid && !ctx->taps_enabled && !ctx->calibrating && !dec0_only;
+  if (!fold0) SPE_CUDA_TRY(cudaMemsetAsync(ctx->TGT, 0, static_cast<size_t>(MQ * 256 * f.es), st));
   // fp32 storage: with 3xTF32 GEMMs the decoder state stays unrounded fp32 end to end; with plain TF32 GEMMs
   // (SPE_DEC_X3=0) whatever feeds a GEMM is rounded by its producer.  The attention products are error-compensated in
   // both cases for the SELF-attention (the learned query embeddings can drive its logits into the hundreds).
@@ -1184,20 +1248,27 @@ static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, fl
   const int ax3 = f.dt == kTF32 ? 1 : 0;
   for (int i = 0; i < LD; ++i) {
     const DecLayer& L = ctx->dec[i];
-    TRY_S(f.gemm(ctx->TGT, MQ, L.sa_qkv, ctx->DQKV, 768, false, L.sa_addend, 768, Q, 1));
-    TRY_S(f.attn(ctx->DQKV, 768, f.col(ctx->DQKV, 256), 768, f.col(ctx->DQKV, 512), 768, ctx->DATT, Q, Q, ex, 0, ax3));
-    TRY_S(f.gemm(ctx->DATT, MQ, L.sa_out, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
-    TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT, ex));
-    TRY_S(f.gemm(ctx->TGT, MQ, L.ca_q, ctx->DQ, 256, false, L.ca_q_addend, 256, Q, 1));
+    const bool folded = i == 0 && fold0;
+    if (!folded) {
+      TRY_S(f.gemm(ctx->TGT, MQ, L.sa_qkv, ctx->DQKV, 768, false, L.sa_addend, 768, Q, 1));
+      TRY_S(f.attn(ctx->DQKV, 768, f.col(ctx->DQKV, 256), 768, f.col(ctx->DQKV, 512), 768, ctx->DATT, Q, Q, ex, 0, ax3));
+      TRY_S(f.gemm(ctx->DATT, MQ, L.sa_out, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
+      TRY_S(f.ln(ctx->TGT2, L.n1g, L.n1b, MQ, ctx->TGT, ex));
+      TRY_S(f.gemm(ctx->TGT, MQ, L.ca_q, ctx->DQ, 256, false, L.ca_q_addend, 256, Q, 1));
+      if (dec0_only) return "";
+    }
     // cross-attention stays on the tcgen05 kernel (plain TF32 operands): its logits are bounded by the LayerNorm-ed
     // memory (tens at most), where TF32 is accurate to ~1e-2 of a logit -- measured harmless; 28 vs ~80 us per layer
-    TRY_S(f.attn(ctx->DQ, 256, f.col(kv, i * 512), kvld, f.col(kv, i * 512 + 256), kvld, ctx->DATT, Q, Ti, ex));
-    TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));
+    TRY_S(f.attn(folded ? ctx->dec0_q : ctx->DQ, 256, f.col(kv, i * 512), kvld, f.col(kv, i * 512 + 256), kvld, ctx->DATT, Q,
+                 Ti, ex, 0, 0, folded));
+    TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, folded ? ctx->dec0_tgt : ctx->TGT, 256, folded ? Q : 0, 0,
+                 true, 0, true));
     TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT, ex));
     TRY_S(f.gemm(ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
     TRY_S(f.gemm(ctx->DHID, MQ, L.ff2, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));
-    TRY_S(f.ln(ctx->TGT2, L.n3g, L.n3b, MQ, ctx->TGT, ex));
-    TRY_S(f.ln(ctx->TGT, ctx->dn_g, ctx->dn_b, MQ, f.col(ctx->HS, static_cast<long long>(i) * MQ * 256), 1));
+    // norm3, and the decoder's shared output norm of it (return_intermediate), in one launch
+    TRY_S(launch_layernorm(f.dt, ctx->TGT2, L.n3g, L.n3b, MQ, 256, ctx->TGT, st, ex, ctx->dn_g, ctx->dn_b,
+                           f.col(ctx->HS, static_cast<long long>(i) * MQ * 256)));
   }
   TRY_S(f.tap("hs", ctx->HS, static_cast<long long>(LD) * MQ * 256));
 
@@ -1222,6 +1293,22 @@ static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, fl
                             ctx->cls_b, ctx->pt2_w, ctx->pt2_b, nullptr, nullptr, aux_logits, aux_points, nullptr,
                             st));
   }
+  return "";
+}
+
+// (re)compute the input-independent part of decoder layer 0 on one image's worth of rows (see spe_ctx::dec0_tgt)
+static std::string use_workspace(spe_ctx* ctx, int set);
+static std::string fold_dec0(spe_ctx* ctx) {
+  ctx->dec0_valid = false;
+  if (!ctx->dec0_fold) return "";
+  TRY_S(use_workspace(ctx, 0));
+  const long long bytes = static_cast<long long>(ctx->cfg.num_queries) * 256 * static_cast<long long>(dtype_size(ctx->dt));
+  cudaStream_t st = nullptr;
+  TRY_S(forward_tail(ctx, 1, ctx->KV, nullptr, nullptr, nullptr, nullptr, nullptr, st, /*dec0_only=*/true));
+  SPE_CUDA_TRY(cudaMemcpyAsync(ctx->dec0_tgt, ctx->TGT, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, st));
+  SPE_CUDA_TRY(cudaMemcpyAsync(ctx->dec0_q, ctx->DQ, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, st));
+  SPE_CUDA_TRY(cudaStreamSynchronize(st));
+  ctx->dec0_valid = true;
   return "";
 }
 
@@ -1383,7 +1470,7 @@ std::string calibrate_impl(spe_ctx* ctx, const float* images, int B, cudaStream_
     ctx->graphs.clear();
   }
   ctx->calibrated = true;
-  return "";
+  return fold_dec0(ctx);
 }
 
 std::string forward_impl(spe_ctx* ctx, const float* images, int B, float* logits, float* points, float* logsig,
@@ -1484,6 +1571,8 @@ int spe_load_weights(spe_ctx* ctx, const spe_tensor_desc* tensors, int n) {
   std::string s = load_weights_impl(ctx, ws);
   if (!s.empty()) return fail(ctx, SPE_ERR_WEIGHTS, "spe_load_weights: " + s);
   ctx->weights_loaded = true;
+  s = fold_dec0(ctx);
+  if (!s.empty()) return fail(ctx, SPE_ERR_CUDA, "spe_load_weights: " + s);
   return SPE_OK;
 }
 

@@ -59,7 +59,8 @@ std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int 
                                    cudaStream_t s);
 // exact = 0: fp32 storage is TF32-rounded; 1: full fp32 result; 2: 3xTF32 operand layout [hi | lo | hi], row stride 768
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
-                             int dim, void* out, cudaStream_t s, int exact = 0);
+                             int dim, void* out, cudaStream_t s, int exact = 0, const float* gamma2 = nullptr,
+                             const float* beta2 = nullptr, void* out2 = nullptr);   // 2: a second LayerNorm of the result -> out2
 
 // ---- attention (attention.cu) ----
 struct AttnDesc {
