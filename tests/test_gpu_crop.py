@@ -80,6 +80,27 @@ def test_crop_properties(eng):
     assert torch.equal(a, b)
 
 
+def test_staged_and_gather_kernels_are_bit_identical(eng):
+    """Two kernels sit behind spe_crop_resize_norm: the shared-memory staged one (frame rows addressable in 16-byte units:
+    the normal case) and the byte-gather one (any layout).  A frame whose row stride is not a multiple of 16 takes the
+    gather kernel; the same pixels in the normal layout take the staged kernel; the results must be the same bits --
+    for boxes inside, across every border of, and outside the frame."""
+    rng = np.random.default_rng(11)
+    det = synth.load_detector_boxes()[200:232].copy()
+    det[:8, [0, 2]] -= 700; det[8:12, [1, 3]] -= 500; det[12:16, [0, 2]] += 900; det[16:20, [1, 3]] += 600
+    det[20] = [-900, -900, -500, -600]
+    frames = rng.integers(0, 256, size=(32, 1200, 1920), dtype=np.uint8)      # white noise: every tap matters
+    fd = torch.from_numpy(frames).cuda()
+    odd = torch.zeros(32, 1200, 1929, dtype=torch.uint8, device="cuda")
+    odd[:, :, :1920] = fd
+    clip = torch.from_numpy(eng.clip_boxes(det)).cuda()
+    staged = eng.crop_resize_norm(fd, clip)
+    gather = eng.crop_resize_norm(odd[:, :, :1920], clip)
+    assert torch.equal(staged, gather)
+    ref, _ = crop_ref.crop_resize_normalize(frames[3], det[3], 224)
+    assert (staged[3].cpu() - ref).abs().max() <= LSB * 1.001
+
+
 def test_crop_other_input_size(eng):
     det = synth.load_detector_boxes()[100:104]
     frames = synth.make_frames(4, det, seed=4)
