@@ -75,6 +75,21 @@ const char* spe_last_error(const spe_ctx* ctx);
 int spe_load_weights(spe_ctx* ctx, const spe_tensor_desc* tensors, int n);
 int spe_sync(spe_ctx* ctx, void* stream);
 
+/* ---- stage 0: image file -> frame --------------------------------------------------------- */
+/* replaces: Image.open(img_path).convert('RGB')   (RV/datasets/speed.py:116, :212; SA/src/data/speed/speed_dataset.py)
+ * for what SPEED ships: baseline (SOF0 / SOF1) Huffman-coded 8-bit single-component JPEG files.  PIL decodes them
+ * through libjpeg's JDCT_ISLOW integer inverse DCT; the frames written here are bit-identical to np.asarray(Image.open(f))
+ * (and .convert('RGB') of a grayscale image replicates that plane, which the crop kernel does on the fly).
+ * files_host[i] / sizes[i]: the bytes of file i in host memory.  The call parses the headers, copies the compressed
+ * scans into a pinned staging buffer owned by the ctx, and enqueues ONE upload + the decode kernel (one warp per image)
+ * on `stream`; frames_dev (image b at frames_dev + b*frame_stride, rows `pitch` bytes apart, every file exactly W x H)
+ * is valid when the stream reaches that point.  Progressive, arithmetic-coded, 12-bit and multi-component files are
+ * refused with SPE_ERR_INVALID (message names the file index); nothing is enqueued in that case. */
+int spe_jpeg_decode_batch(spe_ctx* ctx, const uint8_t* const* files_host, const long long* sizes, int B,
+                          uint8_t* frames_dev, int H, int W, long long pitch, long long frame_stride, void* stream);
+/* header walk only (host; no device needed): width / height of a file spe_jpeg_decode_batch would accept */
+int spe_jpeg_info(const uint8_t* file_host, long long size, int* width, int* height);
+
 /* ---- stage 1: crop -------------------------------------------------------------------------------------------- */
 /* replaces: SpeedSubmission.generate_clip_bbox               (RV/datasets/speed.py:92-108)
  * host-side, float64, int() truncation toward zero; det_boxes [B,4] = x1,y1,x2,y2 ; boxes [B,4] int32 */

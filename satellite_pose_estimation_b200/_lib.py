@@ -41,6 +41,8 @@ SYMBOLS = {
     "spe_clip_boxes": (_i, [_vp, _i, _vp]),
     "spe_clip_boxes_val": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "spe_speed_score": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "spe_jpeg_decode_batch": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _ll, _ll, _vp]),
+    "spe_jpeg_info": (_i, [_vp, _ll, _vp, _vp]),
     "spe_crop_resize_norm": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _i, _i, _vp, _vp]),
     "spe_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spe_calibrate": (_i, [_vp, _vp, _i, _vp]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspe.so")
-SOURCES = ["gemm_tc.cu", "attention.cu", "attention_tc.cu", "ffn_tc.cu", "elementwise.cu", "heads.cu", "crop.cu", "deform_attn.cu", "pnp.cu", "model.cu", "api.cu", "profile.cu"]
+SOURCES = ["gemm_tc.cu", "attention.cu", "attention_tc.cu", "ffn_tc.cu", "elementwise.cu", "heads.cu", "crop.cu", "jpeg.cu", "deform_attn.cu", "pnp.cu", "model.cu", "api.cu", "profile.cu"]
 HEADERS = ["spe_ptx.cuh", "spe_internal.h", "profile.h", os.path.join("..", "..", "include", "spe.h")]
 
 NVCC_FLAGS = [

@@ -25,8 +25,10 @@
 
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace spe {
@@ -36,14 +38,16 @@ int set_error(spe_ctx* ctx, int code, const std::string& msg);
 namespace spe {
 namespace {
 
-constexpr int kLutBits = 9;
+constexpr int kLutBits = 10;
 constexpr int kRing = 2048;       // bytes of scan window per warp (a power of two)
 constexpr int kChunk = 512;       // refill granule: 32 lanes x 16 bytes
 
-struct JpegTables {               // one per image, device memory
+struct alignas(16) JpegTables {   // one per image, device memory
   uint16_t q[64];                 // quantisation table in the file's (zigzag) order
   uint16_t dc_lut[1 << kLutBits]; // (code length << 8) | symbol for codes of <= kLutBits bits, 0 = longer code
   uint16_t ac_lut[1 << kLutBits];
+  int16_t ac_fast[1 << kLutBits]; // AC code AND its magnitude bits inside kLutBits bits: (value << 8) | (run << 4) |
+                                  // total bits, 0 = take the two-step path (most coefficients are small: one lookup)
   int32_t dc_maxcode[18];         // [l] = largest code of length l (l = 1..16), -1 if none; [17] = sentinel
   int32_t ac_maxcode[18];
   int32_t dc_valoff[17];          // [l] = valptr[l] - mincode[l]
@@ -104,8 +108,23 @@ struct BitReader {                // lane 0 only
   uint64_t buf;
   int cnt;
   bool marker;                    // stopped in front of a marker (RSTn / EOI): zeros are fed until a restart clears it
+  // top up to more than 32 valid bits: one call covers a whole symbol (code <= 16 bits + magnitude <= 11 bits).
+  // Fast path: four scan bytes at once when none of them is 0xFF (no stuffing, no marker); else byte by byte.
   __device__ __forceinline__ void fill() {
-    while (cnt <= 56) {
+    while (cnt <= 32) {
+      if (!marker && pos + 4 <= len) {
+        const uint32_t o = static_cast<uint32_t>(pos) & (kRing - 1);
+        const uint32_t lo = *reinterpret_cast<const uint32_t*>(ring + (o & ~3u));
+        const uint32_t hi = *reinterpret_cast<const uint32_t*>(ring + (((o & ~3u) + 4u) & (kRing - 1)));
+        const uint32_t v = __funnelshift_r(lo, hi, (o & 3u) * 8u);          // bytes pos .. pos + 3, little endian
+        const uint32_t nv = ~v;
+        if (((nv - 0x01010101u) & ~nv & 0x80808080u) == 0u) {               // no byte of v is 0xFF
+          buf |= static_cast<uint64_t>(__byte_perm(v, 0, 0x0123)) << (32 - cnt);
+          cnt += 32;
+          pos += 4;
+          continue;
+        }
+      }
       uint32_t b = 0;
       if (!marker && pos < len) {
         b = ring[pos & (kRing - 1)];
@@ -200,18 +219,33 @@ jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restri
         if (im.restart > 0) {
           if (until_restart == 0) {
             // byte-align, step over the RSTn marker the reader stopped at, reset the DC prediction (F.2.2.4 / E.2.4)
+            // (the reader never reads past a marker, so `pos` sits on it whether or not it has been seen yet)
             br.buf = 0; br.cnt = 0;
-            if (br.marker) { br.pos += 2; br.marker = false; }
+            if (br.pos + 1 < br.len && S.ring[br.pos & (kRing - 1)] == 0xFF &&
+                (S.ring[(br.pos + 1) & (kRing - 1)] & 0xF8) == 0xD0)
+              br.pos += 2;
+            br.marker = false;
             pred = 0;
             until_restart = im.restart;
           }
           --until_restart;
         }
         const int t = decode_symbol(br, S.t.dc_lut, S.t.dc_maxcode, S.t.dc_valoff, S.t.dc_vals);
-        if (t > 0) { br.fill(); pred += br.receive_extend(t & 15); }
+        if (t > 0) pred += br.receive_extend(t & 15);
         S.coef[0] = pred * static_cast<int>(S.t.q[0]);
         int k = 1;
         while (k < 64) {
+          br.fill();
+          const int f = S.t.ac_fast[br.peek(kLutBits)];
+          if (f != 0) {                            // run, size and magnitude from one lookup
+            k += (f >> 4) & 15;
+            if (k > 63) { bad = 1; break; }
+            br.skip(f & 15);
+            S.coef[c_zigzag[k]] = (f >> 8) * static_cast<int>(S.t.q[k]);
+            last_k = k;
+            ++k;
+            continue;
+          }
           const int rs = decode_symbol(br, S.t.ac_lut, S.t.ac_maxcode, S.t.ac_valoff, S.t.ac_vals);
           const int r = rs >> 4, s = rs & 15;
           if (s == 0) {
@@ -221,7 +255,6 @@ jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restri
           }
           k += r;
           if (k > 63) { bad = 1; break; }
-          br.fill();
           S.coef[c_zigzag[k]] = br.receive_extend(s) * static_cast<int>(S.t.q[k]);
           last_k = k;
           ++k;
@@ -407,7 +440,34 @@ std::string parse_jpeg(const uint8_t* d, size_t n, Parsed* out) {
   memcpy(out->t.q, qt[comp_tq], sizeof(out->t.q));
   build_huff(dc[td], out->t.dc_lut, out->t.dc_maxcode, out->t.dc_valoff, out->t.dc_vals);
   build_huff(ac[ta], out->t.ac_lut, out->t.ac_maxcode, out->t.ac_valoff, out->t.ac_vals);
+  for (int i = 0; i < (1 << kLutBits); ++i) {
+    const int e = out->t.ac_lut[i];
+    out->t.ac_fast[i] = 0;
+    const int len = e >> 8, run = (e >> 4) & 15, mag = e & 15;
+    if (e == 0 || mag == 0 || len + mag > kLutBits) continue;
+    int v = ((i << len) & ((1 << kLutBits) - 1)) >> (kLutBits - mag);      // the magnitude bits behind the code
+    if (v < (1 << (mag - 1))) v += -(1 << mag) + 1;                        // EXTEND
+    if (v >= -128 && v <= 127) out->t.ac_fast[i] = static_cast<int16_t>(v * 256 + run * 16 + len + mag);
+  }
   return "";
+}
+
+// run f(i) for i in [0, n) on up to 16 host threads (header walks and scan copies of a batch are independent per file)
+template <typename F>
+void parallel_for(int n, F f) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nt = n < 16 ? 1 : static_cast<int>(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+  if (nt <= 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&]() {
+      for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i);
+    });
+  for (auto& t : th) t.join();
 }
 
 struct JpegState {
@@ -469,15 +529,17 @@ int spe_jpeg_decode_batch(spe_ctx* ctx, const uint8_t* const* files_host, const 
   const size_t img_bytes = ((sizeof(JpegImage) * static_cast<size_t>(B)) + 15) / 16 * 16;
   size_t total = tab_bytes + img_bytes;
   std::vector<size_t> offs(static_cast<size_t>(B));
+  std::vector<std::string> errs(static_cast<size_t>(B));
+  parallel_for(B, [&](int i) {
+    if (!files_host[i] || sizes[i] <= 0) { errs[i] = "null / empty"; return; }
+    errs[i] = parse_jpeg(files_host[i], static_cast<size_t>(sizes[i]), &ps[i]);
+    if (errs[i].empty() && (ps[i].width != W || ps[i].height != H))
+      errs[i] = "is " + std::to_string(ps[i].width) + "x" + std::to_string(ps[i].height) + ", the frame buffer " +
+                std::to_string(W) + "x" + std::to_string(H);
+  });
   for (int i = 0; i < B; ++i) {
-    if (!files_host[i] || sizes[i] <= 0)
-      return set_error(ctx, SPE_ERR_INVALID, "spe_jpeg_decode_batch: file " + std::to_string(i) + " is null / empty");
-    const std::string e = parse_jpeg(files_host[i], static_cast<size_t>(sizes[i]), &ps[i]);
-    if (!e.empty()) return set_error(ctx, SPE_ERR_INVALID, "spe_jpeg_decode_batch: file " + std::to_string(i) + ": " + e);
-    if (ps[i].width != W || ps[i].height != H)
-      return set_error(ctx, SPE_ERR_INVALID, "spe_jpeg_decode_batch: file " + std::to_string(i) + " is " +
-                                                 std::to_string(ps[i].width) + "x" + std::to_string(ps[i].height) +
-                                                 ", the frame buffer " + std::to_string(W) + "x" + std::to_string(H));
+    if (!errs[i].empty())
+      return set_error(ctx, SPE_ERR_INVALID, "spe_jpeg_decode_batch: file " + std::to_string(i) + ": " + errs[i]);
     offs[i] = total;
     total += (ps[i].scan_end - ps[i].scan_begin + 15) / 16 * 16 + 2 * kChunk;     // zero padding behind every scan
   }
@@ -508,7 +570,8 @@ int spe_jpeg_decode_batch(spe_ctx* ctx, const uint8_t* const* files_host, const 
     return set_error(ctx, SPE_ERR_CUDA, "spe_jpeg_decode_batch: cudaEventCreate failed");
   JpegTables* th = reinterpret_cast<JpegTables*>(S->stage_h);
   JpegImage* ih = reinterpret_cast<JpegImage*>(S->stage_h + tab_bytes);
-  for (int i = 0; i < B; ++i) {
+  uint8_t* stage = S->stage_h;
+  parallel_for(B, [&](int i) {
     th[i] = ps[i].t;
     const size_t len = ps[i].scan_end - ps[i].scan_begin;
     ih[i].scan_off = static_cast<long long>(offs[i]);
@@ -516,10 +579,10 @@ int spe_jpeg_decode_batch(spe_ctx* ctx, const uint8_t* const* files_host, const 
     ih[i].width = ps[i].width;
     ih[i].height = ps[i].height;
     ih[i].restart = ps[i].restart;
-    memcpy(S->stage_h + offs[i], files_host[i] + ps[i].scan_begin, len);
+    memcpy(stage + offs[i], files_host[i] + ps[i].scan_begin, len);
     const size_t padded = (i + 1 < B ? offs[i + 1] : total) - offs[i];
-    memset(S->stage_h + offs[i] + len, 0, padded - len);
-  }
+    memset(stage + offs[i] + len, 0, padded - len);
+  });
   cudaError_t e = cudaMemcpyAsync(S->stage_d, S->stage_h, total, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaEventRecord(S->copied, st);
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_jpeg_decode_batch: ") + cudaGetErrorString(e));

@@ -363,6 +363,7 @@ struct spe_ctx {
 namespace spe {
 
 void pipeline_release(spe_ctx* ctx);   // api.cu
+void jpeg_release(spe_ctx* ctx);       // jpeg.cu
 bool pipeline_busy(spe_ctx* ctx);      // api.cu
 
 static std::string g_last_error;
@@ -1541,6 +1542,7 @@ void spe_destroy(spe_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   pipeline_release(ctx);
+  jpeg_release(ctx);
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }

@@ -108,6 +108,30 @@ class Engine:
                                        _stream(q.device)), self._ctx)
         return s_t, s_q
 
+    # ---- stage 0 ---------------------------------------------------------------------------------------------
+    def decode_jpeg(self, files, out=None):
+        """files: list of ``bytes`` (baseline grayscale JPEG files of one size, as SPEED ships them) -> uint8 cuda
+        [B,H,W], bit-identical to ``np.asarray(PIL.Image.open(f))`` (RV/datasets/speed.py:116 decodes with PIL and
+        replicates the plane to RGB; the crop stage replicates on the fly).  Huffman decoding and the inverse DCT run
+        on the GPU (one warp per image); only the compressed bytes cross PCIe.  Refuses progressive / colour files."""
+        B = len(files)
+        if B == 0:
+            raise ValueError("decode_jpeg: empty batch")
+        w, h = C.c_int(0), C.c_int(0)
+        files = [bytes(f) if not isinstance(f, bytes) else f for f in files]
+        bufs = [C.c_char_p(f) for f in files]            # pointers into the bytes objects themselves: no copy
+        check(self.lib.spe_jpeg_info(C.cast(bufs[0], C.c_void_p), len(files[0]), C.byref(w), C.byref(h)), None)
+        H, W = h.value, w.value
+        dev = self.device
+        if out is None:
+            out = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        assert out.dtype == torch.uint8 and out.is_cuda and tuple(out.shape) == (B, H, W) and out.stride(2) == 1
+        ptrs = (C.c_void_p * B)(*[C.cast(b, C.c_void_p).value for b in bufs])
+        sizes = (C.c_longlong * B)(*[len(f) for f in files])
+        check(self.lib.spe_jpeg_decode_batch(self._ctx, ptrs, sizes, B, _ptr(out), H, W, out.stride(1), out.stride(0),
+                                             _stream(dev)), self._ctx)
+        return out
+
     def crop_resize_norm(self, frames, boxes, out=None, R=None):
         """frames: uint8 cuda [B,H,W]; boxes: int32 cuda [B,4] -> float32 cuda [B,3,R,R]."""
         R = R or self.R

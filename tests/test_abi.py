@@ -45,8 +45,16 @@ def test_kernels_are_blackwell_native():
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, f"{mnemonic} missing from libspe.so SASS"
-    # issue loops are warp-uniform (elect_one_sync): no per-instruction waterfall loops around UTCHMMA / UTMALDG
-    assert "BRA.U.ANY" not in sass
+    # issue loops are warp-uniform (elect_one_sync): no per-instruction waterfall loops around UTCHMMA / UTMALDG.
+    # The one place a waterfall is the intent: the staged crop kernel, where each of 32 lanes issues the bulk copy of
+    # its OWN frame-row segment (32 different addresses, once per CTA).
+    fn, waterfall = None, set()
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif "BRA.U.ANY" in line:
+            waterfall.add(fn)
+    assert all("crop_resize_norm_staged_kernel" in f for f in waterfall), waterfall
     # programmatic dependent launch: griddepcontrol.wait / .launch_dependents compiled into the step's kernels
     assert sass.count("ACQBULK") >= 20 and sass.count("PREEXIT") >= 20
 
@@ -107,3 +115,29 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+def test_jpeg_header_walk_on_the_host():
+    """spe_jpeg_info needs no device: sizes of baseline grayscale files, refusal of what the decode kernel does not take"""
+    import io
+    from PIL import Image
+    lib = _lib.load()
+    a = (np.arange(48 * 100).reshape(48, 100) % 251).astype(np.uint8)
+
+    def info(**kw):
+        buf = io.BytesIO()
+        img = Image.fromarray(a, "L") if kw.pop("gray", True) else Image.fromarray(np.stack([a] * 3, -1), "RGB")
+        img.save(buf, "JPEG", **kw)
+        b = buf.getvalue()
+        w, h = C.c_int(0), C.c_int(0)
+        rc = lib.spe_jpeg_info(C.cast(C.create_string_buffer(b, len(b)), C.c_void_p), len(b), C.byref(w), C.byref(h))
+        return rc, w.value, h.value, (lib.spe_global_last_error() or b"").decode()
+
+    assert info(quality=80)[:3] == (0, 100, 48)
+    assert info(quality=95, optimize=True, restart_marker_rows=1)[:3] == (0, 100, 48)
+    rc, _, _, msg = info(progressive=True)
+    assert rc == -1 and "progressive" in msg
+    rc, _, _, msg = info(gray=False)
+    assert rc == -1 and "3 components" in msg
+    w, h = C.c_int(0), C.c_int(0)
+    assert lib.spe_jpeg_info(C.cast(C.create_string_buffer(b"abcdefgh", 8), C.c_void_p), 8, C.byref(w), C.byref(h)) == -1

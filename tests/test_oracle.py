@@ -181,3 +181,39 @@ def test_rot_to_quat_and_score():
         q2 = pnp_ref.rot_to_quat(synth.quat_to_rot(q))
         assert np.allclose(q, q2, atol=1e-12)
     assert pnp_ref.speed_score([1, 0, 0, 0], [0, 0, 10], [-1, 0, 0, 0], [0, 0, 10]) == (0.0, 0.0)
+
+
+def test_jpeg_ref_matches_pil():
+    """oracle/jpeg_ref.py (T.81 Huffman decoding + libjpeg's JDCT_ISLOW inverse DCT) against PIL's decoder -- the call
+    the reference makes (RV/datasets/speed.py:116) -- bit for bit: sizes with partial edge blocks, qualities 30..100,
+    optimised Huffman tables, restart intervals, white noise (saturating range limit)."""
+    import io
+    from PIL import Image
+    from oracle import jpeg_ref
+    rng = np.random.default_rng(0)
+
+    def synth_img(h, w):
+        y, x = np.mgrid[0:h, 0:w]
+        img = 40 + 30 * np.sin(x / 7.0) + 25 * np.cos(y / 5.0) + rng.normal(0, 12, (h, w))
+        img[h // 3:h // 2, w // 4:w // 2] += 120
+        return np.clip(img, 0, 255).astype(np.uint8)
+
+    cases = [(64, 48, dict(quality=75)), (117, 203, dict(quality=90)), (40, 40, dict(quality=30, optimize=True)),
+             (96, 160, dict(quality=100)), (80, 72, dict(quality=85, restart_marker_blocks=7)),
+             (33, 9, dict(quality=60, restart_marker_rows=1))]
+    for h, w, kw in cases:
+        buf = io.BytesIO()
+        Image.fromarray(synth_img(h, w), "L").save(buf, "JPEG", **kw)
+        b = buf.getvalue()
+        assert np.array_equal(jpeg_ref.decode(b), np.asarray(Image.open(io.BytesIO(b)))), (h, w, kw)
+    buf = io.BytesIO()
+    Image.fromarray(rng.integers(0, 256, (64, 64), dtype=np.uint8), "L").save(buf, "JPEG", quality=98)
+    b = buf.getvalue()
+    ref = np.asarray(Image.open(io.BytesIO(b)))
+    assert np.array_equal(jpeg_ref.decode(b), ref)
+    rgb = np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))         # what the reference goes on with
+    assert all(np.array_equal(rgb[..., c], ref) for c in range(3))
+    buf = io.BytesIO()
+    Image.fromarray(ref, "L").save(buf, "JPEG", progressive=True)
+    with pytest.raises(jpeg_ref.Unsupported):
+        jpeg_ref.decode(buf.getvalue())
