@@ -426,6 +426,33 @@ def run_b200(args):
     image_set = {"images": n_img, "seconds": set_s, "images_per_s": n_img / set_s, "images_per_rank": b - a,
                  "batches_per_rank": -(-(b - a) // BATCH), "tail_batch": (b - a) % BATCH, "poses_solved": int(n_ok.item()),
                  "frames": "pinned host memory, ROI upload inside the timed region", "timing": "wall clock, max over ranks"}
+    # ---- the same set from JPEG FILES (what the reference's loader starts from: RV/datasets/speed.py:116): the rank's
+    # shard of compressed files in host memory -> GPU Huffman + inverse DCT (bit-identical to PIL) -> frames stay in HBM
+    # -> the pipeline.  16 distinct files (PIL-encoded outside the timed region), cycled over the shard.
+    try:
+        import io
+        from PIL import Image
+        enc = []
+        for k in range(16):
+            buf = io.BytesIO()
+            Image.fromarray(shard_np[k % max(1, b - a)], "L").save(buf, "JPEG", quality=80)
+            enc.append(buf.getvalue())
+        files = [enc[i % 16] for i in range(n_img)]
+        run_image_set(eng, None, det_all, names, batch_size=BATCH, rank=rank, world_size=world, slots=SLOTS, gather=False,
+                      jpeg_files=files)                        # warm-up (staging windows, device buffer of the shard)
+        barrier()
+        t0 = time.perf_counter()
+        jres = run_image_set(eng, None, det_all, names, batch_size=BATCH, rank=rank, world_size=world, slots=SLOTS,
+                             gather=False, jpeg_files=files)
+        torch.cuda.synchronize()
+        jpeg_s = max_over_ranks(time.perf_counter() - t0)
+        image_set["from_jpeg_files"] = {"seconds": jpeg_s, "images_per_s": n_img / jpeg_s,
+                                        "compressed_mb_per_rank": sum(len(f) for f in files[a:b]) / 1e6,
+                                        "poses_solved_this_rank": sum(1 for v in jres.values() if v["status"] == 0),
+                                        "decode": "spe_jpeg_decode_batch: whole shard at once, one warp per image"}
+        del jres, files, enc
+    except ImportError:
+        image_set["from_jpeg_files"] = None
     del shard, shard_np
 
     roofline = p50 = cpu = side = None

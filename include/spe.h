@@ -235,6 +235,10 @@ int spe_debug_gemm(int dtype, const void* A_dev, const void* W_dev, long long M,
                    void* stream);
 /* convolution (stride 1 or 2) as implicit GEMM: x [NB,H,W,C] NHWC, w [Cout, R*S*C] (tap-major, channel-minor),
  * out [NB,Ho,Wo,Cout] with Ho = (H + 2 pad - R) / stride + 1 */
+/* out[M, N] = act([A | A2] . Wt^T + bias): A [M, K]; A2 either [M, K2] (a2_stride 1) or the (2h, 2w) sampling of an NHWC
+ * activation [NB, H, W, K2] with M = NB * ceil(H/2) * ceil(W/2) (a2_stride 2); Wt [N, K + K2] */
+int spe_debug_gemm2(int dtype, const void* A_dev, int K, const void* A2_dev, int K2, int a2_stride, int NB, int H, int W,
+                    const void* Wt_dev, long long M, int N, const float* bias_dev, int relu, void* out_dev, void* stream);
 int spe_debug_conv(int dtype, const void* x_dev, const void* w_dev, int NB, int H, int W, int C, int Cout, int R,
                    int S, int pad, int stride, const float* scale_dev, const float* bias_dev, int relu, void* out_dev,
                    void* stream);

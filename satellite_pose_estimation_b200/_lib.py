@@ -55,6 +55,7 @@ SYMBOLS = {
     "spe_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "spe_run_batch_host": (_i, [_vp, _vp, _i, _i, _vp, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp]),
     "spe_debug_gemm": (_i, [_i, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "spe_debug_gemm2": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _ll, _i, _vp, _i, _vp, _vp]),
     "spe_debug_conv": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "spe_debug_attention": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "spe_debug_ffn": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),

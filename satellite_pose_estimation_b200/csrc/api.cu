@@ -536,6 +536,17 @@ int spe_debug_gemm(int dtype, const void* A, const void* Wt, long long M, int N,
   return SPE_OK;
 }
 
+int spe_debug_gemm2(int dtype, const void* A, int K, const void* A2, int K2, int a2_stride, int NB, int H, int W,
+                    const void* Wt, long long M, int N, const float* bias, int relu, void* out, void* stream) {
+  GemmDesc d;
+  d.mode = 0; d.A = A; d.M = M; d.K = K; d.lda = K; d.Wt = Wt; d.N = N;
+  d.A2 = A2; d.K2 = K2; d.lda2 = K2; d.a2_stride = a2_stride; d.a2_NB = NB; d.a2_H = H; d.a2_W = W;
+  d.bias = bias; d.relu = relu; d.out = out; d.out_ld = N;
+  std::string s = launch_gemm(dtype == 1 ? kBF16 : kTF32, d, sm_count(), static_cast<cudaStream_t>(stream));
+  if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_gemm2: " + s);
+  return SPE_OK;
+}
+
 int spe_debug_conv(int dtype, const void* x, const void* w, int NB, int H, int W, int C, int Cout, int R, int S,
                    int pad, int stride, const float* scale, const float* bias, int relu, void* out, void* stream) {
   GemmDesc d;

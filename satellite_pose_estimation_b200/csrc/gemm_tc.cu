@@ -86,6 +86,8 @@ struct GemmKParams {
   int sub_rows;        // ... image rows per 128-row accumulator
   int stem_im2col;     // mode 2 through an im2col map: tile = 128 consecutive output pixels
   uint32_t a_stage;    // ... bytes of one halo-tile stage
+  int kb_split;        // mode 0 with a second operand source: k-blocks [kb_split, num_kb) come from tmA2 (else = num_kb)
+  int a2_im2col;       // ... through an im2col map (1x1 / stride 2 sampling; uses HW, W, cstride) instead of a plain one
   int dbg;             // SPE_GEMM_DBG bit 0: skip the output stores (profiling experiments only)
   long long* tdbg;     // -DSPE_GEMM_TIMING + SPE_GEMM_TDBG=1: per-CTA wait-cycle counters of gemm_tc_kernel (bring-up only)
 };
@@ -357,7 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
 template <typename T, int BN, bool X3, bool EPI8>
 __global__ void __launch_bounds__((StageCfg<BN, X3, EPI8>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const GemmKParams p) {
   using Tr = GemmTraits<T>;
   using Cfg = StageCfg<BN, X3, EPI8>;
   constexpr int EPI_WARPS = Cfg::EPI_WARPS;
@@ -388,6 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.kb_split < p.num_kb) tma_prefetch_desc(&tmA2);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -425,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.mode == 1) {
           img = m_tile / p.tiles_per_img;
           h0 = (m_tile - img * p.tiles_per_img) * p.hrows;
-        } else if (p.mode == 3) {   // im2col map: 128 consecutive output pixels
+        } else if (p.mode == 3 || (p.mode == 0 && p.a2_im2col)) {   // im2col map: 128 consecutive output pixels
           const int m0 = m_tile * BM;
           img = m0 / p.HW;
           const int rem = m0 - img * p.HW;
@@ -450,7 +453,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + (X3 ? 2 : 1) * Cfg::A_BYTES;
             if (p.mode == 0) {
-              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
+              if (kb < p.kb_split) tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_tile * BM);
+              else if (!p.a2_im2col) tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - p.kb_split) * BK, m_tile * BM);
+              else tma_load_im2col_4d(sa, &tmA2, &full_bar[stage], (kb - p.kb_split) * BK, x0 * p.cstride, h0 * p.cstride,
+                                      img, 0, 0);
             } else if (p.mode == 2) {
               // k-block kb = filter row kb: 8 consecutive padded pixels x Cp channels per output pixel, windows of
               // neighbouring output pixels overlap (dim-1 stride = 2 pixels)
@@ -1231,7 +1237,7 @@ std::string encode_map(CUtensorMap* m, Dtype dt, int rank, const void* base, con
 
 template <typename T, int BN, bool X3, bool EPI8>
 std::string launch_t(const GemmDesc& d, const GemmKParams& kp_in, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                     int num_sms, cudaStream_t stream) {
+                     const CUtensorMap& tmA2, int num_sms, cudaStream_t stream) {
   GemmKParams kp = kp_in;
   static const bool tdbg_on = getenv("SPE_GEMM_TDBG") != nullptr;
   static long long* tdbg_dev = nullptr;
@@ -1249,7 +1255,7 @@ std::string launch_t(const GemmDesc& d, const GemmKParams& kp_in, const CUtensor
   const int grid = tiles < num_sms ? tiles : num_sms;
   {
     ProfScope ps(kFamGemm, stream);
-    SPE_CUDA_TRY(launch_pdl(kfn, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, kp));
+    SPE_CUDA_TRY(launch_pdl(kfn, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmA2, kp));
   }
   SPE_CUDA_TRY(cudaGetLastError());
   (void)d;
@@ -1366,6 +1372,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
   if (d.x3 && d.mode != 0) return "gemm: 3xTF32 is only built for plain matrices";
   if (d.mode < 0 || d.mode > 2) return "gemm: bad mode";
+  if (d.A2 != nullptr && (d.mode != 0 || d.x3)) return "gemm: a second operand source needs a plain, uncompensated GEMM";
   if (d.mode == 1) {
     const std::string c3 = launch_conv3(dt, d, num_sms, stream);
     if (c3 != "skip") return c3;
@@ -1383,6 +1390,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   const int k_est = d.mode == 0 ? d.K : d.R * d.S * d.C;
   bool cg2 = !d.x3 && d.mode != 2 && d.N % 256 == 0 && k_est / BK >= cg2_min_kb && ((m_tiles_est + 1) / 2) * (d.N / 256) >= 48;
   if (cg2_force >= 0) cg2 = cg2 && cg2_force != 0;
+  if (d.A2 != nullptr) cg2 = false;   // the two-source producer is built into gemm_tc_kernel only
   if (cg2) BN = 256;
   static const int bn_force = getenv("SPE_GEMM_BN") ? atoi(getenv("SPE_GEMM_BN")) : 0;   // experiments only
   if (!cg2 && (bn_force == 64 || bn_force == 128) && bn_force <= d.N) BN = bn_force;
@@ -1412,9 +1420,10 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (kp.out_f32 && d.mode != 0) return "gemm: fp32 output from bf16 storage is only built for plain matrices";
   kp.num_n_tiles = (d.N + BN - 1) / BN;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA2;
   std::string err;
   int K;
+  kp.kb_split = 1 << 30;
   if (d.mode == 0) {
     K = d.K;
     if (K % BK != 0) return "gemm: K must be a multiple of the 128-byte k-block";
@@ -1427,6 +1436,26 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), BM};
     err = encode_map(&tmA, dt, 2, d.A, dims, str, box);
     if (!err.empty()) return err;
+    if (d.A2 != nullptr) {
+      if (d.K2 <= 0 || d.K2 % BK != 0) return "gemm: K2 must be a multiple of the 128-byte k-block";
+      kp.kb_split = K / BK;
+      if (d.a2_stride == 1) {
+        if ((static_cast<long long>(d.lda2) * es) % 16 != 0) return "gemm: lda2 must keep rows 16-byte aligned";
+        cuuint64_t dims2[2] = {static_cast<cuuint64_t>(d.K2), static_cast<cuuint64_t>(d.M)};
+        cuuint64_t str2[1] = {static_cast<cuuint64_t>(d.lda2) * es};
+        err = encode_map(&tmA2, dt, 2, d.A2, dims2, str2, box);
+      } else if (d.a2_stride == 2) {
+        const int Ho = (d.a2_H - 1) / 2 + 1, Wo = (d.a2_W - 1) / 2 + 1;
+        if (static_cast<long long>(d.a2_NB) * Ho * Wo != d.M) return "gemm: second source does not sample M pixels";
+        kp.a2_im2col = 1;
+        kp.HW = Ho * Wo; kp.H = Ho; kp.W = Wo; kp.cstride = 2;
+        err = encode_map_im2col(&tmA2, dt, d.A2, d.K2, d.a2_W, d.a2_H, d.a2_NB, 1, 1, 0, 2, BK, BM);
+      } else {
+        return "gemm: second-source stride must be 1 or 2";
+      }
+      if (!err.empty()) return "gemm (second source): " + err;
+      K += d.K2;
+    }
   } else if (d.mode == 2) {
     const int Cp = 16 / es;                              // padded channels per pixel (16 bytes)
     if (d.C != Cp) return "stem: input must be the padded NHWC-Cp image";
@@ -1513,6 +1542,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   }
   kp.num_kb = K / BK;
   kp.K = K;
+  if (d.A2 == nullptr) { tmA2 = tmA; kp.kb_split = kp.num_kb; }
   {
     const int kw = d.x3 ? 2 * K : K;   // X3 weights: [N, 2K] = [W_hi | W_lo]
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(kw), static_cast<cuuint64_t>(d.N)};
@@ -1532,7 +1562,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   // short K loops cannot hide a 4-warp epilogue: give those GEMMs the 8-warp epilogue (and fewer smem stages)
   static const int epi_force = getenv("SPE_GEMM_EPI8") ? atoi(getenv("SPE_GEMM_EPI8")) : -1;
   const bool epi8 = !d.x3 && (epi_force >= 0 ? epi_force != 0 : kp.num_kb <= 16);
-#define SPE_LAUNCH(TT, BNV, X3V, E8V) return launch_t<TT, BNV, X3V, E8V>(d, kp, tmA, tmB, num_sms, stream)
+#define SPE_LAUNCH(TT, BNV, X3V, E8V) return launch_t<TT, BNV, X3V, E8V>(d, kp, tmA, tmB, tmA2, num_sms, stream)
   if (dt == kTF32) {
     if (d.x3) {
       if (BN == 64) SPE_LAUNCH(float, 64, true, false);

@@ -470,15 +470,19 @@ void parallel_for(int n, F f) {
   for (auto& t : th) t.join();
 }
 
+// The compressed bytes travel through two fixed pinned windows (the host threads pack window w + 1 while window w is
+// on the wire) into one device buffer that grows with the largest batch seen; a pinned buffer the size of a whole
+// image set (gigabytes) would cost more to allocate than the set takes to decode.
+constexpr size_t kStageWindow = size_t(96) << 20;
 struct JpegState {
-  uint8_t* stage_h = nullptr;      // pinned: [tables | image records | packed scans]
-  uint8_t* stage_d = nullptr;
-  size_t cap = 0;
+  uint8_t* win_h[2] = {nullptr, nullptr};   // pinned windows
+  size_t win_cap = 0;
+  cudaEvent_t win_free[2] = {nullptr, nullptr};   // fires when the copy out of the window has completed
+  bool win_busy[2] = {false, false};
+  uint8_t* stage_d = nullptr;               // device: [tables | image records | packed scans]
+  size_t cap_d = 0;
   int* status_d = nullptr;
-  int* status_h = nullptr;
   int status_cap = 0;
-  cudaEvent_t copied = nullptr;    // the staging buffer may be rewritten once this has fired
-  bool pending = false;
 };
 std::map<spe_ctx*, JpegState*> g_jpeg;
 
@@ -488,12 +492,13 @@ void jpeg_release(spe_ctx* ctx) {
   auto it = g_jpeg.find(ctx);
   if (it == g_jpeg.end()) return;
   JpegState* s = it->second;
-  if (s->pending) cudaEventSynchronize(s->copied);
-  if (s->stage_h) cudaFreeHost(s->stage_h);
+  for (int w = 0; w < 2; ++w) {
+    if (s->win_busy[w]) cudaEventSynchronize(s->win_free[w]);
+    if (s->win_h[w]) cudaFreeHost(s->win_h[w]);
+    if (s->win_free[w]) cudaEventDestroy(s->win_free[w]);
+  }
   if (s->stage_d) cudaFree(s->stage_d);
   if (s->status_d) cudaFree(s->status_d);
-  if (s->status_h) cudaFreeHost(s->status_h);
-  if (s->copied) cudaEventDestroy(s->copied);
   delete s;
   g_jpeg.erase(it);
 }
@@ -543,50 +548,93 @@ int spe_jpeg_decode_batch(spe_ctx* ctx, const uint8_t* const* files_host, const 
     offs[i] = total;
     total += (ps[i].scan_end - ps[i].scan_begin + 15) / 16 * 16 + 2 * kChunk;     // zero padding behind every scan
   }
-  if (S->pending) { cudaEventSynchronize(S->copied); S->pending = false; }
-  if (total > S->cap) {
-    if (S->stage_h) cudaFreeHost(S->stage_h);
-    if (S->stage_d) cudaFree(S->stage_d);
-    S->stage_h = nullptr; S->stage_d = nullptr; S->cap = 0;
-    const size_t want = total + total / 2;
-    if (cudaMallocHost(reinterpret_cast<void**>(&S->stage_h), want) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&S->stage_d), want) != cudaSuccess) {
-      cudaGetLastError();
-      return set_error(ctx, SPE_ERR_CUDA, "spe_jpeg_decode_batch: out of memory for the staging buffers");
+  // ---- buffers: device buffer for everything, two pinned windows at least as large as the header block / any one scan
+  size_t need_win = tab_bytes + img_bytes;
+  for (int i = 0; i < B; ++i) {
+    const size_t sz = (i + 1 < B ? offs[i + 1] : total) - offs[i];
+    if (sz > need_win) need_win = sz;
+  }
+  if (need_win < kStageWindow) need_win = kStageWindow;
+  if (need_win > S->win_cap) {
+    for (int w = 0; w < 2; ++w) {
+      if (S->win_busy[w]) { cudaEventSynchronize(S->win_free[w]); S->win_busy[w] = false; }
+      if (S->win_h[w]) cudaFreeHost(S->win_h[w]);
+      S->win_h[w] = nullptr;
+      if (cudaMallocHost(reinterpret_cast<void**>(&S->win_h[w]), need_win) != cudaSuccess) {
+        cudaGetLastError();
+        S->win_cap = 0;
+        return set_error(ctx, SPE_ERR_CUDA, "spe_jpeg_decode_batch: out of pinned memory for the staging windows");
+      }
+      if (!S->win_free[w] && cudaEventCreateWithFlags(&S->win_free[w], cudaEventDisableTiming) != cudaSuccess)
+        return set_error(ctx, SPE_ERR_CUDA, "spe_jpeg_decode_batch: cudaEventCreate failed");
     }
-    S->cap = want;
+    S->win_cap = need_win;
+  }
+  if (total > S->cap_d) {
+    // the previous batch's kernel may still read the old buffer: cudaFree waits for the device
+    if (S->stage_d) cudaFree(S->stage_d);
+    S->stage_d = nullptr; S->cap_d = 0;
+    const size_t want = total + total / 4;
+    if (cudaMalloc(reinterpret_cast<void**>(&S->stage_d), want) != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(ctx, SPE_ERR_CUDA, "spe_jpeg_decode_batch: out of device memory for the compressed scans");
+    }
+    S->cap_d = want;
   }
   if (B > S->status_cap) {
     if (S->status_d) cudaFree(S->status_d);
-    if (S->status_h) cudaFreeHost(S->status_h);
-    if (cudaMalloc(reinterpret_cast<void**>(&S->status_d), sizeof(int) * B) != cudaSuccess ||
-        cudaMallocHost(reinterpret_cast<void**>(&S->status_h), sizeof(int) * B) != cudaSuccess) {
+    S->status_d = nullptr; S->status_cap = 0;
+    if (cudaMalloc(reinterpret_cast<void**>(&S->status_d), sizeof(int) * B) != cudaSuccess) {
       cudaGetLastError();
       return set_error(ctx, SPE_ERR_CUDA, "spe_jpeg_decode_batch: out of memory");
     }
     S->status_cap = B;
   }
-  if (!S->copied && cudaEventCreateWithFlags(&S->copied, cudaEventDisableTiming) != cudaSuccess)
-    return set_error(ctx, SPE_ERR_CUDA, "spe_jpeg_decode_batch: cudaEventCreate failed");
-  JpegTables* th = reinterpret_cast<JpegTables*>(S->stage_h);
-  JpegImage* ih = reinterpret_cast<JpegImage*>(S->stage_h + tab_bytes);
-  uint8_t* stage = S->stage_h;
-  parallel_for(B, [&](int i) {
-    th[i] = ps[i].t;
-    const size_t len = ps[i].scan_end - ps[i].scan_begin;
-    ih[i].scan_off = static_cast<long long>(offs[i]);
-    ih[i].scan_len = static_cast<int>(len);
-    ih[i].width = ps[i].width;
-    ih[i].height = ps[i].height;
-    ih[i].restart = ps[i].restart;
-    memcpy(stage + offs[i], files_host[i] + ps[i].scan_begin, len);
-    const size_t padded = (i + 1 < B ? offs[i + 1] : total) - offs[i];
-    memset(stage + offs[i] + len, 0, padded - len);
-  });
-  cudaError_t e = cudaMemcpyAsync(S->stage_d, S->stage_h, total, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaEventRecord(S->copied, st);
+  cudaError_t e = cudaSuccess;
+  int w = 0;
+  auto window = [&]() -> uint8_t* {          // next window, once the copy that last used it has completed
+    w ^= 1;
+    if (S->win_busy[w]) { cudaEventSynchronize(S->win_free[w]); S->win_busy[w] = false; }
+    return S->win_h[w];
+  };
+  auto ship = [&](size_t dev_off, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMemcpyAsync(S->stage_d + dev_off, S->win_h[w], bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(S->win_free[w], st);
+    S->win_busy[w] = true;
+  };
+  // ---- header block: tables + image records
+  {
+    uint8_t* h = window();
+    JpegTables* th = reinterpret_cast<JpegTables*>(h);
+    JpegImage* ih = reinterpret_cast<JpegImage*>(h + tab_bytes);
+    parallel_for(B, [&](int i) {
+      th[i] = ps[i].t;
+      ih[i].scan_off = static_cast<long long>(offs[i]);
+      ih[i].scan_len = static_cast<int>(ps[i].scan_end - ps[i].scan_begin);
+      ih[i].width = ps[i].width;
+      ih[i].height = ps[i].height;
+      ih[i].restart = ps[i].restart;
+    });
+    ship(0, tab_bytes + img_bytes);
+  }
+  // ---- scans, a window's worth of whole files at a time
+  for (int i0 = 0; i0 < B;) {
+    int i1 = i0;
+    const size_t base = offs[i0];
+    while (i1 < B && (i1 + 1 < B ? offs[i1 + 1] : total) - base <= S->win_cap) ++i1;
+    uint8_t* h = window();
+    parallel_for(i1 - i0, [&](int k) {
+      const int i = i0 + k;
+      const size_t len = ps[i].scan_end - ps[i].scan_begin;
+      memcpy(h + (offs[i] - base), files_host[i] + ps[i].scan_begin, len);
+      const size_t padded = (i + 1 < B ? offs[i + 1] : total) - offs[i];
+      memset(h + (offs[i] - base) + len, 0, padded - len);
+    });
+    ship(base, (i1 < B ? offs[i1] : total) - base);
+    i0 = i1;
+  }
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string("spe_jpeg_decode_batch: ") + cudaGetErrorString(e));
-  S->pending = true;
   static bool attr = false;
   const size_t smem = sizeof(WarpSmem) * kWarpsPerCta;
   if (!attr) {

@@ -162,6 +162,12 @@ __global__ void bias_correction_kernel(const float* __restrict__ w32, const T* _
   if (lane == 0) applied[n] = delta;
 }
 
+// a[i] *= f, b[i] *= f (column sums of a second operand source taken over a different number of rows)
+__global__ void scale_pair_kernel(float* __restrict__ a, float* __restrict__ b, int n, float f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] *= f; b[i] *= f; }
+}
+
 // round-to-nearest (ties away) fp32 -> TF32, the host twin of cvt.rna.tf32.f32
 inline float host_rna_tf32(float x) {
   uint32_t u;
@@ -203,6 +209,10 @@ struct GemmW {          // one GEMM's parameters on the device
 
 struct Bottleneck {
   GemmW c1, c2, c3, down;
+  // First block of a layer: out = relu(bn3(conv3(t)) + bn_d(down(x))) is ONE GEMM over the concatenated operand
+  // [t | x (sampled at the block's stride)] with weights [s3 W3 | s_d W_d] (FrozenBN scales folded into the rows) and
+  // bias b3 + b_d: the downsample output (205 MB at layer1, B = 64) is never written or read back, one launch less.
+  GemmW c3d;
   int inplanes = 0, planes = 0, stride = 1;
   bool has_down = false;
 };
@@ -281,6 +291,7 @@ struct spe_ctx {
   void* dec0_q = nullptr;      // [Q, 256] storage dtype: cross-attention query projection of decoder layer 0
   bool dec0_valid = false;
   bool dec0_fold = getenv("SPE_DEC0_FOLD") ? atoi(getenv("SPE_DEC0_FOLD")) != 0 : true;
+  bool fuse_down = getenv("SPE_FUSE_DOWN") ? atoi(getenv("SPE_FUSE_DOWN")) != 0 : true;   // Bottleneck::c3d
   void* L1OUT = nullptr;       // [B, 56, 56, 256] layer1 output of all chunks
   int head_chunk = getenv("SPE_HEAD_CHUNK") ? atoi(getenv("SPE_HEAD_CHUNK")) : 0;
   bool fold_neck = getenv("SPE_FOLD_NECK") ? atoi(getenv("SPE_FOLD_NECK")) != 0 : true;
@@ -490,6 +501,44 @@ static std::string load_bn(spe_ctx* ctx, WeightSource& ws, const std::string& pr
   return "";
 }
 
+// FrozenBatchNorm2d scale / bias on the host (same fp32 op order as load_bn)
+static bool bn_fold_host(WeightSource& ws, const std::string& prefix, int C, std::vector<float>* scale, std::vector<float>* bias) {
+  const HostTensor* w = ws.get(prefix + ".weight", {C});
+  const HostTensor* b = ws.get(prefix + ".bias", {C});
+  const HostTensor* rm = ws.get(prefix + ".running_mean", {C});
+  const HostTensor* rv = ws.get(prefix + ".running_var", {C});
+  if (!w || !b || !rm || !rv) return false;
+  scale->resize(C); bias->resize(C);
+  for (int i = 0; i < C; ++i) {
+    const float sc = w->data[i] * (1.0f / sqrtf(rv->data[i] + 1e-5f));
+    (*scale)[i] = sc;
+    (*bias)[i] = b->data[i] - rm->data[i] * sc;
+  }
+  return true;
+}
+
+static std::string upload_gemm_w(spe_ctx* ctx, const std::vector<float>& host, int N, int K, GemmW* g, bool x3, bool keep32);
+// conv3 + bn3 and downsample.0 + downsample.1 of residual block `p` as one [N, planes + inplanes] weight matrix
+// (Bottleneck::c3d): rows scaled by the two FrozenBN scales, biases added
+static std::string load_fused_down(spe_ctx* ctx, WeightSource& ws, const std::string& p, int planes, int inplanes, GemmW* g) {
+  const int N = planes * 4, K = planes + inplanes;
+  const HostTensor* w3 = ws.get(p + ".conv3.weight", {N, planes, 1, 1});
+  const HostTensor* wd = ws.get(p + ".downsample.0.weight", {N, inplanes, 1, 1});
+  std::vector<float> s3, b3, sd, bd;
+  if (!w3 || !wd || !bn_fold_host(ws, p + ".bn3", N, &s3, &b3) || !bn_fold_host(ws, p + ".downsample.1", N, &sd, &bd))
+    return ws.missing;
+  std::vector<float> w(static_cast<size_t>(N) * K), bias(N);
+  for (int n = 0; n < N; ++n) {
+    float* row = w.data() + static_cast<size_t>(n) * K;
+    for (int k = 0; k < planes; ++k) row[k] = s3[n] * w3->data[static_cast<size_t>(n) * planes + k];
+    for (int k = 0; k < inplanes; ++k) row[planes + k] = sd[n] * wd->data[static_cast<size_t>(n) * inplanes + k];
+    bias[n] = b3[n] + bd[n];
+  }
+  TRY_S(upload_gemm_w(ctx, w, N, K, g, false, true));
+  TRY_S(upload_f32(ctx, bias.data(), N, &g->bias));
+  return "";
+}
+
 static std::string load_conv_bn(spe_ctx* ctx, WeightSource& ws, const std::string& conv, const std::string& bn,
                                 int Cout, int Cin, int R, GemmW* g, int Kpad = 0) {
   const HostTensor* w = ws.get(conv + ".weight", {Cout, Cin, R, R});
@@ -604,8 +653,10 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(load_conv_bn(ctx, ws, p + ".conv1", p + ".bn1", bk.planes, inplanes, 1, &bk.c1));
       TRY_S(load_conv_bn(ctx, ws, p + ".conv2", p + ".bn2", bk.planes, bk.planes, 3, &bk.c2));
       TRY_S(load_conv_bn(ctx, ws, p + ".conv3", p + ".bn3", bk.planes * 4, bk.planes, 1, &bk.c3));
-      if (bk.has_down)
+      if (bk.has_down) {
         TRY_S(load_conv_bn(ctx, ws, p + ".downsample.0", p + ".downsample.1", bk.planes * 4, inplanes, 1, &bk.down));
+        if (ctx->fuse_down) TRY_S(load_fused_down(ctx, ws, p, bk.planes, inplanes, &bk.c3d));
+      }
       inplanes = bk.planes * 4;
       ctx->blocks.push_back(bk);
     }
@@ -909,6 +960,43 @@ struct Fwd {
     return "";
   }
 
+  // calibrate_layer for a GEMM over two concatenated operand sources (GemmDesc::A2): columns [0, C1) are measured on
+  // A1 [rows1, C1], columns [C1, C1 + C2) on A2 [rows2, C2] (for a stride-2 source the mean is taken over every input
+  // pixel, not only the sampled ones: second order, like the zero padding of the 3x3 convolutions)
+  std::string calibrate_two(const void* A1, long long rows1, int C1, const void* A2, long long rows2, int C2, const GemmW& w) {
+    if (!ctx->calibrating || w.w32 == nullptr || rows1 <= 0 || rows2 <= 0) return "";
+    if (C1 + C2 > 4096) return "calibration: more than 4096 input channels";
+    float* cs = ctx->colsum;
+    float* cs_mma = ctx->colsum + 4096;
+    constexpr int kColsumBlocks = 256;
+    float* part = ctx->colsum + 8192;
+    float* part_mma = part + static_cast<long long>(kColsumBlocks) * 4096;
+    const void* src[2] = {A1, A2};
+    const long long rows[2] = {rows1, rows2};
+    const int C[2] = {C1, C2};
+    for (int i = 0; i < 2; ++i) {
+      const unsigned blocks = static_cast<unsigned>(rows[i] < kColsumBlocks ? rows[i] : kColsumBlocks);
+      float* o = cs + (i ? C1 : 0);
+      float* om = cs_mma + (i ? C1 : 0);
+      if (dt == kTF32) colsum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(src[i]), rows[i], C[i], C[i], part, part_mma);
+      else colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src[i]), rows[i], C[i], C[i], part, part_mma);
+      colsum_reduce_kernel<<<(C[i] + 255) / 256, 256, 0, st>>>(part, part_mma, static_cast<int>(blocks), C[i], o, om);
+      if (i == 1 && rows2 != rows1)
+        scale_pair_kernel<<<(C2 + 255) / 256, 256, 0, st>>>(o, om, C2, static_cast<float>(rows1) / static_cast<float>(rows2));
+    }
+    const unsigned cgrid = static_cast<unsigned>((w.N + 7) / 8);
+    const float inv = 1.0f / static_cast<float>(rows1);
+    if (dt == kTF32)
+      bias_correction_kernel<float><<<cgrid, 256, 0, st>>>(w.w32, static_cast<const float*>(w.w), cs, cs_mma, inv, w.N, w.K, C1 + C2,
+                                                           w.scale, w.bias, w.applied, w.addend, w.addend_rows, w.addend_ld);
+    else
+      bias_correction_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>(w.w32, static_cast<const __nv_bfloat16*>(w.w), cs, cs_mma, inv,
+                                                                   w.N, w.K, C1 + C2, w.scale, w.bias, w.applied, w.addend,
+                                                                   w.addend_rows, w.addend_ld);
+    SPE_CUDA_TRY(cudaGetLastError());
+    return "";
+  }
+
   // out[M, N] = act(scale * A W^T + bias (+ residual))
   std::string gemm(const void* A, long long M, const GemmW& w, void* out, int out_ld, bool relu,
                    const void* residual = nullptr, int res_ld = 0, int res_mod = 0, int res_f32 = 0,
@@ -998,6 +1086,21 @@ static std::string run_bottleneck(spe_ctx* ctx, Fwd& f, const Bottleneck& bk, co
     TRY_S(f.conv3x3(ctx->T1, H, bk.planes, bk.c2, ctx->T2, bk.planes, true));
   } else {
     TRY_S(f.conv(ctx->T1, H, bk.planes, 3, 2, bk.c2, ctx->T2, bk.planes, true));   // 3x3 / stride 2
+  }
+  if (bk.has_down && bk.c3d.w != nullptr && !ctx->taps_enabled) {
+    // conv3 and the downsample branch as one GEMM over [T2 | cur sampled at the stride] (see Bottleneck::c3d)
+    TRY_S(f.calibrate_two(ctx->T2, Mout, bk.planes, cur, Min, bk.inplanes, bk.c3d));
+    GemmDesc d;
+    d.mode = 0;
+    d.A = ctx->T2; d.M = Mout; d.K = bk.planes; d.lda = bk.planes;
+    d.A2 = cur; d.K2 = bk.inplanes; d.lda2 = bk.inplanes;
+    d.a2_stride = bk.stride; d.a2_NB = f.B; d.a2_H = H; d.a2_W = H;
+    d.Wt = bk.c3d.w; d.N = bk.c3d.N;
+    d.bias = bk.c3d.bias;
+    d.relu = 1;
+    d.out = nxt; d.out_ld = bk.planes * 4;
+    d.round_out = exact_stream_on(ctx) ? 0 : 1;
+    return launch_gemm(f.dt, d, ctx->num_sms, f.st);
   }
   const void* identity = cur;
   if (bk.has_down) {

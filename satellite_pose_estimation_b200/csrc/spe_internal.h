@@ -39,6 +39,13 @@ struct GemmDesc {
   int round_out = 1;              // fp32 storage: round the result to TF32 (its consumer is a kind::tf32 MMA)
   int x3 = 0;                     // error-compensated 3xTF32: Wt is [N, 2K] = [W_hi | W_lo]; fp32-grade accuracy
   int out_f32 = 0;                // bf16 storage only: `out` is fp32 [M, out_ld] (values rounded to TF32)
+  // mode 0 only: a SECOND operand source concatenated along K -- out = [A | A2] . Wt^T with Wt [N, K + K2].  A2 is
+  // either a plain [M, K2] matrix (a2_stride = 1) or the 1x1 / stride-2 sampling of an NHWC activation
+  // [a2_NB, a2_H, a2_W, K2] (a2_stride = 2: output pixel (h, w) reads input pixel (2h, 2w)).  This is how a residual
+  // block's downsample branch rides in its conv3 GEMM (model.cu: Bottleneck::c3d).
+  const void* A2 = nullptr;
+  int K2 = 0, lda2 = 0;
+  int a2_stride = 1, a2_NB = 0, a2_H = 0, a2_W = 0;
 };
 
 // returns empty string on success, else an error message

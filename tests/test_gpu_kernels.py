@@ -214,3 +214,29 @@ def test_gemm_rejects_bad_shapes(lib, cuda_dev):
     a = torch.zeros(8, 48, device=cuda_dev)
     assert lib.spe_debug_gemm(0, _p(a), _p(a), 8, 8, 48, None, None, None, 0, 0, _p(a), None) != 0
     assert b"gemm" in lib.spe_global_last_error()
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+@pytest.mark.parametrize("NB,H,K1,K2,N,stride", [(3, 56, 64, 64, 256, 1), (5, 56, 128, 256, 512, 2), (7, 28, 256, 512, 1024, 2),
+                                                   (2, 13, 64, 128, 128, 2)])
+def test_gemm_with_a_second_operand_source(lib, cuda_dev, dt, NB, H, K1, K2, N, stride):
+    """The first block of a ResNet layer: conv3 and the (strided) 1x1 downsample branch as ONE GEMM over the concatenated
+    operand [t | x sampled at the stride] (GemmDesc::A2, model.cu Bottleneck::c3d).  Reference: the two matrix products
+    in fp64 on the same (TF32- / bf16-rounded) operands."""
+    torch.manual_seed(NB * 100 + H)
+    Ho = (H - 1) // stride + 1
+    M = NB * Ho * Ho
+    tdt = torch.float32 if dt == 0 else torch.bfloat16
+    rnd = (lambda t: _rna_tf32(t)) if dt == 0 else (lambda t: t.to(torch.bfloat16))
+    t = rnd(torch.randn(M, K1, device=cuda_dev))
+    x = rnd(torch.randn(NB, H, H, K2, device=cuda_dev))
+    w = rnd(torch.randn(N, K1 + K2, device=cuda_dev) * 0.05)
+    bias = torch.randn(N, device=cuda_dev)
+    out = torch.full((M, N), float("nan"), device=cuda_dev, dtype=tdt)
+    assert lib.spe_debug_gemm2(dt, _p(t), K1, _p(x), K2, stride, NB, H, H, _p(w), M, N, _p(bias), 1, _p(out), None) == 0, \
+        lib.spe_global_last_error()
+    torch.cuda.synchronize()
+    xs = x[:, ::stride, ::stride, :].reshape(M, K2)
+    ref = torch.relu(t.double() @ w[:, :K1].double().T + xs.double() @ w[:, K1:].double().T + bias.double())
+    assert not torch.isnan(out.float()).any()
+    assert _rel(out.float(), ref) < (2e-3 if dt == 0 else 8e-3)
