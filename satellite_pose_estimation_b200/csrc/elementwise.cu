@@ -301,7 +301,20 @@ layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, c
     }
     vstore(out + row * 256 + c, r);
   }
-  if (gamma2 == nullptr) return;
+  if (gamma2 == nullptr) {
+    if (out2 != nullptr) {
+      // second copy of the SAME rows rounded to the storage precision of a tensor-core operand (fp32 storage: TF32)
+      // while `out` stays exact: operand and residual of the layer that follows
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        Vec<T> r;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) r.set(e, x[i * VN + e]);
+        vstore(out2 + row * 256 + (i * 32 + lane) * VN, r);
+      }
+    }
+    return;
+  }
   // chained second normalisation of the row just written (decoder: norm3 followed by the shared decoder norm,
   // RV/models/transformer.py:116-118), stored unrounded -- one launch instead of two, same values
   float s2 = 0.f;
@@ -404,24 +417,33 @@ std::string launch_upsample2x(Dtype dt, const void* in, int NB, int H, int W, in
 // so the nine 1024 -> 256 tap matrices are applied to the 14 x 14 map (one GEMM, M = 196 per image instead of 784:
 // a quarter of the multiply-adds) and this kernel gathers:  out[p, o] = sum over the taps that fall inside the 28 x 28
 // map (zero padding) of the bilinear interpolation of Y_tap at p + tap.
-// One CTA = one image x kTapCh output channels; its slice of Y ([196 positions][9 taps][kTapCh], 112 KB with padding) is
-// staged in shared memory once.  One THREAD = one output position x all kTapCh channels: the interpolation indices and
-// weights of the three tap rows / three tap columns are computed once per position (the first version did it per
-// channel and per tap: 269 us at B = 64, bound by its own index arithmetic -- profiles/r02b_launches_summary.md), the
-// shared-memory reads are 16-byte (four channels), and a position's row is padded to kTapStride words so that the
-// quarter-warps of an LDS.128 (eight different source positions at most) fall on different banks.
-constexpr int kTapCh = 16;
-constexpr int kTapStride = 9 * kTapCh + 2;            // 146 words: 2 CTAs of 196 positions still fit one SM (2 x 112 KB)
+// One CTA = one image x kTapCh output channels; its slice of Y ([H*W positions][9 taps][kTapCh]) is staged in shared
+// memory once.  The bilinear interpolation is separable, and the tap index is (r, q) = (row shift, column shift), so the
+// gather runs in two passes through shared memory:
+//   columns:  Z[y, j, r] = sum_q  sum_{two source columns x of upsampled column j + q - 1}  cw * Y[y, x, (r, q)]
+//   rows:     out[i, j]  = sum_r  sum_{two source rows y of upsampled row i + r - 1}        rw * Z[y, j, r]
+// 6 + 6 multiply-adds per output element and channel instead of 36 -- and, what bounds this kernel, 2.4 x fewer
+// shared-memory reads.  History (B = 64, profiles/r02*_launches_summary.md): v1 recomputed the interpolation indices per
+// channel and tap, 269 us (the top launch of the step); v2, one thread per output position with 16 channels in
+// registers, 126 us at its shared-memory-bandwidth floor; this is v3.  Interpolation tables (source index pair +
+// weights of every upsampled row / column, zero weights outside the map = the convolution's zero padding) are built
+// once per CTA.  Z rows are padded to kZStride words so the eight lanes of an LDS.128 fall on different banks.
+constexpr int kTapCh = 8;
+constexpr int kYStride = 9 * kTapCh;                  // words per source position
+constexpr int kZStride = 3 * kTapCh + 4;              // words per (y, j): three tap rows + padding
 template <typename TO>
 __global__ void __launch_bounds__(256, 2)
 upsample_tapsum_kernel(const float* __restrict__ Y, int H, int W, int Cout, TO* __restrict__ out, int out_ld, int round_tf32) {
   pdl_wait();
   pdl_launch();
-  extern __shared__ float sy[];                       // [H*W][kTapStride]
+  extern __shared__ __align__(16) float sy[];         // [H*W][kYStride] | Z [H][2W][kZStride] | tables
   const int b = blockIdx.x, c0 = blockIdx.y * kTapCh;
   const int HW = H * W, Ho = 2 * H, Wo = 2 * W;
+  float* sz = sy + HW * kYStride;
+  int* tab_i = reinterpret_cast<int*>(sz + H * Wo * kZStride);    // [Wo + 2] column source index, then [Ho + 2] row
+  float* tab_w = reinterpret_cast<float*>(tab_i + (Wo + 2) + (Ho + 2));   // weight of the SECOND source (first = 1 - w), or -1 = outside
   const float* yb = Y + static_cast<long long>(b) * HW * 9 * Cout;
-  // eight independent 16-byte loads in flight per thread (the loop-carried form waited out one DRAM latency per element)
+  // eight independent 16-byte loads in flight per thread
   const int nvec = HW * 9 * (kTapCh / 4);
   for (int u0 = threadIdx.x; u0 < nvec; u0 += 8 * blockDim.x) {
     float4 v[8];
@@ -434,56 +456,69 @@ upsample_tapsum_kernel(const float* __restrict__ Y, int H, int W, int Cout, TO* 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int u = u0 + k * blockDim.x;
-      if (u < nvec) {
-        const int seg = u / (kTapCh / 4), v4 = u % (kTapCh / 4);     // seg = position * 9 + tap
-        float* d = sy + (seg / 9) * kTapStride + (seg % 9) * kTapCh + v4 * 4;
-        *reinterpret_cast<float2*>(d) = make_float2(v[k].x, v[k].y);       // rows are 8-byte aligned only (146 words)
-        *reinterpret_cast<float2*>(d + 2) = make_float2(v[k].z, v[k].w);
-      }
+      if (u < nvec) *reinterpret_cast<float4*>(sy + (u / (kTapCh / 4)) * kTapCh + (u % (kTapCh / 4)) * 4) = v[k];
     }
   }
+  // interpolation tables: entry t <-> upsampled coordinate t - 1 (nn.UpsamplingBilinear2d: align_corners=True)
+  for (int t = threadIdx.x; t < (Wo + 2) + (Ho + 2); t += blockDim.x) {
+    const bool col = t < Wo + 2;
+    const int u = (col ? t : t - (Wo + 2)) - 1, n_out = col ? Wo : Ho, n_in = col ? W : H;
+    if (u < 0 || u >= n_out) { tab_i[t] = 0; tab_w[t] = -1.f; continue; }
+    const float f = (static_cast<float>(n_in - 1) / static_cast<float>(n_out - 1)) * u;
+    const int i0 = static_cast<int>(f);
+    tab_i[t] = i0;
+    tab_w[t] = i0 < n_in - 1 ? f - i0 : 0.f;          // at the last source the second neighbour is the first again
+  }
   __syncthreads();
-  const float sh = static_cast<float>(H - 1) / static_cast<float>(Ho - 1);
-  const float sw = static_cast<float>(W - 1) / static_cast<float>(Wo - 1);
+  // ---- columns
+  for (int it = threadIdx.x; it < H * Wo * 3; it += blockDim.x) {
+    const int r = it % 3, yj = it / 3, j = yj % Wo, y = yj / Wo;
+    float acc[kTapCh];
+#pragma unroll
+    for (int c = 0; c < kTapCh; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float w1 = tab_w[j + q];
+      if (w1 < 0.f) continue;                         // outside the 2W-wide map: zero padding
+      const int x0 = tab_i[j + q];
+      const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+      const float w0 = 1.f - w1;
+      const float* s0 = sy + (y * W + x0) * kYStride + (r * 3 + q) * kTapCh;
+      const float* s1 = sy + (y * W + x1) * kYStride + (r * 3 + q) * kTapCh;
+#pragma unroll
+      for (int c = 0; c < kTapCh; c += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(s0 + c), bb = *reinterpret_cast<const float4*>(s1 + c);
+        acc[c] += w0 * a.x + w1 * bb.x; acc[c + 1] += w0 * a.y + w1 * bb.y;
+        acc[c + 2] += w0 * a.z + w1 * bb.z; acc[c + 3] += w0 * a.w + w1 * bb.w;
+      }
+    }
+    float* z = sz + yj * kZStride + r * kTapCh;
+#pragma unroll
+    for (int c = 0; c < kTapCh; c += 4) *reinterpret_cast<float4*>(z + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+  }
+  __syncthreads();
+  // ---- rows
+  const int* rtab_i = tab_i + (Wo + 2);
+  const float* rtab_w = tab_w + (Wo + 2);
   for (int p = threadIdx.x; p < Ho * Wo; p += blockDim.x) {
     const int i = p / Wo, j = p % Wo;
-    // the three tap rows / columns of this output: source index pair and the interpolation weight (0 = outside the
-    // 2H x 2W map, the convolution's zero padding)
-    int ro[3][2], co[3][2];
-    float rw[3][2], cw[3][2];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int ii = i + r - 1, jj = j + r - 1;
-      const bool vi = ii >= 0 && ii < Ho, vj = jj >= 0 && jj < Wo;
-      const float fy = sh * (vi ? ii : 0), fx = sw * (vj ? jj : 0);
-      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-      ro[r][0] = y0 * W; ro[r][1] = (y0 + (y0 < H - 1 ? 1 : 0)) * W;
-      co[r][0] = x0; co[r][1] = x0 + (x0 < W - 1 ? 1 : 0);
-      rw[r][1] = vi ? fy - y0 : 0.f; rw[r][0] = vi ? 1.f - (fy - y0) : 0.f;
-      cw[r][1] = vj ? fx - x0 : 0.f; cw[r][0] = vj ? 1.f - (fx - x0) : 0.f;
-    }
     float acc[kTapCh];
 #pragma unroll
     for (int c = 0; c < kTapCh; ++c) acc[c] = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
+      const float w1 = rtab_w[i + r];
+      if (w1 < 0.f) continue;
+      const int y0 = rtab_i[i + r];
+      const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+      const float w0 = 1.f - w1;
+      const float* s0 = sz + (y0 * Wo + j) * kZStride + r * kTapCh;
+      const float* s1 = sz + (y1 * Wo + j) * kZStride + r * kTapCh;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int t = r * 3 + q;
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float w = rw[r][a] * cw[q][e];
-            const float* src = sy + (ro[r][a] + co[q][e]) * kTapStride + t * kTapCh;
-#pragma unroll
-            for (int c = 0; c < kTapCh; c += 2) {
-              const float2 v = *reinterpret_cast<const float2*>(src + c);
-              acc[c] = fmaf(w, v.x, acc[c]);
-              acc[c + 1] = fmaf(w, v.y, acc[c + 1]);
-            }
-          }
-        }
+      for (int c = 0; c < kTapCh; c += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(s0 + c), bb = *reinterpret_cast<const float4*>(s1 + c);
+        acc[c] += w0 * a.x + w1 * bb.x; acc[c + 1] += w0 * a.y + w1 * bb.y;
+        acc[c + 2] += w0 * a.z + w1 * bb.z; acc[c + 3] += w0 * a.w + w1 * bb.w;
       }
     }
     const long long o = (static_cast<long long>(b) * Ho * Wo + p) * out_ld + c0;
@@ -502,14 +537,11 @@ upsample_tapsum_kernel(const float* __restrict__ Y, int H, int W, int Cout, TO* 
       }
     } else {
       __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out) + o;
+      uint4 o8;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
 #pragma unroll
-      for (int c = 0; c < kTapCh; c += 8) {
-        uint4 o8;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o8);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(acc[c + 2 * u], acc[c + 2 * u + 1]);
-        *reinterpret_cast<uint4*>(op + c) = o8;
-      }
+      for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(acc[2 * u], acc[2 * u + 1]);
+      *reinterpret_cast<uint4*>(op) = o8;
     }
   }
 }
@@ -517,8 +549,9 @@ upsample_tapsum_kernel(const float* __restrict__ Y, int H, int W, int Cout, TO* 
 std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int W, int Cout, void* out, int out_ld,
                                    cudaStream_t s) {
   if (NB <= 0) return "";
-  if (Cout % kTapCh) return "upsample_tapsum: output channels must be a multiple of 16";
-  const size_t smem = static_cast<size_t>(H) * W * kTapStride * sizeof(float);
+  if (Cout % kTapCh) return "upsample_tapsum: output channels must be a multiple of 8";
+  const size_t smem = (static_cast<size_t>(H) * W * kYStride + static_cast<size_t>(H) * 2 * W * kZStride) * sizeof(float) +
+                      static_cast<size_t>(2 * W + 2 + 2 * H + 2) * 8;
   if (smem > 200 * 1024) return "upsample_tapsum: feature map too large for the shared-memory slice";
   ProfScope ps(kFamElementwise, s);
   if (dt == kTF32) {

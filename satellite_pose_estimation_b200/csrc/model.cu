@@ -347,6 +347,10 @@ struct spe_ctx {
   // GEMM branch that a bias cannot absorb.
   // error-compensated 3xTF32 for the decoder + head GEMMs / for the cross-attention K/V projection (fp32 storage only)
   bool dec_x3 = getenv("SPE_DEC_X3") ? atoi(getenv("SPE_DEC_X3")) != 0 : true;
+  // ... and separately for the decoder's feed-forward pair (linear1 / linear2: 0.28 of the decoder's GEMM time).  With
+  // plain TF32 there, norm2 writes a second, TF32-ROUNDED copy of its output as linear1's operand (the exact copy
+  // stays the residual), so the tensor core's truncation adds no bias.  SPE_DEC_FFN_X3.
+  bool dec_ffn_x3 = getenv("SPE_DEC_FFN_X3") ? atoi(getenv("SPE_DEC_FFN_X3")) != 0 : true;
   // K/V projection: -1 (default) = 3xTF32 until the context is calibrated, plain TF32 afterwards -- with the rounding
   // bias folded into the addend the plain product is as accurate as the compensated one (measured: 0.12 vs 0.14 px at
   // S = 1748, whole-chain keypoints 0.27 vs 0.49 px) and a third of the tensor work (213 -> ~75 us at B = 64);
@@ -770,8 +774,8 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(make_addend(ctx, nullptr, T, E, w->data + 2 * E * E, bb->data + 2 * E, E, ctx->ca_kv_addend,
                         LD * 2 * E, i * 2 * E + E));
       TRY_S(load_linear(ctx, ws, p + ".multihead_attn.out_proj", E, E, &L.ca_out, ctx->dec_x3));
-      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1, ctx->dec_x3));
-      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2, ctx->dec_x3));
+      TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1, ctx->dec_x3 && ctx->dec_ffn_x3));
+      TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2, ctx->dec_x3 && ctx->dec_ffn_x3));
       TRY_S(load_vec(ctx, ws, p + ".norm1.weight", E, &L.n1g));
       TRY_S(load_vec(ctx, ws, p + ".norm1.bias", E, &L.n1b));
       TRY_S(load_vec(ctx, ws, p + ".norm2.weight", E, &L.n2g));
@@ -1367,8 +1371,11 @@ static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, fl
                  Ti, ex, 0, 0, folded));
     TRY_S(f.gemm(ctx->DATT, MQ, L.ca_out, ctx->TGT2, 256, false, folded ? ctx->dec0_tgt : ctx->TGT, 256, folded ? Q : 0, 0,
                  true, 0, true));
-    TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT, ex));
-    TRY_S(f.gemm(ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
+    // plain-TF32 feed-forward inside a 3xTF32 decoder: linear1 reads a rounded copy of norm2's output
+    const bool ffn_plain = ex && !L.ff1.x3;
+    if (ffn_plain) TRY_S(launch_layernorm(f.dt, ctx->TGT2, L.n2g, L.n2b, MQ, 256, ctx->TGT, st, ex, nullptr, nullptr, ctx->DQ));
+    else TRY_S(f.ln(ctx->TGT2, L.n2g, L.n2b, MQ, ctx->TGT, ex));
+    TRY_S(f.gemm(ffn_plain ? ctx->DQ : ctx->TGT, MQ, L.ff1, ctx->DHID, c.dim_feedforward, true));
     TRY_S(f.gemm(ctx->DHID, MQ, L.ff2, ctx->TGT2, 256, false, ctx->TGT, 256, 0, 0, true, 0, true));
     // norm3, and the decoder's shared output norm of it (return_intermediate), in one launch
     TRY_S(launch_layernorm(f.dt, ctx->TGT2, L.n3g, L.n3b, MQ, 256, ctx->TGT, st, ex, ctx->dn_g, ctx->dn_b,
