@@ -50,7 +50,11 @@ typedef struct {
   int hidden_dim;       /* must be 256                                                   (--hidden_dim)      */
   int nheads;           /* must be 8 (head_dim 32)                                       (--nheads)          */
   int dim_feedforward;  /*                                                               (--dim_feedforward) */
-  int backbone;         /* 0: ResNet-50 stride-8 fusion neck (Backbone8s), 1: ResNet-50 layer3 stride 16     */
+  int backbone;         /* 0: ResNet-50 stride-8 fusion neck (Backbone8s), 1: ResNet-50 layer3 stride 16,
+                         * 2: the SA drop's RT-DETR predictor (PResNet-50-vd + HybridEncoder + RTDETRTransformer,
+                         *    SA/configs/rtdetr_speed/rtdetr_r50vd_6x_speed_kl_*.yml): input_size = eval_spatial_size
+                         *    (256), num_queries 30, enc_layers 1 (AIFI), dec_layers 3, dim_feedforward 1024,
+                         *    precision 0, has_sigma 1; weights in the SA state_dict layout                        */
   int precision;        /* 0: fp32 storage + TF32 tensor cores, 1: bf16 storage + BF16 tensor cores          */
   int has_sigma;        /* 1: self-assessment variant, sigma_embed.* head -> pred_sigmas                     */
   int max_batch;        /* workspace is sized for this many images per call                                  */
@@ -113,6 +117,18 @@ int spe_crop_resize_norm(spe_ctx* ctx, const uint8_t* frames_dev, int H, int W, 
  * aux_logits [(L-1),B,Q,12] / aux_points [(L-1),B,Q,2] or NULL (the 'aux_outputs' list). */
 int spe_forward(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev, float* points_dev,
                 float* log_sigma_dev, float* aux_logits_dev, float* aux_points_dev, void* stream);
+
+/* replaces: RTDETR.forward in eval mode                      (SA/src/zoo/rtdetr/rtdetr.py:36-52, rtdetr_decoder.py:686-751)
+ * for a ctx created with backbone = 2 (spe_forward serves the same ctx when only the last layer is wanted).
+ * logits [B,Q,12] 'pred_logits', points [B,Q,2] 'pred_pts', log_sigma [B,Q,2] 'pred_sigmas' (or NULL);
+ * the 'aux_outputs' list, each or all NULL: aux_logits [L,B,Q,12] / aux_points [L,B,Q,2] = decoder layers 0..L-2 followed
+ * by the encoder's top-k proposals (enc_topk_logits / enc_topk_bboxes), aux_log_sigma [(L-1),B,Q,2];
+ * topk_idx [B,Q] int32 or NULL receives the selected anchor of every query (torch.topk order, :646-648);
+ * topk_override [B,Q] int32 or NULL replaces the selection (parity tests: the selection is a discontinuous function of
+ * scores that differ by rounding between any two implementations).  Runs eagerly (no graph replay). */
+int spe_forward_sa(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev, float* points_dev, float* log_sigma_dev,
+                   float* aux_logits_dev, float* aux_points_dev, float* aux_log_sigma_dev, int32_t* topk_idx_dev,
+                   const int32_t* topk_override_dev, void* stream);
 
 /* Optional accuracy step with no counterpart in the reference (whose fp32 weights need none).  The tensor cores read
  * TF32 / BF16 weights; what the rounded weights lose, (W - round(W)) . x, is to first order the same for every image:

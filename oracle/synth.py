@@ -363,3 +363,102 @@ def make_multi_predictions(n, num_models=5, Q=40, seed=7, noise_px=1.0, outlier_
                 logits[m, i, s, :] = np.log((1 - top) / 11)
                 logits[m, i, s, 11] = np.log(top)
     return {"logits": logits, "points": points, "boxes": boxes, "q_gt": q_gt, "t_gt": t_gt}
+
+
+# -------------------------------------------------------------------------------------------------------------
+# SA drop: RT-DETR keypoint predictor (oracle/sa_model_ref.py) -- state_dict of
+# configs/rtdetr_speed/rtdetr_r50vd_6x_speed_kl_1.yml (636 tensors, 31.3 M values), seeded
+# -------------------------------------------------------------------------------------------------------------
+def _bn2d(rng, sd, prefix, c, gamma_scale=1.0):
+    _bn(rng, sd, prefix, c, gamma_scale)
+    sd[prefix + ".num_batches_tracked"] = np.zeros((), dtype=np.int64)
+
+
+def _conv_norm(rng, sd, prefix, cout, cin, k, gain=1.0, gamma_scale=1.0):
+    sd[prefix + ".conv.weight"] = _conv(rng, cout, cin, k, gain)
+    _bn2d(rng, sd, prefix + ".norm", cout, gamma_scale)
+
+
+def _mlp(rng, sd, prefix, dims, last_gain=1.0):
+    for i, (i_f, o_f) in enumerate(zip(dims[:-1], dims[1:])):
+        _linear(rng, sd, f"{prefix}.layers.{i}", o_f, i_f)
+        if i == len(dims) - 2:
+            sd[f"{prefix}.layers.{i}.weight"] *= np.float32(last_gain)
+
+
+def make_sa_state_dict(cfg=None, seed=0):
+    """Random weights in the SA reference's ``state_dict`` layout.  Every tensor is non-degenerate on purpose: the
+    reference's own init zeroes the sampling-offset / attention-weight projections and the last layer of every keypoint
+    head (SA/src/zoo/rtdetr/rtdetr_decoder.py:70-92, :487-497), which would hide a wrong kernel behind zeros."""
+    from .sa_model_ref import SaCfg, PRESNET50_BLOCKS, STAGE_PLANES
+    cfg = cfg or SaCfg()
+    rng = np.random.default_rng(seed)
+    sd = {"temper_param": rng.standard_normal(1).astype(np.float32)}
+    b = "backbone"
+    _conv_norm(rng, sd, b + ".conv1.conv1_1", 32, 3, 3)
+    _conv_norm(rng, sd, b + ".conv1.conv1_2", 32, 32, 3)
+    _conv_norm(rng, sd, b + ".conv1.conv1_3", 64, 32, 3)
+    cin = 64
+    for si, (nb, planes) in enumerate(zip(PRESNET50_BLOCKS, STAGE_PLANES)):
+        for bi in range(nb):
+            p = f"{b}.res_layers.{si}.blocks.{bi}"
+            _conv_norm(rng, sd, p + ".branch2a", planes, cin, 1)
+            _conv_norm(rng, sd, p + ".branch2b", planes, planes, 3)
+            _conv_norm(rng, sd, p + ".branch2c", planes * 4, planes, 1, gamma_scale=0.5)
+            if bi == 0:
+                _conv_norm(rng, sd, p + (".short" if si == 0 else ".short.conv"), planes * 4, cin, 1, gamma_scale=0.5)
+                cin = planes * 4
+    e, E = "encoder", cfg.hidden_dim
+    for i, c in enumerate((512, 1024, 2048)):
+        sd[f"{e}.input_proj.{i}.0.weight"] = _conv(rng, E, c, 1, gain=0.7)
+        _bn2d(rng, sd, f"{e}.input_proj.{i}.1", E)
+    sd[e + ".encoder_fusion_input.weight"] = _conv(rng, 256, 3 * E, 1)        # defined, never used by forward
+    p = e + ".encoder.0.layers.0"
+    _mha(rng, sd, p + ".self_attn", E)
+    _linear(rng, sd, p + ".linear1", cfg.enc_ff, E)
+    _linear(rng, sd, p + ".linear2", E, cfg.enc_ff)
+    _ln(rng, sd, p + ".norm1", E)
+    _ln(rng, sd, p + ".norm2", E)
+    for i in range(2):
+        _conv_norm(rng, sd, f"{e}.lateral_convs.{i}", E, E, 1)
+    for grp in ("fpn_blocks", "pan_blocks"):
+        for i in range(2):
+            p = f"{e}.{grp}.{i}"
+            h = cfg.csp_hidden
+            _conv_norm(rng, sd, p + ".conv1", h, 2 * E, 1)
+            _conv_norm(rng, sd, p + ".conv2", h, 2 * E, 1)
+            _conv_norm(rng, sd, p + ".bottlenecks.0.conv1", h, h, 3, gain=0.8)
+            _conv_norm(rng, sd, p + ".bottlenecks.0.conv2", h, h, 1, gain=0.6)
+            _conv_norm(rng, sd, p + ".conv3", E, h, 1)
+    d = "decoder"
+    for i in range(cfg.num_levels):
+        sd[f"{d}.input_proj.{i}.conv.weight"] = _conv(rng, E, E, 1, gain=0.7)
+        _bn2d(rng, sd, f"{d}.input_proj.{i}.norm", E)
+    nl_np = cfg.nheads * cfg.num_levels * cfg.num_points
+    for i in range(cfg.dec_layers):
+        p = f"{d}.decoder.layers.{i}"
+        _mha(rng, sd, p + ".self_attn", E)
+        _ln(rng, sd, p + ".norm1", E)
+        _linear(rng, sd, p + ".cross_attn.sampling_offsets", nl_np * 2, E)
+        # offsets of a few cells around the reference point, like the reference's grid_init bias (:72-84)
+        sd[p + ".cross_attn.sampling_offsets.bias"] = rng.uniform(-3.0, 3.0, nl_np * 2).astype(np.float32)
+        _linear(rng, sd, p + ".cross_attn.attention_weights", nl_np, E)
+        _linear(rng, sd, p + ".cross_attn.value_proj", E, E)
+        _linear(rng, sd, p + ".cross_attn.output_proj", E, E)
+        _ln(rng, sd, p + ".norm2", E)
+        _linear(rng, sd, p + ".linear1", cfg.dec_ff, E)
+        _linear(rng, sd, p + ".linear2", E, cfg.dec_ff)
+        _ln(rng, sd, p + ".norm3", E)
+    for i in range(cfg.dec_layers):
+        _mlp(rng, sd, f"{d}.decoder.sigma_embed.{i}", (E, E, E, 1))
+    _mlp(rng, sd, d + ".query_pos_head", (2, 2 * E, E))
+    _linear(rng, sd, d + ".enc_output.0", E, E)
+    _ln(rng, sd, d + ".enc_output.1", E)
+    _linear(rng, sd, d + ".enc_score_head", cfg.num_classes + 1, E)
+    sd[d + ".enc_score_head.weight"] *= np.float32(4.0)          # spread the anchor scores: robust top-k selection
+    _mlp(rng, sd, d + ".enc_bbox_head", (E, E, E, 2), last_gain=0.5)
+    for i in range(cfg.dec_layers):
+        _linear(rng, sd, f"{d}.dec_score_head.{i}", cfg.num_classes + 1, E)
+    for i in range(cfg.dec_layers):
+        _mlp(rng, sd, f"{d}.dec_bbox_head.{i}", (E, E, E, 2), last_gain=0.5)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}

@@ -45,6 +45,7 @@ SYMBOLS = {
     "spe_jpeg_info": (_i, [_vp, _ll, _vp, _vp]),
     "spe_crop_resize_norm": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _i, _i, _vp, _vp]),
     "spe_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spe_forward_sa": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spe_calibrate": (_i, [_vp, _vp, _i, _vp]),
     "spe_is_calibrated": (_i, [_vp]),
     "spe_assign_pnp": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(SpePnpParams), _vp, _vp, _vp, _vp, _vp, _vp,

@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspe.so")
-SOURCES = ["gemm_tc.cu", "attention.cu", "attention_tc.cu", "ffn_tc.cu", "elementwise.cu", "heads.cu", "crop.cu", "jpeg.cu", "deform_attn.cu", "pnp.cu", "model.cu", "api.cu", "profile.cu"]
-HEADERS = ["spe_ptx.cuh", "spe_internal.h", "profile.h", os.path.join("..", "..", "include", "spe.h")]
+SOURCES = ["gemm_tc.cu", "attention.cu", "attention_tc.cu", "ffn_tc.cu", "elementwise.cu", "heads.cu", "crop.cu", "jpeg.cu", "deform_attn.cu", "sa_kernels.cu", "pnp.cu", "model.cu", "api.cu", "profile.cu"]
+HEADERS = ["spe_ptx.cuh", "spe_internal.h", "profile.h", "sa_model.inl", os.path.join("..", "..", "include", "spe.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -32,6 +32,9 @@ struct DeformParams {
   const float* ref;               // fused only: reference points [B, Lq, ref_levels, 2] (ref_levels = 1 or L)
   float* out;                     // [B, Lq, heads*32]
   int B, Lq, Lv, heads, L, P, ref_levels, fused;
+  // row strides in floats: value rows (default heads*32), offset / attention-logit rows per (image, query) (defaults
+  // heads*L*P*2 and heads*L*P) -- the SA forward reads all three straight out of wider GEMM outputs
+  long long value_ld, loc_ld, attn_ld;
   int h[kMaxLevels], w[kMaxLevels], start[kMaxLevels];
 };
 
@@ -47,8 +50,9 @@ ms_deform_attn_kernel(const DeformParams p) {
   const int b = warp_global / (p.heads * p.Lq);
   const int LP = p.L * p.P;
   const long long qh = (static_cast<long long>(b) * p.Lq + q) * p.heads + hd;
-  const float* loc = p.loc + qh * LP * 2;
-  const float* att = p.attn + qh * LP;
+  const long long bq = static_cast<long long>(b) * p.Lq + q;
+  const float* loc = p.loc + bq * p.loc_ld + static_cast<long long>(hd) * LP * 2;
+  const float* att = p.attn + bq * p.attn_ld + static_cast<long long>(hd) * LP;
 
   // attention weights of this (query, head): lanes hold one (level, point) each (LP <= 64 -> two per lane)
   float w0 = lane < LP ? att[lane] : -INFINITY, w1 = lane + 32 < LP ? att[lane + 32] : -INFINITY;
@@ -64,8 +68,8 @@ ms_deform_attn_kernel(const DeformParams p) {
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     w0 /= sum; w1 /= sum;
   }
-  const float* vb = p.value + static_cast<long long>(b) * p.Lv * p.heads * 32 + hd * 32 + lane;
-  const long long vrow = static_cast<long long>(p.heads) * 32;
+  const long long vrow = p.value_ld;
+  const float* vb = p.value + static_cast<long long>(b) * p.Lv * vrow + hd * 32 + lane;
   float acc = 0.f;
   for (int l = 0; l < p.L; ++l) {
     const int H = p.h[l], W = p.w[l];
@@ -168,13 +172,16 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t*
 
 std::string launch_ms_deform_attn(const float* value, const int* shapes_hw, int L, const float* loc, const float* attn,
                                   const float* ref, int ref_levels, int B, int Lq, int heads, int P, int fused,
-                                  float* out, cudaStream_t s) {
+                                  float* out, cudaStream_t s, long long value_ld, long long loc_ld, long long attn_ld) {
   if (B <= 0 || Lq <= 0) return "";
   if (L <= 0 || L > kMaxLevels || P <= 0 || L * P > kMaxLP) return "ms_deform_attn: levels x points outside [1, 64]";
   if (fused && (!ref || (ref_levels != 1 && ref_levels != L))) return "ms_deform_attn: fused mode needs reference points";
   DeformParams p{};
   p.value = value; p.loc = loc; p.attn = attn; p.ref = ref; p.out = out;
   p.B = B; p.Lq = Lq; p.heads = heads; p.L = L; p.P = P; p.ref_levels = ref_levels; p.fused = fused;
+  p.value_ld = value_ld > 0 ? value_ld : static_cast<long long>(heads) * 32;
+  p.loc_ld = loc_ld > 0 ? loc_ld : static_cast<long long>(heads) * L * P * 2;
+  p.attn_ld = attn_ld > 0 ? attn_ld : static_cast<long long>(heads) * L * P;
   int start = 0;
   for (int l = 0; l < L; ++l) {
     p.h[l] = shapes_hw[2 * l]; p.w[l] = shapes_hw[2 * l + 1]; p.start[l] = start;

@@ -1298,6 +1298,7 @@ static std::string launch_conv3(Dtype dt, const GemmDesc& d, int num_sms, cudaSt
   const int hrows = BM / Wp;
   const int dbl = 2 * hrows;
   if (dbl + 2 > 256) return "skip";
+  if (d.H < dbl) return "skip";   // maps smaller than one double-row tile (8 x 8 of the SA predictor): generic path
   const int need_rows = std::max(Wp * (dbl + 2), (hrows + 2) * Wp + 2 + BM);
   const uint32_t a_stage = (static_cast<uint32_t>(need_rows) * 128u + 1023u) & ~1023u;
   const int b_bytes = d.N * 128;

@@ -250,8 +250,11 @@ struct GraphEntry {
   long long launches[kNumFamilies] = {0, 0, 0, 0, 0, 0};
 };
 
+namespace spe { struct SaModel; }   // SA (RT-DETR) predictor: weights + workspace, sa_model.inl
+
 struct spe_ctx {
   spe_config cfg{};
+  spe::SaModel* sa = nullptr;   // cfg.backbone == 2
   int device = 0;
   int num_sms = 148;
   Dtype dt = kTF32;
@@ -621,8 +624,13 @@ static std::string load_mha_self(spe_ctx* ctx, WeightSource& ws, const std::stri
   return "";
 }
 
+std::string sa_load_weights(spe_ctx* ctx, WeightSource& ws);   // sa_model.inl
+std::string sa_alloc_workspace(spe_ctx* ctx);
+void sa_release(spe_ctx* ctx);
+
 std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
   const spe_config& c = ctx->cfg;
+  if (c.backbone == 2) return sa_load_weights(ctx, ws);
   const int E = 256, FF = c.dim_feedforward, Q = c.num_queries, T = ctx->tokens;
   const std::string b = "backbone.0.body";
   // ---- stem + layers
@@ -845,6 +853,9 @@ std::string alloc_workspace(spe_ctx* ctx) {
     return e;
   };
   auto A = [&](void** p, long long elems) { return AB(p, elems * es); };
+  if (c.backbone == 2) {
+    TRY_S(sa_alloc_workspace(ctx));
+  } else {
   TRY_S(A(&ctx->S0, B * h2 * h2 * 192));
   TRY_S(AB(&ctx->SP, B * (R + 6) * (R + 6) * 16));
   TRY_S(A(&ctx->S1, B * h2 * h2 * 64));
@@ -882,6 +893,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
   TRY_S(A(&ctx->H2, LD * B * Q * 256));
   TRY_S(A(&ctx->G1, B * Q * 256));
   TRY_S(A(&ctx->G2, B * Q * 256));
+  }
   {
     std::vector<void*> set0;
     for (const auto& f : ctx->ws_fields) set0.push_back(*f.field);
@@ -1407,11 +1419,17 @@ static std::string forward_tail(spe_ctx* ctx, int B, void* kv, float* logits, fl
   return "";
 }
 
+#include "sa_model.inl"
+void sa_release(spe_ctx* ctx) {
+  delete ctx->sa;
+  ctx->sa = nullptr;
+}
+
 // (re)compute the input-independent part of decoder layer 0 on one image's worth of rows (see spe_ctx::dec0_tgt)
 static std::string use_workspace(spe_ctx* ctx, int set);
 static std::string fold_dec0(spe_ctx* ctx) {
   ctx->dec0_valid = false;
-  if (!ctx->dec0_fold) return "";
+  if (!ctx->dec0_fold || ctx->cfg.backbone == 2) return "";
   TRY_S(use_workspace(ctx, 0));
   const long long bytes = static_cast<long long>(ctx->cfg.num_queries) * 256 * static_cast<long long>(dtype_size(ctx->dt));
   cudaStream_t st = nullptr;
@@ -1461,6 +1479,11 @@ static std::string forward_schedule(spe_ctx* ctx, int parts, int kv_slot, const 
                                     float* points, float* logsig, float* aux_logits, float* aux_points,
                                     cudaStream_t st) {
   TRY_S(use_workspace(ctx, kv_slot));
+  if (ctx->cfg.backbone == 2) {
+    if (aux_logits != nullptr || aux_points != nullptr) return "the SA predictor returns its aux outputs through spe_forward_sa";
+    if (parts != 3) return "the SA predictor runs as one schedule (parts = 3)";
+    return sa_forward(ctx, images, B, logits, points, logsig, st);
+  }
   void* kv = ctx->KV;
   if (parts & 1) {
     const long long es = static_cast<long long>(dtype_size(ctx->dt));
@@ -1607,7 +1630,15 @@ int spe_create(const spe_config* cfg, int device, spe_ctx** out) {
     return fail(nullptr, SPE_ERR_INVALID, "spe_create: only hidden_dim=256, nheads=8 (head_dim 32) is built");
   if (cfg->input_size <= 0 || cfg->input_size % 32 != 0)
     return fail(nullptr, SPE_ERR_INVALID, "spe_create: input_size must be a positive multiple of 32");
-  if (cfg->backbone != 0 && cfg->backbone != 1) return fail(nullptr, SPE_ERR_INVALID, "spe_create: backbone must be 0 or 1");
+  if (cfg->backbone < 0 || cfg->backbone > 2) return fail(nullptr, SPE_ERR_INVALID, "spe_create: backbone must be 0, 1 or 2");
+  if (cfg->backbone == 2) {
+    if (cfg->precision != 0 || cfg->has_sigma != 1 || cfg->enc_layers != 1)
+      return fail(nullptr, SPE_ERR_INVALID, "spe_create: the SA predictor needs precision 0 (fp32 / TF32), has_sigma 1, enc_layers 1");
+    if (cfg->input_size > 512) return fail(nullptr, SPE_ERR_INVALID, "spe_create: the SA predictor is built for inputs up to 512 x 512");
+    const int h8 = cfg->input_size / 8;
+    if (cfg->num_queries > h8 * h8 + (h8 / 2) * (h8 / 2) + (h8 / 4) * (h8 / 4) || cfg->num_queries % 2)
+      return fail(nullptr, SPE_ERR_INVALID, "spe_create: the SA predictor needs an even num_queries <= the number of anchors");
+  }
   if (cfg->precision != 0 && cfg->precision != 1) return fail(nullptr, SPE_ERR_INVALID, "spe_create: precision must be 0 or 1");
   if (cfg->num_queries <= 0 || cfg->enc_layers <= 0 || cfg->dec_layers <= 0 || cfg->max_batch <= 0 ||
       cfg->dim_feedforward <= 0 || cfg->dim_feedforward % 64 != 0)
@@ -1660,6 +1691,7 @@ void spe_destroy(spe_ctx* ctx) {
   if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->frames_dev) cudaFree(ctx->frames_dev);
+  sa_release(ctx);
   delete ctx;
 }
 
@@ -1709,6 +1741,28 @@ int spe_forward(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev,
   std::string s = forward_impl(ctx, images_dev, B, logits_dev, points_dev, log_sigma_dev, aux_logits_dev,
                                aux_points_dev, static_cast<cudaStream_t>(stream));
   if (!s.empty()) return fail(ctx, SPE_ERR_CUDA, "spe_forward: " + s);
+  return SPE_OK;
+}
+
+int spe_forward_sa(spe_ctx* ctx, const float* images_dev, int B, float* logits_dev, float* points_dev, float* log_sigma_dev,
+                   float* aux_logits_dev, float* aux_points_dev, float* aux_log_sigma_dev, int32_t* topk_idx_dev,
+                   const int32_t* topk_override_dev, void* stream) {
+  if (!ctx) return fail(nullptr, SPE_ERR_INVALID, "spe_forward_sa: null ctx");
+  if (ctx->cfg.backbone != 2 || ctx->sa == nullptr) return fail(ctx, SPE_ERR_INVALID, "spe_forward_sa: the ctx was not created with backbone 2");
+  if (!ctx->weights_loaded) return fail(ctx, SPE_ERR_STATE, "spe_forward_sa: call spe_load_weights first");
+  if (!images_dev || !logits_dev || !points_dev) return fail(ctx, SPE_ERR_INVALID, "spe_forward_sa: null buffer");
+  if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, SPE_ERR_INVALID, "spe_forward_sa: batch outside [1, max_batch]");
+  cudaSetDevice(ctx->device);
+  std::string s = use_workspace(ctx, 0);
+  if (s.empty()) {
+    SaModel& m = *ctx->sa;
+    m.aux_logits = aux_logits_dev; m.aux_points = aux_points_dev; m.aux_logsig = aux_log_sigma_dev;
+    m.topk_out = topk_idx_dev; m.topk_in = topk_override_dev;
+    s = sa_forward(ctx, images_dev, B, logits_dev, points_dev, log_sigma_dev, static_cast<cudaStream_t>(stream));
+    m.aux_logits = m.aux_points = m.aux_logsig = nullptr;
+    m.topk_out = nullptr; m.topk_in = nullptr;
+  }
+  if (!s.empty()) return fail(ctx, SPE_ERR_CUDA, "spe_forward_sa: " + s);
   return SPE_OK;
 }
 

@@ -116,9 +116,28 @@ std::string launch_head_final(Dtype dt, const void* hs, const void* h2, const vo
 // ---- SA (RT-DETR) decoder pieces (deform_attn.cu) ----
 std::string launch_ms_deform_attn(const float* value, const int* shapes_hw, int L, const float* loc, const float* attn,
                                   const float* ref, int ref_levels, int B, int Lq, int heads, int P, int fused,
-                                  float* out, cudaStream_t s);
+                                  float* out, cudaStream_t s, long long value_ld = 0, long long loc_ld = 0,
+                                  long long attn_ld = 0);   // row strides in floats, 0 = dense reference layout
 std::string launch_topk_queries(const float* cls, int B, int Lv, int C, int k, int32_t* idx, float* vals, cudaStream_t s);
 std::string launch_gather_rows(const float* src, const int32_t* idx, int B, int Lv, int k, int D, float* out, cudaStream_t s);
+
+// ---- SA (RT-DETR) predictor: everything that is not a GEMM / attention / LayerNorm (sa_kernels.cu) ----
+std::string launch_sa_stem_im2col(const float* nchw, int NB, int H, int W, float* out /*[NB*H/2*W/2, 32]*/, cudaStream_t s);
+std::string launch_avgpool2x2(const float* in, int NB, int H, int W, int C, float* out, cudaStream_t s);
+// kind: 0 identity, 1 SiLU, 2 GELU (erf), 3 sigmoid; out[r, 0:C] = act(in[r, 0:C]) (+ add[r, 0:C]); round: to TF32
+std::string launch_act_rows(const float* in, int in_ld, const float* add, int add_ld, float* out, int out_ld,
+                            long long rows, int C, int kind, int round, cudaStream_t s);
+std::string launch_upsample_nearest2x(const float* in, int in_ld, int NB, int H, int W, int C, float* out, int out_ld,
+                                      cudaStream_t s);
+std::string launch_bicubic_half(const float* in, int NB, int H, int W, int C, float* out, int out_ld, cudaStream_t s);
+std::string launch_small_linear(const float* x, int ldx, long long rows, int K, const float* Wt, const float* b, int N,
+                                float* out, int ldo, const float* addend, int add_mod, cudaStream_t s);
+std::string launch_query_pos_hidden(const float* ref, const float* W0, const float* b0, int Hd, long long rows, float* out,
+                                    cudaStream_t s);
+std::string launch_sa_head(const float* tgt, const float* h2, const float* g2, const float* ref_in, long long rows,
+                           const float* Wc, const float* bc, const float* Wb, const float* bb, const float* Ws,
+                           const float* bs, float* logits, float* pts, float* logsig, float* ref_out, cudaStream_t s);
+std::string launch_add(const float* a, const float* b, float* out, long long n, cudaStream_t s);
 
 // ---- crop (crop.cu) ----
 std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long long pitch, long long frame_stride,

@@ -7,7 +7,8 @@ import torch
 from . import _lib
 from ._lib import SpeConfig, SpePnpParams, SpeTensorDesc, check
 
-BACKBONE_S8, BACKBONE_S16 = 0, 1
+BACKBONE_S8, BACKBONE_S16, BACKBONE_SA_RTDETR = 0, 1, 2
+SA_BACKBONES = ("rtdetr_r50vd", "sa_rtdetr")
 PRECISION = {"tf32": 0, "fp32": 0, "bf16": 1}
 
 
@@ -32,10 +33,12 @@ class Engine:
         self.cfg = SpeConfig(
             input_size=input_size, num_queries=num_queries, enc_layers=enc_layers, dec_layers=dec_layers,
             hidden_dim=hidden_dim, nheads=nheads, dim_feedforward=dim_feedforward,
-            backbone=BACKBONE_S16 if backbone in ("resnet18", "resnet34", "resnet50") else BACKBONE_S8,
+            backbone=(BACKBONE_SA_RTDETR if backbone in SA_BACKBONES else
+                      BACKBONE_S16 if backbone in ("resnet18", "resnet34", "resnet50") else BACKBONE_S8),
             precision=PRECISION[precision], has_sigma=int(bool(has_sigma)), max_batch=max_batch)
         self.precision = precision
         self.has_sigma = bool(has_sigma)
+        self.is_sa = backbone in SA_BACKBONES
         self.max_batch = max_batch
         self.Q, self.L, self.R = num_queries, dec_layers, input_size
         self._ctx = C.c_void_p()
@@ -184,6 +187,37 @@ class Engine:
             out["pred_sigmas"] = logsig
         if aux_l is not None:
             out["aux_outputs"] = [{"pred_logits": aux_l[i], "pred_points": aux_p[i]} for i in range(self.L - 1)]
+        return out
+
+    def forward_sa(self, images, want_aux=True, topk_override=None):
+        """The SA drop's RT-DETR predictor (``Engine(backbone="rtdetr_r50vd", ...)``): images float32 cuda [B,3,R,R] ->
+        the dict ``RTDETR.forward`` returns in eval mode (SA/src/zoo/rtdetr/rtdetr_decoder.py:732-751): ``pred_logits``
+        [B,Q,12], ``pred_pts`` [B,Q,2], ``pred_sigmas`` [B,Q,2] (log sigma) and ``aux_outputs`` (decoder layers 0..L-2 with
+        sigmas, then the encoder's top-k proposals without), plus ``topk_ind`` [B,Q] int32, the anchors the queries were
+        taken from.  ``topk_override`` (int32 cuda [B,Q]) replaces the top-k selection."""
+        if not self.is_sa:
+            raise ValueError("forward_sa needs an Engine built with backbone='rtdetr_r50vd'")
+        assert images.is_cuda and images.dtype == torch.float32
+        B = images.shape[0]
+        if images.shape[1:] != (3, self.R, self.R):
+            raise ValueError(f"expected images [B,3,{self.R},{self.R}], got {tuple(images.shape)}")
+        dev, Q, L = images.device, self.Q, self.L
+        x = images.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        logits, points, logsig = torch.empty((B, Q, 12), **f32), torch.empty((B, Q, 2), **f32), torch.empty((B, Q, 2), **f32)
+        aux_l = torch.empty((L, B, Q, 12), **f32) if want_aux else None
+        aux_p = torch.empty((L, B, Q, 2), **f32) if want_aux else None
+        aux_s = torch.empty((max(L - 1, 1), B, Q, 2), **f32) if want_aux else None
+        topk = torch.empty((B, Q), dtype=torch.int32, device=dev)
+        if topk_override is not None:
+            topk_override = topk_override.to(device=dev, dtype=torch.int32).contiguous()
+            assert tuple(topk_override.shape) == (B, Q)
+        check(self.lib.spe_forward_sa(self._ctx, _ptr(x), B, _ptr(logits), _ptr(points), _ptr(logsig), _ptr(aux_l),
+                                      _ptr(aux_p), _ptr(aux_s), _ptr(topk), _ptr(topk_override), _stream(dev)), self._ctx)
+        out = {"pred_logits": logits, "pred_pts": points, "pred_sigmas": logsig, "topk_ind": topk}
+        if want_aux:
+            out["aux_outputs"] = [{"pred_logits": aux_l[i], "pred_pts": aux_p[i], "pred_sigmas": aux_s[i]} for i in range(L - 1)]
+            out["aux_outputs"].append({"pred_logits": aux_l[L - 1], "pred_pts": aux_p[L - 1]})
         return out
 
     def calibrate(self, images, max_images=16):

@@ -1,0 +1,93 @@
+"""GPU bring-up probe for the SA (RT-DETR) predictor: per-stage error of the CUDA schedule against the oracle's taps.
+Not collected by pytest (run: python tests/sa_bringup.py [B])."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import sa_model_ref, synth  # noqa: E402
+from satellite_pose_estimation_b200 import Engine  # noqa: E402
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item(), ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    cfg = sa_model_ref.SaCfg()
+    sd = synth.make_sa_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 3, cfg.input_size, cfg.input_size, generator=g)
+    taps = {}
+    ref = sa_model_ref.forward(sd, cfg, x, taps)
+    eng = Engine(input_size=cfg.input_size, num_queries=cfg.num_queries, enc_layers=1, dec_layers=cfg.dec_layers,
+                 dim_feedforward=cfg.dec_ff, backbone="rtdetr_r50vd", precision="tf32", has_sigma=True, max_batch=B)
+    t0 = time.time()
+    eng.load_state_dict(sd)
+    print(f"weights loaded in {time.time() - t0:.1f} s")
+    eng.enable_taps(True)
+    xc = x.cuda()
+    out = eng.forward_sa(xc, topk_override=taps["topk"].to(torch.int32).cuda())
+    torch.cuda.synchronize()
+    R = cfg.input_size
+
+    def nhwc(name, H, C):
+        return eng.read_tap(name, (B, H, H, C)).permute(0, 3, 1, 2)
+
+    print("stem   ", rel(nhwc("sa_stem", R // 2, 64), taps["stem"]))
+    for i, (s, c) in enumerate(((4, 256), (8, 512), (16, 1024), (32, 2048))):
+        print(f"stage{i} ", rel(nhwc(f"sa_stage{i}", R // s, c), taps[f"stage{i}"]))
+    print("aifi   ", rel(nhwc("sa_aifi", R // 32, 256), taps["aifi"]))
+    for i, s in enumerate((8, 16, 32)):
+        print(f"enc_out{i}", rel(nhwc(f"sa_enc{i}", R // s, 256), taps[f"enc_out{i}"]))
+    Lv = taps["memory"].shape[1]
+    print("memory ", rel(eng.read_tap("sa_memory", (B, Lv, 256)), taps["memory"]))
+    sc = eng.read_tap("sa_enc_scores", (B, Lv, 12)).max(-1).values
+    print("scores ", rel(sc, taps["enc_scores"]), "abs", (sc - taps["enc_scores"]).abs().max().item())
+    for i in range(cfg.dec_layers):
+        print(f"dec{i}   ", rel(eng.read_tap(f"sa_dec{i}", (B, cfg.num_queries, 256)), taps[f"dec{i}"]))
+    for k in ("pred_logits", "pred_pts", "pred_sigmas"):
+        d = (out[k].cpu() - ref[k]).abs().max().item()
+        print(k, d, "(px at S=1748: %.3f)" % (d * 1748) if k == "pred_pts" else "")
+    for i, (a, b) in enumerate(zip(out["aux_outputs"], ref["aux_outputs"])):
+        print("aux", i, {k: (a[k].cpu() - b[k]).abs().max().item() for k in b})
+    # own top-k
+    eng.enable_taps(False)
+    out2 = eng.forward_sa(xc)
+    tk = out2["topk_ind"].cpu().long()
+    same = [len(set(tk[b].tolist()) & set(taps["topk"][b].tolist())) for b in range(B)]
+    print("own top-k: anchors in common with the oracle per image", same, "same order", (tk == taps["topk"]).float().mean().item())
+    ref2 = sa_model_ref.forward(sd, cfg, x, None, topk_override=tk)
+    for k in ("pred_logits", "pred_pts", "pred_sigmas"):
+        print("own top-k", k, (out2[k].cpu() - ref2[k]).abs().max().item())
+    # plain spe_forward path (graph replay on the third call)
+    for _ in range(3):
+        o3 = eng.forward(xc)
+    torch.cuda.synchronize()
+    print("spe_forward vs forward_sa", (o3["pred_logits"] - out2["pred_logits"]).abs().max().item(),
+          (o3["pred_points"] - out2["pred_pts"]).abs().max().item(), (o3["pred_sigmas"] - out2["pred_sigmas"]).abs().max().item())
+    # calibration
+    eng.calibrate(xc)
+    out4 = eng.forward_sa(xc, topk_override=tk.to(torch.int32).cuda())
+    for k in ("pred_logits", "pred_pts", "pred_sigmas"):
+        print("calibrated", k, (out4[k].cpu() - ref2[k]).abs().max().item())
+    # timing
+    for Bt in (B,):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            eng.forward(xc)
+        e0.record()
+        for _ in range(10):
+            eng.forward(xc)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"B={Bt}: {e0.elapsed_time(e1) / 10:.3f} ms per forward")
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
