@@ -16,6 +16,7 @@ Fixtures written:
   model_golden.npz    reference model outputs for seeded weights/inputs (weights are regenerated, never stored)
   pnp_golden.npz      reference SimplePoseSolver poses for seeded synthetic predictions
   deform_attn_golden.npz  the SA drop's deformable_attention_core_func and live MSDeformableAttention module on seeded inputs
+  sa_model_golden.npz  the SA drop's live RT-DETR model (PResNet-50-vd + HybridEncoder + RTDETRTransformer) on seeded weights
   model_b256_golden.npz  reference model (calibrated heads, oracle/make_chain_fixture.py) + PostProcess + solver on the
                       256 crops of the benchmarked frame sets; sigma head through the SA drop's own MLP class
 """
@@ -349,6 +350,42 @@ def write_deform_attn():
     print("deformable attention goldens:", core.shape, got["core"].shape, out.shape)
 
 
+SA_MODEL_CASE = dict(batch=4, seed=7, weights_seed=0)
+
+
+def write_sa_model():
+    """The LIVE SA ``RTDETR`` model (ref_import.build_sa_reference_model) on seeded weights / inputs -> sa_model_golden.npz:
+    the eval-mode output dict (SA/src/zoo/rtdetr/rtdetr_decoder.py:732-751), the anchor scores and the top-k selection
+    (recomputed with the reference's own ``torch.topk`` call, :646-648, on the live ``enc_score_head`` output)."""
+    from . import sa_model_ref
+    case = SA_MODEL_CASE
+    cfg = sa_model_ref.SaCfg()
+    sd = synth.make_sa_state_dict(cfg, seed=case["weights_seed"])
+    model = ref_import.build_sa_reference_model(sd)
+    x = model_inputs(case["batch"], cfg.input_size, case["seed"])
+    got = {}
+    model.decoder.enc_score_head.register_forward_hook(lambda mod, inp, out: got.__setitem__("cls", out.detach().clone()))
+    with torch.no_grad():
+        out = model(x)
+    scores = got["cls"].max(-1).values
+    topk = torch.topk(scores, cfg.num_queries, dim=1)[1]
+    taps = {}
+    mine = sa_model_ref.forward(sd, cfg, x, taps)
+    assert torch.equal(taps["topk"], topk), "restatement selects other anchors than the live model"
+    for k in ("pred_logits", "pred_pts", "pred_sigmas"):
+        d = (mine[k] - out[k]).abs().max().item()
+        assert d < 5e-5, (k, d)
+    aux = out["aux_outputs"]
+    assert len(aux) == cfg.dec_layers
+    np.savez_compressed(
+        os.path.join(GOLDEN, "sa_model_golden.npz"), weights_sha256=synth.weights_checksum(sd),
+        pred_logits=out["pred_logits"].numpy(), pred_pts=out["pred_pts"].numpy(), pred_sigmas=out["pred_sigmas"].numpy(),
+        aux_logits=torch.stack([a["pred_logits"] for a in aux]).numpy(), aux_pts=torch.stack([a["pred_pts"] for a in aux]).numpy(),
+        aux_sigmas=torch.stack([a["pred_sigmas"] for a in aux[:-1]]).numpy(), enc_scores=scores.numpy(),
+        topk=topk.numpy().astype(np.int32))
+    print("SA model golden written:", tuple(out["pred_logits"].shape), "restatement within 5e-5 of the live model")
+
+
 def write_pnp(rv_eval, n=400):
     import cv2
     d = synth.make_predictions(n, seed=1)
@@ -435,6 +472,7 @@ def main():
     write_model_b256(rv_eval)
     write_model_b64_random()
     write_deform_attn()
+    write_sa_model()
     write_pnp(rv_eval)
     write_pnp_multi(rv_eval)
 

@@ -85,3 +85,26 @@ def import_sa_rtdetr():
         import src.nn.backbone.presnet  # noqa: F401
         import src.zoo.rtdetr  # noqa: F401
     return sys.modules["src.zoo.rtdetr"]
+
+
+SA_MODEL_YML = "configs/rtdetr_speed/rtdetr_r50vd_6x_speed_kl_1.yml"
+
+
+def build_sa_reference_model(state_dict=None):
+    """The SA drop's live ``RTDETR`` model of ``configs/rtdetr_speed/rtdetr_r50vd_6x_speed_kl_1.yml`` (PResNet-50-vd,
+    HybridEncoder, RTDETRTransformer with 30 queries / 3 decoder layers, eval size 256), built by the reference's own
+    ``YAMLConfig`` with the pretrained-weight download switched off; eval mode, optional weights (strict)."""
+    import warnings
+    import torch
+    import_sa_rtdetr()
+    from src.core import YAMLConfig
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cfg = YAMLConfig(os.path.join(SA_ROOT, SA_MODEL_YML))
+        cfg.yaml_cfg["PResNet"]["pretrained"] = False
+        torch.manual_seed(0)
+        model = cfg.model
+    model.eval()
+    if state_dict is not None:
+        model.load_state_dict(state_dict, strict=True)
+    return model

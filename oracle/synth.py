@@ -461,4 +461,4 @@ def make_sa_state_dict(cfg=None, seed=0):
         _linear(rng, sd, f"{d}.dec_score_head.{i}", cfg.num_classes + 1, E)
     for i in range(cfg.dec_layers):
         _mlp(rng, sd, f"{d}.dec_bbox_head.{i}", (E, E, E, 2), last_gain=0.5)
-    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).reshape(v.shape) for k, v in sd.items()}

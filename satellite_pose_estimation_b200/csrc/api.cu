@@ -553,7 +553,8 @@ int spe_debug_conv(int dtype, const void* x, const void* w, int NB, int H, int W
   d.mode = 1; d.A = x; d.NB = NB; d.H = H; d.W = W; d.C = C; d.R = R; d.S = S; d.pad = pad; d.Wt = w; d.N = Cout;
   d.conv_stride = stride;
   d.scale = scale; d.bias = bias; d.relu = relu; d.out = out; d.out_ld = Cout;
-  std::string s = launch_gemm(dtype == 0 ? kTF32 : kBF16, d, sm_count(), static_cast<cudaStream_t>(stream));
+  if (dtype == 2) { d.x3 = 1; d.round_out = 0; }   // 3xTF32: w is the pre-split [Cout, 2 R S C] matrix
+  std::string s = launch_gemm(dtype == 1 ? kBF16 : kTF32, d, sm_count(), static_cast<cudaStream_t>(stream));
   if (!s.empty()) return set_error(nullptr, SPE_ERR_CUDA, "spe_debug_conv: " + s);
   return SPE_OK;
 }

@@ -1371,7 +1371,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.N % 32 != 0) return "gemm: N must be a multiple of 32";
   if (d.out_ld % (16 / es) != 0 && !d.out_f32) return "gemm: out_ld must keep rows 16-byte aligned";
   if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
-  if (d.x3 && d.mode != 0) return "gemm: 3xTF32 is only built for plain matrices";
+  if (d.x3 && d.mode == 2) return "gemm: 3xTF32 is not built for the windowed stem";
   if (d.mode < 0 || d.mode > 2) return "gemm: bad mode";
   if (d.A2 != nullptr && (d.mode != 0 || d.x3)) return "gemm: a second operand source needs a plain, uncompensated GEMM";
   if (d.mode == 1) {

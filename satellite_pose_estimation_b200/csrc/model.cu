@@ -547,10 +547,10 @@ static std::string load_fused_down(spe_ctx* ctx, WeightSource& ws, const std::st
 }
 
 static std::string load_conv_bn(spe_ctx* ctx, WeightSource& ws, const std::string& conv, const std::string& bn,
-                                int Cout, int Cin, int R, GemmW* g, int Kpad = 0) {
+                                int Cout, int Cin, int R, GemmW* g, int Kpad = 0, bool x3 = false) {
   const HostTensor* w = ws.get(conv + ".weight", {Cout, Cin, R, R});
   if (!w) return ws.missing;
-  TRY_S(upload_gemm_w(ctx, repack_conv(*w, Kpad), Cout, Kpad > 0 ? Kpad : R * R * Cin, g));
+  TRY_S(upload_gemm_w(ctx, repack_conv(*w, Kpad), Cout, Kpad > 0 ? Kpad : R * R * Cin, g, x3));
   if (!bn.empty()) TRY_S(load_bn(ctx, ws, bn, Cout, g));
   return "";
 }
@@ -1046,7 +1046,8 @@ struct Fwd {
     d.scale = w.scale; d.bias = w.bias;
     d.relu = relu ? 1 : 0;
     d.out = out; d.out_ld = out_ld;
-    d.round_out = exact_out ? 0 : 1;
+    d.x3 = w.x3;
+    d.round_out = (exact_out || w.x3) ? 0 : 1;
     return launch_gemm(dt, d, ctx->num_sms, st);
   }
   std::string conv3x3(const void* x, int H, int C, const GemmW& w, void* out, int out_ld, bool relu) {

@@ -37,7 +37,7 @@ inline unsigned blocks_for(long long total, int threads) {
 
 // out[(b, ho, wo), (r*3 + s)*3 + c] = img[b, c, 2 ho - 1 + r, 2 wo - 1 + s]  (zero outside), columns 27..31 zero
 __global__ void sa_stem_im2col_kernel(const float* __restrict__ img, int H, int W, int Ho, int Wo, long long total,
-                                      float* __restrict__ out) {
+                                      int round, float* __restrict__ out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one (pixel, tap) per thread
   if (i >= total) return;
   const int tap = static_cast<int>(i % 11);          // taps 0..8, 9 and 10 write the zero tail
@@ -57,11 +57,11 @@ __global__ void sa_stem_im2col_kernel(const float* __restrict__ img, int H, int 
   const float* p = img + (b * 3 * H + y) * static_cast<long long>(W) + x;
   const long long plane = static_cast<long long>(H) * W;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) o[tap * 3 + c] = in ? rna_tf32(p[c * plane]) : 0.f;
+  for (int c = 0; c < 3; ++c) o[tap * 3 + c] = in ? (round ? rna_tf32(p[c * plane]) : p[c * plane]) : 0.f;
 }
 
 // NHWC 2x2 / stride-2 average (H, W even), float4 per thread
-__global__ void avgpool2x2_kernel(const float4* __restrict__ in, int H, int W, int C4, long long total,
+__global__ void avgpool2x2_kernel(const float4* __restrict__ in, int H, int W, int C4, long long total, int round,
                                   float4* __restrict__ out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -74,10 +74,11 @@ __global__ void avgpool2x2_kernel(const float4* __restrict__ in, int H, int W, i
   const float4* p = in + ((b * H + 2 * ho) * W + 2 * wo) * C4 + c;
   const float4 a = p[0], bq = p[C4], cq = p[static_cast<long long>(W) * C4], d = p[static_cast<long long>(W) * C4 + C4];
   float4 r;
-  r.x = rna_tf32((a.x + bq.x + cq.x + d.x) * 0.25f);
-  r.y = rna_tf32((a.y + bq.y + cq.y + d.y) * 0.25f);
-  r.z = rna_tf32((a.z + bq.z + cq.z + d.z) * 0.25f);
-  r.w = rna_tf32((a.w + bq.w + cq.w + d.w) * 0.25f);
+  r.x = (a.x + bq.x + cq.x + d.x) * 0.25f;
+  r.y = (a.y + bq.y + cq.y + d.y) * 0.25f;
+  r.z = (a.z + bq.z + cq.z + d.z) * 0.25f;
+  r.w = (a.w + bq.w + cq.w + d.w) * 0.25f;
+  if (round) { r.x = rna_tf32(r.x); r.y = rna_tf32(r.y); r.z = rna_tf32(r.z); r.w = rna_tf32(r.w); }
   out[i] = r;
 }
 
@@ -123,7 +124,7 @@ __global__ void upsample_nearest2x_kernel(const float* __restrict__ in, int in_l
 // Bicubic x0.5 as torch computes it (upsample_bicubic2d, align_corners=False, A = -0.75, no antialias): the source
 // coordinate of output o is 2 o + 0.5, so the four taps 2o-1 .. 2o+2 always carry the weights of t = 0.5,
 // (-0.09375, 0.59375, 0.59375, -0.09375), with indices clamped to the map.
-__global__ void bicubic_half_kernel(const float* __restrict__ in, int H, int W, int C4, long long total,
+__global__ void bicubic_half_kernel(const float* __restrict__ in, int H, int W, int C4, long long total, int round,
                                     float* __restrict__ out, int out_ld) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -155,7 +156,7 @@ __global__ void bicubic_half_kernel(const float* __restrict__ in, int H, int W, 
     }
     acc.x += row.x * wgt[r]; acc.y += row.y * wgt[r]; acc.z += row.z * wgt[r]; acc.w += row.w * wgt[r];
   }
-  acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w);
+  if (round) { acc.x = rna_tf32(acc.x); acc.y = rna_tf32(acc.y); acc.z = rna_tf32(acc.z); acc.w = rna_tf32(acc.w); }
   *reinterpret_cast<float4*>(out + pix * out_ld + c * 4) = acc;
 }
 
@@ -274,21 +275,21 @@ __global__ void add_kernel(const float4* __restrict__ a, const float4* __restric
 
 }  // namespace
 
-std::string launch_sa_stem_im2col(const float* nchw, int NB, int H, int W, float* out, cudaStream_t s) {
+std::string launch_sa_stem_im2col(const float* nchw, int NB, int H, int W, float* out, int round, cudaStream_t s) {
   if (H % 2 || W % 2) return "sa stem: input extent must be even";
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(NB) * Ho * Wo * 11;
   ProfScope ps(kFamElementwise, s);
-  sa_stem_im2col_kernel<<<blocks_for(total, 256), 256, 0, s>>>(nchw, H, W, Ho, Wo, total, out);
+  sa_stem_im2col_kernel<<<blocks_for(total, 256), 256, 0, s>>>(nchw, H, W, Ho, Wo, total, round, out);
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
 }
 
-std::string launch_avgpool2x2(const float* in, int NB, int H, int W, int C, float* out, cudaStream_t s) {
+std::string launch_avgpool2x2(const float* in, int NB, int H, int W, int C, float* out, int round, cudaStream_t s) {
   if (H % 2 || W % 2 || C % 4) return "avgpool2x2: extent must be even and C a multiple of 4";
   const long long total = static_cast<long long>(NB) * (H / 2) * (W / 2) * (C / 4);
   ProfScope ps(kFamElementwise, s);
-  avgpool2x2_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in), H, W, C / 4, total,
+  avgpool2x2_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in), H, W, C / 4, total, round,
                                                            reinterpret_cast<float4*>(out));
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
@@ -314,11 +315,12 @@ std::string launch_upsample_nearest2x(const float* in, int in_ld, int NB, int H,
   return "";
 }
 
-std::string launch_bicubic_half(const float* in, int NB, int H, int W, int C, float* out, int out_ld, cudaStream_t s) {
+std::string launch_bicubic_half(const float* in, int NB, int H, int W, int C, float* out, int out_ld, int round,
+                                cudaStream_t s) {
   if (H % 2 || W % 2 || C % 4 || out_ld % 4) return "bicubic_half: extent must be even and C a multiple of 4";
   const long long total = static_cast<long long>(NB) * (H / 2) * (W / 2) * (C / 4);
   ProfScope ps(kFamElementwise, s);
-  bicubic_half_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, H, W, C / 4, total, out, out_ld);
+  bicubic_half_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, H, W, C / 4, total, round, out, out_ld);
   SPE_CUDA_TRY(cudaGetLastError());
   return "";
 }

@@ -38,6 +38,11 @@ struct SaDecLayer {
 };
 struct SaModel {
   int R = 0, hl[3] = {0, 0, 0}, start[3] = {0, 0, 0}, Lv = 0;
+  // 3xTF32 (fp32-grade products) for backbone + encoder too.  With plain TF32 there the encoder memory carries ~1e-3 of
+  // relative rounding noise, which the keypoint logits (anchor logit + MLP(memory), refined through
+  // sigmoid(delta + inverse_sigmoid(ref)) three times) turn into up to 0.7 px at a 1748 px crop -- above the 0.5 px bar;
+  // the decoder side is always 3xTF32.  SPE_SA_X3=0 selects the plain-TF32 trunk (3x less tensor work).
+  bool x3 = getenv("SPE_SA_X3") ? atoi(getenv("SPE_SA_X3")) != 0 : true;
   int shapes_hw[6] = {0, 0, 0, 0, 0, 0};
   GemmW c11, c12, c13;
   std::vector<SaBlock> blocks;
@@ -98,7 +103,7 @@ static std::string sa_load_bn_padded(spe_ctx* ctx, WeightSource& ws, const std::
 }
 
 static std::string sa_load_conv_norm(spe_ctx* ctx, WeightSource& ws, const std::string& p, int Cout, int Cin, int R, GemmW* g) {
-  return load_conv_bn(ctx, ws, p + ".conv", p + ".norm", Cout, Cin, R, g);
+  return load_conv_bn(ctx, ws, p + ".conv", p + ".norm", Cout, Cin, R, g, 0, ctx->sa->x3);
 }
 
 // rows [N, K] (+ bias) as GEMM weights
@@ -129,7 +134,7 @@ static std::string sa_load_csp(spe_ctx* ctx, WeightSource& ws, const std::string
     for (int ci = 0; ci < Hc; ++ci) row[4 * Hc + ci] += s1[o] * w1->data[static_cast<size_t>(o) * Hc + ci];   // centre tap
     bias[o] = b3[o] + b1[o];
   }
-  TRY_S(upload_gemm_w(ctx, w, Hc, K, &c->rep));
+  TRY_S(upload_gemm_w(ctx, w, Hc, K, &c->rep, ctx->sa->x3));
   TRY_S(upload_f32(ctx, bias.data(), Hc, &c->rep.bias));
   return "";
 }
@@ -147,11 +152,11 @@ std::string sa_load_weights(spe_ctx* ctx, WeightSource& ws) {
     if (!w1 || !w2 || !w3) return ws.missing;
     std::vector<float> a = repack_conv(*w1, 32);                 // [32][27 -> 32]
     a.resize(static_cast<size_t>(64) * 32, 0.f);                 // 32 zero output channels
-    TRY_S(upload_gemm_w(ctx, a, 64, 32, &m.c11));
+    TRY_S(upload_gemm_w(ctx, a, 64, 32, &m.c11, m.x3));
     TRY_S(sa_load_bn_padded(ctx, ws, "backbone.conv1.conv1_1.norm", 32, 64, &m.c11));
-    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w2, 64, 64), 64, 9 * 64, &m.c12));
+    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w2, 64, 64), 64, 9 * 64, &m.c12, m.x3));
     TRY_S(sa_load_bn_padded(ctx, ws, "backbone.conv1.conv1_2.norm", 32, 64, &m.c12));
-    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w3, 64, 64), 64, 9 * 64, &m.c13));
+    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w3, 64, 64), 64, 9 * 64, &m.c13, m.x3));
     TRY_S(sa_load_bn_padded(ctx, ws, "backbone.conv1.conv1_3.norm", 64, 64, &m.c13));
   }
   m.blocks.clear();
@@ -175,7 +180,7 @@ std::string sa_load_weights(spe_ctx* ctx, WeightSource& ws) {
   const int cins[3] = {512, 1024, 2048};
   for (int i = 0; i < 3; ++i) {
     const std::string p = "encoder.input_proj." + std::to_string(i);
-    TRY_S(load_conv_bn(ctx, ws, p + ".0", p + ".1", E, cins[i], 1, &m.eproj[i]));
+    TRY_S(load_conv_bn(ctx, ws, p + ".0", p + ".1", E, cins[i], 1, &m.eproj[i], 0, m.x3));
   }
   {
     // 2-D sin-cos positions of the /32 level (hybrid_encoder.py:306-326): token n = y * W + x carries
@@ -195,11 +200,11 @@ std::string sa_load_weights(spe_ctx* ctx, WeightSource& ws) {
     SPE_CUDA_TRY(cudaMalloc(&pos_dev, pos.size() * sizeof(float)));
     cudaMemcpy(pos_dev, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice);
     const std::string p = "encoder.encoder.0.layers.0";
-    std::string s = load_mha_self(ctx, ws, p + ".self_attn", pos_dev, T, &m.a_qkv, &m.a_out, &m.a_addend);
+    std::string s = load_mha_self(ctx, ws, p + ".self_attn", pos_dev, T, &m.a_qkv, &m.a_out, &m.a_addend, m.x3);
     cudaFree(pos_dev);
     if (!s.empty()) return s;
-    TRY_S(load_linear(ctx, ws, p + ".linear1", c.dim_feedforward, E, &m.a_ff1));
-    TRY_S(load_linear(ctx, ws, p + ".linear2", E, c.dim_feedforward, &m.a_ff2));
+    TRY_S(load_linear(ctx, ws, p + ".linear1", c.dim_feedforward, E, &m.a_ff1, m.x3));
+    TRY_S(load_linear(ctx, ws, p + ".linear2", E, c.dim_feedforward, &m.a_ff2, m.x3));
     TRY_S(load_vec(ctx, ws, p + ".norm1.weight", E, &m.an1g));
     TRY_S(load_vec(ctx, ws, p + ".norm1.bias", E, &m.an1b));
     TRY_S(load_vec(ctx, ws, p + ".norm2.weight", E, &m.an2g));
@@ -433,7 +438,8 @@ struct SaFwd {
     return launch_gemm(kTF32, d, ctx->num_sms, st);
   }
   std::string act(const void* in, int in_ld, const void* add, int add_ld, void* out, int out_ld, long long rows, int C,
-                  int kind, int round = 1) {
+                  int kind, int round = -1) {
+    if (round < 0) round = m.x3 ? 0 : 1;   // a 3xTF32 consumer splits its operand itself
     return launch_act_rows(F(const_cast<void*>(in)), in_ld, add ? F(const_cast<void*>(add)) : nullptr, add_ld, F(out),
                            out_ld, rows, C, kind, round, st);
   }
@@ -468,7 +474,8 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
   const long long MQ = B * Q;
 
   // ---- PResNet stem: conv1_1 (3x3 / s2) as im2col + GEMM, conv1_2, conv1_3 (3x3), max-pool
-  TRY_S(launch_sa_stem_im2col(images, Bi, R, R, SaFwd::F(m.IM2), st));
+  const int rnd = m.x3 ? 0 : 1;
+  TRY_S(launch_sa_stem_im2col(images, Bi, R, R, SaFwd::F(m.IM2), rnd, st));
   TRY_S(s.gemm(m.IM2, 32, B * h2 * h2, m.c11, m.SA0, 64, true, false));
   TRY_S(f.conv(m.SA0, h2, 64, 3, 1, m.c12, m.SA1, 64, true));
   TRY_S(f.conv(m.SA1, h2, 64, 3, 1, m.c13, m.SA0, 64, true));
@@ -491,7 +498,7 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
       if (bk.has_short) {
         const void* src = cur;
         if (bk.stride == 2) {                                             // variant d: AvgPool2d(2, 2) then 1x1
-          TRY_S(launch_avgpool2x2(SaFwd::F(const_cast<void*>(cur)), Bi, H, H, bk.cin, SaFwd::F(m.AP), st));
+          TRY_S(launch_avgpool2x2(SaFwd::F(const_cast<void*>(cur)), Bi, H, H, bk.cin, SaFwd::F(m.AP), rnd, st));
           src = m.AP;
         }
         TRY_S(s.gemm(src, bk.cin, Mout, bk.sc, m.DS, bk.planes * 4, false, true));
@@ -515,13 +522,13 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
   {
     const int T = h32 * h32;
     TRY_S(s.gemm(m.E2, 256, M32, m.a_qkv, m.QKV, 768, false, false, m.a_addend, 768, T, 1));
-    TRY_S(f.attn(m.QKV, 768, SaFwd::col(m.QKV, 256), 768, SaFwd::col(m.QKV, 512), 768, m.ATT, T, T));
+    TRY_S(f.attn(m.QKV, 768, SaFwd::col(m.QKV, 256), 768, SaFwd::col(m.QKV, 512), 768, m.ATT, T, T, m.x3 ? 1 : 0, 0, m.x3 ? 1 : 0));
     TRY_S(s.gemm(m.ATT, 256, M32, m.a_out, m.X2, 256, false, true, m.E2, 256));
-    TRY_S(f.ln(m.X2, m.an1g, m.an1b, M32, m.E2));
+    TRY_S(f.ln(m.X2, m.an1g, m.an1b, M32, m.E2, m.x3 ? 1 : 0));
     TRY_S(s.gemm(m.E2, 256, M32, m.a_ff1, m.HID, FF, false, true));
     TRY_S(s.act(m.HID, FF, nullptr, 0, m.HID, FF, M32, FF, 2));
     TRY_S(s.gemm(m.HID, FF, M32, m.a_ff2, m.X2, 256, false, true, m.E2, 256));
-    TRY_S(f.ln(m.X2, m.an2g, m.an2b, M32, m.E2));
+    TRY_S(f.ln(m.X2, m.an2g, m.an2b, M32, m.E2, m.x3 ? 1 : 0));
     TRY_S(f.tap("sa_aifi", m.E2, M32 * 256));
   }
   // top-down: lateral conv -> nearest x2 -> concat with the finer level -> CSPRep
@@ -532,9 +539,9 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
   TRY_S(launch_upsample_nearest2x(SaFwd::col(m.CATP16, 256), 512, Bi, h16, h16, 256, SaFwd::F(m.CAT8), 512, st));
   TRY_S(s.csp(m.CAT8, h8, m.fpn[1], m.O8));                                                  // outs[0]
   // bottom-up: bicubic x0.5 -> concat with the lateral output -> CSPRep
-  TRY_S(launch_bicubic_half(SaFwd::F(m.O8), Bi, h8, h8, 256, SaFwd::F(m.CATP16), 512, st));
+  TRY_S(launch_bicubic_half(SaFwd::F(m.O8), Bi, h8, h8, 256, SaFwd::F(m.CATP16), 512, rnd, st));
   TRY_S(s.csp(m.CATP16, h16, m.pan[0], m.O16));                                              // outs[1]
-  TRY_S(launch_bicubic_half(SaFwd::F(m.O16), Bi, h16, h16, 256, SaFwd::F(m.CATP32), 512, st));
+  TRY_S(launch_bicubic_half(SaFwd::F(m.O16), Bi, h16, h16, 256, SaFwd::F(m.CATP32), 512, rnd, st));
   TRY_S(s.csp(m.CATP32, h32, m.pan[1], m.O32));                                              // outs[2]
   TRY_S(f.tap("sa_enc0", m.O8, M8 * 256));
   TRY_S(f.tap("sa_enc1", m.O16, M16 * 256));

@@ -122,14 +122,17 @@ std::string launch_topk_queries(const float* cls, int B, int Lv, int C, int k, i
 std::string launch_gather_rows(const float* src, const int32_t* idx, int B, int Lv, int k, int D, float* out, cudaStream_t s);
 
 // ---- SA (RT-DETR) predictor: everything that is not a GEMM / attention / LayerNorm (sa_kernels.cu) ----
-std::string launch_sa_stem_im2col(const float* nchw, int NB, int H, int W, float* out /*[NB*H/2*W/2, 32]*/, cudaStream_t s);
-std::string launch_avgpool2x2(const float* in, int NB, int H, int W, int C, float* out, cudaStream_t s);
+// round: 1 = results rounded to TF32 (consumer is a plain kind::tf32 GEMM), 0 = full fp32 (consumer is a 3xTF32 GEMM)
+std::string launch_sa_stem_im2col(const float* nchw, int NB, int H, int W, float* out /*[NB*H/2*W/2, 32]*/, int round,
+                                  cudaStream_t s);
+std::string launch_avgpool2x2(const float* in, int NB, int H, int W, int C, float* out, int round, cudaStream_t s);
 // kind: 0 identity, 1 SiLU, 2 GELU (erf), 3 sigmoid; out[r, 0:C] = act(in[r, 0:C]) (+ add[r, 0:C]); round: to TF32
 std::string launch_act_rows(const float* in, int in_ld, const float* add, int add_ld, float* out, int out_ld,
                             long long rows, int C, int kind, int round, cudaStream_t s);
 std::string launch_upsample_nearest2x(const float* in, int in_ld, int NB, int H, int W, int C, float* out, int out_ld,
                                       cudaStream_t s);
-std::string launch_bicubic_half(const float* in, int NB, int H, int W, int C, float* out, int out_ld, cudaStream_t s);
+std::string launch_bicubic_half(const float* in, int NB, int H, int W, int C, float* out, int out_ld, int round,
+                                cudaStream_t s);
 std::string launch_small_linear(const float* x, int ldx, long long rows, int K, const float* Wt, const float* b, int N,
                                 float* out, int ldo, const float* addend, int add_mod, cudaStream_t s);
 std::string launch_query_pos_hidden(const float* ref, const float* W0, const float* b0, int Hd, long long rows, float* out,

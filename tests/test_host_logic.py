@@ -200,3 +200,23 @@ def test_speed_eval_matches_reference(tmp_path):
         ref.summarize()
         assert ref.log == ev.log
         assert ref.stats == ev.stats
+
+
+def test_sa_state_dict_layout_matches_reference_keys():
+    """B200RTDETR registers exactly the tensors of the SA reference's state_dict (636 at rtdetr_r50vd_6x_speed_kl_*.yml;
+    the seeded generator's layout was checked key by key against the live model, tests/test_oracle.py) and loads them
+    with strict=True; parameters stay frozen, sub-modules only hold parameters."""
+    from satellite_pose_estimation_b200.sa_models import B200RTDETR, sa_param_specs
+    sd = synth.make_sa_state_dict(seed=0)
+    specs = sa_param_specs()
+    assert len(specs) == len(sd) == 636
+    assert {n: tuple(s) for n, s, _ in specs} == {k: tuple(v.shape) for k, v in sd.items()}
+    m = B200RTDETR(max_batch=2)
+    assert list(m.state_dict().keys()) and set(m.state_dict().keys()) == set(sd.keys())
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(not p.requires_grad for p in m.parameters())
+    with pytest.raises(RuntimeError):
+        m.train()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 3, 256, 256))          # no CPU fallback

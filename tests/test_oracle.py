@@ -217,3 +217,55 @@ def test_jpeg_ref_matches_pil():
     Image.fromarray(ref, "L").save(buf, "JPEG", progressive=True)
     with pytest.raises(jpeg_ref.Unsupported):
         jpeg_ref.decode(buf.getvalue())
+
+
+# ------------------------------------------------------------------------------------- SA drop: RT-DETR predictor
+def _sa_golden():
+    from oracle.make_golden import SA_MODEL_CASE
+    from oracle import sa_model_ref
+    g = np.load(os.path.join(G, "sa_model_golden.npz"))
+    cfg = sa_model_ref.SaCfg()
+    sd = synth.make_sa_state_dict(cfg, seed=SA_MODEL_CASE["weights_seed"])
+    x = model_inputs(SA_MODEL_CASE["batch"], cfg.input_size, SA_MODEL_CASE["seed"])
+    return g, cfg, sd, x
+
+
+def test_sa_model_oracle_matches_live_reference_golden():
+    """oracle/sa_model_ref.py against outputs of the SA drop's LIVE RTDETR model (PResNet-50-vd, HybridEncoder,
+    RTDETRTransformer; oracle/make_golden.py:write_sa_model): weights regenerated bit-exactly, same anchors selected,
+    outputs of every decoder layer within fp32 noise."""
+    from oracle import sa_model_ref
+    g, cfg, sd, x = _sa_golden()
+    assert synth.weights_checksum(sd) == str(g["weights_sha256"]), "SA weights not regenerated bit-exactly"
+    taps = {}
+    out = sa_model_ref.forward(sd, cfg, x, taps)
+    assert np.array_equal(taps["topk"].numpy(), g["topk"])
+    assert np.abs(taps["enc_scores"].numpy() - g["enc_scores"]).max() < 5e-5
+    assert np.abs(out["pred_logits"].numpy() - g["pred_logits"]).max() < 5e-5
+    assert np.abs(out["pred_pts"].numpy() - g["pred_pts"]).max() < 5e-6
+    assert np.abs(out["pred_sigmas"].numpy() - g["pred_sigmas"]).max() < 5e-5
+    aux = out["aux_outputs"]
+    assert len(aux) == cfg.dec_layers and "pred_sigmas" not in aux[-1]       # last entry: encoder top-k proposals
+    assert np.abs(torch.stack([a["pred_logits"] for a in aux]).numpy() - g["aux_logits"]).max() < 5e-5
+    assert np.abs(torch.stack([a["pred_pts"] for a in aux]).numpy() - g["aux_pts"]).max() < 5e-6
+    assert np.abs(torch.stack([a["pred_sigmas"] for a in aux[:-1]]).numpy() - g["aux_sigmas"]).max() < 5e-5
+    s = out["pred_sigmas"]
+    assert torch.equal(s[..., 0], s[..., 1])          # one log-sigma per query, repeated (rtdetr_decoder.py:367)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference only exists in the build container")
+def test_sa_model_oracle_matches_live_reference():
+    from oracle import sa_model_ref
+    cfg = sa_model_ref.SaCfg()
+    sd = synth.make_sa_state_dict(cfg, seed=3)
+    model = ref_import.build_sa_reference_model(sd)
+    x = model_inputs(2, cfg.input_size, 11)
+    with torch.no_grad():
+        ref = model(x)
+    out = sa_model_ref.forward(sd, cfg, x)
+    for k in ("pred_logits", "pred_pts", "pred_sigmas"):
+        assert (ref[k] - out[k]).abs().max() < 5e-5, k
+    for a, b in zip(ref["aux_outputs"], out["aux_outputs"]):
+        assert set(a) == set(b)
+        for k in a:
+            assert (a[k] - b[k]).abs().max() < 5e-5, k
