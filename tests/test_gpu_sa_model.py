@@ -194,3 +194,24 @@ def test_sa_plain_tf32_trunk_opt_in(lib, cuda_dev, case, monkeypatch):
         assert np.abs(out["pred_logits"].cpu().numpy() - g["pred_logits"]).max() < 2e-2
     finally:
         e.close()
+
+
+def test_sa_whole_path_through_pipeline_slots(eng, case):
+    """crop (256 x 256) -> SA predictor -> sigma-weighted assignment + PnP through spe_submit_batch_dev / spe_collect_batch_host on
+    two slots equals the same three stages called one by one (the pipeline is the same kernels on a slot's own buffers)."""
+    cfg, sd, x, g = case
+    B = 6
+    det = synth.load_detector_boxes()[:B]
+    frames = torch.from_numpy(synth.make_frames(B, det, seed=3)).cuda()
+    boxes = torch.from_numpy(eng.clip_boxes(det)).cuda()
+    imgs = eng.crop_resize_norm(frames, boxes)
+    assert tuple(imgs.shape) == (B, 3, cfg.input_size, cfg.input_size)
+    out = eng.forward_sa(imgs, want_aux=False)
+    r = eng.assign_pnp(out["pred_logits"], out["pred_pts"], boxes, log_sigma=out["pred_sigmas"], reproj=25.0, weighted=True)
+    torch.cuda.synchronize()
+    for slot in (0, 1):
+        eng.submit_batch_dev(slot, frames, boxes, reproj=25.0, weighted=True)
+    for slot in (0, 1):
+        got = eng.collect_batch_host(slot)
+        assert np.array_equal(got["status"], r["status"].cpu().numpy())
+        assert np.allclose(got["quat"], r["quat"].cpu().numpy(), atol=1e-9) and np.allclose(got["tvec"], r["tvec"].cpu().numpy(), atol=1e-9)
