@@ -17,6 +17,8 @@ TF32_BURST = PK.get("bf16_tflops", PK["bf16_tflops_sustained"]) / 2 * 1e12   # t
 HBM = PK["hbm_gbs"] * 1e9
 FOLD = os.environ.get("FOLD", "1") == "1"       # round 2: algebraically folded neck (SPE_FOLD_NECK, default on)
 KV_X3 = os.environ.get("KV_X3", "0") == "1"     # round 2: the K/V projection is plain TF32 once calibrated
+FUSE_DOWN = os.environ.get("FUSE_DOWN", "1") == "1"   # round 2 (r02d on): conv3 + downsample of a layer's first block as one GEMM
+DEC0_FOLD = os.environ.get("DEC0_FOLD", "1") == "1"   # round 2 (r02c on): decoder layer 0's query-only projections precomputed
 
 
 def schedule():
@@ -32,6 +34,11 @@ def schedule():
             Ho = H // s
             add(f"l{li + 1}.{bi}.conv1", B * H * H, pl, inpl)
             add(f"l{li + 1}.{bi}.conv2 3x3", B * Ho * Ho, pl, 9 * pl)
+            if bi == 0 and FUSE_DOWN:
+                # out = relu([t | x sampled at the stride] . [s3 W3 | s_d W_d]^T + b): K = planes + inplanes
+                add(f"l{li + 1}.{bi}.conv3|down (K-concat)", B * Ho * Ho, 4 * pl, pl + inpl)
+                inpl, H = 4 * pl, Ho
+                continue
             if bi == 0:
                 add(f"l{li + 1}.{bi}.down", B * Ho * Ho, 4 * pl, inpl)
             add(f"l{li + 1}.{bi}.conv3+res", B * Ho * Ho, 4 * pl, pl, res=B * Ho * Ho * 4 * pl)
@@ -55,9 +62,10 @@ def schedule():
     add("dec.kv_all" + (" (3xTF32)" if KV_X3 else ""), B * T, 2048, 256, x3=KV_X3)
     Q = 40
     for i in range(4):
-        add(f"dec{i}.sa_qkv x3", B * Q, 768, 256, x3=True)
-        add(f"dec{i}.sa_out x3", B * Q, 256, 256, x3=True)
-        add(f"dec{i}.ca_q x3", B * Q, 256, 256, x3=True)
+        if not (i == 0 and DEC0_FOLD):
+            add(f"dec{i}.sa_qkv x3", B * Q, 768, 256, x3=True)
+            add(f"dec{i}.sa_out x3", B * Q, 256, 256, x3=True)
+            add(f"dec{i}.ca_q x3", B * Q, 256, 256, x3=True)
         add(f"dec{i}.ca_out x3", B * Q, 256, 256, x3=True)
         add(f"dec{i}.ff1 x3", B * Q, 2048, 256, x3=True)
         add(f"dec{i}.ff2 x3", B * Q, 256, 2048, x3=True)

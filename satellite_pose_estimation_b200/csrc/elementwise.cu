@@ -245,7 +245,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
                     long long rows, T* __restrict__ out, int exact, const float* __restrict__ gamma2,
-                    const float* __restrict__ beta2, T* __restrict__ out2) {
+                    const float* __restrict__ beta2, T* __restrict__ out2, float* __restrict__ out32) {
   pdl_wait();
   pdl_launch();
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -276,6 +276,7 @@ layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, c
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * VN;
     Vec<T> r;
+    float yv[VN];
 #pragma unroll
     if (exact == 2) {
       // 3xTF32 operand layout [hi | lo | hi] (row stride 768): the consumer is a plain K = 768 GEMM against
@@ -298,8 +299,16 @@ layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, c
       const float y = (x[i * VN + e] - mean) * rstd * gamma[c + e] + beta[c + e];
       if (exact) r.set_exact(e, y); else r.set(e, y);
       x[i * VN + e] = r.get(e);          // what a second kernel would read back
+      if (out32 != nullptr) yv[e] = rna_tf32(y);
     }
     vstore(out + row * 256 + c, r);
+    if (out32 != nullptr) {
+      // the same rows as fp32 holding TF32 values (bf16 storage: operand + residual of the fused feed-forward kernel,
+      // which is built for fp32 / TF32 -- two more mantissa bits than the bf16 copy)
+#pragma unroll
+      for (int e = 0; e < VN; e += 4)
+        *reinterpret_cast<float4*>(out32 + row * 256 + c + e) = make_float4(yv[e], yv[e + 1], yv[e + 2], yv[e + 3]);
+    }
   }
   if (gamma2 == nullptr) {
     if (out2 != nullptr) {
@@ -578,14 +587,14 @@ std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int 
 
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
                              int dim, void* out, cudaStream_t s, int exact, const float* gamma2, const float* beta2,
-                             void* out2) {
+                             void* out2, float* out_f32) {
   if (dim != 256) return "layernorm: only hidden_dim 256 is built";
   if (rows <= 0) return "";
   ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     SPE_CUDA_TRY(launch_pdl(layernorm256_kernel<T>, dim3(blocks_for(rows, 8)), dim3(256), 0, s,
                             reinterpret_cast<const T*>(in), gamma, beta, rows, reinterpret_cast<T*>(out), exact, gamma2,
-                            beta2, reinterpret_cast<T*>(out2)));
+                            beta2, reinterpret_cast<T*>(out2), out_f32));
   });
   SPE_CUDA_TRY(cudaGetLastError());
   return "";

@@ -41,6 +41,7 @@
 #include "profile.h"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace spe {
 
@@ -435,7 +436,18 @@ ffn_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           y[k].z = (__uint_as_float(v[4 * k + 2]) - mean) * rstd * g4.z + e4.z;
           y[k].w = (__uint_as_float(v[4 * k + 3]) - mean) * rstd * g4.w + e4.w;
         }
-        if (p.out_mode == 2) {
+        if (p.out_mode == 3) {
+          // bf16 storage: the row's 32 columns as 16 packed words (one staged 64-byte segment per row)
+          float4 pk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b0 = __floats2bfloat162_rn(y[2 * k].x, y[2 * k].y), b1 = __floats2bfloat162_rn(y[2 * k].z, y[2 * k].w);
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(y[2 * k + 1].x, y[2 * k + 1].y), b3 = __floats2bfloat162_rn(y[2 * k + 1].z, y[2 * k + 1].w);
+            pk[k] = make_float4(__uint_as_float(*reinterpret_cast<const uint32_t*>(&b0)), __uint_as_float(*reinterpret_cast<const uint32_t*>(&b1)),
+                                __uint_as_float(*reinterpret_cast<const uint32_t*>(&b2)), __uint_as_float(*reinterpret_cast<const uint32_t*>(&b3)));
+          }
+          store_half_block(stage, lane, pk, p.out + row0 * 128 + col0 / 2, nullptr, 128, rows_ok);
+        } else if (p.out_mode == 2) {
           float4 hi[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {

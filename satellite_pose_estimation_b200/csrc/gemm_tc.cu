@@ -1174,14 +1174,15 @@ std::string encode_map_im2col_stem(CUtensorMap* m, Dtype dt, const void* base, i
 }
 
 std::string encode_map_im2col(CUtensorMap* m, Dtype dt, const void* base, int C, int W, int H, int NB, int R, int S,
-                              int pad, int stride, int channels, int pixels) {
+                              int pad, int stride, int channels, int pixels, int c_ld = 0) {
   EncodeIm2colFn fn = get_im2col_fn();
   if (!fn) return "cuTensorMapEncodeIm2col not available";
   const long long es = static_cast<long long>(dtype_size(dt));
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                         static_cast<cuuint64_t>(NB)};
-  cuuint64_t str[3] = {static_cast<cuuint64_t>(C * es), static_cast<cuuint64_t>(W * C * es),
-                       static_cast<cuuint64_t>(static_cast<long long>(H) * W * C * es)};
+  const long long ld = c_ld > 0 ? c_ld : C;    // elements between consecutive pixels (a channel slice of a wider tensor)
+  cuuint64_t str[3] = {static_cast<cuuint64_t>(ld * es), static_cast<cuuint64_t>(W * ld * es),
+                       static_cast<cuuint64_t>(static_cast<long long>(H) * W * ld * es)};
   int lower[2] = {-pad, -pad};
   int upper[2] = {pad - (S - 1), pad - (R - 1)};
   // traversal stride of the base pixel = convolution stride
@@ -1291,7 +1292,8 @@ static std::string launch_conv3(Dtype dt, const GemmDesc& d, int num_sms, cudaSt
   const int es = static_cast<int>(dtype_size(dt));
   const int BK = 128 / es;
   const int cs = d.conv_stride > 0 ? d.conv_stride : 1;
-  if (!env_on || d.mode != 1 || d.R != 3 || d.S != 3 || d.pad != 1 || cs != 1 || d.x3 || d.residual != nullptr)
+  if (!env_on || d.mode != 1 || d.R != 3 || d.S != 3 || d.pad != 1 || cs != 1 || d.x3 || d.residual != nullptr ||
+      (d.c_ld > 0 && d.c_ld != d.C))
     return "skip";
   if ((d.N != 64 && d.N != 128) || d.C % BK != 0 || d.W + 2 > 128 || d.H < 1) return "skip";
   const int Wp = d.W + 2;
@@ -1496,6 +1498,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     }
   } else {
     if (d.C % BK != 0) return "conv: C must be a multiple of the 128-byte k-block";
+    if (d.c_ld > 0 && (d.c_ld < d.C || (static_cast<long long>(d.c_ld) * es) % 16 != 0)) return "conv: bad input pixel stride";
     const int cs = d.conv_stride > 0 ? d.conv_stride : 1;
     if (cs != 1 && cs != 2) return "conv: stride must be 1 or 2";
     const int Ho = (d.H + 2 * d.pad - d.R) / cs + 1, Wo = (d.W + 2 * d.pad - d.S) / cs + 1;
@@ -1516,7 +1519,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
       kp.HW = Ho * Wo; kp.H = Ho; kp.W = Wo; kp.S = d.S; kp.pad = d.pad; kp.cstride = cs;
       kp.kb_per_tap = d.C / BK;
       kp.a_bytes = BM * 128;
-      err = encode_map_im2col(&tmA, dt, d.A, d.C, d.W, d.H, d.NB, d.R, d.S, d.pad, cs, BK, BM);
+      err = encode_map_im2col(&tmA, dt, d.A, d.C, d.W, d.H, d.NB, d.R, d.S, d.pad, cs, BK, BM, d.c_ld);
       if (!err.empty()) return err;
     } else {
     kp.hrows = hrows;
@@ -1533,8 +1536,8 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
     kp.a_bytes = static_cast<uint32_t>(Wo * hrows * 128);
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.C), static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H),
                           static_cast<cuuint64_t>(d.NB)};
-    cuuint64_t str[3] = {static_cast<cuuint64_t>(d.C) * es, static_cast<cuuint64_t>(d.W) * d.C * es,
-                         static_cast<cuuint64_t>(d.H) * d.W * d.C * es};
+    const cuuint64_t cld = static_cast<cuuint64_t>(d.c_ld > 0 ? d.c_ld : d.C);
+    cuuint64_t str[3] = {cld * es, static_cast<cuuint64_t>(d.W) * cld * es, static_cast<cuuint64_t>(d.H) * d.W * cld * es};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(Wo * cs),
                          static_cast<cuuint32_t>(hrows * cs), 1};
     err = encode_map(&tmA, dt, 4, d.A, dims, str, box, cs);

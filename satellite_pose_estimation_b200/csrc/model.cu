@@ -219,6 +219,9 @@ struct Bottleneck {
 
 struct EncLayer {
   GemmW qkv, out, ff1, ff2;
+  // bf16 storage: TF32 copies of the feed-forward weights (own, uncalibrated bias vectors) for the fused feed-forward
+  // kernel, which is built for fp32 / TF32 operands (spe_ctx::mixed_ffn)
+  GemmW ff1_32, ff2_32;
   float* addend = nullptr;  // [tokens, 768]
   float *n1g, *n1b, *n2g, *n2b;
 };
@@ -314,6 +317,11 @@ struct spe_ctx {
        *COL = nullptr, *L2OUT = nullptr, *L3OUT = nullptr, *UP = nullptr, *CAT = nullptr, *FEAT = nullptr,
        *X = nullptr, *X2 = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr, *KV = nullptr;
   bool mixed_attention = getenv("SPE_MIXED_ATTN") ? atoi(getenv("SPE_MIXED_ATTN")) != 0 : true;
+  // bf16 storage: norm1 also writes its rows as fp32 (TF32 values) and the encoder's feed-forward block + norm2 run on
+  // the fused tcgen05 kernel (hidden activation in tensor memory) with a bf16 output, instead of two bf16 GEMMs with the
+  // 2048-wide hidden tensor in HBM and a LayerNorm pass (SPE_MIXED_FFN=0: the bf16 GEMM pair)
+  bool mixed_ffn = getenv("SPE_MIXED_FFN") ? atoi(getenv("SPE_MIXED_FFN")) != 0 : true;
+  float* XF = nullptr;         // [B * tokens, 256] fp32: norm1 output for the fused feed-forward kernel (bf16 storage)
   void *TGT = nullptr, *TGT2 = nullptr, *DQKV = nullptr, *DQ = nullptr, *DATT = nullptr, *DHID = nullptr,
        *HS = nullptr, *H1 = nullptr, *H2 = nullptr, *G1 = nullptr, *G2 = nullptr;
   float *logits_all = nullptr, *points_all = nullptr;
@@ -450,6 +458,23 @@ static std::string upload_gemm_w(spe_ctx* ctx, const std::vector<float>& host, i
   } else {
     cudaFree(tmp);
   }
+  return "";
+}
+
+// host fp32 [N, K] -> device fp32 rounded to TF32, whatever the storage dtype of the ctx
+static std::string upload_tf32_copy(spe_ctx* ctx, const float* host, int N, int K, GemmW* g) {
+  const long long n = static_cast<long long>(N) * K;
+  float* tmp = nullptr;
+  SPE_CUDA_TRY(cudaMalloc(&tmp, static_cast<size_t>(n) * sizeof(float)));
+  cudaError_t e = cudaMemcpy(tmp, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(tmp); return std::string("upload weights: ") + cudaGetErrorString(e); }
+  std::string s = dmalloc_bytes(ctx, &g->w, n * 4);
+  if (!s.empty()) { cudaFree(tmp); return s; }
+  f32_to_tf32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(tmp, reinterpret_cast<float*>(g->w), n);
+  e = cudaDeviceSynchronize();
+  cudaFree(tmp);
+  if (e != cudaSuccess) return std::string("convert weights: ") + cudaGetErrorString(e);
+  g->N = N; g->K = K; g->x3 = 0;
   return "";
 }
 
@@ -751,6 +776,15 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
       TRY_S(load_mha_self(ctx, ws, p + ".self_attn", pos_dev, T, &L.qkv, &L.out, &L.addend));
       TRY_S(load_linear(ctx, ws, p + ".linear1", FF, E, &L.ff1));
       TRY_S(load_linear(ctx, ws, p + ".linear2", E, FF, &L.ff2));
+      if (ctx->dt == kBF16 && ctx->mixed_ffn && ffn_fused_supported(kTF32, E, FF)) {
+        const HostTensor* w1 = ws.get(p + ".linear1.weight", {FF, E});
+        const HostTensor* w2 = ws.get(p + ".linear2.weight", {E, FF});
+        if (!w1 || !w2) return ws.missing;
+        TRY_S(upload_tf32_copy(ctx, w1->data, FF, E, &L.ff1_32));
+        TRY_S(upload_tf32_copy(ctx, w2->data, E, FF, &L.ff2_32));
+        TRY_S(load_vec(ctx, ws, p + ".linear1.bias", FF, &L.ff1_32.bias));
+        TRY_S(load_vec(ctx, ws, p + ".linear2.bias", E, &L.ff2_32.bias));
+      }
       TRY_S(load_vec(ctx, ws, p + ".norm1.weight", E, &L.n1g));
       TRY_S(load_vec(ctx, ws, p + ".norm1.bias", E, &L.n1b));
       TRY_S(load_vec(ctx, ws, p + ".norm2.weight", E, &L.n2g));
@@ -877,6 +911,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
   TRY_S(A(&ctx->X, B * T * 256));
   TRY_S(A(&ctx->X2, B * T * 256));
   if (ctx->dt == kTF32) TRY_S(A(&ctx->XS, B * T * 768));
+  if (ctx->dt == kBF16) TRY_S(AB(reinterpret_cast<void**>(&ctx->XF), B * T * 256 * 4));
   // bf16 storage: the encoder's Q|K|V are written as fp32 (TF32 values) for the tcgen05 attention kernel -> 4 B/element
   TRY_S(A(&ctx->QKV, B * T * 768 * (ctx->dt == kTF32 ? 1 : 2)));
   TRY_S(A(&ctx->ATT, B * T * 256));
@@ -1036,12 +1071,13 @@ struct Fwd {
   }
   // R x R convolution (pad = R/2, stride 1 or 2) as implicit GEMM; H = input extent
   std::string conv(const void* x, int H, int C, int R, int stride, const GemmW& w, void* out, int out_ld,
-                   bool relu, bool exact_out = false) {
+                   bool relu, bool exact_out = false, int c_ld = 0) {
     // the mean is taken over every input position; the zero padding at the border is ignored (second-order)
-    TRY_S(calibrate_layer(x, static_cast<long long>(B) * H * H, C, C, w));
+    TRY_S(calibrate_layer(x, static_cast<long long>(B) * H * H, C, c_ld > 0 ? c_ld : C, w));
     GemmDesc d;
     d.mode = 1;
     d.A = x; d.NB = B; d.H = H; d.W = H; d.C = C; d.R = R; d.S = R; d.pad = R / 2; d.conv_stride = stride;
+    d.c_ld = c_ld;
     d.Wt = w.w; d.N = w.N;
     d.scale = w.scale; d.bias = w.bias;
     d.relu = relu ? 1 : 0;
@@ -1290,6 +1326,23 @@ static std::string forward_trunk(spe_ctx* ctx, const float* images, int B, void*
       TRY_S(f.attn(q32, 768, q32 + 256, 768, q32 + 512, 768, ctx->ATT, Ti, Ti, 0, 1));
     }
     if (!(dbg_skip() & 256)) TRY_S(f.gemm(ctx->ATT, Bl * T, L.out, ctx->X2, 256, false, Xc, 256, 0, 0, true, 0, true));   // feeds LayerNorm only
+    const bool ffn_mixed = f.dt == kBF16 && ctx->mixed_ffn && L.ff1_32.w != nullptr && !ctx->taps_enabled && !ctx->calibrating &&
+                           (Bl * T + 127) / 128 >= ctx->num_sms / 2 && !(dbg_skip() & 4);
+    if (ffn_mixed) {
+      float* XFc = ctx->XF + (static_cast<uint8_t*>(Xc) - static_cast<uint8_t*>(ctx->X)) / 2;   // same row offset, fp32
+      TRY_S(launch_layernorm(f.dt, ctx->X2, L.n1g, L.n1b, Bl * T, 256, Xc, st, 0, nullptr, nullptr, nullptr, XFc));
+      FfnDesc d;
+      d.X = XFc; d.M = Bl * T;
+      d.W1 = L.ff1_32.w; d.b1 = L.ff1_32.bias; d.W2 = L.ff2_32.w; d.b2 = L.ff2_32.bias;
+      d.gamma = L.n2g; d.beta = L.n2b;
+      d.hidden = c.dim_feedforward;
+      d.out = Xc;
+      d.out_mode = 3;
+      TRY_S(launch_ffn_fused(d, ctx->num_sms, st));
+      const std::string nm = "enc" + std::to_string(i);
+      TRY_S(f.tap(nm.c_str(), Xc, Bl * T * 256));
+      continue;
+    }
     TRY_S(f.ln(ctx->X2, L.n1g, L.n1b, Bl * T, Xc, exact_stream_on(ctx) ? 1 : 0));
     // the last encoder output feeds only the (3xTF32) cross-attention K/V projection: emit it pre-split
     const bool last = i == c.enc_layers - 1;

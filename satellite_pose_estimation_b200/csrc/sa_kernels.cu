@@ -180,8 +180,10 @@ small_linear_kernel(const float* __restrict__ x, int ldx, long long rows, int K,
   }
 #pragma unroll
   for (int n = 0; n < 16; ++n) {
+    if (n < N) {                       // warp-uniform
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+      for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    }
   }
   if (lane < N) {
     float v = 0.f;

@@ -20,7 +20,8 @@
 // Same-function rewrites done at weight load (exact in real arithmetic):
 //   * RepVggBlock's 3x3+BN and 1x1+BN branches are one 3x3 convolution + bias (the reference's own
 //     get_equivalent_kernel_bias, hybrid_encoder.py:66-93);
-//   * conv1_1 / conv1_2 have 32 channels: zero-padded to 64 so that every GEMM keeps 128-byte K blocks;
+//   * conv1_1 / conv1_2 have 32 output channels: their weight matrices carry 32 zero rows (the GEMM's narrowest tile
+//     is 64 wide) and the next convolution reads channels [0, 32) of the 64-channel rows (GemmDesc::c_ld);
 //   * the value projections of all decoder layers read the same memory: one GEMM with N = layers x 256;
 //   * sampling_offsets | attention_weights of a layer share their input: one GEMM with N = 192 + 96 (+ 32 zero rows);
 //   * dec_bbox_head[i].layers.0 | sigma_embed[i].layers.0 share their input: one GEMM with N = 512.
@@ -154,9 +155,9 @@ std::string sa_load_weights(spe_ctx* ctx, WeightSource& ws) {
     a.resize(static_cast<size_t>(64) * 32, 0.f);                 // 32 zero output channels
     TRY_S(upload_gemm_w(ctx, a, 64, 32, &m.c11, m.x3));
     TRY_S(sa_load_bn_padded(ctx, ws, "backbone.conv1.conv1_1.norm", 32, 64, &m.c11));
-    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w2, 64, 64), 64, 9 * 64, &m.c12, m.x3));
+    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w2, 64, 32), 64, 9 * 32, &m.c12, m.x3));
     TRY_S(sa_load_bn_padded(ctx, ws, "backbone.conv1.conv1_2.norm", 32, 64, &m.c12));
-    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w3, 64, 64), 64, 9 * 64, &m.c13, m.x3));
+    TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w3, 64, 32), 64, 9 * 32, &m.c13, m.x3));
     TRY_S(sa_load_bn_padded(ctx, ws, "backbone.conv1.conv1_3.norm", 64, 64, &m.c13));
   }
   m.blocks.clear();
@@ -477,8 +478,9 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
   const int rnd = m.x3 ? 0 : 1;
   TRY_S(launch_sa_stem_im2col(images, Bi, R, R, SaFwd::F(m.IM2), rnd, st));
   TRY_S(s.gemm(m.IM2, 32, B * h2 * h2, m.c11, m.SA0, 64, true, false));
-  TRY_S(f.conv(m.SA0, h2, 64, 3, 1, m.c12, m.SA1, 64, true));
-  TRY_S(f.conv(m.SA1, h2, 64, 3, 1, m.c13, m.SA0, 64, true));
+  // conv1_1 / conv1_2 write 64-channel rows whose upper half is zero; their consumers read channels [0, 32) only
+  TRY_S(f.conv(m.SA0, h2, 32, 3, 1, m.c12, m.SA1, 64, true, false, 64));
+  TRY_S(f.conv(m.SA1, h2, 32, 3, 1, m.c13, m.SA0, 64, true, false, 64));
   TRY_S(f.tap("sa_stem", m.SA0, B * h2 * h2 * 64));
   TRY_S(launch_maxpool3x3s2(kTF32, m.SA0, Bi, h2, h2, 64, m.P0, st));
 

@@ -23,6 +23,7 @@ struct GemmDesc {
   // mode 1: A = activation [NB, H, W, C]; K = R*S*C; M = NB*H*W
   int NB = 0, H = 0, W = 0, C = 0, R = 1, S = 1, pad = 0;   // H, W = input extent
   int conv_stride = 1;            // 1 or 2 (TMA traversal stride); output extent = (H + 2 pad - R) / stride + 1
+  int c_ld = 0;                   // mode 1: elements between consecutive input pixels (0 = C): channels [0, C) of a wider tensor
   // weights Wt[N, K] row-major (K contiguous)
   const void* Wt = nullptr;
   int N = 0;
@@ -67,7 +68,8 @@ std::string launch_upsample_tapsum(Dtype dt, const float* Y, int NB, int H, int 
 // exact = 0: fp32 storage is TF32-rounded; 1: full fp32 result; 2: 3xTF32 operand layout [hi | lo | hi], row stride 768
 std::string launch_layernorm(Dtype dt, const void* in, const float* gamma, const float* beta, long long rows,
                              int dim, void* out, cudaStream_t s, int exact = 0, const float* gamma2 = nullptr,
-                             const float* beta2 = nullptr, void* out2 = nullptr);   // 2: a second LayerNorm of the result -> out2
+                             const float* beta2 = nullptr, void* out2 = nullptr,    // 2: a second LayerNorm of the result -> out2
+                             float* out_f32 = nullptr);   // also the rows as fp32 [rows, 256] holding TF32 values
 
 // ---- attention (attention.cu) ----
 struct AttnDesc {
@@ -101,7 +103,7 @@ struct FfnDesc {
   const float* gamma = nullptr;
   const float* beta = nullptr;
   void* out = nullptr;          // may alias X (each tile is read completely before it is written)
-  int out_mode = 0;             // 0: rounded to TF32, 1: exact fp32, 2: [M, 768] = [hi | lo | hi]
+  int out_mode = 0;             // 0: rounded to TF32, 1: exact fp32, 2: [M, 768] = [hi | lo | hi], 3: bf16 [M, 256]
   int hidden = 0;
 };
 bool ffn_fused_supported(Dtype dt, int d_model, int hidden);

@@ -176,7 +176,7 @@ def test_gemm_3xtf32_reaches_fp32_accuracy(lib, cuda_dev, M, N, K, relu, res_mod
 
 
 @pytest.mark.parametrize("M,hidden,mode", [(128, 256, 0), (784, 2048, 0), (3 * 784, 2048, 2), (1000, 512, 1),
-                                           (50176, 2048, 0)])
+                                           (50176, 2048, 0), (1000, 2048, 3), (50176, 2048, 3)])
 def test_fused_ffn_layernorm(lib, cuda_dev, M, hidden, mode):
     """LayerNorm(X + relu(X W1^T + b1) W2^T + b2) in one kernel (hidden tile in tensor memory) vs fp64 on the same
     TF32-rounded operands; ragged last tile, several tiles per CTA, in-place output, 3xTF32 operand form."""
@@ -191,12 +191,18 @@ def test_fused_ffn_layernorm(lib, cuda_dev, M, hidden, mode):
     ref = (v - v.mean(1, keepdim=True)) / torch.sqrt(v.var(1, unbiased=False, keepdim=True) + 1e-5) * g.double() + be.double()
     if mode == 2:
         out = torch.full((M, 768), float("nan"), device=cuda_dev)
+    elif mode == 3:                                       # bf16 output (bf16 storage with the fp32 / TF32 feed-forward)
+        out = torch.full((M, 256), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
     else:
         out = X.clone()                                   # in place, like the encoder schedule
-    src = X if mode == 2 else out
+    src = X if mode in (2, 3) else out
     assert lib.spe_debug_ffn(_p(src), M, _p(W1), _p(b1), _p(W2), _p(b2), _p(g), _p(be), hidden, mode, _p(out), None) == 0
     torch.cuda.synchronize()
-    assert not torch.isnan(out).any()
+    assert not torch.isnan(out.float()).any()
+    if mode == 3:
+        got = out.double()
+        assert ((got - ref).abs() <= 1e-3 + 2.0 ** -8 * ref.abs()).all()      # bf16 rounding of the result
+        return
     if mode == 2:
         hi, lo, hi2 = out[:, :256], out[:, 256:512], out[:, 512:]
         assert torch.equal(hi, hi2) and torch.equal(hi, _rna_tf32(hi))
