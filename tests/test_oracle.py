@@ -269,3 +269,23 @@ def test_sa_model_oracle_matches_live_reference():
         assert set(a) == set(b)
         for k in a:
             assert (a[k] - b[k]).abs().max() < 5e-5, k
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference only exists in the build container")
+def test_sa_postprocess_restatement_matches_live_postprocessor():
+    """``pnp_ref.post_process`` (+ exp of the log-sigmas) against the SA drop's own ``RTDETRPostProcessor.forward``
+    (SA/src/zoo/rtdetr/rtdetr_postprocessor.py:43-78), imported live: probabilities, pixel keypoints, sigmas."""
+    ref_import.import_sa_rtdetr()
+    from src.zoo.rtdetr.rtdetr_postprocessor import RTDETRPostProcessor
+    rng = np.random.default_rng(17)
+    B, Q = 3, 30
+    out = {"pred_logits": torch.from_numpy(rng.standard_normal((B, Q, 12)).astype(np.float32) * 3),
+           "pred_pts": torch.from_numpy(rng.random((B, Q, 2)).astype(np.float32)),
+           "pred_sigmas": torch.from_numpy(rng.standard_normal((B, Q, 2)).astype(np.float32))}
+    boxes = [torch.tensor([100, 50, 612, 562]), torch.tensor([-40, 300, 700, 1040]), torch.tensor([900, 200, 1500, 800])]
+    live = RTDETRPostProcessor(num_classes=11)({k: v.clone() for k, v in out.items()}, boxes)
+    mine = pnp_ref.post_process(out["pred_logits"], out["pred_pts"], boxes)
+    for i in range(B):
+        assert np.abs(live[i]["logits"] - mine[i]["logits"]).max() < 1e-6
+        assert np.abs(live[i]["points"] - mine[i]["points"]).max() < 1e-3
+        assert np.abs(live[i]["sigmas"] - np.exp(out["pred_sigmas"][i].numpy())).max() < 1e-5
