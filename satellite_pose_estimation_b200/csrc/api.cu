@@ -25,6 +25,7 @@ void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points, co
 int set_error(spe_ctx* ctx, int code, const std::string& msg);
 int forward_half(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits, float* points,
                  float* logsig, cudaStream_t st);
+void* stem_input_buffer(spe_ctx* ctx, int slot, int* is_bf16);
 }  // namespace spe
 
 using namespace spe;
@@ -378,10 +379,18 @@ static int pipe_enqueue(spe_ctx* ctx, const char* who, int slot, const PipelineB
   cudaStream_t st = S.compute;
   cudaError_t e = cudaStreamWaitEvent(st, ready, 0);
   if (e != cudaSuccess) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
-  int rc = spe_crop_resize_norm(ctx, frames_dev, H, W, pitch, frame_stride, boxes_dev, B, pb.R, S.images_dev, st);
-  if (rc != SPE_OK) return rc;
+  // the crop writes the predictor's padded stem input of this slot directly when it can (staged kernel, windowed stem)
+  int stem_bf16 = 0;
+  void* stem_buf = stem_input_buffer(ctx, slot, &stem_bf16);
+  bool stem_written = false;
+  {
+    const std::string s = launch_crop_resize_norm(frames_dev, H, W, pitch, frame_stride, boxes_dev, B, pb.R, S.images_dev, st,
+                                                  stem_buf, stem_bf16, &stem_written);
+    if (!s.empty()) return set_error(ctx, SPE_ERR_CUDA, std::string(who) + ": crop: " + s);
+  }
+  int rc;
   const bool sig = pb.has_sigma != 0;
-  rc = forward_half(ctx, 3, slot, S.images_dev, B, S.logits_dev, S.points_dev, sig ? S.logsig_dev : nullptr, st);
+  rc = forward_half(ctx, stem_written ? 7 : 3, slot, S.images_dev, B, S.logits_dev, S.points_dev, sig ? S.logsig_dev : nullptr, st);
   if (rc != SPE_OK) return rc;
   spe_pnp_params pp = *params;
   if (!sig) pp.weighted = 0;

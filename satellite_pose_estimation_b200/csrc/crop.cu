@@ -13,6 +13,8 @@
 // The gray frame is read once per tap through the read-only path; the three output channels are the same
 // uint8 value pushed through three per-channel affine maps, exactly like the reference's replicated RGB image.
 #include "spe_internal.h"
+
+#include <cuda_bf16.h>
 #include "profile.h"
 #include "spe_ptx.cuh"
 
@@ -147,7 +149,8 @@ crop_resize_norm_kernel(const uint8_t* __restrict__ frames, int H, int W, long l
 // boundaries; rows outside the frame are not loaded (their weight path is skipped, zero canvas).
 __global__ void __launch_bounds__(256, 3)
 crop_resize_norm_staged_kernel(const uint8_t* __restrict__ frames, int H, int W, long long pitch, long long frame_stride,
-                               const int32_t* __restrict__ boxes, int R, float* __restrict__ out, int row_stride) {
+                               const int32_t* __restrict__ boxes, int R, float* __restrict__ out, int row_stride,
+                               void* __restrict__ stem_out, int stem_bf16) {
   extern __shared__ __align__(16) uint8_t s_rows[];      // [kCropRows * 4][row_stride]
   __shared__ double s_wy[kCropRows][4];
   __shared__ int s_gy[kCropRows][4];          // frame row of each vertical tap, -1 = outside the frame (zero canvas)
@@ -254,6 +257,25 @@ crop_resize_norm_staged_kernel(const uint8_t* __restrict__ frames, int H, int W,
       iv = __double2loint(magic);
       iv = iv < 0 ? 0 : (iv > 255 ? 255 : iv);
     }
+    if (stem_out != nullptr) {
+      // the predictor's stem input directly: zero-bordered NHWC with the three channels padded to 16 bytes (what
+      // stem_pad_kernel would make of the NCHW tensor, same rounding) -- the border was zeroed when the buffer was allocated
+      const long long Rp = R + 6;
+      const long long pix = (static_cast<long long>(b) * Rp + (oy0 + r + 3)) * Rp + (ox + 3);
+      if (!stem_bf16) {
+        uint32_t a0, a1, a2;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a0) : "f"(s_norm[0][iv]));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a1) : "f"(s_norm[1][iv]));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a2) : "f"(s_norm[2][iv]));
+        reinterpret_cast<uint4*>(stem_out)[pix] = make_uint4(a0, a1, a2, 0u);
+      } else {
+        const __nv_bfloat162 p01 = __floats2bfloat162_rn(s_norm[0][iv], s_norm[1][iv]);
+        const __nv_bfloat162 p2z = __floats2bfloat162_rn(s_norm[2][iv], 0.f);
+        reinterpret_cast<uint4*>(stem_out)[pix] = make_uint4(*reinterpret_cast<const uint32_t*>(&p01),
+                                                              *reinterpret_cast<const uint32_t*>(&p2z), 0u, 0u);
+      }
+      continue;
+    }
     o[0] = s_norm[0][iv];
     o[plane] = s_norm[1][iv];
     o[2 * plane] = s_norm[2][iv];
@@ -263,7 +285,9 @@ crop_resize_norm_staged_kernel(const uint8_t* __restrict__ frames, int H, int W,
 }  // namespace
 
 std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long long pitch, long long frame_stride,
-                                    const int32_t* boxes, int B, int R, float* out_nchw, cudaStream_t s) {
+                                    const int32_t* boxes, int B, int R, float* out_nchw, cudaStream_t s, void* stem_out,
+                                    int stem_bf16, bool* stem_written) {
+  if (stem_written) *stem_written = false;
   if (B <= 0) return "";
   if (R <= 0 || R > 4096) return "crop: bad output size";
   const int tx = R >= 256 ? 256 : ((R + 31) / 32) * 32;
@@ -283,7 +307,9 @@ std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long lo
       SPE_CUDA_TRY(cudaFuncSetAttribute(crop_resize_norm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       attr = true;
     }
-    crop_resize_norm_staged_kernel<<<grid, block, smem, s>>>(frames, H, W, pitch, frame_stride, boxes, R, out_nchw, row_stride);
+    crop_resize_norm_staged_kernel<<<grid, block, smem, s>>>(frames, H, W, pitch, frame_stride, boxes, R, out_nchw, row_stride,
+                                                             stem_out, stem_bf16);
+    if (stem_written) *stem_written = stem_out != nullptr;
   } else {
     crop_resize_norm_kernel<<<grid, block, 0, s>>>(frames, H, W, pitch, frame_stride, boxes, R, out_nchw);
   }

@@ -272,6 +272,10 @@ struct spe_ctx {
   GemmW stem;                  // im2col form [64, 192]
   GemmW stem2;                 // TMA-window form [64, 7 rows x 8 taps x Cp]
   bool stem_windowed = true;   // cleared if the overlapping-window tensor map is refused by the driver
+  // pipeline slots: the crop kernel writes the padded stem input (SP) itself and the schedule skips stem_pad_kernel
+  // (one launch and a 38 MB write + read per batch of 64 less; SPE_CROP_STEM=0 restores the NCHW hand-over)
+  bool crop_writes_stem = getenv("SPE_CROP_STEM") ? atoi(getenv("SPE_CROP_STEM")) != 0 : true;
+  bool stem_prefilled = false; // set for the duration of one forward_schedule call (parts bit 2)
   void* SP = nullptr;          // padded NHWC-Cp stem input
   std::vector<Bottleneck> blocks;
   GemmW s8_lat, s16_lat, out_conv, input_proj;
@@ -929,6 +933,7 @@ std::string alloc_workspace(spe_ctx* ctx) {
   TRY_S(A(&ctx->G1, B * Q * 256));
   TRY_S(A(&ctx->G2, B * Q * 256));
   }
+  if (ctx->SP != nullptr) SPE_CUDA_TRY(cudaMemset(ctx->SP, 0, static_cast<size_t>(B * (R + 6) * (R + 6) * 16)));   // zero border
   {
     std::vector<void*> set0;
     for (const auto& f : ctx->ws_fields) set0.push_back(*f.field);
@@ -1193,7 +1198,7 @@ static std::string trunk_head(spe_ctx* ctx, const float* images, int B, void* l1
   }
   bool stem_done = false;
   if (ctx->stem_windowed) {
-    TRY_S(launch_stem_pad(f.dt, images, B, R, R, ctx->SP, st));
+    if (!(ctx->stem_prefilled && !ctx->calibrating && !ctx->taps_enabled)) TRY_S(launch_stem_pad(f.dt, images, B, R, R, ctx->SP, st));
     GemmDesc d;
     d.mode = 2;
     d.A = ctx->SP; d.NB = B; d.H = R; d.W = R; d.C = 16 / static_cast<int>(f.es);
@@ -1205,6 +1210,8 @@ static std::string trunk_head(spe_ctx* ctx, const float* images, int B, void* l1
     else return e;
   }
   if (!stem_done) {
+    if (ctx->stem_prefilled)
+      return "stem: the windowed tensor map was refused although the crop kernel already wrote the padded layout (SPE_CROP_STEM=0 avoids this)";
     TRY_S(launch_stem_im2col(f.dt, images, B, R, R, ctx->S0, st));
     {
       const bool cal = ctx->calibrating;
@@ -1516,6 +1523,7 @@ static std::string use_workspace(spe_ctx* ctx, int set) {
         for (void* q : ns) cudaFree(q);
         return "out of device memory (activation set " + std::to_string(ctx->ws_sets.size()) + ")";
       }
+      if (f.field == &ctx->SP) cudaMemset(p, 0, static_cast<size_t>(f.bytes));   // zero border of the stem input (crop writes the interior)
       ns.push_back(p);
     }
     for (void* q : ns) ctx->allocs.push_back(q);
@@ -1533,6 +1541,12 @@ static std::string forward_schedule(spe_ctx* ctx, int parts, int kv_slot, const 
                                     float* points, float* logsig, float* aux_logits, float* aux_points,
                                     cudaStream_t st) {
   TRY_S(use_workspace(ctx, kv_slot));
+  struct PrefillScope {            // parts bit 2: the crop kernel already wrote this slot's stem input
+    spe_ctx* c;
+    ~PrefillScope() { c->stem_prefilled = false; }
+  } prefill_scope{ctx};
+  ctx->stem_prefilled = (parts & 4) != 0;
+  parts &= 3;
   if (ctx->cfg.backbone == 2) {
     if (aux_logits != nullptr || aux_points != nullptr) return "the SA predictor returns its aux outputs through spe_forward_sa";
     if (parts != 3) return "the SA predictor runs as one schedule (parts = 3)";
@@ -1882,6 +1896,15 @@ void set_pnp_override(spe_ctx* ctx, const float* logits, const float* points, co
   ctx->ov_boxes = boxes;
 }
 int set_error(spe_ctx* ctx, int code, const std::string& msg) { return fail(ctx, code, msg); }
+// the stem input buffer of activation set `slot` when the crop kernel may write it directly (else null)
+void* stem_input_buffer(spe_ctx* ctx, int slot, int* is_bf16) {
+  if (!ctx->crop_writes_stem || ctx->cfg.backbone == 2 || !ctx->stem_windowed || ctx->head_chunk > 0 || ctx->taps_enabled ||
+      ctx->calibrating || ctx->sub_batch > 0)
+    return nullptr;
+  if (!use_workspace(ctx, slot).empty()) return nullptr;
+  *is_bf16 = ctx->dt == kBF16 ? 1 : 0;
+  return ctx->SP;
+}
 // the forward (parts: 1 = trunk + decoder K/V, 2 = decoder + heads, 3 = both) on activation set `kv_slot`
 int forward_half(spe_ctx* ctx, int parts, int kv_slot, const float* images, int B, float* logits, float* points,
                  float* logsig, cudaStream_t st) {

@@ -145,8 +145,12 @@ std::string launch_sa_head(const float* tgt, const float* h2, const float* g2, c
 std::string launch_add(const float* a, const float* b, float* out, long long n, cudaStream_t s);
 
 // ---- crop (crop.cu) ----
+// stem_out (optional): write the predictor's stem input instead of the NCHW tensor -- zero-bordered NHWC [B, R+6, R+6]
+// pixels of 16 bytes (3 channels + padding; fp32 rounded to TF32, or bf16), border already zero.  Only the staged kernel
+// does that: *stem_written tells whether it ran (otherwise out_nchw was written as usual).
 std::string launch_crop_resize_norm(const uint8_t* frames, int H, int W, long long pitch, long long frame_stride,
-                                    const int32_t* boxes, int B, int R, float* out_nchw, cudaStream_t s);
+                                    const int32_t* boxes, int B, int R, float* out_nchw, cudaStream_t s,
+                                    void* stem_out = nullptr, int stem_bf16 = 0, bool* stem_written = nullptr);
 
 // ---- pnp (pnp.cu) ----
 struct PnpDesc {
