@@ -1,5 +1,5 @@
 """Throughput of the GPU JPEG decode: B synthetic SPEED-sized frames, PIL-encoded, decoded as one batch.
-    python tools/jpeg_probe.py [B] [quality]
+    python tests/probes/jpeg_probe.py [B] [quality]
 """
 import io
 import os
@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from PIL import Image
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import synth                                         # noqa: E402  (synthetic frames only)
 from satellite_pose_estimation_b200 import Engine               # noqa: E402
 

@@ -1,7 +1,7 @@
 """Stand-alone launches of the crop kernel (64 frames of bench.py's frame set 0, real box distribution) and of the encoder
 self-attention shape (B = 64, 8 heads, 784 x 784, d = 32) for `ncu --set full` captures (profiles/r02_ncu_*.md).
 
-    python tools/ncu_probe_r02.py [reps]
+    python tests/probes/ncu_probe_r02.py [reps]
 """
 import ctypes as C
 import os
@@ -9,7 +9,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import synth                                         # noqa: E402  (synthetic frames only)
 from satellite_pose_estimation_b200 import Engine, _lib          # noqa: E402
 

@@ -1,12 +1,12 @@
 """GPU bring-up probe for the SA (RT-DETR) predictor: per-stage error of the CUDA schedule against the oracle's taps.
-Not collected by pytest (run: python tests/sa_bringup.py [B])."""
+Not collected by pytest (run: python tests/probes/sa_bringup.py [B])."""
 import os
 import sys
 import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import sa_model_ref, synth  # noqa: E402
 from satellite_pose_estimation_b200 import Engine  # noqa: E402
 

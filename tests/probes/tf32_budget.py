@@ -4,7 +4,7 @@
 Runs the oracle forward with cvt.rna.tf32 rounding applied to the operands (activations AND weights) of the GEMMs /
 convolutions of ONE stage group at a time (fp32 accumulation, everything else exact) and reports the resulting keypoint
 error in pixels at the largest crop side (1748 px).  The decoder and the heads run 3xTF32 on the GPU (error ~1e-6) and
-are therefore treated as exact.  Usage: python tools/tf32_budget.py [n_images] [--spread]
+are therefore treated as exact.  Usage: python tests/probes/tf32_budget.py [n_images] [--spread]
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import crop_ref, model_ref, synth  # noqa: E402
 
 

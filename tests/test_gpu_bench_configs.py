@@ -8,7 +8,7 @@ Two weight sets:
   * the same trunk with calibrated heads (oracle/make_chain_fixture.py) whose queries emit 11 distinct labels at a
     PnP-consistent layout, so that crop -> predictor -> assignment -> PnP is checked as ONE chain on the network's own
     output against the reference's own PostProcess + SimplePoseSolver.
-Bars are stated where they are asserted; tools/parity_report.py prints the full statistics (profiles/r02_parity.json).
+Bars are stated where they are asserted; tests/probes/parity_report.py prints the full statistics (profiles/r02_parity.json).
 """
 import os
 

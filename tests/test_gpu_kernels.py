@@ -246,3 +246,28 @@ def test_gemm_with_a_second_operand_source(lib, cuda_dev, dt, NB, H, K1, K2, N, 
     ref = torch.relu(t.double() @ w[:, :K1].double().T + xs.double() @ w[:, K1:].double().T + bias.double())
     assert not torch.isnan(out.float()).any()
     assert _rel(out.float(), ref) < (2e-3 if dt == 0 else 8e-3)
+
+
+def _split_tf32(w):
+    hi = _rna_tf32(w)
+    return torch.cat([hi, _rna_tf32(w - hi)], 1).contiguous()
+
+
+@pytest.mark.parametrize("NB,H,Cin,Cout,stride", [(2, 128, 64, 64, 1), (2, 64, 128, 128, 2), (2, 32, 128, 128, 1), (2, 16, 256, 256, 1),
+                                                  (2, 16, 512, 512, 2), (3, 8, 128, 128, 1), (2, 8, 512, 512, 1)])
+def test_implicit_conv3x3_3xtf32(lib, cuda_dev, NB, H, Cin, Cout, stride):
+    """Error-compensated 3xTF32 on the implicit-convolution modes (row-block boxes, im2col tensor maps, stride 2; the SA
+    predictor's shapes down to its 8 x 8 maps) with folded-BN scale / bias + ReLU, against fp64: fp32-grade results."""
+    torch.manual_seed(H * Cin + stride)
+    x = torch.randn(NB, H, H, Cin, device=cuda_dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=cuda_dev) / (9 * Cin) ** 0.5
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    sc, bi = torch.rand(Cout, device=cuda_dev) + 0.5, torch.randn(Cout, device=cuda_dev)
+    Ho = (H + 2 - 3) // stride + 1
+    out = torch.full((NB, Ho, Ho, Cout), float("nan"), device=cuda_dev)
+    assert lib.spe_debug_conv(2, _p(x), _p(_split_tf32(wk)), NB, H, H, Cin, Cout, 3, 3, 1, stride, _p(sc), _p(bi), 1, _p(out), None) == 0
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), None, stride=stride, padding=1)
+    ref = (ref * sc.double()[None, :, None, None] + bi.double()[None, :, None, None]).clamp_min(0).permute(0, 2, 3, 1)
+    assert not torch.isnan(out).any()
+    assert _rel(out, ref) < 6e-5       # plain TF32 sits at ~5e-4; fp32 accumulation over up to 4608 products
