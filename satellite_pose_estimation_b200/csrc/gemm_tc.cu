@@ -162,7 +162,9 @@ __device__ __forceinline__ void store_chunk(float (&f)[NIT][G], uint8_t* gp, con
 
 // One 128 x BN accumulator tile of one epilogue warp: rows [q*32, q*32+32) of the tile (its TMEM lane quarter), column
 // chunks half, half + CSTEP, ...  `taddr` = TMEM address of the warp's lane quarter in the accumulator buffer.
-template <typename T, int BN, int CSTEP, bool REMAP = false>
+// ACT: the instantiation also knows SiLU (relu == 2) and GELU (relu == 3) -- only the 3xTF32 kernels carry it (the SA
+// predictor's ConvNormLayer / AIFI activations), so the plain-TF32 / bf16 epilogues keep their register budget.
+template <typename T, int BN, int CSTEP, bool REMAP = false, bool ACT = false>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg, const int lane, const int q,
                                               const int half, const uint32_t taddr, const int valid_rows,
                                               const long long m_base, const int n0, const float* s_scale,
@@ -192,7 +194,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
                                  : 0;
   const uint8_t* res_base = reinterpret_cast<const uint8_t*>(p.residual);
   // which store_chunk instance this tile uses (uniform over the warp)
-  const int variant = (p.relu ? 1 : 0) | ((sizeof(T) == 4 && p.round_out) ? 2 : 0) | (rows_here >= 32 ? 4 : 0);
+  const int variant = (p.relu == 1 ? 1 : 0) | ((sizeof(T) == 4 && p.round_out) ? 2 : 0) | (rows_here >= 32 ? 4 : 0);
   // this lane's staging addresses (byte offsets): its own row for the transposing write, its column group for reads
   const uint32_t stg_w = smem_u32(stg) + lane * 128;
   const int wsw = lane & 7;
@@ -299,6 +301,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
     const long long k4 = GEMM_CLOCK();
     if (resid && c + CSTEP < BN / 32) fetch_residual(ncol + 32 * CSTEP);   // next chunk, in flight during the stores
     const long long k5 = GEMM_CLOCK();
+    if constexpr (ACT) {
+      if (p.relu == 2) {                                   // SiLU
+#pragma unroll
+        for (int i = 0; i < NIT; ++i)
+#pragma unroll
+          for (int u = 0; u < G; ++u) f[i][u] = f[i][u] / (1.f + expf(-f[i][u]));
+      } else if (p.relu == 3) {                            // GELU, erf form (nn.GELU default)
+#pragma unroll
+        for (int i = 0; i < NIT; ++i)
+#pragma unroll
+          for (int u = 0; u < G; ++u) f[i][u] = 0.5f * f[i][u] * (1.f + erff(f[i][u] * 0.70710678118654752f));
+      }
+    }
     if constexpr (REMAP) {
       // accumulator row r is pixel (h, w) = (r / Wp, r % Wp) of the padded grid; columns w >= W are the halo (their
       // values are meaningless) and valid_rows counts the image rows of this sub-tile that exist
@@ -309,7 +324,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint8_t* stg
           const int hl = r / p.remap_wp;
           const int w = r - hl * p.remap_wp;
           if (w < p.W && hl < valid_rows) {
-            if (p.relu) {
+            if (p.relu == 1) {
 #pragma unroll
               for (int u = 0; u < G; ++u) f[i][u] = fmaxf(f[i][u], 0.0f);
             }
@@ -623,7 +638,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long c2 = GEMM_CLOCK();
       tc_fence_after();
 
-      epilogue_tile<T, BN, CSTEP>(p, sm_staging + (warp - 2) * 4096, lane, q, half,
+      epilogue_tile<T, BN, CSTEP, false, X3>(p, sm_staging + (warp - 2) * 4096, lane, q, half,
                                   tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN),
                                   valid_rows, m_base, n0, s_scale, s_bias, tcs);
       tc_fence_before();
@@ -1374,6 +1389,7 @@ std::string launch_gemm(Dtype dt, const GemmDesc& d, int num_sms, cudaStream_t s
   if (d.out_ld % (16 / es) != 0 && !d.out_f32) return "gemm: out_ld must keep rows 16-byte aligned";
   if (d.x3 && dt != kTF32) return "gemm: 3xTF32 needs fp32 storage";
   if (d.x3 && d.mode == 2) return "gemm: 3xTF32 is not built for the windowed stem";
+  if (d.relu < 0 || d.relu > 3 || (d.relu > 1 && !d.x3)) return "gemm: SiLU / GELU epilogues are only built for 3xTF32";
   if (d.mode < 0 || d.mode > 2) return "gemm: bad mode";
   if (d.A2 != nullptr && (d.mode != 0 || d.x3)) return "gemm: a second operand source needs a plain, uncompensated GEMM";
   if (d.mode == 1) {

@@ -1076,7 +1076,7 @@ struct Fwd {
   }
   // R x R convolution (pad = R/2, stride 1 or 2) as implicit GEMM; H = input extent
   std::string conv(const void* x, int H, int C, int R, int stride, const GemmW& w, void* out, int out_ld,
-                   bool relu, bool exact_out = false, int c_ld = 0) {
+                   bool relu, bool exact_out = false, int c_ld = 0, int act = 0) {
     // the mean is taken over every input position; the zero padding at the border is ignored (second-order)
     TRY_S(calibrate_layer(x, static_cast<long long>(B) * H * H, C, c_ld > 0 ? c_ld : C, w));
     GemmDesc d;
@@ -1085,7 +1085,7 @@ struct Fwd {
     d.c_ld = c_ld;
     d.Wt = w.w; d.N = w.N;
     d.scale = w.scale; d.bias = w.bias;
-    d.relu = relu ? 1 : 0;
+    d.relu = act > 1 ? act : (relu ? 1 : 0);      // act 2 / 3: SiLU / GELU (3xTF32 kernels only)
     d.out = out; d.out_ld = out_ld;
     d.x3 = w.x3;
     d.round_out = (exact_out || w.x3) ? 0 : 1;

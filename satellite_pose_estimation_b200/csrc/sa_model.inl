@@ -44,6 +44,11 @@ struct SaModel {
   // sigmoid(delta + inverse_sigmoid(ref)) three times) turn into up to 0.7 px at a 1748 px crop -- above the 0.5 px bar;
   // the decoder side is always 3xTF32.  SPE_SA_X3=0 selects the plain-TF32 trunk (3x less tensor work).
   bool x3 = getenv("SPE_SA_X3") ? atoi(getenv("SPE_SA_X3")) != 0 : true;
+  // SiLU / GELU inside the epilogue of the 3xTF32 GEMM kernels instead of a separate pass.  MEASURED AND LEFT OFF
+  // (SPE_SA_ACT_EPI=1 enables it): 8.38 vs 7.98 ms per forward at B = 64 -- the 3xTF32 kernels spend their extra warps on
+  // the operand split and keep a four-warp epilogue, which ~10 more instructions per element turn into the long pole of
+  // the K <= 512 layers; the separate pass is a 3 % memory-bound tail.
+  bool act_epi = getenv("SPE_SA_ACT_EPI") ? atoi(getenv("SPE_SA_ACT_EPI")) != 0 : false;
   int shapes_hw[6] = {0, 0, 0, 0, 0, 0};
   GemmW c11, c12, c13;
   std::vector<SaBlock> blocks;
@@ -424,7 +429,7 @@ struct SaFwd {
 
   // out = A W^T (+ bias, BN scale) (+ residual) with an explicit A row stride; exact: leave the result unrounded
   std::string gemm(const void* A, int lda, long long M, const GemmW& w, void* out, int out_ld, bool relu, bool exact,
-                   const void* residual = nullptr, int res_ld = 0, int res_mod = 0, int res_f32 = 0) {
+                   const void* residual = nullptr, int res_ld = 0, int res_mod = 0, int res_f32 = 0, int act = 0) {
     if (lda == w.K) TRY_S(f.calibrate_layer(A, M, w.K, w.K, w));
     GemmDesc d;
     d.mode = 0;
@@ -432,7 +437,7 @@ struct SaFwd {
     d.Wt = w.w; d.N = w.N;
     d.scale = w.scale; d.bias = w.bias;
     d.residual = residual; d.res_ld = res_ld; d.res_mod = res_mod; d.res_f32 = res_f32;
-    d.relu = relu ? 1 : 0;
+    d.relu = act > 1 ? act : (relu ? 1 : 0);     // act 2 / 3: SiLU / GELU in the epilogue (3xTF32 kernels only)
     d.out = out; d.out_ld = out_ld;
     d.x3 = w.x3;
     d.round_out = (w.x3 || exact) ? 0 : 1;
@@ -446,6 +451,7 @@ struct SaFwd {
   }
   // ConvNormLayer 1x1 + SiLU: x [rows, w.K] -> out[:, 0:w.N] (row stride out_ld)
   std::string conv1_silu(const void* x, long long rows, const GemmW& w, void* tmp, void* out, int out_ld) {
+    if (w.x3 && m.act_epi) return gemm(x, w.K, rows, w, out, out_ld, false, true, nullptr, 0, 0, 0, 2);   // SiLU in the epilogue
     TRY_S(gemm(x, w.K, rows, w, tmp, w.N, false, true));
     return act(tmp, w.N, nullptr, 0, out, out_ld, rows, w.N, 1);
   }
@@ -527,8 +533,12 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
     TRY_S(f.attn(m.QKV, 768, SaFwd::col(m.QKV, 256), 768, SaFwd::col(m.QKV, 512), 768, m.ATT, T, T, m.x3 ? 1 : 0, 0, m.x3 ? 1 : 0));
     TRY_S(s.gemm(m.ATT, 256, M32, m.a_out, m.X2, 256, false, true, m.E2, 256));
     TRY_S(f.ln(m.X2, m.an1g, m.an1b, M32, m.E2, m.x3 ? 1 : 0));
-    TRY_S(s.gemm(m.E2, 256, M32, m.a_ff1, m.HID, FF, false, true));
-    TRY_S(s.act(m.HID, FF, nullptr, 0, m.HID, FF, M32, FF, 2));
+    if (m.a_ff1.x3 && m.act_epi) {
+      TRY_S(s.gemm(m.E2, 256, M32, m.a_ff1, m.HID, FF, false, true, nullptr, 0, 0, 0, 3));   // GELU in the epilogue
+    } else {
+      TRY_S(s.gemm(m.E2, 256, M32, m.a_ff1, m.HID, FF, false, true));
+      TRY_S(s.act(m.HID, FF, nullptr, 0, m.HID, FF, M32, FF, 2));
+    }
     TRY_S(s.gemm(m.HID, FF, M32, m.a_ff2, m.X2, 256, false, true, m.E2, 256));
     TRY_S(f.ln(m.X2, m.an2g, m.an2b, M32, m.E2, m.x3 ? 1 : 0));
     TRY_S(f.tap("sa_aifi", m.E2, M32 * 256));

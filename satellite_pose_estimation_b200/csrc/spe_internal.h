@@ -34,7 +34,7 @@ struct GemmDesc {
   int res_ld = 0;
   int res_mod = 0;                // 0: residual row = output row, >0: row % res_mod (batch-broadcast addend)
   int res_f32 = 0;                // residual stored as fp32 even when the storage dtype is bf16
-  int relu = 0;
+  int relu = 0;                   // 0 none, 1 ReLU; 3xTF32 kernels also: 2 SiLU, 3 GELU (erf form)
   void* out = nullptr;            // [M, out_ld] storage dtype
   int out_ld = 0;
   int round_out = 1;              // fp32 storage: round the result to TF32 (its consumer is a kind::tf32 MMA)
