@@ -250,3 +250,12 @@ def build_sa_model(*, input_size=256, num_queries=30, num_decoder_layers=3, hidd
     model.eval()
     post = RTDETRPostProcessor(lambda: model.engine, reproj=reproj, weighted=True, reject=self_assessment)
     return model, post
+
+
+def build_sigma_solver(model=None, postprocessor=None, reproj=25.0, self_assessment=False):
+    """``build_sigma_solver()`` of the SA drop (SA/utils/speed_eval.py:27-28 -> ``SimplePoseSolverSigma``, :322-420):
+    ``solver(points, logits, sigmas) -> (quat, tvec)``, ``IndexError`` when fewer than four keypoints are found or the
+    solve fails.  With the ``model`` / ``postprocessor`` of ``build_sa_model`` it answers from the batched solve the
+    post-processor already launched."""
+    from .solver import BatchedPoseSolver
+    return BatchedPoseSolver(reproj=reproj, weighted=True, reject=self_assessment, post=postprocessor, model=model)

@@ -22,7 +22,7 @@ import torch
 from oracle import pnp_ref, sa_model_ref, synth
 from oracle.make_golden import SA_MODEL_CASE, model_inputs
 from satellite_pose_estimation_b200 import Engine
-from satellite_pose_estimation_b200.sa_models import build_sa_model
+from satellite_pose_estimation_b200.sa_models import build_sa_model, build_sigma_solver
 
 pytestmark = pytest.mark.gpu
 
@@ -173,6 +173,27 @@ def test_sa_model_mirror_and_postprocessor_chain(lib, cuda_dev, case):
         assert np.abs(res[i]["logits"] - want[i]["logits"]).max() < 1e-6
         assert np.array_equal(res[i]["points"], want[i]["points"])
         assert np.abs(res[i]["sigmas"] - np.exp(sig[i].numpy())).max() < 1e-5
+    # per-image solver calls of the SA engine (SA/src/data/speed/speed_dataset.py:399): answered from the batched solve;
+    # seeded random heads emit one label, i.e. fewer than four keypoints -> the reference's IndexError contract
+    solver = build_sigma_solver(model, post)
+    for i in range(3):
+        hit = post.pose_cache[id(res[i]["points"])]
+        if hit[3] == 0:
+            q, t = solver(res[i]["points"], res[i]["logits"], res[i]["sigmas"])
+            assert np.array_equal(q, hit[1]) and np.array_equal(t, hit[2])
+        else:
+            with pytest.raises(IndexError):
+                solver(res[i]["points"], res[i]["logits"], res[i]["sigmas"])
+    # ... and without the cache (a fresh array): the per-image kernel call on post-processed inputs agrees
+    d = synth.make_predictions(4, Q=cfg.num_queries, seed=9, with_sigma=True)
+    r = model.engine.assign_pnp(torch.from_numpy(d["logits"]).cuda(), torch.from_numpy(d["points"]).cuda(),
+                                torch.from_numpy(d["boxes"]).cuda(), log_sigma=torch.from_numpy(d["logsig"]).cuda(),
+                                reproj=25.0, weighted=True, want_post=True)
+    for i in range(4):
+        if int(r["status"][i]) != 0:
+            continue
+        q, t = solver(r["points_px"][i].cpu().numpy().copy(), r["probs"][i].cpu().numpy(), r["sigmas"][i].cpu().numpy())
+        assert np.abs(q - r["quat"][i].cpu().numpy()).max() < 1e-6 and np.abs(t - r["tvec"][i].cpu().numpy()).max() < 1e-5
     model.engine.close()
 
 
