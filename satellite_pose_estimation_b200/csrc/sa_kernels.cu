@@ -83,7 +83,9 @@ __global__ void avgpool2x2_kernel(const float4* __restrict__ in, int H, int W, i
 }
 
 __device__ __forceinline__ float act_apply(float v, int kind) {
-  if (kind == 1) return v / (1.f + expf(-v));                               // SiLU
+  // SiLU: ex2.approx + one approximate division (relative error ~4e-7, far below the 3xTF32 products around it); the
+  // IEEE expf + division made this memory-bound pass issue-bound (ncu r02: SM throughput 80 %, 45 us for 93 MB)
+  if (kind == 1) return __fdividef(v, 1.f + __expf(-v));
   if (kind == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // GELU (erf form, nn.GELU default)
   if (kind == 3) return 1.f / (1.f + expf(-v));                             // sigmoid
   return v;
