@@ -198,6 +198,46 @@ small_linear_kernel(const float* __restrict__ x, int ldx, long long rows, int K,
   }
 }
 
+// The same for the two shapes the SA predictor uses (K = 256; N = 12 class scores, N = 2 keypoint logits) with the
+// weights held in registers and a warp walking `rows_per_warp` rows: the generic kernel re-reads N x 1 KB of weights
+// from L1 for every row (12 KB per 1 KB row at N = 12).  Same summation order per row as the generic kernel.
+template <int N>
+__global__ void __launch_bounds__(256)
+small_linear256_kernel(const float* __restrict__ x, int ldx, long long rows, const float* __restrict__ Wt,
+                       const float* __restrict__ b, float* __restrict__ out, int ldo, const float* __restrict__ addend,
+                       int add_mod, int rows_per_warp) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  float w[N][8];
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[n][j] = Wt[n * 256 + lane + 32 * j];
+  const float bias = lane < N ? (b ? b[lane] : 0.f) : 0.f;
+  const long long r0 = warp * rows_per_warp;
+  for (long long row = r0; row < r0 + rows_per_warp && row < rows; ++row) {
+    const float* xr = x + row * ldx;
+    float xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = xr[lane + 32 * j];
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fmaf(xv[j], w[n][j], a);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (n == lane) mine = a;
+    }
+    if (lane < N) {
+      float v = mine + bias;
+      if (addend) v += addend[(row % add_mod) * N + lane];
+      out[row * ldo + lane] = v;
+    }
+  }
+}
+
 // out[r, j] = relu(W0[j, 0] ref[r, 0] + W0[j, 1] ref[r, 1] + b0[j]),  j < H
 __global__ void query_pos_hidden_kernel(const float* __restrict__ ref, const float* __restrict__ W0,
                                         const float* __restrict__ b0, int Hd, long long total, float* __restrict__ out) {
@@ -334,6 +374,18 @@ std::string launch_small_linear(const float* x, int ldx, long long rows, int K, 
   if (N <= 0 || N > 16) return "small_linear: 1..16 outputs";
   if (rows <= 0) return "";
   ProfScope ps(kFamHeads, s);
+  if (K == 256 && (N == 12 || N == 2) && rows >= 4096) {
+    const int rpw = 16;
+    const long long warps = (rows + rpw - 1) / rpw;
+    if (N == 12)
+      small_linear256_kernel<12><<<blocks_for(warps * 32, 256), 256, 0, s>>>(x, ldx, rows, Wt, b, out, ldo, addend,
+                                                                             add_mod > 0 ? add_mod : 1, rpw);
+    else
+      small_linear256_kernel<2><<<blocks_for(warps * 32, 256), 256, 0, s>>>(x, ldx, rows, Wt, b, out, ldo, addend,
+                                                                            add_mod > 0 ? add_mod : 1, rpw);
+    SPE_CUDA_TRY(cudaGetLastError());
+    return "";
+  }
   small_linear_kernel<<<blocks_for(rows * 32, 256), 256, 0, s>>>(x, ldx, rows, K, Wt, b, N, out, ldo, addend,
                                                                  add_mod > 0 ? add_mod : 1);
   SPE_CUDA_TRY(cudaGetLastError());
