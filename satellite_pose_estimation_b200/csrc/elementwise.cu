@@ -157,14 +157,17 @@ maxpool3x3s2_kernel(const T* __restrict__ in, int H, int W, int C, int Ho, int W
   pdl_wait();
   pdl_launch();
   constexpr int VN = Vec<T>::N;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total_vec) return;
+  // grid (x: vectors of one output row, y: output row, z: image): one 32-bit division per thread -- the flat 64-bit
+  // index decode kept the XU pipe 18 % and the issue slots 72 % busy in a kernel that should only move bytes (ncu r02)
+  (void)total_vec;
   const int cv = C / VN;
-  const int c0 = static_cast<int>(idx % cv) * VN;
-  const long long pix = idx / cv;
-  const int ox = static_cast<int>(pix % Wo);
-  const int oy = static_cast<int>((pix / Wo) % Ho);
-  const long long n = pix / (static_cast<long long>(Wo) * Ho);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= static_cast<unsigned>(Wo * cv)) return;
+  const int ox = static_cast<int>(t / static_cast<unsigned>(cv));
+  const int c0 = static_cast<int>(t - static_cast<unsigned>(ox) * cv) * VN;
+  const int oy = blockIdx.y;
+  const long long n = blockIdx.z;
+  const long long pix = (n * Ho + oy) * Wo + ox;
   float m[VN];
 #pragma unroll
   for (int e = 0; e < VN; ++e) m[e] = -INFINITY;
@@ -463,7 +466,10 @@ std::string launch_maxpool3x3s2(Dtype dt, const void* in, int NB, int H, int W, 
   ProfScope ps(kFamElementwise, s);
   DISPATCH_T(dt, {
     const long long total = static_cast<long long>(NB) * Ho * Wo * (C / Vec<T>::N);
-    SPE_CUDA_TRY(launch_pdl(maxpool3x3s2_kernel<T>, dim3(blocks_for(total, 256)), dim3(256), 0, s,
+    const int row_vecs = Wo * (C / Vec<T>::N);
+    const int threads = row_vecs >= 256 ? 256 : ((row_vecs + 31) / 32) * 32;
+    if (Ho > 65535 || NB > 65535) return "maxpool: extent outside the launch grid";
+    SPE_CUDA_TRY(launch_pdl(maxpool3x3s2_kernel<T>, dim3((row_vecs + threads - 1) / threads, Ho, NB), dim3(threads), 0, s,
                             reinterpret_cast<const T*>(in), H, W, C, Ho, Wo, total, reinterpret_cast<T*>(out)));
   });
   SPE_CUDA_TRY(cudaGetLastError());
