@@ -249,17 +249,17 @@ long long spe_last_h2d_bytes(spe_ctx* ctx);
 int spe_debug_gemm(int dtype, const void* A_dev, const void* W_dev, long long M, int N, int K, const float* scale_dev,
                    const float* bias_dev, const void* residual_dev, int res_mod, int relu, void* out_dev,
                    void* stream);
-/* convolution (stride 1 or 2) as implicit GEMM: x [NB,H,W,C] NHWC, w [Cout, R*S*C] (tap-major, channel-minor),
- * out [NB,Ho,Wo,Cout] with Ho = (H + 2 pad - R) / stride + 1 */
 /* out[M, N] = act([A | A2] . Wt^T + bias): A [M, K]; A2 either [M, K2] (a2_stride 1) or the (2h, 2w) sampling of an NHWC
  * activation [NB, H, W, K2] with M = NB * ceil(H/2) * ceil(W/2) (a2_stride 2); Wt [N, K + K2] */
 int spe_debug_gemm2(int dtype, const void* A_dev, int K, const void* A2_dev, int K2, int a2_stride, int NB, int H, int W,
                     const void* Wt_dev, long long M, int N, const float* bias_dev, int relu, void* out_dev, void* stream);
+/* convolution (stride 1 or 2) as implicit GEMM: x [NB,H,W,C] NHWC, w [Cout, R*S*C] (tap-major, channel-minor),
+ * out [NB,Ho,Wo,Cout] with Ho = (H + 2 pad - R) / stride + 1; dtype as in spe_debug_gemm (2: w is [Cout, 2*R*S*C]) */
 int spe_debug_conv(int dtype, const void* x_dev, const void* w_dev, int NB, int H, int W, int C, int Cout, int R,
                    int S, int pad, int stride, const float* scale_dev, const float* bias_dev, int relu, void* out_dev,
                    void* stream);
 /* fused encoder feed-forward block, fp32/TF32: out = LayerNorm(X + relu(X W1^T + b1) W2^T + b2); X [M,256], W1
- * [hidden,256], W2 [256,hidden]; out_mode 0 rounded / 1 exact [M,256], 2 = [M,768] 3xTF32 operand form */
+ * [hidden,256], W2 [256,hidden]; out_mode 0 rounded / 1 exact [M,256], 2 = [M,768] 3xTF32 operand form, 3 = bf16 [M,256] */
 int spe_debug_ffn(const float* X, long long M, const float* W1, const float* b1, const float* W2, const float* b2,
                   const float* gamma, const float* beta, int hidden, int out_mode, float* out, void* stream);
 int spe_debug_attention(int dtype, const void* q_dev, const void* k_dev, const void* v_dev, void* out_dev, int B,
