@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json configs[1]): Revisiting-Transformer ResNet-50 stride-8 keypoint-set predictor (224^2, 40
 queries, 4+4 layers), batch 64, fp32 storage / TF32 tensor cores, fused crop-resize, batched PnP (exhaustive P3P
-consensus + LM, one CTA of four warps per image).  A step = one pass of the whole hot path over one batch of 64
+consensus + LM, one CTA of six warps per image).  A step = one pass of the whole hot path over one batch of 64
 frames: crop -> predictor -> assignment + PnP ON THE PREDICTOR'S OWN OUTPUT (the weights carry calibrated heads so that
 the queries emit 11 distinct keypoint labels, oracle/make_chain_fixture.py; random-init heads collapse to one label and
 the pose stage would exit early).  `value` times the path with the frames already resident in HBM; `e2e` times the
@@ -38,7 +38,7 @@ SIGMA = bool(int(os.environ.get("SPE_BENCH_SIGMA", "0"))) if "--quick" in sys.ar
 R = 224
 Q = 40
 WORKLOAD = ("Revisiting-Transformer ResNet-50 s8 keypoint-set predictor (224^2, Q=40, enc4/dec4, d_ff 2048), "
-            "batch 64 fp32/TF32, fused crop-resize + batched PnP (exhaustive P3P consensus + LM, 4 warps per image) "
+            "batch 64 fp32/TF32, fused crop-resize + batched PnP (exhaustive P3P consensus + LM, 6 warps per image) "
             "on the predictor's own output, synthetic 1920x1200 uint8 frames, real detector-box distribution")
 METRIC = "images/s crop->keypoints->PnP"
 UNIT = "images/s"

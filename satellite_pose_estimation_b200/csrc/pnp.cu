@@ -419,7 +419,8 @@ __device__ void rot_to_quat(const double (&R)[9], double (&q)[4]) {
   q[0] *= sg; q[1] *= sg; q[2] *= sg; q[3] *= sg;
 }
 
-constexpr int kPnpThreads = 128;
+constexpr int kPnpThreads = 192;   // 165 triples of 11 correspondences in ONE round of the consensus loop (128: two)
+constexpr int kPnpWarps = kPnpThreads / 32;
 constexpr int kMaxPooled = 4096;     // ensemble: models x queries per image
 
 __global__ void __launch_bounds__(kPnpThreads)
@@ -435,10 +436,10 @@ assign_pnp_kernel(const PnpDesc d) {
   __shared__ double s_uv[22];
   __shared__ double s_sig[22];
   __shared__ double s_bear[33];
-  __shared__ int s_bcnt[4];
-  __shared__ double s_berr[4];
-  __shared__ unsigned s_bmask[4];
-  __shared__ double s_bpose[4][12];
+  __shared__ int s_bcnt[kPnpWarps];
+  __shared__ double s_berr[kPnpWarps];
+  __shared__ unsigned s_bmask[kPnpWarps];
+  __shared__ double s_bpose[kPnpWarps][12];
   __shared__ double s_J[16 * 14];
   __shared__ double s_A[27];
   __shared__ unsigned char s_elab[kMaxPooled];   // ensemble: label of every pooled prediction
@@ -662,7 +663,7 @@ assign_pnp_kernel(const PnpDesc d) {
   if (n < 4) { write_out(1); return; }  // cv2.solvePnPRansac raises -> caller records the zero pose
 
   const long long t_assign = clock64();
-  // ---- exhaustive minimal-sample consensus: triple #c goes to thread c % 128
+  // ---- exhaustive minimal-sample consensus: triple #c goes to thread c % kPnpThreads
   Hyp best;
   best.cnt = 0; best.err = 1e300; best.mask = 0u;
 #pragma unroll
@@ -721,7 +722,7 @@ assign_pnp_kernel(const PnpDesc d) {
   if (warp != 0) return;
   const long long t_cons = clock64();
   int bw_ = 0;
-  for (int w = 1; w < 4; ++w)
+  for (int w = 1; w < kPnpWarps; ++w)
     if (s_bcnt[w] > s_bcnt[bw_] || (s_bcnt[w] == s_bcnt[bw_] && s_berr[w] < s_berr[bw_])) bw_ = w;
   if (s_bcnt[bw_] < 4) { write_out(1); return; }  // no hypothesis supported by >= 4 correspondences
   double R[9], t[3];
