@@ -558,6 +558,10 @@ def run_b200(args):
                           "sigma_head": sig, "batches_in_flight": 3, "steps": 12,
                           "poses_solved_per_batch": int((np.asarray(last2["status"]) == 0).sum())}
             if name.startswith("sa_"):
+                sa_gflop = 14.44          # per image: 13.04 convolutions + 1.41 linear layers
+                side[name].update({"algorithmic_gflop_per_image": sa_gflop,
+                                   "algorithmic_tflops": side[name]["images_per_s"] * sa_gflop / 1e3,
+                                   "executed_tflops_3xtf32": 3 * side[name]["images_per_s"] * sa_gflop / 1e3})
                 side[name].update({"model": "SA drop's full RT-DETR predictor (PResNet-50-vd + HybridEncoder + 3 deformable decoder "
                                             "layers, 256^2 crops, 30 queries), fp32 storage / 3xTF32 tensor-core products",
                                    "note": "seeded random weights: the class head collapses to one label, so the pose stage exits "
