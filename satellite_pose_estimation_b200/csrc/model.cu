@@ -1702,7 +1702,8 @@ int spe_create(const spe_config* cfg, int device, spe_ctx** out) {
   if (cfg->backbone == 2) {
     if (cfg->precision != 0 || cfg->has_sigma != 1 || cfg->enc_layers != 1)
       return fail(nullptr, SPE_ERR_INVALID, "spe_create: the SA predictor needs precision 0 (fp32 / TF32), has_sigma 1, enc_layers 1");
-    if (cfg->input_size > 512) return fail(nullptr, SPE_ERR_INVALID, "spe_create: the SA predictor is built for inputs up to 512 x 512");
+    if (cfg->input_size > 256)   // the implicit-GEMM convolution takes output rows of up to 128 pixels: conv1_2 / conv1_3 run at R / 2
+      return fail(nullptr, SPE_ERR_INVALID, "spe_create: the SA predictor is built for inputs up to 256 x 256 (the recipe's eval_spatial_size)");
     const int h8 = cfg->input_size / 8;
     if (cfg->num_queries > h8 * h8 + (h8 / 2) * (h8 / 2) + (h8 / 4) * (h8 / 4) || cfg->num_queries % 2)
       return fail(nullptr, SPE_ERR_INVALID, "spe_create: the SA predictor needs an even num_queries <= the number of anchors");
