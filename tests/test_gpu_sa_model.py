@@ -236,3 +236,28 @@ def test_sa_whole_path_through_pipeline_slots(eng, case):
         got = eng.collect_batch_host(slot)
         assert np.array_equal(got["status"], r["status"].cpu().numpy())
         assert np.allclose(got["quat"], r["quat"].cpu().numpy(), atol=1e-9) and np.allclose(got["tvec"], r["tvec"].cpu().numpy(), atol=1e-9)
+
+
+@pytest.mark.parametrize("R,B", [(224, 3), (160, 1)])
+def test_sa_other_input_sizes(lib, cuda_dev, R, B):
+    """Input sizes other than the recipe's 256: odd feature maps (224 -> 28 / 14 / 7, 160 -> 20 / 10 / 5) through every
+    convolution path, the bicubic x0.5 and nearest x2 kernels, and a batch of one -- against the oracle."""
+    cfg = sa_model_ref.SaCfg(input_size=R)
+    sd = synth.make_sa_state_dict(cfg, seed=0)
+    x = torch.randn(B, 3, R, R, generator=torch.Generator().manual_seed(R))
+    taps = {}
+    ref = sa_model_ref.forward(sd, cfg, x, taps)
+    e = Engine(input_size=R, num_queries=cfg.num_queries, enc_layers=1, dec_layers=cfg.dec_layers, dim_feedforward=cfg.dec_ff,
+               backbone="rtdetr_r50vd", precision="tf32", has_sigma=True, max_batch=B)
+    try:
+        e.load_state_dict(sd)
+        o = e.forward_sa(x.cuda(), topk_override=taps["topk"].to(torch.int32).cuda())
+        torch.cuda.synchronize()
+        assert (o["pred_pts"].cpu() - ref["pred_pts"]).abs().max().item() <= PTS_TOL
+        assert (o["pred_logits"].cpu() - ref["pred_logits"]).abs().max().item() <= LOGIT_TOL
+        assert (o["pred_sigmas"].cpu() - ref["pred_sigmas"]).abs().max().item() <= LOGIT_TOL
+    finally:
+        e.close()
+    with pytest.raises(Exception, match="256"):
+        Engine(input_size=512, num_queries=30, enc_layers=1, dec_layers=3, dim_feedforward=1024, backbone="rtdetr_r50vd",
+               precision="tf32", has_sigma=True, max_batch=1)
