@@ -351,17 +351,18 @@ def write_deform_attn():
 
 
 SA_MODEL_CASE = dict(batch=4, seed=7, weights_seed=0)
+SA_R18_CASE = dict(batch=3, seed=8, weights_seed=1, depth=18)
 
 
-def write_sa_model():
+def write_sa_model(case=None, name="sa_model_golden.npz", yml=None):
     """The LIVE SA ``RTDETR`` model (ref_import.build_sa_reference_model) on seeded weights / inputs -> sa_model_golden.npz:
     the eval-mode output dict (SA/src/zoo/rtdetr/rtdetr_decoder.py:732-751), the anchor scores and the top-k selection
     (recomputed with the reference's own ``torch.topk`` call, :646-648, on the live ``enc_score_head`` output)."""
     from . import sa_model_ref
-    case = SA_MODEL_CASE
-    cfg = sa_model_ref.SaCfg()
+    case = case or SA_MODEL_CASE
+    cfg = sa_model_ref.SaCfg(depth=case.get("depth", 50))
     sd = synth.make_sa_state_dict(cfg, seed=case["weights_seed"])
-    model = ref_import.build_sa_reference_model(sd)
+    model = ref_import.build_sa_reference_model(sd, yml)
     x = model_inputs(case["batch"], cfg.input_size, case["seed"])
     got = {}
     model.decoder.enc_score_head.register_forward_hook(lambda mod, inp, out: got.__setitem__("cls", out.detach().clone()))
@@ -378,7 +379,7 @@ def write_sa_model():
     aux = out["aux_outputs"]
     assert len(aux) == cfg.dec_layers
     np.savez_compressed(
-        os.path.join(GOLDEN, "sa_model_golden.npz"), weights_sha256=synth.weights_checksum(sd),
+        os.path.join(GOLDEN, name), weights_sha256=synth.weights_checksum(sd),
         pred_logits=out["pred_logits"].numpy(), pred_pts=out["pred_pts"].numpy(), pred_sigmas=out["pred_sigmas"].numpy(),
         aux_logits=torch.stack([a["pred_logits"] for a in aux]).numpy(), aux_pts=torch.stack([a["pred_pts"] for a in aux]).numpy(),
         aux_sigmas=torch.stack([a["pred_sigmas"] for a in aux[:-1]]).numpy(), enc_scores=scores.numpy(),
@@ -473,6 +474,7 @@ def main():
     write_model_b64_random()
     write_deform_attn()
     write_sa_model()
+    write_sa_model(SA_R18_CASE, "sa_r18_model_golden.npz", ref_import.SA_MODEL_YML_R18)   # rtdetr_r18vd_6x_speed_kl_1.yml
     write_pnp(rv_eval)
     write_pnp_multi(rv_eval)
 

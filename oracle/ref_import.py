@@ -90,7 +90,10 @@ def import_sa_rtdetr():
 SA_MODEL_YML = "configs/rtdetr_speed/rtdetr_r50vd_6x_speed_kl_1.yml"
 
 
-def build_sa_reference_model(state_dict=None):
+SA_MODEL_YML_R18 = "configs/rtdetr_speed/rtdetr_r18vd_6x_speed_kl_1.yml"
+
+
+def build_sa_reference_model(state_dict=None, yml=None):
     """The SA drop's live ``RTDETR`` model of ``configs/rtdetr_speed/rtdetr_r50vd_6x_speed_kl_1.yml`` (PResNet-50-vd,
     HybridEncoder, RTDETRTransformer with 30 queries / 3 decoder layers, eval size 256), built by the reference's own
     ``YAMLConfig`` with the pretrained-weight download switched off; eval mode, optional weights (strict)."""
@@ -100,7 +103,7 @@ def build_sa_reference_model(state_dict=None):
     from src.core import YAMLConfig
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        cfg = YAMLConfig(os.path.join(SA_ROOT, SA_MODEL_YML))
+        cfg = YAMLConfig(os.path.join(SA_ROOT, yml or SA_MODEL_YML))
         cfg.yaml_cfg["PResNet"]["pretrained"] = False
         torch.manual_seed(0)
         model = cfg.model

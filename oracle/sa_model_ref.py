@@ -32,9 +32,11 @@ class SaCfg:
     num_points: int = 4
     num_classes: int = 11            # + 1 background logit
     anchor_eps: float = 1e-2
+    depth: int = 50                  # PResNet depth: 50 (BottleNeck, rtdetr_r50vd_*.yml) or 18 / 34 (BasicBlock, rtdetr_r18vd_*.yml)
 
 
 PRESNET50_BLOCKS = (3, 4, 6, 3)
+PRESNET_BLOCKS = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3)}      # ResNet_cfg, SA/nn/backbone/presnet.py:18-24
 STAGE_PLANES = (64, 128, 256, 512)
 
 
@@ -73,8 +75,23 @@ def bottleneck_vd(x, sd, p, stride, shortcut):
     return F.relu(out + short)
 
 
-def presnet(x, sd, taps=None):
-    """PResNet.forward (SA/nn/backbone/presnet.py:245-265), depth 50, variant d, return_idx [1, 2, 3]."""
+def basic_block_vd(x, sd, p, stride, shortcut):
+    """BasicBlock.forward, variant 'd' (SA/nn/backbone/presnet.py:35-70): 3x3 (stride) + BN + ReLU, 3x3 + BN, shortcut as
+    in the bottleneck (AvgPool2d(2, 2) + 1x1 when stride == 2, plain 1x1 in the first stage), ReLU of the sum."""
+    out = conv_norm(x, sd, p + ".branch2a", stride, "relu")
+    out = conv_norm(out, sd, p + ".branch2b", 1, None)
+    if shortcut:
+        short = x
+    elif stride == 2:
+        short = conv_norm(F.avg_pool2d(x, 2, 2, 0, ceil_mode=True), sd, p + ".short.conv", 1, None)
+    else:
+        short = conv_norm(x, sd, p + ".short", 1, None)
+    return F.relu(out + short)
+
+
+def presnet(x, sd, taps=None, depth=50):
+    """PResNet.forward (SA/nn/backbone/presnet.py:245-265), variant d, return_idx [1, 2, 3]; depth 50 = BottleNeck,
+    18 / 34 = BasicBlock."""
     b = "backbone"
     x = conv_norm(x, sd, b + ".conv1.conv1_1", 2, "relu")
     x = conv_norm(x, sd, b + ".conv1.conv1_2", 1, "relu")
@@ -83,10 +100,11 @@ def presnet(x, sd, taps=None):
         taps["stem"] = x
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     outs = []
-    for si, nb in enumerate(PRESNET50_BLOCKS):
+    block = bottleneck_vd if depth >= 50 else basic_block_vd
+    for si, nb in enumerate(PRESNET_BLOCKS[depth]):
         for bi in range(nb):
             stride = 2 if (bi == 0 and si != 0) else 1          # Blocks.__init__: stage_num != 2 (:137)
-            x = bottleneck_vd(x, sd, f"{b}.res_layers.{si}.blocks.{bi}", stride, shortcut=bi != 0)
+            x = block(x, sd, f"{b}.res_layers.{si}.blocks.{bi}", stride, shortcut=bi != 0)
         if taps is not None:
             taps[f"stage{si}"] = x
         if si >= 1:
@@ -295,6 +313,6 @@ def rtdetr_decoder(feats, sd, cfg: SaCfg, taps=None, topk_override=None):
 def forward(sd, cfg: SaCfg, images, taps=None, topk_override=None):
     """RTDETR.forward (SA/src/zoo/rtdetr/rtdetr.py:36-52), eval mode."""
     with torch.no_grad():
-        feats = presnet(images, sd, taps)
+        feats = presnet(images, sd, taps, cfg.depth)
         feats = hybrid_encoder(feats, sd, cfg, taps)
         return rtdetr_decoder(feats, sd, cfg, taps, topk_override)

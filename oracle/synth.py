@@ -390,7 +390,7 @@ def make_sa_state_dict(cfg=None, seed=0):
     """Random weights in the SA reference's ``state_dict`` layout.  Every tensor is non-degenerate on purpose: the
     reference's own init zeroes the sampling-offset / attention-weight projections and the last layer of every keypoint
     head (SA/src/zoo/rtdetr/rtdetr_decoder.py:70-92, :487-497), which would hide a wrong kernel behind zeros."""
-    from .sa_model_ref import SaCfg, PRESNET50_BLOCKS, STAGE_PLANES
+    from .sa_model_ref import SaCfg, PRESNET_BLOCKS, STAGE_PLANES
     cfg = cfg or SaCfg()
     rng = np.random.default_rng(seed)
     sd = {"temper_param": rng.standard_normal(1).astype(np.float32)}
@@ -399,17 +399,23 @@ def make_sa_state_dict(cfg=None, seed=0):
     _conv_norm(rng, sd, b + ".conv1.conv1_2", 32, 32, 3)
     _conv_norm(rng, sd, b + ".conv1.conv1_3", 64, 32, 3)
     cin = 64
-    for si, (nb, planes) in enumerate(zip(PRESNET50_BLOCKS, STAGE_PLANES)):
+    bottleneck = cfg.depth >= 50
+    exp = 4 if bottleneck else 1
+    for si, (nb, planes) in enumerate(zip(PRESNET_BLOCKS[cfg.depth], STAGE_PLANES)):
         for bi in range(nb):
             p = f"{b}.res_layers.{si}.blocks.{bi}"
-            _conv_norm(rng, sd, p + ".branch2a", planes, cin, 1)
-            _conv_norm(rng, sd, p + ".branch2b", planes, planes, 3)
-            _conv_norm(rng, sd, p + ".branch2c", planes * 4, planes, 1, gamma_scale=0.5)
+            if bottleneck:
+                _conv_norm(rng, sd, p + ".branch2a", planes, cin, 1)
+                _conv_norm(rng, sd, p + ".branch2b", planes, planes, 3)
+                _conv_norm(rng, sd, p + ".branch2c", planes * 4, planes, 1, gamma_scale=0.5)
+            else:
+                _conv_norm(rng, sd, p + ".branch2a", planes, cin, 3)
+                _conv_norm(rng, sd, p + ".branch2b", planes, planes, 3, gamma_scale=0.5)
             if bi == 0:
-                _conv_norm(rng, sd, p + (".short" if si == 0 else ".short.conv"), planes * 4, cin, 1, gamma_scale=0.5)
-                cin = planes * 4
+                _conv_norm(rng, sd, p + (".short" if si == 0 else ".short.conv"), planes * exp, cin, 1, gamma_scale=0.5)
+                cin = planes * exp
     e, E = "encoder", cfg.hidden_dim
-    for i, c in enumerate((512, 1024, 2048)):
+    for i, c in enumerate((128 * exp, 256 * exp, 512 * exp)):
         sd[f"{e}.input_proj.{i}.0.weight"] = _conv(rng, E, c, 1, gain=0.7)
         _bn2d(rng, sd, f"{e}.input_proj.{i}.1", E)
     sd[e + ".encoder_fusion_input.weight"] = _conv(rng, 256, 3 * E, 1)        # defined, never used by forward

@@ -27,9 +27,10 @@
 //   * dec_bbox_head[i].layers.0 | sigma_embed[i].layers.0 share their input: one GEMM with N = 512.
 
 struct SaBlock {
-  GemmW a, b, c, sc;
+  GemmW a, b, c, sc;       // BottleNeck: 1x1, 3x3 (stride), 1x1; BasicBlock (depth 18 / 34): 3x3 (stride), 3x3, c unused
   int cin = 0, planes = 0, stride = 1;
   bool has_short = false;
+  bool basic = false;
 };
 struct SaCsp { GemmW c1, c2, rep, c3; };
 struct SaDecLayer {
@@ -50,6 +51,8 @@ struct SaModel {
   // the K <= 512 layers; the separate pass is a 3 % memory-bound tail.
   bool act_epi = getenv("SPE_SA_ACT_EPI") ? atoi(getenv("SPE_SA_ACT_EPI")) != 0 : false;
   int shapes_hw[6] = {0, 0, 0, 0, 0, 0};
+  int nblocks[4] = {3, 4, 6, 3};   // per stage, read off the state_dict at load (PResNet depth 50 / 34 / 18)
+  int expansion = 4;               // 4: BottleNeck, 1: BasicBlock
   GemmW c11, c12, c13;
   std::vector<SaBlock> blocks;
   GemmW eproj[3];
@@ -165,25 +168,42 @@ std::string sa_load_weights(spe_ctx* ctx, WeightSource& ws) {
     TRY_S(upload_gemm_w(ctx, sa_repack_conv_padded(*w3, 64, 32), 64, 9 * 32, &m.c13, m.x3));
     TRY_S(sa_load_bn_padded(ctx, ws, "backbone.conv1.conv1_3.norm", 64, 64, &m.c13));
   }
+  // the recipe's depth is read off the checkpoint: BottleNeck blocks carry a branch2c (depth 50), BasicBlocks do not
+  // (depth 18: 2 + 2 + 2 + 2 blocks, depth 34: 3 + 4 + 6 + 3) -- SA/nn/backbone/presnet.py:18-24, :35-123
+  const bool basic = ws.t.find("backbone.res_layers.0.blocks.0.branch2c.conv.weight") == ws.t.end();
+  m.expansion = basic ? 1 : 4;
+  for (int si = 0; si < 4; ++si) {
+    int nb = 0;
+    while (ws.t.find("backbone.res_layers." + std::to_string(si) + ".blocks." + std::to_string(nb) + ".branch2a.conv.weight") != ws.t.end()) ++nb;
+    if (nb < 1 || nb > 64) return "backbone.res_layers." + std::to_string(si) + ": no residual blocks found";
+    m.nblocks[si] = nb;
+  }
   m.blocks.clear();
   int cin = 64;
   for (int si = 0; si < 4; ++si)
-    for (int bi = 0; bi < kSaBlocks[si]; ++bi) {
+    for (int bi = 0; bi < m.nblocks[si]; ++bi) {
       SaBlock bk;
       bk.cin = cin;
       bk.planes = kSaPlanes[si];
       bk.stride = (bi == 0 && si != 0) ? 2 : 1;
       bk.has_short = bi == 0;
+      bk.basic = basic;
       const std::string p = "backbone.res_layers." + std::to_string(si) + ".blocks." + std::to_string(bi);
-      TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2a", bk.planes, cin, 1, &bk.a));
-      TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2b", bk.planes, bk.planes, 3, &bk.b));
-      TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2c", bk.planes * 4, bk.planes, 1, &bk.c));
-      if (bk.has_short) TRY_S(sa_load_conv_norm(ctx, ws, p + (si == 0 ? ".short" : ".short.conv"), bk.planes * 4, cin, 1, &bk.sc));
-      cin = bk.planes * 4;
+      if (basic) {
+        TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2a", bk.planes, cin, 3, &bk.a));
+        TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2b", bk.planes, bk.planes, 3, &bk.b));
+      } else {
+        TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2a", bk.planes, cin, 1, &bk.a));
+        TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2b", bk.planes, bk.planes, 3, &bk.b));
+        TRY_S(sa_load_conv_norm(ctx, ws, p + ".branch2c", bk.planes * 4, bk.planes, 1, &bk.c));
+      }
+      if (bk.has_short)
+        TRY_S(sa_load_conv_norm(ctx, ws, p + (si == 0 ? ".short" : ".short.conv"), bk.planes * m.expansion, cin, 1, &bk.sc));
+      cin = bk.planes * m.expansion;
       m.blocks.push_back(bk);
     }
   // ---- HybridEncoder
-  const int cins[3] = {512, 1024, 2048};
+  const int cins[3] = {128 * m.expansion, 256 * m.expansion, 512 * m.expansion};
   for (int i = 0; i < 3; ++i) {
     const std::string p = "encoder.input_proj." + std::to_string(i);
     TRY_S(load_conv_bn(ctx, ws, p + ".0", p + ".1", E, cins[i], 1, &m.eproj[i], 0, m.x3));
@@ -443,6 +463,21 @@ struct SaFwd {
     d.round_out = (w.x3 || exact) ? 0 : 1;
     return launch_gemm(kTF32, d, ctx->num_sms, st);
   }
+  // 3x3 / stride 1 convolution + BN + residual + ReLU (second convolution of a BasicBlock), H = map extent
+  std::string conv_res(const void* x, int H, int C, const GemmW& w, void* out, int out_ld, const void* residual) {
+    TRY_S(f.calibrate_layer(x, B * H * H, C, C, w));
+    GemmDesc d;
+    d.mode = 1;
+    d.A = x; d.NB = static_cast<int>(B); d.H = H; d.W = H; d.C = C; d.R = 3; d.S = 3; d.pad = 1; d.conv_stride = 1;
+    d.Wt = w.w; d.N = w.N;
+    d.scale = w.scale; d.bias = w.bias;
+    d.residual = residual; d.res_ld = out_ld;
+    d.relu = 1;
+    d.out = out; d.out_ld = out_ld;
+    d.x3 = w.x3;
+    d.round_out = w.x3 ? 0 : 1;
+    return launch_gemm(kTF32, d, ctx->num_sms, st);
+  }
   std::string act(const void* in, int in_ld, const void* add, int add_ld, void* out, int out_ld, long long rows, int C,
                   int kind, int round = -1) {
     if (round < 0) round = m.x3 ? 0 : 1;   // a 3xTF32 consumer splits its operand itself
@@ -495,13 +530,17 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
   int H = h4, bidx = 0;
   void* stage_out[4] = {nullptr, m.C3, m.C4, m.C5};
   for (int si = 0; si < 4; ++si) {
-    for (int bi = 0; bi < kSaBlocks[si]; ++bi, ++bidx) {
+    for (int bi = 0; bi < m.nblocks[si]; ++bi, ++bidx) {
       const SaBlock& bk = m.blocks[bidx];
       const int Ho = H / bk.stride;
       const long long Min = B * H * H, Mout = B * Ho * Ho;
-      void* nxt = (bi == kSaBlocks[si] - 1 && stage_out[si] != nullptr) ? stage_out[si] : ((cur == m.P0) ? m.P1 : m.P0);
-      TRY_S(s.gemm(cur, bk.cin, Min, bk.a, m.T1, bk.planes, true, false));
-      TRY_S(f.conv(m.T1, H, bk.planes, 3, bk.stride, bk.b, m.T2, bk.planes, true));
+      const int cout = bk.planes * m.expansion;
+      void* nxt = (bi == m.nblocks[si] - 1 && stage_out[si] != nullptr) ? stage_out[si] : ((cur == m.P0) ? m.P1 : m.P0);
+      if (bk.basic) TRY_S(f.conv(cur, H, bk.cin, 3, bk.stride, bk.a, m.T1, bk.planes, true));
+      else {
+        TRY_S(s.gemm(cur, bk.cin, Min, bk.a, m.T1, bk.planes, true, false));
+        TRY_S(f.conv(m.T1, H, bk.planes, 3, bk.stride, bk.b, m.T2, bk.planes, true));
+      }
       const void* identity = cur;
       if (bk.has_short) {
         const void* src = cur;
@@ -509,23 +548,24 @@ std::string sa_forward(spe_ctx* ctx, const float* images, int Bi, float* logits,
           TRY_S(launch_avgpool2x2(SaFwd::F(const_cast<void*>(cur)), Bi, H, H, bk.cin, SaFwd::F(m.AP), rnd, st));
           src = m.AP;
         }
-        TRY_S(s.gemm(src, bk.cin, Mout, bk.sc, m.DS, bk.planes * 4, false, true));
+        TRY_S(s.gemm(src, bk.cin, Mout, bk.sc, m.DS, cout, false, true));
         identity = m.DS;
       }
-      TRY_S(s.gemm(m.T2, bk.planes, Mout, bk.c, nxt, bk.planes * 4, true, false, identity, bk.planes * 4));
+      if (bk.basic) TRY_S(s.conv_res(m.T1, Ho, bk.planes, bk.b, nxt, cout, identity));   // 3x3 + BN, + shortcut, ReLU
+      else TRY_S(s.gemm(m.T2, bk.planes, Mout, bk.c, nxt, cout, true, false, identity, cout));
       cur = nxt;
       H = Ho;
     }
     const std::string nm = "sa_stage" + std::to_string(si);
-    TRY_S(f.tap(nm.c_str(), cur, B * H * H * kSaPlanes[si] * 4));
+    TRY_S(f.tap(nm.c_str(), cur, B * H * H * kSaPlanes[si] * m.expansion));
   }
 
   // ---- HybridEncoder: projections (levels 0 / 1 straight into their concatenation slots)
   const int h8 = m.hl[0], h16 = m.hl[1], h32 = m.hl[2];
   const long long M8 = B * h8 * h8, M16 = B * h16 * h16, M32 = B * h32 * h32;
-  TRY_S(s.gemm(m.C3, 512, M8, m.eproj[0], SaFwd::col(m.CAT8, 256), 512, false, false));
-  TRY_S(s.gemm(m.C4, 1024, M16, m.eproj[1], SaFwd::col(m.CAT16, 256), 512, false, false));
-  TRY_S(s.gemm(m.C5, 2048, M32, m.eproj[2], m.E2, 256, false, false));
+  TRY_S(s.gemm(m.C3, m.eproj[0].K, M8, m.eproj[0], SaFwd::col(m.CAT8, 256), 512, false, false));
+  TRY_S(s.gemm(m.C4, m.eproj[1].K, M16, m.eproj[1], SaFwd::col(m.CAT16, 256), 512, false, false));
+  TRY_S(s.gemm(m.C5, m.eproj[2].K, M32, m.eproj[2], m.E2, 256, false, false));
   // AIFI layer on the /32 level (post-norm, GELU)
   {
     const int T = h32 * h32;

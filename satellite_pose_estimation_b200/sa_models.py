@@ -18,12 +18,12 @@ from torch import nn
 from .engine import Engine
 from .models import _Holder, _register
 
-PRESNET50_BLOCKS = (3, 4, 6, 3)
+PRESNET_BLOCKS = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3)}   # SA/nn/backbone/presnet.py:18-24
 STAGE_PLANES = (64, 128, 256, 512)
 
 
 def sa_param_specs(num_queries=30, dec_layers=3, hidden_dim=256, nheads=8, enc_ff=1024, dec_ff=1024, csp_hidden=128,
-                   num_levels=3, num_points=4, num_classes=11):
+                   num_levels=3, num_points=4, num_classes=11, depth=50):
     """(name, shape, kind) for every tensor of the SA reference's state_dict; kind: 'p' parameter, 'b' float buffer,
     'n' the int64 ``num_batches_tracked`` counters of nn.BatchNorm2d (the kl configs set ``freeze_norm: False``)."""
     specs, E = [("temper_param", (1,), "p")], hidden_dim      # RTDETR.temper_param, rtdetr.py:34 (unused in forward)
@@ -54,15 +54,20 @@ def sa_param_specs(num_queries=30, dec_layers=3, hidden_dim=256, nheads=8, enc_f
     conv_norm("backbone.conv1.conv1_2", 32, 32, 3)
     conv_norm("backbone.conv1.conv1_3", 64, 32, 3)
     cin = 64
-    for si, (nb, planes) in enumerate(zip(PRESNET50_BLOCKS, STAGE_PLANES)):
+    exp = 4 if depth >= 50 else 1            # BottleNeck (depth 50) / BasicBlock (depth 18, 34), presnet.py:35-123
+    for si, (nb, planes) in enumerate(zip(PRESNET_BLOCKS[depth], STAGE_PLANES)):
         for bi in range(nb):
             p = f"backbone.res_layers.{si}.blocks.{bi}"
-            conv_norm(p + ".branch2a", planes, cin, 1)
-            conv_norm(p + ".branch2b", planes, planes, 3)
-            conv_norm(p + ".branch2c", planes * 4, planes, 1)
+            if exp == 4:
+                conv_norm(p + ".branch2a", planes, cin, 1)
+                conv_norm(p + ".branch2b", planes, planes, 3)
+                conv_norm(p + ".branch2c", planes * 4, planes, 1)
+            else:
+                conv_norm(p + ".branch2a", planes, cin, 3)
+                conv_norm(p + ".branch2b", planes, planes, 3)
             if bi == 0:
-                conv_norm(p + (".short" if si == 0 else ".short.conv"), planes * 4, cin, 1)
-                cin = planes * 4
+                conv_norm(p + (".short" if si == 0 else ".short.conv"), planes * exp, cin, 1)
+                cin = planes * exp
     for i in range(num_levels):
         specs.append((f"decoder.input_proj.{i}.conv.weight", (E, E, 1, 1), "p"))
         bn(f"decoder.input_proj.{i}.norm", E)
@@ -83,7 +88,7 @@ def sa_param_specs(num_queries=30, dec_layers=3, hidden_dim=256, nheads=8, enc_f
         linear(f"decoder.dec_score_head.{i}", num_classes + 1, E)
     for i in range(dec_layers):
         mlp(f"decoder.dec_bbox_head.{i}", (E, E, E, 2))
-    for i, c in enumerate((512, 1024, 2048)):
+    for i, c in enumerate((128 * exp, 256 * exp, 512 * exp)):
         specs.append((f"encoder.input_proj.{i}.0.weight", (E, c, 1, 1), "p"))
         bn(f"encoder.input_proj.{i}.1", E)
     specs.append(("encoder.encoder_fusion_input.weight", (256, 3 * E, 1, 1), "p"))   # defined, unused by forward
@@ -107,8 +112,10 @@ class B200RTDETR(nn.Module):
     ``forward(x, targets=None)`` -> ``{'pred_logits', 'pred_pts', 'pred_sigmas', 'aux_outputs'}``."""
 
     def __init__(self, *, input_size=256, num_queries=30, dec_layers=3, hidden_dim=256, nheads=8, enc_ff=1024,
-                 dec_ff=1024, expansion=0.5, num_classes=11, max_batch=64, calibrate=False):
+                 dec_ff=1024, expansion=0.5, num_classes=11, max_batch=64, calibrate=False, depth=50):
         super().__init__()
+        if depth not in PRESNET_BLOCKS:
+            raise ValueError("PResNet depth must be 18, 34 or 50 (rtdetr_r18vd_* / rtdetr_r50vd_* recipes)")
         if hidden_dim != 256 or nheads != 8 or enc_ff != dec_ff or int(hidden_dim * expansion) != 128 or num_classes != 11:
             raise ValueError("libspe.so builds the rtdetr_r50vd speed recipe: hidden_dim 256, 8 heads, equal encoder / "
                              "decoder feed-forward widths, expansion 0.5, 11 keypoint classes")
@@ -117,7 +124,7 @@ class B200RTDETR(nn.Module):
         self.max_batch, self.calibrate = max_batch, bool(calibrate)
         gen = torch.Generator().manual_seed(0)
         for name, shape, kind in sa_param_specs(num_queries, dec_layers, hidden_dim, nheads, enc_ff, dec_ff,
-                                                int(hidden_dim * expansion)):
+                                                int(hidden_dim * expansion), depth=depth):
             if kind == "n":
                 _register(self, name, torch.zeros((), dtype=torch.int64), True)
             else:
@@ -240,13 +247,13 @@ class RTDETRPostProcessor(nn.Module):
 
 
 def build_sa_model(*, input_size=256, num_queries=30, num_decoder_layers=3, hidden_dim=256, nhead=8, dim_feedforward=1024,
-                   expansion=0.5, max_batch=64, reproj=25.0, self_assessment=False, calibrate=False):
+                   expansion=0.5, max_batch=64, reproj=25.0, self_assessment=False, calibrate=False, depth=50):
     """What ``cfg.model`` / ``cfg.postprocessor`` give the SA drop's engine, from the values its YAML recipe sets
     (``HybridEncoder`` / ``RTDETRTransformer`` blocks of configs/rtdetr_speed/rtdetr_r50vd_6x_speed_kl_*.yml; ``eval_
-    spatial_size`` -> ``input_size``).  Returns ``(model, postprocessor)``; the caller moves the model: model.to('cuda')."""
+    spatial_size`` -> ``input_size``; ``PResNet.depth`` -> ``depth``: 50 for the rtdetr_r50vd recipes, 18 / 34 for rtdetr_r18vd).  Returns ``(model, postprocessor)``; the caller moves the model: model.to('cuda')."""
     model = B200RTDETR(input_size=input_size, num_queries=num_queries, dec_layers=num_decoder_layers, hidden_dim=hidden_dim,
                        nheads=nhead, enc_ff=dim_feedforward, dec_ff=dim_feedforward, expansion=expansion,
-                       max_batch=max_batch, calibrate=calibrate)
+                       max_batch=max_batch, calibrate=calibrate, depth=depth)
     model.eval()
     post = RTDETRPostProcessor(lambda: model.engine, reproj=reproj, weighted=True, reject=self_assessment)
     return model, post

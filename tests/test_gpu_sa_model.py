@@ -261,3 +261,30 @@ def test_sa_other_input_sizes(lib, cuda_dev, R, B):
     with pytest.raises(Exception, match="256"):
         Engine(input_size=512, num_queries=30, enc_layers=1, dec_layers=3, dim_feedforward=1024, backbone="rtdetr_r50vd",
                precision="tf32", has_sigma=True, max_batch=1)
+
+
+def test_sa_r18vd_recipe_vs_live_reference_golden(lib, cuda_dev):
+    """rtdetr_r18vd_6x_speed_kl_*.yml: PResNet depth 18 (BasicBlocks: 3x3 + 3x3 with the residual in the second
+    convolution's epilogue, 128 / 256 / 512-channel pyramid) behind the same encoder / decoder -- the library reads the
+    depth off the checkpoint's tensor names.  Against the live model's outputs (its own top-k selection handed in)."""
+    from oracle.make_golden import SA_R18_CASE
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "sa_r18_model_golden.npz"))
+    cfg = sa_model_ref.SaCfg(depth=18)
+    sd = synth.make_sa_state_dict(cfg, seed=SA_R18_CASE["weights_seed"])
+    assert synth.weights_checksum(sd) == str(g["weights_sha256"])
+    x = model_inputs(SA_R18_CASE["batch"], cfg.input_size, SA_R18_CASE["seed"])
+    model, post = build_sa_model(max_batch=4, depth=18)
+    model.load_state_dict(sd, strict=True)
+    model.to("cuda")
+    model(x[:2].cuda())                       # creates the engine
+    out = model.engine.forward_sa(x.cuda(), topk_override=torch.from_numpy(g["topk"]).cuda())
+    torch.cuda.synchronize()
+    d_p = np.abs(out["pred_pts"].cpu().numpy() - g["pred_pts"]).max()
+    d_l = np.abs(out["pred_logits"].cpu().numpy() - g["pred_logits"]).max()
+    d_s = np.abs(out["pred_sigmas"].cpu().numpy() - g["pred_sigmas"]).max()
+    a_p = np.abs(torch.stack([a["pred_pts"] for a in out["aux_outputs"]]).cpu().numpy() - g["aux_pts"]).max()
+    print(f"SA r18vd vs live reference: keypoints {d_p * 1748:.3f} px at S=1748 (aux {a_p * 1748:.3f}), logits {d_l:.1e}, log-sigma {d_s:.1e}")
+    assert d_p <= PTS_TOL and a_p <= PTS_TOL and d_l <= LOGIT_TOL and d_s <= LOGIT_TOL
+    own = model.engine.forward_sa(x.cuda())
+    assert min(len(set(own["topk_ind"][b].tolist()) & set(g["topk"][b].tolist())) for b in range(x.shape[0])) >= cfg.num_queries - 2
+    model.engine.close()

@@ -220,3 +220,17 @@ def test_sa_state_dict_layout_matches_reference_keys():
         m.train()
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(2, 3, 256, 256))          # no CPU fallback
+
+
+def test_sa_r18vd_state_dict_layout():
+    """PResNet depth 18 (BasicBlock) recipe: 444 tensors, strict load."""
+    from oracle import sa_model_ref
+    from satellite_pose_estimation_b200.sa_models import B200RTDETR, sa_param_specs
+    sd = synth.make_sa_state_dict(sa_model_ref.SaCfg(depth=18), seed=1)
+    specs = sa_param_specs(depth=18)
+    assert {n: tuple(s) for n, s, _ in specs} == {k: tuple(v.shape) for k, v in sd.items()} and len(sd) == 444
+    m = B200RTDETR(depth=18, max_batch=2)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    with pytest.raises(RuntimeError):            # a depth-50 checkpoint does not fit a depth-18 model
+        m.load_state_dict(synth.make_sa_state_dict(seed=0), strict=True)

@@ -289,3 +289,21 @@ def test_sa_postprocess_restatement_matches_live_postprocessor():
         assert np.abs(live[i]["logits"] - mine[i]["logits"]).max() < 1e-6
         assert np.abs(live[i]["points"] - mine[i]["points"]).max() < 1e-3
         assert np.abs(live[i]["sigmas"] - np.exp(out["pred_sigmas"][i].numpy())).max() < 1e-5
+
+
+def test_sa_r18vd_oracle_matches_live_reference_golden():
+    """The BasicBlock recipe (configs/rtdetr_speed/rtdetr_r18vd_6x_speed_kl_1.yml, PResNet depth 18): restatement against
+    outputs of the LIVE model (oracle/make_golden.py: SA_R18_CASE)."""
+    from oracle.make_golden import SA_R18_CASE
+    from oracle import sa_model_ref
+    g = np.load(os.path.join(G, "sa_r18_model_golden.npz"))
+    cfg = sa_model_ref.SaCfg(depth=SA_R18_CASE["depth"])
+    sd = synth.make_sa_state_dict(cfg, seed=SA_R18_CASE["weights_seed"])
+    assert len(sd) == 444 and synth.weights_checksum(sd) == str(g["weights_sha256"])
+    x = model_inputs(SA_R18_CASE["batch"], cfg.input_size, SA_R18_CASE["seed"])
+    taps = {}
+    out = sa_model_ref.forward(sd, cfg, x, taps)
+    assert np.array_equal(taps["topk"].numpy(), g["topk"])
+    assert np.abs(out["pred_logits"].numpy() - g["pred_logits"]).max() < 5e-5
+    assert np.abs(out["pred_pts"].numpy() - g["pred_pts"]).max() < 5e-6
+    assert np.abs(out["pred_sigmas"].numpy() - g["pred_sigmas"]).max() < 5e-5
