@@ -23,6 +23,7 @@ class ModelCfg:
     dim_feedforward: int = 2048
     aux_loss: bool = True
     sigma_head: bool = False         # self-assessment variant: per-keypoint log-sigma head
+    position_embedding: str = "sine"  # 'sine' ('v2') or 'learned' ('v3'), RV/models/position_encoding.py:84-95
 
     @property
     def stride8(self):
@@ -176,7 +177,14 @@ def forward(sd, cfg: ModelCfg, images, taps=None):
     B = x.shape[0]
     feat = backbone8s(x, sd, taps) if cfg.stride8 else backbone16(x, sd, taps)
     _, _, H, W = feat.shape
-    pos = position_embedding_sine(B, H, W, cfg.hidden_dim)
+    if cfg.position_embedding in ("learned", "v3"):
+        # PositionEmbeddingLearned.forward, RV/models/position_encoding.py:69-81: cat(col_embed[x], row_embed[y])
+        x_emb = sd["backbone.1.col_embed.weight"][:W]
+        y_emb = sd["backbone.1.row_embed.weight"][:H]
+        pos = torch.cat([x_emb.unsqueeze(0).repeat(H, 1, 1), y_emb.unsqueeze(1).repeat(1, W, 1)], dim=-1)
+        pos = pos.permute(2, 0, 1).unsqueeze(0).repeat(B, 1, 1, 1)
+    else:
+        pos = position_embedding_sine(B, H, W, cfg.hidden_dim)
     src = F.conv2d(feat, sd["input_proj.weight"], sd["input_proj.bias"])          # detr_speed.py:54-55, :81
     # Transformer.forward, RV/models/transformer.py:51-63
     src = src.flatten(2).permute(2, 0, 1)

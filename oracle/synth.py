@@ -20,7 +20,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 def reference_args(cfg: ModelCfg, device="cpu"):
     """argparse namespace the reference's ``build_model(args)`` reads (RV/main.py:90-187 defaults)."""
     return Namespace(
-        backbone=cfg.backbone, dilation=False, position_embedding="sine", bn="frozen_bn",
+        backbone=cfg.backbone, dilation=False, position_embedding=getattr(cfg, "position_embedding", "sine"), bn="frozen_bn",
         enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers, dim_feedforward=cfg.dim_feedforward,
         hidden_dim=cfg.hidden_dim, dropout=0.1, nheads=cfg.nheads, num_queries=cfg.num_queries, pre_norm=False,
         aux_loss=cfg.aux_loss, lr_backbone=1e-5, device=device, set_cost_class=1, set_cost_pts=5,
@@ -98,6 +98,12 @@ def make_state_dict(cfg: ModelCfg, seed=0, spread_labels=False):
     else:
         nch = 1024
     e = cfg.hidden_dim
+    if getattr(cfg, "position_embedding", "sine") in ("learned", "v3"):
+        # nn.init.uniform_ tables of PositionEmbeddingLearned (RV/models/position_encoding.py:59-67); drawn from their own
+        # generator so that the other tensors of a seed do not depend on the embedding type
+        rpe = np.random.default_rng(seed + 7919)
+        sd["backbone.1.row_embed.weight"] = rpe.random((50, e // 2)).astype(np.float32)
+        sd["backbone.1.col_embed.weight"] = rpe.random((50, e // 2)).astype(np.float32)
     sd["input_proj.weight"] = _conv(rng, e, nch, 1, gain=0.7)
     sd["input_proj.bias"] = (0.02 * rng.standard_normal(e)).astype(np.float32)
     sd["query_embed.weight"] = rng.standard_normal((cfg.num_queries, e)).astype(np.float32)

@@ -762,6 +762,25 @@ std::string load_weights_impl(spe_ctx* ctx, WeightSource& ws) {
 
   // ---- positional embedding and query embedding on the device (fp32) for the addends
   std::vector<float> pos = make_pos(ctx->featH, ctx->featH, E);
+  {
+    // --position_embedding learned ('v3'): PositionEmbeddingLearned (RV/models/position_encoding.py:55-81) -- the two
+    // nn.Embedding(50, 128) tables travel with the checkpoint; pos[y, x] = cat(col_embed[x], row_embed[y]), again a
+    // constant of the model, so it folds into the same addends as the sine embedding
+    auto ir = ws.t.find("backbone.1.row_embed.weight"), ic = ws.t.find("backbone.1.col_embed.weight");
+    if (ir != ws.t.end() && ic != ws.t.end()) {
+      const HostTensor* row = ws.get("backbone.1.row_embed.weight", {50, E / 2});
+      const HostTensor* col = ws.get("backbone.1.col_embed.weight", {50, E / 2});
+      if (!row || !col) return ws.missing;
+      const int H = ctx->featH;
+      if (H > 50) return "learned position embedding: feature map larger than the 50-entry tables";
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < H; ++x) {
+          float* p = pos.data() + (static_cast<size_t>(y) * H + x) * E;
+          memcpy(p, col->data + static_cast<size_t>(x) * (E / 2), sizeof(float) * (E / 2));
+          memcpy(p + E / 2, row->data + static_cast<size_t>(y) * (E / 2), sizeof(float) * (E / 2));
+        }
+    }
+  }
   float *pos_dev = nullptr, *qe_dev = nullptr;
   SPE_CUDA_TRY(cudaMalloc(&pos_dev, pos.size() * sizeof(float)));
   cudaMemcpy(pos_dev, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice);

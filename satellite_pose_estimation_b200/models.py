@@ -23,7 +23,8 @@ def is_stride8(backbone):
     return backbone not in ("resnet18", "resnet34", "resnet50")
 
 
-def param_specs(backbone, num_queries, enc_layers, dec_layers, hidden_dim, dim_feedforward, sigma_head):
+def param_specs(backbone, num_queries, enc_layers, dec_layers, hidden_dim, dim_feedforward, sigma_head,
+                position_embedding="sine"):
     """(name, shape, is_buffer) for every tensor of the reference state_dict."""
     if backbone in ("resnet18", "resnet34"):
         raise ValueError("only the ResNet-50 backbones of the reference recipes are built (resnet50 / resnet50s8)")
@@ -80,6 +81,11 @@ def param_specs(backbone, num_queries, enc_layers, dec_layers, hidden_dim, dim_f
     linear("point_embed.layers.0", e, e); linear("point_embed.layers.1", e, e); linear("point_embed.layers.2", 2, e)
     if sigma_head:
         linear("sigma_embed.layers.0", e, e); linear("sigma_embed.layers.1", e, e); linear("sigma_embed.layers.2", 1, e)
+    if position_embedding in ("learned", "v3"):     # PositionEmbeddingLearned, RV/models/position_encoding.py:59-63
+        specs.append(("backbone.1.row_embed.weight", (50, e // 2), False))
+        specs.append(("backbone.1.col_embed.weight", (50, e // 2), False))
+    elif position_embedding not in ("sine", "v2"):
+        raise ValueError(f"not supported {position_embedding}")
     specs.append(("query_embed.weight", (num_queries, e), False))
     specs.append(("input_proj.weight", (e, nch, 1, 1), False)); specs.append(("input_proj.bias", (e,), False))
     return specs
@@ -138,7 +144,13 @@ class _BackboneView(_Holder):
             eng.enable_taps(False)
         feat = feat.permute(0, 3, 1, 2).contiguous().to(dev)
         mask = torch.zeros((B, h, h), dtype=torch.bool, device=dev)
-        pos = position_embedding_sine(B, h, h, root.cfg.hidden_dim, device=dev)
+        if root.cfg.position_embedding in ("learned", "v3"):       # RV/models/position_encoding.py:69-81
+            tables = self._modules["1"]
+            x_emb, y_emb = tables.col_embed.weight[:h], tables.row_embed.weight[:h]
+            pos = torch.cat([x_emb.unsqueeze(0).repeat(h, 1, 1), y_emb.unsqueeze(1).repeat(1, h, 1)], dim=-1)
+            pos = pos.permute(2, 0, 1).unsqueeze(0).repeat(B, 1, 1, 1)
+        else:
+            pos = position_embedding_sine(B, h, h, root.cfg.hidden_dim, device=dev)
         return [SimpleNamespace(tensors=feat, mask=mask, decompose=lambda: (feat, mask))], [pos]
 
 
@@ -161,21 +173,22 @@ class B200DETR(nn.Module):
 
     def __init__(self, *, backbone="resnet50s8", num_queries=40, enc_layers=4, dec_layers=4, hidden_dim=256, nheads=8,
                  dim_feedforward=2048, aux_loss=True, input_size=None, precision="tf32", sigma_head=False,
-                 max_batch=64, calibrate=True):
+                 max_batch=64, calibrate=True, position_embedding="sine"):
         super().__init__()
         if hidden_dim != 256 or nheads != 8:
             raise ValueError("libspe.so is built for hidden_dim=256, nheads=8 (every recipe of the reference)")
         self.num_queries, self.aux_loss = num_queries, aux_loss
         self.cfg = SimpleNamespace(backbone=backbone, num_queries=num_queries, enc_layers=enc_layers,
                                    dec_layers=dec_layers, hidden_dim=hidden_dim, nheads=nheads,
-                                   dim_feedforward=dim_feedforward, sigma_head=sigma_head)
+                                   dim_feedforward=dim_feedforward, sigma_head=sigma_head,
+                                   position_embedding=position_embedding)
         self.input_size, self.precision, self.max_batch = input_size, precision, max_batch
         # fold the mean effect of the TF32 / BF16 weight rounding into the biases, measured on the first batch this
         # model sees after (re)loading weights (Engine.calibrate / spe_calibrate)
         self.calibrate = bool(calibrate)
         gen = torch.Generator().manual_seed(0)
         for name, shape, is_buffer in param_specs(backbone, num_queries, enc_layers, dec_layers, hidden_dim,
-                                                  dim_feedforward, sigma_head):
+                                                  dim_feedforward, sigma_head, position_embedding):
             _register(self, name, self._init_tensor(name, shape, gen), is_buffer)
         self._engine = None
         self._engine_key = None
@@ -198,6 +211,8 @@ class B200DETR(nn.Module):
             return torch.randn(shape, generator=gen) * math.sqrt(2.0 / fan_out)
         if name == "query_embed.weight":
             return torch.randn(shape, generator=gen)
+        if name.endswith("_embed.weight"):                       # PositionEmbeddingLearned: nn.init.uniform_
+            return torch.rand(shape, generator=gen)
         a = math.sqrt(6.0 / (shape[0] + shape[1]))
         return (torch.rand(shape, generator=gen) * 2 - 1) * a
 
@@ -360,7 +375,7 @@ def build_model(args):
         hidden_dim=args.hidden_dim, nheads=args.nheads, dim_feedforward=args.dim_feedforward,
         aux_loss=getattr(args, "aux_loss", True), input_size=getattr(args, "input_size", None),
         precision=getattr(args, "precision", "tf32"), sigma_head=getattr(args, "sigma_head", False),
-        calibrate=getattr(args, "calibrate", True),
+        calibrate=getattr(args, "calibrate", True), position_embedding=getattr(args, "position_embedding", "sine"),
         max_batch=getattr(args, "max_batch", None) or max(int(getattr(args, "batch_size", 64) or 64), 1))
     if is_stride8(args.backbone):
         args.backbone = "resnet50"   # the reference's build_backbone rewrites it too (RV/models/backbone.py:193)

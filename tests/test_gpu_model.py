@@ -354,3 +354,25 @@ def test_backbone_view_like_get_backbone_time(lib, cuda_dev):
     assert torch.allclose(pos[0].cpu(), model_ref.position_embedding_sine(2, 28, 28), atol=1e-6)
     out = model(x.cuda())                     # the fused forward still works after the tap round trip
     assert out["pred_points"].shape == (2, 40, 2)
+
+
+def test_learned_position_embedding_vs_oracle(lib, cuda_dev):
+    """--position_embedding learned: the embedding tables of the checkpoint replace the sine table in the folded
+    positional addends (encoder Q|K, decoder cross-attention K); forward against the oracle."""
+    cfg = model_ref.ModelCfg(num_queries=20, enc_layers=2, dec_layers=2, position_embedding="learned")
+    sd = synth.make_state_dict(cfg, seed=6)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(4))
+    ref = model_ref.forward(sd, cfg, x)
+    sine = model_ref.forward({k: v for k, v in sd.items() if not k.startswith("backbone.1.")},
+                             model_ref.ModelCfg(num_queries=20, enc_layers=2, dec_layers=2), x)
+    e = Engine(num_queries=20, enc_layers=2, dec_layers=2, max_batch=2)
+    try:
+        e.load_state_dict(sd)
+        out = e.forward(x.cuda())
+        torch.cuda.synchronize()
+        d = (out["pred_points"].cpu() - ref["pred_points"]).abs().max().item()
+        assert d <= 0.5 / 1748, d * 1748
+        # the two embeddings give different predictions: the tables were really used
+        assert (ref["pred_points"] - sine["pred_points"]).abs().max().item() > 20 * d
+    finally:
+        e.close()

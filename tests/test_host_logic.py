@@ -234,3 +234,17 @@ def test_sa_r18vd_state_dict_layout():
     assert not res.missing_keys and not res.unexpected_keys
     with pytest.raises(RuntimeError):            # a depth-50 checkpoint does not fit a depth-18 model
         m.load_state_dict(synth.make_sa_state_dict(seed=0), strict=True)
+
+
+def test_learned_position_embedding_layout():
+    """build_model(args) with --position_embedding learned: the two nn.Embedding(50, 128) tables are part of the
+    state_dict (strict load of a reference-layout checkpoint); an unknown embedding type is refused like the reference does."""
+    cfg = model_ref.ModelCfg(position_embedding="learned")
+    args = synth.reference_args(cfg)
+    model, _, _ = build_model(args)
+    sd = synth.make_state_dict(cfg, seed=3)
+    assert set(model.state_dict().keys()) == set(sd.keys()) and tuple(sd["backbone.1.col_embed.weight"].shape) == (50, 128)
+    model.load_state_dict(sd, strict=True)
+    args.position_embedding = "v9"
+    with pytest.raises(ValueError, match="not supported"):
+        build_model(args)

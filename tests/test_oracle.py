@@ -307,3 +307,19 @@ def test_sa_r18vd_oracle_matches_live_reference_golden():
     assert np.abs(out["pred_logits"].numpy() - g["pred_logits"]).max() < 5e-5
     assert np.abs(out["pred_pts"].numpy() - g["pred_pts"]).max() < 5e-6
     assert np.abs(out["pred_sigmas"].numpy() - g["pred_sigmas"]).max() < 5e-5
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference only exists in the build container")
+def test_learned_position_embedding_matches_live_reference():
+    """``--position_embedding learned`` (PositionEmbeddingLearned, RV/models/position_encoding.py:55-81): restatement
+    against the live reference model built with that option."""
+    cfg = model_ref.ModelCfg(num_queries=20, enc_layers=2, dec_layers=2, position_embedding="learned")
+    sd = synth.make_state_dict(cfg, seed=6)
+    assert "backbone.1.row_embed.weight" in sd
+    model, _, _ = ref_import.build_reference_model(cfg, sd)          # strict load: the key layout is the reference's
+    x = model_inputs(2, 224, 9)
+    with torch.no_grad():
+        ref = model(x)
+    out = model_ref.forward(sd, cfg, x)
+    assert (ref["pred_logits"] - out["pred_logits"]).abs().max() < 2e-5
+    assert (ref["pred_points"] - out["pred_points"]).abs().max() < 2e-6
