@@ -370,6 +370,10 @@ def build_model(args):
     is outside this path: a ``NoCriterion`` that yields no losses keeps ``engine.evaluate`` running unedited.  Additive optional attributes on ``args``:
     ``precision`` ('tf32' | 'bf16'), ``sigma_head`` (bool), ``max_batch`` (int), ``input_size``, ``calibrate`` (bool,
     default True: rounding-bias calibration on the first batch, see ``Engine.calibrate``)."""
+    if getattr(args, "pre_norm", False):
+        # RV/models/transformer.py:284-294 builds normalize_before layers + an encoder norm for --pre_norm; no recipe of the
+        # reference uses it and the fused schedule is the post-norm one: refuse instead of computing something else
+        raise NotImplementedError("--pre_norm is not built: every recipe of the reference trains the post-norm transformer")
     model = B200DETR(
         backbone=args.backbone, num_queries=args.num_queries, enc_layers=args.enc_layers, dec_layers=args.dec_layers,
         hidden_dim=args.hidden_dim, nheads=args.nheads, dim_feedforward=args.dim_feedforward,

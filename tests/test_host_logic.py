@@ -248,3 +248,10 @@ def test_learned_position_embedding_layout():
     args.position_embedding = "v9"
     with pytest.raises(ValueError, match="not supported"):
         build_model(args)
+
+
+def test_pre_norm_is_refused_loudly():
+    args = synth.reference_args(model_ref.ModelCfg())
+    args.pre_norm = True
+    with pytest.raises(NotImplementedError, match="pre_norm"):
+        build_model(args)
