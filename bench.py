@@ -445,7 +445,7 @@ def run_b200(args):
             Image.fromarray(shard_np[k % max(1, b - a)], "L").save(buf, "JPEG", quality=80)
             enc.append(buf.getvalue())
         files = [enc[i % 16] for i in range(n_img)]
-        jchunks = int(os.environ.get("SPE_JPEG_CHUNKS", "2"))
+        jchunks = int(os.environ["SPE_JPEG_CHUNKS"]) if "SPE_JPEG_CHUNKS" in os.environ else None   # None: by shard size
         run_image_set(eng, None, det_all, names, batch_size=BATCH, rank=rank, world_size=world, slots=SLOTS, gather=False,
                       jpeg_files=files, jpeg_chunks=jchunks)   # warm-up (staging windows, device buffer of the shard)
         barrier()
@@ -457,8 +457,8 @@ def run_b200(args):
         image_set["from_jpeg_files"] = {"seconds": jpeg_s, "images_per_s": n_img / jpeg_s,
                                         "compressed_mb_per_rank": sum(len(f) for f in files[a:b]) / 1e6,
                                         "poses_solved_this_rank": sum(1 for v in jres.values() if v["status"] == 0),
-                                        "decode": f"spe_jpeg_decode_batch: one warp per image, the shard in {jchunks} chunks decoded "
-                                                  "by a helper thread / stream while earlier chunks run through the pipeline"}
+                                        "decode": "spe_jpeg_decode_batch: one warp per image, on a helper thread / stream; shards of 1200+ "
+                                                  "images in two chunks so that the second decodes while the first runs through the pipeline"}
         del jres, files, enc
     except ImportError:
         image_set["from_jpeg_files"] = None

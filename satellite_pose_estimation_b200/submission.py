@@ -261,7 +261,7 @@ def _chunked_jpeg_frames(engine, jpeg_files, a, b, todo, nchunks):
 
 
 def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, rank=0, world_size=1, slots=4,
-                  reproj=20.0, weighted=False, reject=False, gather=True, calibrate=True, jpeg_files=None, jpeg_chunks=2):
+                  reproj=20.0, weighted=False, reject=False, gather=True, calibrate=True, jpeg_files=None, jpeg_chunks=None):
     """crop -> predictor -> PnP for every image of a set (RV/gen_submission_single.py:136-181).
 
     ``get_frames(i0, i1)`` returns the frames ``i0 .. i1-1`` as a uint8 array / tensor [n,H,W] (decoded by the
@@ -271,7 +271,7 @@ def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, ran
     ``jpeg_files`` (list of ``bytes``, one baseline grayscale JPEG file per image, instead of ``get_frames``): the
     rank's shard is decoded on the GPU (``Engine.decode_jpeg``: one warp per image; 2.3 MB of HBM per 1920 x 1200
     frame), replacing the reference's per-image ``Image.open(...).convert('RGB')`` (RV/datasets/speed.py:116).  The
-    shard is decoded in ``jpeg_chunks`` pieces by a helper thread on its own stream: a warp-per-image decoder leaves
+    shard is decoded in ``jpeg_chunks`` pieces (default: two for shards of 1200 images or more, else one) by a helper thread on its own stream: a warp-per-image decoder leaves
     most of the machine idle, so chunk c + 1 is parsed, uploaded and decoded while the batches of chunk c run through the
     pipeline (a batch waits for its chunk's event only).  Returns {filename: {'quat_pr', 'tvec_pr', 'status'}}; with ``gather``
     and an initialised process group, rank 0 gets the merged, filename-sorted dict of all ranks (others ``None``)."""
@@ -288,6 +288,11 @@ def run_image_set(engine, get_frames, det_boxes, filenames, batch_size=None, ran
     if jpeg_files is not None:
         if len(jpeg_files) != n:
             raise ValueError("jpeg_files must hold one file per filename")
+        if jpeg_chunks is None:
+            # a second chunk costs one more scan latency (~80 ms for a dense 1920 x 1200 file) on the decode stream: it
+            # pays once half the shard keeps the pipeline busy for longer than that (measured: 2998 images per rank
+            # 8.1 k -> 9.3 k images/s with two chunks; 375 per rank 28 k -> 17 k)
+            jpeg_chunks = 2 if (b - a) >= 1200 else 1
         get_frames = _chunked_jpeg_frames(engine, jpeg_files, a, b, todo, max(1, int(jpeg_chunks)))   # noqa: F811
     if calibrate and not engine.calibrated and todo:
         # rounding-bias calibration (Engine.calibrate) on the first crops of this shard, before anything is in flight
