@@ -168,23 +168,32 @@ __device__ __forceinline__ int decode_symbol(BitReader& br, const uint16_t* lut,
   return vals[(code + valoff[l]) & 0xFF];
 }
 
-constexpr int kWarpsPerCta = 4;
+// Two warps per image: the entropy decoder (a scan is a sequential bit stream: one lane walks it, all 32 refill the
+// window) and the inverse DCT + store warp, handing blocks over through a double-buffered coefficient array and one
+// named barrier per block -- block n + 1 is Huffman-decoded while block n is transformed and stored.  (One warp doing both
+// in turn spent a quarter of every block's time in the transform with the decoding lane idle.)
+constexpr int kWarpsPerCta = 4;   // images per CTA (two warps each)
 struct WarpSmem {
   JpegTables t;
   __align__(16) uint8_t ring[kRing];
-  int coef[64];                   // dequantised coefficients, natural order
+  int coef[2][64];                // dequantised coefficients, natural order (double buffer: decoder -> transform warp)
+  int last_k[2];                  // index of the last non-zero coefficient of the block in coef[i] (0: DC only)
   int ws[64];                     // after the column pass
 };
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 64)
 jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restrict__ imgs, const JpegTables* __restrict__ tabs,
                    int B, uint8_t* __restrict__ frames, long long pitch, long long frame_stride, int* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kWarpsPerCta + warp;
-  if (b >= B) return;
-  WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
-  {
+  const int slot = warp >> 1;                       // image of this CTA
+  const bool is_decoder = (warp & 1) == 0;
+  const int b = blockIdx.x * kWarpsPerCta + slot;
+  if (b >= B) return;                               // both warps of the slot leave: no barrier is ever entered
+  WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[slot];
+  const int bar_id = 1 + slot;
+  if (is_decoder) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tabs + b);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&S.t);
     for (int i = lane; i < static_cast<int>(sizeof(JpegTables) / 4); i += 32) dst[i] = src[i];
@@ -195,14 +204,72 @@ jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restri
   uint8_t* frame = frames + static_cast<long long>(b) * frame_stride;
   const bool wide_store = (pitch % 8 == 0) && (reinterpret_cast<uintptr_t>(frame) % 8 == 0);
 
+  if (!is_decoder) {
+    // ---- transform warp: block n after the n-th barrier, from coef[n & 1]
+    int n = 0;
+    for (int by = 0; by < bh; ++by) {
+      for (int bx = 0; bx < bw; ++bx, ++n) {
+        pair_barrier(bar_id);
+        const int* coef = S.coef[n & 1];
+        const int last_k = S.last_k[n & 1];
+        const int x0 = bx * 8, y0 = by * 8;
+        // inverse DCT (jpeg_idct_islow); a DC-only block is its shortcut form, which the full formula reproduces
+        if (last_k == 0) {
+          if (lane < 8 && y0 + lane < im.height) {
+            const uint32_t v = range_limit(((coef[0] << 2) + 16) >> 5);
+            uint8_t* o = frame + static_cast<long long>(y0 + lane) * pitch + x0;
+            if (wide_store && x0 + 8 <= im.width) {
+              const uint32_t w = v * 0x01010101u;
+              *reinterpret_cast<uint2*>(o) = make_uint2(w, w);
+            } else {
+              for (int i = 0; i < 8 && x0 + i < im.width; ++i) o[i] = static_cast<uint8_t>(v);
+            }
+          }
+        } else {
+          if (lane < 8) {                            // column `lane`
+            int in[8], out[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) in[i] = coef[i * 8 + lane];
+            idct_1d(in, out, 13 - 2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) S.ws[i * 8 + lane] = out[i];
+          }
+          __syncwarp();
+          if (lane < 8 && y0 + lane < im.height) {   // row `lane`
+            int in[8], out[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) in[i] = S.ws[lane * 8 + i];
+            idct_1d(in, out, 13 + 2 + 3);
+            uint8_t* o = frame + static_cast<long long>(y0 + lane) * pitch + x0;
+            if (wide_store && x0 + 8 <= im.width) {
+              const uint32_t lo = range_limit(out[0]) | (range_limit(out[1]) << 8) | (range_limit(out[2]) << 16) | (range_limit(out[3]) << 24);
+              const uint32_t hi = range_limit(out[4]) | (range_limit(out[5]) << 8) | (range_limit(out[6]) << 16) | (range_limit(out[7]) << 24);
+              *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (x0 + i < im.width) o[i] = static_cast<uint8_t>(range_limit(out[i]));
+            }
+          }
+          __syncwarp();                              // ws is rewritten by the next block's column pass
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- decoder warp: block n into coef[n & 1], then the n-th barrier (the transform warp reaches the (n + 1)-th only
+  // after it has finished block n, so coef[n & 1] is free again when block n + 2 is written)
   long long filled = 0;            // the window holds scan bytes [filled - kRing, filled) (those still unread)
   BitReader br{S.ring, 0, im.scan_len, 0, 0, false};
   long long pos = 0;
   int pred = 0, until_restart = im.restart, bad = 0;
   __syncwarp();
 
+  int nblk = 0;
   for (int by = 0; by < bh; ++by) {
-    for (int bx = 0; bx < bw; ++bx) {
+    for (int bx = 0; bx < bw; ++bx, ++nblk) {
+      int* coef = S.coef[nblk & 1];
       // ---- keep at least 1024 unread bytes in the window (one block consumes < 512 incl. stuffing)
       while (filled - pos < 1024 + kChunk && filled < im.scan_len + kChunk) {
         // the packed buffer is padded with 2 * kChunk zero bytes behind every scan: the over-read is harmless
@@ -210,8 +277,8 @@ jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restri
         *reinterpret_cast<uint4*>(S.ring + ((filled + lane * 16) & (kRing - 1))) = v;
         filled += kChunk;
       }
-      S.coef[lane] = 0;
-      S.coef[lane + 32] = 0;
+      coef[lane] = 0;
+      coef[lane + 32] = 0;
       __syncwarp();
       int last_k = 0;
       if (lane == 0) {
@@ -232,7 +299,7 @@ jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restri
         }
         const int t = decode_symbol(br, S.t.dc_lut, S.t.dc_maxcode, S.t.dc_valoff, S.t.dc_vals);
         if (t > 0) pred += br.receive_extend(t & 15);
-        S.coef[0] = pred * static_cast<int>(S.t.q[0]);
+        coef[0] = pred * static_cast<int>(S.t.q[0]);
         int k = 1;
         while (k < 64) {
           br.fill();
@@ -241,7 +308,7 @@ jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restri
             k += (f >> 4) & 15;
             if (k > 63) { bad = 1; break; }
             br.skip(f & 15);
-            S.coef[c_zigzag[k]] = (f >> 8) * static_cast<int>(S.t.q[k]);
+            coef[c_zigzag[k]] = (f >> 8) * static_cast<int>(S.t.q[k]);
             last_k = k;
             ++k;
             continue;
@@ -255,56 +322,16 @@ jpeg_decode_kernel(const uint8_t* __restrict__ packed, const JpegImage* __restri
           }
           k += r;
           if (k > 63) { bad = 1; break; }
-          S.coef[c_zigzag[k]] = br.receive_extend(s) * static_cast<int>(S.t.q[k]);
+          coef[c_zigzag[k]] = br.receive_extend(s) * static_cast<int>(S.t.q[k]);
           last_k = k;
           ++k;
         }
         pos = br.pos;
+        S.last_k[nblk & 1] = last_k;
       }
       pos = __shfl_sync(0xffffffffu, pos, 0);
-      last_k = __shfl_sync(0xffffffffu, last_k, 0);
       __syncwarp();
-      // ---- inverse DCT (jpeg_idct_islow); a DC-only block is its shortcut form, which the full formula reproduces
-      const int x0 = bx * 8, y0 = by * 8;
-      if (last_k == 0) {
-        if (lane < 8 && y0 + lane < im.height) {
-          const uint32_t v = range_limit(((S.coef[0] << 2) + 16) >> 5);
-          uint8_t* o = frame + static_cast<long long>(y0 + lane) * pitch + x0;
-          if (wide_store && x0 + 8 <= im.width) {
-            const uint32_t w = v * 0x01010101u;
-            *reinterpret_cast<uint2*>(o) = make_uint2(w, w);
-          } else {
-            for (int i = 0; i < 8 && x0 + i < im.width; ++i) o[i] = static_cast<uint8_t>(v);
-          }
-        }
-      } else {
-        if (lane < 8) {                            // column `lane`
-          int in[8], out[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) in[i] = S.coef[i * 8 + lane];
-          idct_1d(in, out, 13 - 2);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) S.ws[i * 8 + lane] = out[i];
-        }
-        __syncwarp();
-        if (lane < 8 && y0 + lane < im.height) {   // row `lane`
-          int in[8], out[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) in[i] = S.ws[lane * 8 + i];
-          idct_1d(in, out, 13 + 2 + 3);
-          uint8_t* o = frame + static_cast<long long>(y0 + lane) * pitch + x0;
-          if (wide_store && x0 + 8 <= im.width) {
-            const uint32_t lo = range_limit(out[0]) | (range_limit(out[1]) << 8) | (range_limit(out[2]) << 16) | (range_limit(out[3]) << 24);
-            const uint32_t hi = range_limit(out[4]) | (range_limit(out[5]) << 8) | (range_limit(out[6]) << 16) | (range_limit(out[7]) << 24);
-            *reinterpret_cast<uint2*>(o) = make_uint2(lo, hi);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (x0 + i < im.width) o[i] = static_cast<uint8_t>(range_limit(out[i]));
-          }
-        }
-      }
-      __syncwarp();
+      pair_barrier(bar_id);                          // block nblk handed over
     }
   }
   if (lane == 0 && status != nullptr) status[b] = bad;
@@ -644,7 +671,7 @@ int spe_jpeg_decode_batch(spe_ctx* ctx, const uint8_t* const* files_host, const 
   }
   {
     ProfScope psc(kFamCrop, st);
-    jpeg_decode_kernel<<<(B + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, smem, st>>>(
+    jpeg_decode_kernel<<<(B + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 64, smem, st>>>(
         S->stage_d, reinterpret_cast<const JpegImage*>(S->stage_d + tab_bytes), reinterpret_cast<const JpegTables*>(S->stage_d), B,
         frames_dev, pitch, frame_stride, S->status_d);
   }
