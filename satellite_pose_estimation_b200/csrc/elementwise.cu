@@ -280,7 +280,6 @@ layernorm256_kernel(const T* __restrict__ in, const float* __restrict__ gamma, c
     const int c = (i * 32 + lane) * VN;
     Vec<T> r;
     float yv[VN];
-#pragma unroll
     if (exact == 2) {
       // 3xTF32 operand layout [hi | lo | hi] (row stride 768): the consumer is a plain K = 768 GEMM against
       // [W_hi | W_hi | W_lo], i.e. A_hi W_hi + A_lo W_hi + A_hi W_lo without any in-kernel operand split

@@ -83,7 +83,6 @@ struct SaModel {
   const int32_t* topk_in = nullptr;
 };
 
-static const int kSaBlocks[4] = {3, 4, 6, 3};
 static const int kSaPlanes[4] = {64, 128, 256, 512};
 
 // conv weight (Cout, Cin, R, R) -> [CoutPad][(r*R + s)*CinPad + c], zero rows / columns for the padding channels
