@@ -141,3 +141,17 @@ def test_jpeg_header_walk_on_the_host():
     assert rc == -1 and "3 components" in msg
     w, h = C.c_int(0), C.c_int(0)
     assert lib.spe_jpeg_info(C.cast(C.create_string_buffer(b"abcdefgh", 8), C.c_void_p), 8, C.byref(w), C.byref(h)) == -1
+
+
+def test_sa_entry_points_validate_before_touching_the_device(lib):
+    """The SA predictor's ABI (spe_config.backbone = 2, spe_forward_sa): argument errors are reported without a device."""
+    assert lib.spe_forward_sa(None, None, 1, None, None, None, None, None, None, None, None, None) != 0
+    assert b"null ctx" in lib.spe_global_last_error()
+    for bad in (dict(precision=1), dict(has_sigma=0), dict(enc_layers=2), dict(input_size=512), dict(num_queries=31)):
+        kw = dict(input_size=256, num_queries=30, enc_layers=1, dec_layers=3, hidden_dim=256, nheads=8, dim_feedforward=1024,
+                  backbone=2, precision=0, has_sigma=1, max_batch=2)
+        kw.update(bad)
+        cfg = _lib.SpeConfig(**kw)
+        ctx = C.c_void_p()
+        assert lib.spe_create(C.byref(cfg), 0, C.byref(ctx)) != 0 and not ctx.value, bad
+        assert b"SA predictor" in lib.spe_global_last_error(), bad
