@@ -285,6 +285,12 @@ def make_engine(batch, precision, sigma, dev_index, arch="rv"):
         eng = Engine(input_size=256, num_queries=30, enc_layers=1, dec_layers=3, dim_feedforward=1024, backbone="rtdetr_r50vd",
                      precision="tf32", has_sigma=True, max_batch=batch, device=dev_index)
         eng.load_state_dict(synth.make_sa_state_dict(seed=0))
+    elif arch == "s16":
+        # the reference's main.py defaults (SURVEY.md section 8d "secondary"): ResNet-50 stride 16, 512^2, 100 queries, 6 + 6 layers
+        cfg16 = model_ref.ModelCfg(backbone="resnet50", num_queries=100, enc_layers=6, dec_layers=6)
+        eng = Engine(input_size=512, num_queries=100, enc_layers=6, dec_layers=6, backbone="resnet50", precision=precision,
+                     has_sigma=False, max_batch=batch, device=dev_index)
+        eng.load_state_dict(synth.make_state_dict(cfg16, seed=0))
     else:
         eng = Engine(input_size=R, num_queries=Q, enc_layers=4, dec_layers=4, backbone="resnet50s8", precision=precision,
                      has_sigma=sigma, max_batch=batch, device=dev_index)
@@ -298,7 +304,7 @@ def make_engine(batch, precision, sigma, dev_index, arch="rv"):
         det = np.concatenate([p[1] for p in parts])
         sets.append({"host": fh, "det": det, "dev": fh.to(dev), "boxes": torch.from_numpy(eng.clip_boxes(det)).to(dev)})
     if arch != "sa":
-        eng.calibrate(eng.crop_resize_norm(sets[1]["dev"][:16], sets[1]["boxes"][:16]))
+        eng.calibrate(eng.crop_resize_norm(sets[1]["dev"][:16 if arch == "rv" else 8], sets[1]["boxes"][:16 if arch == "rv" else 8]))
     return eng, sets
 
 
@@ -550,13 +556,21 @@ def run_b200(args):
     if rank == 0 and world == 1:
         # ---- BASELINE configs[2] / configs[3] at their stated batch of 256 (short runs; N = 1 only)
         side = {}
-        for name, prec, sig in (("bf16_b256", "bf16", False), ("sigma_b256", "tf32", True), ("sa_rtdetr_b256", "tf32", True)):
-            e2, s2 = make_engine(256, prec, sig, local, arch="sa" if name.startswith("sa_") else "rv")
+        for name, prec, sig in (("bf16_b256", "bf16", False), ("sigma_b256", "tf32", True), ("sa_rtdetr_b256", "tf32", True),
+                                ("s16_512_q100_b64", "tf32", False)):
+            arch2 = "sa" if name.startswith("sa_") else ("s16" if name.startswith("s16_") else "rv")
+            b2 = 64 if arch2 == "s16" else 256
+            e2, s2 = make_engine(b2, prec, sig, local, arch=arch2)
             pnp2 = {"reproj": 25.0 if sig else 20.0, "weighted": sig, "reject": sig}
             ms2, last2 = timed_steps(e2, s2, 3, 12, 3, pnp2, lambda: torch.cuda.synchronize())
-            side[name] = {"images_per_s": 256 * 12 / (ms2 / 1e3), "ms_per_batch": ms2 / 12, "batch": 256, "precision": prec,
+            side[name] = {"images_per_s": b2 * 12 / (ms2 / 1e3), "ms_per_batch": ms2 / 12, "batch": b2, "precision": prec,
                           "sigma_head": sig, "batches_in_flight": 3, "steps": 12,
                           "poses_solved_per_batch": int((np.asarray(last2["status"]) == 0).sum())}
+            if arch2 == "s16":
+                side[name].update({"model": "the reference's main.py defaults: ResNet-50 stride 16, 512^2 crops, 100 queries, 6 + 6 layers "
+                                            "(SURVEY.md section 8d, secondary configuration; 61.53 GFLOP per image)",
+                                   "algorithmic_tflops": side[name]["images_per_s"] * 61.53 / 1e3,
+                                   "note": "seeded random heads: one label, the pose stage exits after the assignment"})
             if name.startswith("sa_"):
                 sa_gflop = 14.44          # per image: 13.04 convolutions + 1.41 linear layers
                 side[name].update({"algorithmic_gflop_per_image": sa_gflop,

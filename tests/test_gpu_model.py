@@ -376,3 +376,26 @@ def test_learned_position_embedding_vs_oracle(lib, cuda_dev):
         assert (ref["pred_points"] - sine["pred_points"]).abs().max().item() > 20 * d
     finally:
         e.close()
+
+
+def test_main_py_default_configuration_vs_oracle(lib, cuda_dev):
+    """The reference's main.py defaults (secondary configuration): --backbone resnet50 (stride 16), 512 x 512
+    crops, 100 queries, 6 + 6 layers -- 32 x 32 = 1024 tokens, a 256-wide stem output row (two window tiles per row),
+    128 x 128 layer1 maps.  Keypoints within 0.5 px at S = 1748 after the rounding-bias calibration, same arg-max labels."""
+    cfg = model_ref.ModelCfg(backbone="resnet50", num_queries=100, enc_layers=6, dec_layers=6)
+    sd = synth.make_state_dict(cfg, seed=2)
+    x = torch.randn(2, 3, 512, 512, generator=torch.Generator().manual_seed(12))
+    ref = model_ref.forward(sd, cfg, x)
+    e = Engine(input_size=512, num_queries=100, enc_layers=6, dec_layers=6, backbone="resnet50", max_batch=2)
+    try:
+        e.load_state_dict(sd)
+        xc = x.cuda()
+        e.calibrate(xc)
+        out = e.forward(xc)
+        torch.cuda.synchronize()
+        d = (out["pred_points"].cpu() - ref["pred_points"]).abs().max().item()
+        print(f"main.py defaults (s16, 512^2, Q=100, 6+6): keypoints {d * 1748:.3f} px at S=1748")
+        assert d <= 0.5 / 1748
+        assert torch.equal(out["pred_logits"].argmax(-1).cpu(), ref["pred_logits"].argmax(-1))
+    finally:
+        e.close()
